@@ -1,0 +1,154 @@
+"""TEST INFRASTRUCTURE ONLY -- generate tests/golden/*.json from the UNMODIFIED reference.
+
+Run in the dev container (the only place /root/reference exists):
+    python -m oracle.make_golden
+It (1) builds the reference ``U2`` + ``HybridCTCLoss`` through ``oracle/ref_shims.py``,
+(2) loads the deterministic synthetic weights / batch from ``liteasr_b200.utils.synthetic``,
+(3) runs forward+backward in float64 (and float32 for the record) and (4) stores losses,
+output samples, per-parameter gradient norms/samples, BatchNorm running-stat updates and
+eval-mode greedy-CTC token ids.  It also stores torch.nn.CTCLoss known answers
+(the third-party arithmetic behind criterions/hybrid_ctc_attn.py:32) for the CTC restatement.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from liteasr_b200.schema import U2Dims  # noqa: E402
+from liteasr_b200.utils.synthetic import synth_batch, synth_state_dict  # noqa: E402
+from oracle import ref_shims  # noqa: E402
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+MODEL_CASES = {
+    # name: (dims, batch, tmax, lmax, ctc_weight, smoothing, seed)
+    "tiny": (U2Dims(80, 50, 128, 256, 2, 2, 128, 256, 2, 2), 3, 67, 6, 0.3, 0.1, 7),
+    "tiny_odd": (U2Dims(80, 37, 64, 96, 1, 1, 64, 96, 1, 1), 2, 43, 4, 0.5, 0.0, 11),
+    "c1": (U2Dims(80, 500, 256, 2048, 4, 4, 256, 2048, 4, 6), 8, 500, 30, 0.3, 0.1, 42),
+}
+
+
+def sample_idx(n: int, k: int = 16):
+    if n <= k:
+        return list(range(n))
+    return [int(i) for i in np.linspace(0, n - 1, k).astype(np.int64)]
+
+
+def summarize(t: torch.Tensor, k: int = 16):
+    f = t.detach().double().reshape(-1)
+    idx = sample_idx(f.numel(), k)
+    return dict(shape=list(t.shape), sum=float(f.sum()), abssum=float(f.abs().sum()), l2=float(f.norm()),
+                idx=idx, val=[float(f[i]) for i in idx])
+
+
+def greedy(ids_row, n):
+    out, prev = [], -1
+    for t in range(n):
+        c = int(ids_row[t])
+        if c != prev and c != 0:
+            out.append(c)
+        prev = c
+    return out
+
+
+def run_model_case(name):
+    dims, b, tmax, lmax, w, eps, seed = MODEL_CASES[name]
+    xs, xlens, ys, ylens = synth_batch(b, tmax, lmax, dims.vocab_size, seed=seed)
+    sd = synth_state_dict(dims, seed=seed)
+    out = dict(case=name, dims=dims.__dict__, batch=b, tmax=tmax, lmax=lmax, ctc_weight=w, smoothing=eps, seed=seed,
+               xlens=xlens.tolist(), ylens=ylens.tolist())
+    for dtype, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
+        model, crit = ref_shims.build_reference(dims.__dict__, eps, w)
+        model.load_state_dict(sd, strict=True)
+        model = model.to(dtype)
+        model.train()
+        loss = crit(model, xs.to(dtype), xlens, ys, ylens)
+        loss.backward()
+        rec = dict(loss=float(loss))
+        if tag == "f64":
+            # recompute pieces for the record
+            with torch.no_grad():
+                model2, _ = ref_shims.build_reference(dims.__dict__, eps, w)
+                model2.load_state_dict(sd, strict=True)
+                model2 = model2.to(dtype).train()
+                h_attn, h_ctc = model2(xs.to(dtype), xlens, ys, ylens)
+                h_enc = None
+            rec["h_attn"] = summarize(h_attn)
+            rec["h_ctc"] = summarize(h_ctc)
+            rec["grads"] = {k: summarize(p.grad, 6) for k, p in model.named_parameters()}
+            rec["bn"] = {k: summarize(v, 6) for k, v in model.state_dict().items() if ".conv.norm.running" in k}
+            rec["nbt"] = {k: int(v) for k, v in model.state_dict().items() if k.endswith("num_batches_tracked")}
+            # split losses
+            import liteasr.criterions.hybrid_ctc_attn as H  # noqa
+            lp = h_ctc.transpose(0, 1).log_softmax(-1)
+            lctc = torch.nn.functional.ctc_loss(lp, ys, model.get_pred_len(xlens), ylens, reduction="sum") / b
+            rec["loss_ctc"] = float(lctc)
+            rec["loss_attn"] = float((float(loss) - w * float(lctc)) / (1 - w))
+        # eval-mode greedy CTC (encoder with mask, running BN stats)
+        model.eval()
+        with torch.no_grad():
+            from liteasr.utils.mask import padding_mask
+            h = model.encoder(xs.to(dtype), mask=padding_mask(xlens))
+            lp = model.ctc.log_softmax(h)
+            ids = lp.argmax(-1)
+            plen = model.get_pred_len(xlens)
+            rec["greedy"] = [greedy(ids[i], int(plen[i])) for i in range(b)]
+            rec["eval_h_enc"] = summarize(h)
+        out[tag] = rec
+    return out
+
+
+def ctc_cases():
+    """Known answers from torch.nn.CTCLoss(reduction='none') + log_softmax backward."""
+    g = torch.Generator().manual_seed(1234)
+    cases = []
+    specs = [
+        # T, B, V, targets(list of lists), in_len
+        (5, 1, 4, [[1, 2]], [5]),
+        (6, 2, 5, [[1, 1, 2], [3]], [6, 4]),           # repeated label needs a blank between
+        (4, 2, 3, [[1, 1], [2, 2]], [3, 4]),            # first utt: T=3 < 2L-ish -> exactly feasible (1 _ 1)
+        (3, 1, 3, [[1, 1]], [2]),                       # infeasible -> inf
+        (7, 3, 6, [[], [5, 4, 3], [2]], [7, 7, 1]),     # empty target, len-1 input
+        (12, 2, 9, [[8, 7, 7, 1], [1, 2, 3, 4, 5]], [12, 10]),
+    ]
+    for T, B, V, tg, il in specs:
+        logits = torch.randn(T, B, V, generator=g, dtype=torch.float64)
+        logits.requires_grad_(True)
+        lmax = max(1, max(len(t) for t in tg))
+        tgt = torch.full((B, lmax), -1, dtype=torch.long)
+        for i, t in enumerate(tg):
+            tgt[i, : len(t)] = torch.tensor(t, dtype=torch.long)
+        tl = torch.tensor([len(t) for t in tg])
+        ilen = torch.tensor(il)
+        lp = logits.log_softmax(-1)
+        nll = torch.nn.functional.ctc_loss(lp, tgt.clamp(min=0), ilen, tl, reduction="none", zero_infinity=False)
+        finite = torch.isfinite(nll)
+        (nll * finite).sum().backward() if finite.any() else None
+        cases.append(dict(T=T, B=B, V=V, logits=logits.detach().tolist(), targets=tgt.tolist(), in_len=il,
+                          tgt_len=tl.tolist(), nll=[float(x) if np.isfinite(float(x)) else "inf" for x in nll],
+                          grad_logits=(logits.grad.tolist() if logits.grad is not None else None),
+                          finite=finite.tolist()))
+    return cases
+
+
+def main():
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    for name in MODEL_CASES:
+        rec = run_model_case(name)
+        with open(os.path.join(GOLDEN_DIR, f"u2_{name}.json"), "w") as f:
+            json.dump(rec, f)
+        print(name, "loss f64", rec["f64"]["loss"], "f32", rec["f32"]["loss"])
+    with open(os.path.join(GOLDEN_DIR, "ctc_golden.json"), "w") as f:
+        json.dump(dict(torch=torch.__version__, cases=ctc_cases()), f)
+    print("golden written to", GOLDEN_DIR)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,482 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement of LiteASR's U2 + hybrid CTC/attention path.
+
+This file is the *oracle*: a functional (state_dict in, tensors out) restatement, in plain
+torch CPU ops plus a C/numpy CTC lattice, of exactly the arithmetic the reference performs
+on its training hot path.  It is pinned against the unmodified reference (imported through
+``oracle/ref_shims.py``) by ``oracle/make_golden.py`` -> ``tests/golden/*.json``; see
+``tests/test_oracle_golden.py``.  Only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it.  The product
+(``liteasr_b200``) never does.
+
+Every function cites the reference lines it restates (paths relative to
+``/root/reference/liteasr``).  Tensors are ``(B, T, feat)`` unless stated otherwise; all
+functions are dtype-agnostic (float32 reproduces the reference bit-for-bit on the same
+torch build for most ops, float64 is used for tight pins).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import os
+import subprocess
+from dataclasses import dataclass
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+Tensor = torch.Tensor
+SD = Dict[str, Tensor]
+
+LN_EPS = 1e-12  # nets/layer_norm.py:10
+BN_EPS = 1e-5  # torch BatchNorm1d default, nets/conformer_convolution.py:41
+BN_MOMENTUM = 0.1
+MASK_FILL = -1e38  # nets/attention.py:54
+DW_KERNEL = 15  # nets/transformer_encoder.py:98
+
+
+@dataclass
+class U2Shape:
+    """The subset of ``U2Config`` (models/u2.py:35-67) that changes arithmetic."""
+
+    input_dim: int = 80
+    vocab_size: int = 500
+    enc_dim: int = 256
+    enc_ff_dim: int = 2048
+    enc_attn_heads: int = 4
+    enc_layers: int = 12
+    dec_dim: int = 256
+    dec_ff_dim: int = 2048
+    dec_attn_heads: int = 4
+    dec_layers: int = 6
+
+    def as_ref_cfg(self) -> dict:
+        return dict(self.__dict__)
+
+
+# --------------------------------------------------------------------------------------
+# masks / lengths / targets
+# --------------------------------------------------------------------------------------
+def pad_mask(lens: Tensor, width: Optional[int] = None) -> Tensor:
+    """utils/mask.py:8-27 -- True marks padding. Width defaults to max(lens)."""
+    w = int(lens.max()) if width is None else width
+    return torch.arange(w).unsqueeze(0) >= lens.unsqueeze(1)
+
+
+def causal_mask(n: int) -> Tensor:
+    """utils/mask.py:30-90 with col=0, stage=1, diagonal=1 -- True above the diagonal."""
+    r = torch.arange(n)
+    return r.unsqueeze(0) > r.unsqueeze(1)
+
+
+def subsampled_len(xlens: Tensor) -> Tensor:
+    """models/u2.py:319-321 ``get_pred_len``."""
+    return ((xlens - 1) // 2 - 1) // 2
+
+
+def subsample_mask(mask: Tensor) -> Tensor:
+    """nets/transformer_encoder.py:118 ("convolution simulation")."""
+    return mask[:, :-2:2][:, :-2:2]
+
+
+def decoder_inputs(ys: Tensor, ylens: Tensor, vocab: int) -> Tuple[Tensor, Tensor]:
+    """models/u2.py:339-358 -- ys_in = [sos | ys with -1 -> eos]; ys_mask over ylens+1."""
+    eos = vocab - 1
+    ys_ = torch.where(ys == -1, torch.full_like(ys, eos), ys)
+    sos = torch.full((ys.size(0), 1), eos, dtype=ys.dtype)
+    return torch.cat([sos, ys_], dim=1), pad_mask(ylens + 1)
+
+
+def attention_targets(ys: Tensor, ylens: Tensor, vocab: int) -> Tensor:
+    """models/u2.py:323-328 -- [ys | -1] with eos written at column ylens[b]."""
+    tgt = torch.cat([ys, torch.full((ys.size(0), 1), -1, dtype=ys.dtype)], dim=1)
+    tgt[torch.arange(ys.size(0)), ylens] = vocab - 1
+    return tgt
+
+
+# --------------------------------------------------------------------------------------
+# primitive blocks
+# --------------------------------------------------------------------------------------
+def layer_norm(sd: SD, p: str, x: Tensor) -> Tensor:
+    """nets/layer_norm.py:8-29 (eps = 1e-12, affine)."""
+    mu = x.mean(-1, keepdim=True)
+    var = ((x - mu) ** 2).mean(-1, keepdim=True)
+    return (x - mu) / torch.sqrt(var + LN_EPS) * sd[p + ".weight"] + sd[p + ".bias"]
+
+
+def dense(sd: SD, p: str, x: Tensor, bias: bool = True) -> Tensor:
+    y = x @ sd[p + ".weight"].t()
+    return y + sd[p + ".bias"] if bias else y
+
+
+def swish(x: Tensor) -> Tensor:
+    """nets/swish.py:14-16."""
+    return x * torch.sigmoid(x)
+
+
+def sinusoid_table(n: int, d: int, dtype) -> Tensor:
+    """nets/positional_encoding.py:29-38 (computed in float32 like the buffer, then cast)."""
+    pos = torch.arange(0, n).unsqueeze(1).float()
+    div = torch.exp(torch.arange(0, d, 2).float() * -(math.log(10000.0) / d))
+    pe = torch.zeros(n, d)
+    pe[:, 0::2] = torch.sin(pos * div)
+    pe[:, 1::2] = torch.cos(pos * div)
+    return pe.to(dtype)
+
+
+def conv2d_subsampling(sd: SD, p: str, x: Tensor) -> Tensor:
+    """nets/subsampling.py:42-48 -- two 3x3 stride-2 convs + ReLU, (c,f)-major flatten, Linear."""
+    F = torch.nn.functional
+    h = F.relu(F.conv2d(x.unsqueeze(1), sd[p + ".conv.0.weight"], sd[p + ".conv.0.bias"], stride=2))
+    h = F.relu(F.conv2d(h, sd[p + ".conv.2.weight"], sd[p + ".conv.2.bias"], stride=2))
+    b, c, t, f = h.shape
+    h = h.permute(0, 2, 1, 3).reshape(b, t, c * f)
+    return dense(sd, p + ".out", h)
+
+
+def rel_shift_index(t: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """Closed form of the legacy ``rel_shift`` (nets/attention.py:99-118, zero_triu=False).
+
+    out[i, j] = BD[i, t-1-(i-j)]   if j <= i
+              = 0                   if j == i + 1
+              = BD[i+1, j-i-2]      if j >  i + 1
+    Derived from the pad/view trick: flat = (i+1)*t + j in the (t, t+1) zero-padded buffer,
+    row r = flat // (t+1), col c = flat % (t+1); c == 0 is the pad, else BD[r, c-1].
+    Returns (row, col, is_zero) index tensors of shape (t, t).
+    """
+    i = torch.arange(t).unsqueeze(1).expand(t, t)
+    j = torch.arange(t).unsqueeze(0).expand(t, t)
+    flat = (i + 1) * t + j
+    r = flat // (t + 1)
+    c = flat % (t + 1)
+    zero = c == 0
+    return r.clamp(max=t - 1), (c - 1).clamp(min=0), zero
+
+
+def rel_shift(bd: Tensor) -> Tensor:
+    t = bd.size(-1)
+    r, c, zero = rel_shift_index(t)
+    out = bd[..., r, c]
+    return out.masked_fill(zero, 0.0)
+
+
+def split_heads(x: Tensor, h: int) -> Tensor:
+    b, t, d = x.shape
+    return x.view(b, t, h, d // h).transpose(1, 2)  # (B,H,T,dk)
+
+
+def softmax_attend(scores: Tensor, v: Tensor, mask: Optional[Tensor]) -> Tensor:
+    """nets/attention.py:46-59 minus linear_o: masked_fill(-1e38) -> softmax -> @V -> merge heads.
+    No post-softmax re-zeroing (quirk Q4)."""
+    if mask is not None:
+        scores = scores.masked_fill(mask, MASK_FILL)
+    a = torch.softmax(scores, dim=-1)
+    o = a @ v
+    b, h, t, dk = o.shape
+    return o.transpose(1, 2).reshape(b, t, h * dk)
+
+
+def rel_self_attention(sd: SD, p: str, x: Tensor, pos: Tensor, mask: Optional[Tensor], h: int) -> Tensor:
+    """nets/attention.py:120-154.  x (B,T,d) already layer-normed; pos (1,T,d); mask (B,1,1,T)."""
+    d = x.size(-1)
+    dk = d // h
+    q = split_heads(dense(sd, p + ".linear_q", x), h)
+    k = split_heads(dense(sd, p + ".linear_k", x), h)
+    v = split_heads(dense(sd, p + ".linear_v", x), h)
+    pp = split_heads(dense(sd, p + ".linear_pos", pos, bias=False), h)  # (1,H,T,dk)
+    qu = q + sd[p + ".pos_bias_u"].unsqueeze(0).unsqueeze(2)
+    qv = q + sd[p + ".pos_bias_v"].unsqueeze(0).unsqueeze(2)
+    ac = qu @ k.transpose(-2, -1)
+    bd = rel_shift(qv @ pp.transpose(-2, -1))
+    scores = (ac + bd) * (dk ** -0.5)
+    return dense(sd, p + ".linear_o", softmax_attend(scores, v, mask))
+
+
+def attention(sd: SD, p: str, xq: Tensor, xkv: Tensor, mask: Optional[Tensor], h: int) -> Tensor:
+    """nets/attention.py:61-71 (plain scaled dot-product MHA; decoder self/src attention)."""
+    dk = xq.size(-1) // h
+    q = split_heads(dense(sd, p + ".linear_q", xq), h)
+    k = split_heads(dense(sd, p + ".linear_k", xkv), h)
+    v = split_heads(dense(sd, p + ".linear_v", xkv), h)
+    scores = (dk ** -0.5) * (q @ k.transpose(-2, -1))
+    return dense(sd, p + ".linear_o", softmax_attend(scores, v, mask))
+
+
+def feed_forward(sd: SD, p: str, x: Tensor, act) -> Tensor:
+    """nets/feed_forward.py:18-19 (dropout = identity at rate 0)."""
+    return dense(sd, p + ".fc2", act(dense(sd, p + ".fc1", x)))
+
+
+def conv_module(sd: SD, p: str, x: Tensor, training: bool, bn_out: Optional[dict]) -> Tensor:
+    """nets/conformer_convolution.py:44-57.  x (B,T,d) already layer-normed.
+
+    pointwise(d->2d) -> GLU(first half * sigmoid(second half)) -> depthwise k=15 pad 7 ->
+    BatchNorm1d (train: biased batch stats over ALL B*T frames incl. padding, quirk Q2;
+    eval: running stats) -> Swish -> pointwise(d->d).  ``bn_out`` receives the running-stat
+    update torch would have applied (momentum 0.1, unbiased variance)."""
+    F = torch.nn.functional
+    d = x.size(-1)
+    y = x @ sd[p + ".pointwise_conv1.weight"].squeeze(-1).t() + sd[p + ".pointwise_conv1.bias"]
+    y = y[..., :d] * torch.sigmoid(y[..., d:])
+    y = F.conv1d(
+        y.transpose(1, 2), sd[p + ".depthwise_conv.weight"], sd[p + ".depthwise_conv.bias"],
+        padding=(DW_KERNEL - 1) // 2, groups=d,
+    ).transpose(1, 2)  # (B,T,d)
+    if training:
+        n = y.size(0) * y.size(1)
+        mean = y.mean(dim=(0, 1))
+        var = ((y - mean) ** 2).mean(dim=(0, 1))
+        if bn_out is not None:
+            rm, rv = sd[p + ".norm.running_mean"], sd[p + ".norm.running_var"]
+            bn_out[p + ".norm.running_mean"] = ((1 - BN_MOMENTUM) * rm + BN_MOMENTUM * mean).detach()
+            bn_out[p + ".norm.running_var"] = (
+                (1 - BN_MOMENTUM) * rv + BN_MOMENTUM * var * (n / max(n - 1, 1))
+            ).detach()
+            bn_out[p + ".norm.num_batches_tracked"] = sd[p + ".norm.num_batches_tracked"] + 1
+    else:
+        mean, var = sd[p + ".norm.running_mean"], sd[p + ".norm.running_var"]
+    y = (y - mean) / torch.sqrt(var + BN_EPS) * sd[p + ".norm.weight"] + sd[p + ".norm.bias"]
+    y = swish(y)
+    return y @ sd[p + ".pointwise_conv2.weight"].squeeze(-1).t() + sd[p + ".pointwise_conv2.bias"]
+
+
+def conformer_layer(sd: SD, p: str, x: Tensor, pos: Tensor, mask, h: int, training: bool, bn_out) -> Tensor:
+    """nets/conformer_layer.py:130-147 (pre-norm, macaron FFN scale 0.5, extra final_norm)."""
+    x = x + 0.5 * feed_forward(sd, p + ".feed_forward_macaron", layer_norm(sd, p + ".feed_forward_macaron_norm", x), swish)
+    x = x + rel_self_attention(sd, p + ".self_attn", layer_norm(sd, p + ".self_attn_norm", x), pos, mask, h)
+    x = x + conv_module(sd, p + ".conv", layer_norm(sd, p + ".conv_norm", x), training, bn_out)
+    x = x + 0.5 * feed_forward(sd, p + ".feed_forward", layer_norm(sd, p + ".feed_forward_norm", x), swish)
+    return layer_norm(sd, p + ".final_norm", x)
+
+
+def encoder(sd: SD, cfg: U2Shape, xs: Tensor, xs_mask: Optional[Tensor], training: bool = True,
+            bn_out: Optional[dict] = None) -> Tensor:
+    """nets/transformer_encoder.py:107-127 with use_rel=True, arch=conformer, activation=swish."""
+    d = cfg.enc_dim
+    x = conv2d_subsampling(sd, "encoder.embed", xs)
+    x = x * math.sqrt(d)  # positional_encoding.py:73
+    pos = sinusoid_table(x.size(1), d, x.dtype).unsqueeze(0)  # :74 -- absolute positions 0..T'-1
+    mask = None
+    if xs_mask is not None:
+        assert tuple(xs_mask.shape) == tuple(xs.shape[:2])
+        m = subsample_mask(xs_mask)
+        mask = m.view(m.size(0), 1, 1, m.size(1))
+    for i in range(cfg.enc_layers):
+        x = conformer_layer(sd, f"encoder.enc_layers.{i}", x, pos, mask, cfg.enc_attn_heads, training, bn_out)
+    return layer_norm(sd, "encoder.after_norm", x)
+
+
+def decoder(sd: SD, cfg: U2Shape, ys_in: Tensor, self_mask: Tensor, memory: Tensor,
+            memory_mask: Optional[Tensor]) -> Tensor:
+    """nets/transformer_decoder.py:70-93 + nets/transformer_layer.py:179-221 (ReLU FFN, pre-norm)."""
+    d = cfg.dec_dim
+    h = cfg.dec_attn_heads
+    y = sd["decoder.embed.weight"][ys_in]
+    y = y * math.sqrt(d) + sinusoid_table(y.size(1), d, y.dtype).unsqueeze(0)
+    smask = self_mask.unsqueeze(1)
+    mmask = None
+    if memory_mask is not None:
+        m = subsample_mask(memory_mask)
+        assert tuple(m.shape) == tuple(memory.shape[:2])
+        mmask = m.view(m.size(0), 1, 1, m.size(1))
+    for i in range(cfg.dec_layers):
+        p = f"decoder.dec_layers.{i}"
+        z = layer_norm(sd, p + ".self_attn_norm", y)
+        y = y + attention(sd, p + ".self_attn", z, z, smask, h)
+        z = layer_norm(sd, p + ".src_attn_norm", y)
+        y = y + attention(sd, p + ".src_attn", z, memory, mmask, h)
+        y = y + feed_forward(sd, p + ".feed_forward", layer_norm(sd, p + ".feed_forward_norm", y), torch.relu)
+    return dense(sd, "decoder.linear_out", layer_norm(sd, "decoder.after_norm", y))
+
+
+def u2_forward(sd: SD, cfg: U2Shape, xs, xlens, ys, ylens, training: bool = True, bn_out=None):
+    """models/u2.py:116-159 -> (h_attn (B,L+1,V), h_ctc (B,T',V), h_enc). CTC-head dropout = 0."""
+    xs_mask = pad_mask(xlens, xs.size(1))
+    ys_in, ys_mask = decoder_inputs(ys, ylens, cfg.vocab_size)
+    h_enc = encoder(sd, cfg, xs, xs_mask, training, bn_out)
+    dec_mask = ys_mask.unsqueeze(1) | causal_mask(ys_mask.size(1)).unsqueeze(0)
+    h_attn = decoder(sd, cfg, ys_in, dec_mask, h_enc, xs_mask)
+    h_ctc = dense(sd, "ctc.ctc_lo", h_enc)
+    return h_attn, h_ctc, h_enc
+
+
+# --------------------------------------------------------------------------------------
+# CTC alpha-beta (restates torch.nn.CTCLoss == ATen LossCTC.cpp semantics; torch 2.11.0 pin)
+# --------------------------------------------------------------------------------------
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CLIB = None
+
+
+def build_c_oracle(force: bool = False) -> str:
+    """gcc -O2 oracle/ctc_oracle.c -> oracle/_build/libctc_oracle.so (plain C, no deps)."""
+    out_dir = os.path.join(_HERE, "_build")
+    so = os.path.join(out_dir, "libctc_oracle.so")
+    src = os.path.join(_HERE, "ctc_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        os.makedirs(out_dir, exist_ok=True)
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-fopenmp", "-o", so, src, "-lm"])
+    return so
+
+
+def _clib():
+    global _CLIB
+    if _CLIB is None:
+        lib = ctypes.CDLL(build_c_oracle())
+        lib.ctc_alpha_beta_f64.restype = ctypes.c_int
+        lib.ctc_alpha_beta_f64.argtypes = [ctypes.c_void_p] * 7 + [ctypes.c_long] * 4 + [ctypes.c_int]
+        _CLIB = lib
+    return _CLIB
+
+
+def ctc_alpha_beta_numpy(lp: np.ndarray, targets: np.ndarray, in_len: np.ndarray, tgt_len: np.ndarray,
+                         blank: int = 0):
+    """Pure-numpy float64 alpha-beta (small cases only).  lp (T,B,V) log-probs.
+
+    Returns (nll (B,), dnll_dlp (T,B,V)) where dnll_dlp = -occupancy (the true partial
+    derivative wrt the log-probs; rows t >= in_len[b] are 0).  Infeasible -> nll = +inf."""
+    T, B, V = lp.shape
+    nll = np.zeros(B)
+    g = np.zeros_like(lp, dtype=np.float64)
+    NEG = -np.inf
+
+    def lse(*a):
+        m = max(a)
+        if m == NEG:
+            return NEG
+        return m + math.log(sum(math.exp(x - m) for x in a))
+
+    for b in range(B):
+        Tb, L = int(in_len[b]), int(tgt_len[b])
+        ext = [blank] * (2 * L + 1)
+        for k in range(L):
+            ext[2 * k + 1] = int(targets[b, k])
+        S = 2 * L + 1
+        al = np.full((Tb, S), NEG)
+        be = np.full((Tb, S), NEG)
+        if Tb == 0:
+            nll[b] = 0.0 if L == 0 else np.inf
+            continue
+        al[0, 0] = lp[0, b, blank]
+        if S > 1:
+            al[0, 1] = lp[0, b, ext[1]]
+        for t in range(1, Tb):
+            for s in range(S):
+                a = [al[t - 1, s]]
+                if s >= 1:
+                    a.append(al[t - 1, s - 1])
+                if s >= 2 and ext[s] != blank and ext[s] != ext[s - 2]:
+                    a.append(al[t - 1, s - 2])
+                al[t, s] = lp[t, b, ext[s]] + lse(*a)
+        tot = lse(al[Tb - 1, S - 1], al[Tb - 1, S - 2]) if S > 1 else al[Tb - 1, 0]
+        nll[b] = -tot
+        if not np.isfinite(tot):
+            g[:Tb, b, :] = np.nan
+            continue
+        be[Tb - 1, S - 1] = lp[Tb - 1, b, ext[S - 1]]
+        if S > 1:
+            be[Tb - 1, S - 2] = lp[Tb - 1, b, ext[S - 2]]
+        for t in range(Tb - 2, -1, -1):
+            for s in range(S):
+                a = [be[t + 1, s]]
+                if s + 1 < S:
+                    a.append(be[t + 1, s + 1])
+                if s + 2 < S and ext[s] != blank and ext[s] != ext[s + 2]:
+                    a.append(be[t + 1, s + 2])
+                be[t, s] = lp[t, b, ext[s]] + lse(*a)
+        for t in range(Tb):
+            for s in range(S):
+                ab = al[t, s] + be[t, s]
+                if ab > NEG:
+                    g[t, b, ext[s]] -= math.exp(ab - lp[t, b, ext[s]] - tot)
+    return nll, g
+
+
+def ctc_alpha_beta_c(lp: np.ndarray, targets: np.ndarray, in_len: np.ndarray, tgt_len: np.ndarray):
+    """Same contract as ``ctc_alpha_beta_numpy`` through oracle/ctc_oracle.c (fast)."""
+    lp = np.ascontiguousarray(lp, dtype=np.float64)
+    T, B, V = lp.shape
+    targets = np.ascontiguousarray(targets, dtype=np.int64)
+    if targets.ndim == 1:
+        targets = targets.reshape(B, -1)
+    in_len = np.ascontiguousarray(in_len, dtype=np.int64)
+    tgt_len = np.ascontiguousarray(tgt_len, dtype=np.int64)
+    nll = np.zeros(B, dtype=np.float64)
+    g = np.zeros_like(lp)
+    lmax = targets.shape[1]
+    ws = np.zeros(1, dtype=np.float64)
+    rc = _clib().ctc_alpha_beta_f64(
+        lp.ctypes.data, targets.ctypes.data, in_len.ctypes.data, tgt_len.ctypes.data,
+        nll.ctypes.data, g.ctypes.data, ws.ctypes.data, T, B, V, lmax, 0,
+    )
+    if rc != 0:
+        raise RuntimeError(f"ctc_alpha_beta_f64 failed rc={rc}")
+    return nll, g
+
+
+class _CTCNll(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, lp, targets, in_len, tgt_len):
+        nll, g = ctc_alpha_beta_c(lp.detach().double().numpy(), targets.numpy(), in_len.numpy(), tgt_len.numpy())
+        ctx.save_for_backward(torch.from_numpy(g).to(lp.dtype))
+        return torch.from_numpy(nll).to(lp.dtype)
+
+    @staticmethod
+    def backward(ctx, gout):
+        (g,) = ctx.saved_tensors
+        return g * gout.view(1, -1, 1), None, None, None
+
+
+def ctc_nll(lp: Tensor, targets: Tensor, in_len: Tensor, tgt_len: Tensor) -> Tensor:
+    """Per-utterance -log p(l|x) with autograd; lp (T,B,V) log-probs."""
+    return _CTCNll.apply(lp, targets, in_len, tgt_len)
+
+
+# --------------------------------------------------------------------------------------
+# criterion
+# --------------------------------------------------------------------------------------
+def label_smoothing_kl(h_attn: Tensor, tgt: Tensor, smoothing: float) -> Tensor:
+    """criterions/hybrid_ctc_attn.py:49-64 -- sum over non-ignored rows of KL(q || softmax),
+    q = eps/(V-1) off-target, 1-eps on target.  Returns the SUM (caller divides by B)."""
+    v = h_attn.size(-1)
+    flat = h_attn.reshape(-1, v)
+    t = tgt.reshape(-1)
+    ign = t == -1
+    t0 = t.masked_fill(ign, 0)
+    q = torch.full_like(flat, smoothing / (v - 1))
+    q.scatter_(1, t0.unsqueeze(1), 1.0 - smoothing)
+    logp = torch.log_softmax(flat, dim=1)
+    # KLDivLoss(reduction="none") = xlogy(q, q) - q * logp  (0 where q == 0)
+    kl = torch.xlogy(q, q) - q * logp
+    return kl.masked_fill(ign.unsqueeze(1), 0).sum()
+
+
+def hybrid_loss(sd: SD, cfg: U2Shape, xs, xlens, ys, ylens, ctc_weight: float, smoothing: float,
+                training: bool = True, bn_out=None):
+    """criterions/hybrid_ctc_attn.py:39-79 -> dict(loss, loss_ctc, loss_attn, h_attn, h_ctc, h_enc)."""
+    h_attn, h_ctc, h_enc = u2_forward(sd, cfg, xs, xlens, ys, ylens, training, bn_out)
+    b = ys.size(0)
+    loss_attn = label_smoothing_kl(h_attn, attention_targets(ys, ylens, cfg.vocab_size), smoothing) / b
+    lp = torch.log_softmax(h_ctc.transpose(0, 1), dim=-1)
+    loss_ctc = ctc_nll(lp, ys, subsampled_len(xlens), ylens).sum() / b
+    loss = ctc_weight * loss_ctc + (1 - ctc_weight) * loss_attn
+    return dict(loss=loss, loss_ctc=loss_ctc, loss_attn=loss_attn, h_attn=h_attn, h_ctc=h_ctc, h_enc=h_enc)
+
+
+def greedy_ctc(sd: SD, cfg: U2Shape, xs: Tensor, xlens: Optional[Tensor] = None):
+    """Greedy CTC decode (not in the reference; defined from nets/ctc.py:25-26 as
+    argmax_v log_softmax(ctc_lo(encoder(x))) -> collapse repeats -> drop blank 0).
+    xlens=None mirrors the reference's maskless inference encoder call (models/u2.py:222)."""
+    mask = None if xlens is None else pad_mask(xlens, xs.size(1))
+    h = encoder(sd, cfg, xs, mask, training=False)
+    ids = torch.log_softmax(dense(sd, "ctc.ctc_lo", h), dim=-1).argmax(-1)
+    out = []
+    for b in range(ids.size(0)):
+        n = ids.size(1) if xlens is None else int(subsampled_len(xlens[b]))
+        seq, prev = [], -1
+        for t in range(n):
+            c = int(ids[b, t])
+            if c != prev and c != 0:
+                seq.append(c)
+            prev = c
+        out.append(seq)
+    return out, ids
