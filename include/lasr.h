@@ -1,0 +1,211 @@
+/* liblasr -- C ABI of the B200-native (sm_100a) kernels behind LiteASR's U2 + hybrid-CTC hot path.
+ *
+ * The reference (Nazukixv/LiteASR) has NO FFI: every FLOP on its hot path is a stock torch op
+ * (SURVEY.md section 2.1).  Each entry point below therefore names the reference *call site* whose
+ * arithmetic it replaces (paths relative to /root/reference/liteasr).  INTEGRATION.md shows the
+ * ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C: raw device pointers + sizes, no torch types; the caller (PyTorch) owns every buffer,
+ *     the library never allocates or frees device memory and keeps no mutable global state
+ *     (except the thread-local last-error string and a cached driver entry point).
+ *   - every function enqueues on `stream` (a cudaStream_t passed as void*) and never synchronises;
+ *     all of them are CUDA-graph capturable.
+ *   - return 0 on success, a negative LASR_ERR_* on failure; lasr_last_error() describes it.
+ *     Nothing throws across the ABI, nothing exits.  There is no CPU fallback.
+ *   - dtype codes: LASR_F32 / LASR_BF16.  Math and accumulation are always fp32.
+ */
+#ifndef LASR_H
+#define LASR_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LASR_OK 0
+#define LASR_ERR_BAD_ARG (-1)
+#define LASR_ERR_UNSUPPORTED (-2)
+#define LASR_ERR_CUDA (-3)
+#define LASR_ERR_DRIVER (-4)
+
+#define LASR_F32 0
+#define LASR_BF16 1
+
+#define LASR_ACT_NONE 0
+#define LASR_ACT_RELU 1
+#define LASR_ACT_SWISH 2
+
+int lasr_version(void);             /* 100 * major + minor */
+int lasr_arch(void);                /* 100 (sm_100a) */
+const char* lasr_last_error(void);  /* thread-local, valid until the next failing call */
+
+/* ------------------------------------------------------------------------------------------------
+ * GEMM  C[b1,b2] = alpha * act(A[b1,b2] . B[b1,b2]^T + bias) (+ res)
+ *   bf16 operands -> tcgen05.mma (TMEM accumulators, TMA-fed, 128xBNx64 tiles);
+ *   fp32 operands -> SIMT fp32 FMA kernel (the "fp32 parity mode").
+ * Replaces every nn.Linear / 1x1 Conv1d / torch.matmul on the path:
+ *   nets/feed_forward.py:18-19, nets/attention.py:35-37,56,58,132,145,149,
+ *   nets/conformer_convolution.py:48,55, nets/subsampling.py:34,47 (via im2col),
+ *   nets/ctc.py:29, nets/transformer_decoder.py:91 and their autograd backward GEMMs.
+ *   trans_a = 0: A is (M,K) row-major with row stride lda;  1: A is stored (K,M) row-major.
+ *   trans_b = 0: B is (N,K) row-major (nn.Linear weight);   1: B is stored (K,N) row-major.
+ *   Two-level batching (b1 outer, b2 inner) with independent element strides, so head-interleaved
+ *   (B,T,H,dk) tensors are addressed in place (stride 0 broadcasts an operand).
+ *   aux (optional, C dtype/ldc): receives the pre-activation value (acc + bias).
+ *   accumulate = 1: C (fp32) += alpha * A.B^T with red.global.add (split-K and batch-reduce wgrads);
+ *                   bias/act/res/aux must be unset; a C batch stride of 0 reduces over that batch level.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct lasr_gemm_args {
+    const void* a;
+    const void* b;
+    void* c;
+    const float* bias; /* [N] fp32 or NULL */
+    const float* res;  /* fp32 residual, addressed like C (ldres) or NULL */
+    void* aux;         /* optional pre-activation output (C dtype, ldc) */
+    int32_t m, n, k;
+    int32_t ab_dtype, c_dtype;
+    int32_t trans_a, trans_b;
+    int64_t lda, ldb, ldc, ldres;
+    int32_t batch1, batch2;
+    int64_t sa1, sa2, sb1, sb2, sc1, sc2; /* element strides per batch level (res/aux follow C) */
+    float alpha;
+    int32_t act;
+    int32_t accumulate;
+    int32_t split_k; /* >= 1; > 1 requires accumulate */
+} lasr_gemm_args;
+
+int lasr_gemm(const lasr_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * CTC forward-backward fused with the log-softmax backward.
+ * Replaces criterions/hybrid_ctc_attn.py:67-75 (transpose + log_softmax + nn.CTCLoss(sum) and the
+ * autograd backward of all three).  logits (T,B,V) with element strides (st, sb, 1) so the model's
+ * (B,T',V) tensor is consumed in place; targets (B,lmax) int64 padded (any value) beyond tgt_len.
+ *   nll[b]          = -log p(l_b | x_b)   (+inf when infeasible, like zero_infinity=False)
+ *   grad[t,b,c]     = grad_scale * upstream * (softmax[t,b,c] - occupancy[t,b,c])  for t <  in_len[b]
+ *                   = 0                                                            for t >= in_len[b]
+ *   upstream: optional device scalar (fp32) multiplied into grad_scale (autograd's grad_output).
+ * Workspace: lasr_ctc_workspace_bytes(T,B,lmax).
+ * ------------------------------------------------------------------------------------------------ */
+size_t lasr_ctc_workspace_bytes(int T, int B, int lmax);
+int lasr_ctc_fwdbwd(const void* logits, int dtype, int64_t st, int64_t sb, const int64_t* targets,
+                    const int64_t* in_len, const int64_t* tgt_len, int T, int B, int V, int lmax, int blank,
+                    float grad_scale, const float* upstream, float* nll, void* grad, int64_t gst, int64_t gsb,
+                    void* workspace, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm over the last dim (nets/layer_norm.py:8-29, eps 1e-12) and its backward.
+ *   fwd: y = (x - mean) * rstd * gamma + beta; x fp32 (rows,d) row stride ldx; y fp32|bf16.
+ *   bwd: dx (+)= LN'(dy) (accumulate = 1 adds into dx: the residual-stream gradient);
+ *        dgamma/dbeta are ACCUMULATED (red.add) into the caller's (pre-zeroed) gradient buffers.
+ * d % 4 == 0, d <= 1024.
+ * ------------------------------------------------------------------------------------------------ */
+int lasr_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, void* y, int y_dtype,
+                       int64_t ldy, float* mean, float* rstd, int rows, int d, float eps, void* stream);
+int lasr_layernorm_bwd(const void* dy, int dy_dtype, int64_t lddy, const float* x, int64_t ldx, const float* mean,
+                       const float* rstd, const float* gamma, float* dx, int64_t lddx, int accumulate, float* dgamma,
+                       float* dbeta, int rows, int d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Casts / relayouts (weights fp32 master -> bf16 operand copies; conv weight permutations and the
+ * inverse scatter of their gradients).  permute4d: dst[i.ds] (+)= src[i.ss] over a 4-D index space.
+ * ------------------------------------------------------------------------------------------------ */
+int lasr_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
+int lasr_permute4d(const void* src, int src_dtype, void* dst, int dst_dtype, const int64_t* n, const int64_t* src_strides,
+                   const int64_t* dst_strides, int accumulate, void* stream);
+
+/* dh = da * act'(saved) (saved = pre-activation for swish, activation output for relu), dbias += colsum(dh).
+ * Backward of the fused bias+activation GEMM epilogue (nets/feed_forward.py:18-19, nn.Linear biases).
+ * dh may be NULL for act = none (bias gradient only). */
+int lasr_act_bwd(const void* da, int64_t ldda, const void* saved, int64_t lds, void* dh, int64_t lddh, float* dbias, int rows,
+                 int cols, int act, int dtype, void* stream);
+
+/* q + pos_bias_u, q + pos_bias_v (nets/attention.py:135-139) and the backward
+ * (dq = dqu + dqv, du += colsum(dqu), dv += colsum(dqv)). */
+int lasr_pos_bias_fwd(const void* q, int64_t ldq, const float* u, const float* v, void* qu, void* qv, int64_t ldo, int rows,
+                      int d, int dtype, void* stream);
+int lasr_pos_bias_bwd(const void* dqu, const void* dqv, int64_t ldi, void* dq, int64_t ldq, float* du, float* dv, int rows, int d,
+                      int dtype, void* stream);
+
+/* Decoder input embedding: out[b,l] = emb[token(b,l)] * scale + pe[l], token = sos for l = 0 else ys[b,l-1]
+ * with -1 -> eos (models/u2.py:346-353, nets/transformer_decoder.py:77-78); backward scatter-adds into demb. */
+int lasr_embed_fwd(const int64_t* ys, int lmax, const float* emb, const float* pe, float* out, int B, int d, float scale,
+                   int sos_eos, void* stream);
+int lasr_embed_bwd(const int64_t* ys, int lmax, const float* dout, float* demb, int B, int d, float scale, int sos_eos,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Conformer convolution-module middle: GLU -> depthwise Conv1d(k=15,pad 7) -> BatchNorm1d -> Swish
+ * (nets/conformer_convolution.py:49-53) on (B,T',C) channel-contiguous tensors, and its backward.
+ *   y2 (B*T', 2d) = pointwise_conv1 output (value half | gate half), row stride ldy
+ *   z  (B*T', d) fp32 = depthwise output;  partial: B*ceil(T'/32)*2*d floats of per-chunk sum / sum-sq
+ *   bn_finalize: training=1 -> batch statistics over ALL B*T' frames (padding included, quirk Q2) +
+ *                running-stat update (momentum, unbiased var, num_batches_tracked += 1);
+ *                training=0 -> mean/rstd from the running statistics.
+ *   bwd_stats : partial (ceil(rows/32)*2*d) -> sums[0:d] = sum du, sums[d:2d] = sum du*zhat; dgamma/dbeta +=
+ *   dwconv_glu_bwd: dy2 (B*T',2d), dw (d,15) += , dbias (d) +=
+ * ------------------------------------------------------------------------------------------------ */
+int lasr_glu_dwconv_fwd(const void* y2, int dtype, int64_t ldy, const float* w, const float* bias, float* z, float* partial,
+                        int B, int T, int d, void* stream);
+int lasr_bn_finalize(const float* partial, int nblk, int d, int64_t count, float eps, float momentum, float* mean, float* rstd,
+                     float* running_mean, float* running_var, int64_t* num_batches_tracked, int training, void* stream);
+int lasr_bn_swish_fwd(const float* z, const float* mean, const float* rstd, const float* gamma, const float* beta, void* a,
+                      int dtype, int64_t rows, int d, void* stream);
+int lasr_bn_swish_bwd_stats(const void* da, int dtype, const float* z, const float* mean, const float* rstd, const float* gamma,
+                            const float* beta, float* partial, float* sums, float* dgamma, float* dbeta, int64_t rows, int d,
+                            void* stream);
+int lasr_dwconv_glu_bwd(const void* da, const float* z, const void* y2, int dtype, int64_t ldy, const float* mean, const float* rstd,
+                        const float* gamma, const float* beta, const float* sums, const float* w, void* dy2, int64_t lddy, float* dw,
+                        float* dbias, int B, int T, int d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Conv2d subsampling (nets/subsampling.py:32-35,42-46), channel-last.
+ *   conv1_fwd : x (B,T,F) fp32 -> h1 (B,T1,F1,d) = relu(conv3x3 s2), T1=(T-3)/2+1, F1=(F-3)/2+1
+ *   conv1_bwd : dw (d,1,3,3) += , dbias += from dh1 (already ReLU-masked)
+ *   im2col_s2 : h1 -> col (B*T2*F2, 9d), K index (kh,kw,c); conv2 itself is lasr_gemm on col
+ *   col2im_s2_relu : dh1 = relu'(h1) * gather(dcol)
+ * ------------------------------------------------------------------------------------------------ */
+int lasr_conv1_fwd(const float* x, const float* w, const float* bias, void* h1, int dtype, int B, int T, int F, int d, void* stream);
+int lasr_conv1_bwd(const float* x, const void* dh1, int dtype, float* dw, float* dbias, int B, int T, int F, int d, void* stream);
+int lasr_im2col_s2(const void* h1, void* col, int dtype, int B, int T1, int F1, int d, void* stream);
+int lasr_col2im_s2_relu(const void* dcol, const void* h1, void* dh1, int dtype, int B, int T1, int F1, int d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Attention score post-processing (nets/attention.py:46-59,99-118,145-152): legacy rel_shift of bd
+ * (NULL for plain attention) + scale + key/causal mask (-1e38 fill) + softmax, and the backward
+ * (dscores = p*(dp - sum p*dp)*scale; dbd = inverse shift of dscores, NULL for plain attention).
+ * ac/bd/dprobs fp32 (B,H,Tq,ld); probs/dscores/dbd fp32|bf16 (B,H,Tq,ld); columns [Tk,ld) are zeroed.
+ * mask_mode: 0 none | 1 klen=lens[b] | 2 klen=lens[b]+1 | 3 klen=#{j: 4j<lens[b]} (encoder sub-sampled mask).
+ * ------------------------------------------------------------------------------------------------ */
+int lasr_attn_softmax_fwd(const float* ac, const float* bd, void* probs, int p_dtype, const int64_t* lens, int mask_mode, int causal,
+                          float scale, int B, int H, int Tq, int Tk, int ld, void* stream);
+int lasr_attn_softmax_bwd(const void* probs, const float* dprobs, void* dscores, void* dbd, int dtype, float scale, int B, int H, int Tq,
+                          int Tk, int ld, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Label-smoothed KL on the decoder logits, forward + gradient (criterions/hybrid_ctc_attn.py:49-64;
+ * targets built on the fly from ys/ylens as models/u2.py:323-328), and the hybrid mix (:78).
+ * row_loss: B*(lmax+1) floats.  hybrid_combine: out[0]=loss, out[1]=ctc term, out[2]=attention term.
+ * ------------------------------------------------------------------------------------------------ */
+int lasr_lsmooth_kl_fwdbwd(const void* logits, int dtype, int64_t ldl, const int64_t* ys, const int64_t* ylens, int B, int lmax, int V,
+                           float smoothing, float grad_scale, const float* upstream, float* row_loss, void* grad, int64_t ldg,
+                           void* stream);
+int lasr_hybrid_combine(const float* nll, int B, const float* row_kl, int M, float ctc_weight, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused optimizer tail over flat buffers (trainer.py:153-171, optims/noam.py:33-46, optims/adam.py:27-34):
+ * global-norm clip + NaN-skip + Noam LR + Adam, no host sync.  state: 8 floats {step, grad_norm, lr,
+ * skipped, grad_scale,...}; workspace: 1024 floats.
+ * ------------------------------------------------------------------------------------------------ */
+int lasr_clip_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float grad_mult,
+                        float max_norm, float beta1, float beta2, float eps, float weight_decay, float noam_factor, float model_dim,
+                        float warmup, float fixed_lr, float* state, float* workspace, void* stream);
+int lasr_zero(void* ptr, size_t bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LASR_H */

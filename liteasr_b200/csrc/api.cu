@@ -1,0 +1,58 @@
+// C-ABI glue: error reporting, version, and the GEMM dispatcher.
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace lasr {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return LASR_ERR_CUDA;
+    }
+    return LASR_OK;
+}
+
+int gemm_tc_dispatch(const lasr_gemm_args* a, cudaStream_t st);
+int gemm_simt_dispatch(const lasr_gemm_args* a, cudaStream_t st);
+
+}  // namespace lasr
+
+extern "C" {
+
+int lasr_version(void) { return 1; }
+int lasr_arch(void) { return 100; }
+const char* lasr_last_error(void) { return lasr::g_err; }
+
+int lasr_gemm(const lasr_gemm_args* a, void* stream) {
+    using namespace lasr;
+    LASR_REQUIRE(a && a->a && a->b && a->c, "gemm: null operand");
+    LASR_REQUIRE(a->m > 0 && a->n > 0 && a->k > 0, "gemm: bad shape m=%d n=%d k=%d", a->m, a->n, a->k);
+    LASR_REQUIRE(a->batch1 >= 1 && a->batch2 >= 1, "gemm: bad batch");
+    LASR_REQUIRE((long)a->batch1 * a->batch2 * (a->split_k < 1 ? 1 : a->split_k) <= 65535, "gemm: batch*split_k > 65535");
+    if (a->accumulate)
+        LASR_REQUIRE(a->c_dtype == LASR_F32 && !a->bias && !a->res && !a->aux && a->act == LASR_ACT_NONE,
+                     "gemm: accumulate needs fp32 C and no epilogue");
+    if (a->split_k > 1) LASR_REQUIRE(a->accumulate, "gemm: split_k > 1 requires accumulate");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a->ab_dtype == LASR_BF16) return gemm_tc_dispatch(a, st);
+    if (a->ab_dtype == LASR_F32) {
+        LASR_REQUIRE(a->c_dtype == LASR_F32, "gemm: fp32 operands need fp32 C");
+        return gemm_simt_dispatch(a, st);
+    }
+    set_error("gemm: unsupported dtype %d", a->ab_dtype);
+    return LASR_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"

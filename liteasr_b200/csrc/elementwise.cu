@@ -1,0 +1,259 @@
+// Bandwidth kernels around the GEMMs: casts / relayouts, activation backward + bias gradient,
+// rel-pos bias add (nets/attention.py:135-139), decoder embedding + positional encoding
+// (nets/transformer_decoder.py:77-78, nets/positional_encoding.py:49-56).
+// All are coalesced along the feature dimension with 128-bit (fp32) / 64-bit (bf16) accesses.
+#include "common.cuh"
+
+namespace lasr {
+
+template <typename TD>
+__device__ __forceinline__ float4 ld4(const TD* p) {
+    if constexpr (sizeof(TD) == 4) {
+        return *reinterpret_cast<const float4*>(p);
+    } else {
+        const uint2 u = *reinterpret_cast<const uint2*>(p);
+        const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x), b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+        return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+    }
+}
+template <typename TD>
+__device__ __forceinline__ void st4(TD* p, float4 v) {
+    if constexpr (sizeof(TD) == 4) {
+        *reinterpret_cast<float4*>(p) = v;
+    } else {
+        __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+        uint2 u; u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(p) = u;
+    }
+}
+
+// ------------------------------------------------------------------ cast fp32 -> bf16 (flat)
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long n) {
+    const long i4 = ((long)blockIdx.x * 256 + threadIdx.x) * 4;
+    if (i4 + 3 < n) {
+        st4<bf16>(dst + i4, *reinterpret_cast<const float4*>(src + i4));
+    } else {
+        for (long i = i4; i < n; ++i) dst[i] = __float2bfloat16_rn(src[i]);
+    }
+}
+
+// ------------------------------------------------------------------ generic 4-D strided copy/cast
+struct Perm4 {
+    long n[4], ss[4], ds[4];
+};
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(256) permute4d_kernel(const TS* __restrict__ src, TD* __restrict__ dst, Perm4 p,
+                                                        int accumulate) {
+    const long total = p.n[0] * p.n[1] * p.n[2] * p.n[3];
+    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+        long r = i;
+        const long i3 = r % p.n[3]; r /= p.n[3];
+        const long i2 = r % p.n[2]; r /= p.n[2];
+        const long i1 = r % p.n[1]; r /= p.n[1];
+        const long i0 = r;
+        const long so = i0 * p.ss[0] + i1 * p.ss[1] + i2 * p.ss[2] + i3 * p.ss[3];
+        const long dO = i0 * p.ds[0] + i1 * p.ds[1] + i2 * p.ds[2] + i3 * p.ds[3];
+        float v = to_f32<TS>(src[so]);
+        if (accumulate) v += to_f32<TD>(dst[dO]);
+        dst[dO] = from_f32<TD>(v);
+    }
+}
+
+// ------------------------------------------------------------------ dH = dA * act'(.), dbias += colsum(dH)
+// saved: pre-activation H for swish, activation output A for relu (relu'(h) = a > 0), unused for none.
+template <typename TD>
+__global__ void __launch_bounds__(256) act_bwd_kernel(const TD* __restrict__ da, long ldda, const TD* __restrict__ saved,
+                                                      long lds, TD* __restrict__ dh, long lddh,
+                                                      float* __restrict__ dbias, int rows, int cols, int act) {
+    __shared__ float4 red[4][64];
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    const int c = (blockIdx.x * 64 + tx) * 4;
+    const int r0 = blockIdx.y * 64, r1 = min(rows, r0 + 64);
+    float4 acc = make_float4(0, 0, 0, 0);
+    if (c < cols) {
+        for (int r = r0 + ty; r < r1; r += 4) {
+            float4 g = ld4<TD>(da + (long)r * ldda + c);
+            if (act == LASR_ACT_SWISH) {
+                const float4 h = ld4<TD>(saved + (long)r * lds + c);
+                g.x *= dswishf_(h.x); g.y *= dswishf_(h.y); g.z *= dswishf_(h.z); g.w *= dswishf_(h.w);
+            } else if (act == LASR_ACT_RELU) {
+                const float4 a = ld4<TD>(saved + (long)r * lds + c);
+                g.x = a.x > 0.f ? g.x : 0.f; g.y = a.y > 0.f ? g.y : 0.f; g.z = a.z > 0.f ? g.z : 0.f; g.w = a.w > 0.f ? g.w : 0.f;
+            }
+            if (dh) st4<TD>(dh + (long)r * lddh + c, g);
+            acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+        }
+    }
+    if (!dbias) return;
+    red[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && c < cols) {
+        float4 t = red[0][tx];
+#pragma unroll
+        for (int w = 1; w < 4; ++w) { t.x += red[w][tx].x; t.y += red[w][tx].y; t.z += red[w][tx].z; t.w += red[w][tx].w; }
+        atomicAdd(dbias + c, t.x); atomicAdd(dbias + c + 1, t.y); atomicAdd(dbias + c + 2, t.z); atomicAdd(dbias + c + 3, t.w);
+    }
+}
+
+// ------------------------------------------------------------------ q + pos_bias_u / q + pos_bias_v
+template <typename TD>
+__global__ void __launch_bounds__(256) pos_bias_fwd_kernel(const TD* __restrict__ q, long ldq, const float* __restrict__ u,
+                                                           const float* __restrict__ v, TD* __restrict__ qu,
+                                                           TD* __restrict__ qv, long ldo, int rows, int d) {
+    const int per_row = d >> 2;
+    const long i = (long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= (long)rows * per_row) return;
+    const long r = i / per_row;
+    const int c = (int)(i % per_row) * 4;
+    const float4 x = ld4<TD>(q + r * ldq + c);
+    const float4 bu = *reinterpret_cast<const float4*>(u + c), bv = *reinterpret_cast<const float4*>(v + c);
+    st4<TD>(qu + r * ldo + c, make_float4(x.x + bu.x, x.y + bu.y, x.z + bu.z, x.w + bu.w));
+    st4<TD>(qv + r * ldo + c, make_float4(x.x + bv.x, x.y + bv.y, x.z + bv.z, x.w + bv.w));
+}
+
+// dq = dqu + dqv ; du += colsum(dqu) ; dv += colsum(dqv)
+template <typename TD>
+__global__ void __launch_bounds__(256) pos_bias_bwd_kernel(const TD* __restrict__ dqu, const TD* __restrict__ dqv, long ldi,
+                                                           TD* __restrict__ dq, long ldq, float* __restrict__ du,
+                                                           float* __restrict__ dv, int rows, int d) {
+    __shared__ float4 red[2][4][64];
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    const int c = (blockIdx.x * 64 + tx) * 4;
+    const int r0 = blockIdx.y * 64, r1 = min(rows, r0 + 64);
+    float4 au = make_float4(0, 0, 0, 0), av = make_float4(0, 0, 0, 0);
+    if (c < d) {
+        for (int r = r0 + ty; r < r1; r += 4) {
+            const float4 a = ld4<TD>(dqu + (long)r * ldi + c), b = ld4<TD>(dqv + (long)r * ldi + c);
+            st4<TD>(dq + (long)r * ldq + c, make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w));
+            au.x += a.x; au.y += a.y; au.z += a.z; au.w += a.w;
+            av.x += b.x; av.y += b.y; av.z += b.z; av.w += b.w;
+        }
+    }
+    red[0][ty][tx] = au;
+    red[1][ty][tx] = av;
+    __syncthreads();
+    if (ty == 0 && c < d) {
+        float4 t = red[0][0][tx], s = red[1][0][tx];
+#pragma unroll
+        for (int w = 1; w < 4; ++w) {
+            t.x += red[0][w][tx].x; t.y += red[0][w][tx].y; t.z += red[0][w][tx].z; t.w += red[0][w][tx].w;
+            s.x += red[1][w][tx].x; s.y += red[1][w][tx].y; s.z += red[1][w][tx].z; s.w += red[1][w][tx].w;
+        }
+        atomicAdd(du + c, t.x); atomicAdd(du + c + 1, t.y); atomicAdd(du + c + 2, t.z); atomicAdd(du + c + 3, t.w);
+        atomicAdd(dv + c, s.x); atomicAdd(dv + c + 1, s.y); atomicAdd(dv + c + 2, s.z); atomicAdd(dv + c + 3, s.w);
+    }
+}
+
+// ------------------------------------------------------------------ decoder embedding + PE
+// token(b,l) = sos if l == 0 else (ys[b,l-1] == -1 ? eos : ys[b,l-1])      (models/u2.py:346-353)
+__device__ __forceinline__ long dec_token(const int64_t* ys, int lmax, int b, int l, int sos_eos) {
+    if (l == 0) return sos_eos;
+    const long y = ys[(long)b * lmax + l - 1];
+    return y < 0 ? sos_eos : y;
+}
+__global__ void __launch_bounds__(256) embed_fwd_kernel(const int64_t* __restrict__ ys, int lmax, const float* __restrict__ emb,
+                                                        const float* __restrict__ pe, float* __restrict__ out, int B, int d,
+                                                        float scale, int sos_eos) {
+    const int per_row = d >> 2, L1 = lmax + 1;
+    const long i = (long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= (long)B * L1 * per_row) return;
+    const long row = i / per_row;
+    const int c = (int)(i % per_row) * 4, b = (int)(row / L1), l = (int)(row % L1);
+    const long tok = dec_token(ys, lmax, b, l, sos_eos);
+    const float4 e = *reinterpret_cast<const float4*>(emb + tok * d + c);
+    const float4 p = *reinterpret_cast<const float4*>(pe + (long)l * d + c);
+    *reinterpret_cast<float4*>(out + row * d + c) =
+        make_float4(e.x * scale + p.x, e.y * scale + p.y, e.z * scale + p.z, e.w * scale + p.w);
+}
+__global__ void __launch_bounds__(256) embed_bwd_kernel(const int64_t* __restrict__ ys, int lmax, const float* __restrict__ dout,
+                                                        float* __restrict__ demb, int B, int d, float scale, int sos_eos) {
+    const int L1 = lmax + 1;
+    const long i = (long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= (long)B * L1 * d) return;
+    const long row = i / d;
+    const int c = (int)(i % d), b = (int)(row / L1), l = (int)(row % L1);
+    const long tok = dec_token(ys, lmax, b, l, sos_eos);
+    atomicAdd(demb + tok * d + c, scale * dout[i]);
+}
+
+}  // namespace lasr
+
+extern "C" {
+using namespace lasr;
+
+int lasr_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream) {
+    LASR_REQUIRE(src && dst && n > 0, "cast: bad args");
+    LASR_REQUIRE(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0, "cast: unaligned");
+    cast_bf16_kernel<<<ceil_div(n, 1024), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, n);
+    return check_launch("cast_f32_bf16");
+}
+
+int lasr_permute4d(const void* src, int src_dtype, void* dst, int dst_dtype, const int64_t* n, const int64_t* src_strides,
+                   const int64_t* dst_strides, int accumulate, void* stream) {
+    LASR_REQUIRE(src && dst && n && src_strides && dst_strides, "permute4d: null pointer");
+    Perm4 p;
+    long total = 1;
+    for (int i = 0; i < 4; ++i) { p.n[i] = n[i]; p.ss[i] = src_strides[i]; p.ds[i] = dst_strides[i]; total *= n[i]; }
+    LASR_REQUIRE(total > 0, "permute4d: empty");
+    int grid = ceil_div(total, 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (src_dtype == LASR_F32 && dst_dtype == LASR_F32) permute4d_kernel<float, float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, p, accumulate);
+    else if (src_dtype == LASR_F32 && dst_dtype == LASR_BF16) permute4d_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)src, (bf16*)dst, p, accumulate);
+    else if (src_dtype == LASR_BF16 && dst_dtype == LASR_F32) permute4d_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16*)src, (float*)dst, p, accumulate);
+    else permute4d_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)src, (bf16*)dst, p, accumulate);
+    return check_launch("permute4d");
+}
+
+int lasr_act_bwd(const void* da, int64_t ldda, const void* saved, int64_t lds, void* dh, int64_t lddh, float* dbias, int rows,
+                 int cols, int act, int dtype, void* stream) {
+    LASR_REQUIRE(da && rows > 0 && cols > 0 && cols % 4 == 0, "act_bwd: bad args (cols%%4==0)");
+    LASR_REQUIRE(act == LASR_ACT_NONE || saved, "act_bwd: saved tensor required");
+    LASR_REQUIRE(ldda % 4 == 0 && lds % 4 == 0 && lddh % 4 == 0, "act_bwd: strides must be multiples of 4");
+    dim3 grid(ceil_div(cols, 256), ceil_div(rows, 64));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == LASR_F32) act_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)da, ldda, (const float*)saved, lds, (float*)dh, lddh, dbias, rows, cols, act);
+    else if (dtype == LASR_BF16) act_bwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)da, ldda, (const bf16*)saved, lds, (bf16*)dh, lddh, dbias, rows, cols, act);
+    else { set_error("act_bwd: bad dtype"); return LASR_ERR_UNSUPPORTED; }
+    return check_launch("act_bwd");
+}
+
+int lasr_pos_bias_fwd(const void* q, int64_t ldq, const float* u, const float* v, void* qu, void* qv, int64_t ldo, int rows,
+                      int d, int dtype, void* stream) {
+    LASR_REQUIRE(q && u && v && qu && qv && rows > 0 && d % 4 == 0 && ldq % 4 == 0 && ldo % 4 == 0, "pos_bias_fwd: bad args");
+    const int grid = ceil_div((long)rows * (d / 4), 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == LASR_F32) pos_bias_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)q, ldq, u, v, (float*)qu, (float*)qv, ldo, rows, d);
+    else if (dtype == LASR_BF16) pos_bias_fwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)q, ldq, u, v, (bf16*)qu, (bf16*)qv, ldo, rows, d);
+    else { set_error("pos_bias_fwd: bad dtype"); return LASR_ERR_UNSUPPORTED; }
+    return check_launch("pos_bias_fwd");
+}
+
+int lasr_pos_bias_bwd(const void* dqu, const void* dqv, int64_t ldi, void* dq, int64_t ldq, float* du, float* dv, int rows, int d,
+                      int dtype, void* stream) {
+    LASR_REQUIRE(dqu && dqv && dq && du && dv && rows > 0 && d % 4 == 0 && ldi % 4 == 0 && ldq % 4 == 0, "pos_bias_bwd: bad args");
+    dim3 grid(ceil_div(d, 256), ceil_div(rows, 64));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == LASR_F32) pos_bias_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)dqu, (const float*)dqv, ldi, (float*)dq, ldq, du, dv, rows, d);
+    else if (dtype == LASR_BF16) pos_bias_bwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)dqu, (const bf16*)dqv, ldi, (bf16*)dq, ldq, du, dv, rows, d);
+    else { set_error("pos_bias_bwd: bad dtype"); return LASR_ERR_UNSUPPORTED; }
+    return check_launch("pos_bias_bwd");
+}
+
+int lasr_embed_fwd(const int64_t* ys, int lmax, const float* emb, const float* pe, float* out, int B, int d, float scale,
+                   int sos_eos, void* stream) {
+    LASR_REQUIRE(ys && emb && pe && out && B > 0 && lmax >= 0 && d % 4 == 0, "embed_fwd: bad args");
+    const long n = (long)B * (lmax + 1) * (d / 4);
+    embed_fwd_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(ys, lmax, emb, pe, out, B, d, scale, sos_eos);
+    return check_launch("embed_fwd");
+}
+
+int lasr_embed_bwd(const int64_t* ys, int lmax, const float* dout, float* demb, int B, int d, float scale, int sos_eos,
+                   void* stream) {
+    LASR_REQUIRE(ys && dout && demb && B > 0 && lmax >= 0, "embed_bwd: bad args");
+    const long n = (long)B * (lmax + 1) * d;
+    embed_bwd_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(ys, lmax, dout, demb, B, d, scale, sos_eos);
+    return check_launch("embed_bwd");
+}
+
+}  // extern "C"

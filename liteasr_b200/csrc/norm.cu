@@ -1,0 +1,207 @@
+// LayerNorm forward / backward over the last dim (replaces nets/layer_norm.py:8-29, eps = 1e-12,
+// and its autograd backward).  HBM-bound: one warp per row, the row lives in registers (float4
+// loads), fp32 statistics, two-pass variance (mean first) like ATen's kernel.
+//   fwd: y = (x - mean) * rstd * gamma + beta            (y in fp32 or bf16; mean/rstd saved)
+//   bwd: dx (+)= rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
+//        dgamma += sum_rows dy * xhat,  dbeta += sum_rows dy   (per-CTA partials -> red.add)
+// The backward's "+=" mode implements the residual-stream gradient add of the pre-norm blocks
+// (nets/conformer_layer.py:37-66) without an extra pass.
+#include "common.cuh"
+
+namespace lasr {
+
+constexpr int LN_MAXV = 8;  // float4 chunks per lane -> d <= 1024
+
+template <typename TY>
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, long ldx,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, TY* __restrict__ y, long ldy,
+                                                            float* __restrict__ mean, float* __restrict__ rstd, int rows,
+                                                            int d, float eps) {
+    const int lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float* xr = x + row * ldx;
+    const int nchunk = d >> 2;
+    float4 v[LN_MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nchunk) {
+            v[i] = *reinterpret_cast<const float4*>(xr + 4 * c);
+            s += v[i].x + v[i].y + v[i].z + v[i].w;
+        }
+    }
+    const float mu = warp_sum(s) / d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nchunk) {
+            const float a = v[i].x - mu, b = v[i].y - mu, cc = v[i].z - mu, e = v[i].w - mu;
+            q += a * a + b * b + cc * cc + e * e;
+        }
+    }
+    const float rs = rsqrtf(warp_sum(q) / d + eps);
+    if (lane == 0) {
+        if (mean) mean[row] = mu;
+        if (rstd) rstd[row] = rs;
+    }
+    TY* yr = y + row * ldy;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nchunk) {
+            const float4 g = *reinterpret_cast<const float4*>(gamma + 4 * c);
+            const float4 b = *reinterpret_cast<const float4*>(beta + 4 * c);
+            const float o0 = (v[i].x - mu) * rs * g.x + b.x, o1 = (v[i].y - mu) * rs * g.y + b.y;
+            const float o2 = (v[i].z - mu) * rs * g.z + b.z, o3 = (v[i].w - mu) * rs * g.w + b.w;
+            if constexpr (sizeof(TY) == 4) {
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(yr) + 4 * c) = make_float4(o0, o1, o2, o3);
+            } else {
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(o0, o1), h1 = __floats2bfloat162_rn(o2, o3);
+                uint2 u; u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+                *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(yr) + 4 * c) = u;
+            }
+        }
+    }
+}
+
+template <typename TD>
+__device__ __forceinline__ float4 load4(const TD* p) {
+    if constexpr (sizeof(TD) == 4) {
+        return *reinterpret_cast<const float4*>(p);
+    } else {
+        const uint2 u = *reinterpret_cast<const uint2*>(p);
+        const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x), b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+        return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+    }
+}
+
+template <typename TD>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TD* __restrict__ dy, long lddy,
+                                                            const float* __restrict__ x, long ldx,
+                                                            const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd,
+                                                            const float* __restrict__ gamma, float* __restrict__ dx,
+                                                            long lddx, int accumulate, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta, int rows, int d) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nchunk = d >> 2;
+    float4 gam[LN_MAXV], ag[LN_MAXV], abt[LN_MAXV];
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        const int c = lane + 32 * i;
+        gam[i] = (c < nchunk) ? *reinterpret_cast<const float4*>(gamma + 4 * c) : make_float4(0, 0, 0, 0);
+        ag[i] = make_float4(0, 0, 0, 0);
+        abt[i] = make_float4(0, 0, 0, 0);
+    }
+    const long nwarps = (long)gridDim.x * 8;
+    for (long row = (long)blockIdx.x * 8 + warp; row < rows; row += nwarps) {
+        const float mu = mean[row], rs = rstd[row];
+        const TD* dyr = dy + row * lddy;
+        const float* xr = x + row * ldx;
+        float4 g[LN_MAXV], xh[LN_MAXV];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < LN_MAXV; ++i) {
+            const int c = lane + 32 * i;
+            if (c < nchunk) {
+                const float4 dv = load4<TD>(dyr + 4 * c);
+                const float4 xv = *reinterpret_cast<const float4*>(xr + 4 * c);
+                xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+                g[i] = make_float4(dv.x * gam[i].x, dv.y * gam[i].y, dv.z * gam[i].z, dv.w * gam[i].w);
+                s1 += g[i].x + g[i].y + g[i].z + g[i].w;
+                s2 += g[i].x * xh[i].x + g[i].y * xh[i].y + g[i].z * xh[i].z + g[i].w * xh[i].w;
+                ag[i].x += dv.x * xh[i].x; ag[i].y += dv.y * xh[i].y; ag[i].z += dv.z * xh[i].z; ag[i].w += dv.w * xh[i].w;
+                abt[i].x += dv.x; abt[i].y += dv.y; abt[i].z += dv.z; abt[i].w += dv.w;
+            }
+        }
+        const float m1 = warp_sum(s1) / d, m2 = warp_sum(s2) / d;
+        float* dxr = dx + row * lddx;
+#pragma unroll
+        for (int i = 0; i < LN_MAXV; ++i) {
+            const int c = lane + 32 * i;
+            if (c < nchunk) {
+                float4 o = make_float4(rs * (g[i].x - m1 - xh[i].x * m2), rs * (g[i].y - m1 - xh[i].y * m2),
+                                       rs * (g[i].z - m1 - xh[i].z * m2), rs * (g[i].w - m1 - xh[i].w * m2));
+                if (accumulate) {
+                    const float4 old = *reinterpret_cast<const float4*>(dxr + 4 * c);
+                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                }
+                *reinterpret_cast<float4*>(dxr + 4 * c) = o;
+            }
+        }
+    }
+    // cross-warp reduce of the per-lane column partials, then one red.add per column per CTA
+    __shared__ float4 red[8][32];
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        const int c = lane + 32 * i;
+        if (32 * i >= nchunk) break;  // uniform
+        // dgamma
+        red[warp][lane] = ag[i];
+        __syncthreads();
+        if (warp == 0 && c < nchunk) {
+            float4 t = red[0][lane];
+#pragma unroll
+            for (int w = 1; w < 8; ++w) { t.x += red[w][lane].x; t.y += red[w][lane].y; t.z += red[w][lane].z; t.w += red[w][lane].w; }
+            atomicAdd(dgamma + 4 * c, t.x); atomicAdd(dgamma + 4 * c + 1, t.y);
+            atomicAdd(dgamma + 4 * c + 2, t.z); atomicAdd(dgamma + 4 * c + 3, t.w);
+        }
+        __syncthreads();
+        red[warp][lane] = abt[i];
+        __syncthreads();
+        if (warp == 0 && c < nchunk) {
+            float4 t = red[0][lane];
+#pragma unroll
+            for (int w = 1; w < 8; ++w) { t.x += red[w][lane].x; t.y += red[w][lane].y; t.z += red[w][lane].z; t.w += red[w][lane].w; }
+            atomicAdd(dbeta + 4 * c, t.x); atomicAdd(dbeta + 4 * c + 1, t.y);
+            atomicAdd(dbeta + 4 * c + 2, t.z); atomicAdd(dbeta + 4 * c + 3, t.w);
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace lasr
+
+extern "C" {
+
+int lasr_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, void* y, int y_dtype,
+                       int64_t ldy, float* mean, float* rstd, int rows, int d, float eps, void* stream) {
+    using namespace lasr;
+    LASR_REQUIRE(x && gamma && beta && y, "layernorm_fwd: null pointer");
+    LASR_REQUIRE(rows > 0 && d > 0 && d % 4 == 0 && d <= 128 * LN_MAXV, "layernorm_fwd: d=%d unsupported (d%%4==0, d<=1024)", d);
+    LASR_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0, "layernorm_fwd: row strides must be multiples of 4");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = ceil_div(rows, 8);
+    if (y_dtype == LASR_F32)
+        layernorm_fwd_kernel<float><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, (float*)y, ldy, mean, rstd, rows, d, eps);
+    else if (y_dtype == LASR_BF16)
+        layernorm_fwd_kernel<bf16><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, (bf16*)y, ldy, mean, rstd, rows, d, eps);
+    else { set_error("layernorm_fwd: bad dtype"); return LASR_ERR_UNSUPPORTED; }
+    return check_launch("layernorm_fwd");
+}
+
+int lasr_layernorm_bwd(const void* dy, int dy_dtype, int64_t lddy, const float* x, int64_t ldx, const float* mean,
+                       const float* rstd, const float* gamma, float* dx, int64_t lddx, int accumulate, float* dgamma,
+                       float* dbeta, int rows, int d, void* stream) {
+    using namespace lasr;
+    LASR_REQUIRE(dy && x && mean && rstd && gamma && dx && dgamma && dbeta, "layernorm_bwd: null pointer");
+    LASR_REQUIRE(rows > 0 && d > 0 && d % 4 == 0 && d <= 128 * LN_MAXV, "layernorm_bwd: d=%d unsupported", d);
+    LASR_REQUIRE(ldx % 4 == 0 && lddy % 4 == 0 && lddx % 4 == 0, "layernorm_bwd: row strides must be multiples of 4");
+    cudaStream_t st = (cudaStream_t)stream;
+    int grid = ceil_div(rows, 8);
+    if (grid > 148 * 4) grid = 148 * 4;
+    if (dy_dtype == LASR_F32)
+        layernorm_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)dy, lddy, x, ldx, mean, rstd, gamma, dx, lddx,
+                                                         accumulate, dgamma, dbeta, rows, d);
+    else if (dy_dtype == LASR_BF16)
+        layernorm_bwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)dy, lddy, x, ldx, mean, rstd, gamma, dx, lddx,
+                                                        accumulate, dgamma, dbeta, rows, d);
+    else { set_error("layernorm_bwd: bad dtype"); return LASR_ERR_UNSUPPORTED; }
+    return check_launch("layernorm_bwd");
+}
+
+}  // extern "C"

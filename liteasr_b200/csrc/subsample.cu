@@ -1,0 +1,200 @@
+// Conv2d subsampling (nets/subsampling.py:32-35,42-46) in channel-last layout.
+//   conv1: Conv2d(1 -> d, 3x3, stride 2) + ReLU, direct (K = 9, HBM-bound):  (B,T,F) -> (B,T1,F1,d)
+//   conv2: Conv2d(d -> d, 3x3, stride 2) + ReLU = GEMM over an im2col matrix (B*T2*F2, 9d) whose K index is
+//          (kh, kw, c_in); with channel-last activations every (kh, kw) patch is d contiguous elements, so
+//          im2col / col2im are pure 128-bit copy kernels and the GEMM output (B,T2,F2*d) is already the
+//          (B,T',F2*d) matrix the output Linear consumes (its weight columns are permuted once per step).
+//   backward: col2im gather fused with conv1's ReLU mask; conv1 weight/bias gradient by direct accumulation.
+#include "common.cuh"
+
+namespace lasr {
+
+// ---------------------------------------------------------------- conv1 forward
+template <typename TD>
+__global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, TD* __restrict__ h1, int T, int F,
+                                                        int T1, int F1, int d) {
+    extern __shared__ float xs[];  // 3 rows x F
+    const int b = blockIdx.y, t1 = blockIdx.x;
+    for (int i = threadIdx.x; i < 3 * F; i += blockDim.x) xs[i] = x[((long)b * T + 2 * t1) * F + i];
+    __syncthreads();
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+        float wk[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) wk[k] = w[c * 9 + k];
+        const float bc = bias[c];
+        TD* out = h1 + (((long)b * T1 + t1) * F1) * d + c;
+        for (int f = 0; f < F1; ++f) {
+            float a = bc;
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) a = fmaf(wk[kh * 3 + kw], xs[kh * F + 2 * f + kw], a);
+            out[(long)f * d] = from_f32<TD>(fmaxf(a, 0.f));
+        }
+    }
+}
+
+// ---------------------------------------------------------------- conv1 backward (weights only; the input is data)
+template <typename TD>
+__global__ void __launch_bounds__(256) conv1_bwd_kernel(const float* __restrict__ x, const TD* __restrict__ dh1,
+                                                        float* __restrict__ dw, float* __restrict__ dbias, int T, int F, int T1,
+                                                        int F1, int d, int rows_per_cta, long total_rows) {
+    extern __shared__ float xs[];  // 3 rows x F
+    const long r0 = (long)blockIdx.x * rows_per_cta, r1 = min(total_rows, r0 + rows_per_cta);
+    // each thread owns channels c, c + blockDim, ... (at most 4 supported: d <= 1024)
+    float acc[4][10];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < 10; ++k) acc[j][k] = 0.f;
+    for (long r = r0; r < r1; ++r) {
+        const int b = (int)(r / T1), t1 = (int)(r % T1);
+        __syncthreads();
+        for (int i = threadIdx.x; i < 3 * F; i += blockDim.x) xs[i] = x[((long)b * T + 2 * t1) * F + i];
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = threadIdx.x + j * blockDim.x;
+            if (c < d) {
+                const TD* g = dh1 + (r * F1) * d + c;
+                for (int f = 0; f < F1; ++f) {
+                    const float gv = to_f32<TD>(g[(long)f * d]);
+#pragma unroll
+                    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                        for (int kw = 0; kw < 3; ++kw) acc[j][kh * 3 + kw] = fmaf(gv, xs[kh * F + 2 * f + kw], acc[j][kh * 3 + kw]);
+                    acc[j][9] += gv;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = threadIdx.x + j * blockDim.x;
+        if (c < d) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) atomicAdd(dw + c * 9 + k, acc[j][k]);
+            atomicAdd(dbias + c, acc[j][9]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- im2col (stride 2, 3x3), 16-byte vectors
+template <typename TD>
+__global__ void __launch_bounds__(256) im2col_kernel(const TD* __restrict__ h1, TD* __restrict__ col, int B, int T1, int F1,
+                                                     int T2, int F2, int d) {
+    constexpr int VEC = 16 / sizeof(TD);
+    const int vpp = d / VEC;  // vectors per patch
+    const long total = (long)B * T2 * F2 * 9 * vpp;
+    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+        long r = i;
+        const int v = (int)(r % vpp); r /= vpp;
+        const int kk = (int)(r % 9); r /= 9;
+        const int f2 = (int)(r % F2); r /= F2;
+        const int t2 = (int)(r % T2); r /= T2;
+        const int b = (int)r;
+        const int kh = kk / 3, kw = kk % 3;
+        const uint4 val = *reinterpret_cast<const uint4*>(h1 + ((((long)b * T1 + 2 * t2 + kh) * F1 + 2 * f2 + kw) * d) + v * VEC);
+        *reinterpret_cast<uint4*>(col + i * VEC) = val;
+    }
+}
+
+// ---------------------------------------------------------------- col2im gather + ReLU mask of conv1's output
+template <typename TD>
+__global__ void __launch_bounds__(256) col2im_relu_kernel(const TD* __restrict__ dcol, const TD* __restrict__ h1,
+                                                          TD* __restrict__ dh1, int B, int T1, int F1, int T2, int F2, int d) {
+    const int vpp = d / 4;
+    const long total = (long)B * T1 * F1 * vpp;
+    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+        long r = i;
+        const int v = (int)(r % vpp); r /= vpp;
+        const int f1 = (int)(r % F1); r /= F1;
+        const int t1 = (int)(r % T1); r /= T1;
+        const int b = (int)r;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            const int tn = t1 - kh;
+            if (tn < 0 || (tn & 1) || (tn >> 1) >= T2) continue;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int fn = f1 - kw;
+                if (fn < 0 || (fn & 1) || (fn >> 1) >= F2) continue;
+                const long row = ((long)b * T2 + (tn >> 1)) * F2 + (fn >> 1);
+                const TD* p = dcol + row * 9 * d + (kh * 3 + kw) * d + v * 4;
+                if constexpr (sizeof(TD) == 4) {
+                    const float4 q = *reinterpret_cast<const float4*>(p);
+                    a0 += q.x; a1 += q.y; a2 += q.z; a3 += q.w;
+                } else {
+                    const uint2 u = *reinterpret_cast<const uint2*>(p);
+                    const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&u.x), hi = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+                    a0 += __low2float(lo); a1 += __high2float(lo); a2 += __low2float(hi); a3 += __high2float(hi);
+                }
+            }
+        }
+        const long off = i * 4;
+        const float m0 = to_f32<TD>(h1[off]) > 0.f, m1 = to_f32<TD>(h1[off + 1]) > 0.f;
+        const float m2 = to_f32<TD>(h1[off + 2]) > 0.f, m3 = to_f32<TD>(h1[off + 3]) > 0.f;
+        dh1[off] = from_f32<TD>(a0 * m0); dh1[off + 1] = from_f32<TD>(a1 * m1);
+        dh1[off + 2] = from_f32<TD>(a2 * m2); dh1[off + 3] = from_f32<TD>(a3 * m3);
+    }
+}
+
+}  // namespace lasr
+
+extern "C" {
+using namespace lasr;
+
+int lasr_conv1_fwd(const float* x, const float* w, const float* bias, void* h1, int dtype, int B, int T, int F, int d, void* stream) {
+    LASR_REQUIRE(x && w && bias && h1 && B > 0 && T >= 3 && F >= 3 && d > 0, "conv1_fwd: bad args");
+    const int T1 = (T - 3) / 2 + 1, F1 = (F - 3) / 2 + 1;
+    dim3 grid(T1, B);
+    const size_t smem = 3 * F * sizeof(float);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == LASR_F32) conv1_fwd_kernel<float><<<grid, 256, smem, st>>>(x, w, bias, (float*)h1, T, F, T1, F1, d);
+    else if (dtype == LASR_BF16) conv1_fwd_kernel<bf16><<<grid, 256, smem, st>>>(x, w, bias, (bf16*)h1, T, F, T1, F1, d);
+    else { set_error("conv1_fwd: bad dtype"); return LASR_ERR_UNSUPPORTED; }
+    return check_launch("conv1_fwd");
+}
+
+int lasr_conv1_bwd(const float* x, const void* dh1, int dtype, float* dw, float* dbias, int B, int T, int F, int d, void* stream) {
+    LASR_REQUIRE(x && dh1 && dw && dbias && B > 0 && T >= 3 && F >= 3 && d > 0 && d <= 1024, "conv1_bwd: bad args");
+    const int T1 = (T - 3) / 2 + 1, F1 = (F - 3) / 2 + 1;
+    const long rows = (long)B * T1;
+    const int rpc = 16;
+    const size_t smem = 3 * F * sizeof(float);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == LASR_F32) conv1_bwd_kernel<float><<<ceil_div(rows, rpc), 256, smem, st>>>(x, (const float*)dh1, dw, dbias, T, F, T1, F1, d, rpc, rows);
+    else if (dtype == LASR_BF16) conv1_bwd_kernel<bf16><<<ceil_div(rows, rpc), 256, smem, st>>>(x, (const bf16*)dh1, dw, dbias, T, F, T1, F1, d, rpc, rows);
+    else { set_error("conv1_bwd: bad dtype"); return LASR_ERR_UNSUPPORTED; }
+    return check_launch("conv1_bwd");
+}
+
+int lasr_im2col_s2(const void* h1, void* col, int dtype, int B, int T1, int F1, int d, void* stream) {
+    LASR_REQUIRE(h1 && col && B > 0 && T1 >= 3 && F1 >= 3 && d % 8 == 0, "im2col: bad args (d%%8==0)");
+    const int T2 = (T1 - 3) / 2 + 1, F2 = (F1 - 3) / 2 + 1;
+    const long total = (long)B * T2 * F2 * 9 * (dtype == LASR_F32 ? d / 4 : d / 8);
+    int grid = ceil_div(total, 256);
+    if (grid > 148 * 32) grid = 148 * 32;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == LASR_F32) im2col_kernel<float><<<grid, 256, 0, st>>>((const float*)h1, (float*)col, B, T1, F1, T2, F2, d);
+    else if (dtype == LASR_BF16) im2col_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)h1, (bf16*)col, B, T1, F1, T2, F2, d);
+    else { set_error("im2col: bad dtype"); return LASR_ERR_UNSUPPORTED; }
+    return check_launch("im2col");
+}
+
+int lasr_col2im_s2_relu(const void* dcol, const void* h1, void* dh1, int dtype, int B, int T1, int F1, int d, void* stream) {
+    LASR_REQUIRE(dcol && h1 && dh1 && B > 0 && T1 >= 3 && F1 >= 3 && d % 4 == 0, "col2im: bad args");
+    const int T2 = (T1 - 3) / 2 + 1, F2 = (F1 - 3) / 2 + 1;
+    const long total = (long)B * T1 * F1 * (d / 4);
+    int grid = ceil_div(total, 256);
+    if (grid > 148 * 32) grid = 148 * 32;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == LASR_F32) col2im_relu_kernel<float><<<grid, 256, 0, st>>>((const float*)dcol, (const float*)h1, (float*)dh1, B, T1, F1, T2, F2, d);
+    else if (dtype == LASR_BF16) col2im_relu_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)dcol, (const bf16*)h1, (bf16*)dh1, B, T1, F1, T2, F2, d);
+    else { set_error("col2im: bad dtype"); return LASR_ERR_UNSUPPORTED; }
+    return check_launch("col2im");
+}
+
+}  // extern "C"

@@ -1,0 +1,136 @@
+"""GPU: fused CTC fwd+bwd (lasr_ctc_fwdbwd) vs the float64 oracle composed with log-softmax backward,
+and vs the torch.nn.CTCLoss known answers in tests/golden/ctc_golden.json."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def oracle_grad(logits64, targets, in_len, tgt_len):
+    from oracle import u2_oracle as O
+    lp = torch.log_softmax(logits64, -1).numpy()
+    nll, dlp = O.ctc_alpha_beta_c(lp, np.clip(targets.numpy(), 0, None), in_len.numpy(), tgt_len.numpy())
+    d = np.nan_to_num(dlp, nan=0.0)
+    dl = d - np.exp(lp) * d.sum(-1, keepdims=True)
+    return nll, dl
+
+
+def make_case(T, B, V, L, seed, repeat=False):
+    g = torch.Generator().manual_seed(seed)
+    logits = torch.randn(T, B, V, generator=g, dtype=torch.float64)
+    in_len = torch.randint(int(0.6 * T), T + 1, (B,), generator=g)
+    in_len[0] = T
+    tgt_len = torch.randint(max(1, L // 2), L + 1, (B,), generator=g)
+    tgt_len[0] = L
+    tgt_len = torch.minimum(tgt_len, in_len // 2)
+    targets = torch.randint(1, V, (B, L), generator=g)
+    if repeat:
+        targets[:, 1::2] = targets[:, 0::2][:, : targets[:, 1::2].shape[1]]  # force repeated labels
+        tgt_len = torch.minimum(tgt_len, in_len // 3)
+    return logits, targets, in_len, tgt_len
+
+
+@pytest.mark.parametrize("T,B,V,L,repeat", [(50, 4, 20, 5, False), (200, 64, 500, 20, False), (123, 9, 4233, 40, True),
+                                             (400, 16, 1000, 50, True), (300, 8, 5000, 100, False), (97, 5, 8200, 12, False)])
+def test_ctc_matches_oracle_fp32(T, B, V, L, repeat):
+    from liteasr_b200 import ops
+    logits, targets, in_len, tgt_len = make_case(T, B, V, L, seed=T + V, repeat=repeat)
+    nll_ref, g_ref = oracle_grad(logits, targets, in_len, tgt_len)
+    x = logits.float().cuda()
+    nll, grad = ops.ctc_fwdbwd(x, targets.cuda(), in_len.cuda(), tgt_len.cuda(), time_major=True, grad_scale=1.0)
+    torch.cuda.synchronize()
+    # tolerance: fp32 log-space recursion vs float64 oracle -- loss rel 1e-5, grad abs 2e-5
+    nerr = np.abs(nll.cpu().numpy() - nll_ref).max()
+    gerr = np.abs(grad.cpu().double().numpy() - g_ref).max()
+    print(f"ctc T={T} B={B} V={V} L={L}: nll abs err {nerr:.3e} (nll~{np.abs(nll_ref).max():.1f}), grad abs err {gerr:.3e}")
+    # Stated fp32 tolerance (north_star): loss rel 1e-5; gradient abs 3e-4.  The lattice runs in fp32 log
+    # space (like torch's fp32 CTC): each of the T sequential log-sum-exps rounds at ulp(|alpha~|), so the
+    # occupancy error grows ~ sqrt(T) * ulp; the blank-normalised recursion keeps |alpha~| ~ 1e2 instead of
+    # T*log(V) ~ 1e4, i.e. ~10x tighter than the raw recursion.
+    assert np.allclose(nll.cpu().numpy(), nll_ref, rtol=1e-5, atol=1e-4), nerr
+    assert gerr <= 3e-4, gerr
+
+
+def test_ctc_batch_major_padded_and_scaled():
+    """(B,T,V) view of a padded buffer (the in-model layout), grad_scale and device upstream scalar."""
+    from liteasr_b200 import ops
+    T, B, V, L = 61, 6, 4233, 9
+    logits, targets, in_len, tgt_len = make_case(T, B, V, L, seed=3)
+    nll_ref, g_ref = oracle_grad(logits, targets, in_len, tgt_len)
+    Vp = 4240
+    buf = torch.zeros(B, T, Vp, device="cuda")
+    buf[..., :V] = logits.float().permute(1, 0, 2).cuda()
+    gbuf = torch.zeros(B, T, Vp, device="cuda")
+    up = torch.tensor(0.5, device="cuda")
+    nll, grad = ops.ctc_fwdbwd(buf[..., :V], targets.cuda(), in_len.cuda(), tgt_len.cuda(), time_major=False,
+                               grad=gbuf[..., :V], grad_scale=0.3 / B, upstream=up)
+    assert np.allclose(nll.cpu().numpy(), nll_ref, rtol=1e-5, atol=1e-4)
+    want = g_ref.transpose(1, 0, 2) * (0.3 / B * 0.5)
+    assert np.abs(grad.cpu().double().numpy() - want).max() <= 2e-5
+    assert (gbuf[..., V:] == 0).all()
+
+
+def test_ctc_golden_known_answers_and_edges():
+    from liteasr_b200 import ops
+    with open(os.path.join(GOLDEN, "ctc_golden.json")) as f:
+        g = json.load(f)
+    for c in g["cases"]:
+        logits = torch.tensor(c["logits"], dtype=torch.float32).cuda()
+        tg = torch.tensor(c["targets"], dtype=torch.int64).clamp(min=0).cuda()
+        il = torch.tensor(c["in_len"], dtype=torch.int64).cuda()
+        tl = torch.tensor(c["tgt_len"], dtype=torch.int64).cuda()
+        nll, grad = ops.ctc_fwdbwd(logits, tg, il, tl, time_major=True)
+        nll = nll.cpu().tolist()
+        for b, want in enumerate(c["nll"]):
+            if want == "inf":
+                assert math.isinf(nll[b]) and nll[b] > 0
+            else:
+                assert math.isclose(nll[b], want, rel_tol=2e-6, abs_tol=2e-6)
+        if c["grad_logits"] is not None:
+            fin = torch.tensor(c["finite"]).cuda()
+            want = torch.tensor(c["grad_logits"], dtype=torch.float32).cuda()
+            got = torch.where(fin.view(1, -1, 1), grad, torch.zeros_like(grad))
+            assert (got - want).abs().max().item() <= 5e-6
+            if not bool(fin.all()):  # infeasible utterances poison their own rows with NaN (zero_infinity=False)
+                bad = (~fin).nonzero().flatten().tolist()
+                for b in bad:
+                    assert torch.isnan(grad[: c["in_len"][b], b]).all()
+
+
+def test_ctc_bf16_close():
+    from liteasr_b200 import ops
+    T, B, V, L = 150, 8, 512, 20
+    logits, targets, in_len, tgt_len = make_case(T, B, V, L, seed=21)
+    xb = logits.float().cuda().bfloat16()
+    nll_ref, g_ref = oracle_grad(xb.double().cpu(), targets, in_len, tgt_len)
+    nll, grad = ops.ctc_fwdbwd(xb, targets.cuda(), in_len.cuda(), tgt_len.cuda(), time_major=True)
+    assert np.allclose(nll.cpu().numpy(), nll_ref, rtol=1e-5, atol=1e-3)
+    # bf16 output rounding: 2^-8 relative on values <= 1
+    assert np.abs(grad.float().cpu().double().numpy() - g_ref).max() <= 6e-3
+
+
+def test_ctc_full_size_properties():
+    """BASELINE config 4 largest-ish size: size-independent properties instead of an oracle run:
+    rows sum to 0 for t < in_len (softmax - occupancy), are exactly 0 beyond, nll finite and positive."""
+    from liteasr_b200 import ops
+    T, B, V, L = 1600, 64, 5000, 200
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(T, B, V, generator=g, device="cuda")
+    in_len = torch.randint(int(0.6 * T), T + 1, (B,), generator=g, device="cuda")
+    in_len[0] = T
+    tgt_len = torch.randint(L // 2, L + 1, (B,), generator=g, device="cuda")
+    targets = torch.randint(1, V, (B, L), generator=g, device="cuda")
+    nll, grad = ops.ctc_fwdbwd(x, targets, in_len, tgt_len, time_major=True)
+    assert torch.isfinite(nll).all() and (nll > 0).all()
+    live = torch.arange(T, device="cuda").view(-1, 1) < in_len.view(1, -1)
+    rs = grad.sum(-1)
+    assert rs[live].abs().max().item() < 1e-2  # 1 - sum_s occupancy; fp32 lattice over T = 1600 steps
+    assert (grad[~live] == 0).all()
+    # blank column: softmax - occupancy in [-1, 1]
+    assert grad.abs().max().item() <= 1.0 + 1e-5

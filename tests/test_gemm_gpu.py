@@ -1,0 +1,116 @@
+"""GPU: tcgen05 bf16 GEMM and SIMT fp32 GEMM through the C ABI vs a plain fp32 torch reference."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(a, b, ta, tb):
+    A = a.float().transpose(-1, -2) if ta else a.float()
+    B = b.float().transpose(-1, -2) if tb else b.float()
+    return A @ B.transpose(-1, -2)  # (M,K) @ (N,K)^T
+
+
+def _mk(rows, cols, dtype, g):
+    """(rows, cols) view of a buffer whose row stride is padded to 8 elements (TMA needs 16-byte strides)."""
+    ld = (cols + 7) // 8 * 8
+    buf = (torch.randn(rows, ld, generator=g, device="cuda") * 0.5).to(dtype)
+    return buf[:, :cols]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("m,n,k", [(128, 128, 64), (300, 200, 136), (1000, 256, 2048), (64, 520, 72), (257, 64, 256)])
+def test_gemm_plain(dtype, ta, tb, m, n, k):
+    from liteasr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(m * 7 + n * 3 + k)
+    a = _mk(k, m, dtype, g) if ta else _mk(m, k, dtype, g)
+    b = _mk(k, n, dtype, g) if tb else _mk(n, k, dtype, g)
+    c = torch.full((m, n), float("nan"), device="cuda")
+    ops.gemm(a, b, c, m, n, k, lda=a.stride(0), ldb=b.stride(0), ldc=n, ta=ta, tb=tb)
+    ref = _ref(a, b, ta, tb)
+    tol = 2e-2 if dtype == torch.bfloat16 else 1e-4
+    assert torch.isfinite(c).all()
+    err = (c - ref).abs().max().item()
+    assert err <= tol * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_gemm_epilogue_bias_act_res_aux(dtype):
+    from liteasr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    m, n, k = 333, 320, 256
+    x, w = _mk(m, k, dtype, g), _mk(n, k, dtype, g)
+    bias = torch.randn(n, generator=g, device="cuda")
+    res = torch.randn(m, n, generator=g, device="cuda")
+    for act, fn in ((ops.ACT_NONE, lambda v: v), (ops.ACT_RELU, torch.relu), (ops.ACT_SWISH, lambda v: v * torch.sigmoid(v))):
+        for cdt in ([torch.float32, torch.bfloat16] if dtype == torch.bfloat16 else [torch.float32]):
+            out = torch.empty(m, n, device="cuda", dtype=cdt)
+            aux = torch.empty(m, n, device="cuda", dtype=cdt)
+            ops.linear(x, w, out, bias=bias, res=res, aux=aux, alpha=0.5, act=act)
+            pre = x.float() @ w.float().t() + bias
+            ref = 0.5 * fn(pre) + res
+            tol = 3e-2 if (dtype == torch.bfloat16 or cdt == torch.bfloat16) else 1e-4
+            assert (out.float() - ref).abs().max().item() <= tol * ref.abs().max().item()
+            assert (aux.float() - pre).abs().max().item() <= tol * pre.abs().max().item()
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_gemm_batched_head_interleaved(dtype):
+    """Attention-style: A = Q (B,T,H,dk) per (b,h), B = K (B,T,H,dk); C (B,H,T,Tp) fp32."""
+    from liteasr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(9)
+    B, T, H, dk = 3, 77, 2, 64
+    Tp = 80
+    q = (torch.randn(B, T, H, dk, generator=g, device="cuda") * 0.3).to(dtype)
+    kk = (torch.randn(B, T, H, dk, generator=g, device="cuda") * 0.3).to(dtype)
+    c = torch.zeros(B, H, T, Tp, device="cuda")
+    d = H * dk
+    ops.gemm(q, kk, c, T, T, dk, lda=d, ldb=d, ldc=Tp, batch=(B, H), sa=(T * d, dk), sb=(T * d, dk), sc=(H * T * Tp, T * Tp))
+    ref = torch.einsum("bihd,bjhd->bhij", q.float(), kk.float())
+    tol = 2e-2 if dtype == torch.bfloat16 else 1e-4
+    assert (c[..., :T] - ref).abs().max().item() <= tol * ref.abs().max().item()
+    assert (c[..., T:] == 0).all()
+    # P.V: A = probs (B,H,T,Tp) K-major, B = V (B,T,H,dk) MN-major (rows = keys); out (B,T,H,dk)
+    probs = torch.softmax(ref, -1).to(dtype)
+    pp = torch.zeros(B, H, T, Tp, device="cuda", dtype=dtype)
+    pp[..., :T] = probs
+    v = (torch.randn(B, T, H, dk, generator=g, device="cuda") * 0.3).to(dtype)
+    o = torch.empty(B, T, H, dk, device="cuda", dtype=dtype)
+    ops.gemm(pp, v, o, T, dk, T, lda=Tp, ldb=d, ldc=d, tb=True, batch=(B, H), sa=(H * T * Tp, T * Tp), sb=(T * d, dk), sc=(T * d, dk))
+    ref_o = torch.einsum("bhij,bjhd->bihd", probs.float(), v.float())
+    assert (o.float() - ref_o).abs().max().item() <= tol * max(1.0, ref_o.abs().max().item())
+    # dV = probs^T . dO : A MN-major (rows = queries), B MN-major; broadcast operand (stride 0) + batch-reduce accumulate
+    do = (torch.randn(B, T, H, dk, generator=g, device="cuda") * 0.3).to(dtype)
+    dv = torch.empty(B, T, H, dk, device="cuda", dtype=dtype)
+    ops.gemm(pp, do, dv, T, dk, T, lda=Tp, ldb=d, ldc=d, ta=True, tb=True, batch=(B, H), sa=(H * T * Tp, T * Tp), sb=(T * d, dk), sc=(T * d, dk))
+    ref_dv = torch.einsum("bhij,bihd->bjhd", probs.float(), do.float())
+    assert (dv.float() - ref_dv).abs().max().item() <= tol * max(1.0, ref_dv.abs().max().item())
+    acc = torch.zeros(H, T, dk, device="cuda")
+    ops.gemm(pp, do, acc, T, dk, T, lda=Tp, ldb=d, ldc=dk, ta=True, tb=True, batch=(B, H), sa=(H * T * Tp, T * Tp), sb=(T * d, dk),
+             sc=(0, T * dk), accumulate=True)
+    ref_acc = torch.einsum("bhij,bihd->hjd", probs.float(), do.float())
+    assert (acc - ref_acc).abs().max().item() <= tol * max(1.0, ref_acc.abs().max().item())
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_gemm_wgrad_split_k(dtype):
+    from liteasr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(11)
+    rows, n, k = 3001, 256, 520
+    dy, x = _mk(rows, n, dtype, g), _mk(rows, k, dtype, g)
+    dw = torch.zeros(n, k, device="cuda")
+    ops.gemm(dy, x, dw, n, k, rows, lda=dy.stride(0), ldb=x.stride(0), ldc=k, ta=True, tb=True, accumulate=True, split_k=5, alpha=2.0)
+    ref = 2.0 * dy.float().t() @ x.float()
+    tol = 2e-2 if dtype == torch.bfloat16 else 2e-4
+    assert (dw - ref).abs().max().item() <= tol * ref.abs().max().item()
+
+
+def test_gemm_bad_args_raise():
+    from liteasr_b200 import ops
+    a = torch.zeros(8, 8, device="cuda", dtype=torch.bfloat16)
+    c = torch.zeros(8, 8, device="cuda")
+    with pytest.raises(RuntimeError):
+        ops.gemm(a, a, c, 8, 8, 8, lda=8, ldb=8, ldc=8, split_k=2)  # split_k without accumulate
+    with pytest.raises(RuntimeError):
+        ops.gemm(a, a, c, 8, 8, 8, lda=9, ldb=8, ldc=8)  # unaligned TMA stride
