@@ -117,11 +117,11 @@ int lasr_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
 int lasr_permute4d(const void* src, int src_dtype, void* dst, int dst_dtype, const int64_t* n, const int64_t* src_strides,
                    const int64_t* dst_strides, int accumulate, void* stream);
 
-/* dh = da * act'(saved) (saved = pre-activation for swish, activation output for relu), dbias += colsum(dh).
+/* dh = scale * da * act'(saved) (saved = pre-activation for swish, activation output for relu), dbias += colsum(dh).
  * Backward of the fused bias+activation GEMM epilogue (nets/feed_forward.py:18-19, nn.Linear biases).
  * dh may be NULL for act = none (bias gradient only). */
 int lasr_act_bwd(const void* da, int64_t ldda, const void* saved, int64_t lds, void* dh, int64_t lddh, float* dbias, int rows,
-                 int cols, int act, int dtype, void* stream);
+                 int cols, int act, float scale, int dtype, void* stream);
 
 /* q + pos_bias_u, q + pos_bias_v (nets/attention.py:135-139) and the backward
  * (dq = dqu + dqv, du += colsum(dqu), dv += colsum(dqv)). */
@@ -130,12 +130,14 @@ int lasr_pos_bias_fwd(const void* q, int64_t ldq, const float* u, const float* v
 int lasr_pos_bias_bwd(const void* dqu, const void* dqv, int64_t ldi, void* dq, int64_t ldq, float* du, float* dv, int rows, int d,
                       int dtype, void* stream);
 
-/* Decoder input embedding: out[b,l] = emb[token(b,l)] * scale + pe[l], token = sos for l = 0 else ys[b,l-1]
- * with -1 -> eos (models/u2.py:346-353, nets/transformer_decoder.py:77-78); backward scatter-adds into demb. */
-int lasr_embed_fwd(const int64_t* ys, int lmax, const float* emb, const float* pe, float* out, int B, int d, float scale,
-                   int sos_eos, void* stream);
-int lasr_embed_bwd(const int64_t* ys, int lmax, const float* dout, float* demb, int B, int d, float scale, int sos_eos,
+/* Decoder input embedding: out[b,l] = emb[tokens[b,l]] * scale + pe[l] (nets/transformer_decoder.py:77-78,
+ * nets/positional_encoding.py:49-56); backward scatter-adds scale*dout into demb (red.add). */
+int lasr_embed_fwd(const int64_t* tokens, int L, const float* emb, const float* pe, float* out, int B, int d, float scale,
                    void* stream);
+int lasr_embed_bwd(const int64_t* tokens, const float* dout, float* demb, int64_t rows, int d, float scale, void* stream);
+
+/* x[i] *= *scalar (device scalar): applies autograd's upstream gradient to a loss-gradient buffer without a host sync. */
+int lasr_scale_by_scalar(void* x, int dtype, int64_t n, const float* scalar, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Conformer convolution-module middle: GLU -> depthwise Conv1d(k=15,pad 7) -> BatchNorm1d -> Swish

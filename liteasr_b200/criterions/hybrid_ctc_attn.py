@@ -1,0 +1,58 @@
+"""Hybrid CTC / attention criterion -- the reference's ``criterions/hybrid_ctc_attn.py`` on sm_100a.
+
+``loss = w * CTC(sum)/B + (1-w) * label-smoothed-KL(sum over non-pad tokens)/B`` (:49-78; both terms divided by the BATCH
+size, ``normalize_length`` is dead config there too, quirk Q6).  With a ``liteasr_b200`` U2 the whole step is one fused
+autograd node (``HybridLossFn``); with any other model that returns ``(h_attn, h_ctc)`` logits the two loss kernels are
+applied to the logits it produced.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Optional
+
+import torch
+
+from .. import functions as F
+from ..config import MISSING, LiteasrDataclass
+from . import LiteasrLoss, register_criterion
+
+
+@dataclass
+class HybridCTCLossConfig(LiteasrDataclass):
+    name: Optional[str] = field(default="hybrid_ctc")
+    vocab_size: int = field(default=MISSING)
+    padding_idx: int = field(default=-1)
+    smoothing: float = field(default=0.0)
+    normalize_length: bool = field(default=False)
+    ctc_weight: float = field(default=0.0)
+
+
+@register_criterion("hybrid_ctc", dataclass=HybridCTCLossConfig)
+class HybridCTCLoss(LiteasrLoss):
+    def __init__(self, cfg: HybridCTCLossConfig, task=None):
+        super().__init__(cfg)
+
+    @classmethod
+    def build_criterion(cls, cfg, task):
+        cfg.vocab_size = task.vocab_size
+        return cls(cfg, task)
+
+    def __call__(self, model, xs, xlens, ys, ylens):
+        inner = getattr(model, "module", model)  # DDP / DDPModelWrapper forward attributes through .module
+        inner = getattr(inner, "module", inner)
+        from ..models.u2 import U2
+        if isinstance(inner, U2) and self.cfg.padding_idx == inner.ignore:
+            st, _, _ = F.bind(inner, xs.device)
+            params = [p for _, p in st.named]
+            return F.HybridLossFn.apply(inner, float(self.cfg.ctc_weight), float(self.cfg.smoothing), xs, xlens, ys, ylens,
+                                        st.anchor, *params)
+        # generic path: any model honouring the LiteasrModel contract
+        h_attn, h_ctc = model(xs, xlens, ys, ylens)
+        return self.loss_from_logits(inner, h_attn, h_ctc, xlens, ys, ylens)
+
+    def loss_from_logits(self, model, h_attn, h_ctc, xlens, ys, ylens):
+        b = ys.size(0)
+        row_kl = F.LabelSmoothingFn.apply(h_attn, ys, ylens, float(self.cfg.smoothing))
+        nll = F.CTCLossFn.apply(h_ctc, ys, model.get_pred_len(xlens), ylens, 0)
+        w = self.cfg.ctc_weight
+        return w * (nll.sum() / b) + (1 - w) * (row_kl.sum() / b)

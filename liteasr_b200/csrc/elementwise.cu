@@ -64,34 +64,58 @@ __global__ void __launch_bounds__(256) permute4d_kernel(const TS* __restrict__ s
 template <typename TD>
 __global__ void __launch_bounds__(256) act_bwd_kernel(const TD* __restrict__ da, long ldda, const TD* __restrict__ saved,
                                                       long lds, TD* __restrict__ dh, long lddh,
-                                                      float* __restrict__ dbias, int rows, int cols, int act) {
+                                                      float* __restrict__ dbias, int rows, int cols, int act, float scale) {
     __shared__ float4 red[4][64];
     const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
     const int c = (blockIdx.x * 64 + tx) * 4;
     const int r0 = blockIdx.y * 64, r1 = min(rows, r0 + 64);
-    float4 acc = make_float4(0, 0, 0, 0);
+    const bool full = c + 3 < cols;  // ragged tail (cols % 4 != 0, e.g. V = 4233) goes element-wise
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
     if (c < cols) {
         for (int r = r0 + ty; r < r1; r += 4) {
-            float4 g = ld4<TD>(da + (long)r * ldda + c);
-            if (act == LASR_ACT_SWISH) {
-                const float4 h = ld4<TD>(saved + (long)r * lds + c);
-                g.x *= dswishf_(h.x); g.y *= dswishf_(h.y); g.z *= dswishf_(h.z); g.w *= dswishf_(h.w);
-            } else if (act == LASR_ACT_RELU) {
-                const float4 a = ld4<TD>(saved + (long)r * lds + c);
-                g.x = a.x > 0.f ? g.x : 0.f; g.y = a.y > 0.f ? g.y : 0.f; g.z = a.z > 0.f ? g.z : 0.f; g.w = a.w > 0.f ? g.w : 0.f;
+            float g[4], sv[4] = {0.f, 0.f, 0.f, 0.f};
+            if (full) {
+                const float4 t = ld4<TD>(da + (long)r * ldda + c);
+                g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w;
+                if (act != LASR_ACT_NONE) {
+                    const float4 u = ld4<TD>(saved + (long)r * lds + c);
+                    sv[0] = u.x; sv[1] = u.y; sv[2] = u.z; sv[3] = u.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    g[j] = (c + j < cols) ? to_f32<TD>(da[(long)r * ldda + c + j]) : 0.f;
+                    if (act != LASR_ACT_NONE && c + j < cols) sv[j] = to_f32<TD>(saved[(long)r * lds + c + j]);
+                }
             }
-            if (dh) st4<TD>(dh + (long)r * lddh + c, g);
-            acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                g[j] *= scale;
+                if (act == LASR_ACT_SWISH) g[j] *= dswishf_(sv[j]);
+                else if (act == LASR_ACT_RELU) g[j] = sv[j] > 0.f ? g[j] : 0.f;
+                acc[j] += g[j];
+            }
+            if (dh) {
+                if (full) st4<TD>(dh + (long)r * lddh + c, make_float4(g[0], g[1], g[2], g[3]));
+                else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (c + j < cols) dh[(long)r * lddh + c + j] = from_f32<TD>(g[j]);
+                }
+            }
         }
     }
     if (!dbias) return;
-    red[ty][tx] = acc;
+    red[ty][tx] = make_float4(acc[0], acc[1], acc[2], acc[3]);
     __syncthreads();
     if (ty == 0 && c < cols) {
         float4 t = red[0][tx];
 #pragma unroll
         for (int w = 1; w < 4; ++w) { t.x += red[w][tx].x; t.y += red[w][tx].y; t.z += red[w][tx].z; t.w += red[w][tx].w; }
-        atomicAdd(dbias + c, t.x); atomicAdd(dbias + c + 1, t.y); atomicAdd(dbias + c + 2, t.z); atomicAdd(dbias + c + 3, t.w);
+        atomicAdd(dbias + c, t.x);
+        if (c + 1 < cols) atomicAdd(dbias + c + 1, t.y);
+        if (c + 2 < cols) atomicAdd(dbias + c + 2, t.z);
+        if (c + 3 < cols) atomicAdd(dbias + c + 3, t.w);
     }
 }
 
@@ -145,35 +169,35 @@ __global__ void __launch_bounds__(256) pos_bias_bwd_kernel(const TD* __restrict_
 }
 
 // ------------------------------------------------------------------ decoder embedding + PE
-// token(b,l) = sos if l == 0 else (ys[b,l-1] == -1 ? eos : ys[b,l-1])      (models/u2.py:346-353)
-__device__ __forceinline__ long dec_token(const int64_t* ys, int lmax, int b, int l, int sos_eos) {
-    if (l == 0) return sos_eos;
-    const long y = ys[(long)b * lmax + l - 1];
-    return y < 0 ? sos_eos : y;
-}
-__global__ void __launch_bounds__(256) embed_fwd_kernel(const int64_t* __restrict__ ys, int lmax, const float* __restrict__ emb,
+// out[b,l] = emb[tokens[b,l]] * scale + pe[l]   (nets/transformer_decoder.py:77-78, positional_encoding.py:49-56)
+__global__ void __launch_bounds__(256) embed_fwd_kernel(const int64_t* __restrict__ tokens, int L, const float* __restrict__ emb,
                                                         const float* __restrict__ pe, float* __restrict__ out, int B, int d,
-                                                        float scale, int sos_eos) {
-    const int per_row = d >> 2, L1 = lmax + 1;
+                                                        float scale) {
+    const int per_row = d >> 2;
     const long i = (long)blockIdx.x * 256 + threadIdx.x;
-    if (i >= (long)B * L1 * per_row) return;
+    if (i >= (long)B * L * per_row) return;
     const long row = i / per_row;
-    const int c = (int)(i % per_row) * 4, b = (int)(row / L1), l = (int)(row % L1);
-    const long tok = dec_token(ys, lmax, b, l, sos_eos);
+    const int c = (int)(i % per_row) * 4, l = (int)(row % L);
+    const long tok = tokens[row];
     const float4 e = *reinterpret_cast<const float4*>(emb + tok * d + c);
     const float4 p = *reinterpret_cast<const float4*>(pe + (long)l * d + c);
     *reinterpret_cast<float4*>(out + row * d + c) =
         make_float4(e.x * scale + p.x, e.y * scale + p.y, e.z * scale + p.z, e.w * scale + p.w);
 }
-__global__ void __launch_bounds__(256) embed_bwd_kernel(const int64_t* __restrict__ ys, int lmax, const float* __restrict__ dout,
-                                                        float* __restrict__ demb, int B, int d, float scale, int sos_eos) {
-    const int L1 = lmax + 1;
+__global__ void __launch_bounds__(256) embed_bwd_kernel(const int64_t* __restrict__ tokens, const float* __restrict__ dout,
+                                                        float* __restrict__ demb, long rows, int d, float scale) {
     const long i = (long)blockIdx.x * 256 + threadIdx.x;
-    if (i >= (long)B * L1 * d) return;
+    if (i >= rows * d) return;
     const long row = i / d;
-    const int c = (int)(i % d), b = (int)(row / L1), l = (int)(row % L1);
-    const long tok = dec_token(ys, lmax, b, l, sos_eos);
-    atomicAdd(demb + tok * d + c, scale * dout[i]);
+    const int c = (int)(i % d);
+    atomicAdd(demb + tokens[row] * d + c, scale * dout[i]);
+}
+
+// x[i] *= *scalar   (autograd's upstream gradient applied to a loss-gradient buffer without a host sync)
+template <typename TD>
+__global__ void __launch_bounds__(256) scale_by_scalar_kernel(TD* __restrict__ x, long n, const float* __restrict__ scalar) {
+    const float s = __ldg(scalar);
+    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long)gridDim.x * 256) x[i] = from_f32<TD>(to_f32<TD>(x[i]) * s);
 }
 
 }  // namespace lasr
@@ -206,14 +230,14 @@ int lasr_permute4d(const void* src, int src_dtype, void* dst, int dst_dtype, con
 }
 
 int lasr_act_bwd(const void* da, int64_t ldda, const void* saved, int64_t lds, void* dh, int64_t lddh, float* dbias, int rows,
-                 int cols, int act, int dtype, void* stream) {
-    LASR_REQUIRE(da && rows > 0 && cols > 0 && cols % 4 == 0, "act_bwd: bad args (cols%%4==0)");
+                 int cols, int act, float scale, int dtype, void* stream) {
+    LASR_REQUIRE(da && rows > 0 && cols > 0, "act_bwd: bad args");
     LASR_REQUIRE(act == LASR_ACT_NONE || saved, "act_bwd: saved tensor required");
     LASR_REQUIRE(ldda % 4 == 0 && lds % 4 == 0 && lddh % 4 == 0, "act_bwd: strides must be multiples of 4");
     dim3 grid(ceil_div(cols, 256), ceil_div(rows, 64));
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == LASR_F32) act_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)da, ldda, (const float*)saved, lds, (float*)dh, lddh, dbias, rows, cols, act);
-    else if (dtype == LASR_BF16) act_bwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)da, ldda, (const bf16*)saved, lds, (bf16*)dh, lddh, dbias, rows, cols, act);
+    if (dtype == LASR_F32) act_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)da, ldda, (const float*)saved, lds, (float*)dh, lddh, dbias, rows, cols, act, scale);
+    else if (dtype == LASR_BF16) act_bwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)da, ldda, (const bf16*)saved, lds, (bf16*)dh, lddh, dbias, rows, cols, act, scale);
     else { set_error("act_bwd: bad dtype"); return LASR_ERR_UNSUPPORTED; }
     return check_launch("act_bwd");
 }
@@ -240,20 +264,28 @@ int lasr_pos_bias_bwd(const void* dqu, const void* dqv, int64_t ldi, void* dq, i
     return check_launch("pos_bias_bwd");
 }
 
-int lasr_embed_fwd(const int64_t* ys, int lmax, const float* emb, const float* pe, float* out, int B, int d, float scale,
-                   int sos_eos, void* stream) {
-    LASR_REQUIRE(ys && emb && pe && out && B > 0 && lmax >= 0 && d % 4 == 0, "embed_fwd: bad args");
-    const long n = (long)B * (lmax + 1) * (d / 4);
-    embed_fwd_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(ys, lmax, emb, pe, out, B, d, scale, sos_eos);
+int lasr_embed_fwd(const int64_t* tokens, int L, const float* emb, const float* pe, float* out, int B, int d, float scale,
+                   void* stream) {
+    LASR_REQUIRE(tokens && emb && pe && out && B > 0 && L > 0 && d % 4 == 0, "embed_fwd: bad args");
+    const long n = (long)B * L * (d / 4);
+    embed_fwd_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(tokens, L, emb, pe, out, B, d, scale);
     return check_launch("embed_fwd");
 }
 
-int lasr_embed_bwd(const int64_t* ys, int lmax, const float* dout, float* demb, int B, int d, float scale, int sos_eos,
-                   void* stream) {
-    LASR_REQUIRE(ys && dout && demb && B > 0 && lmax >= 0, "embed_bwd: bad args");
-    const long n = (long)B * (lmax + 1) * d;
-    embed_bwd_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(ys, lmax, dout, demb, B, d, scale, sos_eos);
+int lasr_embed_bwd(const int64_t* tokens, const float* dout, float* demb, int64_t rows, int d, float scale, void* stream) {
+    LASR_REQUIRE(tokens && dout && demb && rows > 0 && d > 0, "embed_bwd: bad args");
+    embed_bwd_kernel<<<ceil_div(rows * d, 256), 256, 0, (cudaStream_t)stream>>>(tokens, dout, demb, rows, d, scale);
     return check_launch("embed_bwd");
+}
+
+int lasr_scale_by_scalar(void* x, int dtype, int64_t n, const float* scalar, void* stream) {
+    LASR_REQUIRE(x && scalar && n > 0, "scale_by_scalar: bad args");
+    int grid = ceil_div(n, 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    if (dtype == LASR_F32) scale_by_scalar_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((float*)x, n, scalar);
+    else if (dtype == LASR_BF16) scale_by_scalar_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((bf16*)x, n, scalar);
+    else { set_error("scale_by_scalar: bad dtype"); return LASR_ERR_UNSUPPORTED; }
+    return check_launch("scale_by_scalar");
 }
 
 }  // extern "C"

@@ -1,0 +1,464 @@
+"""Forward / backward pipelines of the U2 hot path, written against the C ABI (``ops``) and the flat ``ParamStore``.
+
+This is the host-side schedule: which kernel runs on which buffer in which order.  Every arithmetic step is a
+``lasr_*`` kernel; torch is used for allocation (caching allocator -> CUDA-graph friendly), views and streams only.
+
+Numerics / layout decisions:
+  * residual stream and all statistics in fp32; GEMM operands in ``adt`` (bf16 on tcgen05, or fp32 on the SIMT path);
+  * activations are (rows, features) row-major with rows = (batch, time): the reference's transposes for Conv1d /
+    Conv2d / heads disappear (heads are addressed in place through the GEMM's two-level batch strides);
+  * every backward accumulates parameter gradients straight into ``store.gflat`` (split-K ``red.add`` wgrads, column-sum
+    bias gradients), so gradient accumulation and the flat all-reduce need no extra pass.
+
+Reference lines restated by each block are cited inline (paths relative to /root/reference/liteasr).
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace as NS
+from typing import Optional
+
+import torch
+
+from . import ops
+from .ops import ACT_NONE, ACT_RELU, ACT_SWISH
+from .store import ParamStore
+
+LN_EPS = 1e-12
+KW = 15
+
+
+def _ceil(a: int, b: int) -> int:
+    return (a + b - 1) // b * b
+
+
+def _empty(shape, dtype, dev):
+    return torch.empty(shape, dtype=dtype, device=dev)
+
+
+class Engine:
+    def __init__(self, store: ParamStore):
+        self.st = store
+        self.adt = store.adt
+        self.dev = store.device
+
+    # ------------------------------------------------------------------------------------------
+    # small helpers
+    # ------------------------------------------------------------------------------------------
+    def to_adt(self, x32: torch.Tensor) -> torch.Tensor:
+        """fp32 -> operand dtype copy (identity in fp32 mode)."""
+        if self.adt == torch.float32:
+            return x32
+        out = _empty(x32.shape, torch.bfloat16, self.dev)
+        ops.cast_bf16(x32.reshape(-1), out.reshape(-1))
+        return out
+
+    def layernorm(self, x: torch.Tensor, pfx: str, out_dtype) -> NS:
+        rows, d = x.shape
+        y = _empty((rows, d), out_dtype, self.dev)
+        mean = _empty((rows,), torch.float32, self.dev)
+        rstd = _empty((rows,), torch.float32, self.dev)
+        ops.layernorm_fwd(x, self.st.p(pfx + ".weight"), self.st.p(pfx + ".bias"), y, mean, rstd, LN_EPS)
+        return NS(x=x, y=y, mean=mean, rstd=rstd, pfx=pfx)
+
+    def layernorm_bwd(self, ln: NS, dy: torch.Tensor, dx: torch.Tensor, accumulate: bool) -> None:
+        ops.layernorm_bwd(dy, ln.x, ln.mean, ln.rstd, self.st.p(ln.pfx + ".weight"), dx, self.st.g(ln.pfx + ".weight"),
+                          self.st.g(ln.pfx + ".bias"), accumulate)
+
+    def _split_k(self, n_out: int, k_out: int, rows: int) -> int:
+        tiles = ((n_out + 127) // 128) * ((k_out + 127) // 128)
+        s = max(1, min(32, 148 // max(1, tiles)))
+        s = min(s, max(1, rows // 256))
+        return s
+
+    def linear(self, x, wname, out_dtype, *, bias=True, act=ACT_NONE, res=None, alpha=1.0, aux=False, w=None, n=None,
+               bias_t=None):
+        """y = alpha * act(x @ W^T + b) (+ res).  W (N,K) from the store (or ``w``)."""
+        w = self.st.w(wname + ".weight") if w is None else w
+        n = w.shape[0] if n is None else n
+        m = x.shape[0]
+        ld = _ceil(n, 8)
+        buf = _empty((m, ld), out_dtype, self.dev)
+        out = buf[:, :n] if ld != n else buf
+        auxbuf = None
+        if aux:
+            ab = _empty((m, ld), out_dtype, self.dev)
+            auxbuf = ab[:, :n] if ld != n else ab
+        b = bias_t if bias_t is not None else (self.st.p(wname + ".bias") if bias else None)
+        ops.gemm(x, w, out, m, n, x.shape[1], lda=x.stride(0), ldb=w.stride(0), ldc=ld, bias=b, res=res,
+                 ldres=(res.stride(0) if res is not None else 0), aux=auxbuf, alpha=alpha, act=act)
+        return (out, auxbuf) if aux else out
+
+    def linear_bwd(self, dy, x, wname, *, need_dx=True, dx_dtype=None, bias=True, dbias_done=False, alpha=1.0, w=None,
+                   gw=None, gb=None, dx_res=None):
+        """dW += alpha * dy^T x ; db += colsum(dy) (unless fused earlier) ; returns dx = alpha * dy @ W."""
+        w = self.st.w(wname + ".weight") if w is None else w
+        gw = self.st.gw(wname + ".weight") if gw is None else gw
+        m, n = dy.shape
+        k = x.shape[1]
+        if bias and not dbias_done:
+            ops.act_bwd(dy, None, None, self.st.g(wname + ".bias") if gb is None else gb, ACT_NONE, alpha)
+        ops.gemm(dy, x, gw, n, k, m, lda=dy.stride(0), ldb=x.stride(0), ldc=gw.stride(0), ta=True, tb=True, accumulate=True,
+                 split_k=self._split_k(n, k, m), alpha=alpha)
+        if not need_dx:
+            return None
+        dx_dtype = self.adt if dx_dtype is None else dx_dtype
+        dx = _empty((m, k), dx_dtype, self.dev) if dx_res is None else dx_res
+        ops.gemm(dy, w, dx, m, k, n, lda=dy.stride(0), ldb=w.stride(0), ldc=dx.stride(0), tb=True, alpha=alpha,
+                 res=dx_res, ldres=(dx_res.stride(0) if dx_res is not None else 0))
+        return dx
+
+    # ------------------------------------------------------------------------------------------
+    # feed-forward block   x <- x + scale * fc2(act(fc1(LN x)))      nets/feed_forward.py:18-19,
+    #                                                               nets/conformer_layer.py:37-47,58-66
+    # ------------------------------------------------------------------------------------------
+    def ffn_fwd(self, x, pfx_norm, pfx_ff, act, scale) -> NS:
+        ln = self.layernorm(x, pfx_norm, self.adt)
+        if act == ACT_SWISH:
+            a, h = self.linear(ln.y, pfx_ff + ".fc1", self.adt, act=act, aux=True)
+        else:
+            a, h = self.linear(ln.y, pfx_ff + ".fc1", self.adt, act=act), None
+        out = self.linear(a, pfx_ff + ".fc2", torch.float32, res=x, alpha=scale)
+        return NS(out=out, ln=ln, a=a, h=h, act=act, scale=scale, pfx=pfx_ff)
+
+    def ffn_bwd(self, c: NS, dres: torch.Tensor) -> None:
+        """dres (fp32, in/out): gradient wrt the block output on entry, wrt the block input on exit."""
+        dy = self.to_adt(dres)
+        da = self.linear_bwd(dy, c.a, c.pfx + ".fc2", alpha=c.scale)
+        dh = _empty(da.shape, self.adt, self.dev)
+        ops.act_bwd(da, c.h if c.act == ACT_SWISH else c.a, dh, self.st.g(c.pfx + ".fc1.bias"), c.act)
+        dln = self.linear_bwd(dh, c.ln.y, c.pfx + ".fc1", dbias_done=True)
+        self.layernorm_bwd(c.ln, dln, dres, accumulate=True)
+
+    # ------------------------------------------------------------------------------------------
+    # attention core on projected q/k/v  (nets/attention.py:46-59,61-71,120-154)
+    # q: (B*Tq, *) view with row stride ldq, k/v: (B*Tk, *) views; heads addressed via batch strides.
+    # ------------------------------------------------------------------------------------------
+    def attn_core_fwd(self, q, k, v, B, H, Tq, Tk, dk, lens, mask_mode, causal, qv=None, p=None) -> NS:
+        d = H * dk
+        ld = _ceil(Tk, 8)
+        scale = dk ** -0.5
+        ac = _empty((B, H, Tq, ld), torch.float32, self.dev)
+        ops.gemm(q, k, ac, Tq, Tk, dk, lda=q.stride(0), ldb=k.stride(0), ldc=ld, batch=(B, H), sa=(Tq * q.stride(0), dk),
+                 sb=(Tk * k.stride(0), dk), sc=(H * Tq * ld, Tq * ld))
+        bd = None
+        if qv is not None:  # rel-pos term (q + v_bias) . P^T, P broadcast over the batch
+            bd = _empty((B, H, Tq, ld), torch.float32, self.dev)
+            ops.gemm(qv, p, bd, Tq, Tk, dk, lda=qv.stride(0), ldb=p.stride(0), ldc=ld, batch=(B, H),
+                     sa=(Tq * qv.stride(0), dk), sb=(0, dk), sc=(H * Tq * ld, Tq * ld))
+        probs = _empty((B, H, Tq, ld), self.adt, self.dev)
+        ops.attn_softmax_fwd(ac, bd, probs, lens, mask_mode, causal, scale, Tk)
+        o = _empty((B * Tq, d), self.adt, self.dev)
+        ops.gemm(probs, v, o, Tq, dk, Tk, lda=ld, ldb=v.stride(0), ldc=d, tb=True, batch=(B, H), sa=(H * Tq * ld, Tq * ld),
+                 sb=(Tk * v.stride(0), dk), sc=(Tq * d, dk))
+        return NS(q=q, k=k, v=v, qv=qv, p=p, probs=probs, o=o, B=B, H=H, Tq=Tq, Tk=Tk, dk=dk, ld=ld, scale=scale)
+
+    def attn_core_bwd(self, c: NS, do, dq, dk_, dv, dqv=None, dp32=None) -> None:
+        """do (B*Tq,d) adt.  Writes dq/dk_/dv (views with the same strides as q/k/v); rel-pos: dqv and dp32 (+=)."""
+        B, H, Tq, Tk, dk, ld = c.B, c.H, c.Tq, c.Tk, c.dk, c.ld
+        d = H * dk
+        bs = (H * Tq * ld, Tq * ld)
+        dprobs = _empty((B, H, Tq, ld), torch.float32, self.dev)
+        ops.gemm(do, c.v, dprobs, Tq, Tk, dk, lda=do.stride(0), ldb=c.v.stride(0), ldc=ld, batch=(B, H), sa=(Tq * do.stride(0), dk),
+                 sb=(Tk * c.v.stride(0), dk), sc=bs)
+        # dV[j] = sum_i probs[i,j] dO[i]
+        ops.gemm(c.probs, do, dv, Tk, dk, Tq, lda=ld, ldb=do.stride(0), ldc=dv.stride(0), ta=True, tb=True, batch=(B, H), sa=bs,
+                 sb=(Tq * do.stride(0), dk), sc=(Tk * dv.stride(0), dk))
+        dsc = _empty((B, H, Tq, ld), self.adt, self.dev)
+        dbd = _empty((B, H, Tq, ld), self.adt, self.dev) if c.qv is not None else None
+        ops.attn_softmax_bwd(c.probs, dprobs, dsc, dbd, c.scale, Tk)
+        # dQ[i] = sum_j ds[i,j] K[j] ; dK[j] = sum_i ds[i,j] Q[i]
+        ops.gemm(dsc, c.k, dq, Tq, dk, Tk, lda=ld, ldb=c.k.stride(0), ldc=dq.stride(0), tb=True, batch=(B, H), sa=bs,
+                 sb=(Tk * c.k.stride(0), dk), sc=(Tq * dq.stride(0), dk))
+        ops.gemm(dsc, c.q, dk_, Tk, dk, Tq, lda=ld, ldb=c.q.stride(0), ldc=dk_.stride(0), ta=True, tb=True, batch=(B, H), sa=bs,
+                 sb=(Tq * c.q.stride(0), dk), sc=(Tk * dk_.stride(0), dk))
+        if c.qv is not None:
+            ops.gemm(dbd, c.p, dqv, Tq, dk, Tk, lda=ld, ldb=c.p.stride(0), ldc=dqv.stride(0), tb=True, batch=(B, H), sa=bs,
+                     sb=(0, dk), sc=(Tq * dqv.stride(0), dk))
+            ops.gemm(dbd, c.qv, dp32, Tk, dk, Tq, lda=ld, ldb=c.qv.stride(0), ldc=dp32.stride(0), ta=True, tb=True, batch=(B, H),
+                     sa=bs, sb=(Tq * c.qv.stride(0), dk), sc=(0, dk), accumulate=True)
+
+    # ------------------------------------------------------------------------------------------
+    # relative-position self-attention block (nets/conformer_layer.py:107-128, nets/attention.py:120-154)
+    # ------------------------------------------------------------------------------------------
+    def rel_mha_fwd(self, x, pfx_norm, pfx, pos, B, T, H, xlens) -> NS:
+        d = x.shape[1]
+        dk = d // H
+        ln = self.layernorm(x, pfx_norm, self.adt)
+        wqkv = self.st.w(pfx + ".linear_q.weight", 3 * d, d)
+        bqkv = self.st.p_span(pfx + ".linear_q.bias", 3 * d)
+        qkv = self.linear(ln.y, None, self.adt, w=wqkv, bias_t=bqkv)
+        q, k, v = qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
+        qu = _empty((B * T, d), self.adt, self.dev)
+        qv = _empty((B * T, d), self.adt, self.dev)
+        ops.pos_bias_fwd(q, self.st.p(pfx + ".pos_bias_u").view(-1), self.st.p(pfx + ".pos_bias_v").view(-1), qu, qv)
+        p = self.linear(pos, pfx + ".linear_pos", self.adt, bias=False)
+        core = self.attn_core_fwd(qu, k, v, B, H, T, T, dk, xlens, 3 if xlens is not None else 0, 0, qv=qv, p=p)
+        out = self.linear(core.o, pfx + ".linear_o", torch.float32, res=x)
+        return NS(out=out, ln=ln, qkv=qkv, core=core, pos=pos, pfx=pfx, d=d)
+
+    def rel_mha_bwd(self, c: NS, dres) -> None:
+        st, d, core = self.st, c.d, c.core
+        B, T = core.B, core.Tq
+        dy = self.to_adt(dres)
+        do = self.linear_bwd(dy, core.o, c.pfx + ".linear_o")
+        dqkv = _empty((B * T, 3 * d), self.adt, self.dev)
+        dqu = _empty((B * T, d), self.adt, self.dev)
+        dqv = _empty((B * T, d), self.adt, self.dev)
+        dp32 = torch.empty((T, d), dtype=torch.float32, device=self.dev)
+        ops.zero_(dp32)
+        self.attn_core_bwd(core, do, dqu, dqkv[:, d:2 * d], dqkv[:, 2 * d:], dqv=dqv, dp32=dp32)
+        ops.pos_bias_bwd(dqu, dqv, dqkv[:, :d], st.g(c.pfx + ".pos_bias_u").view(-1), st.g(c.pfx + ".pos_bias_v").view(-1))
+        # linear_pos (no bias): dW_pos += dP^T pos
+        dp = self.to_adt(dp32)
+        self.linear_bwd(dp, c.pos, c.pfx + ".linear_pos", need_dx=False, bias=False)
+        # fused q/k/v projection
+        ops.act_bwd(dqkv, None, None, st.g_span(c.pfx + ".linear_q.bias", 3 * d), ACT_NONE)
+        dln = self.linear_bwd(dqkv, c.ln.y, None, dbias_done=True, w=st.w(c.pfx + ".linear_q.weight", 3 * d, d),
+                              gw=st.gw(c.pfx + ".linear_q.weight", 3 * d, d))
+        self.layernorm_bwd(c.ln, dln, dres, accumulate=True)
+
+    # ------------------------------------------------------------------------------------------
+    # plain MHA blocks of the decoder (nets/transformer_layer.py:29-51,161-177, nets/attention.py:61-71)
+    # ------------------------------------------------------------------------------------------
+    def self_mha_fwd(self, y, pfx_norm, pfx, B, L, H, ylens) -> NS:
+        d = y.shape[1]
+        ln = self.layernorm(y, pfx_norm, self.adt)
+        qkv = self.linear(ln.y, None, self.adt, w=self.st.w(pfx + ".linear_q.weight", 3 * d, d),
+                          bias_t=self.st.p_span(pfx + ".linear_q.bias", 3 * d))
+        core = self.attn_core_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], B, H, L, L, d // H, ylens, 2, 1)
+        out = self.linear(core.o, pfx + ".linear_o", torch.float32, res=y)
+        return NS(out=out, ln=ln, core=core, pfx=pfx, d=d)
+
+    def self_mha_bwd(self, c: NS, dres) -> None:
+        st, d, core = self.st, c.d, c.core
+        dy = self.to_adt(dres)
+        do = self.linear_bwd(dy, core.o, c.pfx + ".linear_o")
+        dqkv = _empty((core.B * core.Tq, 3 * d), self.adt, self.dev)
+        self.attn_core_bwd(core, do, dqkv[:, :d], dqkv[:, d:2 * d], dqkv[:, 2 * d:])
+        ops.act_bwd(dqkv, None, None, st.g_span(c.pfx + ".linear_q.bias", 3 * d), ACT_NONE)
+        dln = self.linear_bwd(dqkv, c.ln.y, None, dbias_done=True, w=st.w(c.pfx + ".linear_q.weight", 3 * d, d),
+                              gw=st.gw(c.pfx + ".linear_q.weight", 3 * d, d))
+        self.layernorm_bwd(c.ln, dln, dres, accumulate=True)
+
+    def src_mha_fwd(self, y, mem, pfx_norm, pfx, B, L, T, H, xlens) -> NS:
+        d = y.shape[1]
+        ln = self.layernorm(y, pfx_norm, self.adt)
+        q = self.linear(ln.y, pfx + ".linear_q", self.adt)
+        kv = self.linear(mem, None, self.adt, w=self.st.w(pfx + ".linear_k.weight", 2 * d, d),
+                         bias_t=self.st.p_span(pfx + ".linear_k.bias", 2 * d))
+        core = self.attn_core_fwd(q, kv[:, :d], kv[:, d:], B, H, L, T, d // H, xlens, 3 if xlens is not None else 0, 0)
+        out = self.linear(core.o, pfx + ".linear_o", torch.float32, res=y)
+        return NS(out=out, ln=ln, core=core, mem=mem, pfx=pfx, d=d)
+
+    def src_mha_bwd(self, c: NS, dres, dmem32) -> None:
+        st, d, core = self.st, c.d, c.core
+        dy = self.to_adt(dres)
+        do = self.linear_bwd(dy, core.o, c.pfx + ".linear_o")
+        dq = _empty((core.B * core.Tq, d), self.adt, self.dev)
+        dkv = _empty((core.B * core.Tk, 2 * d), self.adt, self.dev)
+        self.attn_core_bwd(core, do, dq, dkv[:, :d], dkv[:, d:])
+        dln = self.linear_bwd(dq, c.ln.y, c.pfx + ".linear_q")
+        self.layernorm_bwd(c.ln, dln, dres, accumulate=True)
+        ops.act_bwd(dkv, None, None, st.g_span(c.pfx + ".linear_k.bias", 2 * d), ACT_NONE)
+        # dmem += dkv @ W_kv   (fp32, accumulated across the decoder layers through the residual input)
+        self.linear_bwd(dkv, c.mem, None, dbias_done=True, w=st.w(c.pfx + ".linear_k.weight", 2 * d, d),
+                        gw=st.gw(c.pfx + ".linear_k.weight", 2 * d, d), dx_res=dmem32)
+
+    # ------------------------------------------------------------------------------------------
+    # convolution block (nets/conformer_layer.py:49-56, nets/conformer_convolution.py:44-57)
+    # ------------------------------------------------------------------------------------------
+    def conv_fwd(self, x, pfx_norm, pfx, B, T, bn_mod, training) -> NS:
+        st, d = self.st, x.shape[1]
+        ln = self.layernorm(x, pfx_norm, self.adt)
+        y2 = self.linear(ln.y, None, self.adt, w=st.w(pfx + ".pointwise_conv1.weight"), bias_t=st.p(pfx + ".pointwise_conv1.bias"))
+        z = _empty((B * T, d), torch.float32, self.dev)
+        nblk = B * ((T + 31) // 32)
+        partial = _empty((nblk, 2, d), torch.float32, self.dev)
+        ops.glu_dwconv_fwd(y2, st.p(pfx + ".depthwise_conv.weight").view(d, KW), st.p(pfx + ".depthwise_conv.bias"), z, partial, B, T, d)
+        mean = _empty((d,), torch.float32, self.dev)
+        rstd = _empty((d,), torch.float32, self.dev)
+        ops.bn_finalize(partial, nblk, d, B * T, mean, rstd, bn_mod.running_mean, bn_mod.running_var, bn_mod.num_batches_tracked,
+                        training, eps=bn_mod.eps, momentum=bn_mod.momentum if bn_mod.momentum is not None else 0.1)
+        a = _empty((B * T, d), self.adt, self.dev)
+        ops.bn_swish_fwd(z, mean, rstd, st.p(pfx + ".norm.weight"), st.p(pfx + ".norm.bias"), a)
+        out = self.linear(a, None, torch.float32, w=st.w(pfx + ".pointwise_conv2.weight"), bias_t=st.p(pfx + ".pointwise_conv2.bias"), res=x)
+        return NS(out=out, ln=ln, y2=y2, z=z, mean=mean, rstd=rstd, a=a, pfx=pfx, B=B, T=T, d=d, training=training)
+
+    def conv_bwd(self, c: NS, dres) -> None:
+        st, d, pfx = self.st, c.d, c.pfx
+        if not c.training:
+            raise RuntimeError("conv-module backward needs batch statistics (module must be in training mode)")
+        dy = self.to_adt(dres)
+        da = self.linear_bwd(dy, c.a, None, w=st.w(pfx + ".pointwise_conv2.weight"), gw=st.gw(pfx + ".pointwise_conv2.weight"),
+                             gb=st.g(pfx + ".pointwise_conv2.bias"))
+        rows = c.B * c.T
+        partial = _empty(((rows + 31) // 32, 2, d), torch.float32, self.dev)
+        sums = _empty((2, d), torch.float32, self.dev)
+        gam, bet = st.p(pfx + ".norm.weight"), st.p(pfx + ".norm.bias")
+        ops.bn_swish_bwd_stats(da, c.z, c.mean, c.rstd, gam, bet, partial, sums, st.g(pfx + ".norm.weight"), st.g(pfx + ".norm.bias"))
+        dy2 = _empty((rows, 2 * d), self.adt, self.dev)
+        ops.dwconv_glu_bwd(da, c.z, c.y2, c.mean, c.rstd, gam, bet, sums, st.p(pfx + ".depthwise_conv.weight").view(d, KW), dy2,
+                           st.g(pfx + ".depthwise_conv.weight").view(d, KW), st.g(pfx + ".depthwise_conv.bias"), c.B, c.T, d)
+        dln = self.linear_bwd(dy2, c.ln.y, None, w=st.w(pfx + ".pointwise_conv1.weight"), gw=st.gw(pfx + ".pointwise_conv1.weight"),
+                              gb=st.g(pfx + ".pointwise_conv1.bias"))
+        self.layernorm_bwd(c.ln, dln, dres, accumulate=True)
+
+    # ------------------------------------------------------------------------------------------
+    # Conv2d subsampling front end (nets/subsampling.py:42-48) + x*sqrt(d) (nets/positional_encoding.py:73)
+    # ------------------------------------------------------------------------------------------
+    def _conv2_weight(self, pfx, d):
+        key = pfx + ".conv.2.weight/khkwc"
+        if key not in self.st.derived:  # (o,i,kh,kw) -> (o,kh,kw,i): K index matches the channel-last im2col
+            w = _empty((d, 9 * d), self.adt, self.dev)
+            ops.permute4d(self.st.p(pfx + ".conv.2.weight"), w, (d, 3, 3, d), (9 * d, 3, 1, 9), (9 * d, 3 * d, d, 1))
+            self.st.derived[key] = w
+        return self.st.derived[key]
+
+    def _out_weight(self, pfx, d, f2):
+        key = pfx + ".out.weight/fc"
+        if key not in self.st.derived:  # columns (c*F2 + f) -> (f*d + c)
+            w = _empty((d, f2 * d), self.adt, self.dev)
+            ops.permute4d(self.st.p(pfx + ".out.weight"), w, (d, f2, d, 1), (f2 * d, 1, f2, 0), (f2 * d, d, 1, 0))
+            self.st.derived[key] = w
+        return self.st.derived[key]
+
+    def embed_fwd(self, xs, pfx, d) -> NS:
+        B, T, F = xs.shape
+        T1, F1 = (T - 3) // 2 + 1, (F - 3) // 2 + 1
+        T2, F2 = (T1 - 3) // 2 + 1, (F1 - 3) // 2 + 1
+        st = self.st
+        h1 = _empty((B, T1, F1, d), self.adt, self.dev)
+        ops.conv1_fwd(xs, st.p(pfx + ".conv.0.weight").view(d, 9), st.p(pfx + ".conv.0.bias"), h1)
+        col = _empty((B * T2 * F2, 9 * d), self.adt, self.dev)
+        ops.im2col_s2(h1, col)
+        h2 = self.linear(col, None, self.adt, w=self._conv2_weight(pfx, d), bias_t=st.p(pfx + ".conv.2.bias"), act=ACT_RELU)
+        h2v = h2.view(B * T2, F2 * d)
+        x0 = self.linear(h2v, None, torch.float32, w=self._out_weight(pfx, d, F2), bias_t=st.p(pfx + ".out.bias"), alpha=math.sqrt(d))
+        return NS(out=x0, xs=xs, h1=h1, col=col, h2=h2, B=B, T1=T1, F1=F1, T2=T2, F2=F2, d=d, pfx=pfx)
+
+    def embed_bwd(self, c: NS, dx0) -> None:
+        st, d, pfx = self.st, c.d, c.pfx
+        B, T2, F2 = c.B, c.T2, c.F2
+        dy = self.to_adt(dx0)
+        s = math.sqrt(d)
+        gwo = torch.empty((d, F2 * d), dtype=torch.float32, device=self.dev)
+        ops.zero_(gwo)
+        dh2v = self.linear_bwd(dy, c.h2.view(B * T2, F2 * d), None, alpha=s, w=self._out_weight(pfx, d, F2), gw=gwo, gb=st.g(pfx + ".out.bias"))
+        ops.permute4d(gwo, st.g(pfx + ".out.weight"), (d, F2, d, 1), (F2 * d, d, 1, 0), (F2 * d, 1, F2, 0), accumulate=True)
+        dh2 = _empty((B * T2 * F2, d), self.adt, self.dev)
+        ops.act_bwd(dh2v.view(B * T2 * F2, d), c.h2, dh2, st.g(pfx + ".conv.2.bias"), ACT_RELU)
+        gw2 = torch.empty((d, 9 * d), dtype=torch.float32, device=self.dev)
+        ops.zero_(gw2)
+        dcol = self.linear_bwd(dh2, c.col, None, dbias_done=True, w=self._conv2_weight(pfx, d), gw=gw2)
+        ops.permute4d(gw2, st.g(pfx + ".conv.2.weight"), (d, 3, 3, d), (9 * d, 3 * d, d, 1), (9 * d, 3, 1, 9), accumulate=True)
+        dh1 = _empty(c.h1.shape, self.adt, self.dev)
+        ops.col2im_s2_relu(dcol, c.h1, dh1)
+        ops.conv1_bwd(c.xs, dh1, st.g(pfx + ".conv.0.weight").view(d, 9), st.g(pfx + ".conv.0.bias"))
+
+    # ------------------------------------------------------------------------------------------
+    # encoder (nets/transformer_encoder.py:107-127; use_rel=True, arch=conformer, activation=swish)
+    # ------------------------------------------------------------------------------------------
+    def encoder_fwd(self, enc, xs, xlens, training: bool) -> NS:
+        """xs (B,T,F) fp32, xlens (B,) int64 or None (maskless inference call).  Returns ctx with ctx.out (B,T',d) fp32."""
+        d, H = enc.h_dim, enc.n_head
+        B = xs.shape[0]
+        pfx = enc._lasr_prefix
+        emb = self.embed_fwd(xs, pfx + "embed", d)
+        Tp = emb.T2
+        pos = self.to_adt(enc.pe.pe[0, :Tp])  # absolute positions 0..T'-1 (positional_encoding.py:74); contiguous slice
+        x = emb.out
+        layers = []
+        for i, layer in enumerate(enc.enc_layers):
+            lp = f"{pfx}enc_layers.{i}"
+            c1 = self.ffn_fwd(x, lp + ".feed_forward_macaron_norm", lp + ".feed_forward_macaron", ACT_SWISH, 0.5)
+            c2 = self.rel_mha_fwd(c1.out, lp + ".self_attn_norm", lp + ".self_attn", pos, B, Tp, H, xlens)
+            c3 = self.conv_fwd(c2.out, lp + ".conv_norm", lp + ".conv", B, Tp, layer.conv.norm, training)
+            c4 = self.ffn_fwd(c3.out, lp + ".feed_forward_norm", lp + ".feed_forward", ACT_SWISH, 0.5)
+            c5 = self.layernorm(c4.out, lp + ".final_norm", torch.float32)
+            layers.append((c1, c2, c3, c4, c5))
+            x = c5.y
+        fin = self.layernorm(x, pfx + "after_norm", torch.float32)
+        return NS(out=fin.y.view(B, Tp, d), emb=emb, layers=layers, fin=fin, B=B, Tp=Tp, d=d, pfx=pfx)
+
+    def encoder_bwd(self, c: NS, dh: torch.Tensor) -> None:
+        dh = dh.contiguous().view(c.B * c.Tp, c.d)
+        if dh.dtype != torch.float32:
+            raise TypeError("encoder gradient must be fp32")
+        dres = _empty(dh.shape, torch.float32, self.dev)
+        self.layernorm_bwd(c.fin, dh, dres, accumulate=False)
+        hook = self.st.grad_ready_hook
+        for i in range(len(c.layers) - 1, -1, -1):
+            c1, c2, c3, c4, c5 = c.layers[i]
+            nxt = _empty(dres.shape, torch.float32, self.dev)
+            self.layernorm_bwd(c5, dres, nxt, accumulate=False)
+            dres = nxt
+            self.ffn_bwd(c4, dres)
+            self.conv_bwd(c3, dres)
+            self.rel_mha_bwd(c2, dres)
+            self.ffn_bwd(c1, dres)
+            if hook is not None:
+                hook(*self.st.range_of(f"{c.pfx}enc_layers.{i}."))
+        self.embed_bwd(c.emb, dres)
+        if hook is not None:
+            hook(*self.st.range_of(c.pfx + "embed."))
+            hook(*self.st.range_of(c.pfx + "after_norm."))
+
+    # ------------------------------------------------------------------------------------------
+    # CTC head (nets/ctc.py:28-30): logits = ctc_lo(dropout(h)); dropout p must be 0 here
+    # ------------------------------------------------------------------------------------------
+    def ctc_head_fwd(self, ctc, h_enc) -> NS:
+        B, Tp, d = h_enc.shape
+        hb = self.to_adt(h_enc.reshape(B * Tp, d))
+        pfx = ctc._lasr_prefix + "ctc_lo"
+        logits = self.linear(hb, pfx, self.adt)
+        V = logits.shape[1]
+        return NS(out=logits, hb=hb, pfx=pfx, B=B, Tp=Tp, V=V, d=d)
+
+    def ctc_head_bwd(self, c: NS, dlogits, dh32=None) -> torch.Tensor:
+        """dlogits (B*T', V) adt view -> dh (B*T', d) fp32 (accumulated into dh32 when given)."""
+        if dh32 is None:
+            return self.linear_bwd(dlogits, c.hb, c.pfx, dx_dtype=torch.float32)
+        return self.linear_bwd(dlogits, c.hb, c.pfx, dx_res=dh32)
+
+    # ------------------------------------------------------------------------------------------
+    # decoder (nets/transformer_decoder.py:70-93, nets/transformer_layer.py:179-221)
+    # ------------------------------------------------------------------------------------------
+    def decoder_fwd(self, dec, ys, ylens, h_enc, xlens) -> NS:
+        """ys (B,L) int64 decoder input tokens ([sos | ys], models/u2.py:339-358); ylens (B,) so that key j of the
+        self-attention is valid iff j < ylens[b]+1 (and j <= i); h_enc (B,T',d) fp32; xlens raw input lengths or None."""
+        B, L = ys.shape
+        d, H = dec.h_dim, dec.n_head
+        Tp = h_enc.shape[1]
+        pfx = dec._lasr_prefix
+        V = dec.vocab
+        st = self.st
+        y = _empty((B * L, d), torch.float32, self.dev)
+        ops.embed_fwd(ys, st.p(pfx + "embed.weight"), dec.pe.pe[0], y, math.sqrt(d))
+        mem = self.to_adt(h_enc.reshape(B * Tp, d))
+        layers = []
+        for i in range(len(dec.dec_layers)):
+            lp = f"{pfx}dec_layers.{i}"
+            c1 = self.self_mha_fwd(y, lp + ".self_attn_norm", lp + ".self_attn", B, L, H, ylens)
+            c2 = self.src_mha_fwd(c1.out, mem, lp + ".src_attn_norm", lp + ".src_attn", B, L, Tp, H, xlens)
+            c3 = self.ffn_fwd(c2.out, lp + ".feed_forward_norm", lp + ".feed_forward", ACT_RELU, 1.0)
+            layers.append((c1, c2, c3))
+            y = c3.out
+        fin = self.layernorm(y, pfx + "after_norm", self.adt)
+        logits = self.linear(fin.y, pfx + "linear_out", self.adt)
+        return NS(out=logits, ys=ys, layers=layers, fin=fin, mem=mem, B=B, L=L, Tp=Tp, d=d, V=V, pfx=pfx)
+
+    def decoder_bwd(self, c: NS, dlogits, dmem32: torch.Tensor) -> None:
+        """dlogits (B*L, V) adt view; dmem32 (B*T', d) fp32 is accumulated into (memory gradient)."""
+        st = self.st
+        dfin = self.linear_bwd(dlogits, c.fin.y, c.pfx + "linear_out")
+        dres = _empty((c.B * c.L, c.d), torch.float32, self.dev)
+        self.layernorm_bwd(c.fin, dfin, dres, accumulate=False)
+        for i in range(len(c.layers) - 1, -1, -1):
+            c1, c2, c3 = c.layers[i]
+            self.ffn_bwd(c3, dres)
+            self.src_mha_bwd(c2, dres, dmem32)
+            self.self_mha_bwd(c1, dres)
+        ops.embed_bwd(c.ys, dres, st.g(c.pfx + "embed.weight"), math.sqrt(c.d))
+        if st.grad_ready_hook is not None:
+            st.grad_ready_hook(*st.range_of(c.pfx))

@@ -1,0 +1,57 @@
+"""Transformer decoder (nets/transformer_decoder.py:13-93 of the reference)."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from .. import functions as F
+from .layers import (DecoderLayer, LayerNorm, MultiHeadAttention, PositionalEncoding, PositionwiseFeedForward,
+                     check_no_dropout)
+
+
+class TransformerDecoder(nn.Module):
+    def __init__(self, i_dim: int, h_dim: int, ff_dim: int, n_head: int, n_layer: int, dropout_rate: float,
+                 pos_dropout_rate: float, self_attn_dropout_rate: float, src_attn_dropout_rate: float, ff_dropout_rate: float,
+                 arch: str) -> None:
+        super().__init__()
+        check_no_dropout(self, dropout_rate, pos_dropout_rate, self_attn_dropout_rate, src_attn_dropout_rate, ff_dropout_rate)
+        self.vocab, self.h_dim, self.n_head = i_dim, h_dim, n_head
+        self.embed = nn.Embedding(i_dim, h_dim)
+        self.pe = PositionalEncoding(h_dim, dropout_rate=pos_dropout_rate)
+        self.dec_layers = nn.ModuleList([
+            DecoderLayer(
+                size=h_dim,
+                self_attn=MultiHeadAttention(n_head=n_head, i_dim=h_dim, dropout_rate=self_attn_dropout_rate),
+                src_attn=MultiHeadAttention(n_head=n_head, i_dim=h_dim, dropout_rate=src_attn_dropout_rate),
+                feed_forward=PositionwiseFeedForward(i_dim=h_dim, h_units=ff_dim, dropout_rate=ff_dropout_rate),
+                dropout_rate=dropout_rate,
+            ) for _ in range(n_layer)
+        ])
+        self.after_norm = LayerNorm(h_dim)
+        self.linear_out = nn.Linear(h_dim, i_dim)
+
+    def forward_lens(self, y: Tensor, ylens: Tensor, memory: Tensor, xlens: Optional[Tensor]) -> Tensor:
+        """y (B,L) tokens incl. sos; self-attn key j valid iff j <= i and j < ylens[b]+1; memory (B,T',d);
+        xlens raw input lengths for the sub-sampled memory mask (None = unmasked).  -> logits (B,L,V)."""
+        st, _, pfx = F.bind(self, memory.device)
+        self.pe.ensure(y.size(1), memory.device)
+        return F.DecoderFn.apply(self, y, ylens, memory, xlens, st.anchor, *F.net_params(self, st, pfx))
+
+    def forward(self, y: Tensor, mask: Optional[Tensor], memory: Tensor, memory_mask: Optional[Tensor]) -> Tensor:
+        """Reference signature (transformer_decoder.py:70-93): mask (B,L,L) = padding | causal as built by
+        models/u2.py:146-148; memory_mask (B,T) is the PRE-subsampling padding mask (re-subsampled like :83)."""
+        b, l = y.shape
+        if mask is not None:
+            assert mask.shape == (b, l, l)
+            ylens = (~mask[:, -1, :]).sum(dim=-1) - 1  # last row sees every non-padded key
+        else:
+            raise NotImplementedError("TransformerDecoder.forward needs the causal|padding mask the reference builds")
+        xlens = None
+        if memory_mask is not None:
+            sub = memory_mask[:, :-2:2][:, :-2:2]
+            assert sub.shape == (memory.shape[0], memory.shape[1])
+            xlens = (~memory_mask).sum(dim=1)
+        return self.forward_lens(y, ylens, memory, xlens)

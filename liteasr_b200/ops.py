@@ -120,3 +120,179 @@ def ctc_fwdbwd(logits: torch.Tensor, targets: torch.Tensor, in_len: torch.Tensor
         C.c_size_t(workspace.numel() * workspace.element_size()), _stream())
     _lib.check(rc, "ctc_fwdbwd")
     return nll, grad
+
+
+# ----------------------------------------------------------------------------------------------
+# remaining entry points (see include/lasr.h for the contracts)
+# ----------------------------------------------------------------------------------------------
+def _i(v):
+    return C.c_int(int(v))
+
+
+def _l(v):
+    return C.c_int64(int(v))
+
+
+def _f(v):
+    return C.c_float(float(v))
+
+
+def zero_(t: torch.Tensor) -> torch.Tensor:
+    _require_cuda(t)
+    assert t.is_contiguous()
+    _lib.check(_lib.lib().lasr_zero(_ptr(t), C.c_size_t(t.numel() * t.element_size()), _stream()), "zero")
+    return t
+
+
+def cast_bf16(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    _require_cuda(src, dst)
+    assert src.dtype == torch.float32 and dst.dtype == torch.bfloat16 and src.is_contiguous() and dst.is_contiguous()
+    _lib.check(_lib.lib().lasr_cast_f32_bf16(_ptr(src), _ptr(dst), _l(src.numel()), _stream()), "cast_f32_bf16")
+    return dst
+
+
+def permute4d(src, dst, n, src_strides, dst_strides, accumulate=False):
+    _require_cuda(src, dst)
+    A = C.c_int64 * 4
+    _lib.check(_lib.lib().lasr_permute4d(_ptr(src), _i(dtype_code(src)), _ptr(dst), _i(dtype_code(dst)), A(*n), A(*src_strides),
+                                         A(*dst_strides), _i(accumulate), _stream()), "permute4d")
+
+
+def layernorm_fwd(x, gamma, beta, y, mean=None, rstd=None, eps=1e-12):
+    _require_cuda(x, gamma, beta, y)
+    rows, d = x.shape
+    _lib.check(_lib.lib().lasr_layernorm_fwd(_ptr(x), _l(x.stride(0)), _ptr(gamma), _ptr(beta), _ptr(y), _i(dtype_code(y)),
+                                             _l(y.stride(0)), _ptr(mean), _ptr(rstd), _i(rows), _i(d), _f(eps), _stream()),
+               "layernorm_fwd")
+    return y
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, accumulate: bool):
+    _require_cuda(dy, x, dx)
+    rows, d = x.shape
+    _lib.check(_lib.lib().lasr_layernorm_bwd(_ptr(dy), _i(dtype_code(dy)), _l(dy.stride(0)), _ptr(x), _l(x.stride(0)), _ptr(mean),
+                                             _ptr(rstd), _ptr(gamma), _ptr(dx), _l(dx.stride(0)), _i(accumulate), _ptr(dgamma),
+                                             _ptr(dbeta), _i(rows), _i(d), _stream()), "layernorm_bwd")
+
+
+def act_bwd(da, saved, dh, dbias, act, scale=1.0):
+    """dh = scale * da * act'(saved); dbias += colsum(dh).  2-D (rows, cols) views; dh/saved/dbias optional."""
+    _require_cuda(da, saved, dh, dbias)
+    rows, cols = da.shape
+    _lib.check(_lib.lib().lasr_act_bwd(_ptr(da), _l(da.stride(0)), _ptr(saved), _l(saved.stride(0) if saved is not None else 0),
+                                       _ptr(dh), _l(dh.stride(0) if dh is not None else 0), _ptr(dbias), _i(rows), _i(cols),
+                                       _i(act), _f(scale), _i(dtype_code(da)), _stream()), "act_bwd")
+
+
+def pos_bias_fwd(q, u, v, qu, qv):
+    rows, d = q.shape
+    _lib.check(_lib.lib().lasr_pos_bias_fwd(_ptr(q), _l(q.stride(0)), _ptr(u), _ptr(v), _ptr(qu), _ptr(qv), _l(qu.stride(0)),
+                                            _i(rows), _i(d), _i(dtype_code(q)), _stream()), "pos_bias_fwd")
+
+
+def pos_bias_bwd(dqu, dqv, dq, du, dv):
+    rows, d = dqu.shape
+    _lib.check(_lib.lib().lasr_pos_bias_bwd(_ptr(dqu), _ptr(dqv), _l(dqu.stride(0)), _ptr(dq), _l(dq.stride(0)), _ptr(du), _ptr(dv),
+                                            _i(rows), _i(d), _i(dtype_code(dqu)), _stream()), "pos_bias_bwd")
+
+
+def embed_fwd(tokens, emb, pe, out, scale):
+    B, L = tokens.shape
+    _lib.check(_lib.lib().lasr_embed_fwd(_ptr(tokens), _i(L), _ptr(emb), _ptr(pe), _ptr(out), _i(B), _i(emb.shape[1]), _f(scale),
+                                         _stream()), "embed_fwd")
+
+
+def embed_bwd(tokens, dout, demb, scale):
+    _lib.check(_lib.lib().lasr_embed_bwd(_ptr(tokens), _ptr(dout), _ptr(demb), _l(tokens.numel()), _i(demb.shape[1]), _f(scale),
+                                         _stream()), "embed_bwd")
+
+
+def scale_by_scalar(x, scalar):
+    assert x.is_contiguous() and scalar.dtype == torch.float32
+    _lib.check(_lib.lib().lasr_scale_by_scalar(_ptr(x), _i(dtype_code(x)), _l(x.numel()), _ptr(scalar), _stream()), "scale_by_scalar")
+
+
+def glu_dwconv_fwd(y2, w, bias, z, partial, B, T, d):
+    _lib.check(_lib.lib().lasr_glu_dwconv_fwd(_ptr(y2), _i(dtype_code(y2)), _l(y2.stride(0)), _ptr(w), _ptr(bias), _ptr(z),
+                                              _ptr(partial), _i(B), _i(T), _i(d), _stream()), "glu_dwconv_fwd")
+
+
+def bn_finalize(partial, nblk, d, count, mean, rstd, running_mean, running_var, nbt, training, eps=1e-5, momentum=0.1):
+    _lib.check(_lib.lib().lasr_bn_finalize(_ptr(partial), _i(nblk), _i(d), _l(count), _f(eps), _f(momentum), _ptr(mean), _ptr(rstd),
+                                           _ptr(running_mean), _ptr(running_var), _ptr(nbt), _i(training), _stream()), "bn_finalize")
+
+
+def bn_swish_fwd(z, mean, rstd, gamma, beta, a):
+    rows, d = z.shape
+    _lib.check(_lib.lib().lasr_bn_swish_fwd(_ptr(z), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(beta), _ptr(a), _i(dtype_code(a)),
+                                            _l(rows), _i(d), _stream()), "bn_swish_fwd")
+
+
+def bn_swish_bwd_stats(da, z, mean, rstd, gamma, beta, partial, sums, dgamma, dbeta):
+    rows, d = z.shape
+    _lib.check(_lib.lib().lasr_bn_swish_bwd_stats(_ptr(da), _i(dtype_code(da)), _ptr(z), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(beta),
+                                                  _ptr(partial), _ptr(sums), _ptr(dgamma), _ptr(dbeta), _l(rows), _i(d), _stream()),
+               "bn_swish_bwd_stats")
+
+
+def dwconv_glu_bwd(da, z, y2, mean, rstd, gamma, beta, sums, w, dy2, dw, dbias, B, T, d):
+    _lib.check(_lib.lib().lasr_dwconv_glu_bwd(_ptr(da), _ptr(z), _ptr(y2), _i(dtype_code(y2)), _l(y2.stride(0)), _ptr(mean), _ptr(rstd),
+                                              _ptr(gamma), _ptr(beta), _ptr(sums), _ptr(w), _ptr(dy2), _l(dy2.stride(0)), _ptr(dw),
+                                              _ptr(dbias), _i(B), _i(T), _i(d), _stream()), "dwconv_glu_bwd")
+
+
+def conv1_fwd(x, w, bias, h1):
+    B, T, F = x.shape
+    _lib.check(_lib.lib().lasr_conv1_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(h1), _i(dtype_code(h1)), _i(B), _i(T), _i(F),
+                                         _i(h1.shape[-1]), _stream()), "conv1_fwd")
+
+
+def conv1_bwd(x, dh1, dw, dbias):
+    B, T, F = x.shape
+    _lib.check(_lib.lib().lasr_conv1_bwd(_ptr(x), _ptr(dh1), _i(dtype_code(dh1)), _ptr(dw), _ptr(dbias), _i(B), _i(T), _i(F),
+                                         _i(dh1.shape[-1]), _stream()), "conv1_bwd")
+
+
+def im2col_s2(h1, col):
+    B, T1, F1, d = h1.shape
+    _lib.check(_lib.lib().lasr_im2col_s2(_ptr(h1), _ptr(col), _i(dtype_code(h1)), _i(B), _i(T1), _i(F1), _i(d), _stream()), "im2col")
+
+
+def col2im_s2_relu(dcol, h1, dh1):
+    B, T1, F1, d = h1.shape
+    _lib.check(_lib.lib().lasr_col2im_s2_relu(_ptr(dcol), _ptr(h1), _ptr(dh1), _i(dtype_code(h1)), _i(B), _i(T1), _i(F1), _i(d),
+                                              _stream()), "col2im")
+
+
+def attn_softmax_fwd(ac, bd, probs, lens, mask_mode, causal, scale, Tk):
+    B, H, Tq, ld = ac.shape
+    _lib.check(_lib.lib().lasr_attn_softmax_fwd(_ptr(ac), _ptr(bd), _ptr(probs), _i(dtype_code(probs)), _ptr(lens), _i(mask_mode),
+                                                _i(causal), _f(scale), _i(B), _i(H), _i(Tq), _i(Tk), _i(ld), _stream()),
+               "attn_softmax_fwd")
+
+
+def attn_softmax_bwd(probs, dprobs, dsc, dbd, scale, Tk):
+    B, H, Tq, ld = probs.shape
+    _lib.check(_lib.lib().lasr_attn_softmax_bwd(_ptr(probs), _ptr(dprobs), _ptr(dsc), _ptr(dbd), _i(dtype_code(probs)), _f(scale),
+                                                _i(B), _i(H), _i(Tq), _i(Tk), _i(ld), _stream()), "attn_softmax_bwd")
+
+
+def lsmooth_kl_fwdbwd(logits, ys, ylens, V, smoothing, grad_scale, upstream, row_loss, grad):
+    """logits/grad: (B*(lmax+1), >=V) 2-D views (row stride = padded vocab)."""
+    B, lmax = ys.shape
+    _lib.check(_lib.lib().lasr_lsmooth_kl_fwdbwd(_ptr(logits), _i(dtype_code(logits)), _l(logits.stride(0)), _ptr(ys), _ptr(ylens), _i(B),
+                                                 _i(lmax), _i(V), _f(smoothing), _f(grad_scale), _ptr(upstream), _ptr(row_loss),
+                                                 _ptr(grad), _l(grad.stride(0)), _stream()), "lsmooth_kl")
+
+
+def hybrid_combine(nll, row_kl, ctc_weight, out):
+    _lib.check(_lib.lib().lasr_hybrid_combine(_ptr(nll), _i(nll.numel()), _ptr(row_kl), _i(row_kl.numel()), _f(ctc_weight), _ptr(out),
+                                              _stream()), "hybrid_combine")
+
+
+def clip_adam_step(params, grads, exp_avg, exp_avg_sq, state, workspace, *, grad_mult=1.0, max_norm=5.0, beta1=0.9, beta2=0.999,
+                   eps=1e-8, weight_decay=0.0, noam_factor=0.0, model_dim=256.0, warmup=25000.0, lr=1e-3):
+    _lib.check(_lib.lib().lasr_clip_adam_step(_ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), _l(params.numel()),
+                                              _f(grad_mult), _f(max_norm), _f(beta1), _f(beta2), _f(eps), _f(weight_decay),
+                                              _f(noam_factor), _f(model_dim), _f(warmup), _f(lr), _ptr(state), _ptr(workspace),
+                                              _stream()), "clip_adam_step")
