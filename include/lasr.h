@@ -41,6 +41,7 @@ extern "C" {
 int lasr_version(void);             /* 100 * major + minor */
 int lasr_arch(void);                /* 100 (sm_100a) */
 const char* lasr_last_error(void);  /* thread-local, valid until the next failing call */
+unsigned long long lasr_launch_count(void); /* kernels launched by this library so far (bench bookkeeping) */
 
 /* ------------------------------------------------------------------------------------------------
  * GEMM  C[b1,b2] = alpha * act(A[b1,b2] . B[b1,b2]^T + bias) (+ res)

@@ -50,6 +50,7 @@ def lib() -> C.CDLL:
         _lib = C.CDLL(LIB_PATH)
         _lib.lasr_last_error.restype = C.c_char_p
         _lib.lasr_ctc_workspace_bytes.restype = C.c_size_t
+        _lib.lasr_launch_count.restype = C.c_ulonglong
     return _lib
 
 
@@ -57,3 +58,7 @@ def check(rc: int, what: str) -> None:
     if rc != 0:
         msg = lib().lasr_last_error().decode(errors="replace")
         raise RuntimeError(f"liblasr {what} failed (rc={rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(lib().lasr_launch_count())

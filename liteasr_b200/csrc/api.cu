@@ -15,7 +15,10 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static unsigned long long g_launches = 0;
+
 int check_launch(const char* what) {
+    ++g_launches;  // one per kernel launch site (statistics only; benign race across threads)
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("%s: %s", what, cudaGetErrorString(e));
@@ -34,6 +37,7 @@ extern "C" {
 int lasr_version(void) { return 1; }
 int lasr_arch(void) { return 100; }
 const char* lasr_last_error(void) { return lasr::g_err; }
+unsigned long long lasr_launch_count(void) { return lasr::g_launches; }
 
 int lasr_gemm(const lasr_gemm_args* a, void* stream) {
     using namespace lasr;

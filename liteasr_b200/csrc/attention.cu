@@ -158,9 +158,11 @@ int lasr_attn_softmax_bwd(const void* probs, const float* dprobs, void* dscores,
     if (grid2 > 148 * 32) grid2 = 148 * 32;
     if (dtype == LASR_F32) {
         attn_softmax_bwd_kernel<float><<<ceil_div(rows, 8), 256, 0, st>>>((const float*)probs, dprobs, (float*)dscores, scale, rows, Tk, ld);
+        if (dbd && check_launch("attn_softmax_bwd")) return LASR_ERR_CUDA;
         if (dbd) rel_shift_bwd_kernel<float><<<grid2, 256, 0, st>>>((const float*)dscores, (float*)dbd, (long)B * H, Tq, ld);
     } else if (dtype == LASR_BF16) {
         attn_softmax_bwd_kernel<bf16><<<ceil_div(rows, 8), 256, 0, st>>>((const bf16*)probs, dprobs, (bf16*)dscores, scale, rows, Tk, ld);
+        if (dbd && check_launch("attn_softmax_bwd")) return LASR_ERR_CUDA;
         if (dbd) rel_shift_bwd_kernel<bf16><<<grid2, 256, 0, st>>>((const bf16*)dscores, (bf16*)dbd, (long)B * H, Tq, ld);
     } else { set_error("attn_softmax_bwd: bad dtype"); return LASR_ERR_UNSUPPORTED; }
     return check_launch("attn_softmax_bwd");

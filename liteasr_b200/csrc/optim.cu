@@ -103,7 +103,9 @@ int lasr_clip_adam_step(float* params, const float* grads, float* exp_avg, float
     if (nblk > 1024) nblk = 1024;
     if (nblk < 1) nblk = 1;
     sumsq_partial_kernel<<<nblk, 256, 0, st>>>(grads, n, workspace);
+    if (int rc = check_launch("sumsq_partial")) return rc;
     optim_prepare_kernel<<<1, 256, 0, st>>>(workspace, nblk, grad_mult, max_norm, noam_factor, model_dim, warmup, fixed_lr, state);
+    if (int rc = check_launch("optim_prepare")) return rc;
     int grid = ceil_div(n, 1024 * 4);
     if (grid > 148 * 8) grid = 148 * 8;
     adam_step_kernel<<<grid, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, beta1, beta2, eps, weight_decay, state);

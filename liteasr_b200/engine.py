@@ -388,6 +388,8 @@ class Engine:
         dres = _empty(dh.shape, torch.float32, self.dev)
         self.layernorm_bwd(c.fin, dh, dres, accumulate=False)
         hook = self.st.grad_ready_hook
+        if hook is not None:
+            hook(*self.st.range_of(c.pfx + "after_norm."))
         for i in range(len(c.layers) - 1, -1, -1):
             c1, c2, c3, c4, c5 = c.layers[i]
             nxt = _empty(dres.shape, torch.float32, self.dev)
@@ -402,7 +404,6 @@ class Engine:
         self.embed_bwd(c.emb, dres)
         if hook is not None:
             hook(*self.st.range_of(c.pfx + "embed."))
-            hook(*self.st.range_of(c.pfx + "after_norm."))
 
     # ------------------------------------------------------------------------------------------
     # CTC head (nets/ctc.py:28-30): logits = ctc_lo(dropout(h)); dropout p must be 0 here

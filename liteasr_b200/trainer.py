@@ -1,0 +1,183 @@
+"""Training step and loop for the hot path (the reference's ``liteasr/trainer.py``), B200-first.
+
+``TrainStep`` is one optimizer step of ``Trainer.run`` (trainer.py:140-171) restated for a flat-store model:
+    zero grads -> [micro-steps: criterion(model, batch) -> backward (bucketed all-reduce overlapped)] ->
+    fused global-norm clip + non-finite skip + (Noam) Adam.
+Host->device copies excepted, the whole step is captured once per input shape into a CUDA graph and replayed, so the ~1.5k
+kernel launches of a 12-layer Conformer step cost one ``cudaGraphLaunch`` (the d=256 working set is launch-bound otherwise).
+Semantics kept from the reference: losses of the micro-steps are summed un-scaled (quirk Q9); the loss is normalised by the
+batch size inside the criterion; a non-finite gradient norm skips the update (decided on the device, identically on all ranks
+because it is evaluated after the all-reduce); ``grad = None``-style zeroing becomes one memset of the flat buffer.
+"""
+from __future__ import annotations
+
+import time
+from typing import Callable, Dict, Iterable, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import functions as F
+from . import ops
+from .distributed.flat_ddp import FlatDDP
+from .optims import FusedAdam, FusedNoam, NoamConfig
+
+
+class TrainStep:
+    def __init__(self, model, criterion, optimizer=None, *, clip_grad_norm: float = 5.0, accum_grad: int = 1,
+                 use_graph: bool = True, ddp: Optional[bool] = None, bucket_bytes: int = 64 << 20, device=None):
+        self.model, self.criterion = model, criterion
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.store, _, _ = F.bind(model, self.device)
+        self.store.enable_direct_grads()
+        self.optimizer = optimizer if optimizer is not None else FusedNoam(self.store, NoamConfig())
+        self.clip = clip_grad_norm
+        self.accum = accum_grad
+        self.use_graph = use_graph
+        if ddp is None:
+            ddp = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.ddp = FlatDDP(model, self.store, bucket_bytes=bucket_bytes) if ddp else None
+        self.graphs: Dict[Tuple, Tuple] = {}
+        self.loss_out = torch.zeros(3, dtype=torch.float32, device=self.device)
+
+    # ------------------------------------------------------------------ one optimizer step, eager
+    def _body(self, batches) -> torch.Tensor:
+        self.store.zero_grads()
+        if self.ddp is not None:
+            self.ddp.broadcast_buffers()
+        total = None
+        for i, (xs, xlens, ys, ylens) in enumerate(batches):
+            last = i == len(batches) - 1
+            if self.ddp is not None:
+                self.ddp.sync_grads = last  # no_sync on all but the last micro-step (trainer.py:142-145)
+                self.ddp.begin_backward()
+            loss = self.criterion(self.model, xs, xlens, ys, ylens)
+            loss.backward()
+            total = loss.detach() if total is None else total + loss.detach()
+        mult = self.ddp.finish_backward() if self.ddp is not None else 1.0
+        self.optimizer.step(self.clip, grad_mult=mult)
+        return total
+
+    def step_eager(self, *batch) -> torch.Tensor:
+        return self._body(self._split(batch))
+
+    def _split(self, batch):
+        if self.accum == 1:
+            return [tuple(batch)]
+        xs, xlens, ys, ylens = batch
+        return [tuple(t.chunk(self.accum)[i] for t in (xs, xlens, ys, ylens)) for i in range(self.accum)]
+
+    # ------------------------------------------------------------------ CUDA-graph replay per shape bucket
+    def __call__(self, xs, xlens, ys, ylens) -> torch.Tensor:
+        """Device tensors in, device loss out (sum over micro-steps).  Copies the batch into the graph's static buffers."""
+        if not self.use_graph:
+            return self.step_eager(xs, xlens, ys, ylens)
+        key = (tuple(xs.shape), tuple(ys.shape), self.model.training)
+        entry = self.graphs.get(key)
+        if entry is None:
+            entry = self._capture(key, xs, xlens, ys, ylens)
+        graph, static, loss = entry
+        for dst, src in zip(static, (xs, xlens, ys, ylens)):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        graph.replay()
+        return loss
+
+    def static_inputs(self, xs, xlens, ys, ylens):
+        """The static device buffers for this shape (capture on first use) -- fill them in place to skip the D2D copy."""
+        key = (tuple(xs.shape), tuple(ys.shape), self.model.training)
+        if key not in self.graphs:
+            self._capture(key, xs, xlens, ys, ylens)
+        return self.graphs[key][1]
+
+    def _capture(self, key, xs, xlens, ys, ylens):
+        static = tuple(t.clone() for t in (xs, xlens, ys, ylens))
+        # snapshot state mutated by the warm-up steps so capture does not change training semantics
+        snap = (self.store.flat.clone(), self.optimizer.exp_avg.clone(), self.optimizer.exp_avg_sq.clone(),
+                self.optimizer.state.clone(), {k: v.clone() for k, v in self.model.state_dict().items() if "running" in k or "num_batches" in k})
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._body(self._split(static))
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss = self._body(self._split(static))
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            self.store.flat.copy_(snap[0])
+            self.optimizer.exp_avg.copy_(snap[1])
+            self.optimizer.exp_avg_sq.copy_(snap[2])
+            self.optimizer.state.copy_(snap[3])
+            sd = self.model.state_dict()
+            for k, v in snap[4].items():
+                sd[k].copy_(v)
+        self.graphs[key] = (graph, static, loss)
+        return self.graphs[key]
+
+
+class Trigger:
+    """utils/trigger.py:6-34: fires every ``interval`` iterations."""
+
+    def __init__(self, interval: int):
+        self.interval = max(1, int(interval))
+
+    def __call__(self, it: int) -> bool:
+        return it % self.interval == 0
+
+
+class Trainer:
+    """Loop mirror of trainer.py:28-227 over an iterable of collated batches ``(xs, xlens, ys, ylens)`` (CPU or GPU
+    tensors, the collator contract of dataset/asr_dataset.py:115-126).  Data loading itself is out of scope."""
+
+    def __init__(self, model, criterion, optimizer=None, *, clip_grad_norm=5.0, accum_grad=1, report_interval=100,
+                 use_graph=True, device=None, log: Callable[[str], None] = print):
+        self.step_fn = TrainStep(model, criterion, optimizer, clip_grad_norm=clip_grad_norm, accum_grad=accum_grad,
+                                 use_graph=use_graph, device=device)
+        self.model, self.criterion = model, criterion
+        self.device = self.step_fn.device
+        self.report = Trigger(report_interval)
+        self.iter = 0
+        self.log = log
+        self.loss_acc = torch.zeros((), device=self.device)
+
+    def run(self, batches: Iterable, max_iters: Optional[int] = None) -> None:
+        self.model.train()
+        for batch in batches:
+            batch = tuple(t.to(self.device, non_blocking=True) for t in batch)  # trainer.py:140 (async from pinned memory)
+            loss = self.step_fn(*batch)
+            self.loss_acc += loss / self.step_fn.accum
+            self.iter += 1
+            if self.report(self.iter):
+                self.report_loss()
+            if max_iters is not None and self.iter >= max_iters:
+                break
+
+    def report_loss(self) -> None:
+        loss = self.loss_acc.clone()
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.reduce(loss, dst=0)  # trainer.py:176
+            loss /= dist.get_world_size()
+        opt = self.step_fn.optimizer
+        if not dist.is_initialized() or dist.get_rank() == 0:
+            self.log(f"iter {self.iter} loss {float(loss) / self.report.interval:.4f} lr {opt.rate():.3e} "
+                     f"grad_norm {opt.last_grad_norm():.3f} updates {opt.num_updates()}")
+        self.loss_acc.zero_()
+
+    @torch.no_grad()
+    def valid(self, batches: Iterable) -> float:
+        """trainer.py:188-209: criterion under eval() + no_grad (BatchNorm running statistics)."""
+        self.model.eval()
+        tot, n = 0.0, 0
+        for batch in batches:
+            batch = tuple(t.to(self.device) for t in batch)
+            tot += float(self.criterion(self.model, *batch))
+            n += 1
+        self.model.train()
+        return tot / max(n, 1)
+
+    def save_model(self, path: str) -> None:
+        if not dist.is_initialized() or dist.get_rank() == 0:
+            torch.save(self.model.state_dict(), path)  # models/__init__.py:31-32 (model-only checkpoint)

@@ -1,0 +1,79 @@
+"""CPU: host-side logic that needs no GPU -- registries, config mirrors, schema, flat-store ordering, masks."""
+import pytest
+import torch
+
+
+def test_registries_and_config_defaults_mirror_reference():
+    import liteasr_b200.criterions as C
+    import liteasr_b200.models as M
+    from liteasr_b200.criterions.hybrid_ctc_attn import HybridCTCLossConfig
+    from liteasr_b200.models.u2 import U2Config
+    assert "U2" in M.MODEL_REGISTRY and "hybrid_ctc" in C.CRITERION_REGISTRY
+    c = U2Config(input_dim=80, vocab_size=100)
+    # models/u2.py:35-67 defaults
+    assert (c.name, c.dropout_rate, c.use_rel, c.enc_dim, c.enc_ff_dim, c.enc_attn_heads, c.enc_layers, c.activation) == \
+        ("U2", 0.0, True, 256, 2048, 4, 12, "swish")
+    assert (c.dec_dim, c.dec_ff_dim, c.dec_attn_heads, c.dec_layers) == (256, 2048, 4, 6)
+    assert c.enc_attn_dropout_rate == "${model.enc_dropout_rate}"  # II(...) interpolation strings kept
+    h = HybridCTCLossConfig()
+    assert (h.name, h.padding_idx, h.smoothing, h.normalize_length, h.ctc_weight) == ("hybrid_ctc", -1, 0.0, False, 0.0)
+
+
+def test_build_model_and_criterion_through_registry():
+    from types import SimpleNamespace as NS
+    import liteasr_b200.criterions as C
+    import liteasr_b200.models as M
+    task = NS(feat_dim=80, vocab_size=37)
+    m = M.build_model(NS(name="U2", enc_layers=1, dec_layers=1, enc_dim=64, dec_dim=64, enc_attn_heads=1, dec_attn_heads=1,
+                         enc_ff_dim=96, dec_ff_dim=96), task)
+    assert m.sos == m.eos == 36 and m.blank == 0 and m.ignore == -1
+    crit = C.build_criterion(NS(name="hybrid_ctc", ctc_weight=0.3, smoothing=0.1), task)
+    assert crit.cfg.vocab_size == 37 and crit.cfg.ctc_weight == 0.3
+
+
+def test_state_dict_schema_matches_reference_keys():
+    from liteasr_b200.models.u2 import U2, U2Config
+    from liteasr_b200.schema import U2Dims, u2_schema
+    dims = U2Dims(80, 50, 128, 256, 2, 2, 128, 256, 2, 2)
+    m = U2(U2Config(**dims.__dict__))
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {n: tuple(s) for n, s, _ in u2_schema(dims)}
+    from liteasr_b200.utils.synthetic import synth_state_dict
+    m.load_state_dict(synth_state_dict(dims, 1), strict=True)
+
+
+def test_unsupported_configs_fail_loudly():
+    from liteasr_b200.models.u2 import U2, U2Config
+    with pytest.raises(NotImplementedError):
+        U2(U2Config(input_dim=80, vocab_size=50, dropout_rate=0.1))
+    with pytest.raises(NotImplementedError):
+        U2(U2Config(input_dim=80, vocab_size=50, use_rel=False))
+
+
+def test_cpu_forward_fails_loudly():
+    from liteasr_b200.models.u2 import U2, U2Config
+    m = U2(U2Config(input_dim=80, vocab_size=50, enc_layers=1, dec_layers=1, enc_dim=64, dec_dim=64, enc_attn_heads=1,
+                    dec_attn_heads=1, enc_ff_dim=96, dec_ff_dim=96))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.randn(1, 40, 80), torch.tensor([40]), torch.tensor([[3]]), torch.tensor([1]))
+
+
+def test_flat_order_groups_qkv():
+    from liteasr_b200.models.u2 import U2, U2Config
+    from liteasr_b200.store import _ordered_named_parameters
+    m = U2(U2Config(input_dim=80, vocab_size=50, enc_layers=1, dec_layers=1, enc_dim=64, dec_dim=64, enc_attn_heads=1,
+                    dec_attn_heads=1, enc_ff_dim=96, dec_ff_dim=96))
+    names = [n for n, _ in _ordered_named_parameters(m)]
+    assert sorted(names) == sorted(n for n, _ in m.named_parameters())
+    i = names.index("encoder.enc_layers.0.self_attn.linear_q.weight")
+    assert names[i:i + 6] == [f"encoder.enc_layers.0.self_attn.linear_{x}.{k}" for k in ("weight", "bias") for x in "qkv"]
+
+
+def test_masks_and_synthetic_batch_contract():
+    from liteasr_b200.utils.mask import padding_mask, triangle_mask
+    from liteasr_b200.utils.synthetic import pred_len, synth_batch
+    assert padding_mask(torch.tensor([5, 3, 1])).int().tolist() == [[0, 0, 0, 0, 0], [0, 0, 0, 1, 1], [0, 1, 1, 1, 1]]
+    assert triangle_mask(3, 5, diagonal=2).int().tolist() == [[0, 0, 1, 1, 1], [0, 0, 0, 1, 1], [0, 0, 0, 0, 1]]
+    xs, xlens, ys, ylens = synth_batch(8, 500, 30, 500, seed=42)
+    assert xs.shape == (8, 500, 80) and xlens[0] == 500 and (xlens[:-1] >= xlens[1:]).all()
+    assert (ys[torch.arange(8), ylens - 1] > 0).all() and ((ys == -1) == (torch.arange(ys.shape[1])[None] >= ylens[:, None])).all()
+    assert (2 * ylens <= pred_len(xlens)).all() and (xs[1, int(xlens[1]):] == 0).all()

@@ -1,0 +1,140 @@
+"""GPU: the full U2 + hybrid-CTC training step (forward + hand-written backward through the C ABI) against the CPU oracle
+on the golden cases, in fp32 (SIMT GEMMs) and bf16 (tcgen05 GEMMs).  Dropout 0 everywhere."""
+import json
+import math
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _setup(case, precision):
+    from liteasr_b200.criterions.hybrid_ctc_attn import HybridCTCLoss, HybridCTCLossConfig
+    from liteasr_b200.models.u2 import U2, U2Config
+    from liteasr_b200.schema import U2Dims
+    from liteasr_b200.utils.synthetic import synth_batch, synth_state_dict
+    g = json.load(open(os.path.join(GOLDEN, f"u2_{case}.json")))
+    dims = U2Dims(**g["dims"])
+    batch = synth_batch(g["batch"], g["tmax"], g["lmax"], dims.vocab_size, seed=g["seed"])
+    sd = synth_state_dict(dims, seed=g["seed"])
+    model = U2(U2Config(**{**g["dims"], "precision": precision}))
+    model.load_state_dict(sd)
+    model = model.cuda().train()
+    crit = HybridCTCLoss(HybridCTCLossConfig(vocab_size=dims.vocab_size, smoothing=g["smoothing"], ctc_weight=g["ctc_weight"]))
+    return g, dims, batch, sd, model, crit
+
+
+def _oracle(g, sd, batch):
+    from oracle import u2_oracle as O
+    xs, xlens, ys, ylens = batch
+    sd64 = {k: (v.double().requires_grad_(True) if v.is_floating_point() and "running" not in k and ".pe.pe" not in k
+                else (v.double() if v.is_floating_point() else v)) for k, v in sd.items()}
+    bn = {}
+    out = O.hybrid_loss(sd64, O.U2Shape(**g["dims"]), xs.double(), xlens, ys, ylens, g["ctc_weight"], g["smoothing"], True, bn)
+    out["loss"].backward()
+    return sd64, out, bn
+
+
+def _rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30)), float((a - b).abs().max()), float(b.abs().max())
+
+
+@pytest.mark.parametrize("case", ["tiny", "tiny_odd", "c1"])
+def test_train_step_fp32_matches_oracle_and_golden(case):
+    g, dims, batch, sd, model, crit = _setup(case, "fp32")
+    sd64, out, bn = _oracle(g, sd, batch)
+    xs, xlens, ys, ylens = [t.cuda() for t in batch]
+    loss = crit(model, xs, xlens, ys, ylens)
+    loss.backward()
+    # stated fp32 tolerance: loss rel 1e-5 (vs oracle AND vs the reference's golden value)
+    assert math.isclose(float(loss), float(out["loss"]), rel_tol=1e-5)
+    assert math.isclose(float(loss), g["f64"]["loss"], rel_tol=1e-5)
+    parts = model.last_losses.tolist()
+    assert math.isclose(parts[1], g["f64"]["loss_ctc"], rel_tol=1e-5) and math.isclose(parts[2], g["f64"]["loss_attn"], rel_tol=1e-5)
+    gmax = max(float(p.grad.abs().max()) for p in sd64.values() if getattr(p, "grad", None) is not None)
+    for n, p in model.named_parameters():
+        assert p.grad is not None, n
+        r, m, bmax = _rel(p.grad, sd64[n].grad)
+        # grads: max-abs error <= 1e-4 * max|g|; parameters with identically-zero true gradient included
+        assert m <= 1e-4 * max(bmax, 1e-3 * gmax), (n, r, m, bmax)
+    for k, v in bn.items():
+        got = model.state_dict()[k]
+        if "running" in k:
+            assert _rel(got, v)[0] < 1e-5, k
+        else:
+            assert int(got) == int(v)
+
+
+@pytest.mark.parametrize("case", ["tiny", "c1"])
+def test_train_step_bf16_within_tolerance(case):
+    g, dims, batch, sd, model, crit = _setup(case, "bf16")
+    sd64, out, _ = _oracle(g, sd, batch)
+    xs, xlens, ys, ylens = [t.cuda() for t in batch]
+    with torch.no_grad():
+        h_attn, h_ctc = model(xs, xlens, ys, ylens)
+    # stated bf16 tolerance: rel-L2 <= 2e-2 on the logits (bf16 operands, fp32 accumulate / residual stream / statistics)
+    assert _rel(h_ctc.float(), out["h_ctc"])[0] < 2e-2
+    assert _rel(h_attn.float(), out["h_attn"])[0] < 2e-2
+    model.load_state_dict(sd)  # undo the BatchNorm running-stat update of the probe forward
+    loss = crit(model, xs, xlens, ys, ylens)
+    loss.backward()
+    assert math.isclose(float(loss), g["f64"]["loss"], rel_tol=2e-3)
+    rels = []
+    for n, p in model.named_parameters():
+        r, m, bmax = _rel(p.grad, sd64[n].grad)
+        if bmax > 1e-6:  # skip identically-zero gradients (k-projection biases, pre-BatchNorm bias)
+            rels.append(r)
+            assert r < 0.15, (n, r)
+    rels.sort()
+    assert rels[len(rels) // 2] < 2e-2  # median rel-L2 over parameters
+
+
+def test_public_forward_and_generic_criterion_path_fp32():
+    """model.forward -> (h_attn, h_ctc) + loss kernels applied to the logits == fused criterion == oracle."""
+    g, dims, batch, sd, model, crit = _setup("tiny", "fp32")
+    sd64, out, _ = _oracle(g, sd, batch)
+    xs, xlens, ys, ylens = [t.cuda() for t in batch]
+    h_attn, h_ctc = model(xs, xlens, ys, ylens)
+    assert h_attn.shape == tuple(out["h_attn"].shape) and h_ctc.shape == tuple(out["h_ctc"].shape)
+    assert _rel(h_ctc, out["h_ctc"])[0] < 1e-5 and _rel(h_attn, out["h_attn"])[0] < 1e-5
+    loss = crit.loss_from_logits(model, h_attn, h_ctc, xlens, ys, ylens)
+    assert math.isclose(float(loss), float(out["loss"]), rel_tol=1e-5)
+    loss.backward()
+    for n, p in model.named_parameters():
+        r, m, bmax = _rel(p.grad, sd64[n].grad)
+        assert m <= 1e-4 * max(bmax, 1e-6), (n, r, m)
+    tgt_attn, tgt_ctc = model.get_target(ys, ylens)
+    from oracle import u2_oracle as O
+    assert torch.equal(tgt_attn.cpu(), O.attention_targets(batch[2], batch[3], dims.vocab_size))
+    assert torch.equal(model.get_pred_len(xlens).cpu(), O.subsampled_len(batch[1]))
+
+
+def test_grad_accumulation_and_no_grad_eval():
+    g, dims, batch, sd, model, crit = _setup("tiny", "fp32")
+    xs, xlens, ys, ylens = [t.cuda() for t in batch]
+    crit(model, xs, xlens, ys, ylens).backward()
+    g1 = {n: p.grad.clone() for n, p in model.named_parameters()}
+    model.load_state_dict(sd)
+    crit(model, xs, xlens, ys, ylens).backward()  # second micro-step: autograd accumulates (trainer.py:148-150, quirk Q9)
+    for n, p in model.named_parameters():
+        assert torch.allclose(p.grad, 2 * g1[n], rtol=1e-4, atol=1e-7), n
+    model.eval()
+    with torch.no_grad():
+        l_eval = crit(model, xs, xlens, ys, ylens)  # valid(): running BatchNorm stats, no graph
+    assert torch.isfinite(l_eval) and not l_eval.requires_grad
+
+
+def test_state_dict_schema_matches_reference():
+    from liteasr_b200.models.u2 import U2, U2Config
+    from liteasr_b200.schema import U2Dims, u2_schema
+    dims = U2Dims(80, 50, 128, 256, 2, 2, 128, 256, 2, 2)
+    m = U2(U2Config(**dims.__dict__)).cuda()
+    xs = torch.randn(2, 40, 80, device="cuda")
+    m(xs, torch.tensor([40, 33], device="cuda"), torch.tensor([[3, 4], [5, -1]], device="cuda"), torch.tensor([2, 1], device="cuda"))
+    want = {n: tuple(s) for n, s, _ in u2_schema(dims)}
+    got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert got == want
