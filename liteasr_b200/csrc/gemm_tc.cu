@@ -2,12 +2,20 @@
 //
 //   C[b1,b2] (M,N) = alpha * act(A . B^T + bias) (+ res)        (or C += alpha * A.B^T with red.add)
 //
-// One 128 x BN output tile per CTA, K streamed in 64-wide slabs through a STAGES-deep
-// TMA -> mbarrier -> tcgen05.mma pipeline (warp 0 = TMA producer, warp 1 = MMA issuer,
-// warps 2..5 = epilogue, one per TMEM lane quarter).  Both operands may be K-major (row-major
-// (rows,K)) or MN-major (row-major (K,rows)); the difference is only in the TMA box shape, the
-// UMMA shared-memory descriptor (LBO/SBO) and the instruction-descriptor major bits, so backward
-// GEMMs (dgrad: B MN-major, wgrad: A and B MN-major) need no transposed copies.
+// Persistent kernel: one CTA per SM walks the list of (batch, split, m-block, n-block) work units.
+//   warp 0      TMA producer   : K streamed in 64-wide slabs through a STAGES-deep smem ring (runs ahead
+//                                across work units, so short-K problems are not TMA-latency bound)
+//   warp 1      MMA issuer     : tcgen05.mma 128 x BN x 16, fp32 accumulators in TMEM, two accumulator
+//                                buffers (2 x 256 columns) so the epilogue of unit i overlaps the MMAs of i+1
+//   warps 2..9  epilogue       : tcgen05.ld (thread = accumulator row) -> XOR-swizzled shared-memory transpose ->
+//                                column phase (8 lanes per 128 B row segment): + bias (registers), optional
+//                                pre-activation copy (aux), activation, alpha, + residual (coalesced, prefetched)
+//                                -> row-contiguous vector stores; accumulate mode uses red.global.add.v4.f32
+// BN is a run-time value (multiple of 16 up to 256; multiple of 64 when B is MN-major): it only changes the
+// TMA box, the instruction descriptor and the ring stride, so N = 299 runs as 2 x 160 instead of 3 x 128.
+// Both operands may be K-major (row-major (rows,K)) or MN-major (row-major (K,rows)); the difference is only
+// in the TMA box shape, the UMMA shared-memory descriptor (LBO/SBO) and the instruction-descriptor major
+// bits, so backward GEMMs (dgrad: B MN-major, wgrad: A and B MN-major) need no transposed copies.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -17,8 +25,19 @@ namespace lasr {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
-constexpr int GEMM_THREADS = 192;
+constexpr int EPI_WARPS = 8;  // 2 per TMEM lane quarter (and per SM sub-partition): latency hiding for the epilogue
+constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int UMMA_K = 16;
+constexpr int A_BYTES = BM * BK * 2;
+constexpr int MAX_STAGES = 8;
+constexpr int ACC_COLS = 256;  // TMEM columns per accumulator buffer (2 buffers = the whole 512-column TMEM)
+
+// shared-memory carve-up (offsets from the 1024-aligned base)
+constexpr int SM_STAGING = 0;                    // EPI_WARPS x 32 rows x 128 B
+constexpr int SM_BARS = EPI_WARPS * 4096;        // mbarriers + TMEM slot
+constexpr int SM_RING = SM_BARS + 1024;
+constexpr int SM_MAX_DYNAMIC = 232448;   // 227 KB
+constexpr int SM_RING_BUDGET = SM_MAX_DYNAMIC - SM_RING - 1024 /*alignment slack*/;
 
 struct TcParams {
     void* c;
@@ -36,6 +55,9 @@ struct TcParams {
     int accumulate;
     int split_k;
     int vec_ok;
+    int epi_mode;
+    int bn, stages, stage_bytes;
+    int tiles_m, tiles_n, total_units;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -48,6 +70,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
@@ -103,6 +128,9 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void red_add_f32x4(float* p, const float4& v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 
 // UMMA shared-memory descriptor, SWIZZLE_128B (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout (2 = SW128)
@@ -116,97 +144,228 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
     return d;
 }
 
-template <int BN>
-struct TileCfg {
-    static constexpr int A_BYTES = BM * BK * 2;
-    static constexpr int B_BYTES = BN * BK * 2;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+struct Unit {
+    int m0, n0, b1, b2, kb_begin, num_kb;
 };
-
-template <typename CT>
-__device__ __forceinline__ void epilogue_store(const TcParams& p, float* v, long row_off, int m, int nbase) {
-    // v[0..31] are accumulators for columns nbase..nbase+31 of row m
-    CT* crow = reinterpret_cast<CT*>(p.c) + row_off;
-    CT* arow = p.aux ? reinterpret_cast<CT*>(p.aux) + row_off : nullptr;
-    const int nvalid = min(32, p.n - nbase);
-    if (p.accumulate) {
-        float* cf = reinterpret_cast<float*>(p.c) + row_off;
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (j < nvalid) atomicAdd(cf + nbase + j, p.alpha * v[j]);
-        return;
-    }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        float x = v[j];
-        if (p.bias && j < nvalid) x += __ldg(p.bias + nbase + j);
-        v[j] = x;
-    }
-    if (arow) {
-        if (p.vec_ok && nvalid == 32) {
-            if constexpr (sizeof(CT) == 4) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(reinterpret_cast<float*>(arow) + nbase + j) =
-                        make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                    uint4 u;
-                    u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-                    u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-                    *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(arow) + nbase + j) = u;
-                }
-            }
-        } else {
-            for (int j = 0; j < nvalid; ++j) arow[nbase + j] = from_f32<CT>(v[j]);
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = p.alpha * apply_act(v[j], p.act);
-}
-
-template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const TcParams p) {
-    using Cfg = TileCfg<BN>;
-    constexpr int STAGES = Cfg::STAGES;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tmem_full = empty_bar + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-    const int split = blockIdx.z % p.split_k, batch = blockIdx.z / p.split_k;
-    const int b2 = batch % p.batch2, b1 = batch / p.batch2;
+__device__ __forceinline__ Unit decode_unit(const TcParams& p, int u) {
+    Unit w;
+    const int nb = u % p.tiles_n;
+    u /= p.tiles_n;
+    const int mb = u % p.tiles_m;
+    u /= p.tiles_m;
+    const int split = u % p.split_k, batch = u / p.split_k;
+    w.m0 = mb * BM;
+    w.n0 = nb * p.bn;
+    w.b2 = batch % p.batch2;
+    w.b1 = batch / p.batch2;
     const int total_kb = (p.k + BK - 1) / BK;
     const int kb_per = (total_kb + p.split_k - 1) / p.split_k;
-    const int kb_begin = split * kb_per;
-    const int num_kb = min(total_kb, kb_begin + kb_per) - kb_begin;
-    if (num_kb <= 0) return;  // uniform over the CTA (only possible for trailing splits)
+    w.kb_begin = split * kb_per;
+    w.num_kb = min(total_kb, w.kb_begin + kb_per) - w.kb_begin;  // <= 0 only for trailing splits: skipped by every role
+    return w;
+}
+
+// ------------------------------------------------------------------------------------------------
+// epilogue: one warp, one 32-row TMEM lane quarter, every (EPI_WARPS/4)-th 32-column chunk of a work unit
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+// tensor-core path only (bf16 operands): ex2/rcp approximations, ~2 ulp -- far below bf16 resolution
+__device__ __forceinline__ float swish_fast(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+    return x * r;
+}
+__device__ __forceinline__ float act_fast(float x, int act) {
+    if (act == LASR_ACT_RELU) return fmaxf(x, 0.f);
+    if (act == LASR_ACT_SWISH) return swish_fast(x);
+    return x;
+}
+
+// Staging buffer: 32 rows x 128 B of fp32 accumulators; the 16-byte piece `chunk` of row `row` lives at
+// row * 128 + ((chunk ^ (row & 7)) << 4): conflict-free for the row-per-thread writes and the row-contiguous reads.
+template <typename CT>
+__device__ __forceinline__ void store4(CT* dst, const float4& f) {
+    if constexpr (sizeof(CT) == 4) {
+        *reinterpret_cast<float4*>(dst) = f;
+    } else {
+        uint2 u;
+        u.x = pack_bf16x2(f.x, f.y);
+        u.y = pack_bf16x2(f.z, f.w);
+        *reinterpret_cast<uint2*>(dst) = u;
+    }
+}
+
+// Epilogue modes: the column phase is specialised so that its inner loop carries no run-time flag tests.
+enum { EPI_PLAIN = 0, EPI_RELU = 1, EPI_SWISH = 2, EPI_RES = 3, EPI_ACC = 4, EPI_GENERIC = 5 };
+
+template <typename CT, int MODE>
+__device__ __forceinline__ void epilogue_unit(const TcParams& p, const Unit& w, uint32_t tmem_acc, uint8_t* stage, int q, int part,
+                                              int lane) {
+    const long boff = (long)w.b1 * p.sc1 + (long)w.b2 * p.sc2;
+    const int col_limit = min(p.n, w.n0 + p.bn);
+    const int row_base = w.m0 + q * 32;
+    const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
+    const int chunk = lane & 7, rsub = lane >> 3;
+    const int nrows = p.m - row_base - rsub;  // this lane's row 4i + rsub exists iff 4i < nrows
+    const float alpha = p.alpha;
+    CT* cbase = reinterpret_cast<CT*>(p.c) + boff;
+    CT* abase = p.aux ? reinterpret_cast<CT*>(p.aux) + boff : nullptr;
+    const float* rbase = p.res ? p.res + boff : nullptr;
+    uint8_t* wr = stage + lane * 128;
+    const int wx = (lane & 7) << 4;
+    const uint8_t* rd0 = stage + rsub * 128 + ((chunk ^ rsub) << 4);        // rows 4i + rsub, i even
+    const uint8_t* rd1 = stage + rsub * 128 + (((chunk ^ rsub) ^ 4) << 4);  // i odd
+    for (int cc = part * 32; cc < p.bn; cc += 32 * (EPI_WARPS / 4)) {
+        const int col = w.n0 + cc + chunk * 4;  // this lane's 4 columns in the column phase
+        if (w.n0 + cc >= col_limit) break;      // warp-uniform
+        const bool fast = (MODE != EPI_GENERIC) && p.vec_ok && (w.n0 + cc + 32 <= col_limit);
+        // prefetch what the column phase needs from global memory before touching TMEM
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 r4[8];
+        if (fast) {
+            if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+            if constexpr (MODE == EPI_RES) {
+                const float* rp = rbase + (long)(row_base + rsub) * p.ldres + col;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    r4[i] = (4 * i < nrows) ? *reinterpret_cast<const float4*>(rp + (long)(4 * i) * p.ldres) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        } else if (p.bias) {
+            b4.x = (col + 0 < col_limit) ? __ldg(p.bias + col + 0) : 0.f;
+            b4.y = (col + 1 < col_limit) ? __ldg(p.bias + col + 1) : 0.f;
+            b4.z = (col + 2 < col_limit) ? __ldg(p.bias + col + 2) : 0.f;
+            b4.w = (col + 3 < col_limit) ? __ldg(p.bias + col + 3) : 0.f;
+        }
+        // row phase: thread = accumulator row
+        {
+            float v[32];
+            tc_ld32(taddr + (uint32_t)cc, v);
+            __syncwarp();  // the previous chunk's column phase has finished reading the staging buffer
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(wr + ((j << 4) ^ wx)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        __syncwarp();
+        // column phase: 8 lanes cover one 128-byte row segment, 4 rows per instruction
+        if (fast) {
+            const long off0 = (long)(row_base + rsub) * p.ldc + col;
+            CT* crow = cbase + off0;
+            CT* arow = abase ? abase + off0 : nullptr;
+            const long rstride = 4 * p.ldc;
+            float4 ba = b4;
+            if constexpr (MODE == EPI_PLAIN || MODE == EPI_RES) { ba.x *= alpha; ba.y *= alpha; ba.z *= alpha; ba.w *= alpha; }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float4 f = *reinterpret_cast<const float4*>(((i & 1) ? rd1 : rd0) + i * 512);
+                if (4 * i < nrows) {
+                    if constexpr (MODE == EPI_PLAIN) {
+                        f.x = fmaf(f.x, alpha, ba.x); f.y = fmaf(f.y, alpha, ba.y); f.z = fmaf(f.z, alpha, ba.z); f.w = fmaf(f.w, alpha, ba.w);
+                        store4<CT>(crow, f);
+                    } else if constexpr (MODE == EPI_RES) {
+                        f.x = fmaf(f.x, alpha, ba.x) + r4[i].x; f.y = fmaf(f.y, alpha, ba.y) + r4[i].y;
+                        f.z = fmaf(f.z, alpha, ba.z) + r4[i].z; f.w = fmaf(f.w, alpha, ba.w) + r4[i].w;
+                        store4<CT>(crow, f);
+                    } else if constexpr (MODE == EPI_ACC) {
+                        f.x *= alpha; f.y *= alpha; f.z *= alpha; f.w *= alpha;
+                        red_add_f32x4(reinterpret_cast<float*>(crow), f);
+                    } else {  // EPI_RELU / EPI_SWISH (+ optional pre-activation copy)
+                        f.x += b4.x; f.y += b4.y; f.z += b4.z; f.w += b4.w;
+                        if (arow) store4<CT>(arow, f);
+                        if constexpr (MODE == EPI_RELU) {
+                            f.x = alpha * fmaxf(f.x, 0.f); f.y = alpha * fmaxf(f.y, 0.f); f.z = alpha * fmaxf(f.z, 0.f); f.w = alpha * fmaxf(f.w, 0.f);
+                        } else {
+                            f.x = alpha * swish_fast(f.x); f.y = alpha * swish_fast(f.y); f.z = alpha * swish_fast(f.z); f.w = alpha * swish_fast(f.w);
+                        }
+                        store4<CT>(crow, f);
+                    }
+                }
+                crow += rstride;
+                if (arow) arow += rstride;
+            }
+        } else {  // ragged N edge, unaligned C or an unusual flag combination: element-wise, compact (not unrolled)
+#pragma unroll 1
+            for (int i = 0; i < 8; ++i) {
+                const int row = 4 * i + rsub;
+                const int grow = row_base + row;
+                const float4 f4 = *reinterpret_cast<const float4*>(stage + row * 128 + ((chunk ^ (row & 7)) << 4));
+                const float f[4] = {f4.x + b4.x, f4.y + b4.y, f4.z + b4.z, f4.w + b4.w};
+                if (grow >= p.m) continue;
+#pragma unroll 1
+                for (int e = 0; e < 4; ++e) {
+                    if (col + e >= col_limit) break;
+                    const long off = (long)grow * p.ldc + col + e;
+                    if (p.accumulate) {
+                        atomicAdd(reinterpret_cast<float*>(cbase + off), alpha * f[e]);
+                    } else {
+                        if (abase) abase[off] = from_f32<CT>(f[e]);
+                        float x = alpha * act_fast(f[e], p.act);
+                        if (rbase) x += rbase[(long)grow * p.ldres + col + e];
+                        cbase[off] = from_f32<CT>(x);
+                    }
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void epilogue_dispatch(const TcParams& p, const Unit& w, uint32_t tmem_acc, uint8_t* stage, int q, int part,
+                                                  int lane) {
+    if (p.c_dtype == LASR_F32) {
+        switch (p.epi_mode) {
+            case EPI_PLAIN: epilogue_unit<float, EPI_PLAIN>(p, w, tmem_acc, stage, q, part, lane); break;
+            case EPI_RELU: epilogue_unit<float, EPI_RELU>(p, w, tmem_acc, stage, q, part, lane); break;
+            case EPI_SWISH: epilogue_unit<float, EPI_SWISH>(p, w, tmem_acc, stage, q, part, lane); break;
+            case EPI_RES: epilogue_unit<float, EPI_RES>(p, w, tmem_acc, stage, q, part, lane); break;
+            case EPI_ACC: epilogue_unit<float, EPI_ACC>(p, w, tmem_acc, stage, q, part, lane); break;
+            default: epilogue_unit<float, EPI_GENERIC>(p, w, tmem_acc, stage, q, part, lane); break;
+        }
+    } else {
+        switch (p.epi_mode) {
+            case EPI_PLAIN: epilogue_unit<bf16, EPI_PLAIN>(p, w, tmem_acc, stage, q, part, lane); break;
+            case EPI_RELU: epilogue_unit<bf16, EPI_RELU>(p, w, tmem_acc, stage, q, part, lane); break;
+            case EPI_SWISH: epilogue_unit<bf16, EPI_SWISH>(p, w, tmem_acc, stage, q, part, lane); break;
+            default: epilogue_unit<bf16, EPI_GENERIC>(p, w, tmem_acc, stage, q, part, lane); break;
+        }
+    }
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    // align inside the shared window (keeps the address space visible to the compiler: LDS/STS, not generic LD/ST)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM_BARS);
+    uint64_t* empty_bar = full_bar + MAX_STAGES;
+    uint64_t* acc_full = empty_bar + MAX_STAGES;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint8_t* ring = smem + SM_RING;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tma_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tma_b) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < MAX_STAGES; ++s) {
             mbar_init(full_bar + s, 1);
             mbar_init(empty_bar + s, 1);
         }
-        mbar_init(tmem_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(acc_full + s, 1);
+            mbar_init(acc_empty + s, EPI_WARPS);  // one arrival per epilogue warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"((uint32_t)BN)
+                     "r"((uint32_t)(2 * ACC_COLS))
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -217,116 +376,93 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
     if (warp == 0) {
         if (lane == 0) {
-            const int ab1 = b1 * p.a_b1, ab2 = b2 * p.a_b2, bb1 = b1 * p.b_b1, bb2 = b2 * p.b_b2;
-            for (int i = 0; i < num_kb; ++i) {
-                const int s = i % STAGES;
-                const uint32_t ph = (i / STAGES) & 1;
-                mbar_wait(empty_bar + s, ph ^ 1);
-                mbar_arrive_expect_tx(full_bar + s, Cfg::STAGE_BYTES);
-                uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
-                uint8_t* sb = sa + Cfg::A_BYTES;
-                const int k0 = (kb_begin + i) * BK;
-                if constexpr (!A_MN) {
-                    tma_load_4d(sa, &tma_a, full_bar + s, k0, m0, ab2, ab1);  // box {64 k, 128 m}
-                } else {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+                const Unit w = decode_unit(p, u);
+                if (w.num_kb <= 0) continue;
+                const int ab1 = w.b1 * p.a_b1, ab2 = w.b2 * p.a_b2, bb1 = w.b1 * p.b_b1, bb2 = w.b2 * p.b_b2;
+                for (int i = 0; i < w.num_kb; ++i) {
+                    mbar_wait(empty_bar + s, ph ^ 1);
+                    mbar_arrive_expect_tx(full_bar + s, (uint32_t)p.stage_bytes);
+                    uint8_t* sa = ring + s * p.stage_bytes;
+                    uint8_t* sb = sa + A_BYTES;
+                    const int k0 = (w.kb_begin + i) * BK;
+                    if constexpr (!A_MN) {
+                        tma_load_4d(sa, &tma_a, full_bar + s, k0, w.m0, ab2, ab1);  // box {64 k, 128 m}
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < BM / 64; ++j)  // box {64 m, 64 k}
-                        tma_load_4d(sa + j * 8192, &tma_a, full_bar + s, m0 + 64 * j, k0, ab2, ab1);
-                }
-                if constexpr (!B_MN) {
-                    tma_load_4d(sb, &tma_b, full_bar + s, k0, n0, bb2, bb1);  // box {64 k, BN n}
-                } else {
-#pragma unroll
-                    for (int j = 0; j < BN / 64; ++j)
-                        tma_load_4d(sb + j * 8192, &tma_b, full_bar + s, n0 + 64 * j, k0, bb2, bb1);
+                        for (int j = 0; j < BM / 64; ++j)  // box {64 m, 64 k}
+                            tma_load_4d(sa + j * 8192, &tma_a, full_bar + s, w.m0 + 64 * j, k0, ab2, ab1);
+                    }
+                    if constexpr (!B_MN) {
+                        tma_load_4d(sb, &tma_b, full_bar + s, k0, w.n0, bb2, bb1);  // box {64 k, BN n}
+                    } else {
+                        for (int j = 0; j < p.bn / 64; ++j)
+                            tma_load_4d(sb + j * 8192, &tma_b, full_bar + s, w.n0 + 64 * j, k0, bb2, bb1);
+                    }
+                    if (++s == p.stages) { s = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32, a=b=bf16, majors, N>>3, M>>4
-            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
-                                       ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-            for (int i = 0; i < num_kb; ++i) {
-                const int s = i % STAGES;
-                const uint32_t ph = (i / STAGES) & 1;
-                mbar_wait(full_bar + s, ph);
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                                   ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            int s = 0, as = 0;
+            uint32_t ph = 0, aph = 0;
+            for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+                const Unit w = decode_unit(p, u);
+                if (w.num_kb <= 0) continue;
+                mbar_wait(acc_empty + as, aph ^ 1);  // the epilogue has drained this accumulator buffer
                 tc_fence_after();
-                const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
-                const uint32_t sb = sa + Cfg::A_BYTES;
+                const uint32_t tmem_d = tmem_base + (uint32_t)(as * ACC_COLS);
+                for (int i = 0; i < w.num_kb; ++i) {
+                    mbar_wait(full_bar + s, ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(ring + s * p.stage_bytes);
+                    const uint32_t sb = sa + A_BYTES;
 #pragma unroll
-                for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-                    // K-major: +32 B per UMMA_K inside the 128 B swizzle row; SBO = 8 rows * 128 B.
-                    // MN-major: +16 K-rows * 128 B; LBO = next 64-wide MN atom (64 K-rows * 128 B), SBO = 8 K-rows.
-                    const uint64_t da = A_MN ? umma_desc(sa + kk * 2048, 8192, 1024) : umma_desc(sa + kk * 32, 16, 1024);
-                    const uint64_t db = B_MN ? umma_desc(sb + kk * 2048, 8192, 1024) : umma_desc(sb + kk * 32, 16, 1024);
-                    tc_mma_bf16(tmem_base, da, db, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+                    for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                        // K-major: +32 B per UMMA_K inside the 128 B swizzle row; SBO = 8 rows * 128 B.
+                        // MN-major: +16 K-rows * 128 B; LBO = next 64-wide MN atom (64 K-rows * 128 B), SBO = 8 K-rows.
+                        const uint64_t da = A_MN ? umma_desc(sa + kk * 2048, 8192, 1024) : umma_desc(sa + kk * 32, 16, 1024);
+                        const uint64_t db = B_MN ? umma_desc(sb + kk * 2048, 8192, 1024) : umma_desc(sb + kk * 32, 16, 1024);
+                        tc_mma_bf16(tmem_d, da, db, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+                    }
+                    tc_commit(empty_bar + s);  // frees the smem slot once these MMAs retire
+                    if (++s == p.stages) { s = 0; ph ^= 1; }
                 }
-                tc_commit(empty_bar + s);  // frees the smem slot once these MMAs retire
+                tc_commit(acc_full + as);
+                if ((as ^= 1) == 0) aph ^= 1;
             }
-            tc_commit(tmem_full);
         }
     } else {
-        mbar_wait(tmem_full, 0);
-        tc_fence_after();
-        const int q = warp & 3;  // TMEM lane quarter this warp may access
-        const int m = m0 + q * 32 + lane;
-        const long boff = (long)b1 * p.sc1 + (long)b2 * p.sc2;
-        const long row_off = boff + (long)m * p.ldc;
-        const long res_off = boff + (long)m * p.ldres;
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            const int nbase = n0 + c0;
-            if (nbase >= p.n) break;
-            float v[32];
-            tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            if (m >= p.m) continue;
-            const int nvalid = min(32, p.n - nbase);
-            if (p.c_dtype == LASR_F32) epilogue_store<float>(p, v, row_off, m, nbase);
-            else epilogue_store<bf16>(p, v, row_off, m, nbase);
-            if (p.accumulate) continue;
-            if (p.res) {
-                const float* rr = p.res + res_off + nbase;
-                if (p.vec_ok && nvalid == 32) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 r4 = *reinterpret_cast<const float4*>(rr + j);
-                        v[j] += r4.x; v[j + 1] += r4.y; v[j + 2] += r4.z; v[j + 3] += r4.w;
-                    }
-                } else {
-                    for (int j = 0; j < nvalid; ++j) v[j] += rr[j];
-                }
-            }
-            if (p.c_dtype == LASR_F32) {
-                float* cr = reinterpret_cast<float*>(p.c) + row_off + nbase;
-                if (p.vec_ok && nvalid == 32) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(cr + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                } else {
-                    for (int j = 0; j < nvalid; ++j) cr[j] = v[j];
-                }
-            } else {
-                bf16* cr = reinterpret_cast<bf16*>(p.c) + row_off + nbase;
-                if (p.vec_ok && nvalid == 32) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                        uint4 u;
-                        u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-                        u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-                        *reinterpret_cast<uint4*>(cr + j) = u;
-                    }
-                } else {
-                    for (int j = 0; j < nvalid; ++j) cr[j] = __float2bfloat16_rn(v[j]);
-                }
-            }
+        const int q = warp & 3;           // TMEM lane quarter this warp may access
+        const int ew = warp - 2;          // private staging slice
+        const int part = ew >> 2;         // which 32-column chunks of the tile (chunk index % (EPI_WARPS/4))
+        uint8_t* stage = smem + SM_STAGING + ew * 4096;
+        int as = 0;
+        uint32_t aph = 0;
+        for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+            const Unit w = decode_unit(p, u);
+            if (w.num_kb <= 0) continue;
+            mbar_wait(acc_full + as, aph);
+            tc_fence_after();
+            const uint32_t tmem_acc = tmem_base + (uint32_t)(as * ACC_COLS);
+            epilogue_dispatch(p, w, tmem_acc, stage, q, part, lane);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + as);
+            if ((as ^= 1) == 0) aph ^= 1;
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 2) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * ACC_COLS))
+                     : "memory");
     }
 }
 
@@ -343,6 +479,16 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
             fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
     }
     return fn;
+}
+
+static int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
 }
 
 // operand stored row-major as (outer rows, inner contiguous) with row stride ld (elements), two batch levels.
@@ -373,23 +519,36 @@ static int make_map(CUtensorMap* map, const void* base, long inner, long rows, l
     return LASR_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN>
-static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, int nbatch, cudaStream_t st) {
-    using Cfg = TileCfg<BN>;
-    auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
+// N-tile width: a multiple of `gran` (16 for K-major B, 64 for MN-major B) up to 256 that wastes the fewest padded
+// columns; ties go to the wider tile (fewer A re-reads, fewer epilogue tails).
+static int pick_bn(int n, int gran) {
+    if (n <= 256) return (n + gran - 1) / gran * gran;
+    int best = 256;
+    long best_pad = (long)((n + 255) / 256) * 256;
+    for (int bn = 256 - gran; bn >= 128; bn -= gran) {
+        const long pad = (long)((n + bn - 1) / bn) * bn;
+        if (pad < best_pad) { best = bn; best_pad = pad; }
+    }
+    return best;
+}
+
+template <bool A_MN, bool B_MN>
+static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st) {
+    auto kern = gemm_tc_kernel<A_MN, B_MN>;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_MAX_DYNAMIC) != cudaSuccess)
             return check_launch("gemm_tc smem attr");
         configured = true;
     }
-    dim3 grid(ceil_div(p.m, BM), ceil_div(p.n, BN), nbatch * p.split_k);
-    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ma, mb, p);
+    const int smem_bytes = SM_RING + p.stages * p.stage_bytes + 1024;
+    const int grid = p.total_units < sm_count() ? p.total_units : sm_count();
+    kern<<<grid, GEMM_THREADS, smem_bytes, st>>>(ma, mb, p);
     return check_launch("gemm_tc");
 }
 
 int gemm_tc_dispatch(const lasr_gemm_args* a, cudaStream_t st) {
-    const int bn = (a->n > 128 && (a->n % 256 == 0 || a->n > 512)) ? 256 : (a->n > 64 ? 128 : 64);
+    const int bn = pick_bn(a->n, a->trans_b ? 64 : 16);
     CUtensorMap ma, mb;
     int rc;
     if (!a->trans_a) rc = make_map(&ma, a->a, a->k, a->m, a->lda, a->batch2, a->sa2, a->batch1, a->sa1, BK, BM);
@@ -398,6 +557,10 @@ int gemm_tc_dispatch(const lasr_gemm_args* a, cudaStream_t st) {
     if (!a->trans_b) rc = make_map(&mb, a->b, a->k, a->n, a->ldb, a->batch2, a->sb2, a->batch1, a->sb1, BK, bn);
     else rc = make_map(&mb, a->b, a->n, a->k, a->ldb, a->batch2, a->sb2, a->batch1, a->sb1, 64, BK);
     if (rc) return rc;
+    if (a->res && a->c_dtype != LASR_F32) {
+        set_error("gemm_tc: a residual needs an fp32 C");
+        return LASR_ERR_UNSUPPORTED;
+    }
 
     TcParams p;
     p.c = a->c; p.bias = a->bias; p.res = a->res; p.aux = a->aux;
@@ -410,22 +573,31 @@ int gemm_tc_dispatch(const lasr_gemm_args* a, cudaStream_t st) {
     auto al16 = [&](long elems, long es) { return ((elems * es) & 15) == 0; };
     p.vec_ok = ((reinterpret_cast<uintptr_t>(a->c) & 15) == 0) && al16(a->ldc, esz) && al16(a->sc1, esz) && al16(a->sc2, esz);
     if (a->aux) p.vec_ok = p.vec_ok && ((reinterpret_cast<uintptr_t>(a->aux) & 15) == 0);
-    if (a->res) p.vec_ok = p.vec_ok && ((reinterpret_cast<uintptr_t>(a->res) & 15) == 0) && al16(a->ldres, 4) && al16(a->sc1, 4) && al16(a->sc2, 4);
-    const int nb = a->batch1 * a->batch2;
-
-#define LASR_TC_CASE(BN_)                                                                     \
-    if (bn == BN_) {                                                                          \
-        if (!a->trans_a && !a->trans_b) return launch_tc<BN_, false, false>(ma, mb, p, nb, st); \
-        if (!a->trans_a && a->trans_b) return launch_tc<BN_, false, true>(ma, mb, p, nb, st);   \
-        if (a->trans_a && !a->trans_b) return launch_tc<BN_, true, false>(ma, mb, p, nb, st);   \
-        return launch_tc<BN_, true, true>(ma, mb, p, nb, st);                                 \
+    if (a->bias) p.vec_ok = p.vec_ok && ((reinterpret_cast<uintptr_t>(a->bias) & 15) == 0);
+    if (a->res) p.vec_ok = p.vec_ok && ((reinterpret_cast<uintptr_t>(a->res) & 15) == 0) && al16(a->ldres, 4);
+    if (a->accumulate) p.epi_mode = EPI_ACC;
+    else if (a->res && a->act == LASR_ACT_NONE && !a->aux) p.epi_mode = EPI_RES;
+    else if (!a->res && a->act == LASR_ACT_RELU) p.epi_mode = EPI_RELU;
+    else if (!a->res && a->act == LASR_ACT_SWISH) p.epi_mode = EPI_SWISH;
+    else if (!a->res && !a->aux && a->act == LASR_ACT_NONE) p.epi_mode = EPI_PLAIN;
+    else p.epi_mode = EPI_GENERIC;
+    p.bn = bn;
+    p.stage_bytes = A_BYTES + bn * BK * 2;
+    p.stages = SM_RING_BUDGET / p.stage_bytes;
+    if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+    p.tiles_m = ceil_div(a->m, BM);
+    p.tiles_n = ceil_div(a->n, bn);
+    const long units = (long)p.tiles_m * p.tiles_n * p.split_k * a->batch1 * a->batch2;
+    if (units > 0x7fffffffL) {
+        set_error("gemm_tc: too many work units");
+        return LASR_ERR_UNSUPPORTED;
     }
-    LASR_TC_CASE(64)
-    LASR_TC_CASE(128)
-    LASR_TC_CASE(256)
-#undef LASR_TC_CASE
-    set_error("gemm_tc: no tile config");
-    return LASR_ERR_UNSUPPORTED;
+    p.total_units = (int)units;
+
+    if (!a->trans_a && !a->trans_b) return launch_tc<false, false>(ma, mb, p, st);
+    if (!a->trans_a && a->trans_b) return launch_tc<false, true>(ma, mb, p, st);
+    if (a->trans_a && !a->trans_b) return launch_tc<true, false>(ma, mb, p, st);
+    return launch_tc<true, true>(ma, mb, p, st);
 }
 
 }  // namespace lasr

@@ -47,9 +47,10 @@ def test_gemm_epilogue_bias_act_res_aux(dtype):
         for cdt in ([torch.float32, torch.bfloat16] if dtype == torch.bfloat16 else [torch.float32]):
             out = torch.empty(m, n, device="cuda", dtype=cdt)
             aux = torch.empty(m, n, device="cuda", dtype=cdt)
-            ops.linear(x, w, out, bias=bias, res=res, aux=aux, alpha=0.5, act=act)
+            r = res if cdt == torch.float32 else None  # the residual stream is fp32: a residual needs an fp32 C
+            ops.linear(x, w, out, bias=bias, res=r, aux=aux, alpha=0.5, act=act)
             pre = x.float() @ w.float().t() + bias
-            ref = 0.5 * fn(pre) + res
+            ref = 0.5 * fn(pre) + (res if r is not None else 0.0)
             tol = 3e-2 if (dtype == torch.bfloat16 or cdt == torch.bfloat16) else 1e-4
             assert (out.float() - ref).abs().max().item() <= tol * ref.abs().max().item()
             assert (aux.float() - pre).abs().max().item() <= tol * pre.abs().max().item()
@@ -104,6 +105,39 @@ def test_gemm_wgrad_split_k(dtype):
     ref = 2.0 * dy.float().t() @ x.float()
     tol = 2e-2 if dtype == torch.bfloat16 else 2e-4
     assert (dw - ref).abs().max().item() <= tol * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("cdt", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("m,n,k,tb", [(9568, 299, 64, False), (1000, 4233, 256, False), (2000, 4233, 320, True), (5000, 2048, 256, False),
+                                      (41, 299, 64, False), (777, 152, 192, False), (640, 72, 128, True)])
+def test_gemm_persistent_tiles_and_tails(cdt, m, n, k, tb):
+    """More work units than SMs (persistent loop + both TMEM accumulator buffers), run-time BN, ragged N with a padded ld."""
+    from liteasr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(m + n + k)
+    a = _mk(m, k, torch.bfloat16, g)
+    b = _mk(k, n, torch.bfloat16, g) if tb else _mk(n, k, torch.bfloat16, g)
+    bias = torch.randn(n, generator=g, device="cuda")
+    ld = (n + 7) // 8 * 8
+    buf = torch.full((m, ld), 7.0, device="cuda", dtype=cdt)
+    ops.gemm(a, b, buf[:, :n], m, n, k, lda=a.stride(0), ldb=b.stride(0), ldc=ld, tb=tb, bias=bias, act=ops.ACT_RELU)
+    ref = torch.relu(_ref(a, b, False, tb) + bias)
+    assert (buf[:, :n].float() - ref).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item())
+    assert (buf[:, n:] == 7.0).all()  # padding columns untouched
+
+
+def test_gemm_many_small_batches_short_k():
+    """Attention-score shape: 128 batches x (299 x 299 x 64) -> thousands of one-k-block work units."""
+    from liteasr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    B, H, T, dk, ld = 8, 4, 299, 64, 304
+    d = H * dk
+    q = (torch.randn(B, T, H, dk, generator=g, device="cuda") * 0.3).to(torch.bfloat16)
+    kk = (torch.randn(B, T, H, dk, generator=g, device="cuda") * 0.3).to(torch.bfloat16)
+    c = torch.zeros(B, H, T, ld, device="cuda")
+    ops.gemm(q, kk, c, T, T, dk, lda=d, ldb=d, ldc=ld, batch=(B, H), sa=(T * d, dk), sb=(T * d, dk), sc=(H * T * ld, T * ld))
+    ref = torch.einsum("bihd,bjhd->bhij", q.float(), kk.float())
+    assert (c[..., :T] - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
+    assert (c[..., T:] == 0).all()
 
 
 def test_gemm_bad_args_raise():
