@@ -66,6 +66,10 @@ class Engine:
                           self.st.g(ln.pfx + ".bias"), accumulate)
 
     def _split_k(self, n_out: int, k_out: int, rows: int) -> int:
+        if self.adt == torch.float32:
+            # parity mode: keep every sequential fp32 accumulation chain <= 512 terms (the partial sums meet through
+            # red.add), so weight gradients reduced over 1e4-1e5 rows stay within ~1e-6 of a float64 sum
+            return max(1, min(64, rows // 512))
         tiles = ((n_out + 127) // 128) * ((k_out + 127) // 128)
         s = max(1, min(32, 148 // max(1, tiles)))
         s = min(s, max(1, rows // 256))

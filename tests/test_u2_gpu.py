@@ -104,9 +104,11 @@ def test_public_forward_and_generic_criterion_path_fp32():
     loss = crit.loss_from_logits(model, h_attn, h_ctc, xlens, ys, ylens)
     assert math.isclose(float(loss), float(out["loss"]), rel_tol=1e-5)
     loss.backward()
+    gmax = max(float(p.grad.abs().max()) for p in sd64.values() if getattr(p, "grad", None) is not None)
     for n, p in model.named_parameters():
         r, m, bmax = _rel(p.grad, sd64[n].grad)
-        assert m <= 1e-4 * max(bmax, 1e-6), (n, r, m)
+        # identically-zero true gradients (key-projection biases: softmax shift invariance) are judged against max|g| overall
+        assert m <= 1e-4 * max(bmax, 1e-3 * gmax), (n, r, m)
     tgt_attn, tgt_ctc = model.get_target(ys, ylens)
     from oracle import u2_oracle as O
     assert torch.equal(tgt_attn.cpu(), O.attention_targets(batch[2], batch[3], dims.vocab_size))

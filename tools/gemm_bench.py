@@ -19,14 +19,27 @@ def rnd(*shape, dtype=bf):
     return (torch.randn(*shape, device=dev) * 0.1).to(dtype)
 
 
+USE_GRAPH = True
+
+
 def run(name, fn, flops, nbytes, iters=20):
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
+    if USE_GRAPH:  # GPU time only: the Python/ctypes launch path costs ~15 us per call, more than the small GEMMs
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(iters):
+                fn()
+        g.replay()
+        torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(iters):
-        fn()
+    if USE_GRAPH:
+        g.replay()
+    else:
+        for _ in range(iters):
+            fn()
     e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / iters * 1e3
@@ -87,4 +100,8 @@ def main(cases):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1:])
+    args = sys.argv[1:]
+    if "--eager" in args:
+        USE_GRAPH = False
+        args.remove("--eager")
+    main(args)
