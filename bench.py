@@ -336,10 +336,14 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override (0 = the workload's default)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload])
+    if args.batch > 0:
+        wl["desc"] = wl["desc"].replace(f"per-GPU batch {wl['batch']}", f"per-GPU batch {args.batch}").replace(f"batch {wl['batch']},", f"batch {args.batch},")
+        wl["batch"] = args.batch
     if args.impl == "reference":
         run_reference(args, wl)
     else:

@@ -1,8 +1,8 @@
 // fp32 SIMT GEMM ("fp32 parity mode"): same contract as the tcgen05 kernel, arbitrary strides.
 //   C[b1,b2] (M,N) = alpha * act(A . B^T + bias) (+ res)     or   C += alpha * A.B^T (atomics)
 // 64x64 tile, BK = 16, 256 threads x (4x4) register micro-tile, smem double-buffer-free classic loop.
-// Not a roofline kernel: it exists so fp32 runs (loss/grad parity, bit-exact greedy CTC) use true
-// fp32 FMA accumulation like the reference's torch fp32 path.
+// Not a roofline kernel: it exists so fp32 runs (loss/grad parity, bit-exact greedy CTC) see fp32 operands and
+// fp32 results like the reference's torch fp32 path (dot products are accumulated in fp64 and rounded once).
 #include "common.cuh"
 
 namespace lasr {
@@ -39,7 +39,9 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams p) {
     if (kbeg >= kend) return;
 
     const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, each 4x4
-    float acc[4][4] = {};
+    // products of two fp32 values are exact in fp64; accumulating there makes every output a correctly rounded fp32 dot
+    // product, so ReLU masks / argmax decisions flip no more often than in an fp64 run (this kernel is the parity mode)
+    double acc[4][4] = {};
     // loader mapping: choose the index that walks the contiguous dimension fastest
     const bool a_kfast = (p.sak == 1), b_kfast = (p.sbk == 1);
     for (int k0 = kbeg; k0 < kend; k0 += SBK) {
@@ -70,7 +72,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams p) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma((double)av[i], (double)bv[j], acc[i][j]);
         }
         __syncthreads();
     }
@@ -85,10 +87,10 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams p) {
             if (n >= p.n) continue;
             const long off = boff + (long)m * p.ldc + n;
             if (p.accumulate) {
-                atomicAdd(p.c + off, p.alpha * acc[i][j]);
+                atomicAdd(p.c + off, p.alpha * (float)acc[i][j]);
                 continue;
             }
-            float v = acc[i][j];
+            float v = (float)acc[i][j];
             if (p.bias) v += p.bias[n];
             if (p.aux) p.aux[off] = v;
             v = p.alpha * apply_act(v, p.act);

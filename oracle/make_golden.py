@@ -64,6 +64,7 @@ def run_model_case(name):
     sd = synth_state_dict(dims, seed=seed)
     out = dict(case=name, dims=dims.__dict__, batch=b, tmax=tmax, lmax=lmax, ctc_weight=w, smoothing=eps, seed=seed,
                xlens=xlens.tolist(), ylens=ylens.tolist())
+    g64 = {}
     for dtype, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
         model, crit = ref_shims.build_reference(dims.__dict__, eps, w)
         model.load_state_dict(sd, strict=True)
@@ -72,7 +73,12 @@ def run_model_case(name):
         loss = crit(model, xs.to(dtype), xlens, ys, ylens)
         loss.backward()
         rec = dict(loss=float(loss))
+        if tag == "f32":
+            # the reference's OWN fp32 deviation from its fp64 run, per parameter (max-abs): fp32 ReLU/argmax flips and
+            # summation order put a floor under any fp32 implementation's distance to the fp64 truth
+            rec["grad_maxabs_err_vs_f64"] = {k: float((p.grad.double() - g64[k]).abs().max()) for k, p in model.named_parameters()}
         if tag == "f64":
+            g64 = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
             # recompute pieces for the record
             with torch.no_grad():
                 model2, _ = ref_shims.build_reference(dims.__dict__, eps, w)
