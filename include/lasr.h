@@ -57,7 +57,7 @@ unsigned long long lasr_launch_count(void); /* kernels launched by this library 
  *   (B,T,H,dk) tensors are addressed in place (stride 0 broadcasts an operand).
  *   aux (optional, C dtype/ldc): receives the pre-activation value (acc + bias).
  *   accumulate = 1: C (fp32) += alpha * A.B^T with red.global.add (split-K and batch-reduce wgrads);
- *                   bias/act/res/aux must be unset; a C batch stride of 0 reduces over that batch level.
+ *                   bias/act/res/aux/dact/colsum must be unset; a C batch stride of 0 reduces over that batch level.
  * ------------------------------------------------------------------------------------------------ */
 typedef struct lasr_gemm_args {
     const void* a;
@@ -76,6 +76,16 @@ typedef struct lasr_gemm_args {
     int32_t act;
     int32_t accumulate;
     int32_t split_k; /* >= 1; > 1 requires accumulate */
+    /* backward-fusion extras (all optional):
+     *   dact  : saved tensor of the forward activation (operand dtype, addressed like C with row stride lddact):
+     *           C = alpha * (A.B^T) * act'(dact), act' = swish'(pre-activation) | relu'(activation output);
+     *           replaces the separate activation-backward pass of nets/feed_forward.py:18-19; no bias/res/aux.
+     *   colsum: fp32 vector, colsum[b1*cs1 + b2*cs2 + n] += sum_m C[m,n] (red.add): the bias gradient of the
+     *           nn.Linear that produced this GEMM's A-side gradient, without re-reading C. */
+    const void* dact;
+    int64_t lddact;
+    float* colsum;
+    int64_t cs1, cs2;
 } lasr_gemm_args;
 
 int lasr_gemm(const lasr_gemm_args* args, void* stream);
@@ -102,13 +112,16 @@ int lasr_ctc_fwdbwd(const void* logits, int dtype, int64_t st, int64_t sb, const
  *   fwd: y = (x - mean) * rstd * gamma + beta; x fp32 (rows,d) row stride ldx; y fp32|bf16.
  *   bwd: dx (+)= LN'(dy) (accumulate = 1 adds into dx: the residual-stream gradient);
  *        dgamma/dbeta are ACCUMULATED (red.add) into the caller's (pre-zeroed) gradient buffers.
- * d % 4 == 0, d <= 1024.
+ *        Optional fused outputs (NULL to skip): dx_lo = bf16 copy of the final dx (operand of the next block's
+ *        backward GEMMs); colsum[d] += colsum_scale * sum_rows dx (bias gradient of the Linear feeding this residual).
+ * d % 4 == 0, d <= 1024; dgamma/dbeta/colsum 16-byte aligned.
  * ------------------------------------------------------------------------------------------------ */
 int lasr_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, void* y, int y_dtype,
                        int64_t ldy, float* mean, float* rstd, int rows, int d, float eps, void* stream);
 int lasr_layernorm_bwd(const void* dy, int dy_dtype, int64_t lddy, const float* x, int64_t ldx, const float* mean,
                        const float* rstd, const float* gamma, float* dx, int64_t lddx, int accumulate, float* dgamma,
-                       float* dbeta, int rows, int d, void* stream);
+                       float* dbeta, int rows, int d, void* dx_lo, int64_t lddxlo, float* colsum, float colsum_scale,
+                       void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Casts / relayouts (weights fp32 master -> bf16 operand copies; conv weight permutations and the
@@ -125,11 +138,11 @@ int lasr_act_bwd(const void* da, int64_t ldda, const void* saved, int64_t lds, v
                  int cols, int act, float scale, int dtype, void* stream);
 
 /* q + pos_bias_u, q + pos_bias_v (nets/attention.py:135-139) and the backward
- * (dq = dqu + dqv, du += colsum(dqu), dv += colsum(dqv)). */
+ * (dq = dqu + dqv, du += colsum(dqu), dv += colsum(dqv), optional dqbias += colsum(dq): linear_q's bias gradient). */
 int lasr_pos_bias_fwd(const void* q, int64_t ldq, const float* u, const float* v, void* qu, void* qv, int64_t ldo, int rows,
                       int d, int dtype, void* stream);
-int lasr_pos_bias_bwd(const void* dqu, const void* dqv, int64_t ldi, void* dq, int64_t ldq, float* du, float* dv, int rows, int d,
-                      int dtype, void* stream);
+int lasr_pos_bias_bwd(const void* dqu, const void* dqv, int64_t ldi, void* dq, int64_t ldq, float* du, float* dv, float* dqbias,
+                      int rows, int d, int dtype, void* stream);
 
 /* Decoder input embedding: out[b,l] = emb[tokens[b,l]] * scale + pe[l] (nets/transformer_decoder.py:77-78,
  * nets/positional_encoding.py:49-56); backward scatter-adds scale*dout into demb (red.add). */
@@ -149,7 +162,8 @@ int lasr_scale_by_scalar(void* x, int dtype, int64_t n, const float* scalar, voi
  *                running-stat update (momentum, unbiased var, num_batches_tracked += 1);
  *                training=0 -> mean/rstd from the running statistics.
  *   bwd_stats : partial (ceil(rows/32)*2*d) -> sums[0:d] = sum du, sums[d:2d] = sum du*zhat; dgamma/dbeta +=
- *   dwconv_glu_bwd: dy2 (B*T',2d), dw (d,15) += , dbias (d) +=
+ *   dwconv_glu_bwd: dy2 (B*T',2d), dw (d,15) += , dbias (d) += , optional colsum (2d) += sum_rows dy2
+ *                   (pointwise_conv1's bias gradient, taken while the rows are on chip)
  * ------------------------------------------------------------------------------------------------ */
 int lasr_glu_dwconv_fwd(const void* y2, int dtype, int64_t ldy, const float* w, const float* bias, float* z, float* partial,
                         int B, int T, int d, void* stream);
@@ -162,7 +176,7 @@ int lasr_bn_swish_bwd_stats(const void* da, int dtype, const float* z, const flo
                             void* stream);
 int lasr_dwconv_glu_bwd(const void* da, const float* z, const void* y2, int dtype, int64_t ldy, const float* mean, const float* rstd,
                         const float* gamma, const float* beta, const float* sums, const float* w, void* dy2, int64_t lddy, float* dw,
-                        float* dbias, int B, int T, int d, void* stream);
+                        float* dbias, float* colsum, int B, int T, int d, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Conv2d subsampling (nets/subsampling.py:32-35,42-46), channel-last.

@@ -46,8 +46,11 @@ int lasr_gemm(const lasr_gemm_args* a, void* stream) {
     LASR_REQUIRE(a->batch1 >= 1 && a->batch2 >= 1, "gemm: bad batch");
     LASR_REQUIRE((long)a->batch1 * a->batch2 * (a->split_k < 1 ? 1 : a->split_k) <= 65535, "gemm: batch*split_k > 65535");
     if (a->accumulate)
-        LASR_REQUIRE(a->c_dtype == LASR_F32 && !a->bias && !a->res && !a->aux && a->act == LASR_ACT_NONE,
+        LASR_REQUIRE(a->c_dtype == LASR_F32 && !a->bias && !a->res && !a->aux && !a->dact && !a->colsum && a->act == LASR_ACT_NONE,
                      "gemm: accumulate needs fp32 C and no epilogue");
+    if (a->dact)
+        LASR_REQUIRE(!a->bias && !a->res && !a->aux && (a->act == LASR_ACT_SWISH || a->act == LASR_ACT_RELU) && a->lddact > 0,
+                     "gemm: dact needs act = swish|relu and no bias/res/aux");
     if (a->split_k > 1) LASR_REQUIRE(a->accumulate, "gemm: split_k > 1 requires accumulate");
     cudaStream_t st = (cudaStream_t)stream;
     if (a->ab_dtype == LASR_BF16) return gemm_tc_dispatch(a, st);

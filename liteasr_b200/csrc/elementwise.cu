@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) pos_bias_fwd_kernel(const TD* __restrict_
 template <typename TD>
 __global__ void __launch_bounds__(256) pos_bias_bwd_kernel(const TD* __restrict__ dqu, const TD* __restrict__ dqv, long ldi,
                                                            TD* __restrict__ dq, long ldq, float* __restrict__ du,
-                                                           float* __restrict__ dv, int rows, int d) {
+                                                           float* __restrict__ dv, float* __restrict__ dqb, int rows, int d) {
     __shared__ float4 red[2][4][64];
     const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
     const int c = (blockIdx.x * 64 + tx) * 4;
@@ -165,6 +165,9 @@ __global__ void __launch_bounds__(256) pos_bias_bwd_kernel(const TD* __restrict_
         }
         atomicAdd(du + c, t.x); atomicAdd(du + c + 1, t.y); atomicAdd(du + c + 2, t.z); atomicAdd(du + c + 3, t.w);
         atomicAdd(dv + c, s.x); atomicAdd(dv + c + 1, s.y); atomicAdd(dv + c + 2, s.z); atomicAdd(dv + c + 3, s.w);
+        if (dqb) {  // bias gradient of linear_q: colsum(dq) = colsum(dqu) + colsum(dqv)
+            atomicAdd(dqb + c, t.x + s.x); atomicAdd(dqb + c + 1, t.y + s.y); atomicAdd(dqb + c + 2, t.z + s.z); atomicAdd(dqb + c + 3, t.w + s.w);
+        }
     }
 }
 
@@ -253,13 +256,13 @@ int lasr_pos_bias_fwd(const void* q, int64_t ldq, const float* u, const float* v
     return check_launch("pos_bias_fwd");
 }
 
-int lasr_pos_bias_bwd(const void* dqu, const void* dqv, int64_t ldi, void* dq, int64_t ldq, float* du, float* dv, int rows, int d,
-                      int dtype, void* stream) {
+int lasr_pos_bias_bwd(const void* dqu, const void* dqv, int64_t ldi, void* dq, int64_t ldq, float* du, float* dv, float* dqbias,
+                      int rows, int d, int dtype, void* stream) {
     LASR_REQUIRE(dqu && dqv && dq && du && dv && rows > 0 && d % 4 == 0 && ldi % 4 == 0 && ldq % 4 == 0, "pos_bias_bwd: bad args");
     dim3 grid(ceil_div(d, 256), ceil_div(rows, 64));
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == LASR_F32) pos_bias_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)dqu, (const float*)dqv, ldi, (float*)dq, ldq, du, dv, rows, d);
-    else if (dtype == LASR_BF16) pos_bias_bwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)dqu, (const bf16*)dqv, ldi, (bf16*)dq, ldq, du, dv, rows, d);
+    if (dtype == LASR_F32) pos_bias_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)dqu, (const float*)dqv, ldi, (float*)dq, ldq, du, dv, dqbias, rows, d);
+    else if (dtype == LASR_BF16) pos_bias_bwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)dqu, (const bf16*)dqv, ldi, (bf16*)dq, ldq, du, dv, dqbias, rows, d);
     else { set_error("pos_bias_bwd: bad dtype"); return LASR_ERR_UNSUPPORTED; }
     return check_launch("pos_bias_bwd");
 }

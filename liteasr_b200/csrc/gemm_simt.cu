@@ -23,6 +23,10 @@ struct SimtParams {
     long sa1, sa2, sb1, sb2, sc1, sc2;
     float alpha;
     int act, accumulate, split_k;
+    const float* dact;
+    long lddact;
+    float* colsum;
+    long cs1, cs2;
 };
 
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams p) {
@@ -77,6 +81,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams p) {
         __syncthreads();
     }
     const long boff = (long)b1 * p.sc1 + (long)b2 * p.sc2;
+    float cs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int m = m0 + ty * 4 + i;
@@ -91,11 +96,24 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams p) {
                 continue;
             }
             float v = (float)acc[i][j];
-            if (p.bias) v += p.bias[n];
-            if (p.aux) p.aux[off] = v;
-            v = p.alpha * apply_act(v, p.act);
-            if (p.res) v += p.res[boff + (long)m * p.ldres + n];
+            if (p.dact) {
+                const float sv = p.dact[boff + (long)m * p.lddact + n];
+                v *= p.alpha * (p.act == LASR_ACT_SWISH ? dswishf_(sv) : (sv > 0.f ? 1.f : 0.f));
+            } else {
+                if (p.bias) v += p.bias[n];
+                if (p.aux) p.aux[off] = v;
+                v = p.alpha * apply_act(v, p.act);
+                if (p.res) v += p.res[boff + (long)m * p.ldres + n];
+            }
             p.c[off] = v;
+            cs[j] += v;
+        }
+    }
+    if (p.colsum) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n < p.n) atomicAdd(p.colsum + (long)b1 * p.cs1 + (long)b2 * p.cs2 + n, cs[j]);
         }
     }
 }
@@ -110,6 +128,7 @@ int gemm_simt_dispatch(const lasr_gemm_args* a, cudaStream_t st) {
     p.ldc = a->ldc; p.ldres = a->ldres; p.batch2 = a->batch2;
     p.sa1 = a->sa1; p.sa2 = a->sa2; p.sb1 = a->sb1; p.sb2 = a->sb2; p.sc1 = a->sc1; p.sc2 = a->sc2;
     p.alpha = a->alpha; p.act = a->act; p.accumulate = a->accumulate; p.split_k = a->split_k < 1 ? 1 : a->split_k;
+    p.dact = (const float*)a->dact; p.lddact = a->lddact; p.colsum = a->colsum; p.cs1 = a->cs1; p.cs2 = a->cs2;
     dim3 grid(ceil_div(a->m, SBM), ceil_div(a->n, SBN), a->batch1 * a->batch2 * p.split_k);
     gemm_simt_kernel<<<grid, 256, 0, st>>>(p);
     return check_launch("gemm_simt");

@@ -19,6 +19,8 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace lasr {
@@ -50,6 +52,7 @@ struct TcParams {
     int batch2;
     long sc1, sc2;
     int a_b1, a_b2, b_b1, b_b2;  // 1 if the operand really advances along that batch level
+    int a_mn, b_mn;              // operand majors (0 = K-major, 1 = MN-major)
     float alpha;
     int act;
     int accumulate;
@@ -58,6 +61,10 @@ struct TcParams {
     int epi_mode;
     int bn, stages, stage_bytes;
     int tiles_m, tiles_n, total_units;
+    const bf16* dact;  // saved tensor of the activation whose derivative multiplies the result (addressed like C, row stride lddact)
+    long lddact;
+    float* colsum;     // colsum[b1*cs1 + b2*cs2 + n] += sum_m C[m, n]
+    long cs1, cs2;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -179,6 +186,17 @@ __device__ __forceinline__ float swish_fast(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
     return x * r;
 }
+__device__ __forceinline__ float dswish_fast(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+    return r * fmaf(x, 1.f - r, 1.f);
+}
+__device__ __forceinline__ float dact_fast(float saved, int act) {
+    if (act == LASR_ACT_RELU) return saved > 0.f ? 1.f : 0.f;
+    if (act == LASR_ACT_SWISH) return dswish_fast(saved);
+    return 1.f;
+}
 __device__ __forceinline__ float act_fast(float x, int act) {
     if (act == LASR_ACT_RELU) return fmaxf(x, 0.f);
     if (act == LASR_ACT_SWISH) return swish_fast(x);
@@ -200,7 +218,7 @@ __device__ __forceinline__ void store4(CT* dst, const float4& f) {
 }
 
 // Epilogue modes: the column phase is specialised so that its inner loop carries no run-time flag tests.
-enum { EPI_PLAIN = 0, EPI_RELU = 1, EPI_SWISH = 2, EPI_RES = 3, EPI_ACC = 4, EPI_GENERIC = 5 };
+enum { EPI_PLAIN = 0, EPI_RELU = 1, EPI_SWISH = 2, EPI_RES = 3, EPI_ACC = 4, EPI_GENERIC = 5, EPI_DSWISH = 6, EPI_DRELU = 7 };
 
 template <typename CT, int MODE>
 __device__ __forceinline__ void epilogue_unit(const TcParams& p, const Unit& w, uint32_t tmem_acc, uint8_t* stage, int q, int part,
@@ -215,6 +233,9 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, const Unit& w, 
     CT* cbase = reinterpret_cast<CT*>(p.c) + boff;
     CT* abase = p.aux ? reinterpret_cast<CT*>(p.aux) + boff : nullptr;
     const float* rbase = p.res ? p.res + boff : nullptr;
+    const bf16* dbase = p.dact ? p.dact + boff : nullptr;
+    float* csbase = p.colsum ? p.colsum + (long)w.b1 * p.cs1 + (long)w.b2 * p.cs2 : nullptr;
+    constexpr bool DACT = (MODE == EPI_DSWISH || MODE == EPI_DRELU);
     uint8_t* wr = stage + lane * 128;
     const int wx = (lane & 7) << 4;
     const uint8_t* rd0 = stage + rsub * 128 + ((chunk ^ rsub) << 4);        // rows 4i + rsub, i even
@@ -226,8 +247,15 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, const Unit& w, 
         // prefetch what the column phase needs from global memory before touching TMEM
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         float4 r4[8];
+        uint2 s2[8];
         if (fast) {
             if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+            if constexpr (DACT) {
+                const bf16* sp = dbase + (long)(row_base + rsub) * p.lddact + col;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    s2[i] = (4 * i < nrows) ? *reinterpret_cast<const uint2*>(sp + (long)(4 * i) * p.lddact) : make_uint2(0u, 0u);
+            }
             if constexpr (MODE == EPI_RES) {
                 const float* rp = rbase + (long)(row_base + rsub) * p.ldres + col;
 #pragma unroll
@@ -258,6 +286,7 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, const Unit& w, 
             const long rstride = 4 * p.ldc;
             float4 ba = b4;
             if constexpr (MODE == EPI_PLAIN || MODE == EPI_RES) { ba.x *= alpha; ba.y *= alpha; ba.z *= alpha; ba.w *= alpha; }
+            float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 float4 f = *reinterpret_cast<const float4*>(((i & 1) ? rd1 : rd0) + i * 512);
@@ -265,6 +294,18 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, const Unit& w, 
                     if constexpr (MODE == EPI_PLAIN) {
                         f.x = fmaf(f.x, alpha, ba.x); f.y = fmaf(f.y, alpha, ba.y); f.z = fmaf(f.z, alpha, ba.z); f.w = fmaf(f.w, alpha, ba.w);
                         store4<CT>(crow, f);
+                        cs.x += f.x; cs.y += f.y; cs.z += f.z; cs.w += f.w;
+                    } else if constexpr (DACT) {
+                        const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&s2[i].x), h1 = *reinterpret_cast<const __nv_bfloat162*>(&s2[i].y);
+                        if constexpr (MODE == EPI_DSWISH) {
+                            f.x *= alpha * dswish_fast(__low2float(h0)); f.y *= alpha * dswish_fast(__high2float(h0));
+                            f.z *= alpha * dswish_fast(__low2float(h1)); f.w *= alpha * dswish_fast(__high2float(h1));
+                        } else {
+                            f.x = __low2float(h0) > 0.f ? alpha * f.x : 0.f; f.y = __high2float(h0) > 0.f ? alpha * f.y : 0.f;
+                            f.z = __low2float(h1) > 0.f ? alpha * f.z : 0.f; f.w = __high2float(h1) > 0.f ? alpha * f.w : 0.f;
+                        }
+                        store4<CT>(crow, f);
+                        cs.x += f.x; cs.y += f.y; cs.z += f.z; cs.w += f.w;
                     } else if constexpr (MODE == EPI_RES) {
                         f.x = fmaf(f.x, alpha, ba.x) + r4[i].x; f.y = fmaf(f.y, alpha, ba.y) + r4[i].y;
                         f.z = fmaf(f.z, alpha, ba.z) + r4[i].z; f.w = fmaf(f.w, alpha, ba.w) + r4[i].w;
@@ -286,6 +327,15 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, const Unit& w, 
                 crow += rstride;
                 if (arow) arow += rstride;
             }
+            if constexpr (MODE == EPI_PLAIN || DACT) {
+                if (csbase) {  // warp-uniform: fold the 4 row groups, then one vector red per 4 columns
+                    cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 8); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 8);
+                    cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 8); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 8);
+                    cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 16); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 16);
+                    cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 16); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 16);
+                    if (rsub == 0) red_add_f32x4(csbase + col, cs);
+                }
+            }
         } else {  // ragged N edge, unaligned C or an unusual flag combination: element-wise, compact (not unrolled)
 #pragma unroll 1
             for (int i = 0; i < 8; ++i) {
@@ -301,10 +351,16 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, const Unit& w, 
                     if (p.accumulate) {
                         atomicAdd(reinterpret_cast<float*>(cbase + off), alpha * f[e]);
                     } else {
-                        if (abase) abase[off] = from_f32<CT>(f[e]);
-                        float x = alpha * act_fast(f[e], p.act);
-                        if (rbase) x += rbase[(long)grow * p.ldres + col + e];
+                        float x;
+                        if (dbase) {
+                            x = alpha * f[e] * dact_fast(__bfloat162float(dbase[(long)grow * p.lddact + col + e]), p.act);
+                        } else {
+                            if (abase) abase[off] = from_f32<CT>(f[e]);
+                            x = alpha * act_fast(f[e], p.act);
+                            if (rbase) x += rbase[(long)grow * p.ldres + col + e];
+                        }
                         cbase[off] = from_f32<CT>(x);
+                        if (csbase) atomicAdd(csbase + col + e, x);
                     }
                 }
             }
@@ -312,30 +368,12 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, const Unit& w, 
     }
 }
 
-__device__ __forceinline__ void epilogue_dispatch(const TcParams& p, const Unit& w, uint32_t tmem_acc, uint8_t* stage, int q, int part,
-                                                  int lane) {
-    if (p.c_dtype == LASR_F32) {
-        switch (p.epi_mode) {
-            case EPI_PLAIN: epilogue_unit<float, EPI_PLAIN>(p, w, tmem_acc, stage, q, part, lane); break;
-            case EPI_RELU: epilogue_unit<float, EPI_RELU>(p, w, tmem_acc, stage, q, part, lane); break;
-            case EPI_SWISH: epilogue_unit<float, EPI_SWISH>(p, w, tmem_acc, stage, q, part, lane); break;
-            case EPI_RES: epilogue_unit<float, EPI_RES>(p, w, tmem_acc, stage, q, part, lane); break;
-            case EPI_ACC: epilogue_unit<float, EPI_ACC>(p, w, tmem_acc, stage, q, part, lane); break;
-            default: epilogue_unit<float, EPI_GENERIC>(p, w, tmem_acc, stage, q, part, lane); break;
-        }
-    } else {
-        switch (p.epi_mode) {
-            case EPI_PLAIN: epilogue_unit<bf16, EPI_PLAIN>(p, w, tmem_acc, stage, q, part, lane); break;
-            case EPI_RELU: epilogue_unit<bf16, EPI_RELU>(p, w, tmem_acc, stage, q, part, lane); break;
-            case EPI_SWISH: epilogue_unit<bf16, EPI_SWISH>(p, w, tmem_acc, stage, q, part, lane); break;
-            default: epilogue_unit<bf16, EPI_GENERIC>(p, w, tmem_acc, stage, q, part, lane); break;
-        }
-    }
-}
-
-template <bool A_MN, bool B_MN>
+// MODE / C_F32 specialise the epilogue warps (one kernel per epilogue keeps the instruction footprint and the register
+// allocation of each variant minimal); operand majors are run-time values: they only steer the two single-thread roles.
+template <int MODE, bool C_F32>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const TcParams p) {
+    const bool A_MN = p.a_mn != 0, B_MN = p.b_mn != 0;
     extern __shared__ uint8_t smem_raw[];
     // align inside the shared window (keeps the address space visible to the compiler: LDS/STS, not generic LD/ST)
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -388,14 +426,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     uint8_t* sa = ring + s * p.stage_bytes;
                     uint8_t* sb = sa + A_BYTES;
                     const int k0 = (w.kb_begin + i) * BK;
-                    if constexpr (!A_MN) {
+                    if (!A_MN) {
                         tma_load_4d(sa, &tma_a, full_bar + s, k0, w.m0, ab2, ab1);  // box {64 k, 128 m}
                     } else {
 #pragma unroll
                         for (int j = 0; j < BM / 64; ++j)  // box {64 m, 64 k}
                             tma_load_4d(sa + j * 8192, &tma_a, full_bar + s, w.m0 + 64 * j, k0, ab2, ab1);
                     }
-                    if constexpr (!B_MN) {
+                    if (!B_MN) {
                         tma_load_4d(sb, &tma_b, full_bar + s, k0, w.n0, bb2, bb1);  // box {64 k, BN n}
                     } else {
                         for (int j = 0; j < p.bn / 64; ++j)
@@ -451,7 +489,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             mbar_wait(acc_full + as, aph);
             tc_fence_after();
             const uint32_t tmem_acc = tmem_base + (uint32_t)(as * ACC_COLS);
-            epilogue_dispatch(p, w, tmem_acc, stage, q, part, lane);
+            epilogue_unit<typename std::conditional<C_F32, float, bf16>::type, MODE>(p, w, tmem_acc, stage, q, part, lane);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + as);
@@ -532,15 +570,45 @@ static int pick_bn(int n, int gran) {
     return best;
 }
 
-template <bool A_MN, bool B_MN>
-static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st) {
-    auto kern = gemm_tc_kernel<A_MN, B_MN>;
+typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, const TcParams);
+
+template <int MODE, bool C_F32>
+static TcKernel configured_kernel() {
     static bool configured = false;
+    TcKernel k = gemm_tc_kernel<MODE, C_F32>;
     if (!configured) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_MAX_DYNAMIC) != cudaSuccess)
-            return check_launch("gemm_tc smem attr");
+        if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_MAX_DYNAMIC) != cudaSuccess) return nullptr;
         configured = true;
     }
+    return k;
+}
+
+static TcKernel pick_kernel(int mode, bool f32) {
+    if (f32) {
+        switch (mode) {
+            case EPI_PLAIN: return configured_kernel<EPI_PLAIN, true>();
+            case EPI_RELU: return configured_kernel<EPI_RELU, true>();
+            case EPI_SWISH: return configured_kernel<EPI_SWISH, true>();
+            case EPI_RES: return configured_kernel<EPI_RES, true>();
+            case EPI_ACC: return configured_kernel<EPI_ACC, true>();
+            case EPI_DSWISH: return configured_kernel<EPI_DSWISH, true>();
+            case EPI_DRELU: return configured_kernel<EPI_DRELU, true>();
+            default: return configured_kernel<EPI_GENERIC, true>();
+        }
+    }
+    switch (mode) {
+        case EPI_PLAIN: return configured_kernel<EPI_PLAIN, false>();
+        case EPI_RELU: return configured_kernel<EPI_RELU, false>();
+        case EPI_SWISH: return configured_kernel<EPI_SWISH, false>();
+        case EPI_DSWISH: return configured_kernel<EPI_DSWISH, false>();
+        case EPI_DRELU: return configured_kernel<EPI_DRELU, false>();
+        default: return configured_kernel<EPI_GENERIC, false>();
+    }
+}
+
+static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st) {
+    TcKernel kern = pick_kernel(p.epi_mode, p.c_dtype == LASR_F32);
+    if (!kern) return check_launch("gemm_tc smem attr");
     const int smem_bytes = SM_RING + p.stages * p.stage_bytes + 1024;
     const int grid = p.total_units < sm_count() ? p.total_units : sm_count();
     kern<<<grid, GEMM_THREADS, smem_bytes, st>>>(ma, mb, p);
@@ -575,7 +643,14 @@ int gemm_tc_dispatch(const lasr_gemm_args* a, cudaStream_t st) {
     if (a->aux) p.vec_ok = p.vec_ok && ((reinterpret_cast<uintptr_t>(a->aux) & 15) == 0);
     if (a->bias) p.vec_ok = p.vec_ok && ((reinterpret_cast<uintptr_t>(a->bias) & 15) == 0);
     if (a->res) p.vec_ok = p.vec_ok && ((reinterpret_cast<uintptr_t>(a->res) & 15) == 0) && al16(a->ldres, 4);
+    p.dact = reinterpret_cast<const bf16*>(a->dact); p.lddact = a->lddact;
+    p.colsum = a->colsum; p.cs1 = a->cs1; p.cs2 = a->cs2;
+    if (a->dact) p.vec_ok = p.vec_ok && ((reinterpret_cast<uintptr_t>(a->dact) & 7) == 0) && ((a->lddact * 2) % 8 == 0) && al16(a->sc1, 2) && al16(a->sc2, 2);
+    if (a->colsum) p.vec_ok = p.vec_ok && ((reinterpret_cast<uintptr_t>(a->colsum) & 15) == 0) && al16(a->cs1, 4) && al16(a->cs2, 4);
     if (a->accumulate) p.epi_mode = EPI_ACC;
+    else if (a->dact && a->act == LASR_ACT_SWISH) p.epi_mode = EPI_DSWISH;
+    else if (a->dact && a->act == LASR_ACT_RELU) p.epi_mode = EPI_DRELU;
+    else if (a->colsum && (a->res || a->aux || a->act != LASR_ACT_NONE)) p.epi_mode = EPI_GENERIC;
     else if (a->res && a->act == LASR_ACT_NONE && !a->aux) p.epi_mode = EPI_RES;
     else if (!a->res && a->act == LASR_ACT_RELU) p.epi_mode = EPI_RELU;
     else if (!a->res && a->act == LASR_ACT_SWISH) p.epi_mode = EPI_SWISH;
@@ -594,10 +669,10 @@ int gemm_tc_dispatch(const lasr_gemm_args* a, cudaStream_t st) {
     }
     p.total_units = (int)units;
 
-    if (!a->trans_a && !a->trans_b) return launch_tc<false, false>(ma, mb, p, st);
-    if (!a->trans_a && a->trans_b) return launch_tc<false, true>(ma, mb, p, st);
-    if (a->trans_a && !a->trans_b) return launch_tc<true, false>(ma, mb, p, st);
-    return launch_tc<true, true>(ma, mb, p, st);
+    p.a_mn = a->trans_a ? 1 : 0;
+    p.b_mn = a->trans_b ? 1 : 0;
+    if (a->c_dtype != LASR_F32 && (p.epi_mode == EPI_RES || p.epi_mode == EPI_ACC)) p.epi_mode = EPI_GENERIC;
+    return launch_tc(ma, mb, p, st);
 }
 
 }  // namespace lasr

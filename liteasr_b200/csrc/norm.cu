@@ -12,7 +12,7 @@ namespace lasr {
 
 constexpr int LN_MAXV = 8;  // float4 chunks per lane -> d <= 1024
 
-template <typename TY>
+template <typename TY, int NV>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, long ldx,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, TY* __restrict__ y, long ldy,
@@ -23,10 +23,10 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
     if (row >= rows) return;
     const float* xr = x + row * ldx;
     const int nchunk = d >> 2;
-    float4 v[LN_MAXV];
+    float4 v[NV];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
         const int c = lane + 32 * i;
         if (c < nchunk) {
             v[i] = *reinterpret_cast<const float4*>(xr + 4 * c);
@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
     const float mu = warp_sum(s) / d;
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
         const int c = lane + 32 * i;
         if (c < nchunk) {
             const float a = v[i].x - mu, b = v[i].y - mu, cc = v[i].z - mu, e = v[i].w - mu;
@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
     }
     TY* yr = y + row * ldy;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
         const int c = lane + 32 * i;
         if (c < nchunk) {
             const float4 g = *reinterpret_cast<const float4*>(gamma + 4 * c);
@@ -79,37 +79,48 @@ __device__ __forceinline__ float4 load4(const TD* p) {
     }
 }
 
-template <typename TD>
+// NV = float4 chunks per lane (d <= 128 * NV).  Each warp walks rows with stride (grid * 8); the per-column partials
+// (dgamma, dbeta and the optional column sum of the updated dx) stay in registers until the end of the kernel.
+// Optional fused outputs for the pre-norm residual blocks (nets/conformer_layer.py:37-66 backward):
+//   dx_lo  : bf16 copy of the final dx (the A operand of the next block's dgrad / wgrad GEMMs)
+//   colsum : += cs_scale * sum_rows dx  (the bias gradient of the Linear whose output was added to this residual stream)
+template <typename TD, int NV>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TD* __restrict__ dy, long lddy,
                                                             const float* __restrict__ x, long ldx,
                                                             const float* __restrict__ mean,
                                                             const float* __restrict__ rstd,
                                                             const float* __restrict__ gamma, float* __restrict__ dx,
                                                             long lddx, int accumulate, float* __restrict__ dgamma,
-                                                            float* __restrict__ dbeta, int rows, int d) {
+                                                            float* __restrict__ dbeta, int rows, int d,
+                                                            bf16* __restrict__ dx_lo, long lddxlo,
+                                                            float* __restrict__ colsum, float cs_scale) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nchunk = d >> 2;
-    float4 gam[LN_MAXV], ag[LN_MAXV], abt[LN_MAXV];
+    float4 gam[NV], ag[NV], abt[NV], acs[NV];
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
         const int c = lane + 32 * i;
         gam[i] = (c < nchunk) ? *reinterpret_cast<const float4*>(gamma + 4 * c) : make_float4(0, 0, 0, 0);
         ag[i] = make_float4(0, 0, 0, 0);
         abt[i] = make_float4(0, 0, 0, 0);
+        acs[i] = make_float4(0, 0, 0, 0);
     }
     const long nwarps = (long)gridDim.x * 8;
     for (long row = (long)blockIdx.x * 8 + warp; row < rows; row += nwarps) {
         const float mu = mean[row], rs = rstd[row];
         const TD* dyr = dy + row * lddy;
         const float* xr = x + row * ldx;
-        float4 g[LN_MAXV], xh[LN_MAXV];
+        float* dxr = dx + row * lddx;
+        float4 g[NV], xh[NV], old[NV];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int i = 0; i < LN_MAXV; ++i) {
+        for (int i = 0; i < NV; ++i) {
             const int c = lane + 32 * i;
+            old[i] = make_float4(0, 0, 0, 0);
             if (c < nchunk) {
                 const float4 dv = load4<TD>(dyr + 4 * c);
                 const float4 xv = *reinterpret_cast<const float4*>(xr + 4 * c);
+                if (accumulate) old[i] = *reinterpret_cast<const float4*>(dxr + 4 * c);
                 xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
                 g[i] = make_float4(dv.x * gam[i].x, dv.y * gam[i].y, dv.z * gam[i].z, dv.w * gam[i].w);
                 s1 += g[i].x + g[i].y + g[i].z + g[i].w;
@@ -119,46 +130,39 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TD* __restrict
             }
         }
         const float m1 = warp_sum(s1) / d, m2 = warp_sum(s2) / d;
-        float* dxr = dx + row * lddx;
 #pragma unroll
-        for (int i = 0; i < LN_MAXV; ++i) {
+        for (int i = 0; i < NV; ++i) {
             const int c = lane + 32 * i;
             if (c < nchunk) {
-                float4 o = make_float4(rs * (g[i].x - m1 - xh[i].x * m2), rs * (g[i].y - m1 - xh[i].y * m2),
-                                       rs * (g[i].z - m1 - xh[i].z * m2), rs * (g[i].w - m1 - xh[i].w * m2));
-                if (accumulate) {
-                    const float4 old = *reinterpret_cast<const float4*>(dxr + 4 * c);
-                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-                }
+                const float4 o = make_float4(rs * (g[i].x - m1 - xh[i].x * m2) + old[i].x, rs * (g[i].y - m1 - xh[i].y * m2) + old[i].y,
+                                             rs * (g[i].z - m1 - xh[i].z * m2) + old[i].z, rs * (g[i].w - m1 - xh[i].w * m2) + old[i].w);
                 *reinterpret_cast<float4*>(dxr + 4 * c) = o;
+                if (dx_lo) {
+                    __nv_bfloat162 h0 = __floats2bfloat162_rn(o.x, o.y), h1 = __floats2bfloat162_rn(o.z, o.w);
+                    uint2 u; u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+                    *reinterpret_cast<uint2*>(dx_lo + row * lddxlo + 4 * c) = u;
+                }
+                acs[i].x += o.x; acs[i].y += o.y; acs[i].z += o.z; acs[i].w += o.w;
             }
         }
     }
     // cross-warp reduce of the per-lane column partials, then one red.add per column per CTA
-    __shared__ float4 red[8][32];
+    __shared__ float4 red[3][8][32];
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
         const int c = lane + 32 * i;
         if (32 * i >= nchunk) break;  // uniform
-        // dgamma
-        red[warp][lane] = ag[i];
+        red[0][warp][lane] = ag[i];
+        red[1][warp][lane] = abt[i];
+        red[2][warp][lane] = acs[i];
         __syncthreads();
-        if (warp == 0 && c < nchunk) {
-            float4 t = red[0][lane];
+        if (warp < 3 && c < nchunk && (warp < 2 || colsum)) {
+            float4 t = red[warp][0][lane];
 #pragma unroll
-            for (int w = 1; w < 8; ++w) { t.x += red[w][lane].x; t.y += red[w][lane].y; t.z += red[w][lane].z; t.w += red[w][lane].w; }
-            atomicAdd(dgamma + 4 * c, t.x); atomicAdd(dgamma + 4 * c + 1, t.y);
-            atomicAdd(dgamma + 4 * c + 2, t.z); atomicAdd(dgamma + 4 * c + 3, t.w);
-        }
-        __syncthreads();
-        red[warp][lane] = abt[i];
-        __syncthreads();
-        if (warp == 0 && c < nchunk) {
-            float4 t = red[0][lane];
-#pragma unroll
-            for (int w = 1; w < 8; ++w) { t.x += red[w][lane].x; t.y += red[w][lane].y; t.z += red[w][lane].z; t.w += red[w][lane].w; }
-            atomicAdd(dbeta + 4 * c, t.x); atomicAdd(dbeta + 4 * c + 1, t.y);
-            atomicAdd(dbeta + 4 * c + 2, t.z); atomicAdd(dbeta + 4 * c + 3, t.w);
+            for (int w = 1; w < 8; ++w) { t.x += red[warp][w][lane].x; t.y += red[warp][w][lane].y; t.z += red[warp][w][lane].z; t.w += red[warp][w][lane].w; }
+            float* dst = (warp == 0 ? dgamma : (warp == 1 ? dbeta : colsum)) + 4 * c;
+            if (warp == 2) { t.x *= cs_scale; t.y *= cs_scale; t.z *= cs_scale; t.w *= cs_scale; }
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(t.x), "f"(t.y), "f"(t.z), "f"(t.w) : "memory");
         }
         __syncthreads();
     }
@@ -176,31 +180,51 @@ int lasr_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const fl
     LASR_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0, "layernorm_fwd: row strides must be multiples of 4");
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = ceil_div(rows, 8);
-    if (y_dtype == LASR_F32)
-        layernorm_fwd_kernel<float><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, (float*)y, ldy, mean, rstd, rows, d, eps);
-    else if (y_dtype == LASR_BF16)
-        layernorm_fwd_kernel<bf16><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, (bf16*)y, ldy, mean, rstd, rows, d, eps);
+#define LASR_LNF(TY, NV) layernorm_fwd_kernel<TY, NV><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, (TY*)y, ldy, mean, rstd, rows, d, eps)
+#define LASR_LNF_D(TY)                      \
+    do {                                    \
+        if (d <= 128) LASR_LNF(TY, 1);      \
+        else if (d <= 256) LASR_LNF(TY, 2); \
+        else if (d <= 512) LASR_LNF(TY, 4); \
+        else LASR_LNF(TY, 8);               \
+    } while (0)
+    if (y_dtype == LASR_F32) LASR_LNF_D(float);
+    else if (y_dtype == LASR_BF16) LASR_LNF_D(bf16);
     else { set_error("layernorm_fwd: bad dtype"); return LASR_ERR_UNSUPPORTED; }
+#undef LASR_LNF_D
+#undef LASR_LNF
     return check_launch("layernorm_fwd");
 }
 
 int lasr_layernorm_bwd(const void* dy, int dy_dtype, int64_t lddy, const float* x, int64_t ldx, const float* mean,
                        const float* rstd, const float* gamma, float* dx, int64_t lddx, int accumulate, float* dgamma,
-                       float* dbeta, int rows, int d, void* stream) {
+                       float* dbeta, int rows, int d, void* dx_lo, int64_t lddxlo, float* colsum, float colsum_scale,
+                       void* stream) {
     using namespace lasr;
     LASR_REQUIRE(dy && x && mean && rstd && gamma && dx && dgamma && dbeta, "layernorm_bwd: null pointer");
     LASR_REQUIRE(rows > 0 && d > 0 && d % 4 == 0 && d <= 128 * LN_MAXV, "layernorm_bwd: d=%d unsupported", d);
-    LASR_REQUIRE(ldx % 4 == 0 && lddy % 4 == 0 && lddx % 4 == 0, "layernorm_bwd: row strides must be multiples of 4");
+    LASR_REQUIRE(ldx % 4 == 0 && lddy % 4 == 0 && lddx % 4 == 0 && lddxlo % 4 == 0, "layernorm_bwd: row strides must be multiples of 4");
+    LASR_REQUIRE(((uintptr_t)dgamma & 15) == 0 && ((uintptr_t)dbeta & 15) == 0 && ((uintptr_t)colsum & 15) == 0,
+                 "layernorm_bwd: dgamma/dbeta/colsum must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     int grid = ceil_div(rows, 8);
-    if (grid > 148 * 4) grid = 148 * 4;
-    if (dy_dtype == LASR_F32)
-        layernorm_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)dy, lddy, x, ldx, mean, rstd, gamma, dx, lddx,
-                                                         accumulate, dgamma, dbeta, rows, d);
-    else if (dy_dtype == LASR_BF16)
-        layernorm_bwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)dy, lddy, x, ldx, mean, rstd, gamma, dx, lddx,
-                                                        accumulate, dgamma, dbeta, rows, d);
+    if (grid > 148 * 3) grid = 148 * 3;
+    bf16* lo = (bf16*)dx_lo;
+#define LASR_LNB(TD, NV)                                                                                                     \
+    layernorm_bwd_kernel<TD, NV><<<grid, 256, 0, st>>>((const TD*)dy, lddy, x, ldx, mean, rstd, gamma, dx, lddx, accumulate, \
+                                                       dgamma, dbeta, rows, d, lo, lddxlo, colsum, colsum_scale)
+#define LASR_LNB_D(TD)                  \
+    do {                                \
+        if (d <= 128) LASR_LNB(TD, 1);  \
+        else if (d <= 256) LASR_LNB(TD, 2); \
+        else if (d <= 512) LASR_LNB(TD, 4); \
+        else LASR_LNB(TD, 8);           \
+    } while (0)
+    if (dy_dtype == LASR_F32) LASR_LNB_D(float);
+    else if (dy_dtype == LASR_BF16) LASR_LNB_D(bf16);
     else { set_error("layernorm_bwd: bad dtype"); return LASR_ERR_UNSUPPORTED; }
+#undef LASR_LNB_D
+#undef LASR_LNB
     return check_launch("layernorm_bwd");
 }
 

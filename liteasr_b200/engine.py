@@ -61,16 +61,39 @@ class Engine:
         ops.layernorm_fwd(x, self.st.p(pfx + ".weight"), self.st.p(pfx + ".bias"), y, mean, rstd, LN_EPS)
         return NS(x=x, y=y, mean=mean, rstd=rstd, pfx=pfx)
 
-    def layernorm_bwd(self, ln: NS, dy: torch.Tensor, dx: torch.Tensor, accumulate: bool) -> None:
+    def layernorm_bwd(self, ln: NS, dy: torch.Tensor, dx: torch.Tensor, accumulate: bool, nxt=None, want_lo: bool = False):
+        """dx (+)= LN'(dy) and the LayerNorm parameter gradients.  ``nxt = (bias_grad, scale)``: the updated residual-stream
+        gradient dx is also the output gradient of the block that runs next in backward order, so its output Linear's bias
+        gradient (scale * colsum(dx)) and the operand-dtype copy of dx that block's GEMMs read are produced here, in the same
+        pass.  Returns that copy (dx itself in fp32 mode), or None when not requested."""
+        want_lo = want_lo or nxt is not None
+        lo = None
+        if want_lo and self.adt != torch.float32:
+            lo = _empty(dx.shape, self.adt, self.dev)
         ops.layernorm_bwd(dy, ln.x, ln.mean, ln.rstd, self.st.p(ln.pfx + ".weight"), dx, self.st.g(ln.pfx + ".weight"),
-                          self.st.g(ln.pfx + ".bias"), accumulate)
+                          self.st.g(ln.pfx + ".bias"), accumulate, dx_lo=lo, colsum=(nxt[0] if nxt is not None else None),
+                          colsum_scale=(nxt[1] if nxt is not None else 1.0))
+        if not want_lo:
+            return None
+        return lo if lo is not None else dx
+
+    @staticmethod
+    def _pick_bn(n: int, gran: int) -> int:
+        if n <= 256:
+            return (n + gran - 1) // gran * gran
+        best, best_pad = 256, (n + 255) // 256 * 256
+        for bn in range(256 - gran, 127, -gran):
+            pad = (n + bn - 1) // bn * bn
+            if pad < best_pad:
+                best, best_pad = bn, pad
+        return best
 
     def _split_k(self, n_out: int, k_out: int, rows: int) -> int:
         if self.adt == torch.float32:
-            # parity mode: keep every sequential fp32 accumulation chain <= 512 terms (the partial sums meet through
-            # red.add), so weight gradients reduced over 1e4-1e5 rows stay within ~1e-6 of a float64 sum
+            # parity mode: the SIMT kernel accumulates in fp64; a moderate split only adds parallelism
             return max(1, min(64, rows // 512))
-        tiles = ((n_out + 127) // 128) * ((k_out + 127) // 128)
+        bn = self._pick_bn(k_out, 64)  # the wgrad GEMM is (n_out x k_out), B operand MN-major
+        tiles = ((n_out + 127) // 128) * ((k_out + bn - 1) // bn)
         s = max(1, min(32, 148 // max(1, tiles)))
         s = min(s, max(1, rows // 256))
         return s
@@ -93,24 +116,34 @@ class Engine:
                  ldres=(res.stride(0) if res is not None else 0), aux=auxbuf, alpha=alpha, act=act)
         return (out, auxbuf) if aux else out
 
+    def wgrad(self, dy, x, gw, alpha=1.0) -> None:
+        """gw (N_out, K_in) += alpha * dy^T x   (split-K tcgen05 / SIMT GEMM with red.add)."""
+        m, n = dy.shape
+        k = x.shape[1]
+        ops.gemm(dy, x, gw, n, k, m, lda=dy.stride(0), ldb=x.stride(0), ldc=gw.stride(0), ta=True, tb=True, accumulate=True,
+                 split_k=self._split_k(n, k, m), alpha=alpha)
+
+    def dgrad(self, dy, w, *, out_dtype=None, alpha=1.0, dx_res=None, dact=None, act=ACT_NONE, colsum=None):
+        """dx = alpha * dy @ W (W stored (N_out, K_in)); optional fused activation backward (``dact``/``act``), bias-gradient
+        column sum of the result (``colsum``) and fp32 accumulation into ``dx_res``."""
+        m, n = dy.shape
+        k = w.shape[1]
+        dx = _empty((m, k), self.adt if out_dtype is None else out_dtype, self.dev) if dx_res is None else dx_res
+        ops.gemm(dy, w, dx, m, k, n, lda=dy.stride(0), ldb=w.stride(0), ldc=dx.stride(0), tb=True, alpha=alpha,
+                 res=dx_res, ldres=(dx_res.stride(0) if dx_res is not None else 0), dact=dact, act=act, colsum=colsum)
+        return dx
+
     def linear_bwd(self, dy, x, wname, *, need_dx=True, dx_dtype=None, bias=True, dbias_done=False, alpha=1.0, w=None,
                    gw=None, gb=None, dx_res=None):
         """dW += alpha * dy^T x ; db += colsum(dy) (unless fused earlier) ; returns dx = alpha * dy @ W."""
         w = self.st.w(wname + ".weight") if w is None else w
         gw = self.st.gw(wname + ".weight") if gw is None else gw
-        m, n = dy.shape
-        k = x.shape[1]
         if bias and not dbias_done:
             ops.act_bwd(dy, None, None, self.st.g(wname + ".bias") if gb is None else gb, ACT_NONE, alpha)
-        ops.gemm(dy, x, gw, n, k, m, lda=dy.stride(0), ldb=x.stride(0), ldc=gw.stride(0), ta=True, tb=True, accumulate=True,
-                 split_k=self._split_k(n, k, m), alpha=alpha)
+        self.wgrad(dy, x, gw, alpha)
         if not need_dx:
             return None
-        dx_dtype = self.adt if dx_dtype is None else dx_dtype
-        dx = _empty((m, k), dx_dtype, self.dev) if dx_res is None else dx_res
-        ops.gemm(dy, w, dx, m, k, n, lda=dy.stride(0), ldb=w.stride(0), ldc=dx.stride(0), tb=True, alpha=alpha,
-                 res=dx_res, ldres=(dx_res.stride(0) if dx_res is not None else 0))
-        return dx
+        return self.dgrad(dy, w, out_dtype=dx_dtype, alpha=alpha, dx_res=dx_res)
 
     # ------------------------------------------------------------------------------------------
     # feed-forward block   x <- x + scale * fc2(act(fc1(LN x)))      nets/feed_forward.py:18-19,
@@ -125,14 +158,17 @@ class Engine:
         out = self.linear(a, pfx_ff + ".fc2", torch.float32, res=x, alpha=scale)
         return NS(out=out, ln=ln, a=a, h=h, act=act, scale=scale, pfx=pfx_ff)
 
-    def ffn_bwd(self, c: NS, dres: torch.Tensor) -> None:
-        """dres (fp32, in/out): gradient wrt the block output on entry, wrt the block input on exit."""
-        dy = self.to_adt(dres)
-        da = self.linear_bwd(dy, c.a, c.pfx + ".fc2", alpha=c.scale)
-        dh = _empty(da.shape, self.adt, self.dev)
-        ops.act_bwd(da, c.h if c.act == ACT_SWISH else c.a, dh, self.st.g(c.pfx + ".fc1.bias"), c.act)
-        dln = self.linear_bwd(dh, c.ln.y, c.pfx + ".fc1", dbias_done=True)
-        self.layernorm_bwd(c.ln, dln, dres, accumulate=True)
+    def ffn_bwd(self, c: NS, dres: torch.Tensor, dy: torch.Tensor, nxt=None, want_lo=False):
+        """dres (fp32, in/out): gradient wrt the block output on entry, wrt the block input on exit.  dy = operand-dtype copy of
+        dres on entry (fc2's bias gradient was taken by the producer of dy).  Returns the operand copy of the updated dres."""
+        st = self.st
+        self.wgrad(dy, c.a, st.gw(c.pfx + ".fc2.weight"), c.scale)
+        # dh = scale * (dy @ W2) * act'(.)  and  db1 += colsum(dh), both in the dgrad epilogue
+        dh = self.dgrad(dy, st.w(c.pfx + ".fc2.weight"), alpha=c.scale, dact=(c.h if c.act == ACT_SWISH else c.a), act=c.act,
+                        colsum=st.g(c.pfx + ".fc1.bias"))
+        self.wgrad(dh, c.ln.y, st.gw(c.pfx + ".fc1.weight"))
+        dln = self.dgrad(dh, st.w(c.pfx + ".fc1.weight"))
+        return self.layernorm_bwd(c.ln, dln, dres, True, nxt, want_lo)
 
     # ------------------------------------------------------------------------------------------
     # attention core on projected q/k/v  (nets/attention.py:46-59,61-71,120-154)
@@ -157,25 +193,25 @@ class Engine:
                  sb=(Tk * v.stride(0), dk), sc=(Tq * d, dk))
         return NS(q=q, k=k, v=v, qv=qv, p=p, probs=probs, o=o, B=B, H=H, Tq=Tq, Tk=Tk, dk=dk, ld=ld, scale=scale)
 
-    def attn_core_bwd(self, c: NS, do, dq, dk_, dv, dqv=None, dp32=None) -> None:
-        """do (B*Tq,d) adt.  Writes dq/dk_/dv (views with the same strides as q/k/v); rel-pos: dqv and dp32 (+=)."""
+    def attn_core_bwd(self, c: NS, do, dq, dk_, dv, dqv=None, dp32=None, bq=None, bk=None, bv=None) -> None:
+        """do (B*Tq,d) adt.  Writes dq/dk_/dv (views with the same strides as q/k/v); rel-pos: dqv and dp32 (+=).
+        bq/bk/bv: bias-gradient vectors (d,) of the q/k/v projections, accumulated in the GEMM epilogues (head h -> [h*dk, (h+1)*dk))."""
         B, H, Tq, Tk, dk, ld = c.B, c.H, c.Tq, c.Tk, c.dk, c.ld
-        d = H * dk
         bs = (H * Tq * ld, Tq * ld)
         dprobs = _empty((B, H, Tq, ld), torch.float32, self.dev)
         ops.gemm(do, c.v, dprobs, Tq, Tk, dk, lda=do.stride(0), ldb=c.v.stride(0), ldc=ld, batch=(B, H), sa=(Tq * do.stride(0), dk),
                  sb=(Tk * c.v.stride(0), dk), sc=bs)
         # dV[j] = sum_i probs[i,j] dO[i]
         ops.gemm(c.probs, do, dv, Tk, dk, Tq, lda=ld, ldb=do.stride(0), ldc=dv.stride(0), ta=True, tb=True, batch=(B, H), sa=bs,
-                 sb=(Tq * do.stride(0), dk), sc=(Tk * dv.stride(0), dk))
+                 sb=(Tq * do.stride(0), dk), sc=(Tk * dv.stride(0), dk), colsum=bv, cs=(0, dk))
         dsc = _empty((B, H, Tq, ld), self.adt, self.dev)
         dbd = _empty((B, H, Tq, ld), self.adt, self.dev) if c.qv is not None else None
         ops.attn_softmax_bwd(c.probs, dprobs, dsc, dbd, c.scale, Tk)
         # dQ[i] = sum_j ds[i,j] K[j] ; dK[j] = sum_i ds[i,j] Q[i]
         ops.gemm(dsc, c.k, dq, Tq, dk, Tk, lda=ld, ldb=c.k.stride(0), ldc=dq.stride(0), tb=True, batch=(B, H), sa=bs,
-                 sb=(Tk * c.k.stride(0), dk), sc=(Tq * dq.stride(0), dk))
+                 sb=(Tk * c.k.stride(0), dk), sc=(Tq * dq.stride(0), dk), colsum=bq, cs=(0, dk))
         ops.gemm(dsc, c.q, dk_, Tk, dk, Tq, lda=ld, ldb=c.q.stride(0), ldc=dk_.stride(0), ta=True, tb=True, batch=(B, H), sa=bs,
-                 sb=(Tq * c.q.stride(0), dk), sc=(Tk * dk_.stride(0), dk))
+                 sb=(Tq * c.q.stride(0), dk), sc=(Tk * dk_.stride(0), dk), colsum=bk, cs=(0, dk))
         if c.qv is not None:
             ops.gemm(dbd, c.p, dqv, Tq, dk, Tk, lda=ld, ldb=c.p.stride(0), ldc=dqv.stride(0), tb=True, batch=(B, H), sa=bs,
                      sb=(0, dk), sc=(Tq * dqv.stride(0), dk))
@@ -201,26 +237,25 @@ class Engine:
         out = self.linear(core.o, pfx + ".linear_o", torch.float32, res=x)
         return NS(out=out, ln=ln, qkv=qkv, core=core, pos=pos, pfx=pfx, d=d)
 
-    def rel_mha_bwd(self, c: NS, dres) -> None:
+    def rel_mha_bwd(self, c: NS, dres, dy, nxt=None, want_lo=False):
         st, d, core = self.st, c.d, c.core
         B, T = core.B, core.Tq
-        dy = self.to_adt(dres)
-        do = self.linear_bwd(dy, core.o, c.pfx + ".linear_o")
+        self.wgrad(dy, core.o, st.gw(c.pfx + ".linear_o.weight"))
+        do = self.dgrad(dy, st.w(c.pfx + ".linear_o.weight"))
         dqkv = _empty((B * T, 3 * d), self.adt, self.dev)
         dqu = _empty((B * T, d), self.adt, self.dev)
         dqv = _empty((B * T, d), self.adt, self.dev)
         dp32 = torch.empty((T, d), dtype=torch.float32, device=self.dev)
         ops.zero_(dp32)
-        self.attn_core_bwd(core, do, dqu, dqkv[:, d:2 * d], dqkv[:, 2 * d:], dqv=dqv, dp32=dp32)
-        ops.pos_bias_bwd(dqu, dqv, dqkv[:, :d], st.g(c.pfx + ".pos_bias_u").view(-1), st.g(c.pfx + ".pos_bias_v").view(-1))
+        gb = st.g_span(c.pfx + ".linear_q.bias", 3 * d)
+        self.attn_core_bwd(core, do, dqu, dqkv[:, d:2 * d], dqkv[:, 2 * d:], dqv=dqv, dp32=dp32, bk=gb[d:2 * d], bv=gb[2 * d:])
+        ops.pos_bias_bwd(dqu, dqv, dqkv[:, :d], st.g(c.pfx + ".pos_bias_u").view(-1), st.g(c.pfx + ".pos_bias_v").view(-1), gb[:d])
         # linear_pos (no bias): dW_pos += dP^T pos
-        dp = self.to_adt(dp32)
-        self.linear_bwd(dp, c.pos, c.pfx + ".linear_pos", need_dx=False, bias=False)
+        self.wgrad(self.to_adt(dp32), c.pos, st.gw(c.pfx + ".linear_pos.weight"))
         # fused q/k/v projection
-        ops.act_bwd(dqkv, None, None, st.g_span(c.pfx + ".linear_q.bias", 3 * d), ACT_NONE)
-        dln = self.linear_bwd(dqkv, c.ln.y, None, dbias_done=True, w=st.w(c.pfx + ".linear_q.weight", 3 * d, d),
-                              gw=st.gw(c.pfx + ".linear_q.weight", 3 * d, d))
-        self.layernorm_bwd(c.ln, dln, dres, accumulate=True)
+        self.wgrad(dqkv, c.ln.y, st.gw(c.pfx + ".linear_q.weight", 3 * d, d))
+        dln = self.dgrad(dqkv, st.w(c.pfx + ".linear_q.weight", 3 * d, d))
+        return self.layernorm_bwd(c.ln, dln, dres, True, nxt, want_lo)
 
     # ------------------------------------------------------------------------------------------
     # plain MHA blocks of the decoder (nets/transformer_layer.py:29-51,161-177, nets/attention.py:61-71)
@@ -234,16 +269,16 @@ class Engine:
         out = self.linear(core.o, pfx + ".linear_o", torch.float32, res=y)
         return NS(out=out, ln=ln, core=core, pfx=pfx, d=d)
 
-    def self_mha_bwd(self, c: NS, dres) -> None:
+    def self_mha_bwd(self, c: NS, dres, dy, nxt=None, want_lo=False):
         st, d, core = self.st, c.d, c.core
-        dy = self.to_adt(dres)
-        do = self.linear_bwd(dy, core.o, c.pfx + ".linear_o")
+        self.wgrad(dy, core.o, st.gw(c.pfx + ".linear_o.weight"))
+        do = self.dgrad(dy, st.w(c.pfx + ".linear_o.weight"))
         dqkv = _empty((core.B * core.Tq, 3 * d), self.adt, self.dev)
-        self.attn_core_bwd(core, do, dqkv[:, :d], dqkv[:, d:2 * d], dqkv[:, 2 * d:])
-        ops.act_bwd(dqkv, None, None, st.g_span(c.pfx + ".linear_q.bias", 3 * d), ACT_NONE)
-        dln = self.linear_bwd(dqkv, c.ln.y, None, dbias_done=True, w=st.w(c.pfx + ".linear_q.weight", 3 * d, d),
-                              gw=st.gw(c.pfx + ".linear_q.weight", 3 * d, d))
-        self.layernorm_bwd(c.ln, dln, dres, accumulate=True)
+        gb = st.g_span(c.pfx + ".linear_q.bias", 3 * d)
+        self.attn_core_bwd(core, do, dqkv[:, :d], dqkv[:, d:2 * d], dqkv[:, 2 * d:], bq=gb[:d], bk=gb[d:2 * d], bv=gb[2 * d:])
+        self.wgrad(dqkv, c.ln.y, st.gw(c.pfx + ".linear_q.weight", 3 * d, d))
+        dln = self.dgrad(dqkv, st.w(c.pfx + ".linear_q.weight", 3 * d, d))
+        return self.layernorm_bwd(c.ln, dln, dres, True, nxt, want_lo)
 
     def src_mha_fwd(self, y, mem, pfx_norm, pfx, B, L, T, H, xlens) -> NS:
         d = y.shape[1]
@@ -255,19 +290,21 @@ class Engine:
         out = self.linear(core.o, pfx + ".linear_o", torch.float32, res=y)
         return NS(out=out, ln=ln, core=core, mem=mem, pfx=pfx, d=d)
 
-    def src_mha_bwd(self, c: NS, dres, dmem32) -> None:
+    def src_mha_bwd(self, c: NS, dres, dy, dmem32, nxt=None, want_lo=False):
         st, d, core = self.st, c.d, c.core
-        dy = self.to_adt(dres)
-        do = self.linear_bwd(dy, core.o, c.pfx + ".linear_o")
+        self.wgrad(dy, core.o, st.gw(c.pfx + ".linear_o.weight"))
+        do = self.dgrad(dy, st.w(c.pfx + ".linear_o.weight"))
         dq = _empty((core.B * core.Tq, d), self.adt, self.dev)
         dkv = _empty((core.B * core.Tk, 2 * d), self.adt, self.dev)
-        self.attn_core_bwd(core, do, dq, dkv[:, :d], dkv[:, d:])
-        dln = self.linear_bwd(dq, c.ln.y, c.pfx + ".linear_q")
-        self.layernorm_bwd(c.ln, dln, dres, accumulate=True)
-        ops.act_bwd(dkv, None, None, st.g_span(c.pfx + ".linear_k.bias", 2 * d), ACT_NONE)
+        gkv = st.g_span(c.pfx + ".linear_k.bias", 2 * d)
+        self.attn_core_bwd(core, do, dq, dkv[:, :d], dkv[:, d:], bq=st.g(c.pfx + ".linear_q.bias"), bk=gkv[:d], bv=gkv[d:])
+        self.wgrad(dq, c.ln.y, st.gw(c.pfx + ".linear_q.weight"))
+        dln = self.dgrad(dq, st.w(c.pfx + ".linear_q.weight"))
+        lo = self.layernorm_bwd(c.ln, dln, dres, True, nxt, want_lo)
         # dmem += dkv @ W_kv   (fp32, accumulated across the decoder layers through the residual input)
-        self.linear_bwd(dkv, c.mem, None, dbias_done=True, w=st.w(c.pfx + ".linear_k.weight", 2 * d, d),
-                        gw=st.gw(c.pfx + ".linear_k.weight", 2 * d, d), dx_res=dmem32)
+        self.wgrad(dkv, c.mem, st.gw(c.pfx + ".linear_k.weight", 2 * d, d))
+        self.dgrad(dkv, st.w(c.pfx + ".linear_k.weight", 2 * d, d), dx_res=dmem32)
+        return lo
 
     # ------------------------------------------------------------------------------------------
     # convolution block (nets/conformer_layer.py:49-56, nets/conformer_convolution.py:44-57)
@@ -289,13 +326,12 @@ class Engine:
         out = self.linear(a, None, torch.float32, w=st.w(pfx + ".pointwise_conv2.weight"), bias_t=st.p(pfx + ".pointwise_conv2.bias"), res=x)
         return NS(out=out, ln=ln, y2=y2, z=z, mean=mean, rstd=rstd, a=a, pfx=pfx, B=B, T=T, d=d, training=training)
 
-    def conv_bwd(self, c: NS, dres) -> None:
+    def conv_bwd(self, c: NS, dres, dy, nxt=None, want_lo=False):
         st, d, pfx = self.st, c.d, c.pfx
         if not c.training:
             raise RuntimeError("conv-module backward needs batch statistics (module must be in training mode)")
-        dy = self.to_adt(dres)
-        da = self.linear_bwd(dy, c.a, None, w=st.w(pfx + ".pointwise_conv2.weight"), gw=st.gw(pfx + ".pointwise_conv2.weight"),
-                             gb=st.g(pfx + ".pointwise_conv2.bias"))
+        self.wgrad(dy, c.a, st.gw(pfx + ".pointwise_conv2.weight"))
+        da = self.dgrad(dy, st.w(pfx + ".pointwise_conv2.weight"))
         rows = c.B * c.T
         partial = _empty(((rows + 31) // 32, 2, d), torch.float32, self.dev)
         sums = _empty((2, d), torch.float32, self.dev)
@@ -303,10 +339,11 @@ class Engine:
         ops.bn_swish_bwd_stats(da, c.z, c.mean, c.rstd, gam, bet, partial, sums, st.g(pfx + ".norm.weight"), st.g(pfx + ".norm.bias"))
         dy2 = _empty((rows, 2 * d), self.adt, self.dev)
         ops.dwconv_glu_bwd(da, c.z, c.y2, c.mean, c.rstd, gam, bet, sums, st.p(pfx + ".depthwise_conv.weight").view(d, KW), dy2,
-                           st.g(pfx + ".depthwise_conv.weight").view(d, KW), st.g(pfx + ".depthwise_conv.bias"), c.B, c.T, d)
-        dln = self.linear_bwd(dy2, c.ln.y, None, w=st.w(pfx + ".pointwise_conv1.weight"), gw=st.gw(pfx + ".pointwise_conv1.weight"),
-                              gb=st.g(pfx + ".pointwise_conv1.bias"))
-        self.layernorm_bwd(c.ln, dln, dres, accumulate=True)
+                           st.g(pfx + ".depthwise_conv.weight").view(d, KW), st.g(pfx + ".depthwise_conv.bias"), c.B, c.T, d,
+                           colsum=st.g(pfx + ".pointwise_conv1.bias"))
+        self.wgrad(dy2, c.ln.y, st.gw(pfx + ".pointwise_conv1.weight"))
+        dln = self.dgrad(dy2, st.w(pfx + ".pointwise_conv1.weight"))
+        return self.layernorm_bwd(c.ln, dln, dres, True, nxt, want_lo)
 
     # ------------------------------------------------------------------------------------------
     # Conv2d subsampling front end (nets/subsampling.py:42-48) + x*sqrt(d) (nets/positional_encoding.py:73)
@@ -341,20 +378,23 @@ class Engine:
         x0 = self.linear(h2v, None, torch.float32, w=self._out_weight(pfx, d, F2), bias_t=st.p(pfx + ".out.bias"), alpha=math.sqrt(d))
         return NS(out=x0, xs=xs, h1=h1, col=col, h2=h2, B=B, T1=T1, F1=F1, T2=T2, F2=F2, d=d, pfx=pfx)
 
-    def embed_bwd(self, c: NS, dx0) -> None:
+    def embed_bwd(self, c: NS, dy) -> None:
+        """dy: operand-dtype gradient wrt the front end's output (out.bias gradient already taken by the producer of dy)."""
         st, d, pfx = self.st, c.d, c.pfx
         B, T2, F2 = c.B, c.T2, c.F2
-        dy = self.to_adt(dx0)
         s = math.sqrt(d)
         gwo = torch.empty((d, F2 * d), dtype=torch.float32, device=self.dev)
         ops.zero_(gwo)
-        dh2v = self.linear_bwd(dy, c.h2.view(B * T2, F2 * d), None, alpha=s, w=self._out_weight(pfx, d, F2), gw=gwo, gb=st.g(pfx + ".out.bias"))
+        h2v = c.h2.view(B * T2, F2 * d)
+        self.wgrad(dy, h2v, gwo, s)
         ops.permute4d(gwo, st.g(pfx + ".out.weight"), (d, F2, d, 1), (F2 * d, d, 1, 0), (F2 * d, 1, F2, 0), accumulate=True)
-        dh2 = _empty((B * T2 * F2, d), self.adt, self.dev)
-        ops.act_bwd(dh2v.view(B * T2 * F2, d), c.h2, dh2, st.g(pfx + ".conv.2.bias"), ACT_RELU)
+        # dh2 = s * (dy @ W_out) * relu'(h2): conv2's ReLU backward fused into the dgrad epilogue
+        dh2 = self.dgrad(dy, self._out_weight(pfx, d, F2), alpha=s, dact=h2v, act=ACT_RELU).view(B * T2 * F2, d)
+        ops.act_bwd(dh2, None, None, st.g(pfx + ".conv.2.bias"), ACT_NONE)
         gw2 = torch.empty((d, 9 * d), dtype=torch.float32, device=self.dev)
         ops.zero_(gw2)
-        dcol = self.linear_bwd(dh2, c.col, None, dbias_done=True, w=self._conv2_weight(pfx, d), gw=gw2)
+        self.wgrad(dh2, c.col, gw2)
+        dcol = self.dgrad(dh2, self._conv2_weight(pfx, d))
         ops.permute4d(gw2, st.g(pfx + ".conv.2.weight"), (d, 3, 3, d), (9 * d, 3 * d, d, 1), (9 * d, 3, 1, 9), accumulate=True)
         dh1 = _empty(c.h1.shape, self.adt, self.dev)
         ops.col2im_s2_relu(dcol, c.h1, dh1)
@@ -389,25 +429,32 @@ class Engine:
         dh = dh.contiguous().view(c.B * c.Tp, c.d)
         if dh.dtype != torch.float32:
             raise TypeError("encoder gradient must be fp32")
+        st, g = self.st, self.st.g
         dres = _empty(dh.shape, torch.float32, self.dev)
         self.layernorm_bwd(c.fin, dh, dres, accumulate=False)
-        hook = self.st.grad_ready_hook
+        hook = st.grad_ready_hook
         if hook is not None:
-            hook(*self.st.range_of(c.pfx + "after_norm."))
+            hook(*st.range_of(c.pfx + "after_norm."))
         for i in range(len(c.layers) - 1, -1, -1):
             c1, c2, c3, c4, c5 = c.layers[i]
+            lp = f"{c.pfx}enc_layers.{i}"
             nxt = _empty(dres.shape, torch.float32, self.dev)
-            self.layernorm_bwd(c5, dres, nxt, accumulate=False)
+            # every LayerNorm backward also emits the bias gradient of the Linear that closes the block that runs NEXT in
+            # backward order (its output gradient is exactly the residual-stream gradient being written) + the bf16 copy
+            dy = self.layernorm_bwd(c5, dres, nxt, False, (g(lp + ".feed_forward.fc2.bias"), 0.5))
             dres = nxt
-            self.ffn_bwd(c4, dres)
-            self.conv_bwd(c3, dres)
-            self.rel_mha_bwd(c2, dres)
-            self.ffn_bwd(c1, dres)
+            dy = self.ffn_bwd(c4, dres, dy, (g(lp + ".conv.pointwise_conv2.bias"), 1.0))
+            dy = self.conv_bwd(c3, dres, dy, (g(lp + ".self_attn.linear_o.bias"), 1.0))
+            dy = self.rel_mha_bwd(c2, dres, dy, (g(lp + ".feed_forward_macaron.fc2.bias"), 0.5))
+            dy = self.ffn_bwd(c1, dres, dy, (g(c.pfx + "embed.out.bias"), math.sqrt(c.d)) if i == 0 else None)
             if hook is not None:
-                hook(*self.st.range_of(f"{c.pfx}enc_layers.{i}."))
-        self.embed_bwd(c.emb, dres)
+                hook(*st.range_of(lp + "."))
+        if len(c.layers) == 0:
+            dy = self.to_adt(dres)
+            ops.act_bwd(dy, None, None, g(c.pfx + "embed.out.bias"), ACT_NONE, math.sqrt(c.d))
+        self.embed_bwd(c.emb, dy)
         if hook is not None:
-            hook(*self.st.range_of(c.pfx + "embed."))
+            hook(*st.range_of(c.pfx + "embed."))
 
     # ------------------------------------------------------------------------------------------
     # CTC head (nets/ctc.py:28-30): logits = ctc_lo(dropout(h)); dropout p must be 0 here
@@ -455,15 +502,17 @@ class Engine:
 
     def decoder_bwd(self, c: NS, dlogits, dmem32: torch.Tensor) -> None:
         """dlogits (B*L, V) adt view; dmem32 (B*T', d) fp32 is accumulated into (memory gradient)."""
-        st = self.st
+        st, g = self.st, self.st.g
         dfin = self.linear_bwd(dlogits, c.fin.y, c.pfx + "linear_out")
         dres = _empty((c.B * c.L, c.d), torch.float32, self.dev)
-        self.layernorm_bwd(c.fin, dfin, dres, accumulate=False)
-        for i in range(len(c.layers) - 1, -1, -1):
+        n = len(c.layers)
+        dy = self.layernorm_bwd(c.fin, dfin, dres, False, (g(f"{c.pfx}dec_layers.{n - 1}.feed_forward.fc2.bias"), 1.0) if n else None)
+        for i in range(n - 1, -1, -1):
             c1, c2, c3 = c.layers[i]
-            self.ffn_bwd(c3, dres)
-            self.src_mha_bwd(c2, dres, dmem32)
-            self.self_mha_bwd(c1, dres)
+            lp = f"{c.pfx}dec_layers.{i}"
+            dy = self.ffn_bwd(c3, dres, dy, (g(lp + ".src_attn.linear_o.bias"), 1.0))
+            dy = self.src_mha_bwd(c2, dres, dy, dmem32, (g(lp + ".self_attn.linear_o.bias"), 1.0))
+            dy = self.self_mha_bwd(c1, dres, dy, (g(f"{c.pfx}dec_layers.{i - 1}.feed_forward.fc2.bias"), 1.0) if i > 0 else None)
         ops.embed_bwd(c.ys, dres, st.g(c.pfx + "embed.weight"), math.sqrt(c.d))
         if st.grad_ready_hook is not None:
             st.grad_ready_hook(*st.range_of(c.pfx))

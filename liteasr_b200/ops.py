@@ -42,9 +42,10 @@ def gemm(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, m: int, n: int, k: i
          ta: bool = False, tb: bool = False, bias: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None,
          ldres: int = 0, aux: Optional[torch.Tensor] = None, alpha: float = 1.0, act: int = ACT_NONE,
          accumulate: bool = False, split_k: int = 1, batch: Tuple[int, int] = (1, 1), sa: Tuple[int, int] = (0, 0),
-         sb: Tuple[int, int] = (0, 0), sc: Tuple[int, int] = (0, 0)) -> None:
+         sb: Tuple[int, int] = (0, 0), sc: Tuple[int, int] = (0, 0), dact: Optional[torch.Tensor] = None,
+         colsum: Optional[torch.Tensor] = None, cs: Tuple[int, int] = (0, 0)) -> None:
     """C[b1,b2] = alpha * act(A.B^T + bias) (+ res); see include/lasr.h ``lasr_gemm``."""
-    _require_cuda(a, b, c, bias, res, aux)
+    _require_cuda(a, b, c, bias, res, aux, dact, colsum)
     if a.dtype != b.dtype:
         raise TypeError("gemm operands must share a dtype")
     g = _lib.GemmArgs()
@@ -61,6 +62,14 @@ def gemm(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, m: int, n: int, k: i
     g.sb1, g.sb2 = sb
     g.sc1, g.sc2 = sc
     g.alpha, g.act, g.accumulate, g.split_k = alpha, act, int(accumulate), split_k
+    g.dact = dact.data_ptr() if dact is not None else None
+    g.lddact = dact.stride(0) if dact is not None else 0
+    g.colsum = colsum.data_ptr() if colsum is not None else None
+    g.cs1, g.cs2 = cs
+    if dact is not None and (dact.dtype != a.dtype or dact.dim() != 2 or dact.stride(1) != 1):
+        raise TypeError("dact must be a 2-D row-major tensor of the operand dtype")
+    if colsum is not None and colsum.dtype != torch.float32:
+        raise TypeError("colsum must be fp32")
     if bias is not None and bias.dtype != torch.float32:
         raise TypeError("bias must be fp32")
     if res is not None and res.dtype != torch.float32:
@@ -167,12 +176,16 @@ def layernorm_fwd(x, gamma, beta, y, mean=None, rstd=None, eps=1e-12):
     return y
 
 
-def layernorm_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, accumulate: bool):
-    _require_cuda(dy, x, dx)
+def layernorm_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, accumulate: bool, dx_lo=None, colsum=None, colsum_scale=1.0):
+    """dx (+)= LN'(dy); optional fused outputs: dx_lo (bf16 copy of the final dx), colsum += colsum_scale * sum_rows dx."""
+    _require_cuda(dy, x, dx, dx_lo, colsum)
     rows, d = x.shape
+    if dx_lo is not None and dx_lo.dtype != torch.bfloat16:
+        raise TypeError("dx_lo must be bf16")
     _lib.check(_lib.lib().lasr_layernorm_bwd(_ptr(dy), _i(dtype_code(dy)), _l(dy.stride(0)), _ptr(x), _l(x.stride(0)), _ptr(mean),
                                              _ptr(rstd), _ptr(gamma), _ptr(dx), _l(dx.stride(0)), _i(accumulate), _ptr(dgamma),
-                                             _ptr(dbeta), _i(rows), _i(d), _stream()), "layernorm_bwd")
+                                             _ptr(dbeta), _i(rows), _i(d), _ptr(dx_lo), _l(dx_lo.stride(0) if dx_lo is not None else 0),
+                                             _ptr(colsum), _f(colsum_scale), _stream()), "layernorm_bwd")
 
 
 def act_bwd(da, saved, dh, dbias, act, scale=1.0):
@@ -190,10 +203,10 @@ def pos_bias_fwd(q, u, v, qu, qv):
                                             _i(rows), _i(d), _i(dtype_code(q)), _stream()), "pos_bias_fwd")
 
 
-def pos_bias_bwd(dqu, dqv, dq, du, dv):
+def pos_bias_bwd(dqu, dqv, dq, du, dv, dqbias=None):
     rows, d = dqu.shape
     _lib.check(_lib.lib().lasr_pos_bias_bwd(_ptr(dqu), _ptr(dqv), _l(dqu.stride(0)), _ptr(dq), _l(dq.stride(0)), _ptr(du), _ptr(dv),
-                                            _i(rows), _i(d), _i(dtype_code(dqu)), _stream()), "pos_bias_bwd")
+                                            _ptr(dqbias), _i(rows), _i(d), _i(dtype_code(dqu)), _stream()), "pos_bias_bwd")
 
 
 def embed_fwd(tokens, emb, pe, out, scale):
@@ -235,10 +248,10 @@ def bn_swish_bwd_stats(da, z, mean, rstd, gamma, beta, partial, sums, dgamma, db
                "bn_swish_bwd_stats")
 
 
-def dwconv_glu_bwd(da, z, y2, mean, rstd, gamma, beta, sums, w, dy2, dw, dbias, B, T, d):
+def dwconv_glu_bwd(da, z, y2, mean, rstd, gamma, beta, sums, w, dy2, dw, dbias, B, T, d, colsum=None):
     _lib.check(_lib.lib().lasr_dwconv_glu_bwd(_ptr(da), _ptr(z), _ptr(y2), _i(dtype_code(y2)), _l(y2.stride(0)), _ptr(mean), _ptr(rstd),
                                               _ptr(gamma), _ptr(beta), _ptr(sums), _ptr(w), _ptr(dy2), _l(dy2.stride(0)), _ptr(dw),
-                                              _ptr(dbias), _i(B), _i(T), _i(d), _stream()), "dwconv_glu_bwd")
+                                              _ptr(dbias), _ptr(colsum), _i(B), _i(T), _i(d), _stream()), "dwconv_glu_bwd")
 
 
 def conv1_fwd(x, w, bias, h1):

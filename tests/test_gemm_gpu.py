@@ -148,3 +148,47 @@ def test_gemm_bad_args_raise():
         ops.gemm(a, a, c, 8, 8, 8, lda=8, ldb=8, ldc=8, split_k=2)  # split_k without accumulate
     with pytest.raises(RuntimeError):
         ops.gemm(a, a, c, 8, 8, 8, lda=9, ldb=8, ldc=8)  # unaligned TMA stride
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("act", ["swish", "relu"])
+@pytest.mark.parametrize("m,n,k", [(333, 320, 256), (1000, 2048, 256), (77, 100, 64)])
+def test_gemm_fused_activation_backward_and_colsum(dtype, act, m, n, k):
+    """dgrad epilogue: C = alpha * (dy @ W) * act'(saved), colsum += sum_rows C (bias gradient) -- nets/feed_forward.py:18-19 backward."""
+    from liteasr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(m + n)
+    dy, w = _mk(m, k, dtype, g), _mk(k, n, dtype, g)   # W stored (N_out=k, K_in=n): dx = dy @ W
+    saved = _mk(m, n, dtype, g)
+    cs = torch.randn(n, generator=g, device="cuda")
+    cs0 = cs.clone()
+    ld = (n + 7) // 8 * 8
+    out = torch.empty(m, ld, device="cuda", dtype=dtype)[:, :n]
+    code = ops.ACT_SWISH if act == "swish" else ops.ACT_RELU
+    ops.gemm(dy, w, out, m, n, k, lda=dy.stride(0), ldb=w.stride(0), ldc=ld, tb=True, alpha=0.5, dact=saved, act=code, colsum=cs)
+    sv = saved.float()
+    sg = torch.sigmoid(sv)
+    dact = sg * (1 + sv * (1 - sg)) if act == "swish" else (sv > 0).float()
+    ref = 0.5 * (dy.float() @ w.float()) * dact
+    tol = 3e-2 if dtype == torch.bfloat16 else 1e-4
+    assert (out.float() - ref).abs().max().item() <= tol * max(1.0, ref.abs().max().item())
+    assert (cs - cs0 - ref.sum(0)).abs().max().item() <= tol * max(1.0, ref.sum(0).abs().max().item())
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_gemm_batched_colsum_per_head(dtype):
+    """dK-style GEMM: C (B,T,H,dk) head-interleaved; colsum[h*dk + c] += sum over batch and rows (k-projection bias gradient)."""
+    from liteasr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(21)
+    B, T, H, dk, Tp = 3, 77, 2, 64, 80
+    d = H * dk
+    ds = torch.zeros(B, H, T, Tp, device="cuda", dtype=dtype)
+    ds[..., :T] = (torch.randn(B, H, T, T, generator=g, device="cuda") * 0.3).to(dtype)
+    q = (torch.randn(B, T, H, dk, generator=g, device="cuda") * 0.3).to(dtype)
+    dkk = torch.empty(B, T, H, dk, device="cuda", dtype=dtype)
+    cs = torch.zeros(d, device="cuda")
+    ops.gemm(ds, q, dkk, T, dk, T, lda=Tp, ldb=d, ldc=d, ta=True, tb=True, batch=(B, H), sa=(H * T * Tp, T * Tp), sb=(T * d, dk),
+             sc=(T * d, dk), colsum=cs, cs=(0, dk))
+    ref = torch.einsum("bhij,bihd->bjhd", ds[..., :T].float(), q.float())
+    tol = 2e-2 if dtype == torch.bfloat16 else 1e-4
+    assert (dkk.float() - ref).abs().max().item() <= tol * max(1.0, ref.abs().max().item())
+    assert (cs - ref.sum((0, 1)).reshape(-1)).abs().max().item() <= tol * max(1.0, ref.sum((0, 1)).abs().max().item())
