@@ -86,6 +86,10 @@ typedef struct lasr_gemm_args {
     int64_t lddact;
     float* colsum;
     int64_t cs1, cs2;
+    /* n_store: 0, or n <= n_store <= ldc: columns [n, n_store) of C are also written (with zeros: B has no such rows).
+     * Lets a ragged N (T' = 299 attention scores in a 304-wide buffer) run entirely on the vector epilogue; the consumer
+     * ignores those padding columns.  No bias/res/aux/dact/colsum. */
+    int32_t n_store;
 } lasr_gemm_args;
 
 int lasr_gemm(const lasr_gemm_args* args, void* stream);
@@ -163,7 +167,9 @@ int lasr_scale_by_scalar(void* x, int dtype, int64_t n, const float* scalar, voi
  *                training=0 -> mean/rstd from the running statistics.
  *   bwd_stats : partial (ceil(rows/32)*2*d) -> sums[0:d] = sum du, sums[d:2d] = sum du*zhat; dgamma/dbeta +=
  *   dwconv_glu_bwd: dy2 (B*T',2d), dw (d,15) += , dbias (d) += , optional colsum (2d) += sum_rows dy2
- *                   (pointwise_conv1's bias gradient, taken while the rows are on chip)
+ *                   (pointwise_conv1's bias gradient, taken while the rows are on chip); optional wpartial
+ *                   (B*ceil(T'/32)*18*d floats): per-CTA partials + a second reduction kernel instead of atomics
+ *                   (deterministic, and no same-address contention on the 16 KB of depthwise gradients)
  * ------------------------------------------------------------------------------------------------ */
 int lasr_glu_dwconv_fwd(const void* y2, int dtype, int64_t ldy, const float* w, const float* bias, float* z, float* partial,
                         int B, int T, int d, void* stream);
@@ -176,7 +182,7 @@ int lasr_bn_swish_bwd_stats(const void* da, int dtype, const float* z, const flo
                             void* stream);
 int lasr_dwconv_glu_bwd(const void* da, const float* z, const void* y2, int dtype, int64_t ldy, const float* mean, const float* rstd,
                         const float* gamma, const float* beta, const float* sums, const float* w, void* dy2, int64_t lddy, float* dw,
-                        float* dbias, float* colsum, int B, int T, int d, void* stream);
+                        float* dbias, float* colsum, float* wpartial, int B, int T, int d, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Conv2d subsampling (nets/subsampling.py:32-35,42-46), channel-last.

@@ -52,6 +52,9 @@ int lasr_gemm(const lasr_gemm_args* a, void* stream) {
         LASR_REQUIRE(!a->bias && !a->res && !a->aux && (a->act == LASR_ACT_SWISH || a->act == LASR_ACT_RELU) && a->lddact > 0,
                      "gemm: dact needs act = swish|relu and no bias/res/aux");
     if (a->split_k > 1) LASR_REQUIRE(a->accumulate, "gemm: split_k > 1 requires accumulate");
+    if (a->n_store)
+        LASR_REQUIRE(a->n_store >= a->n && a->n_store <= a->ldc && !a->bias && !a->res && !a->aux && !a->dact && !a->colsum && !a->accumulate,
+                     "gemm: n_store must satisfy n <= n_store <= ldc and excludes every epilogue operand");
     cudaStream_t st = (cudaStream_t)stream;
     if (a->ab_dtype == LASR_BF16) return gemm_tc_dispatch(a, st);
     if (a->ab_dtype == LASR_F32) {

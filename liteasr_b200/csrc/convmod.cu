@@ -352,7 +352,8 @@ __global__ void __launch_bounds__(256) dwconv_glu_bwd_kernel(const TD* __restric
                                                              const float* __restrict__ beta, const float* __restrict__ sums,
                                                              const float* __restrict__ w, TD* __restrict__ dy2, long lddy,
                                                              float* __restrict__ dw, float* __restrict__ dbias,
-                                                             float* __restrict__ colsum, int T, int d, float inv_count) {
+                                                             float* __restrict__ colsum, float* __restrict__ wpartial, int T, int d,
+                                                             float inv_count) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
     const int b = blockIdx.y, c0 = blockIdx.z * CB, t0 = blockIdx.x * TCH;
@@ -448,10 +449,33 @@ __global__ void __launch_bounds__(256) dwconv_glu_bwd_kernel(const TD* __restric
         const int k = idx / CB, cc = idx % CB;
         if (c0 + cc >= d) continue;
         const float v = (red[idx] + red[NRED * CB + idx]) + (red[2 * NRED * CB + idx] + red[3 * NRED * CB + idx]);
+        if (wpartial) {  // deterministic two-stage reduction: [CTA (b, chunk)][NRED][d], summed by dwconv_reduce_kernel
+            wpartial[(((long)b * gridDim.x + blockIdx.x) * NRED + k) * d + c0 + cc] = v;
+            continue;
+        }
         if (k < KW) atomicAdd(dw + (long)(c0 + cc) * KW + k, v);
         else if (k == KW) atomicAdd(dbias + c0 + cc, v);
         else if (colsum) atomicAdd(colsum + (k == KW + 1 ? 0 : d) + c0 + cc, v);
     }
+}
+
+// second stage of the depthwise-weight / bias / pointwise-bias gradient: block (32 channels, 8 row groups), grid (d/32, KW+3)
+__global__ void __launch_bounds__(256) dwconv_reduce_kernel(const float* __restrict__ wpartial, int nblk, int d, float* __restrict__ dw,
+                                                            float* __restrict__ dbias, float* __restrict__ colsum) {
+    __shared__ float sh[8][33];
+    constexpr int NRED = KW + 3;
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5, c = blockIdx.x * 32 + cx, k = blockIdx.y;
+    float s = 0.f;
+    if (c < d)
+        for (int i = ry; i < nblk; i += 8) s += wpartial[((long)i * NRED + k) * d + c];
+    sh[ry][cx] = s;
+    __syncthreads();
+    if (ry != 0 || c >= d) return;
+#pragma unroll
+    for (int j = 1; j < 8; ++j) s += sh[j][cx];
+    if (k < KW) dw[(long)c * KW + k] += s;
+    else if (k == KW) dbias[c] += s;
+    else if (colsum) colsum[(k == KW + 1 ? 0 : d) + c] += s;
 }
 
 }  // namespace lasr
@@ -529,7 +553,7 @@ int lasr_bn_swish_bwd_stats(const void* da, int dtype, const float* z, const flo
 
 int lasr_dwconv_glu_bwd(const void* da, const float* z, const void* y2, int dtype, int64_t ldy, const float* mean, const float* rstd,
                         const float* gamma, const float* beta, const float* sums, const float* w, void* dy2, int64_t lddy, float* dw,
-                        float* dbias, float* colsum, int B, int T, int d, void* stream) {
+                        float* dbias, float* colsum, float* wpartial, int B, int T, int d, void* stream) {
     LASR_REQUIRE(da && z && y2 && mean && rstd && gamma && beta && sums && w && dy2 && dw && dbias && B > 0 && T > 0 && d % 2 == 0 &&
                      ldy % 2 == 0 && lddy % 2 == 0, "dwconv_glu_bwd: bad args");
     const float inv = 1.f / (float)((long)B * T);
@@ -550,11 +574,14 @@ int lasr_dwconv_glu_bwd(const void* da, const float* z, const void* y2, int dtyp
         }
         if (dtype == LASR_F32)
             dwconv_glu_bwd_kernel<float><<<grid, 256, smem, st>>>((const float*)da, z, (const float*)y2, ldy, mean, rstd, gamma, beta, sums, w,
-                                                                 (float*)dy2, lddy, dw, dbias, colsum, T, d, inv);
+                                                                 (float*)dy2, lddy, dw, dbias, colsum, wpartial, T, d, inv);
         else
             dwconv_glu_bwd_kernel<bf16><<<grid, 256, smem, st>>>((const bf16*)da, z, (const bf16*)y2, ldy, mean, rstd, gamma, beta, sums, w,
-                                                                (bf16*)dy2, lddy, dw, dbias, colsum, T, d, inv);
-        return check_launch("dwconv_glu_bwd");
+                                                                (bf16*)dy2, lddy, dw, dbias, colsum, wpartial, T, d, inv);
+        int rc = check_launch("dwconv_glu_bwd");
+        if (rc || !wpartial) return rc;
+        dwconv_reduce_kernel<<<dim3(ceil_div(d, 32), KW + 3), 256, 0, st>>>(wpartial, B * ceil_div(T, TCH), d, dw, dbias, colsum);
+        return check_launch("dwconv_reduce");
     }
     dim3 grid(ceil_div(T, TCH), B);
     if (dtype == LASR_F32)

@@ -27,6 +27,7 @@ struct SimtParams {
     long lddact;
     float* colsum;
     long cs1, cs2;
+    int n_store;
 };
 
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams p) {
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams p) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int n = n0 + tx * 4 + j;
-            if (n >= p.n) continue;
+            if (n >= p.n_store) continue;
             const long off = boff + (long)m * p.ldc + n;
             if (p.accumulate) {
                 atomicAdd(p.c + off, p.alpha * (float)acc[i][j]);
@@ -128,8 +129,9 @@ int gemm_simt_dispatch(const lasr_gemm_args* a, cudaStream_t st) {
     p.ldc = a->ldc; p.ldres = a->ldres; p.batch2 = a->batch2;
     p.sa1 = a->sa1; p.sa2 = a->sa2; p.sb1 = a->sb1; p.sb2 = a->sb2; p.sc1 = a->sc1; p.sc2 = a->sc2;
     p.alpha = a->alpha; p.act = a->act; p.accumulate = a->accumulate; p.split_k = a->split_k < 1 ? 1 : a->split_k;
+    p.n_store = a->n_store ? a->n_store : a->n;
     p.dact = (const float*)a->dact; p.lddact = a->lddact; p.colsum = a->colsum; p.cs1 = a->cs1; p.cs2 = a->cs2;
-    dim3 grid(ceil_div(a->m, SBM), ceil_div(a->n, SBN), a->batch1 * a->batch2 * p.split_k);
+    dim3 grid(ceil_div(a->m, SBM), ceil_div(p.n_store, SBN), a->batch1 * a->batch2 * p.split_k);
     gemm_simt_kernel<<<grid, 256, 0, st>>>(p);
     return check_launch("gemm_simt");
 }

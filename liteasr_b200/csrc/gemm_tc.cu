@@ -53,6 +53,7 @@ struct TcParams {
     long sc1, sc2;
     int a_b1, a_b2, b_b1, b_b2;  // 1 if the operand really advances along that batch level
     int a_mn, b_mn;              // operand majors (0 = K-major, 1 = MN-major)
+    int n_store;                 // columns of C that are written (>= n; the extra ones see a zero accumulator)
     float alpha;
     int act;
     int accumulate;
@@ -224,7 +225,7 @@ template <typename CT, int MODE>
 __device__ __forceinline__ void epilogue_unit(const TcParams& p, const Unit& w, uint32_t tmem_acc, uint8_t* stage, int q, int part,
                                               int lane) {
     const long boff = (long)w.b1 * p.sc1 + (long)w.b2 * p.sc2;
-    const int col_limit = min(p.n, w.n0 + p.bn);
+    const int col_limit = min(p.n_store, w.n0 + p.bn);
     const int row_base = w.m0 + q * 32;
     const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
     const int chunk = lane & 7, rsub = lane >> 3;
@@ -243,24 +244,27 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, const Unit& w, 
     for (int cc = part * 32; cc < p.bn; cc += 32 * (EPI_WARPS / 4)) {
         const int col = w.n0 + cc + chunk * 4;  // this lane's 4 columns in the column phase
         if (w.n0 + cc >= col_limit) break;      // warp-uniform
-        const bool fast = (MODE != EPI_GENERIC) && p.vec_ok && (w.n0 + cc + 32 <= col_limit);
+        // vector path: whole 32-column chunks, or a partial chunk whose edge falls on a 4-column boundary (then each lane's
+        // 4 columns are all inside or all outside: N = 304 score tiles, N = 4240 padded vocabularies)
+        const bool fast = (MODE != EPI_GENERIC) && p.vec_ok && ((w.n0 + cc + 32 <= col_limit) || (col_limit & 3) == 0);
+        const bool lane_ok = col < col_limit;
         // prefetch what the column phase needs from global memory before touching TMEM
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         float4 r4[8];
         uint2 s2[8];
         if (fast) {
-            if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+            if (p.bias && lane_ok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
             if constexpr (DACT) {
                 const bf16* sp = dbase + (long)(row_base + rsub) * p.lddact + col;
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
-                    s2[i] = (4 * i < nrows) ? *reinterpret_cast<const uint2*>(sp + (long)(4 * i) * p.lddact) : make_uint2(0u, 0u);
+                    s2[i] = (4 * i < nrows && lane_ok) ? *reinterpret_cast<const uint2*>(sp + (long)(4 * i) * p.lddact) : make_uint2(0u, 0u);
             }
             if constexpr (MODE == EPI_RES) {
                 const float* rp = rbase + (long)(row_base + rsub) * p.ldres + col;
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
-                    r4[i] = (4 * i < nrows) ? *reinterpret_cast<const float4*>(rp + (long)(4 * i) * p.ldres) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    r4[i] = (4 * i < nrows && lane_ok) ? *reinterpret_cast<const float4*>(rp + (long)(4 * i) * p.ldres) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         } else if (p.bias) {
             b4.x = (col + 0 < col_limit) ? __ldg(p.bias + col + 0) : 0.f;
@@ -290,7 +294,7 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, const Unit& w, 
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 float4 f = *reinterpret_cast<const float4*>(((i & 1) ? rd1 : rd0) + i * 512);
-                if (4 * i < nrows) {
+                if (4 * i < nrows && lane_ok) {
                     if constexpr (MODE == EPI_PLAIN) {
                         f.x = fmaf(f.x, alpha, ba.x); f.y = fmaf(f.y, alpha, ba.y); f.z = fmaf(f.z, alpha, ba.z); f.w = fmaf(f.w, alpha, ba.w);
                         store4<CT>(crow, f);
@@ -333,7 +337,7 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, const Unit& w, 
                     cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 8); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 8);
                     cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 16); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 16);
                     cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 16); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 16);
-                    if (rsub == 0) red_add_f32x4(csbase + col, cs);
+                    if (rsub == 0 && lane_ok) red_add_f32x4(csbase + col, cs);
                 }
             }
         } else {  // ragged N edge, unaligned C or an unusual flag combination: element-wise, compact (not unrolled)
@@ -616,7 +620,8 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParam
 }
 
 int gemm_tc_dispatch(const lasr_gemm_args* a, cudaStream_t st) {
-    const int bn = pick_bn(a->n, a->trans_b ? 64 : 16);
+    const int n_store = a->n_store ? a->n_store : a->n;
+    const int bn = pick_bn(n_store, a->trans_b ? 64 : 16);
     CUtensorMap ma, mb;
     int rc;
     if (!a->trans_a) rc = make_map(&ma, a->a, a->k, a->m, a->lda, a->batch2, a->sa2, a->batch1, a->sa1, BK, BM);
@@ -661,7 +666,8 @@ int gemm_tc_dispatch(const lasr_gemm_args* a, cudaStream_t st) {
     p.stages = SM_RING_BUDGET / p.stage_bytes;
     if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
     p.tiles_m = ceil_div(a->m, BM);
-    p.tiles_n = ceil_div(a->n, bn);
+    p.tiles_n = ceil_div(n_store, bn);
+    p.n_store = n_store;
     const long units = (long)p.tiles_m * p.tiles_n * p.split_k * a->batch1 * a->batch2;
     if (units > 0x7fffffffL) {
         set_error("gemm_tc: too many work units");

@@ -179,13 +179,14 @@ class Engine:
         ld = _ceil(Tk, 8)
         scale = dk ** -0.5
         ac = _empty((B, H, Tq, ld), torch.float32, self.dev)
+        # n_store = ld: the padding columns [Tk, ld) are written too (zeros), which keeps the whole epilogue on the vector path
         ops.gemm(q, k, ac, Tq, Tk, dk, lda=q.stride(0), ldb=k.stride(0), ldc=ld, batch=(B, H), sa=(Tq * q.stride(0), dk),
-                 sb=(Tk * k.stride(0), dk), sc=(H * Tq * ld, Tq * ld))
+                 sb=(Tk * k.stride(0), dk), sc=(H * Tq * ld, Tq * ld), n_store=ld)
         bd = None
         if qv is not None:  # rel-pos term (q + v_bias) . P^T, P broadcast over the batch
             bd = _empty((B, H, Tq, ld), torch.float32, self.dev)
             ops.gemm(qv, p, bd, Tq, Tk, dk, lda=qv.stride(0), ldb=p.stride(0), ldc=ld, batch=(B, H),
-                     sa=(Tq * qv.stride(0), dk), sb=(0, dk), sc=(H * Tq * ld, Tq * ld))
+                     sa=(Tq * qv.stride(0), dk), sb=(0, dk), sc=(H * Tq * ld, Tq * ld), n_store=ld)
         probs = _empty((B, H, Tq, ld), self.adt, self.dev)
         ops.attn_softmax_fwd(ac, bd, probs, lens, mask_mode, causal, scale, Tk)
         o = _empty((B * Tq, d), self.adt, self.dev)
@@ -200,7 +201,7 @@ class Engine:
         bs = (H * Tq * ld, Tq * ld)
         dprobs = _empty((B, H, Tq, ld), torch.float32, self.dev)
         ops.gemm(do, c.v, dprobs, Tq, Tk, dk, lda=do.stride(0), ldb=c.v.stride(0), ldc=ld, batch=(B, H), sa=(Tq * do.stride(0), dk),
-                 sb=(Tk * c.v.stride(0), dk), sc=bs)
+                 sb=(Tk * c.v.stride(0), dk), sc=bs, n_store=ld)
         # dV[j] = sum_i probs[i,j] dO[i]
         ops.gemm(c.probs, do, dv, Tk, dk, Tq, lda=ld, ldb=do.stride(0), ldc=dv.stride(0), ta=True, tb=True, batch=(B, H), sa=bs,
                  sb=(Tq * do.stride(0), dk), sc=(Tk * dv.stride(0), dk), colsum=bv, cs=(0, dk))
@@ -338,9 +339,10 @@ class Engine:
         gam, bet = st.p(pfx + ".norm.weight"), st.p(pfx + ".norm.bias")
         ops.bn_swish_bwd_stats(da, c.z, c.mean, c.rstd, gam, bet, partial, sums, st.g(pfx + ".norm.weight"), st.g(pfx + ".norm.bias"))
         dy2 = _empty((rows, 2 * d), self.adt, self.dev)
+        wpart = _empty((c.B * ((c.T + 31) // 32), KW + 3, d), torch.float32, self.dev) if d % 4 == 0 else None
         ops.dwconv_glu_bwd(da, c.z, c.y2, c.mean, c.rstd, gam, bet, sums, st.p(pfx + ".depthwise_conv.weight").view(d, KW), dy2,
                            st.g(pfx + ".depthwise_conv.weight").view(d, KW), st.g(pfx + ".depthwise_conv.bias"), c.B, c.T, d,
-                           colsum=st.g(pfx + ".pointwise_conv1.bias"))
+                           colsum=st.g(pfx + ".pointwise_conv1.bias"), wpartial=wpart)
         self.wgrad(dy2, c.ln.y, st.gw(pfx + ".pointwise_conv1.weight"))
         dln = self.dgrad(dy2, st.w(pfx + ".pointwise_conv1.weight"))
         return self.layernorm_bwd(c.ln, dln, dres, True, nxt, want_lo)

@@ -43,7 +43,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, m: int, n: int, k: i
          ldres: int = 0, aux: Optional[torch.Tensor] = None, alpha: float = 1.0, act: int = ACT_NONE,
          accumulate: bool = False, split_k: int = 1, batch: Tuple[int, int] = (1, 1), sa: Tuple[int, int] = (0, 0),
          sb: Tuple[int, int] = (0, 0), sc: Tuple[int, int] = (0, 0), dact: Optional[torch.Tensor] = None,
-         colsum: Optional[torch.Tensor] = None, cs: Tuple[int, int] = (0, 0)) -> None:
+         colsum: Optional[torch.Tensor] = None, cs: Tuple[int, int] = (0, 0), n_store: int = 0) -> None:
     """C[b1,b2] = alpha * act(A.B^T + bias) (+ res); see include/lasr.h ``lasr_gemm``."""
     _require_cuda(a, b, c, bias, res, aux, dact, colsum)
     if a.dtype != b.dtype:
@@ -66,6 +66,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, m: int, n: int, k: i
     g.lddact = dact.stride(0) if dact is not None else 0
     g.colsum = colsum.data_ptr() if colsum is not None else None
     g.cs1, g.cs2 = cs
+    g.n_store = n_store
     if dact is not None and (dact.dtype != a.dtype or dact.dim() != 2 or dact.stride(1) != 1):
         raise TypeError("dact must be a 2-D row-major tensor of the operand dtype")
     if colsum is not None and colsum.dtype != torch.float32:
@@ -248,10 +249,10 @@ def bn_swish_bwd_stats(da, z, mean, rstd, gamma, beta, partial, sums, dgamma, db
                "bn_swish_bwd_stats")
 
 
-def dwconv_glu_bwd(da, z, y2, mean, rstd, gamma, beta, sums, w, dy2, dw, dbias, B, T, d, colsum=None):
+def dwconv_glu_bwd(da, z, y2, mean, rstd, gamma, beta, sums, w, dy2, dw, dbias, B, T, d, colsum=None, wpartial=None):
     _lib.check(_lib.lib().lasr_dwconv_glu_bwd(_ptr(da), _ptr(z), _ptr(y2), _i(dtype_code(y2)), _l(y2.stride(0)), _ptr(mean), _ptr(rstd),
                                               _ptr(gamma), _ptr(beta), _ptr(sums), _ptr(w), _ptr(dy2), _l(dy2.stride(0)), _ptr(dw),
-                                              _ptr(dbias), _ptr(colsum), _i(B), _i(T), _i(d), _stream()), "dwconv_glu_bwd")
+                                              _ptr(dbias), _ptr(colsum), _ptr(wpartial), _i(B), _i(T), _i(d), _stream()), "dwconv_glu_bwd")
 
 
 def conv1_fwd(x, w, bias, h1):

@@ -192,3 +192,20 @@ def test_gemm_batched_colsum_per_head(dtype):
     tol = 2e-2 if dtype == torch.bfloat16 else 1e-4
     assert (dkk.float() - ref).abs().max().item() <= tol * max(1.0, ref.abs().max().item())
     assert (cs - ref.sum((0, 1)).reshape(-1)).abs().max().item() <= tol * max(1.0, ref.sum((0, 1)).abs().max().item())
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_gemm_n_store_pads_with_zeros(dtype):
+    """Attention-score call: N = 299 keys in a 304-wide buffer, n_store = 304 -> padding columns written as zeros."""
+    from liteasr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(31)
+    B, H, T, dk, ld = 2, 2, 299, 64, 304
+    d = H * dk
+    q = (torch.randn(B, T, H, dk, generator=g, device="cuda") * 0.3).to(dtype)
+    kk = (torch.randn(B, T, H, dk, generator=g, device="cuda") * 0.3).to(dtype)
+    c = torch.full((B, H, T, ld), 5.0, device="cuda")
+    ops.gemm(q, kk, c, T, T, dk, lda=d, ldb=d, ldc=ld, batch=(B, H), sa=(T * d, dk), sb=(T * d, dk), sc=(H * T * ld, T * ld), n_store=ld)
+    ref = torch.einsum("bihd,bjhd->bhij", q.float(), kk.float())
+    tol = 2e-2 if dtype == torch.bfloat16 else 1e-4
+    assert (c[..., :T] - ref).abs().max().item() <= tol * ref.abs().max().item()
+    assert (c[..., T:] == 0).all()

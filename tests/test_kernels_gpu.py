@@ -105,6 +105,12 @@ def test_conv_module_middle_fwd_bwd(B, T, d, dtype):
     dw, dbias = torch.zeros(d, 15, device="cuda"), torch.zeros(d, device="cuda")
     cs = torch.zeros(2 * d, device="cuda")
     ops.dwconv_glu_bwd(da, z, y2.view(rows, 2 * d), mean, rstd, gamma, beta, sums, w, dy2, dw, dbias, B, T, d, colsum=cs)
+    # two-stage (deterministic) reduction of the same gradients
+    dw2, dbias2, cs2 = torch.zeros(d, 15, device="cuda"), torch.zeros(d, device="cuda"), torch.zeros(2 * d, device="cuda")
+    wpart = torch.empty(nblk, 18, d, device="cuda")
+    ops.dwconv_glu_bwd(da, z, y2.view(rows, 2 * d), mean, rstd, gamma, beta, sums, w, torch.empty_like(dy2), dw2, dbias2, B, T, d,
+                       colsum=cs2, wpartial=wpart)
+    assert _close(dw2, dw, 1e-4) and _close(dbias2, dbias, 1e-4) and _close(cs2, cs, 1e-4)
     tolg = 2e-4 if dtype == torch.float32 else 3e-2
     assert _close(dy2, y2f.grad.reshape(rows, 2 * d), tolg)
     assert _close(dw, wr.grad, tolg) and _close(dbias, br.grad, tolg)

@@ -88,6 +88,23 @@ def main(cases):
         dy = rnd(N, d)
         o = torch.empty(N, f, device=dev, dtype=bf)
         run("dgrad tb bf16 9568x2048x256", lambda: ops.gemm(dy, w2, o, N, f, d, lda=d, ldb=f, ldc=f, tb=True), 2 * N * d * f, N * d * 2 + N * f * 2)
+    if allc or "dswish" in cases:
+        dy = rnd(N, d)
+        h = rnd(N, f)
+        o = torch.empty(N, f, device=dev, dtype=bf)
+        cs = torch.zeros(f, device=dev)
+        run("dgrad dswish+colsum 9568x2048x256", lambda: ops.gemm(dy, w2, o, N, f, d, lda=d, ldb=f, ldc=f, tb=True, alpha=0.5, dact=h, act=ops.ACT_SWISH, colsum=cs),
+            2 * N * d * f, N * d * 2 + 2 * N * f * 2)
+        run("dgrad dswish        9568x2048x256", lambda: ops.gemm(dy, w2, o, N, f, d, lda=d, ldb=f, ldc=f, tb=True, alpha=0.5, dact=h, act=ops.ACT_SWISH),
+            2 * N * d * f, N * d * 2 + 2 * N * f * 2)
+        run("dgrad colsum        9568x2048x256", lambda: ops.gemm(dy, w2, o, N, f, d, lda=d, ldb=f, ldc=f, tb=True, colsum=cs),
+            2 * N * d * f, N * d * 2 + N * f * 2)
+    if allc or "scores" in cases:
+        B, H, T, dk, ld = 32, 4, 299, 64, 304
+        q, k = rnd(B * T, d), rnd(B * T, d)
+        ac = torch.empty(B, H, T, ld, device=dev)
+        run("scores f32 n_store=304", lambda: ops.gemm(q, k, ac, T, T, dk, lda=d, ldb=d, ldc=ld, batch=(B, H), sa=(T * d, dk), sb=(T * d, dk),
+                                                      sc=(H * T * ld, T * ld), n_store=ld), 2 * B * H * T * T * dk, 2 * N * d * 2 + B * H * T * ld * 4)
     if allc or "wgrad" in cases:
         dy = rnd(N, f)
         gw = torch.zeros(f, d, device=dev)
