@@ -4,29 +4,18 @@
 //   K_A  ctc_softmax_gather  (all SMs, HBM-bound): one read of the logits, one write of the gradient.
 //        per row (t,b): lse = logsumexp(x); grad = s * softmax(x)   (0 and NO read for t >= in_len[b]);
 //        lp_ext[b][t][0] = x[blank]-lse, lp_ext[b][t][k+1] = x[label_k]-lse  (compact lattice inputs).
-//   K_B  ctc_lattice (one CTA per utterance, latency-bound): thread k owns the state pair
-//        (blank 2k, label 2k+1); the only neighbour traffic per step is one warp shuffle (+ one
-//        shared-memory edge value per warp); alpha stored once, then overwritten in place by the
-//        occupancy exp(alpha+beta-lp+nll) during the beta sweep.  Inputs are register-prefetched one
-//        8-step block ahead so global latency never sits on the recursion's critical path.
-//   K_C  ctc_scatter (all SMs): grad[t,b,blank] -= s * sum_k occ_blank, grad[t,b,label_k] -= s * occ_label
-//        (red.add; only rows t < in_len[b], only L+1 addresses per row).
+//   K_B  ctc_lattice_warp (grid (B, 2): the alpha sweep and the beta sweep of an utterance run CONCURRENTLY on two CTAs;
+//        each thread owns R consecutive state pairs (blank 2k, label 2k+1) in registers, neighbours are registers /
+//        one warp shuffle / one shared-memory edge value per warp; L <= 63 labels fit ONE warp -> no barrier at all).
+//        The recursion is blank-normalised (a~_t(s) = alpha_t(s) - sum_{tau<=t} lp_tau(blank): |a~| ~ 1e2 instead of
+//        T log V ~ 1e4, 10x tighter in fp32) and its inputs are register-prefetched 8 steps ahead.
+//   K_C  ctc_scatter_ab (all SMs): occ = exp(alpha + beta - e - tot); grad[t,b,blank] -= s * sum_k occ_blank,
+//        grad[t,b,label_k] -= s * occ_label  (red.add; only rows t < in_len[b], only L+1 addresses per row).
 // Physical traffic is therefore ~1 read + 1 write of the (T,B,V) tensor plus O(T*B*L) lattice state,
 // instead of the ~7 dense passes of log_softmax + ctc_loss + their backward kernels.
 #include "common.cuh"
 
 namespace lasr {
-
-__device__ __forceinline__ float lse2f(float a, float b) {
-    const float m = fmaxf(a, b);
-    if (m == -INFINITY) return -INFINITY;
-    return m + log1pf(expf(fminf(a, b) - m));
-}
-__device__ __forceinline__ float lse3f(float a, float b, float c) {
-    const float m = fmaxf(fmaxf(a, b), c);
-    if (m == -INFINITY) return -INFINITY;
-    return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
-}
 
 // ---------------------------------------------------------------------------------------------
 // K_A
@@ -203,180 +192,245 @@ __global__ void __launch_bounds__(256) ctc_softmax_gather_generic(const CtcDense
 }
 
 // ---------------------------------------------------------------------------------------------
-// K_B  lattice: thread k owns states (2k = blank, 2k+1 = label k)
+// K_B lattice, register-resident.  grid (B, 2): y = 0 runs the alpha sweep, y = 1 the
+// beta sweep -- the two recursions are independent, so they run concurrently on different SMs and the occupancy
+// exp(alpha + beta - e - tot) is formed by the scatter kernel.  Lane l owns the R consecutive state pairs
+// k = l*R .. l*R + R-1 (W = lmax + 1 <= 32 R): inside a lane the neighbour values are registers, across lanes ONE warp
+// shuffle per step; there is no shared memory and no block barrier on the critical path, whose length per time step is
+// shfl + max + ex2 + add + lg2 (fast intrinsics: their 2^-22 error is below the fp32 ulp of the lattice values).
+// Inputs are register-prefetched PF steps ahead.
 // ---------------------------------------------------------------------------------------------
-constexpr int PF = 8;  // prefetch block (time steps)
+__device__ __forceinline__ float fexp(float x) { return __expf(x); }
+// Branch-free: states at -inf are the common case (unreachable / invalid lattice cells), and a data-dependent early return
+// makes every log-sum-exp a divergent region.  With ms = 0 when all inputs are -inf, exp(-inf - 0) = 0 and log(0) = -inf.
+__device__ __forceinline__ float lse2q(float a, float b) {
+    const float m = fmaxf(a, b);
+    const float ms = (m == -INFINITY) ? 0.f : m;
+    return ms + __logf(fexp(a - ms) + fexp(b - ms));
+}
+__device__ __forceinline__ float lse3q(float a, float b, float c) {
+    const float m = fmaxf(fmaxf(a, b), c);
+    const float ms = (m == -INFINITY) ? 0.f : m;
+    return ms + __logf(fexp(a - ms) + fexp(b - ms) + fexp(c - ms));
+}
 
-template <int MAXT>
-__global__ void __launch_bounds__(MAXT) ctc_lattice_kernel(const float* __restrict__ lp_ext, float2* __restrict__ ab,
-                                                           const int64_t* __restrict__ targets,
-                                                           const int64_t* __restrict__ in_len,
-                                                           const int64_t* __restrict__ tgt_len, float* __restrict__ nll,
-                                                           int T, int lmax) {
-    __shared__ float edge[2][2][32];  // [parity][value 0/1][warp]
+template <int R, int PFW, int NW>
+__global__ void __launch_bounds__(32 * NW) ctc_lattice_warp_kernel(const float* __restrict__ lp_ext, float2* __restrict__ al,
+                                                                   float2* __restrict__ be, const int64_t* __restrict__ targets,
+                                                                   const int64_t* __restrict__ in_len,
+                                                                   const int64_t* __restrict__ tgt_len, float* __restrict__ nll,
+                                                                   float* __restrict__ tot_out, int T, int lmax) {
+    __shared__ float edge[2][2][NW];  // [parity][value][warp]: boundary states handed to the neighbouring warp (NW > 1)
     __shared__ float fin[2];
-    const int b = blockIdx.x, k = threadIdx.x, lane = k & 31, warp = k >> 5;
-    const int nwarp = (blockDim.x + 31) >> 5;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool is_beta = blockIdx.y != 0;
     const int Tb = min((int)in_len[b], T), L = min((int)tgt_len[b], lmax);
     const int W = lmax + 1;
     if (Tb <= 0) {
-        if (k == 0) nll[b] = (L == 0) ? 0.f : INFINITY;
+        if (!is_beta && tid == 0) { nll[b] = (L == 0) ? 0.f : INFINITY; tot_out[b] = (L == 0) ? 0.f : -INFINITY; }
         return;
     }
     const int64_t* tg = targets + (long)b * lmax;
-    const long my = (k < L) ? tg[k] : -1;
-    const bool skip_a = (k >= 1 && k < L) && (tg[k - 1] != my);      // alpha: 2k-1 -> 2k+1 allowed
-    const bool skip_b = (k + 1 < L) && (tg[k + 1] != my);            // beta : 2k+1 -> 2k+3 allowed
-    const bool v_bl = k <= L, v_lb = k < L;
     const float* lpb = lp_ext + (long)b * T * W;
-    float2* abb = ab + (long)b * T * W;
-    const int kk = min(k, lmax);  // clamp so idle threads read valid memory
     const float NEG = -INFINITY;
+    int kcol[R];          // column of this pair's label emission in lp_ext (clamped: idle pairs read valid memory)
+    bool v_bl[R], v_lb[R], skip[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int k = tid * R + r;
+        kcol[r] = min(k, lmax - 1) + 1;
+        v_bl[r] = k <= L;
+        v_lb[r] = k < L;
+        const long my = (k < L) ? tg[k] : -1;
+        if (!is_beta) skip[r] = (k >= 1 && k < L) && (tg[k - 1] != my);   // alpha: 2k-1 -> 2k+1 allowed
+        else skip[r] = (k + 1 < L) && (tg[k + 1] != my);                    // beta : 2k+1 -> 2k+3 allowed
+    }
+    float s_bl[R], s_lb[R];
+    float cl[PFW][R], nl[PFW][R];
 
-    // Normalised recursion: a~_t(s) = alpha_t(s) - sum_{tau<=t} lp_tau(blank) (and the mirror image for
-    // beta).  Blank states then carry no emission term, label states add d_t(k) = x[label_k]-x[blank],
-    // and the big common offset C = sum_t lp_t(blank) cancels analytically in the occupancy:
-    //   occ_t(s) = exp(a~_t(s) + b~_t(s) - e_t(s) - tot~),  e = 0 (blank) | d_t(k) (label),  nll = -(tot~ + C).
-    // This keeps |a~| small (fp32 ulp ~1e-6) where raw log-alpha reaches T*log(V) ~ 1e4 (ulp ~1e-3).
-    // ---------------- alpha sweep ----------------
-    float a_bl, a_lb;
-    double csum = 0.0;
-    {
-        const float l0b = lpb[0], l0d = lpb[min(kk + 1, lmax)];
-        csum = (double)l0b;
-        a_bl = (k == 0) ? 0.f : NEG;
-        a_lb = (k == 0 && L > 0) ? l0d : NEG;
-        if (k < W) abb[k] = make_float2(a_bl, a_lb);
-        if (lane == 31) edge[0][0][warp] = a_lb;
-    }
-    __syncthreads();
-    float cb[PF], cl[PF], nb_[PF], nl_[PF];
+    if (!is_beta) {
+        // C = sum_t lp_t(blank) (double): the normalisation offset of the blank-normalised recursion (see ctc_lattice_kernel)
+        double csum = 0.0;
+        if (warp == 0) {
+            for (int t = lane; t < Tb; t += 32) csum += (double)lpb[(long)t * W];
 #pragma unroll
-    for (int i = 0; i < PF; ++i) {
-        const int t = min(1 + i, Tb - 1);
-        cb[i] = lpb[(long)t * W];
-        cl[i] = lpb[(long)t * W + min(kk + 1, lmax)];
-    }
-    for (int t0 = 1; t0 < Tb; t0 += PF) {
+            for (int o = 16; o > 0; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
+        }
+        float2* alb = al + (long)b * T * W;
 #pragma unroll
-        for (int i = 0; i < PF; ++i) {  // prefetch next block (clamped; unused values are harmless)
-            const int t = min(t0 + PF + i, Tb - 1);
-            nb_[i] = lpb[(long)t * W];
-            nl_[i] = lpb[(long)t * W + min(kk + 1, lmax)];
+        for (int r = 0; r < R; ++r) {
+            const int k = tid * R + r;
+            s_bl[r] = (k == 0) ? 0.f : NEG;
+            s_lb[r] = (k == 0 && L > 0) ? lpb[kcol[r]] : NEG;
+            if (k < W) alb[k] = make_float2(s_bl[r], s_lb[r]);
+        }
+        if (NW > 1) {
+            if (lane == 31) edge[0][0][warp] = s_lb[R - 1];
+            __syncthreads();
         }
 #pragma unroll
-        for (int i = 0; i < PF; ++i) {
-            const int t = t0 + i;
-            if (t < Tb) {  // uniform over the CTA
-                float nbv = __shfl_up_sync(0xffffffffu, a_lb, 1);
-                if (lane == 0) nbv = (warp > 0) ? edge[(t - 1) & 1][0][warp - 1] : NEG;
-                const float n_bl = lse2f(a_bl, nbv);
-                const float n_lb = cl[i] + lse3f(a_lb, a_bl, skip_a ? nbv : NEG);
-                a_bl = v_bl ? n_bl : NEG;
-                a_lb = v_lb ? n_lb : NEG;
-                csum += (double)cb[i];
-                if (lane == 31) edge[t & 1][0][warp] = a_lb;
-                if (k < W) abb[(long)t * W + k] = make_float2(a_bl, a_lb);
-                __syncthreads();
+        for (int i = 0; i < PFW; ++i) {
+            const int t = min(1 + i, Tb - 1);
+#pragma unroll
+            for (int r = 0; r < R; ++r) cl[i][r] = lpb[(long)t * W + kcol[r]];
+        }
+        for (int t0 = 1; t0 < Tb; t0 += PFW) {
+#pragma unroll
+            for (int i = 0; i < PFW; ++i) {
+                const int t = min(t0 + PFW + i, Tb - 1);
+#pragma unroll
+                for (int r = 0; r < R; ++r) nl[i][r] = lpb[(long)t * W + kcol[r]];
             }
-        }
 #pragma unroll
-        for (int i = 0; i < PF; ++i) { cb[i] = nb_[i]; cl[i] = nl_[i]; }
-    }
-    if (k == L) fin[0] = a_bl;
-    if (L > 0 && k == L - 1) fin[1] = a_lb;
-    if (L == 0 && k == 0) fin[1] = NEG;
-    __syncthreads();
-    const float tot = lse2f(fin[0], fin[1]);
-    if (k == 0) nll[b] = (float)(-((double)tot + csum));
-    const bool feasible = (tot > NEG);
-    const float qnan = __int_as_float(0x7fc00000);
-
-    // ---------------- beta sweep (t = Tb-1 handled with alpha still in registers) ----------------
-    float b_bl, b_lb;
-    {
-        const int t = Tb - 1;
-        const float ld_ = lpb[(long)t * W + min(kk + 1, lmax)];
-        b_bl = (k == L) ? 0.f : NEG;
-        b_lb = (L > 0 && k == L - 1) ? ld_ : NEG;
-        float o_bl = (a_bl > NEG && b_bl > NEG) ? expf(a_bl + b_bl - tot) : 0.f;
-        float o_lb = (a_lb > NEG && b_lb > NEG) ? expf(a_lb + b_lb - ld_ - tot) : 0.f;
-        if (!feasible) { o_bl = qnan; o_lb = qnan; }
-        if (k < W) abb[(long)t * W + k] = make_float2(o_bl, o_lb);
-        if (lane == 0) { edge[t & 1][0][warp] = b_bl; edge[t & 1][1][warp] = b_lb; }
-    }
-    __syncthreads();
-    float2 ca[PF], na[PF];
+            for (int i = 0; i < PFW; ++i) {
+                const int t = t0 + i;
+                if (t < Tb) {  // CTA-uniform
+                    float up = __shfl_up_sync(0xffffffffu, s_lb[R - 1], 1);
+                    if (lane == 0) up = (NW > 1 && warp > 0) ? edge[(t - 1) & 1][0][warp - 1] : NEG;
+                    float n_bl[R], n_lb[R];
 #pragma unroll
-    for (int i = 0; i < PF; ++i) {
-        const int t = max(Tb - 2 - i, 0);
-        cl[i] = lpb[(long)t * W + min(kk + 1, lmax)];
-        ca[i] = abb[(long)t * W + kk];
-    }
-    for (int t0 = Tb - 2; t0 >= 0; t0 -= PF) {
+                    for (int r = 0; r < R; ++r) {
+                        const float prev = (r == 0) ? up : s_lb[r - 1];   // alpha_{t-1}(2k-1)
+                        n_bl[r] = lse2q(s_bl[r], prev);
+                        n_lb[r] = cl[i][r] + lse3q(s_lb[r], s_bl[r], skip[r] ? prev : NEG);
+                    }
 #pragma unroll
-        for (int i = 0; i < PF; ++i) {
-            const int t = max(t0 - PF - i, 0);
-            nl_[i] = lpb[(long)t * W + min(kk + 1, lmax)];
-            na[i] = abb[(long)t * W + kk];
-        }
-#pragma unroll
-        for (int i = 0; i < PF; ++i) {
-            const int t = t0 - i;
-            if (t >= 0) {
-                float n1 = __shfl_down_sync(0xffffffffu, b_bl, 1);  // beta_{t+1}(2k+2)
-                float n2 = __shfl_down_sync(0xffffffffu, b_lb, 1);  // beta_{t+1}(2k+3)
-                if (lane == 31) {
-                    const bool has = warp + 1 < nwarp;
-                    n1 = has ? edge[(t + 1) & 1][0][warp + 1] : NEG;
-                    n2 = has ? edge[(t + 1) & 1][1][warp + 1] : NEG;
+                    for (int r = 0; r < R; ++r) {
+                        s_bl[r] = v_bl[r] ? n_bl[r] : NEG;
+                        s_lb[r] = v_lb[r] ? n_lb[r] : NEG;
+                        const int k = tid * R + r;
+                        if (k < W) alb[(long)t * W + k] = make_float2(s_bl[r], s_lb[r]);
+                    }
+                    if (NW > 1) {
+                        if (lane == 31) edge[t & 1][0][warp] = s_lb[R - 1];
+                        __syncthreads();
+                    }
                 }
-                const float n_bl = lse2f(b_bl, b_lb);
-                const float n_lb = cl[i] + lse3f(b_lb, n1, skip_b ? n2 : NEG);
-                b_bl = v_bl ? n_bl : NEG;
-                b_lb = v_lb ? n_lb : NEG;
-                if (lane == 0) { edge[t & 1][0][warp] = b_bl; edge[t & 1][1][warp] = b_lb; }
-                const float al_bl = ca[i].x, al_lb = ca[i].y;
-                float o_bl = (al_bl > NEG && b_bl > NEG) ? expf(al_bl + b_bl - tot) : 0.f;
-                float o_lb = (al_lb > NEG && b_lb > NEG) ? expf(al_lb + b_lb - cl[i] - tot) : 0.f;
-                if (!feasible) { o_bl = qnan; o_lb = qnan; }
-                if (k < W) abb[(long)t * W + k] = make_float2(o_bl, o_lb);
+            }
+#pragma unroll
+            for (int i = 0; i < PFW; ++i)
+#pragma unroll
+                for (int r = 0; r < R; ++r) cl[i][r] = nl[i][r];
+        }
+        if (tid == 0) { fin[0] = NEG; fin[1] = NEG; }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int k = tid * R + r;
+            if (k == L) fin[0] = s_bl[r];
+            if (L > 0 && k == L - 1) fin[1] = s_lb[r];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const float tot = lse2q(fin[0], fin[1]);
+            nll[b] = (float)(-((double)tot + csum));
+            tot_out[b] = tot;
+        }
+    } else {
+        float2* beb = be + (long)b * T * W;
+        {
+            const int t = Tb - 1;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int k = tid * R + r;
+                const float ld_ = lpb[(long)t * W + kcol[r]];
+                s_bl[r] = (k == L) ? 0.f : NEG;
+                s_lb[r] = (L > 0 && k == L - 1) ? ld_ : NEG;
+                if (k < W) beb[(long)t * W + k] = make_float2(s_bl[r], s_lb[r]);
+            }
+            if (NW > 1) {
+                if (lane == 0) { edge[t & 1][0][warp] = s_bl[0]; edge[t & 1][1][warp] = s_lb[0]; }
                 __syncthreads();
             }
         }
 #pragma unroll
-        for (int i = 0; i < PF; ++i) { cl[i] = nl_[i]; ca[i] = na[i]; }
+        for (int i = 0; i < PFW; ++i) {
+            const int t = max(Tb - 2 - i, 0);
+#pragma unroll
+            for (int r = 0; r < R; ++r) cl[i][r] = lpb[(long)t * W + kcol[r]];
+        }
+        for (int t0 = Tb - 2; t0 >= 0; t0 -= PFW) {
+#pragma unroll
+            for (int i = 0; i < PFW; ++i) {
+                const int t = max(t0 - PFW - i, 0);
+#pragma unroll
+                for (int r = 0; r < R; ++r) nl[i][r] = lpb[(long)t * W + kcol[r]];
+            }
+#pragma unroll
+            for (int i = 0; i < PFW; ++i) {
+                const int t = t0 - i;
+                if (t >= 0) {
+                    float d1 = __shfl_down_sync(0xffffffffu, s_bl[0], 1);  // beta_{t+1}(2k+2) of the next thread's first pair
+                    float d2 = __shfl_down_sync(0xffffffffu, s_lb[0], 1);  // beta_{t+1}(2k+3)
+                    if (lane == 31) {
+                        const bool has = NW > 1 && warp + 1 < NW;
+                        d1 = has ? edge[(t + 1) & 1][0][warp + 1] : NEG;
+                        d2 = has ? edge[(t + 1) & 1][1][warp + 1] : NEG;
+                    }
+                    float n_bl[R], n_lb[R];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const float x1 = (r == R - 1) ? d1 : s_bl[r + 1];
+                        const float x2 = (r == R - 1) ? d2 : s_lb[r + 1];
+                        n_bl[r] = lse2q(s_bl[r], s_lb[r]);
+                        n_lb[r] = cl[i][r] + lse3q(s_lb[r], x1, skip[r] ? x2 : NEG);
+                    }
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        s_bl[r] = v_bl[r] ? n_bl[r] : NEG;
+                        s_lb[r] = v_lb[r] ? n_lb[r] : NEG;
+                        const int k = tid * R + r;
+                        if (k < W) beb[(long)t * W + k] = make_float2(s_bl[r], s_lb[r]);
+                    }
+                    if (NW > 1) {
+                        if (lane == 0) { edge[t & 1][0][warp] = s_bl[0]; edge[t & 1][1][warp] = s_lb[0]; }
+                        __syncthreads();
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < PFW; ++i)
+#pragma unroll
+                for (int r = 0; r < R; ++r) cl[i][r] = nl[i][r];
+        }
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// K_C  scatter: one warp per live row (t,b)
-// ---------------------------------------------------------------------------------------------
+// scatter for the split lattice: occupancy formed on the fly from alpha, beta, the label emission term and tot
 template <typename GT>
-__global__ void __launch_bounds__(256) ctc_scatter_kernel(const float2* __restrict__ occ, void* grad, long gst, long gsb,
-                                                          const int64_t* __restrict__ targets,
-                                                          const int64_t* __restrict__ in_len,
-                                                          const int64_t* __restrict__ tgt_len, int T, int B, int lmax,
-                                                          int blank, float grad_scale, const float* upstream) {
+__global__ void __launch_bounds__(256) ctc_scatter_ab_kernel(const float2* __restrict__ al, const float2* __restrict__ be,
+                                                             const float* __restrict__ lp_ext, const float* __restrict__ tot,
+                                                             void* grad, long gst, long gsb, const int64_t* __restrict__ targets,
+                                                             const int64_t* __restrict__ in_len,
+                                                             const int64_t* __restrict__ tgt_len, int T, int B, int lmax,
+                                                             int blank, float grad_scale, const float* upstream) {
     const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= (long)T * B) return;
     const int lane = threadIdx.x & 31;
     const int t = (int)(row / B), b = (int)(row % B);
     if (t >= (int)in_len[b]) return;
-    const int L = (int)tgt_len[b], W = lmax + 1;
+    const int L = min((int)tgt_len[b], lmax), W = lmax + 1;
     float s = grad_scale;
     if (upstream) s *= __ldg(upstream);
-    const float2* o = occ + ((long)b * T + t) * W;
+    const long base = ((long)b * T + t) * W;
+    const float tt = tot[b];
+    const bool feasible = tt > -INFINITY;
+    const float qnan = __int_as_float(0x7fc00000);
     const int64_t* tg = targets + (long)b * lmax;
     GT* g = reinterpret_cast<GT*>(grad) + (long)t * gst + (long)b * gsb;
     float bsum = 0.f;
     for (int k = lane; k <= L; k += 32) {
-        const float2 v = o[k];
-        bsum += v.x;
+        const float2 a = al[base + k], bb = be[base + k];
+        float o_bl = (a.x > -INFINITY && bb.x > -INFINITY) ? __expf(a.x + bb.x - tt) : 0.f;
+        if (!feasible) o_bl = qnan;
+        bsum += o_bl;
         if (k < L) {
+            const float e = lp_ext[base + k + 1];
+            float o_lb = (a.y > -INFINITY && bb.y > -INFINITY) ? __expf(a.y + bb.y - e - tt) : 0.f;
+            if (!feasible) o_lb = qnan;
             const int c = (int)tg[k];
-            if constexpr (sizeof(GT) == 4) atomicAdd(reinterpret_cast<float*>(g) + c, -s * v.y);
-            else atomicAdd(reinterpret_cast<bf16*>(g) + c, __float2bfloat16_rn(-s * v.y));
+            if constexpr (sizeof(GT) == 4) atomicAdd(reinterpret_cast<float*>(g) + c, -s * o_lb);
+            else atomicAdd(reinterpret_cast<bf16*>(g) + c, __float2bfloat16_rn(-s * o_lb));
         }
     }
     bsum = warp_sum(bsum);
@@ -387,7 +441,7 @@ __global__ void __launch_bounds__(256) ctc_scatter_kernel(const float2* __restri
 }
 
 template <typename T>
-static int ctc_launch(const CtcDenseParams& p, float2* ab, float* nll, cudaStream_t st) {
+static int ctc_launch(const CtcDenseParams& p, float2* ab, float2* be, float* tot, float* nll, cudaStream_t st) {
     const long rows = (long)p.T * p.B;
     const bool vec = ((reinterpret_cast<uintptr_t>(p.logits) | reinterpret_cast<uintptr_t>(p.grad)) % (4 * sizeof(T)) == 0) &&
                      p.st % 4 == 0 && p.sb % 4 == 0 && p.gst % 4 == 0 && p.gsb % 4 == 0;
@@ -406,16 +460,25 @@ static int ctc_launch(const CtcDenseParams& p, float2* ab, float* nll, cudaStrea
     if (!done) ctc_softmax_gather_generic<T><<<(unsigned)rows, 256, 0, st>>>(p);
     int rc = check_launch("ctc_softmax_gather");
     if (rc) return rc;
-    const int threads = ((p.lmax + 1 + 31) / 32) * 32;
-    if (threads <= 256)
-        ctc_lattice_kernel<256><<<p.B, threads, 0, st>>>(p.lp_ext, ab, p.targets, p.in_len, p.tgt_len, nll, p.T, p.lmax);
-    else
-        ctc_lattice_kernel<1024><<<p.B, threads, 0, st>>>(p.lp_ext, ab, p.targets, p.in_len, p.tgt_len, nll, p.T, p.lmax);
-    rc = check_launch("ctc_lattice");
-    if (rc) return rc;
-    ctc_scatter_kernel<T><<<ceil_div(rows, 8), 256, 0, st>>>(ab, p.grad, p.gst, p.gsb, p.targets, p.in_len, p.tgt_len,
-                                                            p.T, p.B, p.lmax, p.blank, p.grad_scale, p.upstream);
-    return check_launch("ctc_scatter");
+    const int W = p.lmax + 1;
+    {
+        // alpha and beta sweeps on separate CTAs; R state pairs per thread, NW warps per sweep (32 R NW >= W)
+        dim3 grid(p.B, 2);
+#define LASR_LATTICE(R, PFW, NW) \
+    ctc_lattice_warp_kernel<R, PFW, NW><<<grid, 32 * NW, 0, st>>>(p.lp_ext, ab, be, p.targets, p.in_len, p.tgt_len, nll, tot, p.T, p.lmax)
+        if (W <= 32) LASR_LATTICE(1, 8, 1);
+        else if (W <= 64) LASR_LATTICE(2, 8, 1);
+        else if (W <= 128) LASR_LATTICE(2, 8, 2);
+        else if (W <= 256) LASR_LATTICE(2, 8, 4);
+        else if (W <= 512) LASR_LATTICE(2, 8, 8);
+        else LASR_LATTICE(4, 4, 8);
+#undef LASR_LATTICE
+        rc = check_launch("ctc_lattice_warp");
+        if (rc) return rc;
+        ctc_scatter_ab_kernel<T><<<ceil_div(rows, 8), 256, 0, st>>>(ab, be, p.lp_ext, tot, p.grad, p.gst, p.gsb, p.targets, p.in_len,
+                                                                   p.tgt_len, p.T, p.B, p.lmax, p.blank, p.grad_scale, p.upstream);
+    }
+    return check_launch("ctc_scatter_ab");
 }
 
 }  // namespace lasr
@@ -424,7 +487,8 @@ extern "C" {
 
 size_t lasr_ctc_workspace_bytes(int T, int B, int lmax) {
     const size_t w = (size_t)(lmax < 1 ? 1 : lmax) + 1;
-    return (size_t)T * B * w * (sizeof(float) + sizeof(float2)) + 512;
+    // alpha (float2) + beta (float2) + gathered lattice inputs (float) per (t, b, state pair); tot per utterance
+    return (size_t)T * B * w * (sizeof(float) + 2 * sizeof(float2)) + (size_t)B * sizeof(float) + 1024;
 }
 
 int lasr_ctc_fwdbwd(const void* logits, int dtype, int64_t st, int64_t sb, const int64_t* targets, const int64_t* in_len,
@@ -443,10 +507,12 @@ int lasr_ctc_fwdbwd(const void* logits, int dtype, int64_t st, int64_t sb, const
     const size_t w = (size_t)lmax + 1;
     uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255;
     float2* ab = reinterpret_cast<float2*>(base);
-    p.lp_ext = reinterpret_cast<float*>(base + (size_t)T * B * w * sizeof(float2));
+    float2* be = reinterpret_cast<float2*>(base + (size_t)T * B * w * sizeof(float2));
+    p.lp_ext = reinterpret_cast<float*>(base + 2 * (size_t)T * B * w * sizeof(float2));
+    float* tot = reinterpret_cast<float*>(base + (size_t)T * B * w * (2 * sizeof(float2) + sizeof(float)));
     p.T = T; p.B = B; p.V = V; p.lmax = lmax; p.blank = blank; p.grad_scale = grad_scale; p.upstream = upstream;
-    if (dtype == LASR_F32) return ctc_launch<float>(p, ab, nll, (cudaStream_t)stream);
-    if (dtype == LASR_BF16) return ctc_launch<bf16>(p, ab, nll, (cudaStream_t)stream);
+    if (dtype == LASR_F32) return ctc_launch<float>(p, ab, be, tot, nll, (cudaStream_t)stream);
+    if (dtype == LASR_BF16) return ctc_launch<bf16>(p, ab, be, tot, nll, (cudaStream_t)stream);
     set_error("ctc: unsupported dtype %d", dtype);
     return LASR_ERR_UNSUPPORTED;
 }
