@@ -228,6 +228,23 @@ int lasr_clip_adam_step(float* params, const float* grads, float* exp_avg, float
                         float warmup, float fixed_lr, float* state, float* workspace, void* stream);
 int lasr_zero(void* ptr, size_t bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Inference (models/u2.py:221-317, nets/ctc.py:25-26).
+ *   logsoftmax_topk : per row lse (optional), full log-softmax (optional, fp32, row stride ldf) and the K best classes in
+ *                     (log-prob descending, index ascending) order: top_val (rows,K) fp32 log-probs, top_idx (rows,K) int32.
+ *                     K = 1 is greedy CTC's argmax; K = beam is the per-frame prune of the prefix search (u2.py:230).
+ *   gather_logp     : out[r] = logits[r, tokens[r]] - lse[r]  (attention-rescoring lookups, u2.py:306-310).
+ *   ctc_prefix_beam_search : HOST function (no device work): u2.py:224-261 on host copies of top_val / top_idx for ONE
+ *                     utterance; float64 arithmetic in the reference's operation order, insertion-ordered prefix map, stable
+ *                     sort.  Outputs up to `beam` hypotheses best first: tokens (beam,max_len) padded -1, lengths, scores.
+ * ------------------------------------------------------------------------------------------------ */
+int lasr_logsoftmax_topk(const void* logits, int dtype, int64_t ld, int64_t rows, int V, int K, float* lse, float* logp_full,
+                         int64_t ldf, float* top_val, int32_t* top_idx, void* stream);
+int lasr_gather_logp(const void* logits, int dtype, int64_t ld, const float* lse, const int64_t* tokens, float* out, int64_t rows, int V,
+                     void* stream);
+int lasr_ctc_prefix_beam_search(const float* topk_logp, const int32_t* topk_idx, int frames, int K, int beam, int blank,
+                                int32_t* out_tokens, int32_t* out_lens, double* out_scores, int max_len, int32_t* n_out);
+
 #ifdef __cplusplus
 }
 #endif

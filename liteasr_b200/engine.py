@@ -281,13 +281,13 @@ class Engine:
         dln = self.dgrad(dqkv, st.w(c.pfx + ".linear_q.weight", 3 * d, d))
         return self.layernorm_bwd(c.ln, dln, dres, True, nxt, want_lo)
 
-    def src_mha_fwd(self, y, mem, pfx_norm, pfx, B, L, T, H, xlens) -> NS:
+    def src_mha_fwd(self, y, mem, pfx_norm, pfx, B, L, T, H, xlens, mask_mode=3) -> NS:
         d = y.shape[1]
         ln = self.layernorm(y, pfx_norm, self.adt)
         q = self.linear(ln.y, pfx + ".linear_q", self.adt)
         kv = self.linear(mem, None, self.adt, w=self.st.w(pfx + ".linear_k.weight", 2 * d, d),
                          bias_t=self.st.p_span(pfx + ".linear_k.bias", 2 * d))
-        core = self.attn_core_fwd(q, kv[:, :d], kv[:, d:], B, H, L, T, d // H, xlens, 3 if xlens is not None else 0, 0)
+        core = self.attn_core_fwd(q, kv[:, :d], kv[:, d:], B, H, L, T, d // H, xlens, mask_mode if xlens is not None else 0, 0)
         out = self.linear(core.o, pfx + ".linear_o", torch.float32, res=y)
         return NS(out=out, ln=ln, core=core, mem=mem, pfx=pfx, d=d)
 
@@ -478,9 +478,11 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     # decoder (nets/transformer_decoder.py:70-93, nets/transformer_layer.py:179-221)
     # ------------------------------------------------------------------------------------------
-    def decoder_fwd(self, dec, ys, ylens, h_enc, xlens) -> NS:
+    def decoder_fwd(self, dec, ys, ylens, h_enc, xlens, mem_mask_mode: int = 3) -> NS:
         """ys (B,L) int64 decoder input tokens ([sos | ys], models/u2.py:339-358); ylens (B,) so that key j of the
-        self-attention is valid iff j < ylens[b]+1 (and j <= i); h_enc (B,T',d) fp32; xlens raw input lengths or None."""
+        self-attention is valid iff j < ylens[b]+1 (and j <= i); h_enc (B,T',d) fp32; xlens raw input lengths or None.
+        mem_mask_mode 3: memory key j valid iff 4j < xlens[b] (training: the reference's re-subsampled padding mask);
+        1: xlens holds sub-sampled memory lengths directly (batched rescoring of utterances encoded one by one)."""
         B, L = ys.shape
         d, H = dec.h_dim, dec.n_head
         Tp = h_enc.shape[1]
@@ -494,7 +496,7 @@ class Engine:
         for i in range(len(dec.dec_layers)):
             lp = f"{pfx}dec_layers.{i}"
             c1 = self.self_mha_fwd(y, lp + ".self_attn_norm", lp + ".self_attn", B, L, H, ylens)
-            c2 = self.src_mha_fwd(c1.out, mem, lp + ".src_attn_norm", lp + ".src_attn", B, L, Tp, H, xlens)
+            c2 = self.src_mha_fwd(c1.out, mem, lp + ".src_attn_norm", lp + ".src_attn", B, L, Tp, H, xlens, mem_mask_mode)
             c3 = self.ffn_fwd(c2.out, lp + ".feed_forward_norm", lp + ".feed_forward", ACT_RELU, 1.0)
             layers.append((c1, c2, c3))
             y = c3.out

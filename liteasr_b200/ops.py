@@ -310,3 +310,51 @@ def clip_adam_step(params, grads, exp_avg, exp_avg_sq, state, workspace, *, grad
                                               _f(grad_mult), _f(max_norm), _f(beta1), _f(beta2), _f(eps), _f(weight_decay),
                                               _f(noam_factor), _f(model_dim), _f(warmup), _f(lr), _ptr(state), _ptr(workspace),
                                               _stream()), "clip_adam_step")
+
+
+# ----------------------------------------------------------------------------------------------
+# inference
+# ----------------------------------------------------------------------------------------------
+def logsoftmax_topk(logits: torch.Tensor, k: int, *, vocab: Optional[int] = None, want_lse: bool = False, want_full: bool = False):
+    """logits (rows, >=V) 2-D view (row stride = padded vocab).  Returns (top_val (rows,k) fp32 log-probs, top_idx (rows,k) int32,
+    lse (rows,) or None, logp (rows,V) fp32 or None)."""
+    _require_cuda(logits)
+    assert logits.dim() == 2 and logits.stride(1) == 1
+    rows = logits.shape[0]
+    V = logits.shape[1] if vocab is None else vocab
+    dev = logits.device
+    tv = torch.empty((rows, k), dtype=torch.float32, device=dev) if k else None
+    ti = torch.empty((rows, k), dtype=torch.int32, device=dev) if k else None
+    lse = torch.empty(rows, dtype=torch.float32, device=dev) if want_lse else None
+    full = torch.empty((rows, V), dtype=torch.float32, device=dev) if want_full else None
+    _lib.check(_lib.lib().lasr_logsoftmax_topk(_ptr(logits), _i(dtype_code(logits)), _l(logits.stride(0)), _l(rows), _i(V), _i(k), _ptr(lse),
+                                               _ptr(full), _l(V), _ptr(tv), _ptr(ti), _stream()), "logsoftmax_topk")
+    return tv, ti, lse, full
+
+
+def gather_logp(logits: torch.Tensor, lse: torch.Tensor, tokens: torch.Tensor, vocab: int) -> torch.Tensor:
+    """out[r] = logits[r, tokens[r]] - lse[r] (0 where tokens[r] < 0)."""
+    _require_cuda(logits, lse, tokens)
+    rows = logits.shape[0]
+    assert tokens.dtype == torch.int64 and tokens.numel() == rows and lse.numel() == rows
+    out = torch.empty(rows, dtype=torch.float32, device=logits.device)
+    _lib.check(_lib.lib().lasr_gather_logp(_ptr(logits), _i(dtype_code(logits)), _l(logits.stride(0)), _ptr(lse), _ptr(tokens.contiguous()),
+                                           _ptr(out), _l(rows), _i(vocab), _stream()), "gather_logp")
+    return out
+
+
+def ctc_prefix_beam_search_host(top_val, top_idx, beam: int = 10, blank: int = 0):
+    """HOST: top_val (frames,K) float32 / top_idx (frames,K) int32 numpy arrays -> [(prefix tuple, score float64)] best first."""
+    import numpy as np
+    tv = np.ascontiguousarray(top_val, dtype=np.float32)
+    ti = np.ascontiguousarray(top_idx, dtype=np.int32)
+    frames, K = tv.shape if tv.ndim == 2 else (0, max(1, beam))
+    max_len = max(1, frames)
+    toks = np.empty((beam, max_len), dtype=np.int32)
+    lens = np.empty(beam, dtype=np.int32)
+    scores = np.empty(beam, dtype=np.float64)
+    n = C.c_int32(0)
+    _lib.check(_lib.lib().lasr_ctc_prefix_beam_search(tv.ctypes.data_as(_P), ti.ctypes.data_as(_P), _i(frames), _i(K), _i(beam), _i(blank),
+                                                      toks.ctypes.data_as(_P), lens.ctypes.data_as(_P), scores.ctypes.data_as(_P),
+                                                      _i(max_len), C.byref(n)), "ctc_prefix_beam_search")
+    return [(tuple(int(x) for x in toks[i, : lens[i]]), float(scores[i])) for i in range(n.value)]

@@ -107,6 +107,29 @@ def run_model_case(name):
             plen = model.get_pred_len(xlens)
             rec["greedy"] = [greedy(ids[i], int(plen[i])) for i in range(b)]
             rec["eval_h_enc"] = summarize(h)
+            # batch-1 inference exactly as `liteasr-infer` runs it (infer.py:97-120 -> models/u2.py:160-161,221-317): maskless
+            # encoder on ONE utterance, CTC prefix beam search (beam 10), attention rescoring.  The reference crashes in
+            # attention_rescore at HEAD (quirk Q13: Python lists reach `ylens + 1` / padding_mask); `_preprocess` is wrapped so the
+            # two length lists become tensors -- nothing else is touched.
+            # A FRESH model (pristine BatchNorm running statistics: the training forward above updated `model`'s).
+            minf, _ = ref_shims.build_reference(dims.__dict__, eps, w)
+            minf.load_state_dict(sd, strict=True)
+            minf = minf.to(dtype).eval()
+            orig_pre = minf._preprocess
+
+            def pre(xs, xlens, ys, ylens, _orig=orig_pre):
+                return _orig(xs, torch.as_tensor(xlens), ys, torch.as_tensor(ylens))
+
+            minf._preprocess = pre
+            inf = []
+            for i in range(min(b, 3)):
+                xi = xs[i:i + 1, : int(xlens[i])].to(dtype)
+                hyps, _ = minf._ctc_prefix_beam_search(xi)
+                best = minf.attention_rescore(xi)
+                ids1 = minf.ctc.log_softmax(minf.encoder(xi)).argmax(-1)[0]
+                inf.append(dict(utt=i, frames=int(xlens[i]), hyps=[[list(p), float(sc)] for p, sc in hyps], best=list(best),
+                                greedy=greedy(ids1, ids1.numel())))
+            rec["inference"] = inf
         out[tag] = rec
     return out
 

@@ -480,3 +480,91 @@ def greedy_ctc(sd: SD, cfg: U2Shape, xs: Tensor, xlens: Optional[Tensor] = None)
             prev = c
         out.append(seq)
     return out, ids
+
+
+# --------------------------------------------------------------------------------------
+# inference (models/u2.py:221-317): CTC prefix beam search + attention rescoring, batch 1
+# --------------------------------------------------------------------------------------
+def log_add(args) -> float:
+    """models/u2.py:367-375 (stable log-add over a list of Python floats)."""
+    if all(a == -float("inf") for a in args):
+        return -float("inf")
+    a_max = max(args)
+    lsp = math.log(sum(math.exp(a - a_max) for a in args))
+    return a_max + lsp
+
+
+def prefix_beam_search_logp(ctc_probs: Tensor, beam_size: int = 10):
+    """models/u2.py:226-261 on a (frames, vocab) log-probability matrix.  Returns [(prefix tuple, score)] best first.
+    Kept structurally identical to the reference: per frame torch.topk prune, dict in insertion order, Python floats,
+    stable sort on log_add(pb, pnb) descending."""
+    from collections import defaultdict
+    cur_hyps = [(tuple(), (0.0, -float("inf")))]
+    for logp in ctc_probs:
+        next_hyps = defaultdict(lambda: (-float("inf"), -float("inf")))
+        _, index_topk = torch.topk(logp, beam_size)
+        for s in index_topk:
+            s = s.item()
+            ps = logp[s].item()
+            for prefix, (pb, pnb) in cur_hyps:
+                last = prefix[-1] if len(prefix) > 0 else None
+                if s == 0:  # blank
+                    n_pb, n_pnb = next_hyps[prefix]
+                    n_pb = log_add([n_pb, pb + ps, pnb + ps])
+                    next_hyps[prefix] = (n_pb, n_pnb)
+                elif s == last:
+                    n_pb, n_pnb = next_hyps[prefix]
+                    n_pnb = log_add([n_pnb, pnb + ps])
+                    next_hyps[prefix] = (n_pb, n_pnb)
+                    n_prefix = prefix + (s,)
+                    n_pb, n_pnb = next_hyps[n_prefix]
+                    n_pnb = log_add([n_pnb, pb + ps])
+                    next_hyps[n_prefix] = (n_pb, n_pnb)
+                else:
+                    n_prefix = prefix + (s,)
+                    n_pb, n_pnb = next_hyps[n_prefix]
+                    n_pnb = log_add([n_pnb, pb + ps, pnb + ps])
+                    next_hyps[n_prefix] = (n_pb, n_pnb)
+        next_hyps = sorted(next_hyps.items(), key=lambda x: log_add(list(x[1])), reverse=True)
+        cur_hyps = next_hyps[:beam_size]
+    return [(y[0], log_add([y[1][0], y[1][1]])) for y in cur_hyps]
+
+
+def rescore_scores(attn_score: Tensor, hyps, eos: int, ctc_weight: float = 0.5):
+    """models/u2.py:303-315: per hypothesis sum_j logp[j, y_j] + logp[len, eos] + 0.5 * ctc score, accumulated left to right
+    in the tensor dtype exactly like the reference's `score += attn_score[i][j][w]` (a 0-dim tensor after the first add).
+    Returns (best index, [scores])."""
+    best_score, best_index, scores = -float("inf"), 0, []
+    for i, hyp in enumerate(hyps):
+        score = 0.0
+        for j, w in enumerate(hyp[0]):
+            score += attn_score[i][j][w]
+        score += attn_score[i][len(hyp[0])][eos]
+        score += hyp[1] * ctc_weight
+        scores.append(float(score))
+        if score > best_score:
+            best_score = score
+            best_index = i
+    return best_index, scores
+
+
+def attention_rescore(sd: SD, cfg: U2Shape, x: Tensor, beam_size: int = 10):
+    """models/u2.py:269-317 for one utterance x (1, T, F): maskless encoder (eval-mode BatchNorm), CTC prefix beam search,
+    decoder pass over the padded n-best ([sos | hyp, pad -> eos], mask = padding | causal, memory unmasked), rescoring.
+    Deviation: the reference passes Python lists to `_preprocess` and crashes at HEAD (quirk Q13); the lengths are
+    tensors here.  Returns dict(best, hyps, scores, ctc_logp)."""
+    h = encoder(sd, cfg, x, None, training=False)
+    ctc_logp = torch.log_softmax(dense(sd, "ctc.ctc_lo", h), dim=-1).squeeze(0)
+    hyps = prefix_beam_search_logp(ctc_logp, beam_size)
+    ylens = torch.tensor([len(hy[0]) for hy in hyps], dtype=torch.long)
+    lmax = int(ylens.max())
+    ys = torch.full((len(hyps), max(lmax, 0)), -1, dtype=torch.long)
+    for i, hy in enumerate(hyps):
+        if len(hy[0]):
+            ys[i, : len(hy[0])] = torch.tensor(hy[0], dtype=torch.long)
+    ys_in, ys_mask = decoder_inputs(ys, ylens, cfg.vocab_size)
+    dec_mask = ys_mask.unsqueeze(1) | causal_mask(ys_mask.size(1)).unsqueeze(0)
+    h_attn = decoder(sd, cfg, ys_in, dec_mask, h.repeat(len(hyps), 1, 1), None)
+    attn_score = torch.log_softmax(h_attn, dim=-1)
+    best, scores = rescore_scores(attn_score, hyps, cfg.vocab_size - 1)
+    return dict(best=list(hyps[best][0]), hyps=[(list(p), s) for p, s in hyps], scores=scores, ctc_logp=ctc_logp)

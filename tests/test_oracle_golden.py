@@ -111,3 +111,36 @@ def test_mask_docstring_examples():
     assert m.int().tolist() == [[0, 0, 0, 0, 0], [0, 0, 0, 1, 1], [0, 1, 1, 1, 1]]
     c = O.causal_mask(5).int().tolist()
     assert c == [[0, 1, 1, 1, 1], [0, 0, 1, 1, 1], [0, 0, 0, 1, 1], [0, 0, 0, 0, 1], [0, 0, 0, 0, 0]]
+
+
+@pytest.mark.parametrize("case,nutt", [("tiny", 3), ("tiny_odd", 2), ("c1", 1)])
+def test_oracle_inference_matches_reference(case, nutt):
+    """Batch-1 CTC prefix beam search + attention rescoring (models/u2.py:221-317) and greedy CTC: the oracle restatement
+    reproduces the unmodified reference's n-best lists (prefixes bit-exact, scores to 1e-9) and its final hypothesis."""
+    g = load(f"u2_{case}.json")
+    dims = U2Dims(**g["dims"])
+    xs, xlens, _, _ = synth_batch(g["batch"], g["tmax"], g["lmax"], dims.vocab_size, seed=g["seed"])
+    sd = {k: (v.double() if v.is_floating_point() else v) for k, v in synth_state_dict(dims, seed=g["seed"]).items()}
+    cfg = O.U2Shape(**g["dims"])
+    with torch.no_grad():
+        for rec in g["f64"]["inference"][:nutt]:
+            i = rec["utt"]
+            x = xs[i:i + 1, : rec["frames"]].double()
+            out = O.attention_rescore(sd, cfg, x)
+            assert [p for p, _ in out["hyps"]] == [p for p, _ in rec["hyps"]]
+            assert np.allclose([s for _, s in out["hyps"]], [s for _, s in rec["hyps"]], rtol=1e-9, atol=1e-9)
+            assert out["best"] == rec["best"]
+            greedy, _ = O.greedy_ctc(sd, cfg, x, None)
+            assert greedy[0] == rec["greedy"]
+
+
+def test_log_add_and_prefix_search_small_known_answer():
+    """Hand-checkable lattice: 2 frames, 3 classes (blank 0).  p(prefix) sums every alignment collapsing to it."""
+    lp = torch.log(torch.tensor([[0.6, 0.3, 0.1], [0.5, 0.4, 0.1]], dtype=torch.float64))
+    hyps = dict((p, s) for p, s in O.prefix_beam_search_logp(lp, 3))
+    # () : blank,blank = .30 ; (1,): 1b + b1 + 11 = .15 + .24 + .12 = .51 ; (2,): .05 + .06 + .01 = .12 ; (1,2): .03 ; (2,1): .04
+    assert math.isclose(math.exp(hyps[()]), 0.30, rel_tol=1e-12)
+    assert math.isclose(math.exp(hyps[(1,)]), 0.51, rel_tol=1e-12)
+    assert math.isclose(math.exp(hyps[(2,)]), 0.12, rel_tol=1e-12)
+    assert math.isclose(O.log_add([math.log(0.25), math.log(0.75)]), 0.0, abs_tol=1e-15)
+    assert O.log_add([-float("inf"), -float("inf")]) == -float("inf")
