@@ -39,11 +39,13 @@ __global__ void __launch_bounds__(256) logsoftmax_topk_kernel(const T* __restric
     float sum = 0.f;
     for (int c = threadIdx.x; c < V; c += 256) sum += expf(to_f32<T>(x[c]) - mx);
     sum = block_sum(sum, scratch);
-    const float lse = mx + logf(sum);
-    if (threadIdx.x == 0 && lse_out) lse_out[row] = lse;
+    const float lsum = logf(sum);
+    if (threadIdx.x == 0 && lse_out) lse_out[row] = mx + lsum;
+    // log-probabilities are formed as (x - max) - log(sum), the rounding sequence of torch.log_softmax: the reference ranks the
+    // ROUNDED fp32 log-probs (argmax / torch.topk of log_softmax), where two classes whose logits differ in the last bits can tie
     if (logp_full)
-        for (int c = threadIdx.x; c < V; c += 256) logp_full[row * ldf + c] = to_f32<T>(x[c]) - lse;
-    // K rounds of arg-max in the total order (value descending, index ascending); round r only considers elements that come
+        for (int c = threadIdx.x; c < V; c += 256) logp_full[row * ldf + c] = (to_f32<T>(x[c]) - mx) - lsum;
+    // K rounds of arg-max in the total order (log-prob descending, index ascending); round r only considers elements that come
     // strictly after the previous winner in that order, so no "taken" set is needed
     float last_v = INFINITY;
     int last_i = -1;
@@ -51,7 +53,7 @@ __global__ void __launch_bounds__(256) logsoftmax_topk_kernel(const T* __restric
         float bv = -INFINITY;
         int bi = 0x7fffffff;
         for (int c = threadIdx.x; c < V; c += 256) {
-            const float v = to_f32<T>(x[c]);
+            const float v = (to_f32<T>(x[c]) - mx) - lsum;
             const bool after = (v < last_v) || (v == last_v && c > last_i);
             if (after && (v > bv || (v == bv && c < bi))) { bv = v; bi = c; }
         }
@@ -69,7 +71,7 @@ __global__ void __launch_bounds__(256) logsoftmax_topk_kernel(const T* __restric
         for (int w = 1; w < 8; ++w)
             if (sv[w] > bv || (sv[w] == bv && si[w] < bi)) { bv = sv[w]; bi = si[w]; }
         if (threadIdx.x == 0) {
-            top_val[row * K + r] = (bi == 0x7fffffff) ? -INFINITY : bv - lse;
+            top_val[row * K + r] = (bi == 0x7fffffff) ? -INFINITY : bv;
             top_idx[row * K + r] = (bi == 0x7fffffff) ? -1 : bi;
         }
         last_v = bv;
