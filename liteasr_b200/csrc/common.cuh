@@ -70,7 +70,8 @@ __device__ __forceinline__ float block_max(float v, float* scratch) {
     return r;
 }
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+// ex2 + rcp on the MUFU pipe (__fdividef(1, y) = rcp.approx, <= 1 ulp): the IEEE division expands to ~8 instructions per element
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float swishf_(float x) { return x * sigmoidf_(x); }
 __device__ __forceinline__ float dswishf_(float x) {
     const float s = sigmoidf_(x);

@@ -84,6 +84,35 @@ __global__ void __launch_bounds__(256) bn_swish_fwd_kernel(const float* __restri
     st2<TD>(a + i, swishf_(u0), swishf_(u1));
 }
 
+// d % 4 == 0: one thread = 4 channels x 4 rows (rows strided by the grid), per-channel scale/shift folded once
+template <typename TD>
+__global__ void __launch_bounds__(256) bn_swish_fwd_vec_kernel(const float* __restrict__ z, const float* __restrict__ mean,
+                                                               const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, TD* __restrict__ a, long rows, int d) {
+    const int vpr = d >> 2;
+    const long gid = (long)blockIdx.x * 256 + threadIdx.x;
+    const int cv = (int)(gid % vpr);
+    const long r0 = (gid / vpr) * 4;
+    if (r0 >= rows) return;
+    const int c = cv * 4;
+    const float4 m = *reinterpret_cast<const float4*>(mean + c), rs = *reinterpret_cast<const float4*>(rstd + c);
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
+    const float4 sc = make_float4(rs.x * ga.x, rs.y * ga.y, rs.z * ga.z, rs.w * ga.w);
+    float4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (r0 + j < rows) v[j] = *reinterpret_cast<const float4*>(z + (r0 + j) * d + c);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (r0 + j >= rows) break;
+        const float u0 = (v[j].x - m.x) * sc.x + be.x, u1 = (v[j].y - m.y) * sc.y + be.y;
+        const float u2 = (v[j].z - m.z) * sc.z + be.z, u3 = (v[j].w - m.w) * sc.w + be.w;
+        TD* o = a + (r0 + j) * d + c;
+        st2<TD>(o, swishf_(u0), swishf_(u1));
+        st2<TD>(o + 2, swishf_(u2), swishf_(u3));
+    }
+}
+
 // ---------------------------------------------------------------- bwd 1
 template <typename TD>
 __global__ void __launch_bounds__(128) bn_swish_bwd_stats_generic(const TD* __restrict__ da, const float* __restrict__ z,
@@ -180,7 +209,10 @@ __global__ void __launch_bounds__(128) dwconv_glu_bwd_generic(const TD* __restri
 // =================================================================================================
 // fast kernels
 // =================================================================================================
-constexpr int CB = 128, WIN = TCH + 2 * HALO, TQ = TCH / 4;  // channel block, halo window rows, time steps per thread
+// Tile = FT time steps x FC channels per CTA of 256 threads; thread = ONE channel x FT/4 consecutive time steps, so the
+// register window is FT/4 + 14 floats + 15 taps (~64 registers -> 4 CTAs / 1024 threads per SM) and every shared-memory /
+// global access of a warp covers 32 consecutive channels (conflict-free LDS.32, 128-byte coalesced stores).
+constexpr int FT = 64, FC = 64, FWIN = FT + 2 * HALO, FQ = FT / 4;
 
 template <typename TD> __device__ __forceinline__ float4 ld4c(const TD* p);
 template <> __device__ __forceinline__ float4 ld4c<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -191,70 +223,94 @@ template <> __device__ __forceinline__ float4 ld4c<bf16>(const bf16* p) {
 }
 
 // ---------------------------------------------------------------- fwd 1 (fast)
+// partial rows keep the 32-step granularity of the ABI: a CTA writes one row per 32-step half of its tile.
 template <typename TD>
-__global__ void __launch_bounds__(256) glu_dwconv_fwd_kernel(const TD* __restrict__ y2, long ldy, const float* __restrict__ w,
-                                                             const float* __restrict__ bias, float* __restrict__ z,
-                                                             float* __restrict__ partial, int T, int d) {
-    __shared__ __align__(16) float gt[WIN][CB];
-    __shared__ __align__(16) float red[2][4][CB];
-    const int b = blockIdx.y, chunk = blockIdx.x, nchunk = gridDim.x, c0 = blockIdx.z * CB;
-    const int t0 = chunk * TCH;
-    for (int idx = threadIdx.x; idx < WIN * (CB / 4); idx += 256) {
-        const int r = idx / (CB / 4), cv = (idx % (CB / 4)) * 4, tt = t0 - HALO + r;
-        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (tt >= 0 && tt < T && c0 + cv < d) {
-            const TD* row = y2 + ((long)b * T + tt) * ldy + c0 + cv;
-            const float4 v = ld4c<TD>(row), gate = ld4c<TD>(row + d);
-            g = make_float4(v.x * sigmoidf_(gate.x), v.y * sigmoidf_(gate.y), v.z * sigmoidf_(gate.z), v.w * sigmoidf_(gate.w));
+__global__ void __launch_bounds__(256, 4) glu_dwconv_fwd_kernel(const TD* __restrict__ y2, long ldy, const float* __restrict__ w,
+                                                                const float* __restrict__ bias, float* __restrict__ z,
+                                                                float* __restrict__ partial, int T, int d) {
+    __shared__ __align__(16) float gt[FWIN][FC];
+    __shared__ float wt[FC * KW];
+    __shared__ float red[2][4][FC];
+    const int b = blockIdx.y, c0 = blockIdx.z * FC, t0 = blockIdx.x * FT;
+    for (int i = threadIdx.x; i < FC * KW; i += 256) wt[i] = (c0 + i / KW < d) ? w[(long)c0 * KW + i] : 0.f;
+    // phase 1: GLU of the halo window; a thread's items share the channel quad, all its loads are issued before the math
+    {
+        const int cv = (threadIdx.x & 15) * 4, rbase = threadIdx.x >> 4;
+        constexpr int NIT = (FWIN + 15) / 16;
+        float4 v[NIT], gate[NIT];
+        const bool cok = c0 + cv < d;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int r = rbase + 16 * it, tt = t0 - HALO + r;
+            v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            gate[it] = v[it];
+            if (r < FWIN && tt >= 0 && tt < T && cok) {
+                const TD* row = y2 + ((long)b * T + tt) * ldy + c0 + cv;
+                v[it] = ld4c<TD>(row);
+                gate[it] = ld4c<TD>(row + d);
+            }
         }
-        *reinterpret_cast<float4*>(&gt[r][cv]) = g;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int r = rbase + 16 * it;
+            if (r < FWIN)
+                *reinterpret_cast<float4*>(&gt[r][cv]) = make_float4(v[it].x * sigmoidf_(gate[it].x), v[it].y * sigmoidf_(gate[it].y),
+                                                                    v[it].z * sigmoidf_(gate[it].z), v[it].w * sigmoidf_(gate[it].w));
+        }
     }
     __syncthreads();
-    const int cp = threadIdx.x & 63, qtr = threadIdx.x >> 6, c = 2 * cp, cg = c0 + c;
-    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+    const int c = threadIdx.x & (FC - 1), qtr = threadIdx.x >> 6, cg = c0 + c;
+    float s = 0.f, q = 0.f;
     if (cg < d) {
-        float w0[KW], w1[KW];
+        float wk[KW];
 #pragma unroll
-        for (int k = 0; k < KW; ++k) { w0[k] = w[cg * KW + k]; w1[k] = w[(cg + 1) * KW + k]; }
-        const float b0 = bias[cg], b1 = bias[cg + 1];
-        const int tb = qtr * TQ;
-        float2 win[TQ + KW - 1];
+        for (int k = 0; k < KW; ++k) wk[k] = wt[c * KW + k];
+        const float b0 = bias[cg];
+        const int tb = qtr * FQ;
+        float win[FQ + KW - 1];
 #pragma unroll
-        for (int j = 0; j < TQ + KW - 1; ++j) win[j] = *reinterpret_cast<const float2*>(&gt[tb + j][c]);
+        for (int j = 0; j < FQ + KW - 1; ++j) win[j] = gt[tb + j][c];
+        float* zp = z + ((long)b * T + t0 + tb) * d + cg;
 #pragma unroll
-        for (int i = 0; i < TQ; ++i) {
-            const int t = t0 + tb + i;
-            if (t < T) {
-                float a0 = b0, a1 = b1;
+        for (int i = 0; i < FQ; ++i) {
+            if (t0 + tb + i < T) {
+                float a = b0;
 #pragma unroll
-                for (int k = 0; k < KW; ++k) { a0 = fmaf(w0[k], win[i + k].x, a0); a1 = fmaf(w1[k], win[i + k].y, a1); }
-                *reinterpret_cast<float2*>(z + ((long)b * T + t) * d + cg) = make_float2(a0, a1);
-                s0 += a0; s1 += a1; q0 += a0 * a0; q1 += a1 * a1;
+                for (int k = 0; k < KW; ++k) a = fmaf(wk[k], win[i + k], a);
+                zp[(long)i * d] = a;
+                s += a;
+                q += a * a;
             }
         }
     }
-    red[0][qtr][c] = s0; red[0][qtr][c + 1] = s1;
-    red[1][qtr][c] = q0; red[1][qtr][c + 1] = q1;
+    red[0][qtr][c] = s;
+    red[1][qtr][c] = q;
     __syncthreads();
-    if (threadIdx.x < CB && c0 + threadIdx.x < d) {
-        const int cc = threadIdx.x;
-        float* part = partial + ((long)(b * nchunk + chunk)) * 2 * d;
-        part[c0 + cc] = (red[0][0][cc] + red[0][1][cc]) + (red[0][2][cc] + red[0][3][cc]);
-        part[d + c0 + cc] = (red[1][0][cc] + red[1][1][cc]) + (red[1][2][cc] + red[1][3][cc]);
+    if (threadIdx.x < 2 * FC) {  // thread -> (half, channel): quarters {0,1} are the first 32 steps, {2,3} the second
+        const int half = threadIdx.x >> 6, cc = threadIdx.x & (FC - 1);
+        const int n32 = (T + TCH - 1) / TCH, row32 = blockIdx.x * 2 + half;
+        if (row32 < n32 && c0 + cc < d) {
+            float* part = partial + ((long)b * n32 + row32) * 2 * d;
+            part[c0 + cc] = red[0][2 * half][cc] + red[0][2 * half + 1][cc];
+            part[d + c0 + cc] = red[1][2 * half][cc] + red[1][2 * half + 1][cc];
+        }
     }
 }
 
 // ---------------------------------------------------------------- column reduction of [nblk][2][d] partials (double)
-// block (32 channels, 8 row groups); FIN = 0: BatchNorm statistics + running stats, FIN = 1: backward sums + dgamma/dbeta
+// block (32 channels, RG row groups) = 1024 threads: the reduction is a latency chain per thread, so rows are spread over as
+// many threads as a CTA holds.  FIN = 0: BatchNorm statistics + running stats, FIN = 1: backward sums + dgamma/dbeta
+constexpr int RG = 32;
 template <int FIN>
-__global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict__ partial, int nblk, int d, long count, float eps,
-                                                        float momentum, float* __restrict__ o0, float* __restrict__ o1,
-                                                        float* __restrict__ r0, float* __restrict__ r1, int64_t* __restrict__ nbt) {
-    __shared__ double sh[2][8][33];
+__global__ void __launch_bounds__(32 * RG) bn_reduce_kernel(const float* __restrict__ partial, int nblk, int d, long count, float eps,
+                                                            float momentum, float* __restrict__ o0, float* __restrict__ o1,
+                                                            float* __restrict__ r0, float* __restrict__ r1, int64_t* __restrict__ nbt) {
+    __shared__ double sh[2][RG][33];
     const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5, c = blockIdx.x * 32 + cx;
     double s = 0.0, q = 0.0;
     if (c < d) {
-        for (int i = ry; i < nblk; i += 8) {
+#pragma unroll 4
+        for (int i = ry; i < nblk; i += RG) {
             s += (double)partial[(long)i * 2 * d + c];
             q += (double)partial[(long)i * 2 * d + d + c];
         }
@@ -263,7 +319,7 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict_
     __syncthreads();
     if (ry != 0 || c >= d) return;
 #pragma unroll
-    for (int j = 1; j < 8; ++j) { s += sh[0][j][cx]; q += sh[1][j][cx]; }
+    for (int j = 1; j < RG; ++j) { s += sh[0][j][cx]; q += sh[1][j][cx]; }
     if (FIN == 0) {
         const double mu = s / (double)count;
         double var = q / (double)count - mu * mu;
@@ -338,117 +394,131 @@ __global__ void __launch_bounds__(256) bn_swish_bwd_stats_kernel(const TD* __res
 }
 
 // ---------------------------------------------------------------- bwd 2 (fast)
-// shared: dz tile [WIN][CB], g tile [WIN][CB], sigmoid(gate) tile [TCH][CB]; the dz tile is reused as the reduction buffer
+// Same tiling as the forward kernel (FT x FC, thread = one channel x FT/4 steps).  shared: dz tile [FWIN][FC], g tile [FWIN][FC],
+// sigmoid(gate) tile [FT][FC]; the dz tile is reused as the reduction buffer.
 struct BwdSmem {
-    float dz[WIN][CB];
-    float g[WIN][CB];
-    float sg[TCH][CB];
+    float dz[FWIN][FC];
+    float g[FWIN][FC];
+    float sg[FT][FC];
+    float wt[FC * KW];
 };
+constexpr int NRED = KW + 3;
 
 template <typename TD>
-__global__ void __launch_bounds__(256) dwconv_glu_bwd_kernel(const TD* __restrict__ da, const float* __restrict__ z,
-                                                             const TD* __restrict__ y2, long ldy, const float* __restrict__ mean,
-                                                             const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                                             const float* __restrict__ beta, const float* __restrict__ sums,
-                                                             const float* __restrict__ w, TD* __restrict__ dy2, long lddy,
-                                                             float* __restrict__ dw, float* __restrict__ dbias,
-                                                             float* __restrict__ colsum, float* __restrict__ wpartial, int T, int d,
-                                                             float inv_count) {
+__global__ void __launch_bounds__(256, 3) dwconv_glu_bwd_kernel(const TD* __restrict__ da, const float* __restrict__ z,
+                                                                const TD* __restrict__ y2, long ldy, const float* __restrict__ mean,
+                                                                const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, const float* __restrict__ sums,
+                                                                const float* __restrict__ w, TD* __restrict__ dy2, long lddy,
+                                                                float* __restrict__ dw, float* __restrict__ dbias,
+                                                                float* __restrict__ colsum, float* __restrict__ wpartial, int T, int d,
+                                                                float inv_count) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
-    const int b = blockIdx.y, c0 = blockIdx.z * CB, t0 = blockIdx.x * TCH;
-    // phase 1: dz (BatchNorm + Swish backward) and g (GLU output) for the halo window, sigmoid(gate) for the centre rows
-    for (int idx = threadIdx.x; idx < WIN * (CB / 4); idx += 256) {
-        const int r = idx / (CB / 4), cv = (idx % (CB / 4)) * 4, tt = t0 - HALO + r;
-        float4 dzv = make_float4(0.f, 0.f, 0.f, 0.f), gv = dzv, sgv = dzv;
-        if (tt >= 0 && tt < T && c0 + cv < d) {
-            const int c = c0 + cv;
-            const long rr = (long)b * T + tt;
-            const float4 zz = *reinterpret_cast<const float4*>(z + rr * d + c);
-            const float4 gd = ld4c<TD>(da + rr * d + c);
-            const float4 m = *reinterpret_cast<const float4*>(mean + c), rs = *reinterpret_cast<const float4*>(rstd + c);
-            const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
-            const float4 su = *reinterpret_cast<const float4*>(sums + c), sq = *reinterpret_cast<const float4*>(sums + d + c);
-            const float zh0 = (zz.x - m.x) * rs.x, zh1 = (zz.y - m.y) * rs.y, zh2 = (zz.z - m.z) * rs.z, zh3 = (zz.w - m.w) * rs.w;
-            dzv.x = ga.x * rs.x * (gd.x * dswishf_(ga.x * zh0 + be.x) - su.x * inv_count - zh0 * sq.x * inv_count);
-            dzv.y = ga.y * rs.y * (gd.y * dswishf_(ga.y * zh1 + be.y) - su.y * inv_count - zh1 * sq.y * inv_count);
-            dzv.z = ga.z * rs.z * (gd.z * dswishf_(ga.z * zh2 + be.z) - su.z * inv_count - zh2 * sq.z * inv_count);
-            dzv.w = ga.w * rs.w * (gd.w * dswishf_(ga.w * zh3 + be.w) - su.w * inv_count - zh3 * sq.w * inv_count);
-            const TD* row = y2 + rr * ldy + c;
-            const float4 v = ld4c<TD>(row), gate = ld4c<TD>(row + d);
-            sgv = make_float4(sigmoidf_(gate.x), sigmoidf_(gate.y), sigmoidf_(gate.z), sigmoidf_(gate.w));
-            gv = make_float4(v.x * sgv.x, v.y * sgv.y, v.z * sgv.z, v.w * sgv.w);
+    const int b = blockIdx.y, c0 = blockIdx.z * FC, t0 = blockIdx.x * FT;
+    for (int i = threadIdx.x; i < FC * KW; i += 256) sm.wt[i] = (c0 + i / KW < d) ? w[(long)c0 * KW + i] : 0.f;
+    // phase 1: dz (BatchNorm + Swish backward) and g (GLU output) for the halo window, sigmoid(gate) for the centre rows.
+    // A thread keeps one channel quad for all its rows: the per-channel constants are loaded once.
+    {
+        const int cv = (threadIdx.x & 15) * 4, rbase = threadIdx.x >> 4, c = c0 + cv;
+        const bool cok = c < d;
+        float4 m = make_float4(0.f, 0.f, 0.f, 0.f), rs = m, ga = m, be = m, su = m, sq = m;
+        if (cok) {
+            m = *reinterpret_cast<const float4*>(mean + c); rs = *reinterpret_cast<const float4*>(rstd + c);
+            ga = *reinterpret_cast<const float4*>(gamma + c); be = *reinterpret_cast<const float4*>(beta + c);
+            su = *reinterpret_cast<const float4*>(sums + c); sq = *reinterpret_cast<const float4*>(sums + d + c);
+            su.x *= inv_count; su.y *= inv_count; su.z *= inv_count; su.w *= inv_count;
+            sq.x *= inv_count; sq.y *= inv_count; sq.z *= inv_count; sq.w *= inv_count;
         }
-        *reinterpret_cast<float4*>(&sm.dz[r][cv]) = dzv;
-        *reinterpret_cast<float4*>(&sm.g[r][cv]) = gv;
-        if (r >= HALO && r < HALO + TCH) *reinterpret_cast<float4*>(&sm.sg[r - HALO][cv]) = sgv;
+        constexpr int NIT = (FWIN + 15) / 16;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int r = rbase + 16 * it, tt = t0 - HALO + r;
+            if (r >= FWIN) break;
+            float4 dzv = make_float4(0.f, 0.f, 0.f, 0.f), gv = dzv, sgv = dzv;
+            if (tt >= 0 && tt < T && cok) {
+                const long rr = (long)b * T + tt;
+                const float4 zz = *reinterpret_cast<const float4*>(z + rr * d + c);
+                const float4 gd = ld4c<TD>(da + rr * d + c);
+                const TD* row = y2 + rr * ldy + c;
+                const float4 v = ld4c<TD>(row), gate = ld4c<TD>(row + d);
+                const float zh0 = (zz.x - m.x) * rs.x, zh1 = (zz.y - m.y) * rs.y, zh2 = (zz.z - m.z) * rs.z, zh3 = (zz.w - m.w) * rs.w;
+                dzv.x = ga.x * rs.x * (gd.x * dswishf_(ga.x * zh0 + be.x) - su.x - zh0 * sq.x);
+                dzv.y = ga.y * rs.y * (gd.y * dswishf_(ga.y * zh1 + be.y) - su.y - zh1 * sq.y);
+                dzv.z = ga.z * rs.z * (gd.z * dswishf_(ga.z * zh2 + be.z) - su.z - zh2 * sq.z);
+                dzv.w = ga.w * rs.w * (gd.w * dswishf_(ga.w * zh3 + be.w) - su.w - zh3 * sq.w);
+                sgv = make_float4(sigmoidf_(gate.x), sigmoidf_(gate.y), sigmoidf_(gate.z), sigmoidf_(gate.w));
+                gv = make_float4(v.x * sgv.x, v.y * sgv.y, v.z * sgv.z, v.w * sgv.w);
+            }
+            *reinterpret_cast<float4*>(&sm.dz[r][cv]) = dzv;
+            *reinterpret_cast<float4*>(&sm.g[r][cv]) = gv;
+            if (r >= HALO && r < HALO + FT) *reinterpret_cast<float4*>(&sm.sg[r - HALO][cv]) = sgv;
+        }
     }
     __syncthreads();
     // phase 2
-    const int cp = threadIdx.x & 63, qtr = threadIdx.x >> 6, c = 2 * cp, cg = c0 + c;
+    const int c = threadIdx.x & (FC - 1), qtr = threadIdx.x >> 6, cg = c0 + c;
     const bool act = cg < d;
-    float aw0[KW], aw1[KW];
+    float aw[KW];
 #pragma unroll
-    for (int k = 0; k < KW; ++k) { aw0[k] = 0.f; aw1[k] = 0.f; }
-    float ab0 = 0.f, ab1 = 0.f, cv0 = 0.f, cv1 = 0.f, cg0 = 0.f, cg1 = 0.f;
+    for (int k = 0; k < KW; ++k) aw[k] = 0.f;
+    float ab = 0.f, csv = 0.f, csg = 0.f;
     if (act) {
-        const int tb = qtr * TQ;
+        const int tb = qtr * FQ;
         {
-            float w0[KW], w1[KW];
+            float wk[KW];
 #pragma unroll
-            for (int k = 0; k < KW; ++k) { w0[k] = w[cg * KW + k]; w1[k] = w[(cg + 1) * KW + k]; }
-            float2 dzw[TQ + KW - 1];
+            for (int k = 0; k < KW; ++k) wk[k] = sm.wt[c * KW + k];
+            float dzw[FQ + KW - 1];
 #pragma unroll
-            for (int j = 0; j < TQ + KW - 1; ++j) dzw[j] = *reinterpret_cast<const float2*>(&sm.dz[tb + j][c]);
+            for (int j = 0; j < FQ + KW - 1; ++j) dzw[j] = sm.dz[tb + j][c];
+            TD* orow = dy2 + ((long)b * T + t0 + tb) * lddy + cg;
 #pragma unroll
-            for (int i = 0; i < TQ; ++i) {
-                const int t = t0 + tb + i;
+            for (int i = 0; i < FQ; ++i) {
                 // z[t'] = sum_k w[k] g[t'+k-7]  =>  dg[t] = sum_k w[k] dz[t+7-k]   (window index i + 14 - k)
-                float dg0 = 0.f, dg1 = 0.f;
+                float dg = 0.f;
 #pragma unroll
-                for (int k = 0; k < KW; ++k) { dg0 = fmaf(w0[k], dzw[i + KW - 1 - k].x, dg0); dg1 = fmaf(w1[k], dzw[i + KW - 1 - k].y, dg1); }
-                if (t < T) {
-                    const float2 sg = *reinterpret_cast<const float2*>(&sm.sg[tb + i][c]);
-                    const float2 gg = *reinterpret_cast<const float2*>(&sm.g[tb + i + HALO][c]);
-                    const float v0 = dg0 * sg.x, v1 = dg1 * sg.y;                              // d(value half)
-                    const float g0 = dg0 * gg.x * (1.f - sg.x), g1 = dg1 * gg.y * (1.f - sg.y);  // d(gate half): v*s*(1-s) = g*(1-s)
-                    TD* orow = dy2 + ((long)b * T + t) * lddy + cg;
-                    st2<TD>(orow, v0, v1);
-                    st2<TD>(orow + d, g0, g1);
-                    cv0 += v0; cv1 += v1; cg0 += g0; cg1 += g1;
+                for (int k = 0; k < KW; ++k) dg = fmaf(wk[k], dzw[i + KW - 1 - k], dg);
+                if (t0 + tb + i < T) {
+                    const float sg = sm.sg[tb + i][c], gg = sm.g[tb + i + HALO][c];
+                    const float v0 = dg * sg;                  // d(value half)
+                    const float g0 = dg * gg * (1.f - sg);     // d(gate half): v*s*(1-s) = g*(1-s)
+                    orow[(long)i * lddy] = from_f32<TD>(v0);
+                    orow[(long)i * lddy + d] = from_f32<TD>(g0);
+                    csv += v0;
+                    csg += g0;
                 }
             }
         }
         {
             // dw[k] += dz[t] * g[t+k-7] ; db += dz[t]     (dz[t] = 0 beyond the utterance end)
-            float2 gw[TQ + KW - 1];
+            float gw[FQ + KW - 1];
 #pragma unroll
-            for (int j = 0; j < TQ + KW - 1; ++j) gw[j] = *reinterpret_cast<const float2*>(&sm.g[tb + j][c]);
+            for (int j = 0; j < FQ + KW - 1; ++j) gw[j] = sm.g[tb + j][c];
 #pragma unroll
-            for (int i = 0; i < TQ; ++i) {
-                const float2 dzc = *reinterpret_cast<const float2*>(&sm.dz[tb + i + HALO][c]);
+            for (int i = 0; i < FQ; ++i) {
+                const float dzc = sm.dz[tb + i + HALO][c];
 #pragma unroll
-                for (int k = 0; k < KW; ++k) { aw0[k] = fmaf(dzc.x, gw[i + k].x, aw0[k]); aw1[k] = fmaf(dzc.y, gw[i + k].y, aw1[k]); }
-                ab0 += dzc.x; ab1 += dzc.y;
+                for (int k = 0; k < KW; ++k) aw[k] = fmaf(dzc, gw[i + k], aw[k]);
+                ab += dzc;
             }
         }
     }
-    __syncthreads();  // every thread is done with the tiles: reuse sm.dz as the reduction buffer [4][NRED][CB]
-    constexpr int NRED = KW + 3;
+    __syncthreads();  // every thread is done with the tiles: reuse sm.dz as the reduction buffer [4][NRED][FC]
     float* red = &sm.dz[0][0];
     {
-        float* mine = red + (long)qtr * NRED * CB;
+        float* mine = red + (long)qtr * NRED * FC;
 #pragma unroll
-        for (int k = 0; k < KW; ++k) { mine[k * CB + c] = aw0[k]; mine[k * CB + c + 1] = aw1[k]; }
-        mine[KW * CB + c] = ab0; mine[KW * CB + c + 1] = ab1;
-        mine[(KW + 1) * CB + c] = cv0; mine[(KW + 1) * CB + c + 1] = cv1;
-        mine[(KW + 2) * CB + c] = cg0; mine[(KW + 2) * CB + c + 1] = cg1;
+        for (int k = 0; k < KW; ++k) mine[k * FC + c] = aw[k];
+        mine[KW * FC + c] = ab;
+        mine[(KW + 1) * FC + c] = csv;
+        mine[(KW + 2) * FC + c] = csg;
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < NRED * CB; idx += 256) {
-        const int k = idx / CB, cc = idx % CB;
+    for (int idx = threadIdx.x; idx < NRED * FC; idx += 256) {
+        const int k = idx / FC, cc = idx % FC;
         if (c0 + cc >= d) continue;
-        const float v = (red[idx] + red[NRED * CB + idx]) + (red[2 * NRED * CB + idx] + red[3 * NRED * CB + idx]);
+        const float v = (red[idx] + red[NRED * FC + idx]) + (red[2 * NRED * FC + idx] + red[3 * NRED * FC + idx]);
         if (wpartial) {  // deterministic two-stage reduction: [CTA (b, chunk)][NRED][d], summed by dwconv_reduce_kernel
             wpartial[(((long)b * gridDim.x + blockIdx.x) * NRED + k) * d + c0 + cc] = v;
             continue;
@@ -459,20 +529,21 @@ __global__ void __launch_bounds__(256) dwconv_glu_bwd_kernel(const TD* __restric
     }
 }
 
-// second stage of the depthwise-weight / bias / pointwise-bias gradient: block (32 channels, 8 row groups), grid (d/32, KW+3)
-__global__ void __launch_bounds__(256) dwconv_reduce_kernel(const float* __restrict__ wpartial, int nblk, int d, float* __restrict__ dw,
-                                                            float* __restrict__ dbias, float* __restrict__ colsum) {
-    __shared__ float sh[8][33];
-    constexpr int NRED = KW + 3;
+// second stage of the depthwise-weight / bias / pointwise-bias gradient: block (32 channels, RG row groups), grid (d/32, KW+3)
+__global__ void __launch_bounds__(32 * RG) dwconv_reduce_kernel(const float* __restrict__ wpartial, int nblk, int d, float* __restrict__ dw,
+                                                                float* __restrict__ dbias, float* __restrict__ colsum) {
+    __shared__ float sh[RG][33];
     const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5, c = blockIdx.x * 32 + cx, k = blockIdx.y;
     float s = 0.f;
-    if (c < d)
-        for (int i = ry; i < nblk; i += 8) s += wpartial[((long)i * NRED + k) * d + c];
+    if (c < d) {
+#pragma unroll 4
+        for (int i = ry; i < nblk; i += RG) s += wpartial[((long)i * NRED + k) * d + c];
+    }
     sh[ry][cx] = s;
     __syncthreads();
     if (ry != 0 || c >= d) return;
 #pragma unroll
-    for (int j = 1; j < 8; ++j) s += sh[j][cx];
+    for (int j = 1; j < RG; ++j) s += sh[j][cx];
     if (k < KW) dw[(long)c * KW + k] += s;
     else if (k == KW) dbias[c] += s;
     else if (colsum) colsum[(k == KW + 1 ? 0 : d) + c] += s;
@@ -493,7 +564,7 @@ int lasr_glu_dwconv_fwd(const void* y2, int dtype, int64_t ldy, const float* w, 
     cudaStream_t st = (cudaStream_t)stream;
     const bool fast = fast_d(d) && ldy % 4 == 0 && ((uintptr_t)y2 & 15) == 0 && ((uintptr_t)z & 15) == 0;
     if (fast) {
-        dim3 grid(ceil_div(T, TCH), B, ceil_div(d, CB));
+        dim3 grid(ceil_div(T, FT), B, ceil_div(d, FC));
         if (dtype == LASR_F32) glu_dwconv_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)y2, ldy, w, bias, z, partial, T, d);
         else if (dtype == LASR_BF16) glu_dwconv_fwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)y2, ldy, w, bias, z, partial, T, d);
         else { set_error("glu_dwconv_fwd: bad dtype"); return LASR_ERR_UNSUPPORTED; }
@@ -512,7 +583,7 @@ int lasr_bn_finalize(const float* partial, int nblk, int d, int64_t count, float
     LASR_REQUIRE(!training || ((running_mean != nullptr) == (running_var != nullptr)), "bn_finalize: running stats come in pairs");
     cudaStream_t st = (cudaStream_t)stream;
     if (!training) bn_eval_stats_kernel<<<ceil_div(d, 128), 128, 0, st>>>(running_mean, running_var, eps, mean, rstd, d);
-    else bn_reduce_kernel<0><<<ceil_div(d, 32), 256, 0, st>>>(partial, nblk, d, count, eps, momentum, mean, rstd, running_mean, running_var,
+    else bn_reduce_kernel<0><<<ceil_div(d, 32), 32 * RG, 0, st>>>(partial, nblk, d, count, eps, momentum, mean, rstd, running_mean, running_var,
                                                              num_batches_tracked);
     return check_launch("bn_finalize");
 }
@@ -522,9 +593,14 @@ int lasr_bn_swish_fwd(const float* z, const float* mean, const float* rstd, cons
     LASR_REQUIRE(z && mean && rstd && gamma && beta && a && rows > 0 && d % 2 == 0, "bn_swish_fwd: bad args");
     const long n = rows * d;
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == LASR_F32) bn_swish_fwd_kernel<float><<<ceil_div(n / 2, 256), 256, 0, st>>>(z, mean, rstd, gamma, beta, (float*)a, n, d);
-    else if (dtype == LASR_BF16) bn_swish_fwd_kernel<bf16><<<ceil_div(n / 2, 256), 256, 0, st>>>(z, mean, rstd, gamma, beta, (bf16*)a, n, d);
-    else { set_error("bn_swish_fwd: bad dtype"); return LASR_ERR_UNSUPPORTED; }
+    if (dtype != LASR_F32 && dtype != LASR_BF16) { set_error("bn_swish_fwd: bad dtype"); return LASR_ERR_UNSUPPORTED; }
+    const bool vec = d % 4 == 0 && (((uintptr_t)z | (uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)a) & 15) == 0;
+    if (vec) {
+        const long threads = (long)(d >> 2) * ((rows + 3) / 4);
+        if (dtype == LASR_F32) bn_swish_fwd_vec_kernel<float><<<ceil_div(threads, 256), 256, 0, st>>>(z, mean, rstd, gamma, beta, (float*)a, rows, d);
+        else bn_swish_fwd_vec_kernel<bf16><<<ceil_div(threads, 256), 256, 0, st>>>(z, mean, rstd, gamma, beta, (bf16*)a, rows, d);
+    } else if (dtype == LASR_F32) bn_swish_fwd_kernel<float><<<ceil_div(n / 2, 256), 256, 0, st>>>(z, mean, rstd, gamma, beta, (float*)a, n, d);
+    else bn_swish_fwd_kernel<bf16><<<ceil_div(n / 2, 256), 256, 0, st>>>(z, mean, rstd, gamma, beta, (bf16*)a, n, d);
     return check_launch("bn_swish_fwd");
 }
 
@@ -547,7 +623,7 @@ int lasr_bn_swish_bwd_stats(const void* da, int dtype, const float* z, const flo
     }
     int rc = check_launch("bn_swish_bwd_stats");
     if (rc) return rc;
-    bn_reduce_kernel<1><<<ceil_div(d, 32), 256, 0, st>>>(partial, nblk, d, 0, 0.f, 0.f, sums, nullptr, dgamma, dbeta, nullptr);
+    bn_reduce_kernel<1><<<ceil_div(d, 32), 32 * RG, 0, st>>>(partial, nblk, d, 0, 0.f, 0.f, sums, nullptr, dgamma, dbeta, nullptr);
     return check_launch("bn_bwd_finalize");
 }
 
@@ -563,7 +639,7 @@ int lasr_dwconv_glu_bwd(const void* da, const float* z, const void* y2, int dtyp
                       (((uintptr_t)da | (uintptr_t)z | (uintptr_t)y2 | (uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)gamma | (uintptr_t)beta |
                         (uintptr_t)sums) & 15) == 0;
     if (fast) {
-        dim3 grid(ceil_div(T, TCH), B, ceil_div(d, CB));
+        dim3 grid(ceil_div(T, FT), B, ceil_div(d, FC));
         const int smem = (int)sizeof(BwdSmem);
         static bool configured = false;
         if (!configured) {
@@ -580,7 +656,7 @@ int lasr_dwconv_glu_bwd(const void* da, const float* z, const void* y2, int dtyp
                                                                 (bf16*)dy2, lddy, dw, dbias, colsum, wpartial, T, d, inv);
         int rc = check_launch("dwconv_glu_bwd");
         if (rc || !wpartial) return rc;
-        dwconv_reduce_kernel<<<dim3(ceil_div(d, 32), KW + 3), 256, 0, st>>>(wpartial, B * ceil_div(T, TCH), d, dw, dbias, colsum);
+        dwconv_reduce_kernel<<<dim3(ceil_div(d, 32), KW + 3), 32 * RG, 0, st>>>(wpartial, B * ceil_div(T, FT), d, dw, dbias, colsum);
         return check_launch("dwconv_reduce");
     }
     dim3 grid(ceil_div(T, TCH), B);

@@ -20,6 +20,13 @@ namespace lasr {
 // ---------------------------------------------------------------------------------------------
 // K_A
 // ---------------------------------------------------------------------------------------------
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr double LN2 = 0.6931471805599453;
+// "log zero" of the lattice: a large FINITE sentinel instead of -inf.  max/sub/ex2/lg2 need no guard then (two sentinels
+// combine to sentinel + 1 == sentinel in fp32, a sentinel next to a live value contributes ex2(-1e30) = 0), which removes the
+// compare/select pair from every log-sum-exp on the sequential critical path.
+constexpr float LNEG = -1.0e30f;
+
 template <typename T> struct Vec4;
 template <> struct Vec4<float> {
     typedef float4 type;
@@ -141,8 +148,8 @@ __global__ void __launch_bounds__(256) ctc_softmax_gather_kernel(const CtcDenseP
         float* le = p.lp_ext + ((long)b * p.T + t) * (p.lmax + 1);
         const int64_t* tg = p.targets + (long)b * p.lmax;
         const float xb = to_f32<T>(x[p.blank]);
-        for (int k2 = gl; k2 <= L; k2 += GROUP)
-            le[k2] = (k2 == 0) ? (xb - lse) : (to_f32<T>(x[(int)tg[k2 - 1]]) - xb);
+        for (int k2 = gl; k2 <= L; k2 += GROUP)  // log2 units: the lattice runs on ex2 / lg2 directly
+            le[k2] = LOG2E * ((k2 == 0) ? (xb - lse) : (to_f32<T>(x[(int)tg[k2 - 1]]) - xb));
     } else {
         float z[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -188,7 +195,7 @@ __global__ void __launch_bounds__(256) ctc_softmax_gather_generic(const CtcDense
     const int64_t* tg = p.targets + (long)b * p.lmax;
     const float xb = to_f32<T>(x[p.blank]);
     for (int k2 = threadIdx.x; k2 <= L; k2 += 256)
-        le[k2] = (k2 == 0) ? (xb - lse) : (to_f32<T>(x[(int)tg[k2 - 1]]) - xb);
+        le[k2] = LOG2E * ((k2 == 0) ? (xb - lse) : (to_f32<T>(x[(int)tg[k2 - 1]]) - xb));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -200,18 +207,25 @@ __global__ void __launch_bounds__(256) ctc_softmax_gather_generic(const CtcDense
 // shfl + max + ex2 + add + lg2 (fast intrinsics: their 2^-22 error is below the fp32 ulp of the lattice values).
 // Inputs are register-prefetched PF steps ahead.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float fexp(float x) { return __expf(x); }
-// Branch-free: states at -inf are the common case (unreachable / invalid lattice cells), and a data-dependent early return
-// makes every log-sum-exp a divergent region.  With ms = 0 when all inputs are -inf, exp(-inf - 0) = 0 and log(0) = -inf.
+// log2-domain log-sum-exp on the raw MUFU ops (ex2.approx.ftz / lg2.approx.ftz: no denormal fix-up code, no scaling by
+// log2(e) / ln 2); their 2^-22 relative error is below the fp32 ulp of the lattice values.
+__device__ __forceinline__ float fex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float flg2(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float lse2q(float a, float b) {
     const float m = fmaxf(a, b);
-    const float ms = (m == -INFINITY) ? 0.f : m;
-    return ms + __logf(fexp(a - ms) + fexp(b - ms));
+    return m + flg2(fex2(a - m) + fex2(b - m));
 }
 __device__ __forceinline__ float lse3q(float a, float b, float c) {
     const float m = fmaxf(fmaxf(a, b), c);
-    const float ms = (m == -INFINITY) ? 0.f : m;
-    return ms + __logf(fexp(a - ms) + fexp(b - ms) + fexp(c - ms));
+    return m + flg2(fex2(a - m) + fex2(b - m) + fex2(c - m));
 }
 
 template <int R, int PFW, int NW>
@@ -232,14 +246,13 @@ __global__ void __launch_bounds__(32 * NW) ctc_lattice_warp_kernel(const float* 
     }
     const int64_t* tg = targets + (long)b * lmax;
     const float* lpb = lp_ext + (long)b * T * W;
-    const float NEG = -INFINITY;
+    const float NEG = LNEG;
     int kcol[R];          // column of this pair's label emission in lp_ext (clamped: idle pairs read valid memory)
-    bool v_bl[R], v_lb[R], skip[R];
+    bool v_lb[R], skip[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int k = tid * R + r;
         kcol[r] = min(k, lmax - 1) + 1;
-        v_bl[r] = k <= L;
         v_lb[r] = k < L;
         const long my = (k < L) ? tg[k] : -1;
         if (!is_beta) skip[r] = (k >= 1 && k < L) && (tg[k - 1] != my);   // alpha: 2k-1 -> 2k+1 allowed
@@ -294,10 +307,12 @@ __global__ void __launch_bounds__(32 * NW) ctc_lattice_warp_kernel(const float* 
                         n_bl[r] = lse2q(s_bl[r], prev);
                         n_lb[r] = cl[i][r] + lse3q(s_lb[r], s_bl[r], skip[r] ? prev : NEG);
                     }
+                    // pairs beyond L need no masking here: alpha only flows towards higher states, so whatever they hold never
+                    // reaches a live state (and nothing downstream reads them)
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
-                        s_bl[r] = v_bl[r] ? n_bl[r] : NEG;
-                        s_lb[r] = v_lb[r] ? n_lb[r] : NEG;
+                        s_bl[r] = n_bl[r];
+                        s_lb[r] = n_lb[r];
                         const int k = tid * R + r;
                         if (k < W) alb[(long)t * W + k] = make_float2(s_bl[r], s_lb[r]);
                     }
@@ -322,9 +337,10 @@ __global__ void __launch_bounds__(32 * NW) ctc_lattice_warp_kernel(const float* 
         }
         __syncthreads();
         if (tid == 0) {
-            const float tot = lse2q(fin[0], fin[1]);
-            nll[b] = (float)(-((double)tot + csum));
-            tot_out[b] = tot;
+            const float tot = lse2q(fin[0], fin[1]);          // log2 units, blank-normalised
+            const bool feasible = tot > 0.5f * LNEG;
+            nll[b] = feasible ? (float)(-((double)tot + csum) * LN2) : INFINITY;
+            tot_out[b] = feasible ? tot : -INFINITY;
         }
     } else {
         float2* beb = be + (long)b * T * W;
@@ -375,9 +391,11 @@ __global__ void __launch_bounds__(32 * NW) ctc_lattice_warp_kernel(const float* 
                         n_bl[r] = lse2q(s_bl[r], s_lb[r]);
                         n_lb[r] = cl[i][r] + lse3q(s_lb[r], x1, skip[r] ? x2 : NEG);
                     }
+                    // dead blank states stay at the sentinel by themselves (sentinel + lg2(2) == sentinel); dead LABEL states must be
+                    // forced: their emission column was never written by the gather kernel (k > L), and beta flows downwards
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
-                        s_bl[r] = v_bl[r] ? n_bl[r] : NEG;
+                        s_bl[r] = n_bl[r];
                         s_lb[r] = v_lb[r] ? n_lb[r] : NEG;
                         const int k = tid * R + r;
                         if (k < W) beb[(long)t * W + k] = make_float2(s_bl[r], s_lb[r]);
@@ -421,12 +439,12 @@ __global__ void __launch_bounds__(256) ctc_scatter_ab_kernel(const float2* __res
     float bsum = 0.f;
     for (int k = lane; k <= L; k += 32) {
         const float2 a = al[base + k], bb = be[base + k];
-        float o_bl = (a.x > -INFINITY && bb.x > -INFINITY) ? __expf(a.x + bb.x - tt) : 0.f;
+        float o_bl = fex2(a.x + bb.x - tt);              // log2 units; a sentinel on either side gives ex2(-1e30) = 0
         if (!feasible) o_bl = qnan;
         bsum += o_bl;
         if (k < L) {
             const float e = lp_ext[base + k + 1];
-            float o_lb = (a.y > -INFINITY && bb.y > -INFINITY) ? __expf(a.y + bb.y - e - tt) : 0.f;
+            float o_lb = fex2(a.y + bb.y - e - tt);
             if (!feasible) o_lb = qnan;
             const int c = (int)tg[k];
             if constexpr (sizeof(GT) == 4) atomicAdd(reinterpret_cast<float*>(g) + c, -s * o_lb);

@@ -134,3 +134,21 @@ def test_ctc_full_size_properties():
     assert (grad[~live] == 0).all()
     # blank column: softmax - occupancy in [-1, 1]
     assert grad.abs().max().item() <= 1.0 + 3e-3  # fp32 log-space lattice over T = 1600 steps (occupancy error ~ sqrt(T) * ulp)
+
+
+def test_ctc_poisoned_workspace_is_harmless():
+    """The lattice kernels must never read workspace cells the gather kernel did not write (ragged target lengths leave the
+    emission columns k > L_b untouched): a workspace pre-filled with NaN bit patterns gives bit-identical results."""
+    from liteasr_b200 import ops
+    for (T, B, V, L) in ((300, 8, 1000, 100), (160, 6, 300, 40), (90, 5, 64, 20)):
+        logits, targets, in_len, tgt_len = make_case(T, B, V, L, seed=7 * T + L)
+        tgt_len[1] = max(1, L // 3)
+        x = logits.float().cuda()
+        args = (targets.cuda(), in_len.cuda(), tgt_len.cuda())
+        n = ops.ctc_workspace_bytes(T, B, L)
+        ws0 = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        ws1 = torch.full((n,), 0xFF, dtype=torch.uint8, device="cuda")  # 0xFFFFFFFF = NaN
+        nll0, g0 = ops.ctc_fwdbwd(x, *args, time_major=True, workspace=ws0)
+        nll1, g1 = ops.ctc_fwdbwd(x, *args, time_major=True, workspace=ws1)
+        assert torch.isfinite(g1).all() and torch.isfinite(nll1).all()
+        assert torch.equal(g0, g1) and torch.equal(nll0, nll1)
