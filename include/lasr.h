@@ -196,6 +196,20 @@ int lasr_conv1_bwd(const float* x, const void* dh1, int dtype, float* dw, float*
 int lasr_im2col_s2(const void* h1, void* col, int dtype, int B, int T1, int F1, int d, void* stream);
 int lasr_col2im_s2_relu(const void* dcol, const void* h1, void* dh1, int dtype, int B, int T1, int F1, int d, void* stream);
 
+/* Parity-plane front end (bf16 / tcgen05 mode): conv1 writes h1p (B,4,U*V,d) with t1 = 2u+pt, f1 = 2v+pf, plane = pt*2+pf,
+ * U = ceil(T1/2), V = ceil(F1/2), slots without a (t1,f1) zero; conv2 (nets/subsampling.py:33-34) then runs as an implicit
+ * GEMM whose operand tiles are dense TMA boxes at a per-tap row offset -- no im2col / col2im buffers.
+ *   conv2_fwd  : h2p (B, T2*V, d) bf16 = relu(conv3x3 s2 + bias); slot f2 = V-1 of every t2 row is padding (never read)
+ *   conv2_dgrad: dh1p (B,4,U*V,d) = relu'(h1p) * conv2^T(dy2p); dy2p (B, T2*V, d) bf16 with the padding slot ZERO
+ *   conv2_wgrad: dw2k (d, 9d) fp32 (co, kh, kw, ci) += dy2p^T * h1p patches
+ *   conv1_bwd_planes: conv1 weight / bias gradient from dh1p */
+int lasr_conv1_fwd_planes(const float* x, const float* w, const float* bias, void* h1p, int B, int T, int F, int d, void* stream);
+int lasr_conv1_bwd_planes(const float* x, const void* dh1p, float* dw, float* dbias, int B, int T, int F, int d, void* stream);
+int lasr_conv2_fwd(const void* h1p, const void* w2k, const float* bias, void* h2p, int B, int T, int F, int d, void* stream);
+int lasr_conv2_dgrad(const void* dy2p, const void* w2k, const void* h1p, void* dh1p, int B, int T, int F, int d, void* stream);
+int lasr_conv2_wgrad(const void* dy2p, const void* h1p, float* dw2k, int B, int T, int F, int d, void* stream);
+
+
 /* ------------------------------------------------------------------------------------------------
  * Attention score post-processing (nets/attention.py:46-59,99-118,145-152): legacy rel_shift of bd
  * (NULL for plain attention) + scale + key/causal mask (-1e38 fill) + softmax, and the backward

@@ -19,6 +19,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <cstring>
 #include <type_traits>
 
 #include "common.cuh"
@@ -66,6 +67,13 @@ struct TcParams {
     long lddact;
     float* colsum;     // colsum[b1*cs1 + b2*cs2 + n] += sum_m C[m, n]
     long cs1, cs2;
+    // implicit-GEMM 3x3 stride-2 convolution over parity planes (see conv2_tc_dispatch): only the TMA producer changes
+    int conv_mode;     // 0 plain GEMM | 1 forward | 2 input gradient (one parity class) | 3 weight gradient
+    int conv_kbt;      // K blocks per tap (= channels / 64)
+    int conv_d;        // channels
+    int conv_off[9];   // flattened (u,v) row shift of the tap: (kh >> 1) * V + (kw >> 1)
+    int conv_plane[9]; // parity plane of the tap: (kh & 1) * 2 + (kw & 1)
+    int conv_tap[9];   // tap id kh * 3 + kw (column block of the (co, tap, ci) weight)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -455,6 +463,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     uint8_t* sa = ring + s * p.stage_bytes;
                     uint8_t* sb = sa + A_BYTES;
                     const int k0 = (w.kb_begin + i) * BK;
+                    if (p.conv_mode != 0) {
+                        const int kb = w.kb_begin + i;
+                        if (p.conv_mode == 1) {         // A = h1 planes (rows shifted per tap), B = (co, tap*ci) weight, both K-major
+                            const int tp = kb / p.conv_kbt, kc = kb - tp * p.conv_kbt;
+                            tma_load_4d(sa, &tma_a, full_bar + s, kc * BK, w.m0 + p.conv_off[tp], p.conv_plane[tp], w.b1);
+                            tma_load_4d(sb, &tma_b, full_bar + s, k0, w.n0, 0, 0);
+                        } else if (p.conv_mode == 2) {  // A = dY (K-major, rows shifted back), B = weight MN-major at the tap's columns
+                            const int tp = kb / p.conv_kbt, kc = kb - tp * p.conv_kbt;
+                            tma_load_4d(sa, &tma_a, full_bar + s, kc * BK, w.m0 - p.conv_off[tp], 0, w.b1);
+                            for (int j = 0; j < p.bn / 64; ++j)
+                                tma_load_4d(sb + j * 8192, &tma_b, full_bar + s, w.n0 + 64 * j + p.conv_tap[tp] * p.conv_d, kc * BK, 0, 0);
+                        } else {                        // A = dY^T, B = h1 planes, both MN-major; the N tile selects the tap
+                            const int tp = w.n0 / p.conv_d, nloc = w.n0 - tp * p.conv_d;
+#pragma unroll
+                            for (int j = 0; j < BM / 64; ++j)
+                                tma_load_4d(sa + j * 8192, &tma_a, full_bar + s, w.m0 + 64 * j, k0, 0, w.b1);
+                            for (int j = 0; j < p.bn / 64; ++j)
+                                tma_load_4d(sb + j * 8192, &tma_b, full_bar + s, nloc + 64 * j, k0 + p.conv_off[tp], p.conv_plane[tp], w.b1);
+                        }
+                    } else {
                     if (!A_MN) {
                         tma_load_4d(sa, &tma_a, full_bar + s, k0, w.m0, ab2, ab1);  // box {64 k, 128 m}
                     } else {
@@ -467,6 +495,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     } else {
                         for (int j = 0; j < p.bn / 64; ++j)
                             tma_load_4d(sb + j * 8192, &tma_b, full_bar + s, w.n0 + 64 * j, k0, bb2, bb1);
+                    }
                     }
                     if (++s == p.stages) { s = 0; ph ^= 1; }
                 }
@@ -700,9 +729,98 @@ int gemm_tc_dispatch(const lasr_gemm_args* a, cudaStream_t st) {
     }
     p.total_units = (int)units;
 
+    p.conv_mode = 0;
     p.a_mn = a->trans_a ? 1 : 0;
     p.b_mn = a->trans_b ? 1 : 0;
     if (a->c_dtype != LASR_F32 && (p.epi_mode == EPI_RES || p.epi_mode == EPI_ACC)) p.epi_mode = EPI_GENERIC;
+    return launch_tc(ma, mb, p, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Conv2d(d -> d, 3x3, stride 2) + ReLU of the sub-sampling front end (nets/subsampling.py:33-34) as an implicit GEMM.
+// conv1 writes its output in PARITY PLANES  h1p[b][pt*2+pf][u*V + v][c]  (t1 = 2u+pt, f1 = 2v+pf, U x V slots per plane, pad
+// slots zero), and conv2's output / output gradient live in the padded layout  y[b][t2*V + f2][c]  (V slots per t2 row,
+// F2 = V-1 of them real, the rest zero in the gradient).  With the same row pitch V on both sides, tap (kh,kw) of output row
+// r = t2*V+f2 reads plane (kh&1, kw&1) at row r + (kh>>1)*V + (kw>>1): every operand tile is a dense, unit-stride TMA box at a
+// per-tap row offset, so the 9x im2col matrix (3.3 GB at C2/B=126) and the col2im pass never exist.
+//   forward : C[b][r][co]          = relu(bias + sum_tap sum_ci h1p[b][plane][r+off][ci] W[co][tap][ci])
+//   dgrad   : dh1p[b][pl][r][ci]   = relu'(h1p) * sum_{tap in class pl} sum_co dY[b][r-off][co] W[co][tap][ci]   (4 launches)
+//   wgrad   : dW[co][tap][ci]     += sum_b sum_r dY[b][r][co] h1p[b][plane][r+off][ci]
+// Out-of-range rows are TMA zero-fill (negative or >= extent); in-row wrap-around lands on zero slots.
+// ------------------------------------------------------------------------------------------------
+int conv2_tc_dispatch(int mode, int plane_class, const void* h1p, const void* w2, const float* bias, const void* dy, void* out,
+                      int B, int U, int V, int T2, int d, int split_k, cudaStream_t st) {
+    if (d % 64 != 0 || d > 2304 || B < 1 || U < 1 || V < 1 || T2 < 1) {
+        set_error("conv2: unsupported shape d=%d", d);
+        return LASR_ERR_UNSUPPORTED;
+    }
+    const long PR = (long)U * V;   // rows per parity plane
+    const long YR = (long)T2 * V;  // rows per utterance of the padded conv2 output
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.alpha = 1.f;
+    p.batch2 = 1;
+    p.split_k = 1;
+    p.vec_ok = 1;
+    p.conv_mode = mode;
+    p.conv_kbt = d / BK;
+    p.conv_d = d;
+    int ntaps = 0;
+    for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw) {
+            const int pl = (kh & 1) * 2 + (kw & 1);
+            if (mode == 2 && pl != plane_class) continue;
+            p.conv_off[ntaps] = (kh >> 1) * V + (kw >> 1);
+            p.conv_plane[ntaps] = pl;
+            p.conv_tap[ntaps] = kh * 3 + kw;
+            ++ntaps;
+        }
+    const int bn = d <= 256 ? d : 256;
+    if (d % bn != 0) {
+        set_error("conv2: d must be a multiple of the N tile");
+        return LASR_ERR_UNSUPPORTED;
+    }
+    CUtensorMap ma, mb;
+    int rc;
+    if (mode == 1) {
+        if ((rc = make_map(&ma, h1p, d, PR, d, 4, PR * d, B, 4 * PR * d, BK, BM))) return rc;
+        if ((rc = make_map(&mb, w2, 9L * d, d, 9L * d, 1, 0, 1, 0, BK, bn))) return rc;
+        p.c = out; p.bias = bias; p.c_dtype = LASR_BF16;
+        p.m = (int)YR; p.n = d; p.k = 9 * d; p.n_store = d; p.ldc = d; p.sc1 = YR * d;
+        p.act = LASR_ACT_RELU; p.epi_mode = EPI_RELU;
+        p.a_mn = 0; p.b_mn = 0;
+    } else if (mode == 2) {
+        if ((rc = make_map(&ma, dy, d, YR, d, 1, 0, B, YR * d, BK, BM))) return rc;
+        if ((rc = make_map(&mb, w2, 9L * d, d, 9L * d, 1, 0, 1, 0, 64, BK))) return rc;
+        p.c = reinterpret_cast<bf16*>(out) + (long)plane_class * PR * d;
+        p.dact = reinterpret_cast<const bf16*>(h1p) + (long)plane_class * PR * d;
+        p.lddact = d; p.c_dtype = LASR_BF16;
+        p.m = (int)PR; p.n = d; p.k = ntaps * d; p.n_store = d; p.ldc = d; p.sc1 = 4 * PR * d;
+        p.act = LASR_ACT_RELU; p.epi_mode = EPI_DRELU;
+        p.a_mn = 0; p.b_mn = 1;
+    } else if (mode == 3) {
+        if ((rc = make_map(&ma, dy, d, YR, d, 1, 0, B, YR * d, 64, BK))) return rc;
+        if ((rc = make_map(&mb, h1p, d, PR, d, 4, PR * d, B, 4 * PR * d, 64, BK))) return rc;
+        p.c = out; p.c_dtype = LASR_F32;
+        p.m = d; p.n = 9 * d; p.k = (int)YR; p.n_store = 9 * d; p.ldc = 9L * d; p.sc1 = 0;
+        p.accumulate = 1; p.epi_mode = EPI_ACC; p.split_k = split_k < 1 ? 1 : split_k;
+        p.a_mn = 1; p.b_mn = 1;
+    } else {
+        set_error("conv2: bad mode");
+        return LASR_ERR_BAD_ARG;
+    }
+    p.bn = bn;
+    p.stage_bytes = A_BYTES + bn * BK * 2;
+    p.stages = SM_RING_BUDGET / p.stage_bytes;
+    if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+    p.tiles_m = ceil_div(p.m, BM);
+    p.tiles_n = ceil_div(p.n_store, bn);
+    const long units = (long)p.tiles_m * p.tiles_n * p.split_k * B;
+    if (units > 0x7fffffffL) {
+        set_error("conv2: too many work units");
+        return LASR_ERR_UNSUPPORTED;
+    }
+    p.total_units = (int)units;
     return launch_tc(ma, mb, p, st);
 }
 

@@ -141,6 +141,117 @@ __global__ void __launch_bounds__(256) col2im_relu_kernel(const TD* __restrict__
     }
 }
 
+
+// =================================================================================================
+// parity-plane variants (feed the implicit-GEMM conv2, gemm_tc.cu::conv2_tc_dispatch)
+//   h1p[b][pt*2+pf][u*V + v][c]  with t1 = 2u+pt, f1 = 2v+pf, U = ceil(T1/2), V = ceil(F1/2); slots without a (t1,f1) are ZERO.
+// =================================================================================================
+// one CTA per (b, t1 in [0, 2U)); thread = 4 channels x every (256/(d/4))-th frequency position; 8-byte stores
+template <int DUMMY>
+__global__ void __launch_bounds__(256) conv1_fwd_planes_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                               const float* __restrict__ bias, bf16* __restrict__ h1p, int T, int F,
+                                                               int T1, int F1, int U, int V, int d) {
+    extern __shared__ float xs[];  // 3 rows x F
+    const int b = blockIdx.y, t1 = blockIdx.x, pt = t1 & 1, u = t1 >> 1;
+    const int quads = d >> 2, q = threadIdx.x % quads, g = threadIdx.x / quads, ng = 256 / quads;
+    const long plane_rows = (long)U * V;
+    bf16* base = h1p + ((long)b * 4 + pt * 2) * plane_rows * d + (long)u * V * d + 4 * q;  // plane (pt, pf=0), row u
+    if (t1 >= T1) {  // pad row of the odd-time planes
+        for (int s2 = g; s2 < 2 * V; s2 += ng) {
+            const int pf = s2 & 1, v = s2 >> 1;
+            *reinterpret_cast<uint2*>(base + (long)pf * plane_rows * d + (long)v * d) = make_uint2(0u, 0u);
+        }
+        return;
+    }
+    for (int i = threadIdx.x; i < 3 * F; i += 256) xs[i] = x[((long)b * T + 2 * t1) * F + i];
+    float wk[4][9], bc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) wk[j][k] = w[(4 * q + j) * 9 + k];
+        bc[j] = bias[4 * q + j];
+    }
+    __syncthreads();
+    for (int f = g; f < 2 * V; f += ng) {  // f1 slots 0 .. 2V-1 (the last one may not exist)
+        const int pf = f & 1, v = f >> 1;
+        uint2 o = make_uint2(0u, 0u);
+        if (f < F1) {
+            float a[4] = {bc[0], bc[1], bc[2], bc[3]};
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const float xv = xs[kh * F + 2 * f + kw];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) a[j] = fmaf(wk[j][kh * 3 + kw], xv, a[j]);
+                }
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(fmaxf(a[0], 0.f), fmaxf(a[1], 0.f));
+            const __nv_bfloat162 hi = __floats2bfloat162_rn(fmaxf(a[2], 0.f), fmaxf(a[3], 0.f));
+            o.x = *reinterpret_cast<const uint32_t*>(&lo);
+            o.y = *reinterpret_cast<const uint32_t*>(&hi);
+        }
+        *reinterpret_cast<uint2*>(base + (long)pf * plane_rows * d + (long)v * d) = o;
+    }
+}
+
+// conv1 weight / bias gradient from dh1p (already ReLU-masked, pad slots zero).  Persistent CTAs walk (b, t1) rows; thread =
+// 4 channels x every ng-th frequency position (8-byte loads), 40 accumulators; CTA-level reduction, then one atomic per value.
+template <int DUMMY>
+__global__ void __launch_bounds__(256) conv1_bwd_planes_kernel(const float* __restrict__ x, const bf16* __restrict__ dh1p,
+                                                               float* __restrict__ dw, float* __restrict__ dbias, int T, int F,
+                                                               int T1, int F1, int U, int V, int d, long total_rows) {
+    extern __shared__ float sm[];  // 2 x (3 rows x F) staging, reused as the reduction buffer
+    const int quads = d >> 2, q = threadIdx.x % quads, g = threadIdx.x / quads, ng = 256 / quads;
+    const long plane_rows = (long)U * V;
+    float acc[4][10];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < 10; ++k) acc[j][k] = 0.f;
+    int buf = 0;
+    for (long r = blockIdx.x; r < total_rows; r += gridDim.x, buf ^= 1) {
+        const int b = (int)(r / T1), t1 = (int)(r % T1), pt = t1 & 1, u = t1 >> 1;
+        float* xs = sm + buf * 3 * F;
+        for (int i = threadIdx.x; i < 3 * F; i += 256) xs[i] = x[((long)b * T + 2 * t1) * F + i];
+        __syncthreads();  // staging of this row done; the other buffer may still be read by slower threads of the previous row
+        const bf16* base = dh1p + ((long)b * 4 + pt * 2) * plane_rows * d + (long)u * V * d + 4 * q;
+        for (int f = g; f < F1; f += ng) {
+            const int pf = f & 1, v = f >> 1;
+            const uint2 raw = *reinterpret_cast<const uint2*>(base + (long)pf * plane_rows * d + (long)v * d);
+            const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&raw.x), hi = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
+            const float gv[4] = {__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi)};
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const float xv = xs[kh * F + 2 * f + kw];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[j][kh * 3 + kw] = fmaf(gv[j], xv, acc[j][kh * 3 + kw]);
+                }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j][9] += gv[j];
+        }
+    }
+    __syncthreads();
+    // reduce the ng frequency groups through shared memory: red[g][c][10]
+    float* red = sm;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < 10; ++k) red[((long)g * d + 4 * q + j) * 10 + k] = acc[j][k];
+    __syncthreads();
+    for (int i = threadIdx.x; i < d * 10; i += 256) {
+        float s2 = 0.f;
+        for (int gg = 0; gg < ng; ++gg) s2 += red[(long)gg * d * 10 + i];
+        const int c = i / 10, k = i % 10;
+        if (k < 9) atomicAdd(dw + c * 9 + k, s2);
+        else atomicAdd(dbias + c, s2);
+    }
+}
+
+int conv2_tc_dispatch(int mode, int plane_class, const void* h1p, const void* w2, const float* bias, const void* dy, void* out,
+                      int B, int U, int V, int T2, int d, int split_k, cudaStream_t st);
+
 }  // namespace lasr
 
 extern "C" {
@@ -195,6 +306,59 @@ int lasr_col2im_s2_relu(const void* dcol, const void* h1, void* dh1, int dtype, 
     else if (dtype == LASR_BF16) col2im_relu_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)dcol, (const bf16*)h1, (bf16*)dh1, B, T1, F1, T2, F2, d);
     else { set_error("col2im: bad dtype"); return LASR_ERR_UNSUPPORTED; }
     return check_launch("col2im");
+}
+
+static inline bool planes_ok(int d) { return d % 64 == 0 && d >= 64 && d <= 1024 && 256 % (d / 4) == 0; }
+
+int lasr_conv1_fwd_planes(const float* x, const float* w, const float* bias, void* h1p, int B, int T, int F, int d, void* stream) {
+    LASR_REQUIRE(x && w && bias && h1p && B > 0 && T >= 7 && F >= 7 && planes_ok(d), "conv1_fwd_planes: bad args (d in {64,128,256,512,1024})");
+    const int T1 = (T - 3) / 2 + 1, F1 = (F - 3) / 2 + 1, U = (T1 + 1) / 2, V = (F1 + 1) / 2;
+    dim3 grid(2 * U, B);
+    conv1_fwd_planes_kernel<0><<<grid, 256, 3 * F * sizeof(float), (cudaStream_t)stream>>>(x, w, bias, (bf16*)h1p, T, F, T1, F1, U, V, d);
+    return check_launch("conv1_fwd_planes");
+}
+
+int lasr_conv1_bwd_planes(const float* x, const void* dh1p, float* dw, float* dbias, int B, int T, int F, int d, void* stream) {
+    LASR_REQUIRE(x && dh1p && dw && dbias && B > 0 && T >= 7 && F >= 7 && planes_ok(d), "conv1_bwd_planes: bad args");
+    const int T1 = (T - 3) / 2 + 1, F1 = (F - 3) / 2 + 1, U = (T1 + 1) / 2, V = (F1 + 1) / 2;
+    const long rows = (long)B * T1;
+    const int ng = 256 / (d / 4);
+    size_t smem = (size_t)ng * d * 10 * sizeof(float);
+    if (smem < 6 * (size_t)F * sizeof(float)) smem = 6 * (size_t)F * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(conv1_bwd_planes_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
+            return check_launch("conv1_bwd_planes smem attr");
+        configured = true;
+    }
+    LASR_REQUIRE(smem <= 100 * 1024, "conv1_bwd_planes: F too large");
+    long grid = rows < 148 * 4 ? rows : 148 * 4;
+    conv1_bwd_planes_kernel<0><<<(unsigned)grid, 256, smem, (cudaStream_t)stream>>>(x, (const bf16*)dh1p, dw, dbias, T, F, T1, F1, U, V, d, rows);
+    return check_launch("conv1_bwd_planes");
+}
+
+/* Implicit-GEMM conv2 on the parity planes (bf16 / tcgen05 only).  Shapes: T1=(T-3)/2+1, F1=(F-3)/2+1, U=ceil(T1/2), V=ceil(F1/2),
+ * T2=(T1-3)/2+1, F2=(F1-3)/2+1 = V-1.  w2k = conv.2.weight permuted to (co, kh, kw, ci) bf16. */
+int lasr_conv2_fwd(const void* h1p, const void* w2k, const float* bias, void* h2p, int B, int T, int F, int d, void* stream) {
+    LASR_REQUIRE(h1p && w2k && bias && h2p && planes_ok(d), "conv2_fwd: bad args");
+    const int T1 = (T - 3) / 2 + 1, F1 = (F - 3) / 2 + 1, U = (T1 + 1) / 2, V = (F1 + 1) / 2, T2 = (T1 - 3) / 2 + 1;
+    return conv2_tc_dispatch(1, 0, h1p, w2k, bias, nullptr, h2p, B, U, V, T2, d, 1, (cudaStream_t)stream);
+}
+
+int lasr_conv2_dgrad(const void* dy2p, const void* w2k, const void* h1p, void* dh1p, int B, int T, int F, int d, void* stream) {
+    LASR_REQUIRE(dy2p && w2k && h1p && dh1p && planes_ok(d), "conv2_dgrad: bad args");
+    const int T1 = (T - 3) / 2 + 1, F1 = (F - 3) / 2 + 1, U = (T1 + 1) / 2, V = (F1 + 1) / 2, T2 = (T1 - 3) / 2 + 1;
+    for (int pl = 0; pl < 4; ++pl) {
+        const int rc = conv2_tc_dispatch(2, pl, h1p, w2k, nullptr, dy2p, dh1p, B, U, V, T2, d, 1, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return LASR_OK;
+}
+
+int lasr_conv2_wgrad(const void* dy2p, const void* h1p, float* dw2k, int B, int T, int F, int d, void* stream) {
+    LASR_REQUIRE(dy2p && h1p && dw2k && planes_ok(d), "conv2_wgrad: bad args");
+    const int T1 = (T - 3) / 2 + 1, F1 = (F - 3) / 2 + 1, U = (T1 + 1) / 2, V = (F1 + 1) / 2, T2 = (T1 - 3) / 2 + 1;
+    return conv2_tc_dispatch(3, 0, h1p, nullptr, nullptr, dy2p, dw2k, B, U, V, T2, d, 1, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -368,6 +368,8 @@ class Engine:
 
     def embed_fwd(self, xs, pfx, d) -> NS:
         B, T, F = xs.shape
+        if self.adt == torch.bfloat16 and ops.planes_supported(d, T, F):
+            return self._embed_fwd_planes(xs, pfx, d)
         T1, F1 = (T - 3) // 2 + 1, (F - 3) // 2 + 1
         T2, F2 = (T1 - 3) // 2 + 1, (F1 - 3) // 2 + 1
         st = self.st
@@ -378,10 +380,26 @@ class Engine:
         h2 = self.linear(col, None, self.adt, w=self._conv2_weight(pfx, d), bias_t=st.p(pfx + ".conv.2.bias"), act=ACT_RELU)
         h2v = h2.view(B * T2, F2 * d)
         x0 = self.linear(h2v, None, torch.float32, w=self._out_weight(pfx, d, F2), bias_t=st.p(pfx + ".out.bias"), alpha=math.sqrt(d))
-        return NS(out=x0, xs=xs, h1=h1, col=col, h2=h2, B=B, T1=T1, F1=F1, T2=T2, F2=F2, d=d, pfx=pfx)
+        return NS(out=x0, xs=xs, h1=h1, col=col, h2=h2, B=B, T1=T1, F1=F1, T2=T2, F2=F2, d=d, pfx=pfx, planes=False)
+
+    def _embed_fwd_planes(self, xs, pfx, d) -> NS:
+        """bf16 mode: conv1 writes parity planes, conv2 runs as an implicit GEMM on them (no im2col matrix); conv2's output keeps
+        V = F2 + 1 slots per frame, the output Linear reads the first F2 of them through its row stride."""
+        B, T, F = xs.shape
+        T1, F1, U, V, T2, F2 = ops.plane_dims(T, F)
+        st = self.st
+        h1p = _empty((B, 4, U * V, d), self.adt, self.dev)
+        ops.conv1_fwd_planes(xs, st.p(pfx + ".conv.0.weight").view(d, 9), st.p(pfx + ".conv.0.bias"), h1p)
+        h2p = _empty((B * T2, V * d), self.adt, self.dev)
+        ops.conv2_fwd(h1p, self._conv2_weight(pfx, d), st.p(pfx + ".conv.2.bias"), h2p, B, T, F)
+        h2v = h2p[:, : F2 * d]
+        x0 = self.linear(h2v, None, torch.float32, w=self._out_weight(pfx, d, F2), bias_t=st.p(pfx + ".out.bias"), alpha=math.sqrt(d))
+        return NS(out=x0, xs=xs, h1p=h1p, h2p=h2p, h2v=h2v, B=B, T=T, F=F, T1=T1, F1=F1, U=U, V=V, T2=T2, F2=F2, d=d, pfx=pfx, planes=True)
 
     def embed_bwd(self, c: NS, dy) -> None:
         """dy: operand-dtype gradient wrt the front end's output (out.bias gradient already taken by the producer of dy)."""
+        if c.planes:
+            return self._embed_bwd_planes(c, dy)
         st, d, pfx = self.st, c.d, c.pfx
         B, T2, F2 = c.B, c.T2, c.F2
         s = math.sqrt(d)
@@ -401,6 +419,31 @@ class Engine:
         dh1 = _empty(c.h1.shape, self.adt, self.dev)
         ops.col2im_s2_relu(dcol, c.h1, dh1)
         ops.conv1_bwd(c.xs, dh1, st.g(pfx + ".conv.0.weight").view(d, 9), st.g(pfx + ".conv.0.bias"))
+
+    def _embed_bwd_planes(self, c: NS, dy) -> None:
+        st, d, pfx = self.st, c.d, c.pfx
+        B, T2, F2, V = c.B, c.T2, c.F2, c.V
+        s = math.sqrt(d)
+        gwo = torch.empty((d, F2 * d), dtype=torch.float32, device=self.dev)
+        ops.zero_(gwo)
+        self.wgrad(dy, c.h2v, gwo, s)
+        ops.permute4d(gwo, st.g(pfx + ".out.weight"), (d, F2, d, 1), (F2 * d, d, 1, 0), (F2 * d, 1, F2, 0), accumulate=True)
+        # dh2 = s * (dy @ W_out) * relu'(h2) into the padded (B*T2, V*d) layout, conv.2.bias gradient as the epilogue's column sums
+        dh2p = _empty((B * T2, V * d), self.adt, self.dev)
+        dh2p.view(B * T2, V, d)[:, F2:, :].zero_()  # the padding slot of every frame must be zero for the implicit GEMMs
+        wo = self._out_weight(pfx, d, F2)
+        csum = torch.empty((F2 * d,), dtype=torch.float32, device=self.dev)
+        ops.zero_(csum)
+        ops.gemm(dy, wo, dh2p, B * T2, F2 * d, d, lda=dy.stride(0), ldb=wo.stride(0), ldc=V * d, tb=True, alpha=s, dact=c.h2v,
+                 act=ACT_RELU, colsum=csum)
+        st.g(pfx + ".conv.2.bias").add_(csum.view(F2, d).sum(0))
+        gw2 = torch.empty((d, 9 * d), dtype=torch.float32, device=self.dev)
+        ops.zero_(gw2)
+        ops.conv2_wgrad(dh2p, c.h1p, gw2, B, c.T, c.F)
+        ops.permute4d(gw2, st.g(pfx + ".conv.2.weight"), (d, 3, 3, d), (9 * d, 3 * d, d, 1), (9 * d, 3, 1, 9), accumulate=True)
+        dh1p = _empty(c.h1p.shape, self.adt, self.dev)
+        ops.conv2_dgrad(dh2p, self._conv2_weight(pfx, d), c.h1p, dh1p, B, c.T, c.F)
+        ops.conv1_bwd_planes(c.xs, dh1p, st.g(pfx + ".conv.0.weight").view(d, 9), st.g(pfx + ".conv.0.bias"))
 
     # ------------------------------------------------------------------------------------------
     # encoder (nets/transformer_encoder.py:107-127; use_rel=True, arch=conformer, activation=swish)

@@ -278,6 +278,51 @@ def col2im_s2_relu(dcol, h1, dh1):
                                               _stream()), "col2im")
 
 
+def plane_dims(T: int, F: int):
+    """(T1, F1, U, V, T2, F2) of the parity-plane sub-sampling front end (include/lasr.h)."""
+    T1, F1 = (T - 3) // 2 + 1, (F - 3) // 2 + 1
+    return T1, F1, (T1 + 1) // 2, (F1 + 1) // 2, (T1 - 3) // 2 + 1, (F1 - 3) // 2 + 1
+
+
+def planes_supported(d: int, T: int, F: int) -> bool:
+    return d % 64 == 0 and 64 <= d <= 1024 and 256 % (d // 4) == 0 and T >= 7 and F >= 7
+
+
+def conv1_fwd_planes(x, w, bias, h1p):
+    B, T, F = x.shape
+    _require_cuda(x, w, bias, h1p)
+    _lib.check(_lib.lib().lasr_conv1_fwd_planes(_ptr(x), _ptr(w), _ptr(bias), _ptr(h1p), _i(B), _i(T), _i(F), _i(h1p.shape[-1]), _stream()),
+               "conv1_fwd_planes")
+
+
+def conv1_bwd_planes(x, dh1p, dw, dbias):
+    B, T, F = x.shape
+    _require_cuda(x, dh1p, dw, dbias)
+    _lib.check(_lib.lib().lasr_conv1_bwd_planes(_ptr(x), _ptr(dh1p), _ptr(dw), _ptr(dbias), _i(B), _i(T), _i(F), _i(dh1p.shape[-1]),
+                                                _stream()), "conv1_bwd_planes")
+
+
+def conv2_fwd(h1p, w2k, bias, h2p, B, T, F):
+    _require_cuda(h1p, w2k, bias, h2p)
+    assert h1p.dtype == torch.bfloat16 and w2k.dtype == torch.bfloat16 and h2p.dtype == torch.bfloat16 and bias.dtype == torch.float32
+    _lib.check(_lib.lib().lasr_conv2_fwd(_ptr(h1p), _ptr(w2k), _ptr(bias), _ptr(h2p), _i(B), _i(T), _i(F), _i(h1p.shape[-1]), _stream()),
+               "conv2_fwd")
+
+
+def conv2_dgrad(dy2p, w2k, h1p, dh1p, B, T, F):
+    _require_cuda(dy2p, w2k, h1p, dh1p)
+    assert dy2p.dtype == torch.bfloat16 and dh1p.dtype == torch.bfloat16
+    _lib.check(_lib.lib().lasr_conv2_dgrad(_ptr(dy2p), _ptr(w2k), _ptr(h1p), _ptr(dh1p), _i(B), _i(T), _i(F), _i(h1p.shape[-1]), _stream()),
+               "conv2_dgrad")
+
+
+def conv2_wgrad(dy2p, h1p, dw2k, B, T, F):
+    _require_cuda(dy2p, h1p, dw2k)
+    assert dy2p.dtype == torch.bfloat16 and dw2k.dtype == torch.float32
+    _lib.check(_lib.lib().lasr_conv2_wgrad(_ptr(dy2p), _ptr(h1p), _ptr(dw2k), _i(B), _i(T), _i(F), _i(h1p.shape[-1]), _stream()),
+               "conv2_wgrad")
+
+
 def attn_softmax_fwd(ac, bd, probs, lens, mask_mode, causal, scale, Tk):
     B, H, Tq, ld = ac.shape
     _lib.check(_lib.lib().lasr_attn_softmax_fwd(_ptr(ac), _ptr(bd), _ptr(probs), _i(dtype_code(probs)), _ptr(lens), _i(mask_mode),
