@@ -152,25 +152,40 @@ def gemm_family_replay(step_fn, batch, reps: int = 5):
     from liteasr_b200 import ops
     rec = []
     orig = ops.gemm
+    conv_names = ("conv2_fwd", "conv2_dgrad", "conv2_wgrad")  # the implicit-GEMM convolutions run on the same kernel
+    conv_orig = {n: getattr(ops, n) for n in conv_names}
 
     def recording(a, b, c, m, n, k, **kw):
-        rec.append((a, b, c, m, n, k, kw))
+        bt = kw.get("batch", (1, 1))
+        rec.append((orig, (a, b, c, m, n, k), kw, 2.0 * m * n * k * bt[0] * bt[1]))
         orig(a, b, c, m, n, k, **kw)
 
+    def conv_recorder(name):
+        fn = conv_orig[name]
+
+        def wrapped(*args):
+            B, T, F = args[-3:]
+            d = {"conv2_fwd": args[0], "conv2_dgrad": args[2], "conv2_wgrad": args[1]}[name].shape[-1]  # the h1p operand
+            _, _, _, _, T2, F2 = ops.plane_dims(T, F)
+            rec.append((fn, args, {}, 2.0 * B * T2 * F2 * d * 9 * d))
+            fn(*args)
+        return wrapped
+
     ops.gemm = recording
+    for n in conv_names:
+        setattr(ops, n, conv_recorder(n))
     try:
         step_fn.step_eager(*batch)
         torch.cuda.synchronize()
     finally:
         ops.gemm = orig
-    flops = 0.0
-    for a, b, c, m, n, k, kw in rec:
-        bt = kw.get("batch", (1, 1))
-        flops += 2.0 * m * n * k * bt[0] * bt[1]
+        for n in conv_names:
+            setattr(ops, n, conv_orig[n])
+    flops = sum(r[3] for r in rec)
 
     def replay():
-        for a, b, c, m, n, k, kw in rec:
-            orig(a, b, c, m, n, k, **kw)
+        for fn, args, kw, _ in rec:
+            fn(*args, **kw)
 
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())

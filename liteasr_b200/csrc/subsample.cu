@@ -146,61 +146,68 @@ __global__ void __launch_bounds__(256) col2im_relu_kernel(const TD* __restrict__
 // parity-plane variants (feed the implicit-GEMM conv2, gemm_tc.cu::conv2_tc_dispatch)
 //   h1p[b][pt*2+pf][u*V + v][c]  with t1 = 2u+pt, f1 = 2v+pf, U = ceil(T1/2), V = ceil(F1/2); slots without a (t1,f1) are ZERO.
 // =================================================================================================
-// one CTA per (b, t1 in [0, 2U)); thread = 4 channels x every (256/(d/4))-th frequency position; 8-byte stores
+// CTA = PR_ROWS consecutive t1 rows of one utterance (t1 in [0, 2U)); the 2*PR_ROWS+1 input rows and the transposed conv1
+// weights are staged in shared memory once; thread = 4 channels x every ng-th (row, frequency slot) task; 8-byte stores.
+constexpr int PR_ROWS = 8;
 template <int DUMMY>
 __global__ void __launch_bounds__(256) conv1_fwd_planes_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                const float* __restrict__ bias, bf16* __restrict__ h1p, int T, int F,
                                                                int T1, int F1, int U, int V, int d) {
-    extern __shared__ float xs[];  // 3 rows x F
-    const int b = blockIdx.y, t1 = blockIdx.x, pt = t1 & 1, u = t1 >> 1;
+    extern __shared__ __align__(16) float smf[];
+    float* ws = smf;                  // [9][d] (tap-major: a thread reads its 4 channels as one float4)
+    float* xs = smf + 9 * d;          // (2 * PR_ROWS + 1) rows x F
+    const int b = blockIdx.y, t10 = blockIdx.x * PR_ROWS;
     const int quads = d >> 2, q = threadIdx.x % quads, g = threadIdx.x / quads, ng = 256 / quads;
     const long plane_rows = (long)U * V;
-    bf16* base = h1p + ((long)b * 4 + pt * 2) * plane_rows * d + (long)u * V * d + 4 * q;  // plane (pt, pf=0), row u
-    if (t1 >= T1) {  // pad row of the odd-time planes
-        for (int s2 = g; s2 < 2 * V; s2 += ng) {
-            const int pf = s2 & 1, v = s2 >> 1;
-            *reinterpret_cast<uint2*>(base + (long)pf * plane_rows * d + (long)v * d) = make_uint2(0u, 0u);
-        }
-        return;
-    }
-    for (int i = threadIdx.x; i < 3 * F; i += 256) xs[i] = x[((long)b * T + 2 * t1) * F + i];
-    float wk[4][9], bc[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-#pragma unroll
-        for (int k = 0; k < 9; ++k) wk[j][k] = w[(4 * q + j) * 9 + k];
-        bc[j] = bias[4 * q + j];
+    for (int i = threadIdx.x; i < 9 * d; i += 256) ws[(i % 9) * d + i / 9] = w[i];
+    const int xrows = 2 * PR_ROWS + 1;
+    for (int i = threadIdx.x; i < xrows * F; i += 256) {
+        const int tr = 2 * t10 + i / F;
+        xs[i] = tr < T ? x[((long)b * T + tr) * F + i % F] : 0.f;
     }
     __syncthreads();
-    for (int f = g; f < 2 * V; f += ng) {  // f1 slots 0 .. 2V-1 (the last one may not exist)
-        const int pf = f & 1, v = f >> 1;
-        uint2 o = make_uint2(0u, 0u);
-        if (f < F1) {
-            float a[4] = {bc[0], bc[1], bc[2], bc[3]};
+    float4 wk[9];
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh)
+    for (int k = 0; k < 9; ++k) wk[k] = *reinterpret_cast<const float4*>(ws + k * d + 4 * q);
+    const float4 bc = *reinterpret_cast<const float4*>(bias + 4 * q);
+    bf16* hb = h1p + (long)b * 4 * plane_rows * d + 4 * q;
+    for (int i = 0; i < PR_ROWS; ++i) {
+        const int t1 = t10 + i;
+        if (t1 >= 2 * U) break;
+        const bool row_ok = t1 < T1;
+        bf16* rowp = hb + ((long)((t1 & 1) * 2) * plane_rows + (long)(t1 >> 1) * V) * d;  // plane (pt, pf = 0), row u
+        const float* xrow = xs + (2 * i) * F;
+        for (int f = g; f < 2 * V; f += ng) {  // f1 slots 0 .. 2V-1 (the last one may not exist)
+            uint2 o = make_uint2(0u, 0u);
+            if (row_ok && f < F1) {
+                float4 a = bc;
+                const float* xr = xrow + 2 * f;
 #pragma unroll
-                for (int kw = 0; kw < 3; ++kw) {
-                    const float xv = xs[kh * F + 2 * f + kw];
+                for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) a[j] = fmaf(wk[j][kh * 3 + kw], xv, a[j]);
-                }
-            const __nv_bfloat162 lo = __floats2bfloat162_rn(fmaxf(a[0], 0.f), fmaxf(a[1], 0.f));
-            const __nv_bfloat162 hi = __floats2bfloat162_rn(fmaxf(a[2], 0.f), fmaxf(a[3], 0.f));
-            o.x = *reinterpret_cast<const uint32_t*>(&lo);
-            o.y = *reinterpret_cast<const uint32_t*>(&hi);
+                    for (int kw = 0; kw < 3; ++kw) {
+                        const float xv = xr[kh * F + kw];
+                        const float4 ww = wk[kh * 3 + kw];
+                        a.x = fmaf(ww.x, xv, a.x); a.y = fmaf(ww.y, xv, a.y); a.z = fmaf(ww.z, xv, a.z); a.w = fmaf(ww.w, xv, a.w);
+                    }
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f));
+                const __nv_bfloat162 hi = __floats2bfloat162_rn(fmaxf(a.z, 0.f), fmaxf(a.w, 0.f));
+                o.x = *reinterpret_cast<const uint32_t*>(&lo);
+                o.y = *reinterpret_cast<const uint32_t*>(&hi);
+            }
+            *reinterpret_cast<uint2*>(rowp + ((long)(f & 1) * plane_rows + (f >> 1)) * d) = o;
         }
-        *reinterpret_cast<uint2*>(base + (long)pf * plane_rows * d + (long)v * d) = o;
     }
 }
 
-// conv1 weight / bias gradient from dh1p (already ReLU-masked, pad slots zero).  Persistent CTAs walk (b, t1) rows; thread =
-// 4 channels x every ng-th frequency position (8-byte loads), 40 accumulators; CTA-level reduction, then one atomic per value.
+// conv1 weight / bias gradient from dh1p (already ReLU-masked).  Persistent CTAs walk chunks of PR_ROWS t1 rows of one
+// utterance; thread = 4 channels x every ng-th (row, frequency) task with the loads of 4 tasks in flight; 40 accumulators;
+// CTA-level reduction through shared memory, then one atomic per value.
 template <int DUMMY>
-__global__ void __launch_bounds__(256) conv1_bwd_planes_kernel(const float* __restrict__ x, const bf16* __restrict__ dh1p,
+__global__ void __launch_bounds__(256, 3) conv1_bwd_planes_kernel(const float* __restrict__ x, const bf16* __restrict__ dh1p,
                                                                float* __restrict__ dw, float* __restrict__ dbias, int T, int F,
-                                                               int T1, int F1, int U, int V, int d, long total_rows) {
-    extern __shared__ float sm[];  // 2 x (3 rows x F) staging, reused as the reduction buffer
+                                                               int T1, int F1, int U, int V, int d, int chunks_per_utt, long total_chunks) {
+    extern __shared__ __align__(16) float sm[];  // (2 * PR_ROWS + 1) x F staging, reused as the reduction buffer
     const int quads = d >> 2, q = threadIdx.x % quads, g = threadIdx.x / quads, ng = 256 / quads;
     const long plane_rows = (long)U * V;
     float acc[4][10];
@@ -208,32 +215,49 @@ __global__ void __launch_bounds__(256) conv1_bwd_planes_kernel(const float* __re
     for (int j = 0; j < 4; ++j)
 #pragma unroll
         for (int k = 0; k < 10; ++k) acc[j][k] = 0.f;
-    int buf = 0;
-    for (long r = blockIdx.x; r < total_rows; r += gridDim.x, buf ^= 1) {
-        const int b = (int)(r / T1), t1 = (int)(r % T1), pt = t1 & 1, u = t1 >> 1;
-        float* xs = sm + buf * 3 * F;
-        for (int i = threadIdx.x; i < 3 * F; i += 256) xs[i] = x[((long)b * T + 2 * t1) * F + i];
-        __syncthreads();  // staging of this row done; the other buffer may still be read by slower threads of the previous row
-        const bf16* base = dh1p + ((long)b * 4 + pt * 2) * plane_rows * d + (long)u * V * d + 4 * q;
-        for (int f = g; f < F1; f += ng) {
-            const int pf = f & 1, v = f >> 1;
-            const uint2 raw = *reinterpret_cast<const uint2*>(base + (long)pf * plane_rows * d + (long)v * d);
-            const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&raw.x), hi = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
-            const float gv[4] = {__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi)};
+    const int xrows = 2 * PR_ROWS + 1;
+    for (long ch = blockIdx.x; ch < total_chunks; ch += gridDim.x) {
+        const int b = (int)(ch / chunks_per_utt), t10 = (int)(ch % chunks_per_utt) * PR_ROWS;
+        __syncthreads();  // the previous chunk's readers are done with the staging buffer
+        for (int i = threadIdx.x; i < xrows * F; i += 256) {
+            const int tr = 2 * t10 + i / F;
+            sm[i] = tr < T ? x[((long)b * T + tr) * F + i % F] : 0.f;
+        }
+        __syncthreads();
+        const int nrow = min(PR_ROWS, T1 - t10);
+        const bf16* hb = dh1p + (long)b * 4 * plane_rows * d + 4 * q;
+        for (int i = 0; i < nrow; ++i) {
+            const int t1 = t10 + i;
+            const bf16* rowp = hb + ((long)((t1 & 1) * 2) * plane_rows + (long)(t1 >> 1) * V) * d;
+            const float* xrow = sm + (2 * i) * F;
+            for (int f0 = g; f0 < F1; f0 += 2 * ng) {  // two positions per trip: both loads are issued before the math
+                const int f1b = f0 + ng;
+                const bool two = f1b < F1;
+                const uint2 raw0 = *reinterpret_cast<const uint2*>(rowp + ((long)(f0 & 1) * plane_rows + (f0 >> 1)) * d);
+                uint2 raw1 = make_uint2(0u, 0u);
+                if (two) raw1 = *reinterpret_cast<const uint2*>(rowp + ((long)(f1b & 1) * plane_rows + (f1b >> 1)) * d);
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh)
+                for (int e = 0; e < 2; ++e) {
+                    const uint2 raw = e ? raw1 : raw0;
+                    const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&raw.x), hi = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
+                    const float gv[4] = {__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi)};
+                    const float* xr = xrow + 2 * (e ? (two ? f1b : f0) : f0);
 #pragma unroll
-                for (int kw = 0; kw < 3; ++kw) {
-                    const float xv = xs[kh * F + 2 * f + kw];
+                    for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[j][kh * 3 + kw] = fmaf(gv[j], xv, acc[j][kh * 3 + kw]);
+                        for (int kw = 0; kw < 3; ++kw) {
+                            const float xv = xr[kh * F + kw];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) acc[j][kh * 3 + kw] = fmaf(gv[j], xv, acc[j][kh * 3 + kw]);
+                        }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[j][9] += gv[j];
                 }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[j][9] += gv[j];
+            }
         }
     }
     __syncthreads();
-    // reduce the ng frequency groups through shared memory: red[g][c][10]
+    // reduce the ng task groups through shared memory: red[g][c][10]
     float* red = sm;
 #pragma unroll
     for (int j = 0; j < 4; ++j)
@@ -313,18 +337,22 @@ static inline bool planes_ok(int d) { return d % 64 == 0 && d >= 64 && d <= 1024
 int lasr_conv1_fwd_planes(const float* x, const float* w, const float* bias, void* h1p, int B, int T, int F, int d, void* stream) {
     LASR_REQUIRE(x && w && bias && h1p && B > 0 && T >= 7 && F >= 7 && planes_ok(d), "conv1_fwd_planes: bad args (d in {64,128,256,512,1024})");
     const int T1 = (T - 3) / 2 + 1, F1 = (F - 3) / 2 + 1, U = (T1 + 1) / 2, V = (F1 + 1) / 2;
-    dim3 grid(2 * U, B);
-    conv1_fwd_planes_kernel<0><<<grid, 256, 3 * F * sizeof(float), (cudaStream_t)stream>>>(x, w, bias, (bf16*)h1p, T, F, T1, F1, U, V, d);
+    dim3 grid(ceil_div(2 * U, PR_ROWS), B);
+    const size_t smem = (9 * (size_t)d + (2 * PR_ROWS + 1) * (size_t)F) * sizeof(float);
+    LASR_REQUIRE(smem <= 48 * 1024, "conv1_fwd_planes: F too large");
+    conv1_fwd_planes_kernel<0><<<grid, 256, smem, (cudaStream_t)stream>>>(x, w, bias, (bf16*)h1p, T, F, T1, F1, U, V, d);
     return check_launch("conv1_fwd_planes");
 }
 
 int lasr_conv1_bwd_planes(const float* x, const void* dh1p, float* dw, float* dbias, int B, int T, int F, int d, void* stream) {
     LASR_REQUIRE(x && dh1p && dw && dbias && B > 0 && T >= 7 && F >= 7 && planes_ok(d), "conv1_bwd_planes: bad args");
     const int T1 = (T - 3) / 2 + 1, F1 = (F - 3) / 2 + 1, U = (T1 + 1) / 2, V = (F1 + 1) / 2;
-    const long rows = (long)B * T1;
+    const int cpu = ceil_div(T1, PR_ROWS);
+    const long chunks = (long)B * cpu;
     const int ng = 256 / (d / 4);
     size_t smem = (size_t)ng * d * 10 * sizeof(float);
-    if (smem < 6 * (size_t)F * sizeof(float)) smem = 6 * (size_t)F * sizeof(float);
+    const size_t stage = (2 * PR_ROWS + 1) * (size_t)F * sizeof(float);
+    if (smem < stage) smem = stage;
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(conv1_bwd_planes_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
@@ -332,8 +360,9 @@ int lasr_conv1_bwd_planes(const float* x, const void* dh1p, float* dw, float* db
         configured = true;
     }
     LASR_REQUIRE(smem <= 100 * 1024, "conv1_bwd_planes: F too large");
-    long grid = rows < 148 * 4 ? rows : 148 * 4;
-    conv1_bwd_planes_kernel<0><<<(unsigned)grid, 256, smem, (cudaStream_t)stream>>>(x, (const bf16*)dh1p, dw, dbias, T, F, T1, F1, U, V, d, rows);
+    long grid = chunks < 148 * 3 ? chunks : 148 * 3;
+    conv1_bwd_planes_kernel<0><<<(unsigned)grid, 256, smem, (cudaStream_t)stream>>>(x, (const bf16*)dh1p, dw, dbias, T, F, T1, F1, U, V, d, cpu,
+                                                                                  chunks);
     return check_launch("conv1_bwd_planes");
 }
 
