@@ -48,6 +48,10 @@ template <> struct Vec4<bf16> {
     }
 };
 
+
+__device__ __forceinline__ void red_sub(float* p, float v) { atomicAdd(p, -v); }
+__device__ __forceinline__ void red_sub(bf16* p, float v) { atomicAdd(p, __float2bfloat16_rn(-v)); }
+
 struct CtcDenseParams {
     const void* logits;
     void* grad;
@@ -59,6 +63,10 @@ struct CtcDenseParams {
     int T, B, V, lmax, blank;
     float grad_scale;
     const float* upstream;
+    // two-pass pipeline (see ctc_launch): utterance group [b0, b0 + nb), per-row log-sum-exp, lattice occupancies
+    int b0, nb;
+    float* lse;            // (T, B) natural-log units
+    const float2* occ;     // (B, T, lmax+1): (blank, label) state occupancies written by the lattice
 };
 
 // GROUP threads cooperate on one row; each holds NI chunks of 4 consecutive classes in registers.
@@ -165,6 +173,155 @@ __global__ void __launch_bounds__(256) ctc_softmax_gather_kernel(const CtcDenseP
                     if (c + j < p.V) gout[c + j] = from_f32<T>(0.f);
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// two-pass pipeline kernels.  PASS 1: per row log-sum-exp + compact lattice inputs, no gradient write.
+// PASS 3: grad = s * (exp(x - lse) - occupancy), the occupancy of the row's L+1 classes subtracted with red.add right
+// after the row is written (the sectors are still in L2: no DRAM read-modify-write, unlike a separate scatter pass).
+// Rows are (t, b) with b in the utterance group [b0, b0 + nb).
+// ---------------------------------------------------------------------------------------------
+template <typename T, int GROUP, int NI, int PASS>
+__global__ void __launch_bounds__(256) ctc_pass_kernel(const CtcDenseParams p) {
+    constexpr int ROWS = 256 / GROUP;
+    __shared__ float red[ROWS][8];
+    const int g = threadIdx.x / GROUP, gl = threadIdx.x % GROUP;
+    const long row = (long)blockIdx.x * ROWS + g;
+    const bool row_ok = row < (long)p.T * p.nb;
+    const int t = row_ok ? (int)(row / p.nb) : 0, b = p.b0 + (row_ok ? (int)(row % p.nb) : 0);
+    const int Tb = (int)p.in_len[b];
+    const bool live = row_ok && t < Tb;
+    const T* x = reinterpret_cast<const T*>(p.logits) + (long)t * p.st + (long)b * p.sb;
+    typedef typename Vec4<T>::type V4;
+    float v[NI][4];
+    if (live) {
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            const int c = (i * GROUP + gl) * 4;
+            if (c + 3 < p.V) {
+                const V4 raw = *reinterpret_cast<const V4*>(x + c);
+                Vec4<T>::unpack(raw, v[i]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[i][j] = (c + j < p.V) ? to_f32<T>(x[c + j]) : -INFINITY;
+            }
+        }
+    }
+    if (PASS == 1) {
+        float mx = -INFINITY;
+        if (live) {
+#pragma unroll
+            for (int i = 0; i < NI; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) mx = fmaxf(mx, v[i][j]);
+        }
+        mx = warp_max(mx);
+        if (GROUP != 32) {
+            if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = mx;
+            __syncthreads();
+            mx = red[0][0];
+#pragma unroll
+            for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[0][w]);
+            __syncthreads();
+        }
+        float sum = 0.f;
+        if (live) {
+#pragma unroll
+            for (int i = 0; i < NI; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sum += expf(v[i][j] - mx);  // exp(-inf) = 0 for the padded tail
+        }
+        sum = warp_sum(sum);
+        if (GROUP != 32) {
+            if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = sum;
+            __syncthreads();
+            sum = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) sum += red[0][w];
+        }
+        if (!live) return;
+        const float lse = mx + logf(sum);
+        if (gl == 0) p.lse[(long)t * p.B + b] = lse;
+        const int L = (int)p.tgt_len[b];
+        float* le = p.lp_ext + ((long)b * p.T + t) * (p.lmax + 1);
+        const int64_t* tg = p.targets + (long)b * p.lmax;
+        const float xb = to_f32<T>(x[p.blank]);
+        for (int k2 = gl; k2 <= L; k2 += GROUP)  // log2 units: the lattice runs on ex2 / lg2 directly
+            le[k2] = LOG2E * ((k2 == 0) ? (xb - lse) : (to_f32<T>(x[(int)tg[k2 - 1]]) - xb));
+    } else {
+        T* gout = reinterpret_cast<T*>(p.grad) + (long)t * p.gst + (long)b * p.gsb;
+        float s = p.grad_scale;
+        if (p.upstream) s *= __ldg(p.upstream);
+        float bsum = 0.f;
+        const int L = live ? min((int)p.tgt_len[b], p.lmax) : 0;
+        const float2* oc = p.occ + ((long)b * p.T + t) * (p.lmax + 1);
+        float2 myocc[(GROUP == 32) ? 8 : 4];  // this thread's share of the row's L+1 occupancies (lmax + 1 <= 1024 = 256 * 4)
+        if (live) {
+            const float lse = p.lse[(long)t * p.B + b];
+#pragma unroll
+            for (int e = 0; e < ((GROUP == 32) ? 8 : 4); ++e) {
+                const int k = gl + e * GROUP;
+                myocc[e] = (k <= L) ? __ldcg(oc + k) : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < NI; ++i) {
+                const int c = (i * GROUP + gl) * 4;
+                float o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[j] = s * expf(v[i][j] - lse);
+                if (c + 3 < p.V) {
+                    *reinterpret_cast<V4*>(gout + c) = Vec4<T>::pack(o);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (c + j < p.V) gout[c + j] = from_f32<T>(o[j]);
+                }
+            }
+        } else if (row_ok) {
+            float z[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < NI; ++i) {
+                const int c = (i * GROUP + gl) * 4;
+                if (c + 3 < p.V) {
+                    *reinterpret_cast<V4*>(gout + c) = Vec4<T>::pack(z);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (c + j < p.V) gout[c + j] = from_f32<T>(0.f);
+                }
+            }
+        }
+        __syncthreads();  // the row's plain stores are ordered before the red.adds of other threads of the CTA
+        if (live) {
+            const int64_t* tg = p.targets + (long)b * p.lmax;
+            // GROUP == 32 with lmax + 1 > 256 cannot hold the row's occupancies in 8 registers per lane: loop instead
+            if (GROUP == 32 && p.lmax + 1 > 256) {
+                for (int k = gl; k <= L; k += 32) {
+                    const float2 o = __ldcg(oc + k);
+                    bsum += o.x;
+                    if (k < L) red_sub(gout + (int)tg[k], s * o.y);
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < ((GROUP == 32) ? 8 : 4); ++e) {
+                    const int k = gl + e * GROUP;
+                    if (k <= L) {
+                        bsum += myocc[e].x;
+                        if (k < L) red_sub(gout + (int)tg[k], s * myocc[e].y);
+                    }
+                }
+            }
+        }
+        bsum = warp_sum(bsum);
+        if (GROUP != 32) {
+            if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = bsum;
+            __syncthreads();
+            bsum = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) bsum += red[0][w];
+        }
+        if (live && gl == 0) red_sub(gout + p.blank, s * bsum);
     }
 }
 
@@ -430,10 +587,8 @@ __global__ void __launch_bounds__(32 * NW) ctc_lattice_warp_kernel(const float* 
 // latency-bound recursion leaves idle.  CTA pairs are adjacent in launch order, so a waiting CTA's partner is always resident
 // or next in line; the wait traps after LASR_DEVICE_TIMEOUT_CYCLES instead of hanging.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void red_sub(float* p, float v) { atomicAdd(p, -v); }
-__device__ __forceinline__ void red_sub(bf16* p, float v) { atomicAdd(p, __float2bfloat16_rn(-v)); }
 
-template <typename GT, int R, int PFW, int NW>
+template <typename GT, int R, int PFW, int NW, bool OCC>
 struct MeetLattice {
     const float* lpb;
     float2* own;
@@ -447,6 +602,7 @@ struct MeetLattice {
     bool v_bl[R], v_lb[R], skip[R];
     float s_bl[R], s_lb[R];
     float (*edge)[2][NW];
+    float2* occ;  // OCC: occupancies (blank, label) of row t replace alpha_t in the alpha array (read by the final gradient pass)
 
     __device__ __forceinline__ void scatter(int t, const float2 (&pp)[R], const float (&e)[R]) {
         GT* g = gb + (long)t * gst;
@@ -457,11 +613,17 @@ struct MeetLattice {
             float o_bl = fex2(s_bl[r] + pp[r].x - tot);
             float o_lb = fex2(s_lb[r] + pp[r].y - e[r] - tot);
             if (!feasible) { o_bl = qnan; o_lb = qnan; }
-            if (v_lb[r]) red_sub(g + cls[r], s * o_lb);
-            bsum += v_bl[r] ? o_bl : 0.f;
+            if (OCC) {
+                if (tid * R + r < W) occ[(long)t * W + tid * R + r] = make_float2(v_bl[r] ? o_bl : 0.f, v_lb[r] ? o_lb : 0.f);
+            } else {
+                if (v_lb[r]) red_sub(g + cls[r], s * o_lb);
+                bsum += v_bl[r] ? o_bl : 0.f;
+            }
         }
-        bsum = warp_sum(bsum);
-        if (lane == 0) red_sub(g + blank, s * bsum);
+        if (!OCC) {
+            bsum = warp_sum(bsum);
+            if (lane == 0) red_sub(g + blank, s * bsum);
+        }
     }
 
     // n recursion steps starting at row t_first in sweep direction; PH2: also scatter every row (partner rows prefetched)
@@ -526,9 +688,11 @@ struct MeetLattice {
 #pragma unroll
                         for (int r = 0; r < R; ++r) { s_bl[r] = n_bl[r]; s_lb[r] = v_lb[r] ? n_lb[r] : NEG; }
                     }
+                    if (!(PH2 && OCC)) {  // past the meeting nobody reads this sweep's values from memory
 #pragma unroll
-                    for (int r = 0; r < R; ++r)
-                        if (tid * R + r < W) own[(long)t * W + tid * R + r] = make_float2(s_bl[r], s_lb[r]);
+                        for (int r = 0; r < R; ++r)
+                            if (tid * R + r < W) own[(long)t * W + tid * R + r] = make_float2(s_bl[r], s_lb[r]);
+                    }
                     if (NW > 1) {
                         if (!BETA) {
                             if (lane == 31) edge[t & 1][0][warp] = s_lb[R - 1];
@@ -552,17 +716,17 @@ struct MeetLattice {
     }
 };
 
-template <typename GT, int R, int PFW, int NW>
+template <typename GT, int R, int PFW, int NW, bool OCC>
 __global__ void __launch_bounds__(32 * NW) ctc_lattice_meet_kernel(const float* __restrict__ lp_ext, float2* al, float2* be,
                                                                    const int64_t* __restrict__ targets,
                                                                    const int64_t* __restrict__ in_len,
                                                                    const int64_t* __restrict__ tgt_len, float* __restrict__ nll,
                                                                    float* __restrict__ tot_out, int* flags, void* grad, long gst,
                                                                    long gsb, int blank, float grad_scale, const float* upstream,
-                                                                   int T, int lmax) {
+                                                                   int T, int lmax, int b0) {
     __shared__ float edge[2][2][NW];
     __shared__ float scratch[32];
-    const int b = blockIdx.x >> 1, tid = threadIdx.x;
+    const int b = b0 + (blockIdx.x >> 1), tid = threadIdx.x;
     const bool is_beta = (blockIdx.x & 1) != 0;
     const int Tb = min((int)in_len[b], T), L = min((int)tgt_len[b], lmax);
     const int W = lmax + 1;
@@ -572,7 +736,7 @@ __global__ void __launch_bounds__(32 * NW) ctc_lattice_meet_kernel(const float* 
     }
     const int64_t* tg = targets + (long)b * lmax;
     const float NEG = LNEG;
-    MeetLattice<GT, R, PFW, NW> lt;
+    MeetLattice<GT, R, PFW, NW, OCC> lt;
     lt.lpb = lp_ext + (long)b * T * W;
     lt.own = (is_beta ? be : al) + (long)b * T * W;
     lt.partner = (is_beta ? al : be) + (long)b * T * W;
@@ -581,6 +745,7 @@ __global__ void __launch_bounds__(32 * NW) ctc_lattice_meet_kernel(const float* 
     lt.W = W; lt.tid = tid; lt.lane = tid & 31; lt.warp = tid >> 5; lt.blank = blank;
     lt.s = grad_scale * (upstream ? __ldg(upstream) : 1.f);
     lt.edge = edge;
+    lt.occ = al + (long)b * T * W;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int k = tid * R + r;
@@ -671,9 +836,11 @@ __global__ void __launch_bounds__(32 * NW) ctc_lattice_meet_kernel(const float* 
             nll[b] = lt.feasible ? (float)(-((double)lt.tot + csum) * LN2) : INFINITY;
             tot_out[b] = lt.feasible ? lt.tot : -INFINITY;
         }
-        lt.scatter(m, pm, em);                                  // row m
+        if (!OCC) lt.scatter(m, pm, em);                        // row m (RED mode)
         lt.template run<false, true>(m + 1, Tb - 1 - m);       // rows m+1 .. Tb-1
     } else {
+        // OCC mode: row m belongs to the beta CTA -- it is the only reader of alpha_m in memory, so it may overwrite it
+        if (OCC) lt.scatter(m, pm, em);
         lt.template run<true, true>(m - 1, m);                 // rows m-1 .. 0
     }
 }
@@ -722,11 +889,97 @@ __global__ void __launch_bounds__(256) ctc_scatter_ab_kernel(const float2* __res
     }
 }
 
+template <typename T, int PASS>
+static void launch_pass(const CtcDenseParams& q, cudaStream_t st) {
+    const long rows = (long)q.T * q.nb;
+    const int chunks = (q.V + 3) / 4;
+    bool done = false;
+#define LASR_CTC_CASE(GROUP, NI)                                                                  \
+    if (!done && chunks <= GROUP * NI) {                                                          \
+        ctc_pass_kernel<T, GROUP, NI, PASS><<<ceil_div(rows, 256 / GROUP), 256, 0, st>>>(q);      \
+        done = true;                                                                              \
+    }
+    LASR_CTC_CASE(32, 1) LASR_CTC_CASE(32, 2) LASR_CTC_CASE(32, 4) LASR_CTC_CASE(32, 8)
+    LASR_CTC_CASE(256, 2) LASR_CTC_CASE(256, 4) LASR_CTC_CASE(256, 6) LASR_CTC_CASE(256, 8)
+#undef LASR_CTC_CASE
+}
+
+// Two-pass pipeline (default for vectorisable layouts with V <= 8192):
+//   pass 1 (stream order, all SMs)  per-row log-sum-exp + lattice inputs          reads the logits once
+//   lattice (2 CTAs per utterance)  meet-in-the-middle sweeps, occupancies replace alpha in the workspace
+//   pass 3 (all SMs)                grad = s * (softmax - occupancy)               reads the logits again, writes the gradient
+// Large problems are split into utterance groups: the latency-bound lattice of group g runs on a side stream while pass 1 of
+// the later groups and pass 3 of the earlier groups keep HBM busy on the caller's stream (fork / join with events, legal
+// under stream capture).  No read-modify-write of the gradient in DRAM, no separate scatter pass.
+static const int CTC_MAX_GROUPS = 8;
+template <typename T>
+static int ctc_launch_twopass(CtcDenseParams p, float2* ab, float2* be, float* tot, int* flags, float* nll, cudaStream_t st) {
+    const int W = p.lmax + 1;
+    p.occ = ab;
+    int G = 1;
+    if ((double)p.T * p.B * p.V >= 6.4e7 && p.B >= 16) G = p.B / 8 < CTC_MAX_GROUPS ? p.B / 8 : CTC_MAX_GROUPS;
+    static cudaStream_t side[CTC_MAX_GROUPS];
+    static cudaEvent_t e1[CTC_MAX_GROUPS], e2[CTC_MAX_GROUPS];
+    static bool pool = false;
+    if (G > 1 && !pool) {
+        for (int i = 0; i < CTC_MAX_GROUPS; ++i) {
+            if (cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking) != cudaSuccess ||
+                cudaEventCreateWithFlags(&e1[i], cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&e2[i], cudaEventDisableTiming) != cudaSuccess)
+                return check_launch("ctc stream pool");
+        }
+        pool = true;
+    }
+    if (cudaMemsetAsync(flags, 0, 2 * (size_t)p.B * sizeof(int), st) != cudaSuccess) return check_launch("ctc flags");
+    const int per = ceil_div(p.B, G);
+    for (int g = 0; g < G; ++g) {
+        CtcDenseParams q = p;
+        q.b0 = g * per;
+        q.nb = p.B - q.b0 < per ? p.B - q.b0 : per;
+        if (q.nb <= 0) break;
+        launch_pass<T, 1>(q, st);
+        if (G > 1 && cudaEventRecord(e1[g], st) != cudaSuccess) return check_launch("ctc event");
+    }
+    int rc = check_launch("ctc_pass1");
+    if (rc) return rc;
+    for (int g = 0; g < G; ++g) {
+        const int b0 = g * per, nb = p.B - b0 < per ? p.B - b0 : per;
+        if (nb <= 0) break;
+        cudaStream_t sg = G > 1 ? side[g] : st;
+        if (G > 1 && cudaStreamWaitEvent(sg, e1[g], 0) != cudaSuccess) return check_launch("ctc wait");
+#define LASR_MEET(R, PFW, NW)                                                                                                  \
+    ctc_lattice_meet_kernel<T, R, PFW, NW, true><<<2 * nb, 32 * NW, 0, sg>>>(p.lp_ext, ab, be, p.targets, p.in_len, p.tgt_len, nll, tot, flags, \
+                                                                              p.grad, p.gst, p.gsb, p.blank, p.grad_scale, p.upstream, p.T, p.lmax, b0)
+        if (W <= 32) LASR_MEET(1, 8, 1);
+        else if (W <= 64) LASR_MEET(2, 8, 1);
+        else if (W <= 128) LASR_MEET(2, 8, 2);
+        else if (W <= 256) LASR_MEET(2, 8, 4);
+        else if (W <= 512) LASR_MEET(2, 8, 8);
+        else LASR_MEET(4, 4, 8);
+#undef LASR_MEET
+        if (G > 1 && cudaEventRecord(e2[g], sg) != cudaSuccess) return check_launch("ctc event");
+    }
+    rc = check_launch("ctc_lattice_meet");
+    if (rc) return rc;
+    for (int g = 0; g < G; ++g) {
+        CtcDenseParams q = p;
+        q.b0 = g * per;
+        q.nb = p.B - q.b0 < per ? p.B - q.b0 : per;
+        if (q.nb <= 0) break;
+        if (G > 1 && cudaStreamWaitEvent(st, e2[g], 0) != cudaSuccess) return check_launch("ctc wait");
+        launch_pass<T, 3>(q, st);
+    }
+    return check_launch("ctc_pass3");
+}
+
 template <typename T>
 static int ctc_launch(const CtcDenseParams& p, float2* ab, float2* be, float* tot, int* flags, float* nll, cudaStream_t st) {
     const long rows = (long)p.T * p.B;
     const bool vec = ((reinterpret_cast<uintptr_t>(p.logits) | reinterpret_cast<uintptr_t>(p.grad)) % (4 * sizeof(T)) == 0) &&
                      p.st % 4 == 0 && p.sb % 4 == 0 && p.gst % 4 == 0 && p.gsb % 4 == 0;
+    static int pipe = -1;  // LASR_CTC_PIPE=0: developer switch back to the single-pass gather + separate scatter
+    if (pipe < 0) { const char* e = getenv("LASR_CTC_PIPE"); pipe = e ? atoi(e) : 0; }
+    if (pipe && vec && (p.V + 3) / 4 <= 2048) return ctc_launch_twopass<T>(p, ab, be, tot, flags, nll, st);
     bool done = false;
     if (vec) {
         const int chunks = (p.V + 3) / 4;
@@ -750,8 +1003,8 @@ static int ctc_launch(const CtcDenseParams& p, float2* ab, float2* be, float* to
         if (fused) {
             if (cudaMemsetAsync(flags, 0, 2 * (size_t)p.B * sizeof(int), st) != cudaSuccess) return check_launch("ctc flags");
 #define LASR_MEET(R, PFW, NW)                                                                                                  \
-    ctc_lattice_meet_kernel<T, R, PFW, NW><<<2 * p.B, 32 * NW, 0, st>>>(p.lp_ext, ab, be, p.targets, p.in_len, p.tgt_len, nll, tot, flags, \
-                                                                         p.grad, p.gst, p.gsb, p.blank, p.grad_scale, p.upstream, p.T, p.lmax)
+    ctc_lattice_meet_kernel<T, R, PFW, NW, false><<<2 * p.B, 32 * NW, 0, st>>>(p.lp_ext, ab, be, p.targets, p.in_len, p.tgt_len, nll, tot, flags, \
+                                                                                p.grad, p.gst, p.gsb, p.blank, p.grad_scale, p.upstream, p.T, p.lmax, 0)
             if (W <= 32) LASR_MEET(1, 8, 1);
             else if (W <= 64) LASR_MEET(2, 8, 1);
             else if (W <= 128) LASR_MEET(2, 8, 2);
@@ -786,7 +1039,7 @@ extern "C" {
 size_t lasr_ctc_workspace_bytes(int T, int B, int lmax) {
     const size_t w = (size_t)(lmax < 1 ? 1 : lmax) + 1;
     // alpha (float2) + beta (float2) + gathered lattice inputs (float) per (t, b, state pair); tot + two meeting flags per utterance
-    return (size_t)T * B * w * (sizeof(float) + 2 * sizeof(float2)) + (size_t)B * (sizeof(float) + 2 * sizeof(int)) + 1024;
+    return (size_t)T * B * w * (sizeof(float) + 2 * sizeof(float2)) + (size_t)B * (sizeof(float) + 2 * sizeof(int)) + (size_t)T * B * sizeof(float) + 1024;
 }
 
 int lasr_ctc_fwdbwd(const void* logits, int dtype, int64_t st, int64_t sb, const int64_t* targets, const int64_t* in_len,
@@ -809,6 +1062,8 @@ int lasr_ctc_fwdbwd(const void* logits, int dtype, int64_t st, int64_t sb, const
     p.lp_ext = reinterpret_cast<float*>(base + 2 * (size_t)T * B * w * sizeof(float2));
     float* tot = reinterpret_cast<float*>(base + (size_t)T * B * w * (2 * sizeof(float2) + sizeof(float)));
     int* flags = reinterpret_cast<int*>(tot + B);  // meeting flags of the alpha / beta CTA pairs
+    p.lse = reinterpret_cast<float*>(flags + 2 * B);
+    p.b0 = 0; p.nb = B; p.occ = nullptr;
     p.T = T; p.B = B; p.V = V; p.lmax = lmax; p.blank = blank; p.grad_scale = grad_scale; p.upstream = upstream;
     if (dtype == LASR_F32) return ctc_launch<float>(p, ab, be, tot, flags, nll, (cudaStream_t)stream);
     if (dtype == LASR_BF16) return ctc_launch<bf16>(p, ab, be, tot, flags, nll, (cudaStream_t)stream);
