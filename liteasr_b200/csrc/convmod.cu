@@ -13,6 +13,8 @@
 //   fwd 3: a = swish(gamma * (z - mean) * rstd + beta)
 //   bwd 1: partial sums of du and du*zhat  (du = da * swish'(u))  -> also dgamma / dbeta
 //   bwd 2: dz on the fly -> depthwise dgrad + wgrad -> GLU backward, one pass
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace lasr {
@@ -298,46 +300,63 @@ __global__ void __launch_bounds__(256, 4) glu_dwconv_fwd_kernel(const TD* __rest
 }
 
 // ---------------------------------------------------------------- column reduction of [nblk][2][d] partials (double)
-// block (32 channels, RG row groups) = 1024 threads: the reduction is a latency chain per thread, so rows are spread over as
-// many threads as a CTA holds.  FIN = 0: BatchNorm statistics + running stats, FIN = 1: backward sums + dgamma/dbeta
-constexpr int RG = 32;
+// One thread-block CLUSTER of CL CTAs per 32 channels: every CTA (32 channels x RG row groups = 1024 threads) reduces a
+// 1/CL slice of the rows, rank 0 then adds the CL slice sums through distributed shared memory in a fixed order
+// (deterministic; no global scratch, no atomics).  The reduction is a latency chain per thread, so it is spread over as many
+// threads as possible: 8 CTAs x 1024 threads per 32 channels instead of one CTA of 256.
+// FIN = 0: BatchNorm statistics + running stats, FIN = 1: backward sums + dgamma/dbeta
+constexpr int RG = 32, CL = 8;
 template <int FIN>
-__global__ void __launch_bounds__(32 * RG) bn_reduce_kernel(const float* __restrict__ partial, int nblk, int d, long count, float eps,
-                                                            float momentum, float* __restrict__ o0, float* __restrict__ o1,
-                                                            float* __restrict__ r0, float* __restrict__ r1, int64_t* __restrict__ nbt) {
+__global__ void __cluster_dims__(1, CL, 1) __launch_bounds__(32 * RG)
+bn_reduce_kernel(const float* __restrict__ partial, int nblk, int d, long count, float eps, float momentum, float* __restrict__ o0,
+                 float* __restrict__ o1, float* __restrict__ r0, float* __restrict__ r1, int64_t* __restrict__ nbt) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
     __shared__ double sh[2][RG][33];
-    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5, c = blockIdx.x * 32 + cx;
+    __shared__ double slice[2][32];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5, c = blockIdx.x * 32 + cx, rank = blockIdx.y;
     double s = 0.0, q = 0.0;
     if (c < d) {
 #pragma unroll 4
-        for (int i = ry; i < nblk; i += RG) {
+        for (int i = rank * RG + ry; i < nblk; i += RG * CL) {
             s += (double)partial[(long)i * 2 * d + c];
             q += (double)partial[(long)i * 2 * d + d + c];
         }
     }
     sh[0][ry][cx] = s; sh[1][ry][cx] = q;
     __syncthreads();
-    if (ry != 0 || c >= d) return;
+    if (ry == 0) {
 #pragma unroll
-    for (int j = 1; j < RG; ++j) { s += sh[0][j][cx]; q += sh[1][j][cx]; }
-    if (FIN == 0) {
-        const double mu = s / (double)count;
-        double var = q / (double)count - mu * mu;
-        if (var < 0.0) var = 0.0;
-        o0[c] = (float)mu;
-        o1[c] = (float)(1.0 / sqrt(var + (double)eps));
-        if (r0) {
-            const double unb = count > 1 ? var * (double)count / (double)(count - 1) : var;
-            r0[c] = (float)((1.0 - momentum) * (double)r0[c] + momentum * mu);
-            r1[c] = (float)((1.0 - momentum) * (double)r1[c] + momentum * unb);
-            if (c == 0 && nbt) *nbt += 1;
-        }
-    } else {
-        o0[c] = (float)s;       // sums[0:d]  = sum du
-        o0[d + c] = (float)q;   // sums[d:2d] = sum du * zhat
-        r0[c] += (float)q;      // dgamma
-        r1[c] += (float)s;      // dbeta
+        for (int j = 1; j < RG; ++j) { s += sh[0][j][cx]; q += sh[1][j][cx]; }
+        slice[0][cx] = s; slice[1][cx] = q;
     }
+    cluster.sync();
+    if (rank == 0 && ry == 0 && c < d) {
+        for (int r = 1; r < CL; ++r) {
+            const double* remote = cluster.map_shared_rank(&slice[0][0], r);
+            s += remote[cx];
+            q += remote[32 + cx];
+        }
+        if (FIN == 0) {
+            const double mu = s / (double)count;
+            double var = q / (double)count - mu * mu;
+            if (var < 0.0) var = 0.0;
+            o0[c] = (float)mu;
+            o1[c] = (float)(1.0 / sqrt(var + (double)eps));
+            if (r0) {
+                const double unb = count > 1 ? var * (double)count / (double)(count - 1) : var;
+                r0[c] = (float)((1.0 - momentum) * (double)r0[c] + momentum * mu);
+                r1[c] = (float)((1.0 - momentum) * (double)r1[c] + momentum * unb);
+                if (c == 0 && nbt) *nbt += 1;
+            }
+        } else {
+            o0[c] = (float)s;       // sums[0:d]  = sum du
+            o0[d + c] = (float)q;   // sums[d:2d] = sum du * zhat
+            r0[c] += (float)q;      // dgamma
+            r1[c] += (float)s;      // dbeta
+        }
+    }
+    cluster.sync();  // the slices stay mapped until rank 0 has read them
 }
 
 __global__ void __launch_bounds__(128) bn_eval_stats_kernel(const float* __restrict__ running_mean, const float* __restrict__ running_var,
@@ -530,6 +549,7 @@ __global__ void __launch_bounds__(256, 3) dwconv_glu_bwd_kernel(const TD* __rest
 }
 
 // second stage of the depthwise-weight / bias / pointwise-bias gradient: block (32 channels, RG row groups), grid (d/32, KW+3)
+// (already 144 CTAs of 1024 threads at d = 256: a cluster split like bn_reduce's measured 3x slower here)
 __global__ void __launch_bounds__(32 * RG) dwconv_reduce_kernel(const float* __restrict__ wpartial, int nblk, int d, float* __restrict__ dw,
                                                                 float* __restrict__ dbias, float* __restrict__ colsum) {
     __shared__ float sh[RG][33];
@@ -583,7 +603,7 @@ int lasr_bn_finalize(const float* partial, int nblk, int d, int64_t count, float
     LASR_REQUIRE(!training || ((running_mean != nullptr) == (running_var != nullptr)), "bn_finalize: running stats come in pairs");
     cudaStream_t st = (cudaStream_t)stream;
     if (!training) bn_eval_stats_kernel<<<ceil_div(d, 128), 128, 0, st>>>(running_mean, running_var, eps, mean, rstd, d);
-    else bn_reduce_kernel<0><<<ceil_div(d, 32), 32 * RG, 0, st>>>(partial, nblk, d, count, eps, momentum, mean, rstd, running_mean, running_var,
+    else bn_reduce_kernel<0><<<dim3(ceil_div(d, 32), CL), 32 * RG, 0, st>>>(partial, nblk, d, count, eps, momentum, mean, rstd, running_mean, running_var,
                                                              num_batches_tracked);
     return check_launch("bn_finalize");
 }
@@ -623,7 +643,7 @@ int lasr_bn_swish_bwd_stats(const void* da, int dtype, const float* z, const flo
     }
     int rc = check_launch("bn_swish_bwd_stats");
     if (rc) return rc;
-    bn_reduce_kernel<1><<<ceil_div(d, 32), 32 * RG, 0, st>>>(partial, nblk, d, 0, 0.f, 0.f, sums, nullptr, dgamma, dbeta, nullptr);
+    bn_reduce_kernel<1><<<dim3(ceil_div(d, 32), CL), 32 * RG, 0, st>>>(partial, nblk, d, 0, 0.f, 0.f, sums, nullptr, dgamma, dbeta, nullptr);
     return check_launch("bn_bwd_finalize");
 }
 
