@@ -19,6 +19,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <type_traits>
 
@@ -35,12 +36,15 @@ constexpr int A_BYTES = BM * BK * 2;
 constexpr int MAX_STAGES = 8;
 constexpr int ACC_COLS = 256;  // TMEM columns per accumulator buffer (2 buffers = the whole 512-column TMEM)
 
-// shared-memory carve-up (offsets from the 1024-aligned base)
-constexpr int SM_STAGING = 0;                    // EPI_WARPS x 32 rows x 128 B
-constexpr int SM_BARS = EPI_WARPS * 4096;        // mbarriers + TMEM slot
-constexpr int SM_RING = SM_BARS + 1024;
+// shared-memory carve-up (offsets from the 1024-aligned base): epilogue staging (EPI_WARPS x 32 rows x CW fp32 columns),
+// mbarriers + TMEM slot, then the operand ring.  CW = 32 in the streaming kernels; the B-stationary kernels stage 16 columns
+// at a time (32 KB instead of 64 KB) to make room for a resident weight tile.
+constexpr int sm_bars(int cw) { return EPI_WARPS * 32 * cw * 4; }
+constexpr int sm_ring(int cw) { return sm_bars(cw) + 1024; }
 constexpr int SM_MAX_DYNAMIC = 232448;   // 227 KB
-constexpr int SM_RING_BUDGET = SM_MAX_DYNAMIC - SM_RING - 1024 /*alignment slack*/;
+constexpr int sm_ring_budget(int cw) { return SM_MAX_DYNAMIC - sm_ring(cw) - 1024 /*alignment slack*/; }
+constexpr int SM_RING = sm_ring(32);
+constexpr int SM_RING_BUDGET = sm_ring_budget(32);
 
 struct TcParams {
     void* c;
@@ -68,6 +72,8 @@ struct TcParams {
     float* colsum;     // colsum[b1*cs1 + b2*cs2 + n] += sum_m C[m, n]
     long cs1, cs2;
     // implicit-GEMM 3x3 stride-2 convolution over parity planes (see conv2_tc_dispatch): only the TMA producer changes
+    int b_stationary;  // K <= 256 GEMMs: every CTA keeps ONE N tile of B resident in shared memory and streams A tiles only
+    int bsta_bytes;    // size of that resident tile
     int conv_mode;     // 0 plain GEMM | 1 forward | 2 input gradient (one parity class) | 3 weight gradient
     int conv_kbt;      // K blocks per tap (= channels / 64)
     int conv_d;        // channels
@@ -140,6 +146,17 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
           "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr)
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -254,15 +271,21 @@ __device__ __forceinline__ void store4(CT* dst, const float4& f) {
 // Epilogue modes: the column phase is specialised so that its inner loop carries no run-time flag tests.
 enum { EPI_PLAIN = 0, EPI_RELU = 1, EPI_SWISH = 2, EPI_RES = 3, EPI_ACC = 4, EPI_GENERIC = 5, EPI_DSWISH = 6, EPI_DRELU = 7 };
 
-template <typename CT, int MODE>
+// CW = staged chunk width in fp32 columns (32, or 16 in the B-stationary kernels).  The staging buffer holds 32 rows x CW
+// columns; a row is PIECES = CW/4 16-byte pieces, XOR-swizzled so that both the row-per-thread writes and the row-contiguous
+// reads are bank-conflict free: piece j of row r lives at r*128 + ((j ^ (r & 7)) << 4) for CW = 32 and at
+// r*64 + ((j ^ ((r >> 1) & 3)) << 4) for CW = 16.  In the column phase PIECES lanes own one row segment and a warp covers
+// RGRP = 32 / PIECES rows per instruction.
+template <typename CT, int MODE, int CW>
 __device__ __forceinline__ void epilogue_unit(const TcParams& p, const Unit& w, uint32_t tmem_acc, uint8_t* stage, int q, int part,
                                               int lane) {
+    constexpr int PIECES = CW / 4, RGRP = 32 / PIECES, ITERS = 32 / RGRP, ROWB = CW * 4;
     const long boff = (long)w.b1 * p.sc1 + (long)w.b2 * p.sc2;
     const int col_limit = min(p.n_store, w.n0 + p.bn);
     const int row_base = w.m0 + q * 32;
     const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
-    const int chunk = lane & 7, rsub = lane >> 3;
-    const int nrows = p.m - row_base - rsub;  // this lane's row 4i + rsub exists iff 4i < nrows
+    const int chunk = lane % PIECES, rsub = lane / PIECES;
+    const int nrows = p.m - row_base - rsub;  // this lane's row RGRP*i + rsub exists iff RGRP*i < nrows
     const float alpha = p.alpha;
     CT* cbase = reinterpret_cast<CT*>(p.c) + boff;
     CT* abase = p.aux ? reinterpret_cast<CT*>(p.aux) + boff : nullptr;
@@ -270,34 +293,35 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, const Unit& w, 
     const bf16* dbase = p.dact ? p.dact + boff : nullptr;
     float* csbase = p.colsum ? p.colsum + (long)w.b1 * p.cs1 + (long)w.b2 * p.cs2 : nullptr;
     constexpr bool DACT = (MODE == EPI_DSWISH || MODE == EPI_DRELU);
-    uint8_t* wr = stage + lane * 128;
-    const int wx = (lane & 7) << 4;
-    const uint8_t* rd0 = stage + rsub * 128 + ((chunk ^ rsub) << 4);        // rows 4i + rsub, i even
-    const uint8_t* rd1 = stage + rsub * 128 + (((chunk ^ rsub) ^ 4) << 4);  // i odd
-    for (int cc = part * 32; cc < p.bn; cc += 32 * (EPI_WARPS / 4)) {
+    uint8_t* wr = stage + lane * ROWB;
+    const int wx = (CW == 32) ? ((lane & 7) << 4) : (((lane >> 1) & 3) << 4);
+    // CW = 32: rows 4i + rsub alternate between two swizzle phases (i even / odd); CW = 16: rows 8i + rsub share one
+    const uint8_t* rd0 = (CW == 32) ? stage + rsub * 128 + ((chunk ^ rsub) << 4) : stage + rsub * 64 + ((chunk ^ ((rsub >> 1) & 3)) << 4);
+    const uint8_t* rd1 = (CW == 32) ? stage + rsub * 128 + (((chunk ^ rsub) ^ 4) << 4) : rd0;
+    for (int cc = part * CW; cc < p.bn; cc += CW * (EPI_WARPS / 4)) {
         const int col = w.n0 + cc + chunk * 4;  // this lane's 4 columns in the column phase
         if (w.n0 + cc >= col_limit) break;      // warp-uniform
-        // vector path: whole 32-column chunks, or a partial chunk whose edge falls on a 4-column boundary (then each lane's
+        // vector path: whole chunks, or a partial chunk whose edge falls on a 4-column boundary (then each lane's
         // 4 columns are all inside or all outside: N = 304 score tiles, N = 4240 padded vocabularies)
-        const bool fast = (MODE != EPI_GENERIC) && p.vec_ok && ((w.n0 + cc + 32 <= col_limit) || (col_limit & 3) == 0);
+        const bool fast = (MODE != EPI_GENERIC) && p.vec_ok && ((w.n0 + cc + CW <= col_limit) || (col_limit & 3) == 0);
         const bool lane_ok = col < col_limit;
         // prefetch what the column phase needs from global memory before touching TMEM
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 r4[8];
-        uint2 s2[8];
+        float4 r4[ITERS];
+        uint2 s2[ITERS];
         if (fast) {
             if (p.bias && lane_ok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
             if constexpr (DACT) {
                 const bf16* sp = dbase + (long)(row_base + rsub) * p.lddact + col;
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    s2[i] = ldg_pred_u2(sp + (long)(4 * i) * p.lddact, 4 * i < nrows && lane_ok);
+                for (int i = 0; i < ITERS; ++i)
+                    s2[i] = ldg_pred_u2(sp + (long)(RGRP * i) * p.lddact, RGRP * i < nrows && lane_ok);
             }
             if constexpr (MODE == EPI_RES) {
                 const float* rp = rbase + (long)(row_base + rsub) * p.ldres + col;
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    r4[i] = ldg_pred_f4(rp + (long)(4 * i) * p.ldres, 4 * i < nrows && lane_ok);
+                for (int i = 0; i < ITERS; ++i)
+                    r4[i] = ldg_pred_f4(rp + (long)(RGRP * i) * p.ldres, RGRP * i < nrows && lane_ok);
             }
         } else if (p.bias) {
             b4.x = (col + 0 < col_limit) ? __ldg(p.bias + col + 0) : 0.f;
@@ -307,27 +331,28 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, const Unit& w, 
         }
         // row phase: thread = accumulator row
         {
-            float v[32];
-            tc_ld32(taddr + (uint32_t)cc, v);
+            float v[CW];
+            if constexpr (CW == 32) tc_ld32(taddr + (uint32_t)cc, v);
+            else tc_ld16(taddr + (uint32_t)cc, v);
             __syncwarp();  // the previous chunk's column phase has finished reading the staging buffer
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
+            for (int j = 0; j < PIECES; ++j)
                 *reinterpret_cast<float4*>(wr + ((j << 4) ^ wx)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
         __syncwarp();
-        // column phase: 8 lanes cover one 128-byte row segment, 4 rows per instruction
+        // column phase: PIECES lanes cover one row segment, RGRP rows per instruction
         if (fast) {
             const long off0 = (long)(row_base + rsub) * p.ldc + col;
             CT* crow = cbase + off0;
             CT* arow = abase ? abase + off0 : nullptr;
-            const long rstride = 4 * p.ldc;
+            const long rstride = RGRP * p.ldc;
             float4 ba = b4;
             if constexpr (MODE == EPI_PLAIN || MODE == EPI_RES) { ba.x *= alpha; ba.y *= alpha; ba.z *= alpha; ba.w *= alpha; }
             float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                float4 f = *reinterpret_cast<const float4*>(((i & 1) ? rd1 : rd0) + i * 512);
-                if (4 * i < nrows && lane_ok) {
+            for (int i = 0; i < ITERS; ++i) {
+                float4 f = *reinterpret_cast<const float4*>(((i & 1) ? rd1 : rd0) + i * (RGRP * ROWB));
+                if (RGRP * i < nrows && lane_ok) {
                     if constexpr (MODE == EPI_PLAIN) {
                         f.x = fmaf(f.x, alpha, ba.x); f.y = fmaf(f.y, alpha, ba.y); f.z = fmaf(f.z, alpha, ba.z); f.w = fmaf(f.w, alpha, ba.w);
                         store4<CT>(crow, f);
@@ -365,20 +390,22 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, const Unit& w, 
                 if (arow) arow += rstride;
             }
             if constexpr (MODE == EPI_PLAIN || DACT) {
-                if (csbase) {  // warp-uniform: fold the 4 row groups, then one vector red per 4 columns
-                    cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 8); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 8);
-                    cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 8); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 8);
-                    cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 16); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 16);
-                    cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 16); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 16);
+                if (csbase) {  // warp-uniform: fold the row groups (lanes with the same piece), then one vector red per 4 columns
+#pragma unroll
+                    for (int o = PIECES; o < 32; o <<= 1) {
+                        cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+                        cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+                    }
                     if (rsub == 0 && lane_ok) red_add_f32x4(csbase + col, cs);
                 }
             }
         } else {  // ragged N edge, unaligned C or an unusual flag combination: element-wise, compact (not unrolled)
 #pragma unroll 1
-            for (int i = 0; i < 8; ++i) {
-                const int row = 4 * i + rsub;
+            for (int i = 0; i < ITERS; ++i) {
+                const int row = RGRP * i + rsub;
                 const int grow = row_base + row;
-                const float4 f4 = *reinterpret_cast<const float4*>(stage + row * 128 + ((chunk ^ (row & 7)) << 4));
+                const int swz = (CW == 32) ? (row & 7) : ((row >> 1) & 3);
+                const float4 f4 = *reinterpret_cast<const float4*>(stage + row * ROWB + ((chunk ^ swz) << 4));
                 const float f[4] = {f4.x + b4.x, f4.y + b4.y, f4.z + b4.z, f4.w + b4.w};
                 if (grow >= p.m) continue;
 #pragma unroll 1
@@ -405,21 +432,61 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, const Unit& w, 
     }
 }
 
+// Work-unit walk shared by the three roles.  Streaming kernels: units blockIdx.x, + gridDim.x, ... of the (batch, split, m, n)
+// list.  B-stationary kernels: the CTA owns N tile blockIdx.x % tiles_n for its whole life and takes every
+// (gridDim.x / tiles_n)-th M tile (gridDim.x is a multiple of tiles_n).
+template <bool BS>
+struct Walk {
+    int cur, step, nt;
+    __device__ __forceinline__ explicit Walk(const TcParams& p) {
+        if (BS) {
+            nt = blockIdx.x % p.tiles_n;
+            cur = blockIdx.x / p.tiles_n;
+            step = gridDim.x / p.tiles_n;
+        } else {
+            nt = 0;
+            cur = blockIdx.x;
+            step = gridDim.x;
+        }
+    }
+    __device__ __forceinline__ bool next(const TcParams& p, Unit& w) {
+        if (BS) {
+            if (cur >= p.tiles_m) return false;
+            w.m0 = cur * BM; w.n0 = nt * p.bn; w.b1 = 0; w.b2 = 0; w.kb_begin = 0; w.num_kb = (p.k + BK - 1) / BK;
+            cur += step;
+            return true;
+        }
+        while (cur < p.total_units) {
+            w = decode_unit(p, cur);
+            cur += step;
+            if (w.num_kb > 0) return true;  // <= 0 only for trailing splits: skipped by every role
+        }
+        return false;
+    }
+};
+
 // MODE / C_F32 specialise the epilogue warps (one kernel per epilogue keeps the instruction footprint and the register
 // allocation of each variant minimal); operand majors are run-time values: they only steer the two single-thread roles.
-template <int MODE, bool C_F32>
+// BS (B-stationary, K <= 256): the weight tile of the CTA's N tile is loaded ONCE into shared memory and only 16 KB A slabs
+// stream through the ring -- a K = 256 GEMM otherwise re-fetches its 128 KB B tile for every 128 x 256 output tile and runs
+// at the L2 -> SM bandwidth, not at the tensor or HBM roofline.
+template <int MODE, bool C_F32, bool BS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const TcParams p) {
+    constexpr int CW = BS ? 16 : 32;
     const bool A_MN = p.a_mn != 0, B_MN = p.b_mn != 0;
     extern __shared__ uint8_t smem_raw[];
     // align inside the shared window (keeps the address space visible to the compiler: LDS/STS, not generic LD/ST)
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM_BARS);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + sm_bars(CW));
     uint64_t* empty_bar = full_bar + MAX_STAGES;
     uint64_t* acc_full = empty_bar + MAX_STAGES;
     uint64_t* acc_empty = acc_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-    uint8_t* ring = smem + SM_RING;
+    uint64_t* b_full = acc_empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
+    uint8_t* bsta = smem + sm_ring(CW);                         // resident B k-blocks (BS only)
+    uint8_t* ring = bsta + (BS ? p.bsta_bytes : 0);
+    const int b_kb_bytes = p.bn * BK * 2;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -436,6 +503,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             mbar_init(acc_full + s, 1);
             mbar_init(acc_empty + s, EPI_WARPS);  // one arrival per epilogue warp
         }
+        mbar_init(b_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -453,9 +521,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-            for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
-                const Unit w = decode_unit(p, u);
-                if (w.num_kb <= 0) continue;
+            Walk<BS> walk(p);
+            Unit w;
+            if (BS && walk.cur < p.tiles_m) {  // the CTA's weight tile, once
+                const int total_kb = (p.k + BK - 1) / BK, n0 = walk.nt * p.bn;
+                mbar_arrive_expect_tx(b_full, (uint32_t)(total_kb * b_kb_bytes));
+                for (int kb = 0; kb < total_kb; ++kb) {
+                    uint8_t* sb = bsta + kb * b_kb_bytes;
+                    if (!B_MN) {
+                        tma_load_4d(sb, &tma_b, b_full, kb * BK, n0, 0, 0);
+                    } else {
+                        for (int j = 0; j < p.bn / 64; ++j) tma_load_4d(sb + j * 8192, &tma_b, b_full, n0 + 64 * j, kb * BK, 0, 0);
+                    }
+                }
+            }
+            while (walk.next(p, w)) {
                 const int ab1 = w.b1 * p.a_b1, ab2 = w.b2 * p.a_b2, bb1 = w.b1 * p.b_b1, bb2 = w.b2 * p.b_b2;
                 for (int i = 0; i < w.num_kb; ++i) {
                     mbar_wait(empty_bar + s, ph ^ 1);
@@ -463,7 +543,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     uint8_t* sa = ring + s * p.stage_bytes;
                     uint8_t* sb = sa + A_BYTES;
                     const int k0 = (w.kb_begin + i) * BK;
-                    if (p.conv_mode != 0) {
+                    if (!BS && p.conv_mode != 0) {
                         const int kb = w.kb_begin + i;
                         if (p.conv_mode == 1) {         // A = h1 planes (rows shifted per tap), B = (co, tap*ci) weight, both K-major
                             const int tp = kb / p.conv_kbt, kc = kb - tp * p.conv_kbt;
@@ -483,19 +563,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                                 tma_load_4d(sb + j * 8192, &tma_b, full_bar + s, nloc + 64 * j, k0 + p.conv_off[tp], p.conv_plane[tp], w.b1);
                         }
                     } else {
-                    if (!A_MN) {
-                        tma_load_4d(sa, &tma_a, full_bar + s, k0, w.m0, ab2, ab1);  // box {64 k, 128 m}
-                    } else {
+                        if (!A_MN) {
+                            tma_load_4d(sa, &tma_a, full_bar + s, k0, w.m0, ab2, ab1);  // box {64 k, 128 m}
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < BM / 64; ++j)  // box {64 m, 64 k}
-                            tma_load_4d(sa + j * 8192, &tma_a, full_bar + s, w.m0 + 64 * j, k0, ab2, ab1);
-                    }
-                    if (!B_MN) {
-                        tma_load_4d(sb, &tma_b, full_bar + s, k0, w.n0, bb2, bb1);  // box {64 k, BN n}
-                    } else {
-                        for (int j = 0; j < p.bn / 64; ++j)
-                            tma_load_4d(sb + j * 8192, &tma_b, full_bar + s, w.n0 + 64 * j, k0, bb2, bb1);
-                    }
+                            for (int j = 0; j < BM / 64; ++j)  // box {64 m, 64 k}
+                                tma_load_4d(sa + j * 8192, &tma_a, full_bar + s, w.m0 + 64 * j, k0, ab2, ab1);
+                        }
+                        if (!BS) {
+                            if (!B_MN) {
+                                tma_load_4d(sb, &tma_b, full_bar + s, k0, w.n0, bb2, bb1);  // box {64 k, BN n}
+                            } else {
+                                for (int j = 0; j < p.bn / 64; ++j)
+                                    tma_load_4d(sb + j * 8192, &tma_b, full_bar + s, w.n0 + 64 * j, k0, bb2, bb1);
+                            }
+                        }
                     }
                     if (++s == p.stages) { s = 0; ph ^= 1; }
                 }
@@ -508,9 +590,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                                    ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             int s = 0, as = 0;
             uint32_t ph = 0, aph = 0;
-            for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
-                const Unit w = decode_unit(p, u);
-                if (w.num_kb <= 0) continue;
+            Walk<BS> walk(p);
+            Unit w;
+            if (BS && walk.cur < p.tiles_m) {
+                mbar_wait(b_full, 0);
+                tc_fence_after();
+            }
+            while (walk.next(p, w)) {
                 mbar_wait(acc_empty + as, aph ^ 1);  // the epilogue has drained this accumulator buffer
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(as * ACC_COLS);
@@ -518,7 +604,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     mbar_wait(full_bar + s, ph);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(ring + s * p.stage_bytes);
-                    const uint32_t sb = sa + A_BYTES;
+                    const uint32_t sb = BS ? smem_u32(bsta + i * b_kb_bytes) : sa + A_BYTES;
 #pragma unroll
                     for (int kk = 0; kk < BK / UMMA_K; ++kk) {
                         // K-major: +32 B per UMMA_K inside the 128 B swizzle row; SBO = 8 rows * 128 B.
@@ -537,17 +623,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     } else {
         const int q = warp & 3;           // TMEM lane quarter this warp may access
         const int ew = warp - 2;          // private staging slice
-        const int part = ew >> 2;         // which 32-column chunks of the tile (chunk index % (EPI_WARPS/4))
-        uint8_t* stage = smem + SM_STAGING + ew * 4096;
+        const int part = ew >> 2;         // which CW-column chunks of the tile (chunk index % (EPI_WARPS/4))
+        uint8_t* stage = smem + ew * (32 * CW * 4);
         int as = 0;
         uint32_t aph = 0;
-        for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
-            const Unit w = decode_unit(p, u);
-            if (w.num_kb <= 0) continue;
+        Walk<BS> walk(p);
+        Unit w;
+        while (walk.next(p, w)) {
             mbar_wait(acc_full + as, aph);
             tc_fence_after();
             const uint32_t tmem_acc = tmem_base + (uint32_t)(as * ACC_COLS);
-            epilogue_unit<typename std::conditional<C_F32, float, bf16>::type, MODE>(p, w, tmem_acc, stage, q, part, lane);
+            epilogue_unit<typename std::conditional<C_F32, float, bf16>::type, MODE, CW>(p, w, tmem_acc, stage, q, part, lane);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + as);
@@ -630,10 +716,10 @@ static int pick_bn(int n, int gran) {
 
 typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, const TcParams);
 
-template <int MODE, bool C_F32>
+template <int MODE, bool C_F32, bool BS>
 static TcKernel configured_kernel() {
     static bool configured = false;
-    TcKernel k = gemm_tc_kernel<MODE, C_F32>;
+    TcKernel k = gemm_tc_kernel<MODE, C_F32, BS>;
     if (!configured) {
         if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_MAX_DYNAMIC) != cudaSuccess) return nullptr;
         configured = true;
@@ -641,34 +727,42 @@ static TcKernel configured_kernel() {
     return k;
 }
 
+template <bool BS>
 static TcKernel pick_kernel(int mode, bool f32) {
     if (f32) {
         switch (mode) {
-            case EPI_PLAIN: return configured_kernel<EPI_PLAIN, true>();
-            case EPI_RELU: return configured_kernel<EPI_RELU, true>();
-            case EPI_SWISH: return configured_kernel<EPI_SWISH, true>();
-            case EPI_RES: return configured_kernel<EPI_RES, true>();
-            case EPI_ACC: return configured_kernel<EPI_ACC, true>();
-            case EPI_DSWISH: return configured_kernel<EPI_DSWISH, true>();
-            case EPI_DRELU: return configured_kernel<EPI_DRELU, true>();
-            default: return configured_kernel<EPI_GENERIC, true>();
+            case EPI_PLAIN: return configured_kernel<EPI_PLAIN, true, BS>();
+            case EPI_RELU: return configured_kernel<EPI_RELU, true, BS>();
+            case EPI_SWISH: return configured_kernel<EPI_SWISH, true, BS>();
+            case EPI_RES: return configured_kernel<EPI_RES, true, BS>();
+            case EPI_ACC: return configured_kernel<EPI_ACC, true, BS>();
+            case EPI_DSWISH: return configured_kernel<EPI_DSWISH, true, BS>();
+            case EPI_DRELU: return configured_kernel<EPI_DRELU, true, BS>();
+            default: return configured_kernel<EPI_GENERIC, true, BS>();
         }
     }
     switch (mode) {
-        case EPI_PLAIN: return configured_kernel<EPI_PLAIN, false>();
-        case EPI_RELU: return configured_kernel<EPI_RELU, false>();
-        case EPI_SWISH: return configured_kernel<EPI_SWISH, false>();
-        case EPI_DSWISH: return configured_kernel<EPI_DSWISH, false>();
-        case EPI_DRELU: return configured_kernel<EPI_DRELU, false>();
-        default: return configured_kernel<EPI_GENERIC, false>();
+        case EPI_PLAIN: return configured_kernel<EPI_PLAIN, false, BS>();
+        case EPI_RELU: return configured_kernel<EPI_RELU, false, BS>();
+        case EPI_SWISH: return configured_kernel<EPI_SWISH, false, BS>();
+        case EPI_DSWISH: return configured_kernel<EPI_DSWISH, false, BS>();
+        case EPI_DRELU: return configured_kernel<EPI_DRELU, false, BS>();
+        default: return configured_kernel<EPI_GENERIC, false, BS>();
     }
 }
 
 static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st) {
-    TcKernel kern = pick_kernel(p.epi_mode, p.c_dtype == LASR_F32);
+    const bool f32 = p.c_dtype == LASR_F32;
+    TcKernel kern = p.b_stationary ? pick_kernel<true>(p.epi_mode, f32) : pick_kernel<false>(p.epi_mode, f32);
     if (!kern) return check_launch("gemm_tc smem attr");
-    const int smem_bytes = SM_RING + p.stages * p.stage_bytes + 1024;
-    const int grid = p.total_units < sm_count() ? p.total_units : sm_count();
+    int smem_bytes, grid;
+    if (p.b_stationary) {
+        smem_bytes = sm_ring(16) + p.bsta_bytes + p.stages * p.stage_bytes + 1024;
+        grid = sm_count() / p.tiles_n * p.tiles_n;
+    } else {
+        smem_bytes = SM_RING + p.stages * p.stage_bytes + 1024;
+        grid = p.total_units < sm_count() ? p.total_units : sm_count();
+    }
     kern<<<grid, GEMM_THREADS, smem_bytes, st>>>(ma, mb, p);
     return check_launch("gemm_tc");
 }
@@ -733,6 +827,31 @@ int gemm_tc_dispatch(const lasr_gemm_args* a, cudaStream_t st) {
     p.a_mn = a->trans_a ? 1 : 0;
     p.b_mn = a->trans_b ? 1 : 0;
     if (a->c_dtype != LASR_F32 && (p.epi_mode == EPI_RES || p.epi_mode == EPI_ACC)) p.epi_mode = EPI_GENERIC;
+    // B-stationary: short-K, unbatched, many M tiles per CTA, and an even split of the M tiles over the CTAs of an N tile
+    p.b_stationary = 0;
+    p.bsta_bytes = 0;
+    {
+        // Off by default: measured SLOWER than the streaming kernel on every C2 shape it applies to (fc1 forward 86 vs 80 us,
+        // its input gradient 131 vs 102 us at B = 126) although it moves 37 % less through L2 -- those GEMMs are bound by the
+        // epilogue / HBM write stream, not by operand fetch, and the 16-column staging doubles the TMEM-load count.
+        // LASR_GEMM_BS=1 selects it (read per call so that tests can toggle it).
+        const char* bs_env = getenv("LASR_GEMM_BS");
+        const int bs_on = bs_env ? atoi(bs_env) : 0;
+        const int total_kb = (a->k + BK - 1) / BK;
+        if (bs_on && total_kb <= 4 && p.split_k == 1 && !a->accumulate && a->batch1 * a->batch2 == 1 && p.tiles_n <= sm_count() / 2) {
+            const int per_n = sm_count() / p.tiles_n;                  // CTAs per N tile
+            const int rounds = (p.tiles_m + per_n - 1) / per_n;        // M tiles of the busiest CTA
+            const double eff = (double)p.tiles_m / ((double)rounds * per_n);
+            const int bsta = total_kb * bn * BK * 2;
+            const int stages = (sm_ring_budget(16) - bsta) / A_BYTES;
+            if (rounds >= 2 && eff >= 0.9 && stages >= 3) {
+                p.b_stationary = 1;
+                p.bsta_bytes = bsta;
+                p.stage_bytes = A_BYTES;
+                p.stages = stages > MAX_STAGES ? MAX_STAGES : stages;
+            }
+        }
+    }
     return launch_tc(ma, mb, p, st);
 }
 
