@@ -342,10 +342,13 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, const Unit& w, 
         __syncwarp();
         // column phase: PIECES lanes cover one row segment, RGRP rows per instruction
         if (fast) {
-            const long off0 = (long)(row_base + rsub) * p.ldc + col;
-            CT* crow = cbase + off0;
-            CT* arow = abase ? abase + off0 : nullptr;
+            // one running 64-bit element offset serves C and the optional pre-activation copy (same leading dimension); the
+            // copy's presence and alpha == 1 are warp-uniform flags hoisted out of the loop (a nullable pointer advanced per
+            // iteration costs two 64-bit selects and compares per row group)
+            long off = (long)(row_base + rsub) * p.ldc + col;
             const long rstride = RGRP * p.ldc;
+            const bool has_aux = abase != nullptr;
+            const bool unit_alpha = alpha == 1.f;
             float4 ba = b4;
             if constexpr (MODE == EPI_PLAIN || MODE == EPI_RES) { ba.x *= alpha; ba.y *= alpha; ba.z *= alpha; ba.w *= alpha; }
             float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -353,6 +356,7 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, const Unit& w, 
             for (int i = 0; i < ITERS; ++i) {
                 float4 f = *reinterpret_cast<const float4*>(((i & 1) ? rd1 : rd0) + i * (RGRP * ROWB));
                 if (RGRP * i < nrows && lane_ok) {
+                    CT* crow = cbase + off;
                     if constexpr (MODE == EPI_PLAIN) {
                         f.x = fmaf(f.x, alpha, ba.x); f.y = fmaf(f.y, alpha, ba.y); f.z = fmaf(f.z, alpha, ba.z); f.w = fmaf(f.w, alpha, ba.w);
                         store4<CT>(crow, f);
@@ -377,17 +381,17 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, const Unit& w, 
                         red_add_f32x4(reinterpret_cast<float*>(crow), f);
                     } else {  // EPI_RELU / EPI_SWISH (+ optional pre-activation copy)
                         f.x += b4.x; f.y += b4.y; f.z += b4.z; f.w += b4.w;
-                        if (arow) store4<CT>(arow, f);
+                        if (has_aux) store4<CT>(abase + off, f);
                         if constexpr (MODE == EPI_RELU) {
-                            f.x = alpha * fmaxf(f.x, 0.f); f.y = alpha * fmaxf(f.y, 0.f); f.z = alpha * fmaxf(f.z, 0.f); f.w = alpha * fmaxf(f.w, 0.f);
+                            f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f);
                         } else {
-                            f.x = alpha * swish_fast(f.x); f.y = alpha * swish_fast(f.y); f.z = alpha * swish_fast(f.z); f.w = alpha * swish_fast(f.w);
+                            f.x = swish_fast(f.x); f.y = swish_fast(f.y); f.z = swish_fast(f.z); f.w = swish_fast(f.w);
                         }
+                        if (!unit_alpha) { f.x *= alpha; f.y *= alpha; f.z *= alpha; f.w *= alpha; }
                         store4<CT>(crow, f);
                     }
                 }
-                crow += rstride;
-                if (arow) arow += rstride;
+                off += rstride;
             }
             if constexpr (MODE == EPI_PLAIN || DACT) {
                 if (csbase) {  // warp-uniform: fold the row groups (lanes with the same piece), then one vector red per 4 columns
