@@ -72,6 +72,8 @@ struct TcParams {
     float* colsum;     // colsum[b1*cs1 + b2*cs2 + n] += sum_m C[m, n]
     long cs1, cs2;
     // implicit-GEMM 3x3 stride-2 convolution over parity planes (see conv2_tc_dispatch): only the TMA producer changes
+    int tma_epi;       // epilogue stores through TMA (row-per-thread math, swizzled staging, bulk tensor store / reduce-add)
+    int c_b1, c_b2;    // 1 if C really advances along that batch level (TMA store coordinates)
     int b_stationary;  // K <= 256 GEMMs: every CTA keeps ONE N tile of B resident in shared memory and streams A tiles only
     int bsta_bytes;    // size of that resident tile
     int conv_mode;     // 0 plain GEMM | 1 forward | 2 input gradient (one parity class) | 3 weight gradient
@@ -161,6 +163,20 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"((uint64_t)map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"((uint64_t)map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void red_add_f32x4(float* p, const float4& v) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
@@ -436,6 +452,186 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, const Unit& w, 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// TMA-store epilogue (default whenever C / aux / bias / res / dact meet the 16-byte alignment rules).
+// The accumulator row a thread reads from TMEM (32 consecutive columns) is finished IN PLACE -- bias as warp-uniform float4
+// loads, residual / saved activation as row-contiguous 16-byte loads -- converted, written to a swizzled 32 x 32 staging box
+// (SWIZZLE_64B for bf16, SWIZZLE_128B for fp32: the same XOR patterns that make the row-per-thread 16-byte stores conflict
+// free) and handed to ONE bulk tensor store (or reduce-add) per box.  Compared with the register -> smem -> register ->
+// global column phase this removes every LDS, STG, 64-bit address computation and edge predicate from the 16 epilogue warps
+// (the FFN fc1 + Swish kernel was issue-bound: 59 % issue-slot utilisation, 58 % LSU wavefronts, tensor pipe 21 %); the TMA
+// unit clips rows >= M and columns >= N, so ragged shapes (N = 299, V = 4233) take the same path.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float col_sums_32(float (&v)[32], int lane) {
+    // transpose-reduce: after the five exchange stages lane c holds the sum over the 32 lanes (rows) of column c
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+            const float send = up ? v[i] : v[i + s];
+            const float keep = up ? v[i + s] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    return v[0];
+}
+
+template <typename CT, int MODE>
+__device__ __forceinline__ void epilogue_unit_tma(const TcParams& p, const Unit& w, uint32_t tmem_acc, uint8_t* stage, int q, int part,
+                                                  int lane, const CUtensorMap* mc, const CUtensorMap* mx, int& buf) {
+    constexpr bool BF = sizeof(CT) == 2;
+    constexpr bool DACT = (MODE == EPI_DSWISH || MODE == EPI_DRELU);
+    const long boff = (long)w.b1 * p.sc1 + (long)w.b2 * p.sc2;
+    const int col_limit = min(p.n_store, w.n0 + p.bn);
+    const int row0 = w.m0 + q * 32, row = row0 + lane;
+    const bool row_ok = row < p.m;
+    const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
+    const float alpha = p.alpha;
+    const bool has_aux = p.aux != nullptr;   // warp-uniform
+    const bool dbl = BF && !has_aux;         // two 2 KB boxes alternate; otherwise one 4 KB set (C, or C + aux)
+    const int cb1 = w.b1 * p.c_b1, cb2 = w.b2 * p.c_b2;
+    for (int cc = part * 32; cc < p.bn; cc += 32 * (EPI_WARPS / 4)) {
+        const int col0 = w.n0 + cc;
+        if (col0 >= col_limit) break;  // warp-uniform
+        const bool full = col0 + 32 <= col_limit;
+        // row-wise global operands first (in flight while TMEM is read)
+        float4 r4[MODE == EPI_RES ? 8 : 1];
+        uint4 s4[DACT ? 4 : 1];
+        if constexpr (MODE == EPI_RES) {
+            const float* rp = p.res + boff + (long)row * p.ldres + col0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r4[j] = ldg_pred_f4(rp + 4 * j, row_ok && col0 + 4 * j + 3 < col_limit);
+            if (!full && row_ok && (col_limit & 3)) {  // ragged edge inside a float4: element-wise for that quad
+                const int j = (col_limit - col0) >> 2;
+                float t[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int e = 0; e < (col_limit & 3); ++e) t[e] = rp[4 * j + e];
+                r4[j < 8 ? j : 7] = make_float4(t[0], t[1], t[2], t[3]);
+            }
+        }
+        if constexpr (DACT) {
+            const bf16* sp = p.dact + boff + (long)row * p.lddact + col0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                s4[j] = make_uint4(0u, 0u, 0u, 0u);
+                if (row_ok && col0 + 8 * j + 7 < col_limit) s4[j] = *reinterpret_cast<const uint4*>(sp + 8 * j);
+                else if (row_ok && col0 + 8 * j < col_limit) {
+                    bf16 t[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) t[e] = (col0 + 8 * j + e < col_limit) ? sp[8 * j + e] : __float2bfloat16_rn(0.f);
+                    s4[j] = *reinterpret_cast<const uint4*>(t);
+                }
+            }
+        }
+        float v[32];
+        tc_ld32(taddr + (uint32_t)cc, v);
+        // ---- finish the row in place
+        if constexpr (MODE == EPI_ACC) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= alpha;
+        } else if constexpr (DACT) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&s4[j]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float a0 = __low2float(h[e]), a1 = __high2float(h[e]);
+                    if constexpr (MODE == EPI_DSWISH) {
+                        v[8 * j + 2 * e] *= alpha * dswish_fast(a0);
+                        v[8 * j + 2 * e + 1] *= alpha * dswish_fast(a1);
+                    } else {
+                        v[8 * j + 2 * e] = a0 > 0.f ? alpha * v[8 * j + 2 * e] : 0.f;
+                        v[8 * j + 2 * e + 1] = a1 > 0.f ? alpha * v[8 * j + 2 * e + 1] : 0.f;
+                    }
+                }
+            }
+        } else {
+            // bias: the same 32 floats for every lane (warp-uniform 16-byte loads, L1-resident), consumed quad by quad
+            const bool has_bias = p.bias != nullptr;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (has_bias) {
+                    const int c = col0 + 4 * j;
+                    if (full) {
+                        b = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+                    } else {
+                        b.x = c + 0 < col_limit ? __ldg(p.bias + c + 0) : 0.f;
+                        b.y = c + 1 < col_limit ? __ldg(p.bias + c + 1) : 0.f;
+                        b.z = c + 2 < col_limit ? __ldg(p.bias + c + 2) : 0.f;
+                        b.w = c + 3 < col_limit ? __ldg(p.bias + c + 3) : 0.f;
+                    }
+                }
+                if constexpr (MODE == EPI_PLAIN || MODE == EPI_RES) {
+                    v[4 * j] = fmaf(v[4 * j], alpha, alpha * b.x); v[4 * j + 1] = fmaf(v[4 * j + 1], alpha, alpha * b.y);
+                    v[4 * j + 2] = fmaf(v[4 * j + 2], alpha, alpha * b.z); v[4 * j + 3] = fmaf(v[4 * j + 3], alpha, alpha * b.w);
+                    if constexpr (MODE == EPI_RES) { v[4 * j] += r4[j].x; v[4 * j + 1] += r4[j].y; v[4 * j + 2] += r4[j].z; v[4 * j + 3] += r4[j].w; }
+                } else {  // EPI_RELU / EPI_SWISH: pre-activation = acc + bias
+                    v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+                }
+            }
+        }
+        // ---- staging box free?  (only lane 0 issues bulk stores, so only lane 0 has groups to wait for)
+        uint8_t* sb = stage + (dbl ? buf * 2048 : 0);
+        if (lane == 0) {
+            if (dbl) bulk_wait_read<1>();
+            else bulk_wait_read<0>();
+        }
+        __syncwarp();
+        if constexpr (MODE == EPI_RELU || MODE == EPI_SWISH) {
+            if (has_aux) {  // pre-activation copy (bf16 on this path)
+                uint8_t* sx = stage + 2048;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint4 u;
+                    u.x = pack_bf16x2(v[8 * j], v[8 * j + 1]); u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                    u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                    *reinterpret_cast<uint4*>(sx + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = u;
+                }
+            }
+            const bool unit_alpha = alpha == 1.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float x = (MODE == EPI_RELU) ? fmaxf(v[j], 0.f) : swish_fast(v[j]);
+                v[j] = unit_alpha ? x : alpha * x;
+            }
+        }
+        if constexpr (BF) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint4 u;
+                u.x = pack_bf16x2(v[8 * j], v[8 * j + 1]); u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                *reinterpret_cast<uint4*>(sb + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = u;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(sb + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            if constexpr (MODE == EPI_ACC) tma_reduce_add_4d(mc, sb, col0, row0, cb2, cb1);
+            else tma_store_4d(mc, sb, col0, row0, cb2, cb1);
+            if constexpr (MODE == EPI_RELU || MODE == EPI_SWISH) {
+                if (has_aux) tma_store_4d(mx, stage + 2048, col0, row0, cb2, cb1);
+            }
+            bulk_commit();
+        }
+        if (dbl) buf ^= 1;
+        // ---- bias gradient of the producing Linear: column sums of what was just written (rows >= M excluded)
+        if constexpr (MODE == EPI_PLAIN || DACT) {
+            if (p.colsum) {  // warp-uniform
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = row_ok ? v[j] : 0.f;
+                const float cs = col_sums_32(v, lane);
+                if (col0 + lane < col_limit) atomicAdd(p.colsum + (long)w.b1 * p.cs1 + (long)w.b2 * p.cs2 + col0 + lane, cs);
+            }
+        }
+    }
+}
+
 // Work-unit walk shared by the three roles.  Streaming kernels: units blockIdx.x, + gridDim.x, ... of the (batch, split, m, n)
 // list.  B-stationary kernels: the CTA owns N tile blockIdx.x % tiles_n for its whole life and takes every
 // (gridDim.x / tiles_n)-th M tile (gridDim.x is a multiple of tiles_n).
@@ -476,7 +672,8 @@ struct Walk {
 // at the L2 -> SM bandwidth, not at the tensor or HBM roofline.
 template <int MODE, bool C_F32, bool BS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const TcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+               const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_x, const TcParams p) {
     constexpr int CW = BS ? 16 : 32;
     const bool A_MN = p.a_mn != 0, B_MN = p.b_mn != 0;
     extern __shared__ uint8_t smem_raw[];
@@ -497,6 +694,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tma_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tma_b) : "memory");
+        if (p.tma_epi) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tma_c) : "memory");
+            if (p.aux) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tma_x) : "memory");
+        }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < MAX_STAGES; ++s) {
@@ -629,20 +830,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const int ew = warp - 2;          // private staging slice
         const int part = ew >> 2;         // which CW-column chunks of the tile (chunk index % (EPI_WARPS/4))
         uint8_t* stage = smem + ew * (32 * CW * 4);
-        int as = 0;
+        int as = 0, sbuf = 0;
         uint32_t aph = 0;
         Walk<BS> walk(p);
         Unit w;
+        typedef typename std::conditional<C_F32, float, bf16>::type CT;
+        constexpr bool TMA_OK = !BS && MODE != EPI_GENERIC;
+        const bool tma_epi = TMA_OK && p.tma_epi != 0;
         while (walk.next(p, w)) {
             mbar_wait(acc_full + as, aph);
             tc_fence_after();
             const uint32_t tmem_acc = tmem_base + (uint32_t)(as * ACC_COLS);
-            epilogue_unit<typename std::conditional<C_F32, float, bf16>::type, MODE, CW>(p, w, tmem_acc, stage, q, part, lane);
+            if constexpr (TMA_OK) {
+                if (tma_epi) epilogue_unit_tma<CT, MODE>(p, w, tmem_acc, stage, q, part, lane, &tma_c, &tma_x, sbuf);
+                else epilogue_unit<CT, MODE, CW>(p, w, tmem_acc, stage, q, part, lane);
+            } else {
+                epilogue_unit<CT, MODE, CW>(p, w, tmem_acc, stage, q, part, lane);
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + as);
             if ((as ^= 1) == 0) aph ^= 1;
         }
+        if (tma_epi && lane == 0) bulk_wait_read<0>();  // the staging boxes must outlive the bulk stores that read them
     }
     tc_fence_before();
     __syncthreads();
@@ -705,6 +915,54 @@ static int make_map(CUtensorMap* map, const void* base, long inner, long rows, l
     return LASR_OK;
 }
 
+// C (or the pre-activation copy) as a TMA store target: 32 x 32 boxes, SWIZZLE_64B for bf16 rows (64 B) and SWIZZLE_128B for
+// fp32 rows (128 B).  Returns 1 if the tensor cannot be described (alignment): the caller then keeps the register epilogue.
+static int make_store_map(CUtensorMap* map, const void* base, int dtype, long cols, long rows, long ld, int nb2, long s2, int nb1,
+                          long s1) {
+    auto enc = get_encode();
+    if (!enc || !base) return 1;
+    const long es = dtype == LASR_F32 ? 4 : 2;
+    const bool use2 = (s2 != 0 && nb2 > 1), use1 = (s1 != 0 && nb1 > 1);
+    cuuint64_t dims[4] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)(use2 ? nb2 : 1), (cuuint64_t)(use1 ? nb1 : 1)};
+    const cuuint64_t row_bytes = (cuuint64_t)ld * es;
+    cuuint64_t strides[3] = {row_bytes, use2 ? (cuuint64_t)s2 * es : row_bytes, use1 ? (cuuint64_t)s1 * es : row_bytes};
+    cuuint32_t box[4] = {32, 32, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (strides[0] & 15) || (strides[1] & 15) || (strides[2] & 15)) return 1;
+    CUresult r = enc(map, dtype == LASR_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                     const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     dtype == LASR_F32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : 1;
+}
+
+// Decide whether the TMA-store epilogue applies and build its maps (C and, if present, the pre-activation copy).
+static void setup_tma_epilogue(TcParams& p, CUtensorMap* mc, CUtensorMap* mx, int nb1, int nb2) {
+    memset(mc, 0, sizeof(*mc));
+    memset(mx, 0, sizeof(*mx));
+    p.tma_epi = 0;
+    p.c_b1 = (p.sc1 != 0 && nb1 > 1);
+    p.c_b2 = (p.sc2 != 0 && nb2 > 1);
+    const char* env = getenv("LASR_GEMM_TMA_EPI");  // developer switch (read per call so that tests can toggle it)
+    if (env && atoi(env) == 0) return;
+    if (p.epi_mode == EPI_GENERIC || p.b_stationary) return;
+    // Row-per-thread math makes the residual / saved-activation reads 32-lines-per-instruction gathers and the column sums a
+    // 31-shuffle transpose: measured slower than the column-phase epilogue (fc2 + residual 62 vs 51 us, dswish + colsum 128 vs
+    // 103 us at C2/B=126), so those modes keep it.  LASR_GEMM_TMA_EPI=2 forces the TMA path for every mode (tests).
+    const bool force = env && atoi(env) == 2;
+    if (!force && (p.epi_mode == EPI_RES || p.epi_mode == EPI_DSWISH || p.epi_mode == EPI_DRELU || p.colsum)) return;
+    // bulk tensor stores clip at 16-byte granularity (measured: tools/tma_clip_probe.py): a row whose last 16-byte chunk is
+    // partial would get zeros written past column n_store, so ragged widths keep the register epilogue
+    if (((long)p.n_store * (p.c_dtype == LASR_F32 ? 4 : 2)) & 15) return;
+    if (p.aux && p.c_dtype == LASR_F32) return;                        // the staging set holds C + aux only for bf16
+    if (p.bias && (reinterpret_cast<uintptr_t>(p.bias) & 15)) return;
+    if (p.res && ((reinterpret_cast<uintptr_t>(p.res) & 15) || (p.ldres & 3) || (p.sc1 & 3) || (p.sc2 & 3))) return;
+    if (p.dact && ((reinterpret_cast<uintptr_t>(p.dact) & 15) || (p.lddact & 7) || (p.sc1 & 7) || (p.sc2 & 7))) return;
+    if (make_store_map(mc, p.c, p.c_dtype, p.n_store, p.m, p.ldc, nb2, p.sc2, nb1, p.sc1)) return;
+    if (p.aux && make_store_map(mx, p.aux, p.c_dtype, p.n_store, p.m, p.ldc, nb2, p.sc2, nb1, p.sc1)) return;
+    p.tma_epi = 1;
+}
+
 // N-tile width: a multiple of `gran` (16 for K-major B, 64 for MN-major B) up to 256 that wastes the fewest padded
 // columns; ties go to the wider tile (fewer A re-reads, fewer epilogue tails).
 static int pick_bn(int n, int gran) {
@@ -718,7 +976,7 @@ static int pick_bn(int n, int gran) {
     return best;
 }
 
-typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, const TcParams);
+typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams);
 
 template <int MODE, bool C_F32, bool BS>
 static TcKernel configured_kernel() {
@@ -755,7 +1013,8 @@ static TcKernel pick_kernel(int mode, bool f32) {
     }
 }
 
-static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st) {
+static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mx, const TcParams& p,
+                     cudaStream_t st) {
     const bool f32 = p.c_dtype == LASR_F32;
     TcKernel kern = p.b_stationary ? pick_kernel<true>(p.epi_mode, f32) : pick_kernel<false>(p.epi_mode, f32);
     if (!kern) return check_launch("gemm_tc smem attr");
@@ -767,13 +1026,14 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParam
         smem_bytes = SM_RING + p.stages * p.stage_bytes + 1024;
         grid = p.total_units < sm_count() ? p.total_units : sm_count();
     }
-    kern<<<grid, GEMM_THREADS, smem_bytes, st>>>(ma, mb, p);
+    kern<<<grid, GEMM_THREADS, smem_bytes, st>>>(ma, mb, mc, mx, p);
     return check_launch("gemm_tc");
 }
 
 int gemm_tc_dispatch(const lasr_gemm_args* a, cudaStream_t st) {
     const int n_store = a->n_store ? a->n_store : a->n;
-    const int bn = pick_bn(n_store, a->trans_b ? 64 : 16);
+    // N tiles are multiples of 32 columns: the TMA-store epilogue writes whole 32-column boxes, clipped only at the tensor edge
+    const int bn = pick_bn(n_store, a->trans_b ? 64 : 32);
     CUtensorMap ma, mb;
     int rc;
     if (!a->trans_a) rc = make_map(&ma, a->a, a->k, a->m, a->lda, a->batch2, a->sa2, a->batch1, a->sa1, BK, BM);
@@ -856,7 +1116,9 @@ int gemm_tc_dispatch(const lasr_gemm_args* a, cudaStream_t st) {
             }
         }
     }
-    return launch_tc(ma, mb, p, st);
+    CUtensorMap mc, mx;
+    setup_tma_epilogue(p, &mc, &mx, a->batch1, a->batch2);
+    return launch_tc(ma, mb, mc, mx, p, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -944,7 +1206,9 @@ int conv2_tc_dispatch(int mode, int plane_class, const void* h1p, const void* w2
         return LASR_ERR_UNSUPPORTED;
     }
     p.total_units = (int)units;
-    return launch_tc(ma, mb, p, st);
+    CUtensorMap mc, mx;
+    setup_tma_epilogue(p, &mc, &mx, B, 1);
+    return launch_tc(ma, mb, mc, mx, p, st);
 }
 
 }  // namespace lasr
