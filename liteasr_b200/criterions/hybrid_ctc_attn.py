@@ -50,6 +50,22 @@ class HybridCTCLoss(LiteasrLoss):
         h_attn, h_ctc = model(xs, xlens, ys, ylens)
         return self.loss_from_logits(inner, h_attn, h_ctc, xlens, ys, ylens)
 
+    def direct_step(self, model, xs, xlens, ys, ylens):
+        """Forward + backward of the fused step WITHOUT autograd, for stores in direct-gradient mode (`TrainStep`): the
+        gradients land in the flat buffer, the detached loss is returned.  Returns None when the fused path does not apply
+        (the caller then uses ``loss = self(...); loss.backward()``).  Keeping autograd out of a CUDA-graph capture matters: the
+        engine's end-of-backward stream sync waits on every stream an older, still-alive graph of the same leaves ran on, which
+        is illegal while capturing."""
+        inner = getattr(model, "module", model)
+        inner = getattr(inner, "module", inner)
+        from ..models.u2 import U2
+        if not (isinstance(inner, U2) and self.cfg.padding_idx == inner.ignore):
+            return None
+        st, _, _ = F.bind(inner, xs.device)
+        if not st.direct_grads:
+            return None
+        return F.hybrid_direct_step(inner, float(self.cfg.ctc_weight), float(self.cfg.smoothing), xs, xlens, ys, ylens)
+
     def loss_from_logits(self, model, h_attn, h_ctc, xlens, ys, ylens):
         b = ys.size(0)
         row_kl = F.LabelSmoothingFn.apply(h_attn, ys, ylens, float(self.cfg.smoothing))

@@ -250,3 +250,19 @@ class HybridLossFn(torch.autograd.Function):
             st._keepalive_all = views
             pg = tuple(views)
         return (None,) * 8 + pg
+
+
+class _PlainCtx:
+    """Attribute bag standing in for the autograd context when HybridLossFn's forward/backward are called directly."""
+
+
+def hybrid_direct_step(model, ctc_weight: float, smoothing: float, xs, xlens, ys, ylens) -> torch.Tensor:
+    """HybridLossFn forward + backward with no autograd graph (direct-gradient stores only): parameter gradients are written
+    to the store's flat gradient buffer by the kernels; returns the detached loss (model.last_losses holds the parts)."""
+    ctx = _PlainCtx()
+    with torch.no_grad():
+        loss = HybridLossFn.forward(ctx, model, ctc_weight, smoothing, xs, xlens, ys, ylens, None)
+        if not ctx.st.direct_grads:
+            raise RuntimeError("hybrid_direct_step needs a store in direct-gradient mode (TrainStep enables it)")
+        HybridLossFn.backward(ctx, None)
+    return loss

@@ -51,8 +51,11 @@ class TrainStep:
             if self.ddp is not None:
                 self.ddp.sync_grads = last  # no_sync on all but the last micro-step (trainer.py:142-145)
                 self.ddp.begin_backward()
-            loss = self.criterion(self.model, xs, xlens, ys, ylens)
-            loss.backward()
+            direct = getattr(self.criterion, "direct_step", None)
+            loss = direct(self.model, xs, xlens, ys, ylens) if direct is not None else None
+            if loss is None:  # generic criterion / model: through autograd
+                loss = self.criterion(self.model, xs, xlens, ys, ylens)
+                loss.backward()
             total = loss.detach() if total is None else total + loss.detach()
         mult = self.ddp.finish_backward() if self.ddp is not None else 1.0
         self.optimizer.step(self.clip, grad_mult=mult)

@@ -146,3 +146,25 @@ def test_state_dict_schema_matches_reference():
     want = {n: tuple(s) for n, s, _ in u2_schema(dims)}
     got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
     assert got == want
+
+
+def test_graph_step_after_eager_autograd_use():
+    """TrainStep's CUDA-graph capture must not depend on what ran before: an earlier eager autograd step whose graph is STILL
+    ALIVE (its AccumulateGrad nodes carry the default stream) used to invalidate the capture through the autograd engine's
+    end-of-backward stream sync.  The captured step now bypasses autograd (criterion.direct_step)."""
+    from liteasr_b200.trainer import TrainStep
+    g, dims, batch, sd, model, crit = _setup("tiny", "bf16")
+    dev_batch = [t.cuda() for t in batch]
+    keep_alive = crit(model, *dev_batch)       # autograd mode, graph kept alive on purpose
+    keep_alive.backward(retain_graph=True)
+    torch.cuda.synchronize()
+    g2, _, _, _, model2, _ = _setup("tiny", "fp32")
+    keep2 = crit(model2, *dev_batch)
+    keep2.backward(retain_graph=True)
+    torch.cuda.synchronize()
+    step = TrainStep(model2, crit, device=torch.device("cuda:0"))
+    l0 = float(step(*dev_batch))
+    l1 = float(step(*dev_batch))
+    assert math.isfinite(l0) and math.isfinite(l1) and l1 != l0
+    assert math.isclose(l0, float(keep2), rel_tol=1e-4)  # first graph step = same parameters as the eager call
+    del keep_alive, keep2
