@@ -168,3 +168,26 @@ def test_graph_step_after_eager_autograd_use():
     assert math.isfinite(l0) and math.isfinite(l1) and l1 != l0
     assert math.isclose(l0, float(keep2), rel_tol=1e-4)  # first graph step = same parameters as the eager call
     del keep_alive, keep2
+
+
+def test_checkpoint_save_average_and_reload(tmp_path):
+    """`model.save` files (models/__init__.py:31-32) average through `utils.checkpoint.load_ckpt` and load back with
+    strict=True; averaging a checkpoint with itself is the identity (same greedy CTC tokens)."""
+    import os
+    import time
+    from types import SimpleNamespace
+    from liteasr_b200.models.u2 import U2, U2Config
+    from liteasr_b200.utils.checkpoint import load_ckpt
+    g, dims, batch, sd, model, crit = _setup("tiny", "fp32")
+    xs, xlens = batch[0].cuda(), batch[1].cuda()
+    model.eval()
+    want, _ = model.greedy_ctc(xs, xlens)
+    for i in (1, 2):
+        p = tmp_path / f"model.ep.{i}.pt"
+        model.save(str(p))
+        os.utime(p, (time.time() + i, time.time() + i))
+    avg = load_ckpt(SimpleNamespace(ckpt_path=str(tmp_path), ckpt_name=2, model_avg=True, avg_num=2, avg_policy=None))
+    fresh = U2(U2Config(**{**g["dims"], "precision": "fp32"}))
+    fresh.load_state_dict(avg, strict=True)
+    got, _ = fresh.cuda().eval().greedy_ctc(xs, xlens)
+    assert got == want
