@@ -259,6 +259,18 @@ int lasr_gather_logp(const void* logits, int dtype, int64_t ld, const float* lse
 int lasr_ctc_prefix_beam_search(const float* topk_logp, const int32_t* topk_idx, int frames, int K, int beam, int blank,
                                 int32_t* out_tokens, int32_t* out_lens, double* out_scores, int max_len, int32_t* n_out);
 
+/* ------------------------------------------------------------------------------------------------
+ * SpecAugment on a padded batch (utils/transform/spec_augment.py:19-125), out of place.
+ *   x, y   : (B, ld_batch / F rows, F) fp32, utterance b occupies rows [0, T_b)
+ *   params : int32 (B, lasr_spec_augment_npar()) = {T_b, center, warped, n_freq, n_time, 8 x (lo, hi) frequency masks,
+ *            8 x (lo, hi) time masks}; center < 0 = no time warp.  The decisions are drawn on the host in the reference's
+ *            RNG order; the kernel reproduces PIL's BICUBIC resize (mode "F") bit for bit and fills the masks, in order, with
+ *            the mean of the array at that moment (replace_with_zero = 0) or zero.
+ * ------------------------------------------------------------------------------------------------ */
+int lasr_spec_augment_npar(void);
+int lasr_spec_augment(const float* x, float* y, int64_t ld_batch, int F, const int32_t* params, int B, int replace_with_zero,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

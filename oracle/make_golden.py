@@ -167,6 +167,43 @@ def ctc_cases():
     return cases
 
 
+SPECAUG_CASES = [
+    # seed, T, F, time_warp, freq_mask, freq_mask_times, time_mask, time_mask_times, replace_with_zero, store full output
+    (0, 40, 12, 5, 6, 2, 10, 2, False, True),
+    (1, 200, 80, 80, 27, 1, 100, 1, False, False),   # reference defaults (config/__init__.py:43-51)
+    (2, 170, 80, 80, 27, 2, 100, 2, False, False),
+    (3, 300, 40, 30, 10, 2, 40, 3, True, False),
+    (4, 100, 80, 80, 27, 1, 100, 1, False, False),   # too short for the warp (t - window <= window)
+    (5, 161, 23, 80, 8, 2, 50, 2, False, True),      # shortest warpable length: extreme scale factors
+    (6, 500, 80, 80, 27, 2, 100, 2, False, False),
+]
+
+
+def specaug_cases():
+    """Outputs of the UNMODIFIED reference SpecAugment (utils/transform/spec_augment.py) under seeded `random` / `numpy.random`
+    on seeded inputs (torch.randn(T, F, generator=seed) * 3 + 1)."""
+    import importlib
+    import random
+    from types import SimpleNamespace
+    ref_shims.install()
+    mod = importlib.import_module("liteasr.utils.transform.spec_augment")
+    import PIL
+    out = []
+    for seed, T, F, tw, fm, fmt, tm, tmt, rz, full in SPECAUG_CASES:
+        cfg = SimpleNamespace(time_warp=tw, freq_mask=fm, freq_mask_times=fmt, time_mask=tm, time_mask_times=tmt, inplace=True,
+                              replace_with_zero=rz)
+        x = torch.randn(T, F, generator=torch.Generator().manual_seed(seed)) * 3 + 1
+        random.seed(seed)
+        np.random.seed(seed)
+        y = mod.SpecAugment(cfg)(x.clone())
+        rec = dict(seed=seed, T=T, F=F, cfg=vars(cfg), sum=float(y.double().sum()), abs_sum=float(y.double().abs().sum()),
+                   head=y.flatten()[:16].tolist(), sample=y.flatten()[:: max(1, y.numel() // 61)].tolist())
+        if full:
+            rec["full"] = y.tolist()
+        out.append(rec)
+    return dict(pillow=PIL.__version__, numpy=np.__version__, cases=out)
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     for name in MODEL_CASES:
@@ -176,6 +213,8 @@ def main():
         print(name, "loss f64", rec["f64"]["loss"], "f32", rec["f32"]["loss"])
     with open(os.path.join(GOLDEN_DIR, "ctc_golden.json"), "w") as f:
         json.dump(dict(torch=torch.__version__, cases=ctc_cases()), f)
+    with open(os.path.join(GOLDEN_DIR, "specaug.json"), "w") as f:
+        json.dump(specaug_cases(), f)
     print("golden written to", GOLDEN_DIR)
 
 
