@@ -214,13 +214,14 @@ int lasr_conv2_wgrad(const void* dy2p, const void* h1p, float* dw2k, int B, int 
  * Attention score post-processing (nets/attention.py:46-59,99-118,145-152): legacy rel_shift of bd
  * (NULL for plain attention) + scale + key/causal mask (-1e38 fill) + softmax, and the backward
  * (dscores = p*(dp - sum p*dp)*scale; dbd = inverse shift of dscores, NULL for plain attention).
- * ac/bd/dprobs fp32 (B,H,Tq,ld); probs/dscores/dbd fp32|bf16 (B,H,Tq,ld); columns [Tk,ld) are zeroed.
+ * ac/bd/dprobs (B,H,Tq,ld) of s_dtype: fp32, or bf16 when probs are bf16 (what torch autocast's matmul hands to the softmax;
+ * halves the score traffic); probs/dscores/dbd fp32|bf16 (B,H,Tq,ld); columns [Tk,ld) are zeroed.
  * mask_mode: 0 none | 1 klen=lens[b] | 2 klen=lens[b]+1 | 3 klen=#{j: 4j<lens[b]} (encoder sub-sampled mask).
  * ------------------------------------------------------------------------------------------------ */
-int lasr_attn_softmax_fwd(const float* ac, const float* bd, void* probs, int p_dtype, const int64_t* lens, int mask_mode, int causal,
-                          float scale, int B, int H, int Tq, int Tk, int ld, void* stream);
-int lasr_attn_softmax_bwd(const void* probs, const float* dprobs, void* dscores, void* dbd, int dtype, float scale, int B, int H, int Tq,
-                          int Tk, int ld, void* stream);
+int lasr_attn_softmax_fwd(const void* ac, const void* bd, int s_dtype, void* probs, int p_dtype, const int64_t* lens, int mask_mode,
+                          int causal, float scale, int B, int H, int Tq, int Tk, int ld, void* stream);
+int lasr_attn_softmax_bwd(const void* probs, const void* dprobs, int s_dtype, void* dscores, void* dbd, int dtype, float scale, int B,
+                          int H, int Tq, int Tk, int ld, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Label-smoothed KL on the decoder logits, forward + gradient (criterions/hybrid_ctc_attn.py:49-64;

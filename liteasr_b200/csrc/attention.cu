@@ -39,8 +39,8 @@ template <> __device__ __forceinline__ float2 load_pair<bf16>(const bf16* p) {
 
 // One warp per score row; lane l owns the column pairs (2l + 64e, 2l + 64e + 1), e < NP (Tk <= 64 NP): 64-bit loads of ac,
 // 32/64-bit stores of the probabilities, NP sized to the problem so the kernel runs at full occupancy.  ld must be even.
-template <typename TP, int NP>
-__global__ void __launch_bounds__(256) attn_softmax_fwd_kernel(const float* __restrict__ ac, const float* __restrict__ bd,
+template <typename TP, typename TS, int NP>
+__global__ void __launch_bounds__(256) attn_softmax_fwd_kernel(const TS* __restrict__ ac, const TS* __restrict__ bd,
                                                                TP* __restrict__ probs, const int64_t* __restrict__ lens,
                                                                int mask_mode, int causal, float scale, int B, int H, int Tq,
                                                                int Tk, int ld) {
@@ -50,8 +50,8 @@ __global__ void __launch_bounds__(256) attn_softmax_fwd_kernel(const float* __re
     const int i = (int)(row % Tq);
     const int b = (int)(row / ((long)H * Tq));
     const int klen = key_len(lens, mask_mode, b, Tk);
-    const float* ar = ac + row * ld;
-    const float* br = bd ? bd + row * ld : nullptr;  // bd row i of the same (b,h); row i+1 is br + ld
+    const TS* ar = ac + row * ld;
+    const TS* br = bd ? bd + row * ld : nullptr;  // bd row i of the same (b,h); row i+1 is br + ld
     float2 s[NP];
     float mx = -INFINITY;
 #pragma unroll
@@ -59,12 +59,12 @@ __global__ void __launch_bounds__(256) attn_softmax_fwd_kernel(const float* __re
         const int j = 2 * lane + 64 * e;
         s[e] = make_float2(-INFINITY, -INFINITY);
         if (j < Tk) {
-            float2 v = *reinterpret_cast<const float2*>(ar + j);
+            float2 v = load_pair<TS>(ar + j);
             const bool two = j + 1 < Tk;
             if (br) {
                 // legacy rel_shift: bd[i, Tk-1-(i-j)] (j <= i) | 0 (j == i+1) | bd[i+1, j-i-2] (j > i+1)
-                v.x += (j <= i) ? br[Tk - 1 - i + j] : ((j > i + 1) ? br[ld + j - i - 2] : 0.f);
-                if (two) v.y += (j + 1 <= i) ? br[Tk - i + j] : ((j > i) ? br[ld + j - i - 1] : 0.f);
+                v.x += (j <= i) ? to_f32<TS>(br[Tk - 1 - i + j]) : ((j > i + 1) ? to_f32<TS>(br[ld + j - i - 2]) : 0.f);
+                if (two) v.y += (j + 1 <= i) ? to_f32<TS>(br[Tk - i + j]) : ((j > i) ? to_f32<TS>(br[ld + j - i - 1]) : 0.f);
             }
             v.x *= scale; v.y *= scale;
             if (j >= klen || (causal && j > i)) v.x = MASK_FILL;
@@ -95,15 +95,15 @@ __global__ void __launch_bounds__(256) attn_softmax_fwd_kernel(const float* __re
 // ds = p * (dp - sum_j p dp) * scale, written to dsc in place of the score gradient AND (rel-pos attention) scattered through
 // the inverse of the legacy shift into dbd: ds[i, j <= i] -> dbd[i, Tk-1-i+j], ds[i, j >= i+2] -> dbd[i+1, j-i-2]; every
 // element of a dbd row is written exactly once (row r = [tail of ds row r-1 | head of ds row r]; row 0 starts with zeros).
-template <typename TP, int NP>
-__global__ void __launch_bounds__(256) attn_softmax_bwd_kernel(const TP* __restrict__ probs, const float* __restrict__ dprobs,
+template <typename TP, typename TS, int NP>
+__global__ void __launch_bounds__(256) attn_softmax_bwd_kernel(const TP* __restrict__ probs, const TS* __restrict__ dprobs,
                                                                TP* __restrict__ dsc, TP* __restrict__ dbd, float scale, long rows,
                                                                int Tq, int Tk, int ld) {
     const int lane = threadIdx.x & 31;
     const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= rows) return;
     const TP* pr = probs + row * ld;
-    const float* dr = dprobs + row * ld;
+    const TS* dr = dprobs + row * ld;
     float2 p[NP], g[NP];
     float dot = 0.f;
 #pragma unroll
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) attn_softmax_bwd_kernel(const TP* __restr
         p[e] = make_float2(0.f, 0.f); g[e] = make_float2(0.f, 0.f);
         if (j < Tk) {
             p[e] = load_pair<TP>(pr + j);
-            g[e] = *reinterpret_cast<const float2*>(dr + j);
+            g[e] = load_pair<TS>(dr + j);
             if (j + 1 >= Tk) { p[e].y = 0.f; g[e].y = 0.f; }
             dot += p[e].x * g[e].x + p[e].y * g[e].y;
         }
@@ -154,17 +154,17 @@ __global__ void __launch_bounds__(256) attn_softmax_bwd_kernel(const TP* __restr
 extern "C" {
 using namespace lasr;
 
-#define LASR_SM_DISPATCH(KERNEL, TP, ...)                                            \
+#define LASR_SM_DISPATCH(KERNEL, TP, TS, ...)                                        \
     do {                                                                             \
-        if (Tk <= 64) KERNEL<TP, 1><<<grid, 256, 0, st>>>(__VA_ARGS__);              \
-        else if (Tk <= 128) KERNEL<TP, 2><<<grid, 256, 0, st>>>(__VA_ARGS__);        \
-        else if (Tk <= 320) KERNEL<TP, 5><<<grid, 256, 0, st>>>(__VA_ARGS__);        \
-        else if (Tk <= 448) KERNEL<TP, 7><<<grid, 256, 0, st>>>(__VA_ARGS__);        \
-        else KERNEL<TP, SM_MAXP><<<grid, 256, 0, st>>>(__VA_ARGS__);                 \
+        if (Tk <= 64) KERNEL<TP, TS, 1><<<grid, 256, 0, st>>>(__VA_ARGS__);          \
+        else if (Tk <= 128) KERNEL<TP, TS, 2><<<grid, 256, 0, st>>>(__VA_ARGS__);    \
+        else if (Tk <= 320) KERNEL<TP, TS, 5><<<grid, 256, 0, st>>>(__VA_ARGS__);    \
+        else if (Tk <= 448) KERNEL<TP, TS, 7><<<grid, 256, 0, st>>>(__VA_ARGS__);    \
+        else KERNEL<TP, TS, SM_MAXP><<<grid, 256, 0, st>>>(__VA_ARGS__);             \
     } while (0)
 
-int lasr_attn_softmax_fwd(const float* ac, const float* bd, void* probs, int p_dtype, const int64_t* lens, int mask_mode, int causal,
-                          float scale, int B, int H, int Tq, int Tk, int ld, void* stream) {
+int lasr_attn_softmax_fwd(const void* ac, const void* bd, int s_dtype, void* probs, int p_dtype, const int64_t* lens, int mask_mode,
+                          int causal, float scale, int B, int H, int Tq, int Tk, int ld, void* stream) {
     LASR_REQUIRE(ac && probs && B > 0 && H > 0 && Tq > 0 && Tk > 0 && ld >= Tk && ld <= 64 * SM_MAXP && ld % 2 == 0,
                  "attn_softmax_fwd: bad args (Tk <= ld <= 1024, ld even)");
     LASR_REQUIRE(!bd || Tq == Tk, "attn_softmax_fwd: rel_shift needs Tq == Tk");
@@ -173,14 +173,18 @@ int lasr_attn_softmax_fwd(const float* ac, const float* bd, void* probs, int p_d
     const long rows = (long)B * H * Tq;
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = ceil_div(rows, 8);
-    if (p_dtype == LASR_F32) LASR_SM_DISPATCH(attn_softmax_fwd_kernel, float, ac, bd, (float*)probs, lens, mask_mode, causal, scale, B, H, Tq, Tk, ld);
-    else if (p_dtype == LASR_BF16) LASR_SM_DISPATCH(attn_softmax_fwd_kernel, bf16, ac, bd, (bf16*)probs, lens, mask_mode, causal, scale, B, H, Tq, Tk, ld);
-    else { set_error("attn_softmax_fwd: bad dtype"); return LASR_ERR_UNSUPPORTED; }
+    if (p_dtype == LASR_F32 && s_dtype == LASR_F32)
+        LASR_SM_DISPATCH(attn_softmax_fwd_kernel, float, float, (const float*)ac, (const float*)bd, (float*)probs, lens, mask_mode, causal, scale, B, H, Tq, Tk, ld);
+    else if (p_dtype == LASR_BF16 && s_dtype == LASR_F32)
+        LASR_SM_DISPATCH(attn_softmax_fwd_kernel, bf16, float, (const float*)ac, (const float*)bd, (bf16*)probs, lens, mask_mode, causal, scale, B, H, Tq, Tk, ld);
+    else if (p_dtype == LASR_BF16 && s_dtype == LASR_BF16)
+        LASR_SM_DISPATCH(attn_softmax_fwd_kernel, bf16, bf16, (const bf16*)ac, (const bf16*)bd, (bf16*)probs, lens, mask_mode, causal, scale, B, H, Tq, Tk, ld);
+    else { set_error("attn_softmax_fwd: unsupported dtype combination"); return LASR_ERR_UNSUPPORTED; }
     return check_launch("attn_softmax_fwd");
 }
 
-int lasr_attn_softmax_bwd(const void* probs, const float* dprobs, void* dscores, void* dbd, int dtype, float scale, int B, int H, int Tq,
-                          int Tk, int ld, void* stream) {
+int lasr_attn_softmax_bwd(const void* probs, const void* dprobs, int s_dtype, void* dscores, void* dbd, int dtype, float scale, int B,
+                          int H, int Tq, int Tk, int ld, void* stream) {
     LASR_REQUIRE(probs && dprobs && dscores && B > 0 && H > 0 && Tq > 0 && Tk > 0 && ld >= Tk && ld <= 64 * SM_MAXP && ld % 2 == 0,
                  "attn_softmax_bwd: bad args");
     LASR_REQUIRE(!dbd || Tq == Tk, "attn_softmax_bwd: rel_shift needs Tq == Tk");
@@ -188,9 +192,13 @@ int lasr_attn_softmax_bwd(const void* probs, const float* dprobs, void* dscores,
     const long rows = (long)B * H * Tq;
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = ceil_div(rows, 8);
-    if (dtype == LASR_F32) LASR_SM_DISPATCH(attn_softmax_bwd_kernel, float, (const float*)probs, dprobs, (float*)dscores, (float*)dbd, scale, rows, Tq, Tk, ld);
-    else if (dtype == LASR_BF16) LASR_SM_DISPATCH(attn_softmax_bwd_kernel, bf16, (const bf16*)probs, dprobs, (bf16*)dscores, (bf16*)dbd, scale, rows, Tq, Tk, ld);
-    else { set_error("attn_softmax_bwd: bad dtype"); return LASR_ERR_UNSUPPORTED; }
+    if (dtype == LASR_F32 && s_dtype == LASR_F32)
+        LASR_SM_DISPATCH(attn_softmax_bwd_kernel, float, float, (const float*)probs, (const float*)dprobs, (float*)dscores, (float*)dbd, scale, rows, Tq, Tk, ld);
+    else if (dtype == LASR_BF16 && s_dtype == LASR_F32)
+        LASR_SM_DISPATCH(attn_softmax_bwd_kernel, bf16, float, (const bf16*)probs, (const float*)dprobs, (bf16*)dscores, (bf16*)dbd, scale, rows, Tq, Tk, ld);
+    else if (dtype == LASR_BF16 && s_dtype == LASR_BF16)
+        LASR_SM_DISPATCH(attn_softmax_bwd_kernel, bf16, bf16, (const bf16*)probs, (const bf16*)dprobs, (bf16*)dscores, (bf16*)dbd, scale, rows, Tq, Tk, ld);
+    else { set_error("attn_softmax_bwd: unsupported dtype combination"); return LASR_ERR_UNSUPPORTED; }
     return check_launch("attn_softmax_bwd");
 }
 

@@ -15,6 +15,7 @@ Reference lines restated by each block are cited inline (paths relative to /root
 from __future__ import annotations
 
 import math
+import os
 from types import SimpleNamespace as NS
 from typing import Optional
 
@@ -40,6 +41,9 @@ class Engine:
     def __init__(self, store: ParamStore):
         self.st = store
         self.adt = store.adt
+        # attention score tensors (ac, bd, dprobs): fp32, or the operand dtype with LASR_SCORES_BF16=1 (bf16 mode only) -- what torch
+        # autocast's matmul hands to the softmax; halves the score traffic at a bf16 rounding of the pre-softmax logits
+        self.sdt = store.adt if (store.adt == torch.bfloat16 and os.environ.get("LASR_SCORES_BF16", "0") == "1") else torch.float32
         self.dev = store.device
 
     # ------------------------------------------------------------------------------------------
@@ -178,13 +182,13 @@ class Engine:
         d = H * dk
         ld = _ceil(Tk, 8)
         scale = dk ** -0.5
-        ac = _empty((B, H, Tq, ld), torch.float32, self.dev)
+        ac = _empty((B, H, Tq, ld), self.sdt, self.dev)
         # n_store = ld: the padding columns [Tk, ld) are written too (zeros), which keeps the whole epilogue on the vector path
         ops.gemm(q, k, ac, Tq, Tk, dk, lda=q.stride(0), ldb=k.stride(0), ldc=ld, batch=(B, H), sa=(Tq * q.stride(0), dk),
                  sb=(Tk * k.stride(0), dk), sc=(H * Tq * ld, Tq * ld), n_store=ld)
         bd = None
         if qv is not None:  # rel-pos term (q + v_bias) . P^T, P broadcast over the batch
-            bd = _empty((B, H, Tq, ld), torch.float32, self.dev)
+            bd = _empty((B, H, Tq, ld), self.sdt, self.dev)
             ops.gemm(qv, p, bd, Tq, Tk, dk, lda=qv.stride(0), ldb=p.stride(0), ldc=ld, batch=(B, H),
                      sa=(Tq * qv.stride(0), dk), sb=(0, dk), sc=(H * Tq * ld, Tq * ld), n_store=ld)
         probs = _empty((B, H, Tq, ld), self.adt, self.dev)
@@ -199,7 +203,7 @@ class Engine:
         bq/bk/bv: bias-gradient vectors (d,) of the q/k/v projections, accumulated in the GEMM epilogues (head h -> [h*dk, (h+1)*dk))."""
         B, H, Tq, Tk, dk, ld = c.B, c.H, c.Tq, c.Tk, c.dk, c.ld
         bs = (H * Tq * ld, Tq * ld)
-        dprobs = _empty((B, H, Tq, ld), torch.float32, self.dev)
+        dprobs = _empty((B, H, Tq, ld), self.sdt, self.dev)
         ops.gemm(do, c.v, dprobs, Tq, Tk, dk, lda=do.stride(0), ldb=c.v.stride(0), ldc=ld, batch=(B, H), sa=(Tq * do.stride(0), dk),
                  sb=(Tk * c.v.stride(0), dk), sc=bs, n_store=ld)
         # dV[j] = sum_i probs[i,j] dO[i]

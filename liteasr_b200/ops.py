@@ -325,14 +325,15 @@ def conv2_wgrad(dy2p, h1p, dw2k, B, T, F):
 
 def attn_softmax_fwd(ac, bd, probs, lens, mask_mode, causal, scale, Tk):
     B, H, Tq, ld = ac.shape
-    _lib.check(_lib.lib().lasr_attn_softmax_fwd(_ptr(ac), _ptr(bd), _ptr(probs), _i(dtype_code(probs)), _ptr(lens), _i(mask_mode),
+    assert bd is None or bd.dtype == ac.dtype
+    _lib.check(_lib.lib().lasr_attn_softmax_fwd(_ptr(ac), _ptr(bd), _i(dtype_code(ac)), _ptr(probs), _i(dtype_code(probs)), _ptr(lens), _i(mask_mode),
                                                 _i(causal), _f(scale), _i(B), _i(H), _i(Tq), _i(Tk), _i(ld), _stream()),
                "attn_softmax_fwd")
 
 
 def attn_softmax_bwd(probs, dprobs, dsc, dbd, scale, Tk):
     B, H, Tq, ld = probs.shape
-    _lib.check(_lib.lib().lasr_attn_softmax_bwd(_ptr(probs), _ptr(dprobs), _ptr(dsc), _ptr(dbd), _i(dtype_code(probs)), _f(scale),
+    _lib.check(_lib.lib().lasr_attn_softmax_bwd(_ptr(probs), _ptr(dprobs), _i(dtype_code(dprobs)), _ptr(dsc), _ptr(dbd), _i(dtype_code(probs)), _f(scale),
                                                 _i(B), _i(H), _i(Tq), _i(Tk), _i(ld), _stream()), "attn_softmax_bwd")
 
 
