@@ -339,7 +339,7 @@ def run_gpu(args, wl):
         "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": wl["desc"], "global_batch": wl["batch"] * world, "audio_s_per_step": audio, "parallelism": f"dp{world}",
                    "frame_shift_ms": 10, "cuda_graph": bool(step.use_graph),
-                   "l2": "per-step working set (>1 GB of activations, 162 MB of CTC logits) exceeds the 126 MB L2; no explicit flush"},
+                   "l2": f"per-step working set (several GB of activations, {wl['batch'] * 299 * 4240 * 2 // 1000000} MB of CTC logits) exceeds the 126 MB L2; no explicit flush"},
         "clocks": sampler.result(),
         "e2e": {"value": audio / (ms_e2e * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4},

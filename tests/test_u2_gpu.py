@@ -191,3 +191,35 @@ def test_checkpoint_save_average_and_reload(tmp_path):
     fresh.load_state_dict(avg, strict=True)
     got, _ = fresh.cuda().eval().greedy_ctc(xs, xlens)
     assert got == want
+
+
+@pytest.mark.parametrize("precision,loss_tol,grad_tol", [("fp32", 1e-5, 2e-4), ("bf16", 3e-3, 0.2)])
+def test_c3_shape_class_d512_h8_against_oracle(precision, loss_tol, grad_tol):
+    """BASELINE config 3's shape class (d = 512, 8 heads of 64, 19 x 512 front-end Linear, 2 N tiles per conv2 tap) on a model
+    small enough for the float64 oracle: loss and gradients of the fused step against the oracle (no golden file: the oracle
+    itself is pinned against the reference in test_oracle_golden.py)."""
+    from liteasr_b200.criterions.hybrid_ctc_attn import HybridCTCLoss, HybridCTCLossConfig
+    from liteasr_b200.models.u2 import U2, U2Config
+    from liteasr_b200.schema import U2Dims
+    from liteasr_b200.utils.synthetic import synth_batch, synth_state_dict
+    from oracle import u2_oracle as O
+    dims = U2Dims(80, 61, 512, 384, 8, 2, 512, 384, 8, 1)
+    batch = synth_batch(3, 90, 7, dims.vocab_size, seed=7)
+    sd = synth_state_dict(dims, seed=7)
+    g = dict(dims=dims.__dict__, ctc_weight=0.3, smoothing=0.1)
+    sd64, out, _ = _oracle(g, sd, batch)
+    model = U2(U2Config(**{**dims.__dict__, "precision": precision}))
+    model.load_state_dict(sd)
+    model = model.cuda().train()
+    crit = HybridCTCLoss(HybridCTCLossConfig(vocab_size=dims.vocab_size, smoothing=0.1, ctc_weight=0.3))
+    loss = crit(model, *[t.cuda() for t in batch])
+    loss.backward()
+    assert math.isclose(float(loss), float(out["loss"]), rel_tol=loss_tol)
+    rels = []
+    for n, p in model.named_parameters():
+        r, m, bmax = _rel(p.grad, sd64[n].grad)
+        if bmax > 1e-6:
+            rels.append((r, n))
+    rels.sort()
+    assert rels[len(rels) // 2][0] < grad_tol / 8, rels[len(rels) // 2]
+    assert rels[-1][0] < grad_tol * (1 if precision == "bf16" else 50), rels[-3:]
