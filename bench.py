@@ -306,10 +306,17 @@ def run_gpu(args, wl):
     # end-to-end: pinned host batch -> H2D -> step through the public TrainStep call -> loss read back on the host
     loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
 
+    from liteasr_b200.trainer import Prefetcher
+    pf = Prefetcher(dev)
+    pf.put(host)
+
     def e2e_step():
-        for dst, src in zip(static, host):  # pinned host -> the step's input buffers (async H2D on the compute stream)
-            dst.copy_(src, non_blocking=True)
-        l = step(*static)
+        # the public training API: Prefetcher (pinned host -> device on a copy stream, one step ahead) + TrainStep.__call__
+        # (device-to-device into the graph's static inputs, graph replay); every step starts one H2D copy of a full batch
+        # and reads the loss back on the host
+        dev_batch = pf.get()
+        pf.put(host)
+        l = step(*dev_batch)
         loss_host.copy_(l, non_blocking=False)  # D2H + host sync: the loss is read every step
 
     for _ in range(2):

@@ -131,6 +131,43 @@ class Trigger:
         return it % self.interval == 0
 
 
+class Prefetcher:
+    """Pinned-host -> device double buffering on a copy stream: the batch of step i+1 crosses PCIe while step i computes
+    (SURVEY 8f N3; replaces the synchronous ``to_device`` of trainer.py:140).  ``put`` starts the copy of a host batch into the
+    idle staging slot, ``get`` makes the current stream wait for the oldest pending copy and returns its device tensors; the
+    consumer (``TrainStep.__call__``) copies them device-to-device into the CUDA graph's static inputs."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.slots = [None, None]
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.head = self.tail = 0  # put writes slot head % 2, get reads slot tail % 2
+
+    def put(self, host_batch) -> None:
+        if self.head - self.tail >= 2:
+            raise RuntimeError("Prefetcher: both staging slots are pending (call get first)")
+        k = self.head % 2
+        # the slot's previous contents were consumed by work already enqueued on the current stream
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            slot = self.slots[k]
+            if slot is None or any(d.shape != h.shape or d.dtype != h.dtype for d, h in zip(slot, host_batch)):
+                slot = self.slots[k] = tuple(torch.empty(h.shape, dtype=h.dtype, device=self.device) for h in host_batch)
+            for d, h in zip(slot, host_batch):
+                d.copy_(h, non_blocking=True)
+            self.ready[k].record(self.stream)
+        self.head += 1
+
+    def get(self):
+        if self.tail == self.head:
+            raise RuntimeError("Prefetcher: nothing pending")
+        k = self.tail % 2
+        torch.cuda.current_stream(self.device).wait_event(self.ready[k])
+        self.tail += 1
+        return self.slots[k]
+
+
 class Trainer:
     """Loop mirror of trainer.py:28-227 over an iterable of collated batches ``(xs, xlens, ys, ylens)`` (CPU or GPU
     tensors, the collator contract of dataset/asr_dataset.py:115-126).  Data loading itself is out of scope (SURVEY 2 #12)."""
@@ -148,8 +185,19 @@ class Trainer:
 
     def run(self, batches: Iterable, max_iters: Optional[int] = None) -> None:
         self.model.train()
-        for batch in batches:
-            batch = tuple(t.to(self.device, non_blocking=True) for t in batch)  # trainer.py:140 (async from pinned memory)
+        pf = Prefetcher(self.device)
+        it = iter(batches)
+
+        def stage():  # start the next batch's host-to-device copy (pinned host tensors make it asynchronous)
+            nxt = next(it, None)
+            if nxt is not None:
+                pf.put(tuple(nxt))
+            return nxt is not None
+
+        more = stage()
+        while more:
+            batch = pf.get()
+            more = stage()  # trainer.py:140 moved one step ahead: this copy overlaps the step below
             loss = self.step_fn(*batch)
             self.loss_acc += loss / self.step_fn.accum
             self.iter += 1

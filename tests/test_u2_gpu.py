@@ -223,3 +223,29 @@ def test_c3_shape_class_d512_h8_against_oracle(precision, loss_tol, grad_tol):
     rels.sort()
     assert rels[len(rels) // 2][0] < grad_tol / 8, rels[len(rels) // 2]
     assert rels[-1][0] < grad_tol * (1 if precision == "bf16" else 50), rels[-3:]
+
+
+def test_trainer_run_with_prefetcher_equals_direct_steps():
+    """Trainer.run (pinned host batches, Prefetcher one step ahead, graph replay) == the same batches through TrainStep."""
+    from liteasr_b200.trainer import Prefetcher, Trainer, TrainStep
+    from liteasr_b200.utils.synthetic import synth_batch
+    g, dims, batch, sd, model_a, crit = _setup("tiny", "fp32")
+    _, _, _, _, model_b, _ = _setup("tiny", "fp32")
+    batches = [tuple(t.pin_memory() for t in synth_batch(g["batch"], g["tmax"], g["lmax"], dims.vocab_size, seed=50 + i)) for i in range(4)]
+    logs = []
+    tr = Trainer(model_a, crit, report_interval=2, device=torch.device("cuda:0"), log=logs.append)
+    tr.run(batches)
+    step = TrainStep(model_b, crit, device=torch.device("cuda:0"))
+    for b in batches:
+        step(*[t.cuda() for t in b])
+    torch.cuda.synchronize()
+    assert tr.iter == 4 and len(logs) == 2
+    for (n, pa), (_, pb) in zip(model_a.named_parameters(), model_b.named_parameters()):
+        assert torch.allclose(pa, pb, rtol=1e-5, atol=1e-7), n
+    pf = Prefetcher(torch.device("cuda:0"))
+    with pytest.raises(RuntimeError):
+        pf.get()
+    pf.put(batches[0]); pf.put(batches[1])
+    with pytest.raises(RuntimeError):
+        pf.put(batches[2])
+    assert torch.equal(pf.get()[0].cpu(), batches[0][0]) and torch.equal(pf.get()[0].cpu(), batches[1][0])
