@@ -98,7 +98,7 @@ class Engine:
             return max(1, min(64, rows // 512))
         bn = self._pick_bn(k_out, 64)  # the wgrad GEMM is (n_out x k_out), B operand MN-major
         tiles = ((n_out + 127) // 128) * ((k_out + bn - 1) // bn)
-        s = max(1, min(32, 148 // max(1, tiles)))
+        s = max(1, min(74, 148 // max(1, tiles)))  # one work unit per SM (a 256 x 256 weight gradient is 2 tiles -> 74 splits)
         s = min(s, max(1, rows // 256))
         return s
 
