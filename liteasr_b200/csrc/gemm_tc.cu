@@ -721,6 +721,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, tensor-map prefetch) touches no global
+    // data and may overlap the tail of the previous kernel in the stream; from here on the roles read and write global memory.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (warp == 0) {
         if (lane == 0) {
@@ -1026,7 +1030,19 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtenso
         smem_bytes = SM_RING + p.stages * p.stage_bytes + 1024;
         grid = p.total_units < sm_count() ? p.total_units : sm_count();
     }
-    kern<<<grid, GEMM_THREADS, smem_bytes, st>>>(ma, mb, mc, mx, p);
+    static int pdl = -1;  // LASR_GEMM_PDL=0: developer switch
+    if (pdl < 0) { const char* e = getenv("LASR_GEMM_PDL"); pdl = e ? atoi(e) : 1; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    if (cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, mx, p) != cudaSuccess) return check_launch("gemm_tc launch");
     return check_launch("gemm_tc");
 }
 
