@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(256) attn_softmax_fwd_kernel(const TS* __restr
                                                                TP* __restrict__ probs, const int64_t* __restrict__ lens,
                                                                int mask_mode, int causal, float scale, int B, int H, int Tq,
                                                                int Tk, int ld) {
+    LASR_PDL_SYNC();
     const int lane = threadIdx.x & 31;
     const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= (long)B * H * Tq) return;
@@ -99,6 +100,7 @@ template <typename TP, typename TS, int NP>
 __global__ void __launch_bounds__(256) attn_softmax_bwd_kernel(const TP* __restrict__ probs, const TS* __restrict__ dprobs,
                                                                TP* __restrict__ dsc, TP* __restrict__ dbd, float scale, long rows,
                                                                int Tq, int Tk, int ld) {
+    LASR_PDL_SYNC();
     const int lane = threadIdx.x & 31;
     const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -156,11 +158,11 @@ using namespace lasr;
 
 #define LASR_SM_DISPATCH(KERNEL, TP, TS, ...)                                        \
     do {                                                                             \
-        if (Tk <= 64) KERNEL<TP, TS, 1><<<grid, 256, 0, st>>>(__VA_ARGS__);          \
-        else if (Tk <= 128) KERNEL<TP, TS, 2><<<grid, 256, 0, st>>>(__VA_ARGS__);    \
-        else if (Tk <= 320) KERNEL<TP, TS, 5><<<grid, 256, 0, st>>>(__VA_ARGS__);    \
-        else if (Tk <= 448) KERNEL<TP, TS, 7><<<grid, 256, 0, st>>>(__VA_ARGS__);    \
-        else KERNEL<TP, TS, SM_MAXP><<<grid, 256, 0, st>>>(__VA_ARGS__);             \
+        if (Tk <= 64) launch_pdl(KERNEL<TP, TS, 1>, grid, 256, 0, st, __VA_ARGS__);          \
+        else if (Tk <= 128) launch_pdl(KERNEL<TP, TS, 2>, grid, 256, 0, st, __VA_ARGS__);    \
+        else if (Tk <= 320) launch_pdl(KERNEL<TP, TS, 5>, grid, 256, 0, st, __VA_ARGS__);    \
+        else if (Tk <= 448) launch_pdl(KERNEL<TP, TS, 7>, grid, 256, 0, st, __VA_ARGS__);    \
+        else launch_pdl(KERNEL<TP, TS, SM_MAXP>, grid, 256, 0, st, __VA_ARGS__);             \
     } while (0)
 
 int lasr_attn_softmax_fwd(const void* ac, const void* bd, int s_dtype, void* probs, int p_dtype, const int64_t* lens, int mask_mode,

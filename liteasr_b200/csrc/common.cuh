@@ -27,6 +27,27 @@ int check_launch(const char* what);
 
 static inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 
+// Programmatic dependent launch (sm_90+): a kernel launched through launch_pdl may be scheduled while its predecessor in the
+// stream is still draining; LASR_PDL_SYNC() -- the FIRST statement of every such kernel, before any global-memory access --
+// lets the successor do the same and then blocks until the predecessor has completed and its writes are visible.  Launched
+// with plain <<< >>> the two instructions are no-ops.  ~1 us per launch on the ~1000-launch training step.
+#define LASR_PDL_SYNC() asm volatile("griddepcontrol.launch_dependents;\n\tgriddepcontrol.wait;" ::: "memory")
+
+template <typename... Exp, typename... Act>
+static inline void launch_pdl(void (*kern)(Exp...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Act&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    (void)cudaLaunchKernelEx(&cfg, kern, static_cast<Exp>(args)...);  // failures surface through check_launch()
+}
+
 // ---------------------------------------------------------------------------------------------
 // load/store with dtype conversion (fp32 math everywhere)
 // ---------------------------------------------------------------------------------------------

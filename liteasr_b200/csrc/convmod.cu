@@ -91,6 +91,7 @@ template <typename TD>
 __global__ void __launch_bounds__(256) bn_swish_fwd_vec_kernel(const float* __restrict__ z, const float* __restrict__ mean,
                                                                const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, TD* __restrict__ a, long rows, int d) {
+    LASR_PDL_SYNC();
     const int vpr = d >> 2;
     const long gid = (long)blockIdx.x * 256 + threadIdx.x;
     const int cv = (int)(gid % vpr);
@@ -230,6 +231,7 @@ template <typename TD>
 __global__ void __launch_bounds__(256, 4) glu_dwconv_fwd_kernel(const TD* __restrict__ y2, long ldy, const float* __restrict__ w,
                                                                 const float* __restrict__ bias, float* __restrict__ z,
                                                                 float* __restrict__ partial, int T, int d) {
+    LASR_PDL_SYNC();
     __shared__ __align__(16) float gt[FWIN][FC];
     __shared__ float wt[FC * KW];
     __shared__ float red[2][4][FC];
@@ -373,6 +375,7 @@ __global__ void __launch_bounds__(256) bn_swish_bwd_stats_kernel(const TD* __res
                                                                  const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                  float* __restrict__ partial, long rows, int d) {
+    LASR_PDL_SYNC();
     __shared__ __align__(16) float4 red[2][256];
     const int vpr = d >> 2;                                 // float4 chunks per row
     const long r0 = (long)blockIdx.x * TCH, r1 = min(rows, r0 + TCH);
@@ -432,6 +435,7 @@ __global__ void __launch_bounds__(256, 3) dwconv_glu_bwd_kernel(const TD* __rest
                                                                 float* __restrict__ dw, float* __restrict__ dbias,
                                                                 float* __restrict__ colsum, float* __restrict__ wpartial, int T, int d,
                                                                 float inv_count) {
+    LASR_PDL_SYNC();
     extern __shared__ __align__(16) uint8_t smem_raw[];
     BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
     const int b = blockIdx.y, c0 = blockIdx.z * FC, t0 = blockIdx.x * FT;
@@ -552,6 +556,7 @@ __global__ void __launch_bounds__(256, 3) dwconv_glu_bwd_kernel(const TD* __rest
 // (already 144 CTAs of 1024 threads at d = 256: a cluster split like bn_reduce's measured 3x slower here)
 __global__ void __launch_bounds__(32 * RG) dwconv_reduce_kernel(const float* __restrict__ wpartial, int nblk, int d, float* __restrict__ dw,
                                                                 float* __restrict__ dbias, float* __restrict__ colsum) {
+    LASR_PDL_SYNC();
     __shared__ float sh[RG][33];
     const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5, c = blockIdx.x * 32 + cx, k = blockIdx.y;
     float s = 0.f;
@@ -585,8 +590,8 @@ int lasr_glu_dwconv_fwd(const void* y2, int dtype, int64_t ldy, const float* w, 
     const bool fast = fast_d(d) && ldy % 4 == 0 && ((uintptr_t)y2 & 15) == 0 && ((uintptr_t)z & 15) == 0;
     if (fast) {
         dim3 grid(ceil_div(T, FT), B, ceil_div(d, FC));
-        if (dtype == LASR_F32) glu_dwconv_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)y2, ldy, w, bias, z, partial, T, d);
-        else if (dtype == LASR_BF16) glu_dwconv_fwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)y2, ldy, w, bias, z, partial, T, d);
+        if (dtype == LASR_F32) launch_pdl(glu_dwconv_fwd_kernel<float>, grid, 256, 0, st, (const float*)y2, ldy, w, bias, z, partial, T, d);
+        else if (dtype == LASR_BF16) launch_pdl(glu_dwconv_fwd_kernel<bf16>, grid, 256, 0, st, (const bf16*)y2, ldy, w, bias, z, partial, T, d);
         else { set_error("glu_dwconv_fwd: bad dtype"); return LASR_ERR_UNSUPPORTED; }
     } else {
         dim3 grid(ceil_div(T, TCH), B);
@@ -617,8 +622,8 @@ int lasr_bn_swish_fwd(const float* z, const float* mean, const float* rstd, cons
     const bool vec = d % 4 == 0 && (((uintptr_t)z | (uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)a) & 15) == 0;
     if (vec) {
         const long threads = (long)(d >> 2) * ((rows + 3) / 4);
-        if (dtype == LASR_F32) bn_swish_fwd_vec_kernel<float><<<ceil_div(threads, 256), 256, 0, st>>>(z, mean, rstd, gamma, beta, (float*)a, rows, d);
-        else bn_swish_fwd_vec_kernel<bf16><<<ceil_div(threads, 256), 256, 0, st>>>(z, mean, rstd, gamma, beta, (bf16*)a, rows, d);
+        if (dtype == LASR_F32) launch_pdl(bn_swish_fwd_vec_kernel<float>, ceil_div(threads, 256), 256, 0, st, z, mean, rstd, gamma, beta, (float*)a, rows, d);
+        else launch_pdl(bn_swish_fwd_vec_kernel<bf16>, ceil_div(threads, 256), 256, 0, st, z, mean, rstd, gamma, beta, (bf16*)a, rows, d);
     } else if (dtype == LASR_F32) bn_swish_fwd_kernel<float><<<ceil_div(n / 2, 256), 256, 0, st>>>(z, mean, rstd, gamma, beta, (float*)a, n, d);
     else bn_swish_fwd_kernel<bf16><<<ceil_div(n / 2, 256), 256, 0, st>>>(z, mean, rstd, gamma, beta, (bf16*)a, n, d);
     return check_launch("bn_swish_fwd");
@@ -635,8 +640,8 @@ int lasr_bn_swish_bwd_stats(const void* da, int dtype, const float* z, const flo
                       (((uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0;
     if (dtype != LASR_F32 && dtype != LASR_BF16) { set_error("bn_swish_bwd_stats: bad dtype"); return LASR_ERR_UNSUPPORTED; }
     if (fast) {
-        if (dtype == LASR_F32) bn_swish_bwd_stats_kernel<float><<<nblk, 256, 0, st>>>((const float*)da, z, mean, rstd, gamma, beta, partial, rows, d);
-        else bn_swish_bwd_stats_kernel<bf16><<<nblk, 256, 0, st>>>((const bf16*)da, z, mean, rstd, gamma, beta, partial, rows, d);
+        if (dtype == LASR_F32) launch_pdl(bn_swish_bwd_stats_kernel<float>, nblk, 256, 0, st, (const float*)da, z, mean, rstd, gamma, beta, partial, rows, d);
+        else launch_pdl(bn_swish_bwd_stats_kernel<bf16>, nblk, 256, 0, st, (const bf16*)da, z, mean, rstd, gamma, beta, partial, rows, d);
     } else {
         if (dtype == LASR_F32) bn_swish_bwd_stats_generic<float><<<nblk, 128, 0, st>>>((const float*)da, z, mean, rstd, gamma, beta, partial, rows, d);
         else bn_swish_bwd_stats_generic<bf16><<<nblk, 128, 0, st>>>((const bf16*)da, z, mean, rstd, gamma, beta, partial, rows, d);
@@ -669,14 +674,14 @@ int lasr_dwconv_glu_bwd(const void* da, const float* z, const void* y2, int dtyp
             configured = true;
         }
         if (dtype == LASR_F32)
-            dwconv_glu_bwd_kernel<float><<<grid, 256, smem, st>>>((const float*)da, z, (const float*)y2, ldy, mean, rstd, gamma, beta, sums, w,
+            launch_pdl(dwconv_glu_bwd_kernel<float>, grid, 256, smem, st, (const float*)da, z, (const float*)y2, ldy, mean, rstd, gamma, beta, sums, w,
                                                                  (float*)dy2, lddy, dw, dbias, colsum, wpartial, T, d, inv);
         else
-            dwconv_glu_bwd_kernel<bf16><<<grid, 256, smem, st>>>((const bf16*)da, z, (const bf16*)y2, ldy, mean, rstd, gamma, beta, sums, w,
+            launch_pdl(dwconv_glu_bwd_kernel<bf16>, grid, 256, smem, st, (const bf16*)da, z, (const bf16*)y2, ldy, mean, rstd, gamma, beta, sums, w,
                                                                 (bf16*)dy2, lddy, dw, dbias, colsum, wpartial, T, d, inv);
         int rc = check_launch("dwconv_glu_bwd");
         if (rc || !wpartial) return rc;
-        dwconv_reduce_kernel<<<dim3(ceil_div(d, 32), KW + 3), 32 * RG, 0, st>>>(wpartial, B * ceil_div(T, FT), d, dw, dbias, colsum);
+        launch_pdl(dwconv_reduce_kernel, dim3(ceil_div(d, 32), KW + 3), 32 * RG, 0, st, wpartial, B * ceil_div(T, FT), d, dw, dbias, colsum);
         return check_launch("dwconv_reduce");
     }
     dim3 grid(ceil_div(T, TCH), B);

@@ -29,6 +29,7 @@ __device__ __forceinline__ void st4(TD* p, float4 v) {
 
 // ------------------------------------------------------------------ cast fp32 -> bf16 (flat)
 __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long n) {
+    LASR_PDL_SYNC();
     const long i4 = ((long)blockIdx.x * 256 + threadIdx.x) * 4;
     if (i4 + 3 < n) {
         st4<bf16>(dst + i4, *reinterpret_cast<const float4*>(src + i4));
@@ -65,6 +66,7 @@ template <typename TD>
 __global__ void __launch_bounds__(256) act_bwd_kernel(const TD* __restrict__ da, long ldda, const TD* __restrict__ saved,
                                                       long lds, TD* __restrict__ dh, long lddh,
                                                       float* __restrict__ dbias, int rows, int cols, int act, float scale) {
+    LASR_PDL_SYNC();
     __shared__ float4 red[4][64];
     const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
     const int c = (blockIdx.x * 64 + tx) * 4;
@@ -124,6 +126,7 @@ template <typename TD>
 __global__ void __launch_bounds__(256) pos_bias_fwd_kernel(const TD* __restrict__ q, long ldq, const float* __restrict__ u,
                                                            const float* __restrict__ v, TD* __restrict__ qu,
                                                            TD* __restrict__ qv, long ldo, int rows, int d) {
+    LASR_PDL_SYNC();
     const int per_row = d >> 2;
     const long i = (long)blockIdx.x * 256 + threadIdx.x;
     if (i >= (long)rows * per_row) return;
@@ -140,6 +143,7 @@ template <typename TD>
 __global__ void __launch_bounds__(256) pos_bias_bwd_kernel(const TD* __restrict__ dqu, const TD* __restrict__ dqv, long ldi,
                                                            TD* __restrict__ dq, long ldq, float* __restrict__ du,
                                                            float* __restrict__ dv, float* __restrict__ dqb, int rows, int d) {
+    LASR_PDL_SYNC();
     __shared__ float4 red[2][4][64];
     const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
     const int c = (blockIdx.x * 64 + tx) * 4;
@@ -211,7 +215,7 @@ using namespace lasr;
 int lasr_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream) {
     LASR_REQUIRE(src && dst && n > 0, "cast: bad args");
     LASR_REQUIRE(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0, "cast: unaligned");
-    cast_bf16_kernel<<<ceil_div(n, 1024), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, n);
+    launch_pdl(cast_bf16_kernel, ceil_div(n, 1024), 256, 0, (cudaStream_t)stream, src, (bf16*)dst, n);
     return check_launch("cast_f32_bf16");
 }
 
@@ -239,8 +243,8 @@ int lasr_act_bwd(const void* da, int64_t ldda, const void* saved, int64_t lds, v
     LASR_REQUIRE(ldda % 4 == 0 && lds % 4 == 0 && lddh % 4 == 0, "act_bwd: strides must be multiples of 4");
     dim3 grid(ceil_div(cols, 256), ceil_div(rows, 64));
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == LASR_F32) act_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)da, ldda, (const float*)saved, lds, (float*)dh, lddh, dbias, rows, cols, act, scale);
-    else if (dtype == LASR_BF16) act_bwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)da, ldda, (const bf16*)saved, lds, (bf16*)dh, lddh, dbias, rows, cols, act, scale);
+    if (dtype == LASR_F32) launch_pdl(act_bwd_kernel<float>, grid, 256, 0, st, (const float*)da, ldda, (const float*)saved, lds, (float*)dh, lddh, dbias, rows, cols, act, scale);
+    else if (dtype == LASR_BF16) launch_pdl(act_bwd_kernel<bf16>, grid, 256, 0, st, (const bf16*)da, ldda, (const bf16*)saved, lds, (bf16*)dh, lddh, dbias, rows, cols, act, scale);
     else { set_error("act_bwd: bad dtype"); return LASR_ERR_UNSUPPORTED; }
     return check_launch("act_bwd");
 }
@@ -250,8 +254,8 @@ int lasr_pos_bias_fwd(const void* q, int64_t ldq, const float* u, const float* v
     LASR_REQUIRE(q && u && v && qu && qv && rows > 0 && d % 4 == 0 && ldq % 4 == 0 && ldo % 4 == 0, "pos_bias_fwd: bad args");
     const int grid = ceil_div((long)rows * (d / 4), 256);
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == LASR_F32) pos_bias_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)q, ldq, u, v, (float*)qu, (float*)qv, ldo, rows, d);
-    else if (dtype == LASR_BF16) pos_bias_fwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)q, ldq, u, v, (bf16*)qu, (bf16*)qv, ldo, rows, d);
+    if (dtype == LASR_F32) launch_pdl(pos_bias_fwd_kernel<float>, grid, 256, 0, st, (const float*)q, ldq, u, v, (float*)qu, (float*)qv, ldo, rows, d);
+    else if (dtype == LASR_BF16) launch_pdl(pos_bias_fwd_kernel<bf16>, grid, 256, 0, st, (const bf16*)q, ldq, u, v, (bf16*)qu, (bf16*)qv, ldo, rows, d);
     else { set_error("pos_bias_fwd: bad dtype"); return LASR_ERR_UNSUPPORTED; }
     return check_launch("pos_bias_fwd");
 }
@@ -261,8 +265,8 @@ int lasr_pos_bias_bwd(const void* dqu, const void* dqv, int64_t ldi, void* dq, i
     LASR_REQUIRE(dqu && dqv && dq && du && dv && rows > 0 && d % 4 == 0 && ldi % 4 == 0 && ldq % 4 == 0, "pos_bias_bwd: bad args");
     dim3 grid(ceil_div(d, 256), ceil_div(rows, 64));
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == LASR_F32) pos_bias_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)dqu, (const float*)dqv, ldi, (float*)dq, ldq, du, dv, dqbias, rows, d);
-    else if (dtype == LASR_BF16) pos_bias_bwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)dqu, (const bf16*)dqv, ldi, (bf16*)dq, ldq, du, dv, dqbias, rows, d);
+    if (dtype == LASR_F32) launch_pdl(pos_bias_bwd_kernel<float>, grid, 256, 0, st, (const float*)dqu, (const float*)dqv, ldi, (float*)dq, ldq, du, dv, dqbias, rows, d);
+    else if (dtype == LASR_BF16) launch_pdl(pos_bias_bwd_kernel<bf16>, grid, 256, 0, st, (const bf16*)dqu, (const bf16*)dqv, ldi, (bf16*)dq, ldq, du, dv, dqbias, rows, d);
     else { set_error("pos_bias_bwd: bad dtype"); return LASR_ERR_UNSUPPORTED; }
     return check_launch("pos_bias_bwd");
 }

@@ -18,6 +18,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
                                                             const float* __restrict__ beta, TY* __restrict__ y, long ldy,
                                                             float* __restrict__ mean, float* __restrict__ rstd, int rows,
                                                             int d, float eps) {
+    LASR_PDL_SYNC();
     const int lane = threadIdx.x & 31;
     const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -94,6 +95,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TD* __restrict
                                                             float* __restrict__ dbeta, int rows, int d,
                                                             bf16* __restrict__ dx_lo, long lddxlo,
                                                             float* __restrict__ colsum, float cs_scale) {
+    LASR_PDL_SYNC();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nchunk = d >> 2;
     float4 gam[NV], ag[NV], abt[NV], acs[NV];
@@ -180,7 +182,7 @@ int lasr_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const fl
     LASR_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0, "layernorm_fwd: row strides must be multiples of 4");
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = ceil_div(rows, 8);
-#define LASR_LNF(TY, NV) layernorm_fwd_kernel<TY, NV><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, (TY*)y, ldy, mean, rstd, rows, d, eps)
+#define LASR_LNF(TY, NV) launch_pdl(layernorm_fwd_kernel<TY, NV>, grid, 256, 0, st, x, ldx, gamma, beta, (TY*)y, ldy, mean, rstd, rows, d, eps)
 #define LASR_LNF_D(TY)                      \
     do {                                    \
         if (d <= 128) LASR_LNF(TY, 1);      \
@@ -211,7 +213,7 @@ int lasr_layernorm_bwd(const void* dy, int dy_dtype, int64_t lddy, const float* 
     if (grid > 148 * 3) grid = 148 * 3;
     bf16* lo = (bf16*)dx_lo;
 #define LASR_LNB(TD, NV)                                                                                                     \
-    layernorm_bwd_kernel<TD, NV><<<grid, 256, 0, st>>>((const TD*)dy, lddy, x, ldx, mean, rstd, gamma, dx, lddx, accumulate, \
+    launch_pdl(layernorm_bwd_kernel<TD, NV>, grid, 256, 0, st, (const TD*)dy, lddy, x, ldx, mean, rstd, gamma, dx, lddx, accumulate, \
                                                        dgamma, dbeta, rows, d, lo, lddxlo, colsum, colsum_scale)
 #define LASR_LNB_D(TD)                  \
     do {                                \
