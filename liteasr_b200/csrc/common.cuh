@@ -3,6 +3,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/lasr.h"
 
@@ -43,8 +44,10 @@ static inline void launch_pdl(void (*kern)(Exp...), dim3 grid, dim3 block, size_
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static int pdl = -1;  // LASR_PDL=0: developer switch (plain stream-ordered launches)
+    if (pdl < 0) { const char* e = getenv("LASR_PDL"); pdl = e ? atoi(e) : 1; }
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl ? 1 : 0;
     (void)cudaLaunchKernelEx(&cfg, kern, static_cast<Exp>(args)...);  // failures surface through check_launch()
 }
 

@@ -1030,8 +1030,8 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtenso
         smem_bytes = SM_RING + p.stages * p.stage_bytes + 1024;
         grid = p.total_units < sm_count() ? p.total_units : sm_count();
     }
-    static int pdl = -1;  // LASR_GEMM_PDL=0: developer switch
-    if (pdl < 0) { const char* e = getenv("LASR_GEMM_PDL"); pdl = e ? atoi(e) : 1; }
+    static int pdl = -1;  // LASR_PDL=0: developer switch
+    if (pdl < 0) { const char* e = getenv("LASR_PDL"); pdl = e ? atoi(e) : 1; }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(GEMM_THREADS);
