@@ -224,6 +224,20 @@ int lasr_attn_softmax_bwd(const void* probs, const void* dprobs, int s_dtype, vo
                           int H, int Tq, int Tk, int ld, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Fused relative-position self-attention forward (nets/attention.py:99-154: matrix_ac, matrix_bd, the legacy rel_shift,
+ * scale, key-padding masked_fill(-1e38), softmax, probs . V) in one tcgen05 kernel for bf16 operands:
+ *   qu = q + pos_bias_u, qv = q + pos_bias_v : (B*T, H*dk) rows of stride ldq;  k, v : (B*T, H*dk) views, row stride ldkv;
+ *   pos = linear_pos(pos_emb) : (T, H*dk), row stride ldp (broadcast over the batch)
+ *   probs (B,H,T,ld) bf16 (saved for the backward pass; columns [T,ld) zeroed), o (B*T, H*dk) bf16, row stride ldo.
+ * Replaces lasr_gemm x2 + lasr_attn_softmax_fwd + lasr_gemm for T <= 320, dk == 64 (lasr_rel_attn_fwd_supported);
+ * other shapes return LASR_ERR_UNSUPPORTED and the caller keeps the unfused sequence.  mask_mode as lasr_attn_softmax_fwd.
+ * ------------------------------------------------------------------------------------------------ */
+int lasr_rel_attn_fwd_supported(int T, int dk);
+int lasr_rel_attn_fwd(const void* qu, const void* qv, long ldq, const void* k, const void* v, long ldkv, const void* pos, long ldp,
+                      void* probs, int ld, void* o, long ldo, const int64_t* lens, int mask_mode, float scale, int B, int H, int T,
+                      int dk, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Label-smoothed KL on the decoder logits, forward + gradient (criterions/hybrid_ctc_attn.py:49-64;
  * targets built on the fly from ys/ylens as models/u2.py:323-328), and the hybrid mix (:78).
  * row_loss: B*(lmax+1) floats.  hybrid_combine: out[0]=loss, out[1]=ctc term, out[2]=attention term.

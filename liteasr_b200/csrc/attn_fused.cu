@@ -1,0 +1,423 @@
+// Fused relative-position self-attention forward for one Conformer layer (nets/attention.py:99-154 of the reference):
+//
+//   ac = (q + u) . K^T          bd = (q + v) . P^T          s = (ac + rel_shift(bd)) / sqrt(dk)
+//   s[j >= klen] = -1e38        p = softmax_j(s)            O = p . V
+//
+// in ONE kernel per layer: both score contractions and p.V run on tcgen05 with TMEM accumulators, the legacy rel_shift,
+// scale, key-padding mask and softmax happen between them on chip, and the only HBM traffic is the operands (q+u, q+v, K, P,
+// V: 2 B per element, L2-resident across the tiles of a head), the bf16 probabilities the backward pass needs (written once
+// by bulk tensor stores straight from the shared-memory tile that also feeds the p.V MMA) and O.  The unfused path
+// (two GEMMs -> fp32 score tensors -> attn_softmax_fwd -> GEMM) moves ~10x the bytes.
+//
+// One CTA per (batch, head, row tile); T <= 320 keys, dk = 64.
+//
+// The legacy rel_shift (quirk Q1) is a flat re-view: pad a zero column in front of bd (T x (T+1)), view the same memory as
+// (T+1) x T and drop the first row, i.e. out[i][j] = flat[(i+1) T + j] with flat[r (T+1)] = 0 and flat[r (T+1) + 1 + c] =
+// bd[r][c].  So the tile's bd rows are written CONTIGUOUSLY into a flat shared-memory buffer at r (T+1) + 1 + c and the
+// shifted rows are read back CONTIGUOUSLY at r T + j -- no per-element index arithmetic.  Output row i needs bd rows i and
+// i + 1, hence a 128-row MMA tile yields 127 attention rows (tile stride 127).
+//
+//   warp 0      TMA: (q+v) tile + P, (q+u) tile + K, then V into P's buffer once the bd MMAs retired; at the end the bulk
+//               tensor stores of the probability tile
+//   warp 1      MMA issuer: bd -> TMEM[0,320) ; (drained) ac -> TMEM[0,320) ; p.V -> TMEM[320,384)
+//   warps 2..9  two warps per TMEM lane quarter, each owning one 160-column half of its 32 rows:
+//               shift : bd row (TMEM) -> * scale*log2(e) -> fp16 -> flat buffer
+//               pass 1: s = ac * scale*log2(e) + shifted bd, mask, row max        (s written back to TMEM in place)
+//               pass 2: e = 2^(s - max), row sum                                  (e written back to TMEM in place)
+//               pass 3: p = e / sum -> bf16 -> the K-major SWIZZLE_128B tile (aliases the flat buffer: all its reads
+//                       happened in pass 1) that is both the A operand of p.V and the source of the probability stores
+//               O     : TMEM[320,384) -> bf16 -> global
+#include <cuda_fp16.h>
+
+#include <cstring>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace lasr {
+namespace fa {
+
+constexpr int TM = 128;      // bd rows per tile (MMA M)
+constexpr int TOUT = 127;    // attention rows per tile
+constexpr int TKMAX = 320;   // keys
+constexpr int NHALF = 160;   // MMA N of one score half
+constexpr int DK = 64;
+constexpr int EPI_W = 8;
+constexpr int THREADS = 64 + 32 * EPI_W;
+
+constexpr int OFF_STG = 0;                        // flat fp16 shift buffer, then the 5 x (128 x 64) bf16 probability slabs
+constexpr int STG_BYTES = 5 * TM * 128;           // 81920
+constexpr int OFF_QU = OFF_STG + STG_BYTES;       // (q+u) tile, 128 x 64 bf16
+constexpr int OFF_QV = OFF_QU + TM * 128;         // (q+v) tile
+constexpr int OFF_K = OFF_QV + TM * 128;          // K: two 160-row halves
+constexpr int OFF_P = OFF_K + 2 * NHALF * 128;    // P: two 160-row halves; later V: five 64-key atoms
+constexpr int OFF_BAR = OFF_P + 2 * NHALF * 128;  // 196608
+constexpr int OFF_RED = OFF_BAR + 128;
+constexpr int SMEM_BYTES = OFF_RED + 2 * 2 * TM * 4 + 1024;
+
+enum { BAR_BDIN = 0, BAR_ACIN, BAR_V, BAR_BD_DONE, BAR_BD_DRAINED, BAR_AC_DONE, BAR_P_READY, BAR_O_DONE, NBARS };
+
+struct Params {
+    bf16* o;
+    long ldo;
+    const int64_t* lens;
+    int mask_mode;
+    float c2;  // scale * log2(e)
+    int B, H, T, ld, tiles;
+};
+
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const float* v) {
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_W) : "memory"); }
+__device__ __forceinline__ float ex2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+rel_attn_fwd_kernel(const __grid_constant__ CUtensorMap m_qu, const __grid_constant__ CUtensorMap m_qv,
+                    const __grid_constant__ CUtensorMap m_k, const __grid_constant__ CUtensorMap m_v,
+                    const __grid_constant__ CUtensorMap m_p, const __grid_constant__ CUtensorMap m_probs, const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 8 * NBARS);
+    float* red = reinterpret_cast<float*>(smem + OFF_RED);  // [max|sum][half][row]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x % p.tiles, bh = blockIdx.x / p.tiles;
+    const int h = bh % p.H, b = bh / p.H;
+    const int T = p.T, r0 = tile * TOUT;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&m_qu) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&m_qv) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&m_k) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&m_v) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&m_p) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&m_probs) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < NBARS; ++i) mbar_init(bars + i, (i == BAR_BD_DRAINED || i == BAR_P_READY) ? EPI_W : 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    const int kslabs = (p.ld + 63) >> 6;  // 64-column slabs of the probability tile that hold stored columns
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(bars + BAR_BDIN, TM * 128 + 2 * NHALF * 128);
+            tma_load_4d(smem + OFF_QV, &m_qv, bars + BAR_BDIN, h * DK, r0, b, 0);
+            tma_load_4d(smem + OFF_P, &m_p, bars + BAR_BDIN, h * DK, 0, 0, 0);
+            tma_load_4d(smem + OFF_P + NHALF * 128, &m_p, bars + BAR_BDIN, h * DK, NHALF, 0, 0);
+            mbar_arrive_expect_tx(bars + BAR_ACIN, TM * 128 + 2 * NHALF * 128);
+            tma_load_4d(smem + OFF_QU, &m_qu, bars + BAR_ACIN, h * DK, r0, b, 0);
+            tma_load_4d(smem + OFF_K, &m_k, bars + BAR_ACIN, h * DK, 0, b, 0);
+            tma_load_4d(smem + OFF_K + NHALF * 128, &m_k, bars + BAR_ACIN, h * DK, NHALF, b, 0);
+            // V replaces P once the bd MMAs have read it
+            mbar_wait(bars + BAR_BD_DONE, 0);
+            mbar_arrive_expect_tx(bars + BAR_V, 5 * 8192);
+            for (int kb = 0; kb < 5; ++kb) tma_load_4d(smem + OFF_P + kb * 8192, &m_v, bars + BAR_V, h * DK, 64 * kb, b, 0);
+            // probabilities: rows [r0, r0 + 127) x stored columns, straight from the MMA operand tile
+            mbar_wait(bars + BAR_P_READY, 0);
+            for (int kb = 0; kb < kslabs; ++kb) tma_store_4d(&m_probs, smem + OFF_STG + kb * (TM * 128), 64 * kb, r0, bh, 0);
+            bulk_commit();
+            bulk_wait_read<0>();
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t id_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NHALF >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+            const uint32_t id_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(DK >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+            const uint32_t s_stg = smem_u32(smem + OFF_STG), s_qu = smem_u32(smem + OFF_QU), s_qv = smem_u32(smem + OFF_QV);
+            const uint32_t s_k = smem_u32(smem + OFF_K), s_p = smem_u32(smem + OFF_P);
+            // bd = (q+v) . P^T
+            mbar_wait(bars + BAR_BDIN, 0);
+            tc_fence_after();
+#pragma unroll
+            for (int nh = 0; nh < 2; ++nh)
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    tc_mma_bf16(tmem_base + nh * NHALF, umma_desc(s_qv + kk * 32, 16, 1024),
+                                umma_desc(s_p + nh * (NHALF * 128) + kk * 32, 16, 1024), id_s, kk > 0 ? 1u : 0u);
+            tc_commit(bars + BAR_BD_DONE);
+            // ac = (q+u) . K^T into the same columns once every warp has copied its bd rows out
+            mbar_wait(bars + BAR_ACIN, 0);
+            mbar_wait(bars + BAR_BD_DRAINED, 0);
+            tc_fence_after();
+#pragma unroll
+            for (int nh = 0; nh < 2; ++nh)
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    tc_mma_bf16(tmem_base + nh * NHALF, umma_desc(s_qu + kk * 32, 16, 1024),
+                                umma_desc(s_k + nh * (NHALF * 128) + kk * 32, 16, 1024), id_s, kk > 0 ? 1u : 0u);
+            tc_commit(bars + BAR_AC_DONE);
+            // O = p . V  (K = keys, 16 per instruction; key blocks beyond T hold zero probabilities and are skipped)
+            mbar_wait(bars + BAR_V, 0);
+            mbar_wait(bars + BAR_P_READY, 0);
+            tc_fence_after();
+            const int ksteps = (T + 15) >> 4;
+            for (int ks = 0; ks < ksteps; ++ks) {
+                const int kb = ks >> 2, kk = ks & 3;
+                tc_mma_bf16(tmem_base + TKMAX, umma_desc(s_stg + kb * (TM * 128) + kk * 32, 16, 1024),
+                            umma_desc(s_p + kb * 8192 + kk * 2048, 8192, 1024), id_o, ks > 0 ? 1u : 0u);
+            }
+            tc_commit(bars + BAR_O_DONE);
+        }
+    } else {
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        const int r = q * 32 + lane, g = r0 + r;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const float c2 = p.c2;
+        int klen = T;
+        if (p.mask_mode != 0 && p.lens) {
+            const long l = p.lens[b];
+            long k = l;
+            if (p.mask_mode == 2) k = l + 1;
+            else if (p.mask_mode == 3) k = (l + 3) / 4;
+            klen = (int)(k < T ? (k < 0 ? 0 : k) : T);
+        }
+        const int cbase = half * NHALF;
+
+        // ---- shift: bd row g -> flat buffer (see the header comment)
+        mbar_wait(bars + BAR_BD_DONE, 0);
+        tc_fence_after();
+        {
+            __half* stg = reinterpret_cast<__half*>(smem + OFF_STG);
+            const int off = r * (T + 1) + r0 - T;  // flat position of the padded zero of bd row g
+            const int lmax = TOUT * T;
+            const int lo = max(0, -(off + 1)), hi = min(T, lmax - off - 1);  // columns c with 0 <= off + 1 + c < lmax
+            if (half == 0 && off >= 0 && off < lmax) stg[off] = __float2half_rn(0.f);
+#pragma unroll 1
+            for (int ch = 0; ch < NHALF / 32; ++ch) {
+                const int c0 = cbase + ch * 32;
+                if (c0 >= T) break;  // warp-uniform
+                float v[32];
+                tc_ld32(lane_addr + (uint32_t)c0, v);
+                __half* dst = stg + off + 1 + c0;
+                if (c0 >= lo && c0 + 32 <= hi) {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) dst[e] = __float2half_rn(fminf(fmaxf(v[e] * c2, -60000.f), 60000.f));
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e)
+                        if (c0 + e >= lo && c0 + e < hi) dst[e] = __float2half_rn(fminf(fmaxf(v[e] * c2, -60000.f), 60000.f));
+                }
+            }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + BAR_BD_DRAINED);
+        epi_barrier();  // the flat buffer is complete
+
+        // ---- pass 1: s = ac * c2 + shifted bd, mask, row max; s replaces ac in TMEM
+        mbar_wait(bars + BAR_AC_DONE, 0);
+        tc_fence_after();
+        float mx = -INFINITY;
+        {
+            const __half* src = reinterpret_cast<const __half*>(smem + OFF_STG) + r * T + cbase;
+#pragma unroll 1
+            for (int ch = 0; ch < NHALF / 32; ++ch) {
+                const int j0 = cbase + ch * 32;
+                if (j0 >= T) break;
+                float v[32];
+                tc_ld32(lane_addr + (uint32_t)j0, v);
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const int j = j0 + e;
+                    float s = fmaf(v[e], c2, __half2float(src[ch * 32 + e]));
+                    s = (j < klen) ? s : -1e38f;
+                    s = (j < T) ? s : -INFINITY;
+                    v[e] = s;
+                    mx = fmaxf(mx, s);
+                }
+                tc_st32(lane_addr + (uint32_t)j0, v);
+            }
+        }
+        red[half * TM + r] = mx;
+        tc_wait_st();
+        epi_barrier();
+        mx = fmaxf(red[r], red[TM + r]);
+
+        // ---- pass 2: e = 2^(s - max), row sum; e replaces s in TMEM
+        float sum = 0.f;
+#pragma unroll 1
+        for (int ch = 0; ch < NHALF / 32; ++ch) {
+            const int j0 = cbase + ch * 32;
+            if (j0 >= T) break;
+            float v[32];
+            tc_ld32(lane_addr + (uint32_t)j0, v);
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+                v[e] = ex2_fast(v[e] - mx);
+                sum += v[e];
+            }
+            tc_st32(lane_addr + (uint32_t)j0, v);
+        }
+        red[2 * TM + half * TM + r] = sum;
+        tc_wait_st();
+        epi_barrier();
+        const float inv = 1.f / (red[2 * TM + r] + red[3 * TM + r]);
+
+        // ---- pass 3: p = e / sum -> bf16 -> K-major SWIZZLE_128B slabs (element (r, j): slab j / 64, row r, 16-byte chunk
+        //      ((j % 64) / 8) ^ (r % 8)): the layout TMA produces for a {64, 128} box, which the MMA and the stores consume
+#pragma unroll 1
+        for (int ch = 0; ch < NHALF / 32; ++ch) {
+            const int j0 = cbase + ch * 32;
+            if (j0 >= T) break;
+            float v[32];
+            tc_ld32(lane_addr + (uint32_t)j0, v);
+            uint8_t* rowp = smem + OFF_STG + (j0 >> 6) * (TM * 128) + r * 128;
+            const int ch0 = (j0 & 63) >> 3;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                uint4 u;
+                u.x = pack2(v[8 * t] * inv, v[8 * t + 1] * inv);
+                u.y = pack2(v[8 * t + 2] * inv, v[8 * t + 3] * inv);
+                u.z = pack2(v[8 * t + 4] * inv, v[8 * t + 5] * inv);
+                u.w = pack2(v[8 * t + 6] * inv, v[8 * t + 7] * inv);
+                *reinterpret_cast<uint4*>(rowp + (((ch0 + t) ^ (r & 7)) << 4)) = u;
+            }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + BAR_P_READY);
+
+        // ---- O tile: this warp's 32 rows x 32 of the 64 head columns
+        mbar_wait(bars + BAR_O_DONE, 0);
+        tc_fence_after();
+        {
+            float v[32];
+            tc_ld32(lane_addr + (uint32_t)(TKMAX + 32 * half), v);
+            if (r < TOUT && g < T) {
+                uint4* dst = reinterpret_cast<uint4*>(p.o + ((long)b * T + g) * p.ldo + h * DK + 32 * half);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    uint4 u;
+                    u.x = pack2(v[8 * t], v[8 * t + 1]);
+                    u.y = pack2(v[8 * t + 2], v[8 * t + 3]);
+                    u.z = pack2(v[8 * t + 4], v[8 * t + 5]);
+                    u.w = pack2(v[8 * t + 6], v[8 * t + 7]);
+                    dst[t] = u;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 encoder() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+    }
+    return fn;
+}
+
+// bf16 tensor (batch, rows, inner) with element strides (sbatch, ld, 1); box {64 inner, box_rows}
+static int make_map(CUtensorMap* map, const void* base, long inner, long rows, long ld, long nbatch, long sbatch, int box_rows,
+                    bool store) {
+    auto enc = encoder();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return LASR_ERR_DRIVER; }
+    const cuuint64_t row_bytes = (cuuint64_t)ld * 2;
+    const bool useb = nbatch > 1 && sbatch != 0;
+    cuuint64_t dims[4] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)(useb ? nbatch : 1), 1};
+    cuuint64_t strides[3] = {row_bytes, useb ? (cuuint64_t)sbatch * 2 : row_bytes, useb ? (cuuint64_t)sbatch * 2 : row_bytes};
+    cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (strides[0] & 15) || (strides[1] & 15)) {
+        set_error("rel_attn_fwd: operand base/strides must be 16-byte aligned (base=%p ld=%ld batch stride=%ld)", base, ld, sbatch);
+        return LASR_ERR_BAD_ARG;
+    }
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     store ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("rel_attn_fwd: cuTensorMapEncodeTiled failed (%d): inner=%ld rows=%ld ld=%ld", (int)r, inner, rows, ld);
+        return LASR_ERR_DRIVER;
+    }
+    return LASR_OK;
+}
+
+}  // namespace fa
+}  // namespace lasr
+
+extern "C" {
+using namespace lasr;
+
+int lasr_rel_attn_fwd_supported(int T, int dk) { return (T >= 1 && T <= fa::TKMAX && dk == fa::DK) ? 1 : 0; }
+
+int lasr_rel_attn_fwd(const void* qu, const void* qv, long ldq, const void* k, const void* v, long ldkv, const void* pos, long ldp,
+                      void* probs, int ld, void* o, long ldo, const int64_t* lens, int mask_mode, float scale, int B, int H, int T,
+                      int dk, void* stream) {
+    LASR_REQUIRE(qu && qv && k && v && pos && probs && o && B > 0 && H > 0, "rel_attn_fwd: null operand or empty batch");
+    if (!lasr_rel_attn_fwd_supported(T, dk)) {
+        set_error("rel_attn_fwd: needs 1 <= T <= %d and dk == %d (got T=%d dk=%d)", fa::TKMAX, fa::DK, T, dk);
+        return LASR_ERR_UNSUPPORTED;
+    }
+    LASR_REQUIRE(ld >= T && ld % 8 == 0 && ld <= fa::TKMAX, "rel_attn_fwd: ld must be a multiple of 8 in [T, %d]", fa::TKMAX);
+    LASR_REQUIRE(mask_mode >= 0 && mask_mode <= 3 && (mask_mode == 0 || lens), "rel_attn_fwd: bad mask mode");
+    LASR_REQUIRE(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0, "rel_attn_fwd: O must be 16-byte aligned");
+    const long d = (long)H * dk;
+    CUtensorMap m_qu, m_qv, m_k, m_v, m_p, m_probs;
+    int rc;
+    if ((rc = fa::make_map(&m_qu, qu, d, T, ldq, B, (long)T * ldq, fa::TM, false)) != LASR_OK) return rc;
+    if ((rc = fa::make_map(&m_qv, qv, d, T, ldq, B, (long)T * ldq, fa::TM, false)) != LASR_OK) return rc;
+    if ((rc = fa::make_map(&m_k, k, d, T, ldkv, B, (long)T * ldkv, fa::NHALF, false)) != LASR_OK) return rc;
+    if ((rc = fa::make_map(&m_v, v, d, T, ldkv, B, (long)T * ldkv, 64, false)) != LASR_OK) return rc;
+    if ((rc = fa::make_map(&m_p, pos, d, T, ldp, 1, 0, fa::NHALF, false)) != LASR_OK) return rc;
+    if ((rc = fa::make_map(&m_probs, probs, ld, T, ld, (long)B * H, (long)T * ld, fa::TOUT, true)) != LASR_OK) return rc;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(fa::rel_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fa::SMEM_BYTES) != cudaSuccess)
+            return check_launch("rel_attn_fwd smem attr");
+        configured = true;
+    }
+    fa::Params p;
+    p.o = reinterpret_cast<bf16*>(o);
+    p.ldo = ldo;
+    p.lens = lens;
+    p.mask_mode = mask_mode;
+    p.c2 = scale * 1.4426950408889634f;
+    p.B = B; p.H = H; p.T = T; p.ld = ld;
+    p.tiles = (T + fa::TOUT - 1) / fa::TOUT;
+    launch_pdl(fa::rel_attn_fwd_kernel, dim3((unsigned)(p.tiles * H * B)), dim3(fa::THREADS), (size_t)fa::SMEM_BYTES,
+               (cudaStream_t)stream, m_qu, m_qv, m_k, m_v, m_p, m_probs, p);
+    return check_launch("rel_attn_fwd");
+}
+
+}  // extern "C"

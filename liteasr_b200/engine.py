@@ -45,6 +45,8 @@ class Engine:
         # autocast's matmul hands to the softmax; halves the score traffic at a bf16 rounding of the pre-softmax logits
         self.sdt = store.adt if (store.adt == torch.bfloat16 and os.environ.get("LASR_SCORES_BF16", "0") == "1") else torch.float32
         self.dev = store.device
+        # LASR_FUSED_ATTN=0: developer switch back to GEMM -> softmax kernel -> GEMM for the rel-pos attention forward
+        self.fused_attn = os.environ.get("LASR_FUSED_ATTN", "1") != "0"
 
     # ------------------------------------------------------------------------------------------
     # small helpers
@@ -182,6 +184,13 @@ class Engine:
         d = H * dk
         ld = _ceil(Tk, 8)
         scale = dk ** -0.5
+        if (qv is not None and Tq == Tk and self.adt == torch.bfloat16 and self.fused_attn and ops.rel_attn_fwd_supported(Tk, dk)
+                and q.stride(0) == qv.stride(0) and k.stride(0) == v.stride(0)):
+            # one tcgen05 kernel: both score contractions, rel_shift, scale, mask, softmax and probs.V (csrc/attn_fused.cu)
+            probs = _empty((B, H, Tq, ld), self.adt, self.dev)
+            o = _empty((B * Tq, d), self.adt, self.dev)
+            ops.rel_attn_fwd(q, qv, k, v, p, probs, o, lens, mask_mode, scale, B, H, Tq, dk)
+            return NS(q=q, k=k, v=v, qv=qv, p=p, probs=probs, o=o, B=B, H=H, Tq=Tq, Tk=Tk, dk=dk, ld=ld, scale=scale)
         ac = _empty((B, H, Tq, ld), self.sdt, self.dev)
         # n_store = ld: the padding columns [Tk, ld) are written too (zeros), which keeps the whole epilogue on the vector path
         ops.gemm(q, k, ac, Tq, Tk, dk, lda=q.stride(0), ldb=k.stride(0), ldc=ld, batch=(B, H), sa=(Tq * q.stride(0), dk),

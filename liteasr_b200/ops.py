@@ -331,6 +331,22 @@ def attn_softmax_fwd(ac, bd, probs, lens, mask_mode, causal, scale, Tk):
                "attn_softmax_fwd")
 
 
+def rel_attn_fwd_supported(T: int, dk: int) -> bool:
+    return bool(_lib.lib().lasr_rel_attn_fwd_supported(_i(T), _i(dk)))
+
+
+def rel_attn_fwd(qu, qv, k, v, pos, probs, o, lens, mask_mode, scale, B, H, T, dk):
+    """Fused rel-pos attention forward (bf16): probs (B,H,T,ld) and o (B*T, H*dk) from qu/qv/k/v (B*T, H*dk views) and pos (T, H*dk)."""
+    _require_cuda(qu, qv, k, v, pos, probs, o, lens)
+    for t in (qu, qv, k, v, pos, probs, o):
+        if t.dtype != torch.bfloat16:
+            raise TypeError("rel_attn_fwd takes bf16 tensors")
+    assert qu.stride(0) == qv.stride(0) and k.stride(0) == v.stride(0) and probs.is_contiguous()
+    _lib.check(_lib.lib().lasr_rel_attn_fwd(_ptr(qu), _ptr(qv), _l(qu.stride(0)), _ptr(k), _ptr(v), _l(k.stride(0)), _ptr(pos), _l(pos.stride(0)),
+                                            _ptr(probs), _i(probs.shape[-1]), _ptr(o), _l(o.stride(0)), _ptr(lens), _i(mask_mode), _f(scale),
+                                            _i(B), _i(H), _i(T), _i(dk), _stream()), "rel_attn_fwd")
+
+
 def attn_softmax_bwd(probs, dprobs, dsc, dbd, scale, Tk):
     B, H, Tq, ld = probs.shape
     _lib.check(_lib.lib().lasr_attn_softmax_bwd(_ptr(probs), _ptr(dprobs), _i(dtype_code(dprobs)), _ptr(dsc), _ptr(dbd), _i(dtype_code(probs)), _f(scale),
