@@ -20,7 +20,8 @@
 //   warp 0      TMA: (q+v) tile + P, (q+u) tile + K, then V into P's buffer once the bd MMAs retired; at the end the bulk
 //               tensor stores of the probability tile
 //   warp 1      MMA issuer: bd -> TMEM[0,320) ; (drained) ac -> TMEM[0,320) ; p.V -> TMEM[320,384)
-//   warps 2..9  two warps per TMEM lane quarter, each owning one 160-column half of its 32 rows:
+//   warps 2..17 four warps per TMEM lane quarter, each owning 80 of the 320 columns of its 32 rows (16 columns per TMEM access;
+//               the phases are latency chains per warp, so the warp count is what hides them):
 //               shift : bd row (TMEM) -> * scale*log2(e) -> fp16 -> flat buffer
 //               pass 1: s = ac * scale*log2(e) + shifted bd, mask, row max        (s written back to TMEM in place)
 //               pass 2: e = 2^(s - max), row sum                                  (e written back to TMEM in place)
@@ -42,18 +43,24 @@ constexpr int TOUT = 127;    // attention rows per tile
 constexpr int TKMAX = 320;   // keys
 constexpr int NHALF = 160;   // MMA N of one score half
 constexpr int DK = 64;
-constexpr int EPI_W = 8;
+constexpr int EPI_W = 16;     // four warps per TMEM lane quarter, each owning 80 of the 320 columns of its 32 rows
+constexpr int PARTW = TKMAX / 4;
+constexpr int CH = 16;        // columns per TMEM load / store
 constexpr int THREADS = 64 + 32 * EPI_W;
 
-constexpr int OFF_STG = 0;                        // flat fp16 shift buffer, then the 5 x (128 x 64) bf16 probability slabs
-constexpr int STG_BYTES = 5 * TM * 128;           // 81920
+// Flat fp16 shift buffer: position L = r (T+1) + c + (r0 + 1 - T) of bd[r0 + r][c] ranges over [1 - T, 128 T + 127], so with
+// FLAT_PAD elements in front no write needs a bounds check.  The 5 x (128 x 64) bf16 probability slabs alias its start.
+constexpr int FLAT_PAD = TKMAX;
+constexpr int OFF_STG = 0;
+constexpr int STG_BYTES = ((FLAT_PAD + 129 * TKMAX + 128) * 2 + 1023) / 1024 * 1024;  // 83968 (>= 5 * 128 * 128 = 81920)
 constexpr int OFF_QU = OFF_STG + STG_BYTES;       // (q+u) tile, 128 x 64 bf16
 constexpr int OFF_QV = OFF_QU + TM * 128;         // (q+v) tile
 constexpr int OFF_K = OFF_QV + TM * 128;          // K: two 160-row halves
 constexpr int OFF_P = OFF_K + 2 * NHALF * 128;    // P: two 160-row halves; later V: five 64-key atoms
-constexpr int OFF_BAR = OFF_P + 2 * NHALF * 128;  // 196608
-constexpr int OFF_RED = OFF_BAR + 128;
-constexpr int SMEM_BYTES = OFF_RED + 2 * 2 * TM * 4 + 1024;
+constexpr int OFF_BAR = OFF_P + 2 * NHALF * 128;
+constexpr int OFF_RED = OFF_BAR + 128;            // [max | sum][column part][row]
+constexpr int SMEM_BYTES = OFF_RED + 2 * 4 * TM * 4 + 1024;
+static_assert(STG_BYTES >= 5 * TM * 128 && SMEM_BYTES <= 232448, "shared-memory budget");
 
 enum { BAR_BDIN = 0, BAR_ACIN, BAR_V, BAR_BD_DONE, BAR_BD_DRAINED, BAR_AC_DONE, BAR_P_READY, BAR_O_DONE, NBARS };
 
@@ -77,6 +84,21 @@ __device__ __forceinline__ void tc_st32(uint32_t taddr, const float* v) {
           "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
           "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
         : "memory");
+}
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const float* v) {
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+// two fp32 -> packed fp16 (lo = a, hi = b), round to nearest, saturating to +-65504 (F2FP.SATFINITE.F16.F32.PACK_AB)
+__device__ __forceinline__ uint32_t f16x2_sat(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
 }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_W) : "memory"); }
@@ -191,7 +213,7 @@ rel_attn_fwd_kernel(const __grid_constant__ CUtensorMap m_qu, const __grid_const
             tc_commit(bars + BAR_O_DONE);
         }
     } else {
-        const int q = warp & 3, half = (warp - 2) >> 2;
+        const int q = warp & 3, part = (warp - 2) >> 2;
         const int r = q * 32 + lane, g = r0 + r;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         const float c2 = p.c2;
@@ -203,31 +225,36 @@ rel_attn_fwd_kernel(const __grid_constant__ CUtensorMap m_qu, const __grid_const
             else if (p.mask_mode == 3) k = (l + 3) / 4;
             klen = (int)(k < T ? (k < 0 ? 0 : k) : T);
         }
-        const int cbase = half * NHALF;
+        const int cb = part * PARTW;
+        uint16_t* flat = reinterpret_cast<uint16_t*>(smem + OFF_STG) + FLAT_PAD;
 
         // ---- shift: bd row g -> flat buffer (see the header comment)
         mbar_wait(bars + BAR_BD_DONE, 0);
         tc_fence_after();
         {
-            __half* stg = reinterpret_cast<__half*>(smem + OFF_STG);
             const int off = r * (T + 1) + r0 - T;  // flat position of the padded zero of bd row g
-            const int lmax = TOUT * T;
-            const int lo = max(0, -(off + 1)), hi = min(T, lmax - off - 1);  // columns c with 0 <= off + 1 + c < lmax
-            if (half == 0 && off >= 0 && off < lmax) stg[off] = __float2half_rn(0.f);
+            if (part == 0) flat[off] = 0;
 #pragma unroll 1
-            for (int ch = 0; ch < NHALF / 32; ++ch) {
-                const int c0 = cbase + ch * 32;
+            for (int ch = 0; ch < PARTW / CH; ++ch) {
+                const int c0 = cb + ch * CH;
                 if (c0 >= T) break;  // warp-uniform
-                float v[32];
-                tc_ld32(lane_addr + (uint32_t)c0, v);
-                __half* dst = stg + off + 1 + c0;
-                if (c0 >= lo && c0 + 32 <= hi) {
+                float v[CH];
+                tc_ld16(lane_addr + (uint32_t)c0, v);
+                uint16_t* dst = flat + off + 1 + c0;
+                if (c0 + CH <= T) {
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) dst[e] = __float2half_rn(fminf(fmaxf(v[e] * c2, -60000.f), 60000.f));
-                } else {
+                    for (int e = 0; e < CH; e += 2) {
+                        const uint32_t h2 = f16x2_sat(v[e] * c2, v[e + 1] * c2);
+                        dst[e] = (uint16_t)(h2 & 0xffffu);
+                        dst[e + 1] = (uint16_t)(h2 >> 16);
+                    }
+                } else {  // columns >= T are zero products of the zero-filled P rows: they must not reach the next row's slots
 #pragma unroll
-                    for (int e = 0; e < 32; ++e)
-                        if (c0 + e >= lo && c0 + e < hi) dst[e] = __float2half_rn(fminf(fmaxf(v[e] * c2, -60000.f), 60000.f));
+                    for (int e = 0; e < CH; e += 2) {
+                        const uint32_t h2 = f16x2_sat(v[e] * c2, v[e + 1] * c2);
+                        if (c0 + e < T) dst[e] = (uint16_t)(h2 & 0xffffu);
+                        if (c0 + e + 1 < T) dst[e + 1] = (uint16_t)(h2 >> 16);
+                    }
                 }
             }
         }
@@ -241,62 +268,70 @@ rel_attn_fwd_kernel(const __grid_constant__ CUtensorMap m_qu, const __grid_const
         tc_fence_after();
         float mx = -INFINITY;
         {
-            const __half* src = reinterpret_cast<const __half*>(smem + OFF_STG) + r * T + cbase;
+            const __half_raw* src = reinterpret_cast<const __half_raw*>(flat) + r * T + cb;
 #pragma unroll 1
-            for (int ch = 0; ch < NHALF / 32; ++ch) {
-                const int j0 = cbase + ch * 32;
+            for (int ch = 0; ch < PARTW / CH; ++ch) {
+                const int j0 = cb + ch * CH;
                 if (j0 >= T) break;
-                float v[32];
-                tc_ld32(lane_addr + (uint32_t)j0, v);
+                float v[CH];
+                tc_ld16(lane_addr + (uint32_t)j0, v);
+                if (j0 + CH <= klen) {  // no masked or padding column in this chunk (warp-uniform)
 #pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    const int j = j0 + e;
-                    float s = fmaf(v[e], c2, __half2float(src[ch * 32 + e]));
-                    s = (j < klen) ? s : -1e38f;
-                    s = (j < T) ? s : -INFINITY;
-                    v[e] = s;
-                    mx = fmaxf(mx, s);
+                    for (int e = 0; e < CH; ++e) {
+                        v[e] = fmaf(v[e], c2, __half2float(__half(src[ch * CH + e])));
+                        mx = fmaxf(mx, v[e]);
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < CH; ++e) {
+                        const int j = j0 + e;
+                        float s = fmaf(v[e], c2, __half2float(__half(src[ch * CH + e])));
+                        s = (j < klen) ? s : -1e38f;
+                        s = (j < T) ? s : -INFINITY;
+                        v[e] = s;
+                        mx = fmaxf(mx, s);
+                    }
                 }
-                tc_st32(lane_addr + (uint32_t)j0, v);
+                tc_st16(lane_addr + (uint32_t)j0, v);
             }
         }
-        red[half * TM + r] = mx;
+        red[part * TM + r] = mx;
         tc_wait_st();
         epi_barrier();
-        mx = fmaxf(red[r], red[TM + r]);
+        mx = fmaxf(fmaxf(red[r], red[TM + r]), fmaxf(red[2 * TM + r], red[3 * TM + r]));
 
         // ---- pass 2: e = 2^(s - max), row sum; e replaces s in TMEM
         float sum = 0.f;
 #pragma unroll 1
-        for (int ch = 0; ch < NHALF / 32; ++ch) {
-            const int j0 = cbase + ch * 32;
+        for (int ch = 0; ch < PARTW / CH; ++ch) {
+            const int j0 = cb + ch * CH;
             if (j0 >= T) break;
-            float v[32];
-            tc_ld32(lane_addr + (uint32_t)j0, v);
+            float v[CH];
+            tc_ld16(lane_addr + (uint32_t)j0, v);
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
+            for (int e = 0; e < CH; ++e) {
                 v[e] = ex2_fast(v[e] - mx);
                 sum += v[e];
             }
-            tc_st32(lane_addr + (uint32_t)j0, v);
+            tc_st16(lane_addr + (uint32_t)j0, v);
         }
-        red[2 * TM + half * TM + r] = sum;
+        red[4 * TM + part * TM + r] = sum;
         tc_wait_st();
         epi_barrier();
-        const float inv = 1.f / (red[2 * TM + r] + red[3 * TM + r]);
+        const float inv = 1.f / ((red[4 * TM + r] + red[5 * TM + r]) + (red[6 * TM + r] + red[7 * TM + r]));
 
         // ---- pass 3: p = e / sum -> bf16 -> K-major SWIZZLE_128B slabs (element (r, j): slab j / 64, row r, 16-byte chunk
         //      ((j % 64) / 8) ^ (r % 8)): the layout TMA produces for a {64, 128} box, which the MMA and the stores consume
 #pragma unroll 1
-        for (int ch = 0; ch < NHALF / 32; ++ch) {
-            const int j0 = cbase + ch * 32;
+        for (int ch = 0; ch < PARTW / CH; ++ch) {
+            const int j0 = cb + ch * CH;
             if (j0 >= T) break;
-            float v[32];
-            tc_ld32(lane_addr + (uint32_t)j0, v);
+            float v[CH];
+            tc_ld16(lane_addr + (uint32_t)j0, v);
             uint8_t* rowp = smem + OFF_STG + (j0 >> 6) * (TM * 128) + r * 128;
             const int ch0 = (j0 & 63) >> 3;
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
+            for (int t = 0; t < CH / 8; ++t) {
                 uint4 u;
                 u.x = pack2(v[8 * t] * inv, v[8 * t + 1] * inv);
                 u.y = pack2(v[8 * t + 2] * inv, v[8 * t + 3] * inv);
@@ -310,16 +345,16 @@ rel_attn_fwd_kernel(const __grid_constant__ CUtensorMap m_qu, const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive(bars + BAR_P_READY);
 
-        // ---- O tile: this warp's 32 rows x 32 of the 64 head columns
+        // ---- O tile: this warp's 32 rows x 16 of the 64 head columns
         mbar_wait(bars + BAR_O_DONE, 0);
         tc_fence_after();
         {
-            float v[32];
-            tc_ld32(lane_addr + (uint32_t)(TKMAX + 32 * half), v);
+            float v[CH];
+            tc_ld16(lane_addr + (uint32_t)(TKMAX + CH * part), v);
             if (r < TOUT && g < T) {
-                uint4* dst = reinterpret_cast<uint4*>(p.o + ((long)b * T + g) * p.ldo + h * DK + 32 * half);
+                uint4* dst = reinterpret_cast<uint4*>(p.o + ((long)b * T + g) * p.ldo + h * DK + CH * part);
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
+                for (int t = 0; t < CH / 8; ++t) {
                     uint4 u;
                     u.x = pack2(v[8 * t], v[8 * t + 1]);
                     u.y = pack2(v[8 * t + 2], v[8 * t + 3]);
