@@ -233,6 +233,7 @@ int lasr_attn_softmax_bwd(const void* probs, const void* dprobs, int s_dtype, vo
  * other shapes return LASR_ERR_UNSUPPORTED and the caller keeps the unfused sequence.  mask_mode as lasr_attn_softmax_fwd.
  * ------------------------------------------------------------------------------------------------ */
 int lasr_rel_attn_fwd_supported(int T, int dk);
+void lasr_rel_attn_fwd_set_trace(void* buf); /* developer aid: 16 clock64 stamps per CTA (NULL = off) */
 int lasr_rel_attn_fwd(const void* qu, const void* qv, long ldq, const void* k, const void* v, long ldkv, const void* pos, long ldp,
                       void* probs, int ld, void* o, long ldo, const int64_t* lens, int mask_mode, float scale, int B, int H, int T,
                       int dk, void* stream);

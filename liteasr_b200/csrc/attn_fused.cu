@@ -17,16 +17,16 @@
 // shifted rows are read back CONTIGUOUSLY at r T + j -- no per-element index arithmetic.  Output row i needs bd rows i and
 // i + 1, hence a 128-row MMA tile yields 127 attention rows (tile stride 127).
 //
-//   warp 0      TMA: (q+v) tile + P, (q+u) tile + K, then V into P's buffer once the bd MMAs retired; at the end the bulk
-//               tensor stores of the probability tile
-//   warp 1      MMA issuer: bd -> TMEM[0,320) ; (drained) ac -> TMEM[0,320) ; p.V -> TMEM[320,384)
-//   warps 2..17 four warps per TMEM lane quarter, each owning 80 of the 320 columns of its 32 rows (16 columns per TMEM access;
-//               the phases are latency chains per warp, so the warp count is what hides them):
+//   thread 0    between its own worker phases: TMA ((q+v) tile + P, (q+u) tile + K, V into P's buffer once the bd MMAs
+//               retired, at the end the bulk tensor stores of the probability tile) and MMA issue
+//               (bd -> TMEM[0,320) ; (drained) ac -> TMEM[0,320) ; p.V -> TMEM[320,384)) -- the two roles are sequential
+//   16 warps    four per TMEM lane quarter, each owning 80 of the 320 columns of its 32 rows, held in registers
+//               (16 warps = 128 registers per thread; the phases are latency chains per warp, so the warp count hides them):
 //               shift : bd row (TMEM) -> * scale*log2(e) -> fp16 -> flat buffer
-//               pass 1: s = ac * scale*log2(e) + shifted bd, mask, row max        (s written back to TMEM in place)
-//               pass 2: e = 2^(s - max), row sum                                  (e written back to TMEM in place)
-//               pass 3: p = e / sum -> bf16 -> the K-major SWIZZLE_128B tile (aliases the flat buffer: all its reads
-//                       happened in pass 1) that is both the A operand of p.V and the source of the probability stores
+//               pass A: s = ac * scale*log2(e) + shifted bd, mask; the 80 values stay in registers
+//               pass B: e = 2^(s - m) against the warp's own row maximum m, partial sum; ONE exchange of (m, sum) per row
+//               pass C: p = e * 2^(m - max) / total -> bf16 -> the K-major SWIZZLE_128B tile (aliases the flat buffer: all
+//                       its reads happened in pass A) that is both the A operand of p.V and the source of the stores
 //               O     : TMEM[320,384) -> bf16 -> global
 #include <cuda_fp16.h>
 
@@ -46,7 +46,7 @@ constexpr int DK = 64;
 constexpr int EPI_W = 16;     // four warps per TMEM lane quarter, each owning 80 of the 320 columns of its 32 rows
 constexpr int PARTW = TKMAX / 4;
 constexpr int CH = 16;        // columns per TMEM load / store
-constexpr int THREADS = 64 + 32 * EPI_W;
+constexpr int THREADS = 32 * EPI_W;
 
 // Flat fp16 shift buffer: position L = r (T+1) + c + (r0 + 1 - T) of bd[r0 + r][c] ranges over [1 - T, 128 T + 127], so with
 // FLAT_PAD elements in front no write needs a bounds check.  The 5 x (128 x 64) bf16 probability slabs alias its start.
@@ -71,7 +71,13 @@ struct Params {
     int mask_mode;
     float c2;  // scale * log2(e)
     int B, H, T, ld, tiles;
+    long long* trace;  // developer aid (lasr_rel_attn_fwd_set_trace): 16 clock64 stamps per CTA from one epilogue warp
 };
+
+#define FA_STAMP(i)                                                                  \
+    do {                                                                             \
+        if (p.trace && warp == 6 && lane == 0) p.trace[(long)blockIdx.x * 16 + (i)] = clock64(); \
+    } while (0)
 
 __device__ __forceinline__ void tc_st32(uint32_t taddr, const float* v) {
     const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
@@ -112,6 +118,19 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// 16 x 16 columns of one TMEM row: all loads in flight before the single wait (the phases are latency chains per warp)
+__device__ __forceinline__ void tc_ld16_issue(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 __global__ void __launch_bounds__(THREADS, 1)
 rel_attn_fwd_kernel(const __grid_constant__ CUtensorMap m_qu, const __grid_constant__ CUtensorMap m_qv,
                     const __grid_constant__ CUtensorMap m_k, const __grid_constant__ CUtensorMap m_v,
@@ -120,14 +139,19 @@ rel_attn_fwd_kernel(const __grid_constant__ CUtensorMap m_qu, const __grid_const
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 8 * NBARS);
-    float* red = reinterpret_cast<float*>(smem + OFF_RED);  // [max|sum][half][row]
+    float* red = reinterpret_cast<float*>(smem + OFF_RED);  // [max | sum][column part][row]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    FA_STAMP(0);
     const int tile = blockIdx.x % p.tiles, bh = blockIdx.x / p.tiles;
     const int h = bh % p.H, b = bh / p.H;
     const int T = p.T, r0 = tile * TOUT;
+    // The two single-thread roles (TMA producer, MMA issuer) are strictly sequential here, so ONE thread of an ordinary
+    // worker warp plays both between its own phases: 16 warps = 4 per scheduler leave 128 registers per thread, which is what
+    // keeps a warp's 80 score columns in registers without spills.
+    const bool ctl = (warp == 0 && lane == 0);
 
-    if (warp == 0 && lane == 0) {
+    if (ctl) {
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&m_qu) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&m_qv) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&m_k) : "memory");
@@ -150,184 +174,201 @@ rel_attn_fwd_kernel(const __grid_constant__ CUtensorMap m_qu, const __grid_const
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    FA_STAMP(1);
 
-    const int kslabs = (p.ld + 63) >> 6;  // 64-column slabs of the probability tile that hold stored columns
+    const uint32_t id_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NHALF >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+    const uint32_t id_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(DK >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+    const uint32_t s_stg = smem_u32(smem + OFF_STG), s_qu = smem_u32(smem + OFF_QU), s_qv = smem_u32(smem + OFF_QV);
+    const uint32_t s_k = smem_u32(smem + OFF_K), s_p = smem_u32(smem + OFF_P);
 
-    if (warp == 0) {
-        if (lane == 0) {
-            mbar_arrive_expect_tx(bars + BAR_BDIN, TM * 128 + 2 * NHALF * 128);
-            tma_load_4d(smem + OFF_QV, &m_qv, bars + BAR_BDIN, h * DK, r0, b, 0);
-            tma_load_4d(smem + OFF_P, &m_p, bars + BAR_BDIN, h * DK, 0, 0, 0);
-            tma_load_4d(smem + OFF_P + NHALF * 128, &m_p, bars + BAR_BDIN, h * DK, NHALF, 0, 0);
-            mbar_arrive_expect_tx(bars + BAR_ACIN, TM * 128 + 2 * NHALF * 128);
-            tma_load_4d(smem + OFF_QU, &m_qu, bars + BAR_ACIN, h * DK, r0, b, 0);
-            tma_load_4d(smem + OFF_K, &m_k, bars + BAR_ACIN, h * DK, 0, b, 0);
-            tma_load_4d(smem + OFF_K + NHALF * 128, &m_k, bars + BAR_ACIN, h * DK, NHALF, b, 0);
-            // V replaces P once the bd MMAs have read it
-            mbar_wait(bars + BAR_BD_DONE, 0);
-            mbar_arrive_expect_tx(bars + BAR_V, 5 * 8192);
-            for (int kb = 0; kb < 5; ++kb) tma_load_4d(smem + OFF_P + kb * 8192, &m_v, bars + BAR_V, h * DK, 64 * kb, b, 0);
-            // probabilities: rows [r0, r0 + 127) x stored columns, straight from the MMA operand tile
-            mbar_wait(bars + BAR_P_READY, 0);
-            for (int kb = 0; kb < kslabs; ++kb) tma_store_4d(&m_probs, smem + OFF_STG + kb * (TM * 128), 64 * kb, r0, bh, 0);
-            bulk_commit();
-            bulk_wait_read<0>();
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t id_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NHALF >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-            const uint32_t id_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(DK >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-            const uint32_t s_stg = smem_u32(smem + OFF_STG), s_qu = smem_u32(smem + OFF_QU), s_qv = smem_u32(smem + OFF_QV);
-            const uint32_t s_k = smem_u32(smem + OFF_K), s_p = smem_u32(smem + OFF_P);
-            // bd = (q+v) . P^T
-            mbar_wait(bars + BAR_BDIN, 0);
-            tc_fence_after();
-#pragma unroll
-            for (int nh = 0; nh < 2; ++nh)
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                    tc_mma_bf16(tmem_base + nh * NHALF, umma_desc(s_qv + kk * 32, 16, 1024),
-                                umma_desc(s_p + nh * (NHALF * 128) + kk * 32, 16, 1024), id_s, kk > 0 ? 1u : 0u);
-            tc_commit(bars + BAR_BD_DONE);
-            // ac = (q+u) . K^T into the same columns once every warp has copied its bd rows out
-            mbar_wait(bars + BAR_ACIN, 0);
-            mbar_wait(bars + BAR_BD_DRAINED, 0);
-            tc_fence_after();
-#pragma unroll
-            for (int nh = 0; nh < 2; ++nh)
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                    tc_mma_bf16(tmem_base + nh * NHALF, umma_desc(s_qu + kk * 32, 16, 1024),
-                                umma_desc(s_k + nh * (NHALF * 128) + kk * 32, 16, 1024), id_s, kk > 0 ? 1u : 0u);
-            tc_commit(bars + BAR_AC_DONE);
-            // O = p . V  (K = keys, 16 per instruction; key blocks beyond T hold zero probabilities and are skipped)
-            mbar_wait(bars + BAR_V, 0);
-            mbar_wait(bars + BAR_P_READY, 0);
-            tc_fence_after();
-            const int ksteps = (T + 15) >> 4;
-            for (int ks = 0; ks < ksteps; ++ks) {
-                const int kb = ks >> 2, kk = ks & 3;
-                tc_mma_bf16(tmem_base + TKMAX, umma_desc(s_stg + kb * (TM * 128) + kk * 32, 16, 1024),
-                            umma_desc(s_p + kb * 8192 + kk * 2048, 8192, 1024), id_o, ks > 0 ? 1u : 0u);
-            }
-            tc_commit(bars + BAR_O_DONE);
-        }
-    } else {
-        const int q = warp & 3, part = (warp - 2) >> 2;
-        const int r = q * 32 + lane, g = r0 + r;
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-        const float c2 = p.c2;
-        int klen = T;
-        if (p.mask_mode != 0 && p.lens) {
-            const long l = p.lens[b];
-            long k = l;
-            if (p.mask_mode == 2) k = l + 1;
-            else if (p.mask_mode == 3) k = (l + 3) / 4;
-            klen = (int)(k < T ? (k < 0 ? 0 : k) : T);
-        }
-        const int cb = part * PARTW;
-        uint16_t* flat = reinterpret_cast<uint16_t*>(smem + OFF_STG) + FLAT_PAD;
-
-        // ---- shift: bd row g -> flat buffer (see the header comment)
-        mbar_wait(bars + BAR_BD_DONE, 0);
+    if (ctl) {
+        mbar_arrive_expect_tx(bars + BAR_BDIN, TM * 128 + 2 * NHALF * 128);
+        tma_load_4d(smem + OFF_QV, &m_qv, bars + BAR_BDIN, h * DK, r0, b, 0);
+        tma_load_4d(smem + OFF_P, &m_p, bars + BAR_BDIN, h * DK, 0, 0, 0);
+        tma_load_4d(smem + OFF_P + NHALF * 128, &m_p, bars + BAR_BDIN, h * DK, NHALF, 0, 0);
+        mbar_arrive_expect_tx(bars + BAR_ACIN, TM * 128 + 2 * NHALF * 128);
+        tma_load_4d(smem + OFF_QU, &m_qu, bars + BAR_ACIN, h * DK, r0, b, 0);
+        tma_load_4d(smem + OFF_K, &m_k, bars + BAR_ACIN, h * DK, 0, b, 0);
+        tma_load_4d(smem + OFF_K + NHALF * 128, &m_k, bars + BAR_ACIN, h * DK, NHALF, b, 0);
+        // bd = (q+v) . P^T
+        mbar_wait(bars + BAR_BDIN, 0);
         tc_fence_after();
-        {
-            const int off = r * (T + 1) + r0 - T;  // flat position of the padded zero of bd row g
-            if (part == 0) flat[off] = 0;
-#pragma unroll 1
-            for (int ch = 0; ch < PARTW / CH; ++ch) {
-                const int c0 = cb + ch * CH;
-                if (c0 >= T) break;  // warp-uniform
-                float v[CH];
-                tc_ld16(lane_addr + (uint32_t)c0, v);
-                uint16_t* dst = flat + off + 1 + c0;
-                if (c0 + CH <= T) {
 #pragma unroll
-                    for (int e = 0; e < CH; e += 2) {
-                        const uint32_t h2 = f16x2_sat(v[e] * c2, v[e + 1] * c2);
-                        dst[e] = (uint16_t)(h2 & 0xffffu);
-                        dst[e + 1] = (uint16_t)(h2 >> 16);
-                    }
-                } else {  // columns >= T are zero products of the zero-filled P rows: they must not reach the next row's slots
+        for (int nh = 0; nh < 2; ++nh)
 #pragma unroll
-                    for (int e = 0; e < CH; e += 2) {
-                        const uint32_t h2 = f16x2_sat(v[e] * c2, v[e + 1] * c2);
-                        if (c0 + e < T) dst[e] = (uint16_t)(h2 & 0xffffu);
-                        if (c0 + e + 1 < T) dst[e + 1] = (uint16_t)(h2 >> 16);
-                    }
-                }
-            }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bars + BAR_BD_DRAINED);
-        epi_barrier();  // the flat buffer is complete
+            for (int kk = 0; kk < 4; ++kk)
+                tc_mma_bf16(tmem_base + nh * NHALF, umma_desc(s_qv + kk * 32, 16, 1024),
+                            umma_desc(s_p + nh * (NHALF * 128) + kk * 32, 16, 1024), id_s, kk > 0 ? 1u : 0u);
+        tc_commit(bars + BAR_BD_DONE);
+    }
+    __syncwarp();
 
-        // ---- pass 1: s = ac * c2 + shifted bd, mask, row max; s replaces ac in TMEM
-        mbar_wait(bars + BAR_AC_DONE, 0);
-        tc_fence_after();
-        float mx = -INFINITY;
-        {
-            const __half_raw* src = reinterpret_cast<const __half_raw*>(flat) + r * T + cb;
-#pragma unroll 1
-            for (int ch = 0; ch < PARTW / CH; ++ch) {
-                const int j0 = cb + ch * CH;
-                if (j0 >= T) break;
-                float v[CH];
-                tc_ld16(lane_addr + (uint32_t)j0, v);
-                if (j0 + CH <= klen) {  // no masked or padding column in this chunk (warp-uniform)
+    const int q = warp & 3, part = warp >> 2;
+    const int r = q * 32 + lane, g = r0 + r;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float c2 = p.c2;
+    int klen = T;
+    if (p.mask_mode != 0 && p.lens) {
+        const long l = p.lens[b];
+        long k = l;
+        if (p.mask_mode == 2) k = l + 1;
+        else if (p.mask_mode == 3) k = (l + 3) / 4;
+        klen = (int)(k < T ? (k < 0 ? 0 : k) : T);
+    }
+    const int cb = part * PARTW;
+    uint16_t* flat = reinterpret_cast<uint16_t*>(smem + OFF_STG) + FLAT_PAD;
+    float sv[PARTW];  // the warp's 80 columns of its rows: bd, then scores, then exponentials
+
+    // ---- shift: bd row g -> flat buffer (see the header comment)
+    mbar_wait(bars + BAR_BD_DONE, 0);
+    tc_fence_after();
+    FA_STAMP(2);
+    if (ctl) {  // V replaces P now that the bd MMAs have read it
+        mbar_arrive_expect_tx(bars + BAR_V, 5 * 8192);
+        for (int kb = 0; kb < 5; ++kb) tma_load_4d(smem + OFF_P + kb * 8192, &m_v, bars + BAR_V, h * DK, 64 * kb, b, 0);
+    }
+    __syncwarp();
+    {
 #pragma unroll
-                    for (int e = 0; e < CH; ++e) {
-                        v[e] = fmaf(v[e], c2, __half2float(__half(src[ch * CH + e])));
-                        mx = fmaxf(mx, v[e]);
-                    }
+        for (int ch = 0; ch < PARTW / CH; ++ch)
+            if (cb + ch * CH < T) tc_ld16_issue(lane_addr + (uint32_t)(cb + ch * CH), sv + ch * CH);  // warp-uniform
+        tc_wait_ld();
+        const int off = r * (T + 1) + r0 - T;  // flat position of the padded zero of bd row g
+        if (part == 0) flat[off] = 0;
+        uint16_t* dst = flat + off + 1 + cb;
+        // T odd: the row stride T + 1 is even, so every lane of the warp has the same 4-byte alignment and pairs of
+        // halves go out as 32-bit stores (the phase is bound by shared-memory store wavefronts)
+        const int par = (T & 1) ? ((off + 1 + cb) & 1) : 2;  // 0 aligned | 1 off by one half | 2 per-lane (scalar stores)
+#pragma unroll
+        for (int ch = 0; ch < PARTW / CH; ++ch) {
+            const int c0 = cb + ch * CH;
+            const float* v = sv + ch * CH;
+            uint16_t* d = dst + ch * CH;
+            if (c0 + CH <= T) {  // warp-uniform
+                if (par == 0) {
+#pragma unroll
+                    for (int e = 0; e < CH; e += 2) *reinterpret_cast<uint32_t*>(d + e) = f16x2_sat(v[e] * c2, v[e + 1] * c2);
+                } else if (par == 1) {
+                    d[0] = (uint16_t)(f16x2_sat(v[0] * c2, 0.f) & 0xffffu);
+#pragma unroll
+                    for (int e = 1; e + 1 < CH; e += 2) *reinterpret_cast<uint32_t*>(d + e) = f16x2_sat(v[e] * c2, v[e + 1] * c2);
+                    d[CH - 1] = (uint16_t)(f16x2_sat(v[CH - 1] * c2, 0.f) & 0xffffu);
                 } else {
 #pragma unroll
-                    for (int e = 0; e < CH; ++e) {
-                        const int j = j0 + e;
-                        float s = fmaf(v[e], c2, __half2float(__half(src[ch * CH + e])));
-                        s = (j < klen) ? s : -1e38f;
-                        s = (j < T) ? s : -INFINITY;
-                        v[e] = s;
-                        mx = fmaxf(mx, s);
+                    for (int e = 0; e < CH; e += 2) {
+                        const uint32_t h2 = f16x2_sat(v[e] * c2, v[e + 1] * c2);
+                        d[e] = (uint16_t)(h2 & 0xffffu);
+                        d[e + 1] = (uint16_t)(h2 >> 16);
                     }
                 }
-                tc_st16(lane_addr + (uint32_t)j0, v);
-            }
-        }
-        red[part * TM + r] = mx;
-        tc_wait_st();
-        epi_barrier();
-        mx = fmaxf(fmaxf(red[r], red[TM + r]), fmaxf(red[2 * TM + r], red[3 * TM + r]));
-
-        // ---- pass 2: e = 2^(s - max), row sum; e replaces s in TMEM
-        float sum = 0.f;
-#pragma unroll 1
-        for (int ch = 0; ch < PARTW / CH; ++ch) {
-            const int j0 = cb + ch * CH;
-            if (j0 >= T) break;
-            float v[CH];
-            tc_ld16(lane_addr + (uint32_t)j0, v);
+            } else if (c0 < T) {  // columns >= T are zero products of the zero-filled P rows: they must not reach the next row's slots
 #pragma unroll
-            for (int e = 0; e < CH; ++e) {
-                v[e] = ex2_fast(v[e] - mx);
-                sum += v[e];
+                for (int e = 0; e < CH; e += 2) {
+                    const uint32_t h2 = f16x2_sat(v[e] * c2, v[e + 1] * c2);
+                    if (c0 + e < T) d[e] = (uint16_t)(h2 & 0xffffu);
+                    if (c0 + e + 1 < T) d[e + 1] = (uint16_t)(h2 >> 16);
+                }
             }
-            tc_st16(lane_addr + (uint32_t)j0, v);
         }
-        red[4 * TM + part * TM + r] = sum;
-        tc_wait_st();
-        epi_barrier();
-        const float inv = 1.f / ((red[4 * TM + r] + red[5 * TM + r]) + (red[6 * TM + r] + red[7 * TM + r]));
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bars + BAR_BD_DRAINED);
+    FA_STAMP(3);
+    if (ctl) {  // ac = (q+u) . K^T into the same columns once every warp has copied its bd rows out
+        mbar_wait(bars + BAR_ACIN, 0);
+        mbar_wait(bars + BAR_BD_DRAINED, 0);
+        tc_fence_after();
+#pragma unroll
+        for (int nh = 0; nh < 2; ++nh)
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+                tc_mma_bf16(tmem_base + nh * NHALF, umma_desc(s_qu + kk * 32, 16, 1024),
+                            umma_desc(s_k + nh * (NHALF * 128) + kk * 32, 16, 1024), id_s, kk > 0 ? 1u : 0u);
+        tc_commit(bars + BAR_AC_DONE);
+    }
+    __syncwarp();
+    epi_barrier();  // the flat buffer is complete
+    FA_STAMP(4);
 
-        // ---- pass 3: p = e / sum -> bf16 -> K-major SWIZZLE_128B slabs (element (r, j): slab j / 64, row r, 16-byte chunk
-        //      ((j % 64) / 8) ^ (r % 8)): the layout TMA produces for a {64, 128} box, which the MMA and the stores consume
-#pragma unroll 1
+    // ---- pass A: s = ac * c2 + shifted bd, mask -- the warp's 80 columns stay in registers from here on; pass B: e = 2^(s - m)
+    //      against the warp's OWN row maximum m, so that one exchange of (m, sum) per row part replaces a max round and a sum
+    //      round: p = e * 2^(m - max_parts m) / sum_parts(sum * 2^(m - max))
+    mbar_wait(bars + BAR_AC_DONE, 0);
+    tc_fence_after();
+    FA_STAMP(5);
+    float mx = -INFINITY;
+    {
+#pragma unroll
+        for (int ch = 0; ch < PARTW / CH; ++ch)
+            if (cb + ch * CH < T) tc_ld16_issue(lane_addr + (uint32_t)(cb + ch * CH), sv + ch * CH);
+        tc_wait_ld();
+        // shifted row r starts at half r T + cb of the flat buffer: aligned 32-bit loads from the word below and a funnel
+        // shift by the lane's own parity (row stride T may be odd) instead of 16-bit loads
+        const int h0 = r * T + cb;
+        const int fpar = h0 & 1;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(flat + (h0 - fpar));
+        const uint32_t fsh = 16u * (uint32_t)fpar;
+#pragma unroll
         for (int ch = 0; ch < PARTW / CH; ++ch) {
             const int j0 = cb + ch * CH;
-            if (j0 >= T) break;
-            float v[CH];
-            tc_ld16(lane_addr + (uint32_t)j0, v);
+            float* v = sv + ch * CH;
+            if (j0 < T) {  // warp-uniform
+                uint32_t w[CH / 2 + 1];
+#pragma unroll
+                for (int k = 0; k <= CH / 2; ++k) w[k] = src[ch * (CH / 2) + k];
+                const bool clean = j0 + CH <= klen;  // no masked or padding column in this chunk (warp-uniform)
+#pragma unroll
+                for (int k = 0; k < CH / 2; ++k) {
+                    const uint32_t pr = __funnelshift_r(w[k], w[k + 1], fsh);
+                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&pr));
+                    float s0 = fmaf(v[2 * k], c2, f.x), s1 = fmaf(v[2 * k + 1], c2, f.y);
+                    if (!clean) {
+                        const int j = j0 + 2 * k;
+                        s0 = (j < klen) ? s0 : -1e38f;
+                        s0 = (j < T) ? s0 : -INFINITY;
+                        s1 = (j + 1 < klen) ? s1 : -1e38f;
+                        s1 = (j + 1 < T) ? s1 : -INFINITY;
+                    }
+                    v[2 * k] = s0;
+                    v[2 * k + 1] = s1;
+                    mx = fmaxf(mx, fmaxf(s0, s1));
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < CH; ++e) v[e] = -INFINITY;
+            }
+        }
+    }
+    FA_STAMP(6);
+    const float mloc = (mx == -INFINITY) ? 0.f : mx;  // a part that lies entirely beyond T contributes nothing
+    float sum = 0.f;
+#pragma unroll
+    for (int e = 0; e < PARTW; ++e) {
+        sv[e] = ex2_fast(sv[e] - mloc);
+        sum += sv[e];
+    }
+    red[part * TM + r] = mx;
+    red[4 * TM + part * TM + r] = sum;
+    FA_STAMP(7);
+    epi_barrier();
+    FA_STAMP(8);
+    float inv;
+    {
+        const float m0 = red[r], m1 = red[TM + r], m2 = red[2 * TM + r], m3 = red[3 * TM + r];
+        const float mall = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));  // finite: column 0 exists and masked scores are -1e38
+        const float tot = red[4 * TM + r] * ex2_fast(m0 - mall) + red[5 * TM + r] * ex2_fast(m1 - mall) +
+                          red[6 * TM + r] * ex2_fast(m2 - mall) + red[7 * TM + r] * ex2_fast(m3 - mall);
+        inv = __fdividef(ex2_fast(mloc - mall), tot);
+    }
+
+    // ---- pass C: p = e * inv -> bf16 -> K-major SWIZZLE_128B slabs (element (r, j): slab j / 64, row r, 16-byte chunk
+    //      ((j % 64) / 8) ^ (r % 8)): the layout TMA produces for a {64, 128} box, which the MMA and the stores consume
+#pragma unroll
+    for (int ch = 0; ch < PARTW / CH; ++ch) {
+        const int j0 = cb + ch * CH;
+        if (j0 < T) {
+            const float* v = sv + ch * CH;
             uint8_t* rowp = smem + OFF_STG + (j0 >> 6) * (TM * 128) + r * 128;
             const int ch0 = (j0 & 63) >> 3;
 #pragma unroll
@@ -340,33 +381,56 @@ rel_attn_fwd_kernel(const __grid_constant__ CUtensorMap m_qu, const __grid_const
                 *reinterpret_cast<uint4*>(rowp + (((ch0 + t) ^ (r & 7)) << 4)) = u;
             }
         }
-        fence_proxy_async();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bars + BAR_P_READY);
-
-        // ---- O tile: this warp's 32 rows x 16 of the 64 head columns
-        mbar_wait(bars + BAR_O_DONE, 0);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bars + BAR_P_READY);
+    FA_STAMP(9);
+    if (ctl) {
+        // O = p . V  (K = keys, 16 per instruction; key blocks beyond T hold zero probabilities and are skipped)
+        mbar_wait(bars + BAR_V, 0);
+        mbar_wait(bars + BAR_P_READY, 0);
         tc_fence_after();
-        {
-            float v[CH];
-            tc_ld16(lane_addr + (uint32_t)(TKMAX + CH * part), v);
-            if (r < TOUT && g < T) {
-                uint4* dst = reinterpret_cast<uint4*>(p.o + ((long)b * T + g) * p.ldo + h * DK + CH * part);
+        const int ksteps = (T + 15) >> 4;
+        for (int ks = 0; ks < ksteps; ++ks) {
+            const int kb = ks >> 2, kk = ks & 3;
+            tc_mma_bf16(tmem_base + TKMAX, umma_desc(s_stg + kb * (TM * 128) + kk * 32, 16, 1024),
+                        umma_desc(s_p + kb * 8192 + kk * 2048, 8192, 1024), id_o, ks > 0 ? 1u : 0u);
+        }
+        tc_commit(bars + BAR_O_DONE);
+        // probabilities: rows [r0, r0 + 127) x stored columns, straight from the MMA operand tile
+        const int kslabs = (p.ld + 63) >> 6;
+        for (int kb = 0; kb < kslabs; ++kb) tma_store_4d(&m_probs, smem + OFF_STG + kb * (TM * 128), 64 * kb, r0, bh, 0);
+        bulk_commit();
+    }
+    __syncwarp();
+
+    // ---- O tile: this warp's 32 rows x 16 of the 64 head columns
+    mbar_wait(bars + BAR_O_DONE, 0);
+    tc_fence_after();
+    FA_STAMP(10);
+    {
+        float v[CH];
+        tc_ld16(lane_addr + (uint32_t)(TKMAX + CH * part), v);
+        if (r < TOUT && g < T) {
+            uint4* dst = reinterpret_cast<uint4*>(p.o + ((long)b * T + g) * p.ldo + h * DK + CH * part);
 #pragma unroll
-                for (int t = 0; t < CH / 8; ++t) {
-                    uint4 u;
-                    u.x = pack2(v[8 * t], v[8 * t + 1]);
-                    u.y = pack2(v[8 * t + 2], v[8 * t + 3]);
-                    u.z = pack2(v[8 * t + 4], v[8 * t + 5]);
-                    u.w = pack2(v[8 * t + 6], v[8 * t + 7]);
-                    dst[t] = u;
-                }
+            for (int t = 0; t < CH / 8; ++t) {
+                uint4 u;
+                u.x = pack2(v[8 * t], v[8 * t + 1]);
+                u.y = pack2(v[8 * t + 2], v[8 * t + 3]);
+                u.z = pack2(v[8 * t + 4], v[8 * t + 5]);
+                u.w = pack2(v[8 * t + 6], v[8 * t + 7]);
+                dst[t] = u;
             }
         }
     }
+    if (ctl) bulk_wait_read<0>();  // the probability tile must outlive the bulk stores that read it
+    FA_STAMP(11);
     tc_fence_before();
     __syncthreads();
+    FA_STAMP(12);
     if (warp == 2) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
@@ -414,6 +478,10 @@ static int make_map(CUtensorMap* map, const void* base, long inner, long rows, l
 extern "C" {
 using namespace lasr;
 
+static long long* g_fa_trace = nullptr;
+/* developer aid: device buffer of 16 int64 per CTA that receives clock64 stamps of the kernel's phases (NULL = off) */
+void lasr_rel_attn_fwd_set_trace(void* buf) { g_fa_trace = reinterpret_cast<long long*>(buf); }
+
 int lasr_rel_attn_fwd_supported(int T, int dk) { return (T >= 1 && T <= fa::TKMAX && dk == fa::DK) ? 1 : 0; }
 
 int lasr_rel_attn_fwd(const void* qu, const void* qv, long ldq, const void* k, const void* v, long ldkv, const void* pos, long ldp,
@@ -450,6 +518,7 @@ int lasr_rel_attn_fwd(const void* qu, const void* qv, long ldq, const void* k, c
     p.c2 = scale * 1.4426950408889634f;
     p.B = B; p.H = H; p.T = T; p.ld = ld;
     p.tiles = (T + fa::TOUT - 1) / fa::TOUT;
+    p.trace = g_fa_trace;
     launch_pdl(fa::rel_attn_fwd_kernel, dim3((unsigned)(p.tiles * H * B)), dim3(fa::THREADS), (size_t)fa::SMEM_BYTES,
                (cudaStream_t)stream, m_qu, m_qv, m_k, m_v, m_p, m_probs, p);
     return check_launch("rel_attn_fwd");
