@@ -62,7 +62,7 @@ constexpr int OFF_RED = OFF_BAR + 128;            // [max | sum][column part][ro
 constexpr int SMEM_BYTES = OFF_RED + 2 * 4 * TM * 4 + 1024;
 static_assert(STG_BYTES >= 5 * TM * 128 && SMEM_BYTES <= 232448, "shared-memory budget");
 
-enum { BAR_BDIN = 0, BAR_ACIN, BAR_V, BAR_BD_DONE, BAR_BD_DRAINED, BAR_AC_DONE, BAR_P_READY, BAR_O_DONE, NBARS };
+enum { BAR_BDIN = 0, BAR_ACIN, BAR_V, BAR_BD_DONE, BAR_BD_DRAINED, BAR_AC_DONE, BAR_S_DRAINED, BAR_P_READY, BAR_O_DONE, BAR_O_DRAINED, NBARS };
 
 struct Params {
     bf16* o;
@@ -76,7 +76,7 @@ struct Params {
 
 #define FA_STAMP(i)                                                                  \
     do {                                                                             \
-        if (p.trace && warp == 6 && lane == 0) p.trace[(long)blockIdx.x * 16 + (i)] = clock64(); \
+        if (p.trace && warp == 6 && lane == 0) p.trace[(long)tt * 16 + (i)] = clock64(); \
     } while (0)
 
 __device__ __forceinline__ void tc_st32(uint32_t taddr, const float* v) {
@@ -131,6 +131,74 @@ __device__ __forceinline__ void tc_ld16_issue(uint32_t taddr, float* v) {
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// Control-thread steps, out of line: their descriptors and coordinates must not occupy registers of the 512 worker threads
+// (the workers hold 80 score columns each).
+struct Ctl {
+    uint8_t* smem;
+    uint64_t* bars;
+    uint32_t tmem_base;
+    int H, tiles, T, ld;
+};
+__device__ __noinline__ void ctl_bd_loads(const Ctl& c, const CUtensorMap* m_qv, const CUtensorMap* m_p, int tt) {
+    const int tile = tt % c.tiles, bh = tt / c.tiles;
+    const int h = bh % c.H, b = bh / c.H;
+    mbar_arrive_expect_tx(c.bars + BAR_BDIN, TM * 128 + 2 * NHALF * 128);
+    tma_load_4d(c.smem + OFF_QV, m_qv, c.bars + BAR_BDIN, h * DK, tile * TOUT, b, 0);
+    tma_load_4d(c.smem + OFF_K, m_p, c.bars + BAR_BDIN, h * DK, 0, 0, 0);  // P -> K's buffer
+    tma_load_4d(c.smem + OFF_K + NHALF * 128, m_p, c.bars + BAR_BDIN, h * DK, NHALF, 0, 0);
+}
+__device__ __forceinline__ uint32_t idesc_scores() {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NHALF >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
+// 128 x 320 x 64 score MMA: A = a 128 x 64 query tile at a_off, B = the two 160-row halves in K's buffer -> TMEM[0,320)
+__device__ __noinline__ void ctl_score_mma(const Ctl& c, int a_off, int done_bar) {
+    tc_fence_after();
+    const uint32_t sa = smem_u32(c.smem + a_off), sb = smem_u32(c.smem + OFF_K);
+#pragma unroll
+    for (int nh = 0; nh < 2; ++nh)
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+            tc_mma_bf16(c.tmem_base + nh * NHALF, umma_desc(sa + kk * 32, 16, 1024), umma_desc(sb + nh * (NHALF * 128) + kk * 32, 16, 1024),
+                        idesc_scores(), kk > 0 ? 1u : 0u);
+    tc_commit(c.bars + done_bar);
+}
+__device__ __noinline__ void ctl_ac_loads(const Ctl& c, const CUtensorMap* m_qu, const CUtensorMap* m_k, int tt) {
+    const int tile = tt % c.tiles, bh = tt / c.tiles;
+    const int h = bh % c.H, b = bh / c.H;
+    mbar_arrive_expect_tx(c.bars + BAR_ACIN, TM * 128 + 2 * NHALF * 128);
+    tma_load_4d(c.smem + OFF_QU, m_qu, c.bars + BAR_ACIN, h * DK, tile * TOUT, b, 0);
+    tma_load_4d(c.smem + OFF_K, m_k, c.bars + BAR_ACIN, h * DK, 0, b, 0);
+    tma_load_4d(c.smem + OFF_K + NHALF * 128, m_k, c.bars + BAR_ACIN, h * DK, NHALF, b, 0);
+}
+// V of tile tt and, if there is one, (q+v) and P of tile tn: issued at the start of pass A (the shift before it is bound by
+// shared-memory stores and should not share the port with 96 KB of TMA writes; V is not needed before p.V)
+__device__ __noinline__ void ctl_v_next_loads(const Ctl& c, const CUtensorMap* m_v, const CUtensorMap* m_qv, const CUtensorMap* m_p, int tt,
+                                              int tn) {
+    const int bh = tt / c.tiles;
+    const int h = bh % c.H, b = bh / c.H;
+    mbar_arrive_expect_tx(c.bars + BAR_V, 5 * 8192);
+    for (int kb = 0; kb < 5; ++kb) tma_load_4d(c.smem + OFF_P + kb * 8192, m_v, c.bars + BAR_V, h * DK, 64 * kb, b, 0);
+    if (tn >= 0) ctl_bd_loads(c, m_qv, m_p, tn);
+}
+// O = p . V (K = keys, 16 per instruction; key blocks beyond T hold zero probabilities and are skipped) -> TMEM[320,384), then
+// the bulk tensor stores of the probability tile: rows [r0, r0 + 127) x stored columns, straight from the MMA operand slabs
+__device__ __noinline__ void ctl_pv_mma_store(const Ctl& c, const CUtensorMap* m_probs, int tt) {
+    tc_fence_after();
+    const uint32_t id_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(DK >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+    const uint32_t s_stg = smem_u32(c.smem + OFF_STG), s_v = smem_u32(c.smem + OFF_P);
+    const int ksteps = (c.T + 15) >> 4;
+    for (int ks = 0; ks < ksteps; ++ks) {
+        const int kb = ks >> 2, kk = ks & 3;
+        tc_mma_bf16(c.tmem_base + TKMAX, umma_desc(s_stg + kb * (TM * 128) + kk * 32, 16, 1024),
+                    umma_desc(s_v + kb * 8192 + kk * 2048, 8192, 1024), id_o, ks > 0 ? 1u : 0u);
+    }
+    tc_commit(c.bars + BAR_O_DONE);
+    const int tile = tt % c.tiles, bh = tt / c.tiles;
+    const int kslabs = (c.ld + 63) >> 6;
+    for (int kb = 0; kb < kslabs; ++kb) tma_store_4d(m_probs, c.smem + OFF_STG + kb * (TM * 128), 64 * kb, tile * TOUT, bh, 0);
+    bulk_commit();
+}
+
 __global__ void __launch_bounds__(THREADS, 1)
 rel_attn_fwd_kernel(const __grid_constant__ CUtensorMap m_qu, const __grid_constant__ CUtensorMap m_qv,
                     const __grid_constant__ CUtensorMap m_k, const __grid_constant__ CUtensorMap m_v,
@@ -142,10 +210,8 @@ rel_attn_fwd_kernel(const __grid_constant__ CUtensorMap m_qu, const __grid_const
     float* red = reinterpret_cast<float*>(smem + OFF_RED);  // [max | sum][column part][row]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    FA_STAMP(0);
-    const int tile = blockIdx.x % p.tiles, bh = blockIdx.x / p.tiles;
-    const int h = bh % p.H, b = bh / p.H;
-    const int T = p.T, r0 = tile * TOUT;
+    const int T = p.T;
+    const int total = p.tiles * p.H * p.B;
     // The two single-thread roles (TMA producer, MMA issuer) are strictly sequential here, so ONE thread of an ordinary
     // worker warp plays both between its own phases: 16 warps = 4 per scheduler leave 128 registers per thread, which is what
     // keeps a warp's 80 score columns in registers without spills.
@@ -160,7 +226,8 @@ rel_attn_fwd_kernel(const __grid_constant__ CUtensorMap m_qu, const __grid_const
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&m_probs) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < NBARS; ++i) mbar_init(bars + i, (i == BAR_BD_DRAINED || i == BAR_P_READY) ? EPI_W : 1);
+        for (int i = 0; i < NBARS; ++i)
+            mbar_init(bars + i, (i == BAR_BD_DRAINED || i == BAR_P_READY || i == BAR_S_DRAINED || i == BAR_O_DRAINED) ? EPI_W : 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -174,146 +241,141 @@ rel_attn_fwd_kernel(const __grid_constant__ CUtensorMap m_qu, const __grid_const
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    FA_STAMP(1);
 
-    const uint32_t id_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NHALF >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-    const uint32_t id_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(DK >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-    const uint32_t s_stg = smem_u32(smem + OFF_STG), s_qu = smem_u32(smem + OFF_QU), s_qv = smem_u32(smem + OFF_QV);
-    const uint32_t s_k = smem_u32(smem + OFF_K), s_p = smem_u32(smem + OFF_P);
-
-    if (ctl) {
-        mbar_arrive_expect_tx(bars + BAR_BDIN, TM * 128 + 2 * NHALF * 128);
-        tma_load_4d(smem + OFF_QV, &m_qv, bars + BAR_BDIN, h * DK, r0, b, 0);
-        tma_load_4d(smem + OFF_P, &m_p, bars + BAR_BDIN, h * DK, 0, 0, 0);
-        tma_load_4d(smem + OFF_P + NHALF * 128, &m_p, bars + BAR_BDIN, h * DK, NHALF, 0, 0);
-        mbar_arrive_expect_tx(bars + BAR_ACIN, TM * 128 + 2 * NHALF * 128);
-        tma_load_4d(smem + OFF_QU, &m_qu, bars + BAR_ACIN, h * DK, r0, b, 0);
-        tma_load_4d(smem + OFF_K, &m_k, bars + BAR_ACIN, h * DK, 0, b, 0);
-        tma_load_4d(smem + OFF_K + NHALF * 128, &m_k, bars + BAR_ACIN, h * DK, NHALF, b, 0);
-        // bd = (q+v) . P^T
-        mbar_wait(bars + BAR_BDIN, 0);
-        tc_fence_after();
-#pragma unroll
-        for (int nh = 0; nh < 2; ++nh)
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-                tc_mma_bf16(tmem_base + nh * NHALF, umma_desc(s_qv + kk * 32, 16, 1024),
-                            umma_desc(s_p + nh * (NHALF * 128) + kk * 32, 16, 1024), id_s, kk > 0 ? 1u : 0u);
-        tc_commit(bars + BAR_BD_DONE);
-    }
-    __syncwarp();
+    Ctl cx;
+    cx.smem = smem; cx.bars = bars; cx.tmem_base = tmem_base; cx.H = p.H; cx.tiles = p.tiles; cx.T = T; cx.ld = p.ld;
 
     const int q = warp & 3, part = warp >> 2;
-    const int r = q * 32 + lane, g = r0 + r;
+    const int r = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const float c2 = p.c2;
-    int klen = T;
-    if (p.mask_mode != 0 && p.lens) {
-        const long l = p.lens[b];
-        long k = l;
-        if (p.mask_mode == 2) k = l + 1;
-        else if (p.mask_mode == 3) k = (l + 3) / 4;
-        klen = (int)(k < T ? (k < 0 ? 0 : k) : T);
-    }
     const int cb = part * PARTW;
     uint16_t* flat = reinterpret_cast<uint16_t*>(smem + OFF_STG) + FLAT_PAD;
-    float sv[PARTW];  // the warp's 80 columns of its rows: bd, then scores, then exponentials
 
-    // ---- shift: bd row g -> flat buffer (see the header comment)
-    mbar_wait(bars + BAR_BD_DONE, 0);
-    tc_fence_after();
-    FA_STAMP(2);
-    if (ctl) {  // V replaces P now that the bd MMAs have read it
-        mbar_arrive_expect_tx(bars + BAR_V, 5 * 8192);
-        for (int kb = 0; kb < 5; ++kb) tma_load_4d(smem + OFF_P + kb * 8192, &m_v, bars + BAR_V, h * DK, 64 * kb, b, 0);
+    // Persistent CTA: tiles blockIdx.x, + gridDim.x, ...  While the workers are in the softmax of tile n the control thread
+    // already loads (q+v) and P of tile n + 1 (P into K's buffer, which the ac MMAs of tile n have released) and issues its bd
+    // MMAs as soon as every warp has copied the scores of tile n out of TMEM, so that a tile starts with its shift: no load
+    // or MMA latency, no CTA launch, no TMEM allocation on the per-tile path.  Every barrier completes once per tile:
+    // parity = iteration & 1.
+    if (ctl && (int)blockIdx.x < total) {
+        ctl_bd_loads(cx, &m_qv, &m_p, blockIdx.x);
+        mbar_wait(bars + BAR_BDIN, 0);
+        ctl_score_mma(cx, OFF_QV, BAR_BD_DONE);  // bd = (q+v) . P^T
     }
     __syncwarp();
-    {
+
+    uint32_t ph = 0;
+    for (int tt = blockIdx.x; tt < total; tt += gridDim.x, ph ^= 1u) {
+        // (per-tile coordinates are recomputed where they are needed instead of living across the register-heavy passes)
+        float sv[PARTW];  // the warp's 80 columns of its rows: bd, then scores, then exponentials
+        FA_STAMP(0);
+
+        // ---- shift: bd row g -> flat buffer (see the header comment)
+        mbar_wait(bars + BAR_BD_DONE, ph);
+        tc_fence_after();
+        FA_STAMP(1);
+        if (ctl) {
+            // the bd MMAs have released (q+v) and P: (q+u) and K (into P's place) for the ac MMAs
+            ctl_ac_loads(cx, &m_qu, &m_k, tt);
+            bulk_wait_read<0>();  // the previous tile's probability stores have read the slabs the flat buffer aliases
+        }
+        __syncwarp();
+        epi_barrier();
+        FA_STAMP(2);
+        {
 #pragma unroll
-        for (int ch = 0; ch < PARTW / CH; ++ch)
-            if (cb + ch * CH < T) tc_ld16_issue(lane_addr + (uint32_t)(cb + ch * CH), sv + ch * CH);  // warp-uniform
-        tc_wait_ld();
-        const int off = r * (T + 1) + r0 - T;  // flat position of the padded zero of bd row g
-        if (part == 0) flat[off] = 0;
-        uint16_t* dst = flat + off + 1 + cb;
-        // T odd: the row stride T + 1 is even, so every lane of the warp has the same 4-byte alignment and pairs of
-        // halves go out as 32-bit stores (the phase is bound by shared-memory store wavefronts)
-        const int par = (T & 1) ? ((off + 1 + cb) & 1) : 2;  // 0 aligned | 1 off by one half | 2 per-lane (scalar stores)
+            for (int ch = 0; ch < PARTW / CH; ++ch) tc_ld16_issue(lane_addr + (uint32_t)(cb + ch * CH), sv + ch * CH);
+            tc_wait_ld();
+            const int r0 = (tt % p.tiles) * TOUT;
+            const int off = r * (T + 1) + r0 - T;  // flat position of the padded zero of bd row g
+            if (part == 0) flat[off] = 0;
+            uint16_t* dst = flat + off + 1 + cb;
+            // T odd: the row stride T + 1 is even, so every lane of the warp has the same 4-byte alignment and pairs of
+            // halves go out as 32-bit stores (the phase is bound by shared-memory store wavefronts)
+            const int par = (T & 1) ? ((off + 1 + cb) & 1) : 2;  // 0 aligned | 1 off by one half | 2 per-lane (scalar stores)
 #pragma unroll
-        for (int ch = 0; ch < PARTW / CH; ++ch) {
-            const int c0 = cb + ch * CH;
-            const float* v = sv + ch * CH;
-            uint16_t* d = dst + ch * CH;
-            if (c0 + CH <= T) {  // warp-uniform
-                if (par == 0) {
+            for (int ch = 0; ch < PARTW / CH; ++ch) {
+                const int c0 = cb + ch * CH;
+                const float* v = sv + ch * CH;
+                uint16_t* d = dst + ch * CH;
+                if (c0 + CH <= T) {  // warp-uniform
+                    if (par == 0) {
 #pragma unroll
-                    for (int e = 0; e < CH; e += 2) *reinterpret_cast<uint32_t*>(d + e) = f16x2_sat(v[e] * c2, v[e + 1] * c2);
-                } else if (par == 1) {
-                    d[0] = (uint16_t)(f16x2_sat(v[0] * c2, 0.f) & 0xffffu);
+                        for (int e = 0; e < CH; e += 2) *reinterpret_cast<uint32_t*>(d + e) = f16x2_sat(v[e] * c2, v[e + 1] * c2);
+                    } else if (par == 1) {
+                        d[0] = (uint16_t)(f16x2_sat(v[0] * c2, 0.f) & 0xffffu);
 #pragma unroll
-                    for (int e = 1; e + 1 < CH; e += 2) *reinterpret_cast<uint32_t*>(d + e) = f16x2_sat(v[e] * c2, v[e + 1] * c2);
-                    d[CH - 1] = (uint16_t)(f16x2_sat(v[CH - 1] * c2, 0.f) & 0xffffu);
-                } else {
+                        for (int e = 1; e + 1 < CH; e += 2) *reinterpret_cast<uint32_t*>(d + e) = f16x2_sat(v[e] * c2, v[e + 1] * c2);
+                        d[CH - 1] = (uint16_t)(f16x2_sat(v[CH - 1] * c2, 0.f) & 0xffffu);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < CH; e += 2) {
+                            const uint32_t h2 = f16x2_sat(v[e] * c2, v[e + 1] * c2);
+                            d[e] = (uint16_t)(h2 & 0xffffu);
+                            d[e + 1] = (uint16_t)(h2 >> 16);
+                        }
+                    }
+                } else if (c0 < T) {  // columns >= T are zero products of the zero-filled P rows: they must not reach the next row's slots
 #pragma unroll
                     for (int e = 0; e < CH; e += 2) {
                         const uint32_t h2 = f16x2_sat(v[e] * c2, v[e + 1] * c2);
-                        d[e] = (uint16_t)(h2 & 0xffffu);
-                        d[e + 1] = (uint16_t)(h2 >> 16);
+                        if (c0 + e < T) d[e] = (uint16_t)(h2 & 0xffffu);
+                        if (c0 + e + 1 < T) d[e + 1] = (uint16_t)(h2 >> 16);
                     }
-                }
-            } else if (c0 < T) {  // columns >= T are zero products of the zero-filled P rows: they must not reach the next row's slots
-#pragma unroll
-                for (int e = 0; e < CH; e += 2) {
-                    const uint32_t h2 = f16x2_sat(v[e] * c2, v[e + 1] * c2);
-                    if (c0 + e < T) d[e] = (uint16_t)(h2 & 0xffffu);
-                    if (c0 + e + 1 < T) d[e + 1] = (uint16_t)(h2 >> 16);
                 }
             }
         }
-    }
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bars + BAR_BD_DRAINED);
-    FA_STAMP(3);
-    if (ctl) {  // ac = (q+u) . K^T into the same columns once every warp has copied its bd rows out
-        mbar_wait(bars + BAR_ACIN, 0);
-        mbar_wait(bars + BAR_BD_DRAINED, 0);
-        tc_fence_after();
-#pragma unroll
-        for (int nh = 0; nh < 2; ++nh)
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-                tc_mma_bf16(tmem_base + nh * NHALF, umma_desc(s_qu + kk * 32, 16, 1024),
-                            umma_desc(s_k + nh * (NHALF * 128) + kk * 32, 16, 1024), id_s, kk > 0 ? 1u : 0u);
-        tc_commit(bars + BAR_AC_DONE);
-    }
-    __syncwarp();
-    epi_barrier();  // the flat buffer is complete
-    FA_STAMP(4);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + BAR_BD_DRAINED);
+        FA_STAMP(3);
+        if (ctl) {  // ac = (q+u) . K^T into the same columns once every warp has copied its bd rows out
+            mbar_wait(bars + BAR_ACIN, ph);
+            mbar_wait(bars + BAR_BD_DRAINED, ph);
+            ctl_score_mma(cx, OFF_QU, BAR_AC_DONE);
+        }
+        __syncwarp();
+        epi_barrier();  // the flat buffer is complete
+        FA_STAMP(4);
 
-    // ---- pass A: s = ac * c2 + shifted bd, mask -- the warp's 80 columns stay in registers from here on; pass B: e = 2^(s - m)
-    //      against the warp's OWN row maximum m, so that one exchange of (m, sum) per row part replaces a max round and a sum
-    //      round: p = e * 2^(m - max_parts m) / sum_parts(sum * 2^(m - max))
-    mbar_wait(bars + BAR_AC_DONE, 0);
-    tc_fence_after();
-    FA_STAMP(5);
-    float mx = -INFINITY;
-    {
+        // ---- pass A: s = ac * c2 + shifted bd, mask -- the warp's 80 columns stay in registers from here on; pass B:
+        //      e = 2^(s - m) against the warp's OWN row maximum m, so that one exchange of (m, sum) per row part replaces a max
+        //      round and a sum round: p = e * 2^(m - max_parts m) / sum_parts(sum * 2^(m - max))
+        mbar_wait(bars + BAR_AC_DONE, ph);
+        tc_fence_after();
+        FA_STAMP(5);
+        // the ac MMAs have released (q+u) and K's buffer: next tile's (q+v) and P; V of this tile (its buffer was released by the
+        // previous tile's p.V, whose completion this thread has waited for as a worker).  A call: placed where no score column is live
+        if (ctl) ctl_v_next_loads(cx, &m_v, &m_qv, &m_p, tt, tt + (int)gridDim.x < total ? tt + (int)gridDim.x : -1);
+        __syncwarp();
+        float mx = -INFINITY;
+        {
 #pragma unroll
-        for (int ch = 0; ch < PARTW / CH; ++ch)
-            if (cb + ch * CH < T) tc_ld16_issue(lane_addr + (uint32_t)(cb + ch * CH), sv + ch * CH);
-        tc_wait_ld();
-        // shifted row r starts at half r T + cb of the flat buffer: aligned 32-bit loads from the word below and a funnel
-        // shift by the lane's own parity (row stride T may be odd) instead of 16-bit loads
-        const int h0 = r * T + cb;
-        const int fpar = h0 & 1;
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(flat + (h0 - fpar));
-        const uint32_t fsh = 16u * (uint32_t)fpar;
+            // (all 320 allocated columns are read unconditionally -- columns >= T are replaced below -- so that every element
+            //  of sv is defined on every path and the array stays in registers)
+            for (int ch = 0; ch < PARTW / CH; ++ch) tc_ld16_issue(lane_addr + (uint32_t)(cb + ch * CH), sv + ch * CH);
+            tc_wait_ld();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars + BAR_S_DRAINED);  // TMEM[0,320) may take the next tile's bd
+            // shifted row r starts at half r T + cb of the flat buffer: aligned 32-bit loads from the word below and a funnel
+            // shift by the lane's own parity (row stride T may be odd) instead of 16-bit loads
+            int klen = T;
+            if (p.mask_mode != 0 && p.lens) {
+                const long l = p.lens[(tt / p.tiles) / p.H];
+                long k = l;
+                if (p.mask_mode == 2) k = l + 1;
+                else if (p.mask_mode == 3) k = (l + 3) / 4;
+                klen = (int)(k < T ? (k < 0 ? 0 : k) : T);
+            }
+            const int h0 = r * T + cb;
+            const int fpar = h0 & 1;
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(flat + (h0 - fpar));
+            const uint32_t fsh = 16u * (uint32_t)fpar;
 #pragma unroll
-        for (int ch = 0; ch < PARTW / CH; ++ch) {
-            const int j0 = cb + ch * CH;
-            float* v = sv + ch * CH;
-            if (j0 < T) {  // warp-uniform
+            for (int ch = 0; ch < PARTW / CH; ++ch) {
+                const int j0 = cb + ch * CH;
+                float* v = sv + ch * CH;
                 uint32_t w[CH / 2 + 1];
 #pragma unroll
                 for (int k = 0; k <= CH / 2; ++k) w[k] = src[ch * (CH / 2) + k];
@@ -334,103 +396,99 @@ rel_attn_fwd_kernel(const __grid_constant__ CUtensorMap m_qu, const __grid_const
                     v[2 * k + 1] = s1;
                     mx = fmaxf(mx, fmaxf(s0, s1));
                 }
-            } else {
-#pragma unroll
-                for (int e = 0; e < CH; ++e) v[e] = -INFINITY;
             }
         }
-    }
-    FA_STAMP(6);
-    const float mloc = (mx == -INFINITY) ? 0.f : mx;  // a part that lies entirely beyond T contributes nothing
-    float sum = 0.f;
+        FA_STAMP(6);
+        const float mloc = (mx == -INFINITY) ? 0.f : mx;  // a part that lies entirely beyond T contributes nothing
+        float sum = 0.f;
 #pragma unroll
-    for (int e = 0; e < PARTW; ++e) {
-        sv[e] = ex2_fast(sv[e] - mloc);
-        sum += sv[e];
-    }
-    red[part * TM + r] = mx;
-    red[4 * TM + part * TM + r] = sum;
-    FA_STAMP(7);
-    epi_barrier();
-    FA_STAMP(8);
-    float inv;
-    {
-        const float m0 = red[r], m1 = red[TM + r], m2 = red[2 * TM + r], m3 = red[3 * TM + r];
-        const float mall = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));  // finite: column 0 exists and masked scores are -1e38
-        const float tot = red[4 * TM + r] * ex2_fast(m0 - mall) + red[5 * TM + r] * ex2_fast(m1 - mall) +
-                          red[6 * TM + r] * ex2_fast(m2 - mall) + red[7 * TM + r] * ex2_fast(m3 - mall);
-        inv = __fdividef(ex2_fast(mloc - mall), tot);
-    }
+        for (int e = 0; e < PARTW; ++e) {
+            sv[e] = ex2_fast(sv[e] - mloc);
+            sum += sv[e];
+        }
+        red[part * TM + r] = mx;
+        red[4 * TM + part * TM + r] = sum;
+        FA_STAMP(7);
+        epi_barrier();
+        FA_STAMP(8);
+        float inv;
+        {
+            const float m0 = red[r], m1 = red[TM + r], m2 = red[2 * TM + r], m3 = red[3 * TM + r];
+            const float mall = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));  // finite: column 0 exists and masked scores are -1e38
+            const float tot = red[4 * TM + r] * ex2_fast(m0 - mall) + red[5 * TM + r] * ex2_fast(m1 - mall) +
+                              red[6 * TM + r] * ex2_fast(m2 - mall) + red[7 * TM + r] * ex2_fast(m3 - mall);
+            inv = __fdividef(ex2_fast(mloc - mall), tot);
+        }
 
-    // ---- pass C: p = e * inv -> bf16 -> K-major SWIZZLE_128B slabs (element (r, j): slab j / 64, row r, 16-byte chunk
-    //      ((j % 64) / 8) ^ (r % 8)): the layout TMA produces for a {64, 128} box, which the MMA and the stores consume
+        // ---- pass C: p = e * inv -> bf16 -> K-major SWIZZLE_128B slabs (element (r, j): slab j / 64, row r, 16-byte chunk
+        //      ((j % 64) / 8) ^ (r % 8)): the layout TMA produces for a {64, 128} box, which the MMA and the stores consume
 #pragma unroll
-    for (int ch = 0; ch < PARTW / CH; ++ch) {
-        const int j0 = cb + ch * CH;
-        if (j0 < T) {
-            const float* v = sv + ch * CH;
-            uint8_t* rowp = smem + OFF_STG + (j0 >> 6) * (TM * 128) + r * 128;
-            const int ch0 = (j0 & 63) >> 3;
+        for (int ch = 0; ch < PARTW / CH; ++ch) {
+            const int j0 = cb + ch * CH;
+            if (j0 < T) {
+                const float* v = sv + ch * CH;
+                uint8_t* rowp = smem + OFF_STG + (j0 >> 6) * (TM * 128) + r * 128;
+                const int ch0 = (j0 & 63) >> 3;
 #pragma unroll
-            for (int t = 0; t < CH / 8; ++t) {
-                uint4 u;
-                u.x = pack2(v[8 * t] * inv, v[8 * t + 1] * inv);
-                u.y = pack2(v[8 * t + 2] * inv, v[8 * t + 3] * inv);
-                u.z = pack2(v[8 * t + 4] * inv, v[8 * t + 5] * inv);
-                u.w = pack2(v[8 * t + 6] * inv, v[8 * t + 7] * inv);
-                *reinterpret_cast<uint4*>(rowp + (((ch0 + t) ^ (r & 7)) << 4)) = u;
+                for (int t = 0; t < CH / 8; ++t) {
+                    uint4 u;
+                    u.x = pack2(v[8 * t] * inv, v[8 * t + 1] * inv);
+                    u.y = pack2(v[8 * t + 2] * inv, v[8 * t + 3] * inv);
+                    u.z = pack2(v[8 * t + 4] * inv, v[8 * t + 5] * inv);
+                    u.w = pack2(v[8 * t + 6] * inv, v[8 * t + 7] * inv);
+                    *reinterpret_cast<uint4*>(rowp + (((ch0 + t) ^ (r & 7)) << 4)) = u;
+                }
             }
         }
-    }
-    fence_proxy_async();
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bars + BAR_P_READY);
-    FA_STAMP(9);
-    if (ctl) {
-        // O = p . V  (K = keys, 16 per instruction; key blocks beyond T hold zero probabilities and are skipped)
-        mbar_wait(bars + BAR_V, 0);
-        mbar_wait(bars + BAR_P_READY, 0);
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + BAR_P_READY);
+        FA_STAMP(9);
+        if (ctl) {
+            // O = p . V  (K = keys, 16 per instruction; key blocks beyond T hold zero probabilities and are skipped)
+            mbar_wait(bars + BAR_V, ph);
+            mbar_wait(bars + BAR_P_READY, ph);
+            if (tt != (int)blockIdx.x) mbar_wait(bars + BAR_O_DRAINED, ph ^ 1);  // the workers have read the previous tile's O out of TMEM
+            ctl_pv_mma_store(cx, &m_probs, tt);
+            if (tt + (int)gridDim.x < total) {  // the next tile's bd: every warp has copied this tile's scores out of TMEM[0,320)
+                mbar_wait(bars + BAR_S_DRAINED, ph);
+                mbar_wait(bars + BAR_BDIN, ph ^ 1);
+                ctl_score_mma(cx, OFF_QV, BAR_BD_DONE);
+            }
+        }
+        __syncwarp();
+
+        // ---- O tile: this warp's 32 rows x 16 of the 64 head columns
+        mbar_wait(bars + BAR_O_DONE, ph);
         tc_fence_after();
-        const int ksteps = (T + 15) >> 4;
-        for (int ks = 0; ks < ksteps; ++ks) {
-            const int kb = ks >> 2, kk = ks & 3;
-            tc_mma_bf16(tmem_base + TKMAX, umma_desc(s_stg + kb * (TM * 128) + kk * 32, 16, 1024),
-                        umma_desc(s_p + kb * 8192 + kk * 2048, 8192, 1024), id_o, ks > 0 ? 1u : 0u);
-        }
-        tc_commit(bars + BAR_O_DONE);
-        // probabilities: rows [r0, r0 + 127) x stored columns, straight from the MMA operand tile
-        const int kslabs = (p.ld + 63) >> 6;
-        for (int kb = 0; kb < kslabs; ++kb) tma_store_4d(&m_probs, smem + OFF_STG + kb * (TM * 128), 64 * kb, r0, bh, 0);
-        bulk_commit();
-    }
-    __syncwarp();
-
-    // ---- O tile: this warp's 32 rows x 16 of the 64 head columns
-    mbar_wait(bars + BAR_O_DONE, 0);
-    tc_fence_after();
-    FA_STAMP(10);
-    {
-        float v[CH];
-        tc_ld16(lane_addr + (uint32_t)(TKMAX + CH * part), v);
-        if (r < TOUT && g < T) {
-            uint4* dst = reinterpret_cast<uint4*>(p.o + ((long)b * T + g) * p.ldo + h * DK + CH * part);
+        FA_STAMP(10);
+        {
+            float v[CH];
+            tc_ld16(lane_addr + (uint32_t)(TKMAX + CH * part), v);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars + BAR_O_DRAINED);
+            const int tile = tt % p.tiles, bh = tt / p.tiles;
+            const int h = bh % p.H, b = bh / p.H, g = tile * TOUT + r;
+            if (r < TOUT && g < T) {
+                uint4* dst = reinterpret_cast<uint4*>(p.o + ((long)b * T + g) * p.ldo + h * DK + CH * part);
 #pragma unroll
-            for (int t = 0; t < CH / 8; ++t) {
-                uint4 u;
-                u.x = pack2(v[8 * t], v[8 * t + 1]);
-                u.y = pack2(v[8 * t + 2], v[8 * t + 3]);
-                u.z = pack2(v[8 * t + 4], v[8 * t + 5]);
-                u.w = pack2(v[8 * t + 6], v[8 * t + 7]);
-                dst[t] = u;
+                for (int t = 0; t < CH / 8; ++t) {
+                    uint4 u;
+                    u.x = pack2(v[8 * t], v[8 * t + 1]);
+                    u.y = pack2(v[8 * t + 2], v[8 * t + 3]);
+                    u.z = pack2(v[8 * t + 4], v[8 * t + 5]);
+                    u.w = pack2(v[8 * t + 6], v[8 * t + 7]);
+                    dst[t] = u;
+                }
             }
         }
+        FA_STAMP(11);
     }
     if (ctl) bulk_wait_read<0>();  // the probability tile must outlive the bulk stores that read it
-    FA_STAMP(11);
     tc_fence_before();
     __syncthreads();
-    FA_STAMP(12);
     if (warp == 2) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
@@ -519,7 +577,14 @@ int lasr_rel_attn_fwd(const void* qu, const void* qv, long ldq, const void* k, c
     p.B = B; p.H = H; p.T = T; p.ld = ld;
     p.tiles = (T + fa::TOUT - 1) / fa::TOUT;
     p.trace = g_fa_trace;
-    launch_pdl(fa::rel_attn_fwd_kernel, dim3((unsigned)(p.tiles * H * B)), dim3(fa::THREADS), (size_t)fa::SMEM_BYTES,
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    const long total = (long)p.tiles * H * B;
+    const int grid = (int)(total < sms ? total : sms);  // persistent: one CTA per SM walks the (batch, head, row tile) list
+    launch_pdl(fa::rel_attn_fwd_kernel, dim3((unsigned)grid), dim3(fa::THREADS), (size_t)fa::SMEM_BYTES,
                (cudaStream_t)stream, m_qu, m_qv, m_k, m_v, m_p, m_probs, p);
     return check_launch("rel_attn_fwd");
 }
