@@ -24,10 +24,10 @@ ops.rel_attn_fwd(qu, qv, k, v, pos, probs, o, lens, 3, dk ** -0.5, B, H, T, dk)
 torch.cuda.synchronize()
 _lib.lib().lasr_rel_attn_fwd_set_trace(C.c_void_p(0))
 t = tr.cpu().double()
-names = ["setup+pdl", "wait bd (loads + MMA)", "shift", "barrier", "wait ac", "pass A", "pass B", "barrier", "pass C", "wait O",
-         "O store", "exit barrier"]
-dt = t[:, 1:13] - t[:, 0:12]
-tot = (t[:, 12] - t[:, 0])
-print(f"CTAs {n}, mean cycles per CTA {tot.mean():.0f} (min {tot.min():.0f}, max {tot.max():.0f})")
+names = ["wait bd (issued in the previous tile)", "ac loads + slab-free barrier", "shift", "barrier", "wait ac", "pass A", "pass B",
+         "barrier", "pass C", "wait O", "O store"]
+dt = t[:, 1:12] - t[:, 0:11]
+tot = (t[:, 11] - t[:, 0])
+print(f"tiles {n}, mean cycles per tile {tot.mean():.0f} (min {tot.min():.0f}, max {tot.max():.0f})")
 for i, nm in enumerate(names):
-    print(f"  {nm:24s} {dt[:, i].mean():8.0f}  ({100 * dt[:, i].mean() / tot.mean():4.1f} %)   first-wave {dt[:148, i].mean():8.0f}  later {dt[148:, i].mean():8.0f}")
+    print(f"  {nm:40s} {dt[:, i].mean():8.0f}  ({100 * dt[:, i].mean() / tot.mean():4.1f} %)   first-wave {dt[:148, i].mean():8.0f}  later {dt[148:, i].mean():8.0f}")
