@@ -241,7 +241,6 @@ rel_attn_fwd_kernel(const __grid_constant__ CUtensorMap m_qu, const __grid_const
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
-
     Ctl cx;
     cx.smem = smem; cx.bars = bars; cx.tmem_base = tmem_base; cx.H = p.H; cx.tiles = p.tiles; cx.T = T; cx.ld = p.ld;
 
@@ -261,6 +260,9 @@ rel_attn_fwd_kernel(const __grid_constant__ CUtensorMap m_qu, const __grid_const
         ctl_bd_loads(cx, &m_qv, &m_p, blockIdx.x);
         mbar_wait(bars + BAR_BDIN, 0);
         ctl_score_mma(cx, OFF_QV, BAR_BD_DONE);  // bd = (q+v) . P^T
+        // (q+u) and K (into P's place) once the bd MMAs have released it (later tiles: at the end of the previous tile)
+        mbar_wait(bars + BAR_BD_DONE, 0);
+        ctl_ac_loads(cx, &m_qu, &m_k, blockIdx.x);
     }
     __syncwarp();
 
@@ -274,18 +276,17 @@ rel_attn_fwd_kernel(const __grid_constant__ CUtensorMap m_qu, const __grid_const
         mbar_wait(bars + BAR_BD_DONE, ph);
         tc_fence_after();
         FA_STAMP(1);
-        if (ctl) {
-            // the bd MMAs have released (q+v) and P: (q+u) and K (into P's place) for the ac MMAs
-            ctl_ac_loads(cx, &m_qu, &m_k, tt);
-            bulk_wait_read<0>();  // the previous tile's probability stores have read the slabs the flat buffer aliases
-        }
-        __syncwarp();
-        epi_barrier();
-        FA_STAMP(2);
         {
 #pragma unroll
             for (int ch = 0; ch < PARTW / CH; ++ch) tc_ld16_issue(lane_addr + (uint32_t)(cb + ch * CH), sv + ch * CH);
             tc_wait_ld();
+            FA_STAMP(12);
+            // the flat buffer aliases the slabs the previous tile's probability stores read: they must be done (thread 0 issued
+            // them) before anybody writes it; the barrier sits AFTER the TMEM reads so that it costs nothing
+            if (ctl) bulk_wait_read<0>();
+            __syncwarp();
+            epi_barrier();
+            FA_STAMP(2);
             const int r0 = (tt % p.tiles) * TOUT;
             const int off = r * (T + 1) + r0 - T;  // flat position of the padded zero of bd row g
             if (part == 0) flat[off] = 0;
@@ -355,6 +356,7 @@ rel_attn_fwd_kernel(const __grid_constant__ CUtensorMap m_qu, const __grid_const
             //  of sv is defined on every path and the array stays in registers)
             for (int ch = 0; ch < PARTW / CH; ++ch) tc_ld16_issue(lane_addr + (uint32_t)(cb + ch * CH), sv + ch * CH);
             tc_wait_ld();
+            FA_STAMP(13);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bars + BAR_S_DRAINED);  // TMEM[0,320) may take the next tile's bd
@@ -447,14 +449,21 @@ rel_attn_fwd_kernel(const __grid_constant__ CUtensorMap m_qu, const __grid_const
         FA_STAMP(9);
         if (ctl) {
             // O = p . V  (K = keys, 16 per instruction; key blocks beyond T hold zero probabilities and are skipped)
+            const bool has_next = tt + (int)gridDim.x < total;
+            if (has_next) {  // the next tile's bd first: every warp has copied this tile's scores out of TMEM[0,320)
+                mbar_wait(bars + BAR_S_DRAINED, ph);
+                mbar_wait(bars + BAR_BDIN, ph ^ 1);
+                ctl_score_mma(cx, OFF_QV, BAR_BD_DONE);
+            }
             mbar_wait(bars + BAR_V, ph);
             mbar_wait(bars + BAR_P_READY, ph);
             if (tt != (int)blockIdx.x) mbar_wait(bars + BAR_O_DRAINED, ph ^ 1);  // the workers have read the previous tile's O out of TMEM
             ctl_pv_mma_store(cx, &m_probs, tt);
-            if (tt + (int)gridDim.x < total) {  // the next tile's bd: every warp has copied this tile's scores out of TMEM[0,320)
-                mbar_wait(bars + BAR_S_DRAINED, ph);
-                mbar_wait(bars + BAR_BDIN, ph ^ 1);
-                ctl_score_mma(cx, OFF_QV, BAR_BD_DONE);
+            if (has_next) {
+                // the next tile's (q+u) and K as soon as its bd MMAs have released P: the 56 KB land while this tile's O is
+                // stored, not during the next shift (which is bound by shared-memory store wavefronts)
+                mbar_wait(bars + BAR_BD_DONE, ph ^ 1);
+                ctl_ac_loads(cx, &m_qu, &m_k, tt + gridDim.x);
             }
         }
         __syncwarp();
@@ -552,7 +561,8 @@ int lasr_rel_attn_fwd(const void* qu, const void* qv, long ldq, const void* k, c
     }
     LASR_REQUIRE(ld >= T && ld % 8 == 0 && ld <= fa::TKMAX, "rel_attn_fwd: ld must be a multiple of 8 in [T, %d]", fa::TKMAX);
     LASR_REQUIRE(mask_mode >= 0 && mask_mode <= 3 && (mask_mode == 0 || lens), "rel_attn_fwd: bad mask mode");
-    LASR_REQUIRE(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0, "rel_attn_fwd: O must be 16-byte aligned");
+    LASR_REQUIRE(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0 && (reinterpret_cast<uintptr_t>(probs) & 15) == 0,
+                 "rel_attn_fwd: O and probs must be 16-byte aligned");
     const long d = (long)H * dk;
     CUtensorMap m_qu, m_qv, m_k, m_v, m_p, m_probs;
     int rc;

@@ -150,7 +150,23 @@ __global__ void __launch_bounds__(256) pos_bias_bwd_kernel(const TD* __restrict_
     const int r0 = blockIdx.y * 64, r1 = min(rows, r0 + 64);
     float4 au = make_float4(0, 0, 0, 0), av = make_float4(0, 0, 0, 0);
     if (c < d) {
-        for (int r = r0 + ty; r < r1; r += 4) {
+        // 8 rows per trip with all 16 loads issued before the first use (the kernel ran at 1.7 TB/s with one row in flight)
+        int r = r0 + ty;
+        for (; r + 28 < r1; r += 32) {
+            float4 a[8], b[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                a[i] = ld4<TD>(dqu + (long)(r + 4 * i) * ldi + c);
+                b[i] = ld4<TD>(dqv + (long)(r + 4 * i) * ldi + c);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                st4<TD>(dq + (long)(r + 4 * i) * ldq + c, make_float4(a[i].x + b[i].x, a[i].y + b[i].y, a[i].z + b[i].z, a[i].w + b[i].w));
+                au.x += a[i].x; au.y += a[i].y; au.z += a[i].z; au.w += a[i].w;
+                av.x += b[i].x; av.y += b[i].y; av.z += b[i].z; av.w += b[i].w;
+            }
+        }
+        for (; r < r1; r += 4) {
             const float4 a = ld4<TD>(dqu + (long)r * ldi + c), b = ld4<TD>(dqv + (long)r * ldi + c);
             st4<TD>(dq + (long)r * ldq + c, make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w));
             au.x += a.x; au.y += a.y; au.z += a.z; au.w += a.w;

@@ -24,10 +24,12 @@ ops.rel_attn_fwd(qu, qv, k, v, pos, probs, o, lens, 3, dk ** -0.5, B, H, T, dk)
 torch.cuda.synchronize()
 _lib.lib().lasr_rel_attn_fwd_set_trace(C.c_void_p(0))
 t = tr.cpu().double()
-names = ["wait bd (issued in the previous tile)", "ac loads + slab-free barrier", "shift", "barrier", "wait ac", "pass A", "pass B",
-         "barrier", "pass C", "wait O", "O store"]
-dt = t[:, 1:12] - t[:, 0:11]
-tot = (t[:, 11] - t[:, 0])
+order = [0, 1, 12, 2, 3, 4, 5, 13, 6, 7, 8, 9, 10, 11]
+names = ["wait bd (issued in the previous tile)", "TMEM read of bd", "slab-free barrier", "shift stores", "barrier (flat complete)",
+         "wait ac", "TMEM read of ac", "pass A (scores)", "pass B (ex2, sums)", "barrier (max, sum exchange)", "pass C (bf16 tile)",
+         "wait O", "O store"]
+tot = t[:, 11] - t[:, 0]
 print(f"tiles {n}, mean cycles per tile {tot.mean():.0f} (min {tot.min():.0f}, max {tot.max():.0f})")
 for i, nm in enumerate(names):
-    print(f"  {nm:40s} {dt[:, i].mean():8.0f}  ({100 * dt[:, i].mean() / tot.mean():4.1f} %)   first-wave {dt[:148, i].mean():8.0f}  later {dt[148:, i].mean():8.0f}")
+    d = t[:, order[i + 1]] - t[:, order[i]]
+    print(f"  {nm:40s} {d.mean():8.0f}  ({100 * d.mean() / tot.mean():4.1f} %)   first tile of a CTA {d[:148].mean():8.0f}  later {d[148:].mean():8.0f}")
