@@ -51,6 +51,11 @@ int lasr_gemm(const lasr_gemm_args* a, void* stream) {
     if (a->dact)
         LASR_REQUIRE(!a->bias && !a->res && !a->aux && (a->act == LASR_ACT_SWISH || a->act == LASR_ACT_RELU) && a->lddact > 0,
                      "gemm: dact needs act = swish|relu and no bias/res/aux");
+    if (a->a2)
+        LASR_REQUIRE(a->b2 && a->ab_dtype == LASR_BF16 && a->c_dtype == LASR_BF16 && !a->bias && !a->res && !a->aux && !a->dact &&
+                         !a->accumulate && !a->n_store && a->batch1 == 1 && a->batch2 == 1 && !a->trans_a && a->k2 > 0 &&
+                         (a->k2 + 63) / 64 == (a->k + 63) / 64 && (a->act == LASR_ACT_SWISH || a->act == LASR_ACT_RELU),
+                     "gemm: recompute needs bf16 operands and C, act = swish|relu, equal K block counts, no batching and no other epilogue operand");
     if (a->split_k > 1) LASR_REQUIRE(a->accumulate, "gemm: split_k > 1 requires accumulate");
     if (a->n_store)
         LASR_REQUIRE(a->n_store >= a->n && a->n_store <= a->ldc && !a->bias && !a->res && !a->aux && !a->dact && !a->colsum && !a->accumulate,

@@ -77,6 +77,8 @@ struct TcParams {
     int c_b1, c_b2;    // 1 if C really advances along that batch level (TMA store coordinates)
     int b_stationary;  // K <= 256 GEMMs: every CTA keeps ONE N tile of B resident in shared memory and streams A tiles only
     int bsta_bytes;    // size of that resident tile
+    int dual;          // recompute mode: a second accumulator A2.B2^T (K-major operands) at TMEM columns [128, 128 + bn) of the buffer
+    const float* bias2;  // bias of the recomputed Linear
     int conv_mode;     // 0 plain GEMM | 1 forward | 2 input gradient (one parity class) | 3 weight gradient
     int conv_kbt;      // K blocks per tap (= channels / 64)
     int conv_d;        // channels
@@ -152,7 +154,8 @@ __device__ __forceinline__ void store4(CT* dst, const float4& f) {
 }
 
 // Epilogue modes: the column phase is specialised so that its inner loop carries no run-time flag tests.
-enum { EPI_PLAIN = 0, EPI_RELU = 1, EPI_SWISH = 2, EPI_RES = 3, EPI_ACC = 4, EPI_GENERIC = 5, EPI_DSWISH = 6, EPI_DRELU = 7 };
+enum { EPI_PLAIN = 0, EPI_RELU = 1, EPI_SWISH = 2, EPI_RES = 3, EPI_ACC = 4, EPI_GENERIC = 5, EPI_DSWISH = 6, EPI_DRELU = 7,
+       EPI_DUAL_DSWISH = 8, EPI_DUAL_DRELU = 9 };  // DUAL: act'(.) of a pre-activation recomputed into a second accumulator
 
 // CW = staged chunk width in fp32 columns (32, or 16 in the B-stationary kernels).  The staging buffer holds 32 rows x CW
 // columns; a row is PIECES = CW/4 16-byte pieces, XOR-swizzled so that both the row-per-thread writes and the row-contiguous
@@ -217,6 +220,20 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, const Unit& w, 
             float v[CW];
             if constexpr (CW == 32) tc_ld32(taddr + (uint32_t)cc, v);
             else tc_ld16(taddr + (uint32_t)cc, v);
+            if constexpr (MODE == EPI_DUAL_DSWISH || MODE == EPI_DUAL_DRELU) {
+                // C = alpha * acc * act'(acc2 + bias2): the recomputed pre-activation sits 128 TMEM columns further; its bias is
+                // the same 32 floats for every lane (warp-uniform loads)
+                float pre[32];
+                tc_ld32(taddr + 128u + (uint32_t)cc, pre);
+                const int c0 = w.n0 + cc;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float b = (p.bias2 && c0 + j < p.n) ? __ldg(p.bias2 + c0 + j) : 0.f;
+                    const float x = pre[j] + b;
+                    if constexpr (MODE == EPI_DUAL_DSWISH) v[j] *= alpha * dswish_fast(x);
+                    else v[j] = x > 0.f ? alpha * v[j] : 0.f;
+                }
+            }
             __syncwarp();  // the previous chunk's column phase has finished reading the staging buffer
 #pragma unroll
             for (int j = 0; j < PIECES; ++j)
@@ -255,6 +272,9 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, const Unit& w, 
                         }
                         store4<CT>(crow, f);
                         cs.x += f.x; cs.y += f.y; cs.z += f.z; cs.w += f.w;
+                    } else if constexpr (MODE == EPI_DUAL_DSWISH || MODE == EPI_DUAL_DRELU) {
+                        store4<CT>(crow, f);  // finished in the row phase
+                        cs.x += f.x; cs.y += f.y; cs.z += f.z; cs.w += f.w;
                     } else if constexpr (MODE == EPI_RES) {
                         f.x = fmaf(f.x, alpha, ba.x) + r4[i].x; f.y = fmaf(f.y, alpha, ba.y) + r4[i].y;
                         f.z = fmaf(f.z, alpha, ba.z) + r4[i].z; f.w = fmaf(f.w, alpha, ba.w) + r4[i].w;
@@ -276,7 +296,7 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, const Unit& w, 
                 }
                 off += rstride;
             }
-            if constexpr (MODE == EPI_PLAIN || DACT) {
+            if constexpr (MODE == EPI_PLAIN || DACT || MODE == EPI_DUAL_DSWISH || MODE == EPI_DUAL_DRELU) {
                 if (csbase) {  // warp-uniform: fold the row groups (lanes with the same piece), then one vector red per 4 columns
 #pragma unroll
                     for (int o = PIECES; o < 32; o <<= 1) {
@@ -540,7 +560,8 @@ struct Walk {
 template <int MODE, bool C_F32, bool BS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-               const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_x, const TcParams p) {
+               const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_x,
+               const __grid_constant__ CUtensorMap tma_a2, const __grid_constant__ CUtensorMap tma_b2, const TcParams p) {
     constexpr int CW = BS ? 16 : 32;
     const bool A_MN = p.a_mn != 0, B_MN = p.b_mn != 0;
     extern __shared__ uint8_t smem_raw[];
@@ -561,6 +582,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tma_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tma_b) : "memory");
+        if (p.dual) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tma_a2) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tma_b2) : "memory");
+        }
         if (p.tma_epi) {
             asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tma_c) : "memory");
             if (p.aux) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tma_x) : "memory");
@@ -653,6 +678,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                                 for (int j = 0; j < p.bn / 64; ++j)
                                     tma_load_4d(sb + j * 8192, &tma_b, full_bar + s, w.n0 + 64 * j, k0, bb2, bb1);
                             }
+                            if (p.dual) {  // the recomputed Linear's input and weight slabs, both K-major, behind A and B in the stage
+                                uint8_t* sa2 = sb + b_kb_bytes;
+                                tma_load_4d(sa2, &tma_a2, full_bar + s, k0, w.m0, 0, 0);
+                                tma_load_4d(sa2 + A_BYTES, &tma_b2, full_bar + s, k0, w.n0, 0, 0);
+                            }
                         }
                     }
                     if (++s == p.stages) { s = 0; ph ^= 1; }
@@ -688,6 +718,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         const uint64_t da = A_MN ? umma_desc(sa + kk * 2048, 8192, 1024) : umma_desc(sa + kk * 32, 16, 1024);
                         const uint64_t db = B_MN ? umma_desc(sb + kk * 2048, 8192, 1024) : umma_desc(sb + kk * 32, 16, 1024);
                         tc_mma_bf16(tmem_d, da, db, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+                        if (!BS && p.dual) {  // second accumulator (bn <= 128): A2.B2^T, K-major operands
+                            const uint32_t sa2 = sb + (uint32_t)b_kb_bytes;
+                            tc_mma_bf16(tmem_d + 128u, umma_desc(sa2 + kk * 32, 16, 1024), umma_desc(sa2 + A_BYTES + kk * 32, 16, 1024),
+                                        idesc & ~((1u << 15) | (1u << 16)), (i > 0 || kk > 0) ? 1u : 0u);
+                        }
                     }
                     tc_commit(empty_bar + s);  // frees the smem slot once these MMAs retire
                     if (++s == p.stages) { s = 0; ph ^= 1; }
@@ -706,7 +741,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         Walk<BS> walk(p);
         Unit w;
         typedef typename std::conditional<C_F32, float, bf16>::type CT;
-        constexpr bool TMA_OK = !BS && MODE != EPI_GENERIC;
+        constexpr bool TMA_OK = !BS && MODE != EPI_GENERIC && MODE != EPI_DUAL_DSWISH && MODE != EPI_DUAL_DRELU;
         const bool tma_epi = TMA_OK && p.tma_epi != 0;
         while (walk.next(p, w)) {
             mbar_wait(acc_full + as, aph);
@@ -816,7 +851,7 @@ static void setup_tma_epilogue(TcParams& p, CUtensorMap* mc, CUtensorMap* mx, in
     p.c_b2 = (p.sc2 != 0 && nb2 > 1);
     const char* env = getenv("LASR_GEMM_TMA_EPI");  // developer switch (read per call so that tests can toggle it)
     if (env && atoi(env) == 0) return;
-    if (p.epi_mode == EPI_GENERIC || p.b_stationary) return;
+    if (p.epi_mode == EPI_GENERIC || p.b_stationary || p.dual) return;
     // Row-per-thread math makes the residual / saved-activation reads 32-lines-per-instruction gathers and the column sums a
     // 31-shuffle transpose: measured slower than the column-phase epilogue (fc2 + residual 62 vs 51 us, dswish + colsum 128 vs
     // 103 us at C2/B=126), so those modes keep it.  LASR_GEMM_TMA_EPI=2 forces the TMA path for every mode (tests).
@@ -847,7 +882,8 @@ static int pick_bn(int n, int gran) {
     return best;
 }
 
-typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams);
+typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                         const TcParams);
 
 template <int MODE, bool C_F32, bool BS>
 static TcKernel configured_kernel() {
@@ -880,12 +916,14 @@ static TcKernel pick_kernel(int mode, bool f32) {
         case EPI_SWISH: return configured_kernel<EPI_SWISH, false, BS>();
         case EPI_DSWISH: return configured_kernel<EPI_DSWISH, false, BS>();
         case EPI_DRELU: return configured_kernel<EPI_DRELU, false, BS>();
+        case EPI_DUAL_DSWISH: return BS ? nullptr : configured_kernel<EPI_DUAL_DSWISH, false, false>();
+        case EPI_DUAL_DRELU: return BS ? nullptr : configured_kernel<EPI_DUAL_DRELU, false, false>();
         default: return configured_kernel<EPI_GENERIC, false, BS>();
     }
 }
 
 static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mx, const TcParams& p,
-                     cudaStream_t st) {
+                     cudaStream_t st, const CUtensorMap* ma2 = nullptr, const CUtensorMap* mb2 = nullptr) {
     const bool f32 = p.c_dtype == LASR_F32;
     TcKernel kern = p.b_stationary ? pick_kernel<true>(p.epi_mode, f32) : pick_kernel<false>(p.epi_mode, f32);
     if (!kern) return check_launch("gemm_tc smem attr");
@@ -909,16 +947,21 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtenso
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    if (cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, mx, p) != cudaSuccess) return check_launch("gemm_tc launch");
+    if (cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, mx, ma2 ? *ma2 : ma, mb2 ? *mb2 : mb, p) != cudaSuccess) return check_launch("gemm_tc launch");
     return check_launch("gemm_tc");
 }
 
 int gemm_tc_dispatch(const lasr_gemm_args* a, cudaStream_t st) {
     const int n_store = a->n_store ? a->n_store : a->n;
     // N tiles are multiples of 32 columns: the TMA-store epilogue writes whole 32-column boxes, clipped only at the tensor edge
-    const int bn = pick_bn(n_store, a->trans_b ? 64 : 32);
-    CUtensorMap ma, mb;
+    // recompute mode: two accumulators share a 256-column TMEM buffer -> N tiles of at most 128 columns
+    const int bn = a->a2 ? (n_store >= 128 ? 128 : pick_bn(n_store, 64)) : pick_bn(n_store, a->trans_b ? 64 : 32);
+    CUtensorMap ma, mb, ma2, mb2;
     int rc;
+    if (a->a2) {
+        if ((rc = make_map(&ma2, a->a2, a->k2, a->m, a->lda2, 1, 0, 1, 0, BK, BM))) return rc;
+        if ((rc = make_map(&mb2, a->b2, a->k2, a->n, a->ldb2, 1, 0, 1, 0, BK, bn))) return rc;
+    }
     if (!a->trans_a) rc = make_map(&ma, a->a, a->k, a->m, a->lda, a->batch2, a->sa2, a->batch1, a->sa1, BK, BM);
     else rc = make_map(&ma, a->a, a->m, a->k, a->lda, a->batch2, a->sa2, a->batch1, a->sa1, 64, BK);
     if (rc) return rc;
@@ -947,7 +990,10 @@ int gemm_tc_dispatch(const lasr_gemm_args* a, cudaStream_t st) {
     p.colsum = a->colsum; p.cs1 = a->cs1; p.cs2 = a->cs2;
     if (a->dact) p.vec_ok = p.vec_ok && ((reinterpret_cast<uintptr_t>(a->dact) & 7) == 0) && ((a->lddact * 2) % 8 == 0) && al16(a->sc1, 2) && al16(a->sc2, 2);
     if (a->colsum) p.vec_ok = p.vec_ok && ((reinterpret_cast<uintptr_t>(a->colsum) & 15) == 0) && al16(a->cs1, 4) && al16(a->cs2, 4);
-    if (a->accumulate) p.epi_mode = EPI_ACC;
+    p.dual = a->a2 ? 1 : 0;
+    p.bias2 = a->bias2;
+    if (a->a2) p.epi_mode = a->act == LASR_ACT_SWISH ? EPI_DUAL_DSWISH : EPI_DUAL_DRELU;
+    else if (a->accumulate) p.epi_mode = EPI_ACC;
     else if (a->dact && a->act == LASR_ACT_SWISH) p.epi_mode = EPI_DSWISH;
     else if (a->dact && a->act == LASR_ACT_RELU) p.epi_mode = EPI_DRELU;
     else if (a->colsum && (a->res || a->aux || a->act != LASR_ACT_NONE)) p.epi_mode = EPI_GENERIC;
@@ -957,7 +1003,7 @@ int gemm_tc_dispatch(const lasr_gemm_args* a, cudaStream_t st) {
     else if (!a->res && !a->aux && a->act == LASR_ACT_NONE) p.epi_mode = EPI_PLAIN;
     else p.epi_mode = EPI_GENERIC;
     p.bn = bn;
-    p.stage_bytes = A_BYTES + bn * BK * 2;
+    p.stage_bytes = (A_BYTES + bn * BK * 2) * (p.dual ? 2 : 1);
     p.stages = SM_RING_BUDGET / p.stage_bytes;
     if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
     p.tiles_m = ceil_div(a->m, BM);
@@ -985,7 +1031,7 @@ int gemm_tc_dispatch(const lasr_gemm_args* a, cudaStream_t st) {
         const char* bs_env = getenv("LASR_GEMM_BS");
         const int bs_on = bs_env ? atoi(bs_env) : 0;
         const int total_kb = (a->k + BK - 1) / BK;
-        if (bs_on && total_kb <= 4 && p.split_k == 1 && !a->accumulate && a->batch1 * a->batch2 == 1 && p.tiles_n <= sm_count() / 2) {
+        if (bs_on && !p.dual && total_kb <= 4 && p.split_k == 1 && !a->accumulate && a->batch1 * a->batch2 == 1 && p.tiles_n <= sm_count() / 2) {
             const int per_n = sm_count() / p.tiles_n;                  // CTAs per N tile
             const int rounds = (p.tiles_m + per_n - 1) / per_n;        // M tiles of the busiest CTA
             const double eff = (double)p.tiles_m / ((double)rounds * per_n);
@@ -1001,6 +1047,10 @@ int gemm_tc_dispatch(const lasr_gemm_args* a, cudaStream_t st) {
     }
     CUtensorMap mc, mx;
     setup_tma_epilogue(p, &mc, &mx, a->batch1, a->batch2);
+    if (p.dual) {
+        if (p.vec_ok == 0 || p.stages < 2 || (a->n & 3)) { set_error("gemm_tc: recompute mode needs 16-byte aligned C / colsum and N % 4 == 0"); return LASR_ERR_UNSUPPORTED; }
+        return launch_tc(ma, mb, mc, mx, p, st, &ma2, &mb2);
+    }
     return launch_tc(ma, mb, mc, mx, p, st);
 }
 
@@ -1078,7 +1128,7 @@ int conv2_tc_dispatch(int mode, int plane_class, const void* h1p, const void* w2
         return LASR_ERR_BAD_ARG;
     }
     p.bn = bn;
-    p.stage_bytes = A_BYTES + bn * BK * 2;
+    p.stage_bytes = (A_BYTES + bn * BK * 2) * (p.dual ? 2 : 1);
     p.stages = SM_RING_BUDGET / p.stage_bytes;
     if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
     p.tiles_m = ceil_div(p.m, BM);

@@ -41,12 +41,19 @@ class Engine:
     def __init__(self, store: ParamStore):
         self.st = store
         self.adt = store.adt
-        # attention score tensors (ac, bd, dprobs): fp32, or the operand dtype with LASR_SCORES_BF16=1 (bf16 mode only) -- what torch
-        # autocast's matmul hands to the softmax; halves the score traffic at a bf16 rounding of the pre-softmax logits
-        self.sdt = store.adt if (store.adt == torch.bfloat16 and os.environ.get("LASR_SCORES_BF16", "0") == "1") else torch.float32
+        # attention score tensors that still round-trip through HBM (dprobs of every attention backward; ac / bd of the unfused
+        # forward: decoder attentions, T' > 320): the operand dtype in bf16 mode -- what torch autocast's matmul hands to the softmax
+        # in the reference's bf16 run -- which halves their traffic (183 -> 91 MB per tensor at C2/B=126; 0.9 % of the step).
+        # LASR_SCORES_BF16=0 keeps them in fp32.
+        self.sdt = store.adt if (store.adt == torch.bfloat16 and os.environ.get("LASR_SCORES_BF16", "1") != "0") else torch.float32
         self.dev = store.device
         # LASR_FUSED_ATTN=0: developer switch back to GEMM -> softmax kernel -> GEMM for the rel-pos attention forward
         self.fused_attn = os.environ.get("LASR_FUSED_ATTN", "1") != "0"
+        # LASR_FFN_RECOMPUTE=1 (developer switch, off): fc1 of a Swish FFN does not save its pre-activation and the backward GEMM
+        # recomputes it into a second TMEM accumulator.  Saves 154 MB written + 135 MB read per FFN at C2/B=126 but measured
+        # SLOWER (32.0 vs 30.7 ms per step): two accumulators force 128-column N tiles, and at K = 256 the four operand slabs of a
+        # tile (256 KB for a 128 x 128 output) make the GEMM L2 -> shared-memory bound (1.2 GB per launch against 0.45 GB).
+        self.ffn_recompute = store.adt == torch.bfloat16 and os.environ.get("LASR_FFN_RECOMPUTE", "0") == "1"
 
     # ------------------------------------------------------------------------------------------
     # small helpers
@@ -129,14 +136,15 @@ class Engine:
         ops.gemm(dy, x, gw, n, k, m, lda=dy.stride(0), ldb=x.stride(0), ldc=gw.stride(0), ta=True, tb=True, accumulate=True,
                  split_k=self._split_k(n, k, m), alpha=alpha)
 
-    def dgrad(self, dy, w, *, out_dtype=None, alpha=1.0, dx_res=None, dact=None, act=ACT_NONE, colsum=None):
+    def dgrad(self, dy, w, *, out_dtype=None, alpha=1.0, dx_res=None, dact=None, act=ACT_NONE, colsum=None, recompute=None):
         """dx = alpha * dy @ W (W stored (N_out, K_in)); optional fused activation backward (``dact``/``act``), bias-gradient
         column sum of the result (``colsum``) and fp32 accumulation into ``dx_res``."""
         m, n = dy.shape
         k = w.shape[1]
         dx = _empty((m, k), self.adt if out_dtype is None else out_dtype, self.dev) if dx_res is None else dx_res
         ops.gemm(dy, w, dx, m, k, n, lda=dy.stride(0), ldb=w.stride(0), ldc=dx.stride(0), tb=True, alpha=alpha,
-                 res=dx_res, ldres=(dx_res.stride(0) if dx_res is not None else 0), dact=dact, act=act, colsum=colsum)
+                 res=dx_res, ldres=(dx_res.stride(0) if dx_res is not None else 0), dact=dact, act=act, colsum=colsum,
+                 recompute=recompute)
         return dx
 
     def linear_bwd(self, dy, x, wname, *, need_dx=True, dx_dtype=None, bias=True, dbias_done=False, alpha=1.0, w=None,
@@ -157,9 +165,9 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     def ffn_fwd(self, x, pfx_norm, pfx_ff, act, scale) -> NS:
         ln = self.layernorm(x, pfx_norm, self.adt)
-        if act == ACT_SWISH:
+        if act == ACT_SWISH and not self.ffn_recompute:
             a, h = self.linear(ln.y, pfx_ff + ".fc1", self.adt, act=act, aux=True)
-        else:
+        else:  # ReLU: act'(.) from the output; Swish in bf16 mode: the pre-activation is recomputed in the backward GEMM
             a, h = self.linear(ln.y, pfx_ff + ".fc1", self.adt, act=act), None
         out = self.linear(a, pfx_ff + ".fc2", torch.float32, res=x, alpha=scale)
         return NS(out=out, ln=ln, a=a, h=h, act=act, scale=scale, pfx=pfx_ff)
@@ -170,8 +178,14 @@ class Engine:
         st = self.st
         self.wgrad(dy, c.a, st.gw(c.pfx + ".fc2.weight"), c.scale)
         # dh = scale * (dy @ W2) * act'(.)  and  db1 += colsum(dh), both in the dgrad epilogue
-        dh = self.dgrad(dy, st.w(c.pfx + ".fc2.weight"), alpha=c.scale, dact=(c.h if c.act == ACT_SWISH else c.a), act=c.act,
-                        colsum=st.g(c.pfx + ".fc1.bias"))
+        if c.act == ACT_SWISH and c.h is None:
+            # fc1's pre-activation is recomputed on the tensor cores inside this GEMM (second TMEM accumulator) instead of being
+            # written by the forward pass and read back: 154 MB less written and 135 MB less read per FFN at C2/B=126
+            dh = self.dgrad(dy, st.w(c.pfx + ".fc2.weight"), alpha=c.scale, act=c.act, colsum=st.g(c.pfx + ".fc1.bias"),
+                            recompute=(c.ln.y, st.w(c.pfx + ".fc1.weight"), st.p(c.pfx + ".fc1.bias")))
+        else:
+            dh = self.dgrad(dy, st.w(c.pfx + ".fc2.weight"), alpha=c.scale, dact=(c.h if c.act == ACT_SWISH else c.a), act=c.act,
+                            colsum=st.g(c.pfx + ".fc1.bias"))
         self.wgrad(dh, c.ln.y, st.gw(c.pfx + ".fc1.weight"))
         dln = self.dgrad(dh, st.w(c.pfx + ".fc1.weight"))
         return self.layernorm_bwd(c.ln, dln, dres, True, nxt, want_lo)

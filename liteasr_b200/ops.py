@@ -43,7 +43,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, m: int, n: int, k: i
          ldres: int = 0, aux: Optional[torch.Tensor] = None, alpha: float = 1.0, act: int = ACT_NONE,
          accumulate: bool = False, split_k: int = 1, batch: Tuple[int, int] = (1, 1), sa: Tuple[int, int] = (0, 0),
          sb: Tuple[int, int] = (0, 0), sc: Tuple[int, int] = (0, 0), dact: Optional[torch.Tensor] = None,
-         colsum: Optional[torch.Tensor] = None, cs: Tuple[int, int] = (0, 0), n_store: int = 0) -> None:
+         colsum: Optional[torch.Tensor] = None, cs: Tuple[int, int] = (0, 0), n_store: int = 0,
+         recompute: Optional[Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]] = None) -> None:
     """C[b1,b2] = alpha * act(A.B^T + bias) (+ res); see include/lasr.h ``lasr_gemm``."""
     _require_cuda(a, b, c, bias, res, aux, dact, colsum)
     if a.dtype != b.dtype:
@@ -67,6 +68,14 @@ def gemm(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, m: int, n: int, k: i
     g.colsum = colsum.data_ptr() if colsum is not None else None
     g.cs1, g.cs2 = cs
     g.n_store = n_store
+    if recompute is not None:  # (x, W, bias) of the forward Linear whose pre-activation is recomputed in the epilogue
+        x2, w2, b2 = recompute
+        _require_cuda(x2, w2, b2)
+        if x2.dtype != a.dtype or w2.dtype != a.dtype or x2.stride(1) != 1 or w2.stride(1) != 1:
+            raise TypeError("recompute operands must be row-major tensors of the operand dtype")
+        g.a2, g.b2 = x2.data_ptr(), w2.data_ptr()
+        g.bias2 = b2.data_ptr() if b2 is not None else None
+        g.lda2, g.ldb2, g.k2 = x2.stride(0), w2.stride(0), x2.shape[1]
     if dact is not None and (dact.dtype != a.dtype or dact.dim() != 2 or dact.stride(1) != 1):
         raise TypeError("dact must be a 2-D row-major tensor of the operand dtype")
     if colsum is not None and colsum.dtype != torch.float32:

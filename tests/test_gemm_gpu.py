@@ -209,3 +209,51 @@ def test_gemm_n_store_pads_with_zeros(dtype):
     tol = 2e-2 if dtype == torch.bfloat16 else 1e-4
     assert (c[..., :T] - ref).abs().max().item() <= tol * ref.abs().max().item()
     assert (c[..., T:] == 0).all()
+
+
+@pytest.mark.parametrize("act", ["swish", "relu"])
+@pytest.mark.parametrize("m,n,k", [(333, 320, 256), (1000, 2048, 256), (77, 100, 64), (129, 128, 128), (4000, 1024, 256)])
+def test_gemm_recomputed_preactivation_backward(act, m, n, k):
+    """Recompute mode (bf16): C = alpha * (dy @ W2) * act'(x @ W1^T + b1) with the pre-activation rebuilt by a second MMA into
+    a second TMEM accumulator of the same tile, colsum += sum_rows C -- the FFN backward of nets/feed_forward.py:18-19 without a
+    saved pre-activation tensor.  Reference: plain torch fp32 on the same bf16-rounded operands."""
+    from liteasr_b200 import ops
+    dtype = torch.bfloat16
+    g = torch.Generator(device="cuda").manual_seed(m + n + k)
+    dy, w2 = _mk(m, k, dtype, g), _mk(k, n, dtype, g)    # W2 stored (N_out=k, K_in=n): dh = dy @ W2
+    x, w1 = _mk(m, k, dtype, g), _mk(n, k, dtype, g)     # fc1: pre = x @ W1^T + b1, W1 stored (n, k)
+    b1 = torch.randn(n, generator=g, device="cuda") * 0.3
+    cs = torch.randn(n, generator=g, device="cuda")
+    cs0 = cs.clone()
+    ld = (n + 7) // 8 * 8
+    out = torch.full((m, ld), float("nan"), device="cuda", dtype=dtype)[:, :n]
+    code = ops.ACT_SWISH if act == "swish" else ops.ACT_RELU
+    ops.gemm(dy, w2, out, m, n, k, lda=dy.stride(0), ldb=w2.stride(0), ldc=ld, tb=True, alpha=0.5, act=code, colsum=cs,
+             recompute=(x, w1, b1))
+    pre = x.float() @ w1.float().t() + b1
+    sg = torch.sigmoid(pre)
+    dact = sg * (1 + pre * (1 - sg)) if act == "swish" else (pre > 0).float()
+    ref = 0.5 * (dy.float() @ w2.float()) * dact
+    assert torch.isfinite(out.float()).all()
+    err = (out.float() - ref).abs()
+    if act == "relu":  # a pre-activation within rounding of 0 may flip the mask: exclude |pre| < 1e-3
+        err = err * (pre.abs() > 1e-3)
+        ref_cs = None
+    assert err.max().item() <= 3e-2 * max(1.0, ref.abs().max().item())
+    if act == "swish":
+        assert (cs - cs0 - ref.sum(0)).abs().max().item() <= 3e-2 * max(1.0, ref.sum(0).abs().max().item())
+    # the same values as the saved-pre-activation path it replaces (which rounds the pre-activation to bf16 first)
+    out2 = torch.empty(m, ld, device="cuda", dtype=dtype)[:, :n]
+    ops.gemm(dy, w2, out2, m, n, k, lda=dy.stride(0), ldb=w2.stride(0), ldc=ld, tb=True, alpha=0.5, dact=pre.to(dtype).contiguous(), act=code)
+    if act == "swish":
+        assert (out.float() - out2.float()).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item())
+
+
+def test_gemm_recompute_rejects_unsupported():
+    from liteasr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(0)
+    dy, w2 = _mk(64, 64, torch.float32, g), _mk(64, 128, torch.float32, g)
+    x, w1 = _mk(64, 64, torch.float32, g), _mk(128, 64, torch.float32, g)
+    out = torch.empty(64, 128, device="cuda")
+    with pytest.raises(RuntimeError):  # fp32 (SIMT) mode has no recompute path
+        ops.gemm(dy, w2, out, 64, 128, 64, lda=64, ldb=128, ldc=128, tb=True, act=ops.ACT_SWISH, recompute=(x, w1, None))
