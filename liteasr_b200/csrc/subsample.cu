@@ -275,6 +275,7 @@ __global__ void __launch_bounds__(256, 3) conv1_bwd_planes_kernel(const float* _
 
 int conv2_tc_dispatch(int mode, int plane_class, const void* h1p, const void* w2, const float* bias, const void* dy, void* out,
                       int B, int U, int V, int T2, int d, int split_k, cudaStream_t st);
+int conv1_wgrad_tc_dispatch(const float* x, const void* dh1p, float* dw, float* dbias, int B, int T, int F, int d, cudaStream_t st);
 
 }  // namespace lasr
 
@@ -346,6 +347,14 @@ int lasr_conv1_fwd_planes(const float* x, const float* w, const float* bias, voi
 
 int lasr_conv1_bwd_planes(const float* x, const void* dh1p, float* dw, float* dbias, int B, int T, int F, int d, void* stream) {
     LASR_REQUIRE(x && dh1p && dw && dbias && B > 0 && T >= 7 && F >= 7 && planes_ok(d), "conv1_bwd_planes: bad args");
+    {
+        // tensor-core path (csrc/conv1_wgrad_tc.cu) for d = 128 / 256 / 384 / 512; LASR_CONV1_TC=0 keeps the SIMT kernel below
+        const char* e = getenv("LASR_CONV1_TC");
+        if (!(e && atoi(e) == 0)) {
+            const int rc = conv1_wgrad_tc_dispatch(x, dh1p, dw, dbias, B, T, F, d, (cudaStream_t)stream);
+            if (rc != LASR_ERR_UNSUPPORTED) return rc;
+        }
+    }
     const int T1 = (T - 3) / 2 + 1, F1 = (F - 3) / 2 + 1, U = (T1 + 1) / 2, V = (F1 + 1) / 2;
     const int cpu = ceil_div(T1, PR_ROWS);
     const long chunks = (long)B * cpu;
