@@ -1,0 +1,257 @@
+// First sub-sampling convolution (Conv2d(1 -> d, 3x3, stride 2) + ReLU, nets/subsampling.py:33) on the tensor cores, output in
+// the parity planes the implicit-GEMM conv2 reads (h1p[b][pt*2+pf][u*V+v][c], slots without a (t1, f1) exactly zero).
+//
+// The SIMT kernel spends 9 fp32 FMAs per output element (6.8 G per step at C2/B = 126) and runs at 2.5 TB/s; the op's floor is
+// its 1.55 GB store stream.  As a GEMM: M = output positions (128 per tile), N = d channels, K = 32:
+//
+//   A[row][k]  = [ xh(9 taps) | xl(9) | xh(9) | 1 | 1 | 0 0 0 ]      x = xh + xl (bf16 head + bf16 tail of the fp32 feature)
+//   B[c][k]    = [ wh(9)      | wh(9) | wl(9) | bh| bl| 0 0 0 ]      w = wh + wl, bias = bh + bl
+//
+// so that A.B^T = bias + sum_tap x.w to ~2^-17 relative although the MMA operands are bf16 (the xl.wl term is dropped).  A row of
+// an invalid slot is all zeros INCLUDING the bias columns, so its output is exactly relu(0) = 0.
+//
+//   warp 1      MMA issuer: two K = 16 steps per tile into one of two 256-column TMEM accumulators
+//   warps 2..5  A builders: thread = row, 9 loads of x (L2-resident), four 16-byte K-major SWIZZLE_128B pieces
+//   warps 6..13 epilogue: TMEM -> ReLU -> bf16 -> swizzled 32 x 32 staging box -> bulk tensor store (two boxes in flight per warp)
+// B is built once per CTA by all threads and stays resident; CTAs are persistent over the (utterance, plane, row block) list.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace lasr {
+namespace c1f {
+
+constexpr int TM = 128;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = TM * 128;
+constexpr int EPI_W = 8;
+constexpr int THREADS = 64 + 128 + 32 * EPI_W;  // 448
+constexpr int OFF_W = 0;                          // d x 128 B (<= 32 KB)
+constexpr int OFF_A = 32768;
+constexpr int OFF_STAGE = OFF_A + STAGES * A_BYTES;        // EPI_W x 2 boxes x 2 KB
+constexpr int OFF_BAR = OFF_STAGE + EPI_W * 2 * 2048;
+constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+
+struct Params {
+    const float* x;
+    const float* w;
+    const float* bias;
+    int B, T, F, T1, F1, U, V, d;
+    int rblocks;  // 128-row blocks per plane
+    long units;   // B * 4 * rblocks
+};
+
+__device__ __forceinline__ uint32_t bf2(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void split(float v, float& h, float& l) {
+    h = __bfloat162float(__float2bfloat16_rn(v));
+    l = v - h;
+}
+
+__global__ void __launch_bounds__(THREADS, 1) conv1_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_out, const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* full_a = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    uint64_t* empty_a = full_a + STAGES;
+    uint64_t* acc_full = empty_a + STAGES;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int d = p.d;
+
+    if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tma_out) : "memory");
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_a + s, 4);
+            mbar_init(empty_a + s, 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(acc_full + s, 1);
+            mbar_init(acc_empty + s, EPI_W);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    LASR_PDL_SYNC();  // the weights are written by the previous step's optimizer kernel: nothing global is read before this
+    // resident B: row c = [wh(9) | wh(9) | wl(9) | bh | bl | 0 0 0], K-major SWIZZLE_128B
+    for (int c = threadIdx.x; c < d; c += THREADS) {
+        float wh[9], wl[9], bh, bl;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) split(p.w[c * 9 + k], wh[k], wl[k]);
+        split(p.bias[c], bh, bl);
+        uint4 q[4];
+        q[0] = make_uint4(bf2(wh[0], wh[1]), bf2(wh[2], wh[3]), bf2(wh[4], wh[5]), bf2(wh[6], wh[7]));
+        q[1] = make_uint4(bf2(wh[8], wh[0]), bf2(wh[1], wh[2]), bf2(wh[3], wh[4]), bf2(wh[5], wh[6]));
+        q[2] = make_uint4(bf2(wh[7], wh[8]), bf2(wl[0], wl[1]), bf2(wl[2], wl[3]), bf2(wl[4], wl[5]));
+        q[3] = make_uint4(bf2(wl[6], wl[7]), bf2(wl[8], bh), bf2(bl, 0.f), 0u);
+        uint8_t* row = smem + OFF_W + c * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(row + ((j ^ (c & 7)) << 4)) = q[j];
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+    const int PR = p.U * p.V;
+
+    if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(d >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+            const uint32_t sw = smem_u32(smem + OFF_W);
+            int s = 0, as = 0;
+            uint32_t ph = 0, aph = 0;
+            for (long u = blockIdx.x; u < p.units; u += gridDim.x) {
+                mbar_wait(acc_empty + as, aph ^ 1);
+                mbar_wait(full_a + s, ph);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + OFF_A + s * A_BYTES);
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk)
+                    tc_mma_bf16(tmem_base + (uint32_t)(as * 256), umma_desc(sa + kk * 32, 16, 1024), umma_desc(sw + kk * 32, 16, 1024),
+                                idesc, kk > 0 ? 1u : 0u);
+                tc_commit(empty_a + s);
+                tc_commit(acc_full + as);
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+                if ((as ^= 1) == 0) aph ^= 1;
+            }
+        }
+    } else if (warp >= 2 && warp < 6) {
+        // ---- A builders: thread = row of the tile
+        const int i = threadIdx.x - 64;
+        int s = 0;
+        uint32_t ph = 0;
+        for (long u = blockIdx.x; u < p.units; u += gridDim.x) {
+            const int rb = (int)(u % p.rblocks);
+            const int bp = (int)(u / p.rblocks);
+            const int b = bp >> 2, pt = (bp >> 1) & 1, pf = bp & 1;
+            const int r = rb * TM + i;
+            const int uu = r / p.V, v = r - uu * p.V;
+            const int t1 = 2 * uu + pt, f1 = 2 * v + pf;
+            uint4 q[4] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)};
+            if (r < PR && t1 < p.T1 && f1 < p.F1) {
+                const float* xr = p.x + ((long)b * p.T + 2 * t1) * p.F + 2 * f1;
+                float xh[9], xl[9];
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) split(__ldg(xr + kh * p.F + kw), xh[kh * 3 + kw], xl[kh * 3 + kw]);
+                q[0] = make_uint4(bf2(xh[0], xh[1]), bf2(xh[2], xh[3]), bf2(xh[4], xh[5]), bf2(xh[6], xh[7]));
+                q[1] = make_uint4(bf2(xh[8], xl[0]), bf2(xl[1], xl[2]), bf2(xl[3], xl[4]), bf2(xl[5], xl[6]));
+                q[2] = make_uint4(bf2(xl[7], xl[8]), bf2(xh[0], xh[1]), bf2(xh[2], xh[3]), bf2(xh[4], xh[5]));
+                q[3] = make_uint4(bf2(xh[6], xh[7]), bf2(xh[8], 1.f), bf2(1.f, 0.f), 0u);
+            }
+            mbar_wait(empty_a + s, ph ^ 1);
+            uint8_t* row = smem + OFF_A + s * A_BYTES + i * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(row + ((j ^ (i & 7)) << 4)) = q[j];
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_a + s);
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+    } else if (warp >= 6) {
+        // ---- epilogue: warp = (TMEM lane quarter, half of the 32-column chunks)
+        const int q = warp & 3, part = (warp - 6) >> 2;
+        uint8_t* stage = smem + OFF_STAGE + (warp - 6) * 4096;
+        int as = 0, buf = 0;
+        uint32_t aph = 0;
+        for (long u = blockIdx.x; u < p.units; u += gridDim.x) {
+            const int rb = (int)(u % p.rblocks);
+            const int bp = (int)(u / p.rblocks);
+            mbar_wait(acc_full + as, aph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256);
+            for (int cc = part * 32; cc < d; cc += 64) {
+                float v[32];
+                tc_ld32(taddr + (uint32_t)cc, v);
+                uint8_t* sb = stage + buf * 2048;
+                if (lane == 0) bulk_wait_read<1>();  // the box written two stores ago has been read
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint4 o;
+                    o.x = bf2(fmaxf(v[8 * j], 0.f), fmaxf(v[8 * j + 1], 0.f));
+                    o.y = bf2(fmaxf(v[8 * j + 2], 0.f), fmaxf(v[8 * j + 3], 0.f));
+                    o.z = bf2(fmaxf(v[8 * j + 4], 0.f), fmaxf(v[8 * j + 5], 0.f));
+                    o.w = bf2(fmaxf(v[8 * j + 6], 0.f), fmaxf(v[8 * j + 7], 0.f));
+                    *reinterpret_cast<uint4*>(sb + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = o;  // SWIZZLE_64B box
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_4d(&tma_out, sb, cc, rb * TM + q * 32, bp, 0);
+                    bulk_commit();
+                }
+                buf ^= 1;
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + as);
+            if ((as ^= 1) == 0) aph ^= 1;
+        }
+        if (lane == 0) bulk_wait_read<0>();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 encoder() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+    }
+    return fn;
+}
+
+}  // namespace c1f
+
+// returns LASR_ERR_UNSUPPORTED (without setting an error) when the shape is outside the kernel's range: the caller keeps the SIMT path
+int conv1_fwd_tc_dispatch(const float* x, const float* w, const float* bias, void* h1p, int B, int T, int F, int d, cudaStream_t st) {
+    using namespace c1f;
+    if (d != 128 && d != 256) return LASR_ERR_UNSUPPORTED;
+    auto enc = encoder();
+    if (!enc || (reinterpret_cast<uintptr_t>(h1p) & 15)) return LASR_ERR_UNSUPPORTED;
+    Params p;
+    p.x = x; p.w = w; p.bias = bias;
+    p.B = B; p.T = T; p.F = F; p.d = d;
+    p.T1 = (T - 3) / 2 + 1; p.F1 = (F - 3) / 2 + 1; p.U = (p.T1 + 1) / 2; p.V = (p.F1 + 1) / 2;
+    const long PR = (long)p.U * p.V;
+    p.rblocks = (int)((PR + TM - 1) / TM);
+    p.units = (long)B * 4 * p.rblocks;
+    CUtensorMap mo;
+    cuuint64_t dims[4] = {(cuuint64_t)d, (cuuint64_t)PR, (cuuint64_t)B * 4, 1};
+    cuuint64_t strides[3] = {(cuuint64_t)d * 2, (cuuint64_t)PR * d * 2, (cuuint64_t)PR * d * 2};
+    cuuint32_t box[4] = {32, 32, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (enc(&mo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, h1p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return LASR_ERR_UNSUPPORTED;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(conv1_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
+            return check_launch("conv1_fwd_tc smem attr");
+        configured = true;
+    }
+    int sms = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) (void)cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = (int)(p.units < sms ? p.units : sms);
+    launch_pdl(conv1_fwd_tc_kernel, dim3((unsigned)grid), dim3(THREADS), (size_t)SMEM_BYTES, st, mo, p);
+    return check_launch("conv1_fwd_tc");
+}
+
+}  // namespace lasr

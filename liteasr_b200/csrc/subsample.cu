@@ -276,6 +276,7 @@ __global__ void __launch_bounds__(256, 3) conv1_bwd_planes_kernel(const float* _
 int conv2_tc_dispatch(int mode, int plane_class, const void* h1p, const void* w2, const float* bias, const void* dy, void* out,
                       int B, int U, int V, int T2, int d, int split_k, cudaStream_t st);
 int conv1_wgrad_tc_dispatch(const float* x, const void* dh1p, float* dw, float* dbias, int B, int T, int F, int d, cudaStream_t st);
+int conv1_fwd_tc_dispatch(const float* x, const float* w, const float* bias, void* h1p, int B, int T, int F, int d, cudaStream_t st);
 
 }  // namespace lasr
 
@@ -337,6 +338,14 @@ static inline bool planes_ok(int d) { return d % 64 == 0 && d >= 64 && d <= 1024
 
 int lasr_conv1_fwd_planes(const float* x, const float* w, const float* bias, void* h1p, int B, int T, int F, int d, void* stream) {
     LASR_REQUIRE(x && w && bias && h1p && B > 0 && T >= 7 && F >= 7 && planes_ok(d), "conv1_fwd_planes: bad args (d in {64,128,256,512,1024})");
+    {
+        // tensor-core path (csrc/conv1_fwd_tc.cu) for d = 128 / 256; LASR_CONV1_TC=0 keeps the SIMT kernel below
+        const char* e = getenv("LASR_CONV1_TC");
+        if (!(e && atoi(e) == 0)) {
+            const int rc = conv1_fwd_tc_dispatch(x, w, bias, h1p, B, T, F, d, (cudaStream_t)stream);
+            if (rc != LASR_ERR_UNSUPPORTED) return rc;
+        }
+    }
     const int T1 = (T - 3) / 2 + 1, F1 = (F - 3) / 2 + 1, U = (T1 + 1) / 2, V = (F1 + 1) / 2;
     dim3 grid(ceil_div(2 * U, PR_ROWS), B);
     const size_t smem = (9 * (size_t)d + (2 * PR_ROWS + 1) * (size_t)F) * sizeof(float);
