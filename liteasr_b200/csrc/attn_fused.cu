@@ -427,7 +427,7 @@ rel_attn_fwd_kernel(const __grid_constant__ CUtensorMap m_qu, const __grid_const
 #pragma unroll
         for (int ch = 0; ch < PARTW / CH; ++ch) {
             const int j0 = cb + ch * CH;
-            if (j0 < T) {
+            if (j0 < p.ld) {  // every stored column: [T, ld) holds exact zeros (e = 2^-inf)
                 const float* v = sv + ch * CH;
                 uint8_t* rowp = smem + OFF_STG + (j0 >> 6) * (TM * 128) + r * 128;
                 const int ch0 = (j0 & 63) >> 3;

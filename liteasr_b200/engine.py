@@ -198,6 +198,10 @@ class Engine:
         d = H * dk
         ld = _ceil(Tk, 8)
         scale = dk ** -0.5
+        fused = (qv is not None and Tq == Tk and self.adt == torch.bfloat16 and self.fused_attn and ops.rel_attn_fwd_supported(Tk, dk)
+                 and q.stride(0) == qv.stride(0) and k.stride(0) == v.stride(0))
+        if fused and os.environ.get("LASR_ATTN_LD64", "1") != "0":
+            ld = _ceil(Tk, 64)  # 128-byte aligned probability rows: every 128-byte piece the kernel stores is a whole line
         if (qv is not None and Tq == Tk and self.adt == torch.bfloat16 and self.fused_attn and ops.rel_attn_fwd_supported(Tk, dk)
                 and q.stride(0) == qv.stride(0) and k.stride(0) == v.stride(0)):
             # one tcgen05 kernel: both score contractions, rel_shift, scale, mask, softmax and probs.V (csrc/attn_fused.cu)

@@ -240,7 +240,14 @@ def test_trainer_run_with_prefetcher_equals_direct_steps():
         step(*[t.cuda() for t in b])
     torch.cuda.synchronize()
     assert tr.iter == 4 and len(logs) == 2
+    lr = float(step.optimizer.state[2])  # Noam learning rate of the last step (the largest of the four)
     for (n, pa), (_, pb) in zip(model_a.named_parameters(), model_b.named_parameters()):
+        if n.endswith("conv.depthwise_conv.bias") or n.endswith("linear_k.bias"):
+            # true gradient identically zero (a bias in front of BatchNorm; softmax shift invariance): Adam normalises pure
+            # rounding noise -- whose sign depends on the order of the float atomics -- into +-lr steps, so two runs may differ by
+            # up to 2 * lr per step
+            assert (pa - pb).abs().max().item() <= 2.0 * 4 * lr + 1e-7, n
+            continue
         assert torch.allclose(pa, pb, rtol=1e-5, atol=1e-7), n
     pf = Prefetcher(torch.device("cuda:0"))
     with pytest.raises(RuntimeError):
