@@ -7,7 +7,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblasr.so")
+LIB_PATH = os.environ.get("LASR_LIB_PATH") or os.path.join(_HERE, "liblasr.so")  # LASR_LIB_PATH: developer A/B builds
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "lasr.h")
 
 F32, BF16 = 0, 1

@@ -123,8 +123,7 @@ __device__ __forceinline__ float sigmoid_fast(float x) {
     asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
     return fmaf(t, 0.5f, 0.5f);
 }
-// With h = x/2 and t = tanh(h):  swish(x) = x (1 + t)/2 = h + h t  and  swish'(x) = (1 + t + h (1 - t^2))/2 -- three and five
-// instructions (MUFU included) instead of four and six, and a scale factor folds into the last FMA for free
+// With h = x/2 and t = tanh(h):  swish(x) = x (1 + t)/2 = h + h t -- three instructions (MUFU included) instead of four
 __device__ __forceinline__ float swish_fast(float x) {
     const float h = 0.5f * x;
     float t;
@@ -133,12 +132,10 @@ __device__ __forceinline__ float swish_fast(float x) {
 }
 // half_scale * 2 * swish'(x): pass half_scale = alpha / 2
 __device__ __forceinline__ float dswish_scaled(float x, float half_scale) {
-    const float h = 0.5f * x;
-    float t;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
-    const float u = fmaf(-t, t, 1.f);
-    const float w = fmaf(h, u, t);
-    return fmaf(half_scale, w, half_scale);
+    // (the shorter form (1 + t + h (1 - t^2)) * half_scale with t = tanh(x/2), h = x/2 measured 4.7 % SLOWER in the FFN input-gradient
+    //  GEMM: 34.4 vs 32.8 us at 9568 x 2048 x 256)
+    const float r = sigmoid_fast(x);
+    return (2.f * half_scale) * (r * fmaf(x, 1.f - r, 1.f));
 }
 __device__ __forceinline__ float dswish_fast(float x) { return dswish_scaled(x, 0.5f); }
 __device__ __forceinline__ float dact_fast(float saved, int act) {
