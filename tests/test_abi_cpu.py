@@ -30,3 +30,27 @@ def test_ops_reject_cpu_tensors():
     a = torch.zeros(8, 8, dtype=torch.bfloat16)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.gemm(a, a, torch.zeros(8, 8), 8, 8, 8, lda=8, ldb=8, ldc=8)
+
+
+def test_gemm_args_ctypes_layout_matches_the_header():
+    """The ctypes mirror of ``lasr_gemm_args`` must list the same fields, in the same order and with the same C types as
+    include/lasr.h (a drift would silently shift every later argument)."""
+    import re
+    from liteasr_b200 import _lib
+    src = open(_lib.HEADER_PATH).read()
+    body = re.search(r"typedef struct lasr_gemm_args \{(.*?)\} lasr_gemm_args;", src, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    ctype_of = {"const void*": ctypes.c_void_p, "void*": ctypes.c_void_p, "const float*": ctypes.c_void_p, "float*": ctypes.c_void_p,
+                "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "float": ctypes.c_float}
+    header = []
+    for decl in body.split(";"):
+        decl = " ".join(decl.split())
+        if not decl:
+            continue
+        m = re.match(r"((?:const )?\w+\s?\*?)\s*(.+)", decl)
+        ctype, names = m.group(1).replace(" *", "*").strip(), [n.strip() for n in m.group(2).split(",")]
+        header += [(n, ctype_of[ctype]) for n in names]
+    mirror = [(n, t) for n, t in _lib.GemmArgs._fields_]
+    assert [n for n, _ in mirror] == [n for n, _ in header]
+    for (n, t), (_, th) in zip(mirror, header):
+        assert t is th, (n, t, th)
