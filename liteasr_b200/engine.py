@@ -351,8 +351,10 @@ class Engine:
         ops.glu_dwconv_fwd(y2, st.p(pfx + ".depthwise_conv.weight").view(d, KW), st.p(pfx + ".depthwise_conv.bias"), z, partial, B, T, d)
         mean = _empty((d,), torch.float32, self.dev)
         rstd = _empty((d,), torch.float32, self.dev)
+        if bn_mod.momentum is None:  # cumulative moving average: never configured by the reference (conformer_convolution.py:41)
+            raise NotImplementedError("BatchNorm1d(momentum=None) is not implemented (the reference uses the default 0.1)")
         ops.bn_finalize(partial, nblk, d, B * T, mean, rstd, bn_mod.running_mean, bn_mod.running_var, bn_mod.num_batches_tracked,
-                        training, eps=bn_mod.eps, momentum=bn_mod.momentum if bn_mod.momentum is not None else 0.1)
+                        training, eps=bn_mod.eps, momentum=bn_mod.momentum)
         a = _empty((B * T, d), self.adt, self.dev)
         ops.bn_swish_fwd(z, mean, rstd, st.p(pfx + ".norm.weight"), st.p(pfx + ".norm.bias"), a)
         out = self.linear(a, None, torch.float32, w=st.w(pfx + ".pointwise_conv2.weight"), bias_t=st.p(pfx + ".pointwise_conv2.bias"), res=x)
@@ -486,6 +488,7 @@ class Engine:
         pfx = enc._lasr_prefix
         emb = self.embed_fwd(xs, pfx + "embed", d)
         Tp = emb.T2
+        enc.pe.ensure(Tp, self.dev)  # extend_pe (positional_encoding.py:40-53): T' may exceed max_len = 5000
         pos = self.to_adt(enc.pe.pe[0, :Tp])  # absolute positions 0..T'-1 (positional_encoding.py:74); contiguous slice
         x = emb.out
         layers = []
@@ -564,6 +567,7 @@ class Engine:
         V = dec.vocab
         st = self.st
         y = _empty((B * L, d), torch.float32, self.dev)
+        dec.pe.ensure(L, self.dev)
         ops.embed_fwd(ys, st.p(pfx + "embed.weight"), dec.pe.pe[0], y, math.sqrt(d))
         mem = self.to_adt(h_enc.reshape(B * Tp, d))
         layers = []

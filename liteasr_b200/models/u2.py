@@ -62,27 +62,36 @@ class U2Config(LiteasrDataclass):
     precision: str = field(default="bf16")
 
 
-def _arch_value(a):
-    return a.value if isinstance(a, Enum) else str(a)
+def _arch_value(a, enum_cls=None):
+    """Enum member, its value ("conformer") or its name ("Conformer", what a YAML file holds before OmegaConf converts it)."""
+    if isinstance(a, Enum):
+        return a.value
+    s = str(a)
+    if enum_cls is not None:
+        for e in enum_cls:
+            if s == e.value or s == e.name:
+                return e.value
+    return s
 
 
 @register_model("U2", dataclass=U2Config)
 class U2(LiteasrModel):
     def __init__(self, cfg: U2Config, task=None):
         super().__init__()
-        cfg = resolve_interpolations(cfg, "model")
-        assert _arch_value(cfg.enc_arch) in [e.value for e in EncoderArch]
+        import dataclasses
+        cfg = resolve_interpolations(cfg, "model", fields=[f.name for f in dataclasses.fields(U2Config)])
+        assert _arch_value(cfg.enc_arch, EncoderArch) in [e.value for e in EncoderArch]
         self.encoder = TransformerEncoder(
             use_rel=cfg.use_rel, i_dim=cfg.input_dim, h_dim=cfg.enc_dim, ff_dim=cfg.enc_ff_dim, n_head=cfg.enc_attn_heads,
             n_layer=cfg.enc_layers, dropout_rate=cfg.enc_dropout_rate, pos_dropout_rate=cfg.enc_pos_dropout_rate,
             attn_dropout_rate=cfg.enc_attn_dropout_rate, ff_dropout_rate=cfg.enc_ff_dropout_rate, activation=cfg.activation,
-            arch=_arch_value(cfg.enc_arch))
-        assert _arch_value(cfg.dec_arch) in [e.value for e in DecoderArch]
+            arch=_arch_value(cfg.enc_arch, EncoderArch))
+        assert _arch_value(cfg.dec_arch, DecoderArch) in [e.value for e in DecoderArch]
         self.decoder = TransformerDecoder(
             i_dim=cfg.vocab_size, h_dim=cfg.dec_dim, ff_dim=cfg.dec_ff_dim, n_head=cfg.dec_attn_heads, n_layer=cfg.dec_layers,
             dropout_rate=cfg.dec_dropout_rate, pos_dropout_rate=cfg.dec_pos_dropout_rate,
             self_attn_dropout_rate=cfg.dec_self_attn_dropout_rate, src_attn_dropout_rate=cfg.dec_src_attn_dropout_rate,
-            ff_dropout_rate=cfg.dec_ff_dropout_rate, arch=_arch_value(cfg.dec_arch))
+            ff_dropout_rate=cfg.dec_ff_dropout_rate, arch=_arch_value(cfg.dec_arch, DecoderArch))
         self.ctc = CTC(i_dim=cfg.enc_dim, o_dim=cfg.vocab_size, dropout_rate=cfg.dropout_rate)
         if cfg.enc_dim != cfg.dec_dim:
             raise NotImplementedError("enc_dim != dec_dim is not implemented (the reference configs use equal dims)")

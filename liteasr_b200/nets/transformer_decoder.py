@@ -55,3 +55,23 @@ class TransformerDecoder(nn.Module):
             assert sub.shape == (memory.shape[0], memory.shape[1])
             xlens = (~memory_mask).sum(dim=1)
         return self.forward_lens(y, ylens, memory, xlens)
+
+    @torch.no_grad()
+    def forward_one_step(self, y: Tensor, mask: Optional[Tensor], memory: Tensor, memory_mask: Optional[Tensor], cache=None):
+        """transformer_decoder.py:58-68 (used by the reference's unused attention beam search, models/u2.py:161-219):
+        y (B,i) tokens, mask (1|B,i,i) causal -> (log-probs of the LAST position (B,V) fp32, new_cache = per-layer outputs
+        (B,i,d)).  The reference recomputes only the last query per layer and concatenates it behind ``cache``; every layer is
+        causal and position-wise, so re-running the whole prefix through the fused decoder gives the same tensors -- ``cache``
+        is accepted for signature compatibility and ignored (i <= T' tokens: the prefix pass is one small launch sequence)."""
+        from .. import decoding
+        if memory_mask is not None:
+            raise NotImplementedError("forward_one_step: the reference only ever passes memory_mask=None (models/u2.py:188-194)")
+        st, eng, _ = F.bind(self, memory.device)
+        st.refresh_operands()
+        b, i = y.shape
+        ylens = torch.full((b,), i - 1, dtype=torch.int64, device=y.device)  # every key j <= position is valid (causal mask only)
+        c = eng.decoder_fwd(self, y.contiguous(), ylens, memory.contiguous().float(), None)
+        logits = c.out.view(b, i, -1)[:, -1] if c.out.is_contiguous() else c.out.unflatten(0, (b, i))[:, -1]
+        logp = decoding.log_softmax(logits.contiguous())
+        new_cache = [layer[2].out.view(b, i, self.h_dim) for layer in c.layers]
+        return logp, new_cache

@@ -35,18 +35,30 @@ class AdamConfig(LiteasrDataclass):
     beta2: float = field(default=0.999)
     eps: float = field(default=1e-8)
     weight_decay: float = field(default=0.0)
+    amsgrad: bool = field(default=False)
 
 
 @dataclass
-class NoamConfig(LiteasrDataclass):
+class NoamConfig(AdamConfig):
+    """optims/noam.py:10-17: an AdamConfig with beta2 = 0.98, eps = 1e-9 and the schedule fields."""
     name: Optional[str] = field(default="noam")
-    factor: float = field(default=1.0)
+    beta2: float = field(default=0.98)
+    eps: float = field(default=1e-9)
     model_dim: int = field(default=256)
+    factor: float = field(default=1.0)
     warmup: int = field(default=25000)
-    weight_decay: float = field(default=0.0)
+
+
+def _reject_amsgrad(cfg) -> None:
+    if getattr(cfg, "amsgrad", False):
+        raise NotImplementedError("amsgrad=True is not implemented by the fused optimizer step (the reference default is False)")
 
 
 class _FusedFlatOptimizer:
+    """Difference from the reference, on purpose: ``trainer.py:157`` skips the update only when the gradient norm is NaN; an
+    *infinite* norm there makes ``clip_grad_norm_`` scale by 0 and step on NaN/0 gradients.  The fused step skips on any
+    non-finite norm (NaN or inf)."""
+
     def __init__(self, store: ParamStore, *, beta1, beta2, eps, weight_decay, lr=0.0, noam_factor=0.0, model_dim=256.0,
                  warmup=25000.0):
         self.store = store
@@ -81,14 +93,19 @@ class _FusedFlatOptimizer:
 class FusedAdam(_FusedFlatOptimizer):
     def __init__(self, store: ParamStore, cfg: AdamConfig = None):
         cfg = cfg or AdamConfig()
+        _reject_amsgrad(cfg)
         super().__init__(store, beta1=cfg.beta1, beta2=cfg.beta2, eps=cfg.eps, weight_decay=cfg.weight_decay, lr=cfg.lr)
 
 
 @register_optimzer("noam", dataclass=NoamConfig)
 class FusedNoam(_FusedFlatOptimizer):
-    """Adam(betas=(0.9, 0.98), eps=1e-9) with lr = factor * d^-0.5 * min(step^-0.5, step * warmup^-1.5) (optims/noam.py:17-46)."""
+    """Adam (NoamConfig defaults: betas (0.9, 0.98), eps 1e-9) with lr = factor * d^-0.5 * min(step^-0.5, step * warmup^-1.5)
+    (optims/noam.py:10-46; the ``lr`` field is overwritten by the schedule before every step, as there)."""
 
     def __init__(self, store: ParamStore, cfg: NoamConfig = None):
         cfg = cfg or NoamConfig()
-        super().__init__(store, beta1=0.9, beta2=0.98, eps=1e-9, weight_decay=cfg.weight_decay, noam_factor=cfg.factor,
+        _reject_amsgrad(cfg)
+        if not cfg.factor > 0:
+            raise ValueError("noam: factor must be > 0")
+        super().__init__(store, beta1=cfg.beta1, beta2=cfg.beta2, eps=cfg.eps, weight_decay=cfg.weight_decay, noam_factor=cfg.factor,
                          model_dim=cfg.model_dim, warmup=cfg.warmup)

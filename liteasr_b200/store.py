@@ -22,10 +22,13 @@ from . import ops
 ALIGN = 64  # elements: every parameter starts on a 256-byte (fp32) / 128-byte (bf16) boundary
 
 
-def _ordered_named_parameters(root: nn.Module) -> List[Tuple[str, nn.Parameter]]:
+def _ordered_named_parameters(root: nn.Module) -> Tuple[List[Tuple[str, nn.Parameter]], set]:
+    """Parameters in layout order + the names that are packed TIGHTLY against their successor (no alignment padding): the
+    q/k/v weights of an attention module form one (3d, d) matrix and their biases one (3d,) vector, for any d (the fused
+    projections read them as single spans, engine.py::rel_mha_fwd / self_mha_fwd / src_mha_fwd)."""
     named = list(root.named_parameters())
     by_name = dict(named)
-    out, done = [], set()
+    out, done, tight = [], set(), set()
     pat = re.compile(r"^(.*)\.linear_q\.weight$")
     for name, p in named:
         if name in done:
@@ -34,13 +37,17 @@ def _ordered_named_parameters(root: nn.Module) -> List[Tuple[str, nn.Parameter]]
         if m:
             pre = m.group(1)
             group = [f"{pre}.linear_{x}.weight" for x in "qkv"] + [f"{pre}.linear_{x}.bias" for x in "qkv"]
+            d = by_name[group[0]].shape[0]
+            if d % 4 != 0:  # 16-byte alignment of the k / v sub-matrices (bf16 operands) and of the k / v bias vectors (fp32)
+                raise NotImplementedError(f"{pre}: attention width {d} must be a multiple of 4 for the fused q/k/v projection")
             for g in group:
                 out.append((g, by_name[g]))
                 done.add(g)
+            tight.update(group[0:2] + group[3:5])
             continue
         out.append((name, p))
         done.add(name)
-    return out
+    return out, tight
 
 
 class ParamStore:
@@ -50,12 +57,15 @@ class ParamStore:
         self.device = device
         self.precision = precision
         self.adt = torch.bfloat16 if precision == "bf16" else torch.float32
-        self.named = _ordered_named_parameters(root)
+        self.named, self.tight = _ordered_named_parameters(root)
         self.off: Dict[str, Tuple[int, torch.Size]] = {}
+        self.span: Dict[str, int] = {}  # elements a parameter occupies including its padding
         n = 0
         for name, p in self.named:
             self.off[name] = (n, p.shape)
-            n += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
+            self.span[name] = p.numel() if name in self.tight else (n + p.numel() + ALIGN - 1) // ALIGN * ALIGN - n
+            n += self.span[name]
+        n = (n + ALIGN - 1) // ALIGN * ALIGN
         self.numel = n
         self.flat = torch.zeros(n, dtype=torch.float32, device=device)
         self.gflat = torch.zeros(n, dtype=torch.float32, device=device)
@@ -66,6 +76,12 @@ class ParamStore:
                 view = self.flat[o:o + p.numel()].view(shp)
                 view.copy_(p.data.to(device=device, dtype=torch.float32))
                 p.data = view
+            # buffers (BatchNorm running statistics, the sinusoid tables) are read by the kernels through raw pointers: they must
+            # live on the store's device as well (module.to(device) normally did that already)
+            for mod in root.modules():
+                for bname, buf in list(mod._buffers.items()):
+                    if buf is not None and buf.device != device:
+                        mod._buffers[bname] = buf.to(device)
         self.direct_grads = False
         self._cast_version = None
         self.derived: Dict[str, torch.Tensor] = {}
@@ -114,7 +130,7 @@ class ParamStore:
         return self.gflat[o:o + rows * cols].view(rows, cols)
 
     def range_of(self, prefix: str) -> Tuple[int, int]:
-        offs = [(o, o + (s.numel() + ALIGN - 1) // ALIGN * ALIGN) for n, (o, s) in self.off.items() if n.startswith(prefix)]
+        offs = [(o, o + self.span[n]) for n, (o, s) in self.off.items() if n.startswith(prefix)]
         return min(a for a, _ in offs), max(b for _, b in offs)
 
     # ------------------------------------------------------------------ per-step maintenance

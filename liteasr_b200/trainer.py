@@ -173,15 +173,17 @@ class Trainer:
     tensors, the collator contract of dataset/asr_dataset.py:115-126).  Data loading itself is out of scope (SURVEY 2 #12)."""
 
     def __init__(self, model, criterion, optimizer=None, *, clip_grad_norm=5.0, accum_grad=1, report_interval=100,
-                 use_graph=True, device=None, log: Callable[[str], None] = print):
+                 use_graph=True, device=None, log: Callable[[str], None] = print, max_iter: int = 0, max_epoch: int = 0):
         self.step_fn = TrainStep(model, criterion, optimizer, clip_grad_norm=clip_grad_norm, accum_grad=accum_grad,
                                  use_graph=use_graph, device=device)
         self.model, self.criterion = model, criterion
         self.device = self.step_fn.device
         self.report = Trigger(report_interval)
         self.iter = 0
+        self.epoch = 0
+        self.max_iter, self.max_epoch = max_iter, max_epoch
         self.log = log
-        self.loss_acc = torch.zeros((), device=self.device)
+        self.loss = torch.zeros((), device=self.device)  # loss of the CURRENT step (trainer.py:148-149,171: reset after every step)
 
     def run(self, batches: Iterable, max_iters: Optional[int] = None) -> None:
         self.model.train()
@@ -199,35 +201,47 @@ class Trainer:
             batch = pf.get()
             more = stage()  # trainer.py:140 moved one step ahead: this copy overlaps the step below
             loss = self.step_fn(*batch)
-            self.loss_acc += loss / self.step_fn.accum
+            self.loss = loss / self.step_fn.accum
             self.iter += 1
             if self.report(self.iter):
                 self.report_loss()
             if max_iters is not None and self.iter >= max_iters:
                 break
 
+    def _progress(self) -> str:
+        return "{} / {} iters, {} / {} epochs".format(self.iter, self.max_iter, self.epoch, self.max_epoch)
+
     def report_loss(self) -> None:
-        loss = self.loss_acc.clone()
+        """trainer.py:174-186: the loss of the current step, reduced to rank 0 and divided by the world size; same log line."""
+        loss = self.loss.clone()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.reduce(loss, dst=0)  # trainer.py:176
+            dist.reduce(loss, dst=0)
             loss /= dist.get_world_size()
         opt = self.step_fn.optimizer
         if not dist.is_initialized() or dist.get_rank() == 0:
-            self.log(f"iter {self.iter} loss {float(loss) / self.report.interval:.4f} lr {opt.rate():.3e} "
-                     f"grad_norm {opt.last_grad_norm():.3f} updates {opt.num_updates()}")
-        self.loss_acc.zero_()
+            self.log("{} - current loss: {:.2f}".format(self._progress(), loss.item()))
+            self.log(f"    lr {opt.rate():.3e} grad_norm {opt.last_grad_norm():.3f} updates {opt.num_updates()}")
 
     @torch.no_grad()
     def valid(self, batches: Iterable) -> float:
-        """trainer.py:188-209: criterion under eval() + no_grad (BatchNorm running statistics)."""
+        """trainer.py:188-209: criterion under eval() + no_grad (BatchNorm running statistics), every batch loss reduced to rank 0
+        and divided by the world size, mean over batches, and the ``... - valid loss: {:.2f}`` line that
+        ``utils/checkpoint.load_ckpt(avg_policy=<log>)`` parses (utils/checkpoint.py:55-60)."""
         self.model.eval()
-        tot, n = 0.0, 0
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        losses = []
         for batch in batches:
             batch = tuple(t.to(self.device) for t in batch)
-            tot += float(self.criterion(self.model, *batch))
-            n += 1
+            loss = self.criterion(self.model, *batch).detach().clone()
+            if world > 1:
+                dist.reduce(loss, dst=0)
+                loss /= world
+            losses.append(loss)
+        reduced = float(torch.stack(losses).mean()) if losses else 0.0
+        if not dist.is_initialized() or dist.get_rank() == 0:
+            self.log("{} - valid loss: {:.2f}".format(self._progress(), reduced))
         self.model.train()
-        return tot / max(n, 1)
+        return reduced
 
     def save_model(self, path: str) -> None:
         if not dist.is_initialized() or dist.get_rank() == 0:

@@ -152,3 +152,59 @@ def test_ctc_poisoned_workspace_is_harmless():
         nll1, g1 = ops.ctc_fwdbwd(x, *args, time_major=True, workspace=ws1)
         assert torch.isfinite(g1).all() and torch.isfinite(nll1).all()
         assert torch.equal(g0, g1) and torch.equal(nll0, nll1)
+
+
+# BASELINE config 4, the whole grid (B = 64): the reference's own call (criterions/hybrid_ctc_attn.py:67-75: log_softmax +
+# nn.CTCLoss(sum)) evaluated in float64 on the GPU is the yardstick; torch's fp32 evaluation of the same call is the
+# "reference fp32 path" whose own deviation from float64 is recorded next to ours.
+C4_GRID = [(T, L, V) for (T, L) in ((200, 20), (400, 50), (800, 100), (1600, 200)) for V in (500, 1000, 2000, 5000)]
+
+
+def c4_case(T, L, V, B=64, device="cuda"):
+    g = torch.Generator(device=device).manual_seed(1000 * T + V)
+    x = torch.randn(T, B, V, generator=g, device=device)
+    il = torch.randint(int(0.6 * T), T + 1, (B,), generator=g, device=device)
+    il[0] = T
+    tl = torch.randint(L // 2, L + 1, (B,), generator=g, device=device)
+    tl[0] = L
+    tg = torch.randint(1, V, (B, L), generator=g, device=device)
+    tg[1, 1] = tg[1, 0]          # a repeated label at the start ...
+    tg[2, 2:6] = tg[2, 1]        # ... and a run of five equal labels
+    tg[3, L - 1] = tg[3, L - 2]
+    return x, tg, il, tl
+
+
+def c4_tolerance(T):
+    """Gradient tolerance of the fp32 log-space lattice against float64, absolute on |grad| <= 1.
+    SURVEY 8d asks 1e-4 * max|g| 'vs the reference fp32 path'; that path (torch fp32 CTC) itself deviates from float64 by
+    1e-3 (T = 200) ... 2.4e-2 (T = 1600), so the bound that can be checked against an exact answer is T-dependent: every one
+    of the T sequential log-sum-exps rounds alpha~ / beta~ at ulp(|alpha~|) with |alpha~| <~ 2^10 in log2 units (2^-13 absolute
+    = 1.2e-4 relative on the occupancy), the errors of a sweep add like a random walk with drift, and measured growth on this
+    grid is 4e-7 * T ... 1.5e-6 * T.  Stated bound: max(1e-4, 2e-6 * T) -- 4e-4 at T = 200, 3.2e-3 at T = 1600 -- and, checked in
+    the same test, never worse than HALF of torch's own fp32 error at the same point."""
+    return max(1e-4, 2e-6 * T)
+
+
+@pytest.mark.parametrize("T,L,V", C4_GRID)
+def test_ctc_c4_grid_vs_torch_float64(T, L, V):
+    from liteasr_b200 import ops
+    B = 64
+    x, tg, il, tl = c4_case(T, L, V, B)
+    n = ops.ctc_workspace_bytes(T, B, L)
+    ws = torch.full((n,), 0xFF, dtype=torch.uint8, device="cuda")  # NaN bit patterns: nothing unwritten may be read
+    nll, grad = ops.ctc_fwdbwd(x, tg, il, tl, time_major=True, workspace=ws)
+    assert torch.isfinite(nll).all() and torch.isfinite(grad).all()
+    x64 = x.double().requires_grad_(True)
+    l64 = torch.nn.functional.ctc_loss(x64.log_softmax(-1), tg, il, tl, blank=0, reduction="none", zero_infinity=False)
+    l64.sum().backward()
+    gerr = (grad.double() - x64.grad).abs().max().item()
+    nerr = ((nll.double() - l64).abs() / l64.abs()).max().item()
+    x32 = x.clone().requires_grad_(True)
+    torch.nn.functional.ctc_loss(x32.log_softmax(-1), tg, il, tl, blank=0, reduction="sum", zero_infinity=False).backward()
+    terr = (x32.grad.double() - x64.grad).abs().max().item()
+    print(f"c4 T={T} L={L} V={V}: nll rel err {nerr:.2e}, grad abs err {gerr:.2e} (tolerance {c4_tolerance(T):.1e}; torch fp32: {terr:.2e})")
+    assert nerr <= 1e-6            # SURVEY 8d: CTC fp32 loss vs the float64 restatement, rel 1e-6
+    assert gerr <= c4_tolerance(T)
+    assert gerr <= 0.5 * terr
+    live = torch.arange(T, device="cuda").view(-1, 1) < il.view(1, -1)
+    assert (grad[~live] == 0).all()

@@ -62,10 +62,38 @@ def test_flat_order_groups_qkv():
     from liteasr_b200.store import _ordered_named_parameters
     m = U2(U2Config(input_dim=80, vocab_size=50, enc_layers=1, dec_layers=1, enc_dim=64, dec_dim=64, enc_attn_heads=1,
                     dec_attn_heads=1, enc_ff_dim=96, dec_ff_dim=96))
-    names = [n for n, _ in _ordered_named_parameters(m)]
+    named, tight = _ordered_named_parameters(m)
+    names = [n for n, _ in named]
     assert sorted(names) == sorted(n for n, _ in m.named_parameters())
     i = names.index("encoder.enc_layers.0.self_attn.linear_q.weight")
     assert names[i:i + 6] == [f"encoder.enc_layers.0.self_attn.linear_{x}.{k}" for k in ("weight", "bias") for x in "qkv"]
+    assert {names[i], names[i + 1], names[i + 3], names[i + 4]} <= tight and names[i + 2] not in tight
+
+
+def test_qkv_spans_are_contiguous_for_widths_that_are_not_multiples_of_64():
+    """the fused q/k/v projection reads the three biases / weights as ONE span; with a 64-element padding
+    after every parameter that only held for d % 64 == 0.  The group is now packed tightly for any d % 4 == 0."""
+    from liteasr_b200.models.u2 import U2, U2Config
+    from liteasr_b200.store import ParamStore
+    m = U2(U2Config(input_dim=80, vocab_size=50, enc_layers=1, dec_layers=1, enc_dim=144, dec_dim=144, enc_attn_heads=4,
+                    dec_attn_heads=4, enc_ff_dim=96, dec_ff_dim=96))
+    want = {n: p.detach().clone() for n, p in m.named_parameters()}
+    st = ParamStore(m, torch.device("cpu"), "fp32")
+    d = 144
+    for pre in ("encoder.enc_layers.0.self_attn", "decoder.dec_layers.0.self_attn"):
+        w = st.w(pre + ".linear_q.weight", 3 * d, d)
+        b = st.p_span(pre + ".linear_q.bias", 3 * d)
+        for j, x in enumerate("qkv"):
+            assert torch.equal(w[j * d:(j + 1) * d], want[f"{pre}.linear_{x}.weight"])
+            assert torch.equal(b[j * d:(j + 1) * d], want[f"{pre}.linear_{x}.bias"])
+            assert st.off[f"{pre}.linear_{x}.weight"][0] % 4 == 0 and st.off[f"{pre}.linear_{x}.bias"][0] % 4 == 0
+    pre = "decoder.dec_layers.0.src_attn"
+    kv = st.p_span(pre + ".linear_k.bias", 2 * d)
+    assert torch.equal(kv[:d], want[pre + ".linear_k.bias"]) and torch.equal(kv[d:], want[pre + ".linear_v.bias"])
+    lo, hi = st.range_of("decoder.")
+    assert lo % 64 == 0 and hi % 64 == 0 and hi <= st.numel
+    for n, p in m.named_parameters():  # parameters are views of the flat buffer and keep their values
+        assert torch.equal(p, want[n]) and p.data_ptr() == st.flat.data_ptr() + 4 * st.off[n][0]
 
 
 def test_masks_and_synthetic_batch_contract():
