@@ -256,7 +256,10 @@ def run_gpu(args, wl):
     pk = peaks()
     dims = U2Dims(*wl["dims"])
     torch.manual_seed(42)
-    model = U2(U2Config(**dims.__dict__, precision=args.precision)).to(dev).train()
+    rates = {}
+    if args.dropout > 0:  # config/model/my_U2.yaml: one rate everywhere, the three attention-probability rates 0.0
+        rates = dict(dropout_rate=args.dropout, enc_attn_dropout_rate=0.0, dec_self_attn_dropout_rate=0.0, dec_src_attn_dropout_rate=0.0)
+    model = U2(U2Config(**dims.__dict__, precision=args.precision, **rates)).to(dev).train()
     crit = HybridCTCLoss(HybridCTCLossConfig(vocab_size=dims.vocab_size, smoothing=wl["smoothing"], ctc_weight=wl["ctc_weight"]))
     step = TrainStep(model, crit, None, clip_grad_norm=5.0, use_graph=not args.no_graph, device=dev)
     step.optimizer = FusedNoam(step.store, NoamConfig(model_dim=dims.enc_dim))
@@ -387,9 +390,12 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override (0 = the workload's default)")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--dropout", type=float, default=0.0, help="model.dropout_rate (the reference's my_U2.yaml trains with 0.1; attention rates stay 0.0)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
+    if args.dropout > 0:
+        wl["desc"] = wl["desc"].replace("dropout 0 (U2Config default)", f"dropout {args.dropout} (my_U2.yaml rates, own Philox stream)")
     if args.batch > 0:
         wl["desc"] = wl["desc"].replace(f"per-GPU batch {wl['batch']}", f"per-GPU batch {args.batch}").replace(f"batch {wl['batch']},", f"batch {args.batch},")
         wl["batch"] = args.batch

@@ -102,6 +102,20 @@ typedef struct lasr_gemm_args {
     const float* bias2;
     int64_t lda2, ldb2;
     int32_t k2;
+    /* dropout on the output (optional; the reference's nn.Dropout sites that sit right behind a Linear: nets/feed_forward.py:19,
+     * nets/conformer_layer.py:42,54,63,125, nets/transformer_layer.py:48,58,174, nets/positional_encoding.py:75, and -- as the
+     * backward of nets/ctc.py:29 -- the input gradient of ctc_lo):
+     *   C = keep(m,n) * drop_scale * alpha * act(A.B^T + bias)  (+ res: the residual is added AFTER the mask)
+     * keep(m,n) comes from Philox4x32-10 keyed by drop_state = device {seed, step} (two uint64), drop_site and the element's
+     * (row, column) -- see the "dropout" section below; drop_thr = round(p * 65536) (0 = off), drop_scale = 65536 / (65536 - thr).
+     * drop_mark_aux = 1: dropped elements of `aux` (the saved pre-activation) receive -1e30, whose act'() is exactly 0, so the
+     * activation-backward GEMM (dact = aux) applies the SAME mask without regenerating it (its alpha carries drop_scale).
+     * Unbatched GEMMs only; not with accumulate / dact / n_store / recompute. */
+    const void* drop_state;
+    uint32_t drop_site;
+    uint32_t drop_thr;
+    float drop_scale;
+    int32_t drop_mark_aux;
 } lasr_gemm_args;
 
 int lasr_gemm(const lasr_gemm_args* args, void* stream);
@@ -138,6 +152,33 @@ int lasr_layernorm_bwd(const void* dy, int dy_dtype, int64_t lddy, const float* 
                        const float* rstd, const float* gamma, float* dx, int64_t lddx, int accumulate, float* dgamma,
                        float* dbeta, int rows, int d, void* dx_lo, int64_t lddxlo, float* colsum, float colsum_scale,
                        void* stream);
+/* The same with (a) dx_lo of either dtype (lo_dtype = LASR_BF16 | LASR_F32) and (b) dropout applied to the two fused outputs:
+ * the block that consumes dx_lo / colsum sits behind nn.Dropout on its output in the forward pass (x + drop(f(LN x)),
+ * nets/conformer_layer.py:37-66, nets/transformer_layer.py:29-61,161-177), so what it must receive is keep * scale * dx with
+ * the mask of THAT site, regenerated here; dx itself stays unmasked.  drop_thr = 0: identical to lasr_layernorm_bwd. */
+int lasr_layernorm_bwd_drop(const void* dy, int dy_dtype, int64_t lddy, const float* x, int64_t ldx, const float* mean,
+                            const float* rstd, const float* gamma, float* dx, int64_t lddx, int accumulate, float* dgamma,
+                            float* dbeta, int rows, int d, void* dx_lo, int lo_dtype, int64_t lddxlo, float* colsum,
+                            float colsum_scale, const void* drop_state, uint32_t drop_site, uint32_t drop_thr, float drop_scale,
+                            void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Dropout (the reference's nn.Dropout / F.dropout sites: nets/positional_encoding.py:55,75, nets/attention.py:55,
+ * nets/feed_forward.py:19, nets/conformer_layer.py:42,54,63,125, nets/transformer_layer.py:48,58,174, nets/ctc.py:29).
+ * torch's generator stream cannot be replayed by fused kernels, so the masks come from the library's own counter-based
+ * stream (Philox4x32-10): for a logical row-major (rows, n) tensor
+ *     keep(r, c)  <=>  16-bit lane (c & 7) of philox4x32_10(counter = (c >> 3, r, site, step), key = seed)  >=  thr
+ * with thr = round(p * 65536) and kept values multiplied by scale = 65536 / (65536 - thr).  `state` is a device array
+ * {uint64 seed, uint64 step}; lasr_rng_advance (one tiny kernel, CUDA-graph capturable) increments step, so every optimizer
+ * step -- every replay of a captured step -- draws fresh masks.  Masks are never stored: lasr_gemm / lasr_layernorm_bwd_drop
+ * evaluate them in their epilogues, the backward pass regenerates them from the same (step, site, row, column).
+ *   lasr_dropout: y[r,c] = keep * scale * x[r,c] as a stand-alone pass (x fp32|bf16 -> y fp32|bf16; in place allowed when the
+ *   dtypes agree) for the sites that sit behind no GEMM: pos_emb, the CTC head's input (fused with the operand cast), the
+ *   decoder's embedded input and its gradient, attention probabilities when an attention dropout rate is non-zero.
+ * ------------------------------------------------------------------------------------------------ */
+int lasr_rng_advance(void* state, void* stream);
+int lasr_dropout(const void* x, int x_dtype, int64_t ldx, void* y, int y_dtype, int64_t ldy, int64_t rows, int cols,
+                 const void* state, uint32_t site, uint32_t thr, float scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Casts / relayouts (weights fp32 master -> bf16 operand copies; conv weight permutations and the

@@ -4,6 +4,7 @@
 // Not a roofline kernel: it exists so fp32 runs (loss/grad parity, bit-exact greedy CTC) see fp32 operands and
 // fp32 results like the reference's torch fp32 path (dot products are accumulated in fp64 and rounded once).
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace lasr {
 
@@ -28,6 +29,8 @@ struct SimtParams {
     float* colsum;
     long cs1, cs2;
     int n_store;
+    DropCfg drop;
+    int drop_mark;
 };
 
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams p) {
@@ -83,10 +86,15 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams p) {
     }
     const long boff = (long)b1 * p.sc1 + (long)b2 * p.sc2;
     float cs[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool drop_on = p.drop.thr != 0;
+    DropKey dk = {};
+    if (drop_on) dk = drop_key(p.drop);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int m = m0 + ty * 4 + i;
         if (m >= p.m) continue;
+        // the thread's 4 columns n0 + 4 tx .. + 3 share one Philox call (same 8-column group)
+        const uint32_t keep4 = drop_on ? drop_keep4(dk, (uint32_t)m, (uint32_t)(n0 + tx * 4)) : 15u;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int n = n0 + tx * 4 + j;
@@ -97,13 +105,15 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams p) {
                 continue;
             }
             float v = (float)acc[i][j];
+            const bool keep = (keep4 >> j) & 1u;
             if (p.dact) {
                 const float sv = p.dact[boff + (long)m * p.lddact + n];
                 v *= p.alpha * (p.act == LASR_ACT_SWISH ? dswishf_(sv) : (sv > 0.f ? 1.f : 0.f));
             } else {
                 if (p.bias) v += p.bias[n];
-                if (p.aux) p.aux[off] = v;
+                if (p.aux) p.aux[off] = (keep || !p.drop_mark) ? v : LASR_DROP_MARK;
                 v = p.alpha * apply_act(v, p.act);
+                if (drop_on) v = keep ? v * dk.scale : 0.f;
                 if (p.res) v += p.res[boff + (long)m * p.ldres + n];
             }
             p.c[off] = v;
@@ -131,6 +141,8 @@ int gemm_simt_dispatch(const lasr_gemm_args* a, cudaStream_t st) {
     p.alpha = a->alpha; p.act = a->act; p.accumulate = a->accumulate; p.split_k = a->split_k < 1 ? 1 : a->split_k;
     p.n_store = a->n_store ? a->n_store : a->n;
     p.dact = (const float*)a->dact; p.lddact = a->lddact; p.colsum = a->colsum; p.cs1 = a->cs1; p.cs2 = a->cs2;
+    p.drop.state = (const unsigned long long*)a->drop_state; p.drop.site = a->drop_site; p.drop.thr = a->drop_thr; p.drop.scale = a->drop_scale;
+    p.drop_mark = a->drop_mark_aux;
     dim3 grid(ceil_div(a->m, SBM), ceil_div(p.n_store, SBN), a->batch1 * a->batch2 * p.split_k);
     gemm_simt_kernel<<<grid, 256, 0, st>>>(p);
     return check_launch("gemm_simt");

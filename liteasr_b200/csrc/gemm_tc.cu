@@ -24,6 +24,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "philox.cuh"
 #include "tc_ptx.cuh"
 
 namespace lasr {
@@ -85,6 +86,8 @@ struct TcParams {
     int conv_off[9];   // flattened (u,v) row shift of the tap: (kh >> 1) * V + (kw >> 1)
     int conv_plane[9]; // parity plane of the tap: (kh & 1) * 2 + (kw & 1)
     int conv_tap[9];   // tap id kh * 3 + kw (column block of the (co, tap, ci) weight)
+    DropCfg drop;      // dropout on the output (philox.cuh); thr = 0: off
+    int drop_mark;     // dropped elements of aux receive LASR_DROP_MARK
 };
 
 
@@ -172,7 +175,7 @@ enum { EPI_PLAIN = 0, EPI_RELU = 1, EPI_SWISH = 2, EPI_RES = 3, EPI_ACC = 4, EPI
 // reads are bank-conflict free: piece j of row r lives at r*128 + ((j ^ (r & 7)) << 4) for CW = 32 and at
 // r*64 + ((j ^ ((r >> 1) & 3)) << 4) for CW = 16.  In the column phase PIECES lanes own one row segment and a warp covers
 // RGRP = 32 / PIECES rows per instruction.
-template <typename CT, int MODE, int CW>
+template <typename CT, int MODE, int CW, bool DROP>
 __device__ __forceinline__ void epilogue_unit(const TcParams& p, const Unit& w, uint32_t tmem_acc, uint8_t* stage, int q, int part,
                                               int lane) {
     constexpr int PIECES = CW / 4, RGRP = 32 / PIECES, ITERS = 32 / RGRP, ROWB = CW * 4;
@@ -194,6 +197,9 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, const Unit& w, 
     // CW = 32: rows 4i + rsub alternate between two swizzle phases (i even / odd); CW = 16: rows 8i + rsub share one
     const uint8_t* rd0 = (CW == 32) ? stage + rsub * 128 + ((chunk ^ rsub) << 4) : stage + rsub * 64 + ((chunk ^ ((rsub >> 1) & 3)) << 4);
     const uint8_t* rd1 = (CW == 32) ? stage + rsub * 128 + (((chunk ^ rsub) ^ 4) << 4) : rd0;
+    const bool drop_on = DROP && p.drop.thr != 0;  // warp-uniform; DROP = false kernels carry none of the dropout code
+    DropKey dk = {};
+    if (drop_on) dk = drop_key(p.drop);
     for (int cc = part * CW; cc < p.bn; cc += CW * (EPI_WARPS / 4)) {
         const int col = w.n0 + cc + chunk * 4;  // this lane's 4 columns in the column phase
         if (w.n0 + cc >= col_limit) break;      // warp-uniform
@@ -267,8 +273,17 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, const Unit& w, 
                 float4 f = *reinterpret_cast<const float4*>(((i & 1) ? rd1 : rd0) + i * (RGRP * ROWB));
                 if (RGRP * i < nrows && lane_ok) {
                     CT* crow = cbase + off;
+                    // dropout (PLAIN / RES / RELU / SWISH): one Philox call per (row, 4 columns); kx..kw = scale or 0
+                    float kx = 1.f, ky = 1.f, kz = 1.f, kw = 1.f;
+                    uint32_t keep4 = 15u;
+                    if (drop_on) {
+                        keep4 = drop_keep4(dk, (uint32_t)(row_base + rsub + RGRP * i), (uint32_t)col);
+                        kx = (keep4 & 1u) ? dk.scale : 0.f; ky = (keep4 & 2u) ? dk.scale : 0.f;
+                        kz = (keep4 & 4u) ? dk.scale : 0.f; kw = (keep4 & 8u) ? dk.scale : 0.f;
+                    }
                     if constexpr (MODE == EPI_PLAIN) {
                         f.x = fmaf(f.x, alpha, ba.x); f.y = fmaf(f.y, alpha, ba.y); f.z = fmaf(f.z, alpha, ba.z); f.w = fmaf(f.w, alpha, ba.w);
+                        if (drop_on) { f.x *= kx; f.y *= ky; f.z *= kz; f.w *= kw; }
                         store4<CT>(crow, f);
                         cs.x += f.x; cs.y += f.y; cs.z += f.z; cs.w += f.w;
                     } else if constexpr (DACT) {
@@ -287,21 +302,34 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, const Unit& w, 
                         store4<CT>(crow, f);  // finished in the row phase
                         cs.x += f.x; cs.y += f.y; cs.z += f.z; cs.w += f.w;
                     } else if constexpr (MODE == EPI_RES) {
-                        f.x = fmaf(f.x, alpha, ba.x) + r4[i].x; f.y = fmaf(f.y, alpha, ba.y) + r4[i].y;
-                        f.z = fmaf(f.z, alpha, ba.z) + r4[i].z; f.w = fmaf(f.w, alpha, ba.w) + r4[i].w;
+                        if (drop_on) {  // res + keep * scale * (alpha * acc + alpha * bias)
+                            f.x = fmaf(fmaf(f.x, alpha, ba.x), kx, r4[i].x); f.y = fmaf(fmaf(f.y, alpha, ba.y), ky, r4[i].y);
+                            f.z = fmaf(fmaf(f.z, alpha, ba.z), kz, r4[i].z); f.w = fmaf(fmaf(f.w, alpha, ba.w), kw, r4[i].w);
+                        } else {
+                            f.x = fmaf(f.x, alpha, ba.x) + r4[i].x; f.y = fmaf(f.y, alpha, ba.y) + r4[i].y;
+                            f.z = fmaf(f.z, alpha, ba.z) + r4[i].z; f.w = fmaf(f.w, alpha, ba.w) + r4[i].w;
+                        }
                         store4<CT>(crow, f);
                     } else if constexpr (MODE == EPI_ACC) {
                         f.x *= alpha; f.y *= alpha; f.z *= alpha; f.w *= alpha;
                         red_add_f32x4(reinterpret_cast<float*>(crow), f);
                     } else {  // EPI_RELU / EPI_SWISH (+ optional pre-activation copy)
                         f.x += b4.x; f.y += b4.y; f.z += b4.z; f.w += b4.w;
-                        if (has_aux) store4<CT>(abase + off, f);
+                        if (has_aux) {
+                            float4 h = f;
+                            if (drop_on && p.drop_mark) {
+                                h.x = (keep4 & 1u) ? h.x : LASR_DROP_MARK; h.y = (keep4 & 2u) ? h.y : LASR_DROP_MARK;
+                                h.z = (keep4 & 4u) ? h.z : LASR_DROP_MARK; h.w = (keep4 & 8u) ? h.w : LASR_DROP_MARK;
+                            }
+                            store4<CT>(abase + off, h);
+                        }
                         if constexpr (MODE == EPI_RELU) {
                             f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f);
                         } else {
                             f.x = swish_fast(f.x); f.y = swish_fast(f.y); f.z = swish_fast(f.z); f.w = swish_fast(f.w);
                         }
                         if (!unit_alpha) { f.x *= alpha; f.y *= alpha; f.z *= alpha; f.w *= alpha; }
+                        if (drop_on) { f.x *= kx; f.y *= ky; f.z *= kz; f.w *= kw; }
                         store4<CT>(crow, f);
                     }
                 }
@@ -337,8 +365,10 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, const Unit& w, 
                         if (dbase) {
                             x = alpha * f[e] * dact_fast(__bfloat162float(dbase[(long)grow * p.lddact + col + e]), p.act);
                         } else {
-                            if (abase) abase[off] = from_f32<CT>(f[e]);
+                            const bool keep = !drop_on || drop_keep1(dk, (uint32_t)grow, (uint32_t)(col + e));
+                            if (abase) abase[off] = from_f32<CT>((keep || !p.drop_mark) ? f[e] : LASR_DROP_MARK);
                             x = alpha * act_fast(f[e], p.act);
+                            if (drop_on) x = keep ? x * dk.scale : 0.f;
                             if (rbase) x += rbase[(long)grow * p.ldres + col + e];
                         }
                         cbase[off] = from_f32<CT>(x);
@@ -375,7 +405,7 @@ __device__ __forceinline__ float col_sums_32(float (&v)[32], int lane) {
     return v[0];
 }
 
-template <typename CT, int MODE>
+template <typename CT, int MODE, bool DROP>
 __device__ __forceinline__ void epilogue_unit_tma(const TcParams& p, const Unit& w, uint32_t tmem_acc, uint8_t* stage, int q, int part,
                                                   int lane, const CUtensorMap* mc, const CUtensorMap* mx, int& buf) {
     constexpr bool BF = sizeof(CT) == 2;
@@ -389,10 +419,18 @@ __device__ __forceinline__ void epilogue_unit_tma(const TcParams& p, const Unit&
     const bool has_aux = p.aux != nullptr;   // warp-uniform
     const bool dbl = BF && !has_aux;         // two 2 KB boxes alternate; otherwise one 4 KB set (C, or C + aux)
     const int cb1 = w.b1 * p.c_b1, cb2 = w.b2 * p.c_b2;
+    const bool drop_on = DROP && p.drop.thr != 0;  // warp-uniform
+    DropKey dk = {};
+    if (drop_on) dk = drop_key(p.drop);
     for (int cc = part * 32; cc < p.bn; cc += 32 * (EPI_WARPS / 4)) {
         const int col0 = w.n0 + cc;
         if (col0 >= col_limit) break;  // warp-uniform
         const bool full = col0 + 32 <= col_limit;
+        // dropout: the 32 keep bits of this thread's row segment (4 Philox calls), computed BEFORE the TMEM load is waited for:
+        // they depend on nothing the accumulator holds, so their ~300 integer instructions fill issue slots the latency chain
+        // TMEM -> math -> staging leaves idle
+        uint32_t keep = 0xffffffffu;
+        if (drop_on) keep = drop_keep32(dk, (uint32_t)row, (uint32_t)col0);
         // row-wise global operands first (in flight while TMEM is read)
         float4 r4[MODE == EPI_RES ? 8 : 1];
         uint4 s4[DACT ? 4 : 1];
@@ -463,6 +501,10 @@ __device__ __forceinline__ void epilogue_unit_tma(const TcParams& p, const Unit&
                 if constexpr (MODE == EPI_PLAIN || MODE == EPI_RES) {
                     v[4 * j] = fmaf(v[4 * j], alpha, alpha * b.x); v[4 * j + 1] = fmaf(v[4 * j + 1], alpha, alpha * b.y);
                     v[4 * j + 2] = fmaf(v[4 * j + 2], alpha, alpha * b.z); v[4 * j + 3] = fmaf(v[4 * j + 3], alpha, alpha * b.w);
+                    if (drop_on) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) v[4 * j + e] = ((keep >> (4 * j + e)) & 1u) ? v[4 * j + e] * dk.scale : 0.f;
+                    }
                     if constexpr (MODE == EPI_RES) { v[4 * j] += r4[j].x; v[4 * j + 1] += r4[j].y; v[4 * j + 2] += r4[j].z; v[4 * j + 3] += r4[j].w; }
                 } else {  // EPI_RELU / EPI_SWISH: pre-activation = acc + bias
                     v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
@@ -477,13 +519,17 @@ __device__ __forceinline__ void epilogue_unit_tma(const TcParams& p, const Unit&
         }
         __syncwarp();
         if constexpr (MODE == EPI_RELU || MODE == EPI_SWISH) {
-            if (has_aux) {  // pre-activation copy (bf16 on this path)
+            if (has_aux) {  // pre-activation copy (bf16 on this path); dropped elements carry the marker whose act'() is 0
                 uint8_t* sx = stage + 2048;
+                const uint32_t hk = (drop_on && p.drop_mark) ? keep : 0xffffffffu;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
+                    float h[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) h[e] = ((hk >> (8 * j + e)) & 1u) ? v[8 * j + e] : LASR_DROP_MARK;
                     uint4 u;
-                    u.x = pack_bf16x2(v[8 * j], v[8 * j + 1]); u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-                    u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                    u.x = pack_bf16x2(h[0], h[1]); u.y = pack_bf16x2(h[2], h[3]);
+                    u.z = pack_bf16x2(h[4], h[5]); u.w = pack_bf16x2(h[6], h[7]);
                     *reinterpret_cast<uint4*>(sx + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = u;
                 }
             }
@@ -493,6 +539,10 @@ __device__ __forceinline__ void epilogue_unit_tma(const TcParams& p, const Unit&
             if (!unit_alpha) {  // warp-uniform: no multiply on the alpha == 1 path (every FFN fc1)
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] *= alpha;
+            }
+            if (drop_on) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = ((keep >> j) & 1u) ? v[j] * dk.scale : 0.f;
             }
         }
         if constexpr (BF) {
@@ -569,7 +619,7 @@ struct Walk {
 // BS (B-stationary, K <= 256): the weight tile of the CTA's N tile is loaded ONCE into shared memory and only 16 KB A slabs
 // stream through the ring -- a K = 256 GEMM otherwise re-fetches its 128 KB B tile for every 128 x 256 output tile and runs
 // at the L2 -> SM bandwidth, not at the tensor or HBM roofline.
-template <int MODE, bool C_F32, bool BS>
+template <int MODE, bool C_F32, bool BS, bool DROP>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_x,
@@ -760,10 +810,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             tc_fence_after();
             const uint32_t tmem_acc = tmem_base + (uint32_t)(as * ACC_COLS);
             if constexpr (TMA_OK) {
-                if (tma_epi) epilogue_unit_tma<CT, MODE>(p, w, tmem_acc, stage, q, part, lane, &tma_c, &tma_x, sbuf);
-                else epilogue_unit<CT, MODE, CW>(p, w, tmem_acc, stage, q, part, lane);
+                if (tma_epi) epilogue_unit_tma<CT, MODE, DROP>(p, w, tmem_acc, stage, q, part, lane, &tma_c, &tma_x, sbuf);
+                else epilogue_unit<CT, MODE, CW, DROP>(p, w, tmem_acc, stage, q, part, lane);
             } else {
-                epilogue_unit<CT, MODE, CW>(p, w, tmem_acc, stage, q, part, lane);
+                epilogue_unit<CT, MODE, CW, DROP>(p, w, tmem_acc, stage, q, part, lane);
             }
             tc_fence_before();
             __syncwarp();
@@ -897,10 +947,10 @@ static int pick_bn(int n, int gran) {
 typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
                          const TcParams);
 
-template <int MODE, bool C_F32, bool BS>
+template <int MODE, bool C_F32, bool BS, bool DROP = false>
 static TcKernel configured_kernel() {
     static bool configured = false;
-    TcKernel k = gemm_tc_kernel<MODE, C_F32, BS>;
+    TcKernel k = gemm_tc_kernel<MODE, C_F32, BS, DROP>;
     if (!configured) {
         if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_MAX_DYNAMIC) != cudaSuccess) return nullptr;
         configured = true;
@@ -934,10 +984,38 @@ static TcKernel pick_kernel(int mode, bool f32) {
     }
 }
 
+// dropout variants (streaming kernels only): separate instantiations, so that the p = 0 kernels are the round-1 kernels
+static TcKernel pick_drop_kernel(int mode, bool f32) {
+    if (f32) {
+        switch (mode) {
+            case EPI_PLAIN: return configured_kernel<EPI_PLAIN, true, false, true>();
+            case EPI_RELU: return configured_kernel<EPI_RELU, true, false, true>();
+            case EPI_SWISH: return configured_kernel<EPI_SWISH, true, false, true>();
+            case EPI_RES: return configured_kernel<EPI_RES, true, false, true>();
+            default: return configured_kernel<EPI_GENERIC, true, false, true>();
+        }
+    }
+    switch (mode) {
+        case EPI_PLAIN: return configured_kernel<EPI_PLAIN, false, false, true>();
+        case EPI_RELU: return configured_kernel<EPI_RELU, false, false, true>();
+        case EPI_SWISH: return configured_kernel<EPI_SWISH, false, false, true>();
+        default: return configured_kernel<EPI_GENERIC, false, false, true>();
+    }
+}
+
 static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mx, const TcParams& p,
                      cudaStream_t st, const CUtensorMap* ma2 = nullptr, const CUtensorMap* mb2 = nullptr) {
     const bool f32 = p.c_dtype == LASR_F32;
-    TcKernel kern = p.b_stationary ? pick_kernel<true>(p.epi_mode, f32) : pick_kernel<false>(p.epi_mode, f32);
+    TcKernel kern;
+    if (p.drop.thr != 0) {
+        if (p.b_stationary || p.dual || p.epi_mode == EPI_ACC || p.epi_mode == EPI_DSWISH || p.epi_mode == EPI_DRELU) {
+            set_error("gemm_tc: dropout is not available with this epilogue");
+            return LASR_ERR_UNSUPPORTED;
+        }
+        kern = pick_drop_kernel(p.epi_mode, f32);
+    } else {
+        kern = p.b_stationary ? pick_kernel<true>(p.epi_mode, f32) : pick_kernel<false>(p.epi_mode, f32);
+    }
     if (!kern) return check_launch("gemm_tc smem attr");
     int smem_bytes, grid;
     if (p.b_stationary) {
@@ -1004,6 +1082,9 @@ int gemm_tc_dispatch(const lasr_gemm_args* a, cudaStream_t st) {
     if (a->colsum) p.vec_ok = p.vec_ok && ((reinterpret_cast<uintptr_t>(a->colsum) & 15) == 0) && al16(a->cs1, 4) && al16(a->cs2, 4);
     p.dual = a->a2 ? 1 : 0;
     p.bias2 = a->bias2;
+    p.drop.state = reinterpret_cast<const unsigned long long*>(a->drop_state);
+    p.drop.site = a->drop_site; p.drop.thr = a->drop_thr; p.drop.scale = a->drop_scale;
+    p.drop_mark = a->drop_mark_aux;
     if (a->a2) p.epi_mode = a->act == LASR_ACT_SWISH ? EPI_DUAL_DSWISH : EPI_DUAL_DRELU;
     else if (a->accumulate) p.epi_mode = EPI_ACC;
     else if (a->dact && a->act == LASR_ACT_SWISH) p.epi_mode = EPI_DSWISH;
@@ -1043,7 +1124,7 @@ int gemm_tc_dispatch(const lasr_gemm_args* a, cudaStream_t st) {
         const char* bs_env = getenv("LASR_GEMM_BS");
         const int bs_on = bs_env ? atoi(bs_env) : 0;
         const int total_kb = (a->k + BK - 1) / BK;
-        if (bs_on && !p.dual && total_kb <= 4 && p.split_k == 1 && !a->accumulate && a->batch1 * a->batch2 == 1 && p.tiles_n <= sm_count() / 2) {
+        if (bs_on && !p.dual && p.drop.thr == 0 && total_kb <= 4 && p.split_k == 1 && !a->accumulate && a->batch1 * a->batch2 == 1 && p.tiles_n <= sm_count() / 2) {
             const int per_n = sm_count() / p.tiles_n;                  // CTAs per N tile
             const int rounds = (p.tiles_m + per_n - 1) / per_n;        // M tiles of the busiest CTA
             const double eff = (double)p.tiles_m / ((double)rounds * per_n);

@@ -7,6 +7,7 @@
 // The backward's "+=" mode implements the residual-stream gradient add of the pre-norm blocks
 // (nets/conformer_layer.py:37-66) without an extra pass.
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace lasr {
 
@@ -85,7 +86,11 @@ __device__ __forceinline__ float4 load4(const TD* p) {
 // Optional fused outputs for the pre-norm residual blocks (nets/conformer_layer.py:37-66 backward):
 //   dx_lo  : bf16 copy of the final dx (the A operand of the next block's dgrad / wgrad GEMMs)
 //   colsum : += cs_scale * sum_rows dx  (the bias gradient of the Linear whose output was added to this residual stream)
-template <typename TD, int NV>
+// Dropout (drop.thr != 0): the block that consumes dx_lo / colsum sits behind a dropout on its OUTPUT in the forward pass
+// (x + drop(f(LN x)), nets/conformer_layer.py:37-66), so the gradient it must see is keep * scale * dx: the mask of that site is
+// regenerated here (philox.cuh) and applied to dx_lo and to the column sums; dx itself (the residual-stream gradient) is not
+// masked.  TLO = bf16 (tensor-core mode) or float (fp32 parity mode, where the masked copy is a second fp32 tensor).
+template <typename TD, typename TLO, int NV>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TD* __restrict__ dy, long lddy,
                                                             const float* __restrict__ x, long ldx,
                                                             const float* __restrict__ mean,
@@ -93,11 +98,14 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TD* __restrict
                                                             const float* __restrict__ gamma, float* __restrict__ dx,
                                                             long lddx, int accumulate, float* __restrict__ dgamma,
                                                             float* __restrict__ dbeta, int rows, int d,
-                                                            bf16* __restrict__ dx_lo, long lddxlo,
-                                                            float* __restrict__ colsum, float cs_scale) {
+                                                            TLO* __restrict__ dx_lo, long lddxlo,
+                                                            float* __restrict__ colsum, float cs_scale, DropCfg drop) {
     LASR_PDL_SYNC();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nchunk = d >> 2;
+    const bool drop_on = drop.thr != 0;
+    DropKey dk = {};
+    if (drop_on) dk = drop_key(drop);
     float4 gam[NV], ag[NV], abt[NV], acs[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -139,12 +147,22 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TD* __restrict
                 const float4 o = make_float4(rs * (g[i].x - m1 - xh[i].x * m2) + old[i].x, rs * (g[i].y - m1 - xh[i].y * m2) + old[i].y,
                                              rs * (g[i].z - m1 - xh[i].z * m2) + old[i].z, rs * (g[i].w - m1 - xh[i].w * m2) + old[i].w);
                 *reinterpret_cast<float4*>(dxr + 4 * c) = o;
-                if (dx_lo) {
-                    __nv_bfloat162 h0 = __floats2bfloat162_rn(o.x, o.y), h1 = __floats2bfloat162_rn(o.z, o.w);
-                    uint2 u; u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-                    *reinterpret_cast<uint2*>(dx_lo + row * lddxlo + 4 * c) = u;
+                float4 om = o;
+                if (drop_on) {
+                    const uint32_t k4 = drop_keep4(dk, (uint32_t)row, (uint32_t)(4 * c));
+                    om.x = (k4 & 1u) ? o.x * dk.scale : 0.f; om.y = (k4 & 2u) ? o.y * dk.scale : 0.f;
+                    om.z = (k4 & 4u) ? o.z * dk.scale : 0.f; om.w = (k4 & 8u) ? o.w * dk.scale : 0.f;
                 }
-                acs[i].x += o.x; acs[i].y += o.y; acs[i].z += o.z; acs[i].w += o.w;
+                if (dx_lo) {
+                    if constexpr (sizeof(TLO) == 4) {
+                        *reinterpret_cast<float4*>(dx_lo + row * lddxlo + 4 * c) = om;
+                    } else {
+                        __nv_bfloat162 h0 = __floats2bfloat162_rn(om.x, om.y), h1 = __floats2bfloat162_rn(om.z, om.w);
+                        uint2 u; u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+                        *reinterpret_cast<uint2*>(dx_lo + row * lddxlo + 4 * c) = u;
+                    }
+                }
+                acs[i].x += om.x; acs[i].y += om.y; acs[i].z += om.z; acs[i].w += om.w;
             }
         }
     }
@@ -202,7 +220,20 @@ int lasr_layernorm_bwd(const void* dy, int dy_dtype, int64_t lddy, const float* 
                        const float* rstd, const float* gamma, float* dx, int64_t lddx, int accumulate, float* dgamma,
                        float* dbeta, int rows, int d, void* dx_lo, int64_t lddxlo, float* colsum, float colsum_scale,
                        void* stream) {
+    return lasr_layernorm_bwd_drop(dy, dy_dtype, lddy, x, ldx, mean, rstd, gamma, dx, lddx, accumulate, dgamma, dbeta, rows, d, dx_lo,
+                                   LASR_BF16, lddxlo, colsum, colsum_scale, nullptr, 0u, 0u, 1.f, stream);
+}
+
+int lasr_layernorm_bwd_drop(const void* dy, int dy_dtype, int64_t lddy, const float* x, int64_t ldx, const float* mean,
+                            const float* rstd, const float* gamma, float* dx, int64_t lddx, int accumulate, float* dgamma,
+                            float* dbeta, int rows, int d, void* dx_lo, int lo_dtype, int64_t lddxlo, float* colsum,
+                            float colsum_scale, const void* drop_state, uint32_t drop_site, uint32_t drop_thr, float drop_scale,
+                            void* stream) {
     using namespace lasr;
+    LASR_REQUIRE(drop_thr == 0 || (drop_state && drop_thr < 65536u), "layernorm_bwd: dropout needs drop_state and thr < 65536");
+    LASR_REQUIRE(lo_dtype == LASR_BF16 || lo_dtype == LASR_F32, "layernorm_bwd: bad dx_lo dtype");
+    DropCfg drop;
+    drop.state = (const unsigned long long*)drop_state; drop.site = drop_site; drop.thr = drop_thr; drop.scale = drop_scale;
     LASR_REQUIRE(dy && x && mean && rstd && gamma && dx && dgamma && dbeta, "layernorm_bwd: null pointer");
     LASR_REQUIRE(rows > 0 && d > 0 && d % 4 == 0 && d <= 128 * LN_MAXV, "layernorm_bwd: d=%d unsupported", d);
     LASR_REQUIRE(ldx % 4 == 0 && lddy % 4 == 0 && lddx % 4 == 0 && lddxlo % 4 == 0, "layernorm_bwd: row strides must be multiples of 4");
@@ -211,10 +242,15 @@ int lasr_layernorm_bwd(const void* dy, int dy_dtype, int64_t lddy, const float* 
     cudaStream_t st = (cudaStream_t)stream;
     int grid = ceil_div(rows, 8);
     if (grid > 148 * 3) grid = 148 * 3;
-    bf16* lo = (bf16*)dx_lo;
-#define LASR_LNB(TD, NV)                                                                                                     \
-    launch_pdl(layernorm_bwd_kernel<TD, NV>, grid, 256, 0, st, (const TD*)dy, lddy, x, ldx, mean, rstd, gamma, dx, lddx, accumulate, \
-                                                       dgamma, dbeta, rows, d, lo, lddxlo, colsum, colsum_scale)
+#define LASR_LNB(TD, NV)                                                                                                            \
+    do {                                                                                                                            \
+        if (lo_dtype == LASR_F32)                                                                                                   \
+            launch_pdl(layernorm_bwd_kernel<TD, float, NV>, grid, 256, 0, st, (const TD*)dy, lddy, x, ldx, mean, rstd, gamma, dx, lddx,  \
+                       accumulate, dgamma, dbeta, rows, d, (float*)dx_lo, lddxlo, colsum, colsum_scale, drop);                      \
+        else                                                                                                                        \
+            launch_pdl(layernorm_bwd_kernel<TD, bf16, NV>, grid, 256, 0, st, (const TD*)dy, lddy, x, ldx, mean, rstd, gamma, dx, lddx,   \
+                       accumulate, dgamma, dbeta, rows, d, (bf16*)dx_lo, lddxlo, colsum, colsum_scale, drop);                       \
+    } while (0)
 #define LASR_LNB_D(TD)                  \
     do {                                \
         if (d <= 128) LASR_LNB(TD, 1);  \

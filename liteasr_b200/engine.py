@@ -21,6 +21,7 @@ from typing import Optional
 
 import torch
 
+from . import dropout as DR
 from . import ops
 from .ops import ACT_NONE, ACT_RELU, ACT_SWISH
 from .store import ParamStore
@@ -75,17 +76,19 @@ class Engine:
         return NS(x=x, y=y, mean=mean, rstd=rstd, pfx=pfx)
 
     def layernorm_bwd(self, ln: NS, dy: torch.Tensor, dx: torch.Tensor, accumulate: bool, nxt=None, want_lo: bool = False):
-        """dx (+)= LN'(dy) and the LayerNorm parameter gradients.  ``nxt = (bias_grad, scale)``: the updated residual-stream
+        """dx (+)= LN'(dy) and the LayerNorm parameter gradients.  ``nxt = (bias_grad, scale, drop)``: the updated residual-stream
         gradient dx is also the output gradient of the block that runs next in backward order, so its output Linear's bias
         gradient (scale * colsum(dx)) and the operand-dtype copy of dx that block's GEMMs read are produced here, in the same
-        pass.  Returns that copy (dx itself in fp32 mode), or None when not requested."""
+        pass -- both masked with that block's output-dropout site ``drop`` (None = no dropout there).  Returns that copy (dx
+        itself in fp32 mode without dropout), or None when not requested."""
         want_lo = want_lo or nxt is not None
+        drop = nxt[2] if nxt is not None and len(nxt) > 2 else None
         lo = None
-        if want_lo and self.adt != torch.float32:
+        if want_lo and (self.adt != torch.float32 or drop is not None):
             lo = _empty(dx.shape, self.adt, self.dev)
         ops.layernorm_bwd(dy, ln.x, ln.mean, ln.rstd, self.st.p(ln.pfx + ".weight"), dx, self.st.g(ln.pfx + ".weight"),
                           self.st.g(ln.pfx + ".bias"), accumulate, dx_lo=lo, colsum=(nxt[0] if nxt is not None else None),
-                          colsum_scale=(nxt[1] if nxt is not None else 1.0))
+                          colsum_scale=(nxt[1] if nxt is not None else 1.0), drop=drop)
         if not want_lo:
             return None
         return lo if lo is not None else dx
@@ -112,8 +115,8 @@ class Engine:
         return s
 
     def linear(self, x, wname, out_dtype, *, bias=True, act=ACT_NONE, res=None, alpha=1.0, aux=False, w=None, n=None,
-               bias_t=None):
-        """y = alpha * act(x @ W^T + b) (+ res).  W (N,K) from the store (or ``w``)."""
+               bias_t=None, drop=None, drop_mark_aux=False):
+        """y = drop(alpha * act(x @ W^T + b)) (+ res).  W (N,K) from the store (or ``w``)."""
         w = self.st.w(wname + ".weight") if w is None else w
         n = w.shape[0] if n is None else n
         m = x.shape[0]
@@ -126,7 +129,8 @@ class Engine:
             auxbuf = ab[:, :n] if ld != n else ab
         b = bias_t if bias_t is not None else (self.st.p(wname + ".bias") if bias else None)
         ops.gemm(x, w, out, m, n, x.shape[1], lda=x.stride(0), ldb=w.stride(0), ldc=ld, bias=b, res=res,
-                 ldres=(res.stride(0) if res is not None else 0), aux=auxbuf, alpha=alpha, act=act)
+                 ldres=(res.stride(0) if res is not None else 0), aux=auxbuf, alpha=alpha, act=act, drop=drop,
+                 drop_mark_aux=drop_mark_aux)
         return (out, auxbuf) if aux else out
 
     def wgrad(self, dy, x, gw, alpha=1.0) -> None:
@@ -136,7 +140,8 @@ class Engine:
         ops.gemm(dy, x, gw, n, k, m, lda=dy.stride(0), ldb=x.stride(0), ldc=gw.stride(0), ta=True, tb=True, accumulate=True,
                  split_k=self._split_k(n, k, m), alpha=alpha)
 
-    def dgrad(self, dy, w, *, out_dtype=None, alpha=1.0, dx_res=None, dact=None, act=ACT_NONE, colsum=None, recompute=None):
+    def dgrad(self, dy, w, *, out_dtype=None, alpha=1.0, dx_res=None, dact=None, act=ACT_NONE, colsum=None, recompute=None,
+              drop=None):
         """dx = alpha * dy @ W (W stored (N_out, K_in)); optional fused activation backward (``dact``/``act``), bias-gradient
         column sum of the result (``colsum``) and fp32 accumulation into ``dx_res``."""
         m, n = dy.shape
@@ -144,11 +149,11 @@ class Engine:
         dx = _empty((m, k), self.adt if out_dtype is None else out_dtype, self.dev) if dx_res is None else dx_res
         ops.gemm(dy, w, dx, m, k, n, lda=dy.stride(0), ldb=w.stride(0), ldc=dx.stride(0), tb=True, alpha=alpha,
                  res=dx_res, ldres=(dx_res.stride(0) if dx_res is not None else 0), dact=dact, act=act, colsum=colsum,
-                 recompute=recompute)
+                 recompute=recompute, drop=drop)
         return dx
 
     def linear_bwd(self, dy, x, wname, *, need_dx=True, dx_dtype=None, bias=True, dbias_done=False, alpha=1.0, w=None,
-                   gw=None, gb=None, dx_res=None):
+                   gw=None, gb=None, dx_res=None, dx_drop=None):
         """dW += alpha * dy^T x ; db += colsum(dy) (unless fused earlier) ; returns dx = alpha * dy @ W."""
         w = self.st.w(wname + ".weight") if w is None else w
         gw = self.st.gw(wname + ".weight") if gw is None else gw
@@ -157,34 +162,41 @@ class Engine:
         self.wgrad(dy, x, gw, alpha)
         if not need_dx:
             return None
-        return self.dgrad(dy, w, out_dtype=dx_dtype, alpha=alpha, dx_res=dx_res)
+        return self.dgrad(dy, w, out_dtype=dx_dtype, alpha=alpha, dx_res=dx_res, drop=dx_drop)
 
     # ------------------------------------------------------------------------------------------
     # feed-forward block   x <- x + scale * fc2(act(fc1(LN x)))      nets/feed_forward.py:18-19,
     #                                                               nets/conformer_layer.py:37-47,58-66
     # ------------------------------------------------------------------------------------------
-    def ffn_fwd(self, x, pfx_norm, pfx_ff, act, scale) -> NS:
+    def ffn_fwd(self, x, pfx_norm, pfx_ff, act, scale, d_in=None, d_out=None) -> NS:
+        """d_in: dropout on the activation (feed_forward.py:19); d_out: dropout on the block output before the residual add
+        (conformer_layer.py:42,63, transformer_layer.py:58).  The inner mask is not regenerated in backward: the dropped
+        elements of the saved pre-activation carry a marker whose Swish' is 0 (Swish), or the saved output is 0 there (ReLU)."""
         ln = self.layernorm(x, pfx_norm, self.adt)
+        if act == ACT_SWISH and d_in is not None and self.ffn_recompute:
+            raise NotImplementedError("LASR_FFN_RECOMPUTE=1 cannot be combined with FFN dropout (the mask lives in the saved pre-activation)")
         if act == ACT_SWISH and not self.ffn_recompute:
-            a, h = self.linear(ln.y, pfx_ff + ".fc1", self.adt, act=act, aux=True)
+            a, h = self.linear(ln.y, pfx_ff + ".fc1", self.adt, act=act, aux=True, drop=d_in, drop_mark_aux=True)
         else:  # ReLU: act'(.) from the output; Swish in bf16 mode: the pre-activation is recomputed in the backward GEMM
-            a, h = self.linear(ln.y, pfx_ff + ".fc1", self.adt, act=act), None
-        out = self.linear(a, pfx_ff + ".fc2", torch.float32, res=x, alpha=scale)
-        return NS(out=out, ln=ln, a=a, h=h, act=act, scale=scale, pfx=pfx_ff)
+            a, h = self.linear(ln.y, pfx_ff + ".fc1", self.adt, act=act, drop=d_in), None
+        out = self.linear(a, pfx_ff + ".fc2", torch.float32, res=x, alpha=scale, drop=d_out)
+        return NS(out=out, ln=ln, a=a, h=h, act=act, scale=scale, pfx=pfx_ff, d_in=d_in, d_out=d_out)
 
     def ffn_bwd(self, c: NS, dres: torch.Tensor, dy: torch.Tensor, nxt=None, want_lo=False):
         """dres (fp32, in/out): gradient wrt the block output on entry, wrt the block input on exit.  dy = operand-dtype copy of
         dres on entry (fc2's bias gradient was taken by the producer of dy).  Returns the operand copy of the updated dres."""
         st = self.st
         self.wgrad(dy, c.a, st.gw(c.pfx + ".fc2.weight"), c.scale)
-        # dh = scale * (dy @ W2) * act'(.)  and  db1 += colsum(dh), both in the dgrad epilogue
+        # dh = scale * (dy @ W2) * act'(.)  and  db1 += colsum(dh), both in the dgrad epilogue; with inner dropout the 1/(1-p)
+        # factor rides on alpha and the mask is implied by the saved tensor (marker / zero)
+        s_in = c.scale * (c.d_in.scale if c.d_in is not None else 1.0)
         if c.act == ACT_SWISH and c.h is None:
             # fc1's pre-activation is recomputed on the tensor cores inside this GEMM (second TMEM accumulator) instead of being
             # written by the forward pass and read back: 154 MB less written and 135 MB less read per FFN at C2/B=126
             dh = self.dgrad(dy, st.w(c.pfx + ".fc2.weight"), alpha=c.scale, act=c.act, colsum=st.g(c.pfx + ".fc1.bias"),
                             recompute=(c.ln.y, st.w(c.pfx + ".fc1.weight"), st.p(c.pfx + ".fc1.bias")))
         else:
-            dh = self.dgrad(dy, st.w(c.pfx + ".fc2.weight"), alpha=c.scale, dact=(c.h if c.act == ACT_SWISH else c.a), act=c.act,
+            dh = self.dgrad(dy, st.w(c.pfx + ".fc2.weight"), alpha=s_in, dact=(c.h if c.act == ACT_SWISH else c.a), act=c.act,
                             colsum=st.g(c.pfx + ".fc1.bias"))
         self.wgrad(dh, c.ln.y, st.gw(c.pfx + ".fc1.weight"))
         dln = self.dgrad(dh, st.w(c.pfx + ".fc1.weight"))
@@ -194,21 +206,24 @@ class Engine:
     # attention core on projected q/k/v  (nets/attention.py:46-59,61-71,120-154)
     # q: (B*Tq, *) view with row stride ldq, k/v: (B*Tk, *) views; heads addressed via batch strides.
     # ------------------------------------------------------------------------------------------
-    def attn_core_fwd(self, q, k, v, B, H, Tq, Tk, dk, lens, mask_mode, causal, qv=None, p=None) -> NS:
+    def attn_core_fwd(self, q, k, v, B, H, Tq, Tk, dk, lens, mask_mode, causal, qv=None, p=None, drop=None) -> NS:
+        """``drop``: dropout on the attention probabilities (attention.py:55).  0.0 in the reference's shipped config; a
+        non-zero rate keeps the unfused sequence and costs one extra pass in each direction (probabilities are saved undropped
+        for the softmax backward, the dropped copy feeds probs.V and dV)."""
         d = H * dk
         ld = _ceil(Tk, 8)
         scale = dk ** -0.5
-        fused = (qv is not None and Tq == Tk and self.adt == torch.bfloat16 and self.fused_attn and ops.rel_attn_fwd_supported(Tk, dk)
-                 and q.stride(0) == qv.stride(0) and k.stride(0) == v.stride(0))
+        fused = (qv is not None and drop is None and Tq == Tk and self.adt == torch.bfloat16 and self.fused_attn
+                 and ops.rel_attn_fwd_supported(Tk, dk) and q.stride(0) == qv.stride(0) and k.stride(0) == v.stride(0))
         if fused and os.environ.get("LASR_ATTN_LD64", "1") != "0":
             ld = _ceil(Tk, 64)  # 128-byte aligned probability rows: every 128-byte piece the kernel stores is a whole line
-        if (qv is not None and Tq == Tk and self.adt == torch.bfloat16 and self.fused_attn and ops.rel_attn_fwd_supported(Tk, dk)
-                and q.stride(0) == qv.stride(0) and k.stride(0) == v.stride(0)):
+        if fused:
             # one tcgen05 kernel: both score contractions, rel_shift, scale, mask, softmax and probs.V (csrc/attn_fused.cu)
             probs = _empty((B, H, Tq, ld), self.adt, self.dev)
             o = _empty((B * Tq, d), self.adt, self.dev)
             ops.rel_attn_fwd(q, qv, k, v, p, probs, o, lens, mask_mode, scale, B, H, Tq, dk)
-            return NS(q=q, k=k, v=v, qv=qv, p=p, probs=probs, o=o, B=B, H=H, Tq=Tq, Tk=Tk, dk=dk, ld=ld, scale=scale)
+            return NS(q=q, k=k, v=v, qv=qv, p=p, probs=probs, probs_d=probs, drop=None, o=o, B=B, H=H, Tq=Tq, Tk=Tk, dk=dk, ld=ld,
+                      scale=scale)
         ac = _empty((B, H, Tq, ld), self.sdt, self.dev)
         # n_store = ld: the padding columns [Tk, ld) are written too (zeros), which keeps the whole epilogue on the vector path
         ops.gemm(q, k, ac, Tq, Tk, dk, lda=q.stride(0), ldb=k.stride(0), ldc=ld, batch=(B, H), sa=(Tq * q.stride(0), dk),
@@ -220,10 +235,17 @@ class Engine:
                      sa=(Tq * qv.stride(0), dk), sb=(0, dk), sc=(H * Tq * ld, Tq * ld), n_store=ld)
         probs = _empty((B, H, Tq, ld), self.adt, self.dev)
         ops.attn_softmax_fwd(ac, bd, probs, lens, mask_mode, causal, scale, Tk)
+        probs_d = probs
+        if drop is not None:  # logical tensor (B*H*Tq, Tk); the padding columns [Tk, ld) stay zero
+            probs_d = _empty(probs.shape, self.adt, self.dev)
+            if ld != Tk:
+                ops.zero_(probs_d)
+            ops.dropout(probs.view(-1, ld)[:, :Tk], probs_d.view(-1, ld)[:, :Tk], drop)
         o = _empty((B * Tq, d), self.adt, self.dev)
-        ops.gemm(probs, v, o, Tq, dk, Tk, lda=ld, ldb=v.stride(0), ldc=d, tb=True, batch=(B, H), sa=(H * Tq * ld, Tq * ld),
+        ops.gemm(probs_d, v, o, Tq, dk, Tk, lda=ld, ldb=v.stride(0), ldc=d, tb=True, batch=(B, H), sa=(H * Tq * ld, Tq * ld),
                  sb=(Tk * v.stride(0), dk), sc=(Tq * d, dk))
-        return NS(q=q, k=k, v=v, qv=qv, p=p, probs=probs, o=o, B=B, H=H, Tq=Tq, Tk=Tk, dk=dk, ld=ld, scale=scale)
+        return NS(q=q, k=k, v=v, qv=qv, p=p, probs=probs, probs_d=probs_d, drop=drop, o=o, B=B, H=H, Tq=Tq, Tk=Tk, dk=dk, ld=ld,
+                  scale=scale)
 
     def attn_core_bwd(self, c: NS, do, dq, dk_, dv, dqv=None, dp32=None, bq=None, bk=None, bv=None) -> None:
         """do (B*Tq,d) adt.  Writes dq/dk_/dv (views with the same strides as q/k/v); rel-pos: dqv and dp32 (+=).
@@ -233,8 +255,10 @@ class Engine:
         dprobs = _empty((B, H, Tq, ld), self.sdt, self.dev)
         ops.gemm(do, c.v, dprobs, Tq, Tk, dk, lda=do.stride(0), ldb=c.v.stride(0), ldc=ld, batch=(B, H), sa=(Tq * do.stride(0), dk),
                  sb=(Tk * c.v.stride(0), dk), sc=bs, n_store=ld)
-        # dV[j] = sum_i probs[i,j] dO[i]
-        ops.gemm(c.probs, do, dv, Tk, dk, Tq, lda=ld, ldb=do.stride(0), ldc=dv.stride(0), ta=True, tb=True, batch=(B, H), sa=bs,
+        if c.drop is not None:  # d(probs) = keep * scale * d(dropped probs): the forward mask, regenerated in place
+            ops.dropout(dprobs.view(-1, ld)[:, :Tk], dprobs.view(-1, ld)[:, :Tk], c.drop)
+        # dV[j] = sum_i probs[i,j] dO[i]   (the probabilities that multiplied V: the dropped copy)
+        ops.gemm(c.probs_d, do, dv, Tk, dk, Tq, lda=ld, ldb=do.stride(0), ldc=dv.stride(0), ta=True, tb=True, batch=(B, H), sa=bs,
                  sb=(Tq * do.stride(0), dk), sc=(Tk * dv.stride(0), dk), colsum=bv, cs=(0, dk))
         dsc = _empty((B, H, Tq, ld), self.adt, self.dev)
         dbd = _empty((B, H, Tq, ld), self.adt, self.dev) if c.qv is not None else None
@@ -253,7 +277,7 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     # relative-position self-attention block (nets/conformer_layer.py:107-128, nets/attention.py:120-154)
     # ------------------------------------------------------------------------------------------
-    def rel_mha_fwd(self, x, pfx_norm, pfx, pos, B, T, H, xlens) -> NS:
+    def rel_mha_fwd(self, x, pfx_norm, pfx, pos, B, T, H, xlens, d_att=None, d_out=None) -> NS:
         d = x.shape[1]
         dk = d // H
         ln = self.layernorm(x, pfx_norm, self.adt)
@@ -265,9 +289,9 @@ class Engine:
         qv = _empty((B * T, d), self.adt, self.dev)
         ops.pos_bias_fwd(q, self.st.p(pfx + ".pos_bias_u").view(-1), self.st.p(pfx + ".pos_bias_v").view(-1), qu, qv)
         p = self.linear(pos, pfx + ".linear_pos", self.adt, bias=False)
-        core = self.attn_core_fwd(qu, k, v, B, H, T, T, dk, xlens, 3 if xlens is not None else 0, 0, qv=qv, p=p)
-        out = self.linear(core.o, pfx + ".linear_o", torch.float32, res=x)
-        return NS(out=out, ln=ln, qkv=qkv, core=core, pos=pos, pfx=pfx, d=d)
+        core = self.attn_core_fwd(qu, k, v, B, H, T, T, dk, xlens, 3 if xlens is not None else 0, 0, qv=qv, p=p, drop=d_att)
+        out = self.linear(core.o, pfx + ".linear_o", torch.float32, res=x, drop=d_out)
+        return NS(out=out, ln=ln, qkv=qkv, core=core, pos=pos, pfx=pfx, d=d, d_out=d_out)
 
     def rel_mha_bwd(self, c: NS, dres, dy, nxt=None, want_lo=False):
         st, d, core = self.st, c.d, c.core
@@ -292,14 +316,14 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     # plain MHA blocks of the decoder (nets/transformer_layer.py:29-51,161-177, nets/attention.py:61-71)
     # ------------------------------------------------------------------------------------------
-    def self_mha_fwd(self, y, pfx_norm, pfx, B, L, H, ylens) -> NS:
+    def self_mha_fwd(self, y, pfx_norm, pfx, B, L, H, ylens, d_att=None, d_out=None) -> NS:
         d = y.shape[1]
         ln = self.layernorm(y, pfx_norm, self.adt)
         qkv = self.linear(ln.y, None, self.adt, w=self.st.w(pfx + ".linear_q.weight", 3 * d, d),
                           bias_t=self.st.p_span(pfx + ".linear_q.bias", 3 * d))
-        core = self.attn_core_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], B, H, L, L, d // H, ylens, 2, 1)
-        out = self.linear(core.o, pfx + ".linear_o", torch.float32, res=y)
-        return NS(out=out, ln=ln, core=core, pfx=pfx, d=d)
+        core = self.attn_core_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], B, H, L, L, d // H, ylens, 2, 1, drop=d_att)
+        out = self.linear(core.o, pfx + ".linear_o", torch.float32, res=y, drop=d_out)
+        return NS(out=out, ln=ln, core=core, pfx=pfx, d=d, d_out=d_out)
 
     def self_mha_bwd(self, c: NS, dres, dy, nxt=None, want_lo=False):
         st, d, core = self.st, c.d, c.core
@@ -312,15 +336,16 @@ class Engine:
         dln = self.dgrad(dqkv, st.w(c.pfx + ".linear_q.weight", 3 * d, d))
         return self.layernorm_bwd(c.ln, dln, dres, True, nxt, want_lo)
 
-    def src_mha_fwd(self, y, mem, pfx_norm, pfx, B, L, T, H, xlens, mask_mode=3) -> NS:
+    def src_mha_fwd(self, y, mem, pfx_norm, pfx, B, L, T, H, xlens, mask_mode=3, d_att=None, d_out=None) -> NS:
         d = y.shape[1]
         ln = self.layernorm(y, pfx_norm, self.adt)
         q = self.linear(ln.y, pfx + ".linear_q", self.adt)
         kv = self.linear(mem, None, self.adt, w=self.st.w(pfx + ".linear_k.weight", 2 * d, d),
                          bias_t=self.st.p_span(pfx + ".linear_k.bias", 2 * d))
-        core = self.attn_core_fwd(q, kv[:, :d], kv[:, d:], B, H, L, T, d // H, xlens, mask_mode if xlens is not None else 0, 0)
-        out = self.linear(core.o, pfx + ".linear_o", torch.float32, res=y)
-        return NS(out=out, ln=ln, core=core, mem=mem, pfx=pfx, d=d)
+        core = self.attn_core_fwd(q, kv[:, :d], kv[:, d:], B, H, L, T, d // H, xlens, mask_mode if xlens is not None else 0, 0,
+                                  drop=d_att)
+        out = self.linear(core.o, pfx + ".linear_o", torch.float32, res=y, drop=d_out)
+        return NS(out=out, ln=ln, core=core, mem=mem, pfx=pfx, d=d, d_out=d_out)
 
     def src_mha_bwd(self, c: NS, dres, dy, dmem32, nxt=None, want_lo=False):
         st, d, core = self.st, c.d, c.core
@@ -341,7 +366,7 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     # convolution block (nets/conformer_layer.py:49-56, nets/conformer_convolution.py:44-57)
     # ------------------------------------------------------------------------------------------
-    def conv_fwd(self, x, pfx_norm, pfx, B, T, bn_mod, training) -> NS:
+    def conv_fwd(self, x, pfx_norm, pfx, B, T, bn_mod, training, d_out=None) -> NS:
         st, d = self.st, x.shape[1]
         ln = self.layernorm(x, pfx_norm, self.adt)
         y2 = self.linear(ln.y, None, self.adt, w=st.w(pfx + ".pointwise_conv1.weight"), bias_t=st.p(pfx + ".pointwise_conv1.bias"))
@@ -357,8 +382,9 @@ class Engine:
                         training, eps=bn_mod.eps, momentum=bn_mod.momentum)
         a = _empty((B * T, d), self.adt, self.dev)
         ops.bn_swish_fwd(z, mean, rstd, st.p(pfx + ".norm.weight"), st.p(pfx + ".norm.bias"), a)
-        out = self.linear(a, None, torch.float32, w=st.w(pfx + ".pointwise_conv2.weight"), bias_t=st.p(pfx + ".pointwise_conv2.bias"), res=x)
-        return NS(out=out, ln=ln, y2=y2, z=z, mean=mean, rstd=rstd, a=a, pfx=pfx, B=B, T=T, d=d, training=training)
+        out = self.linear(a, None, torch.float32, w=st.w(pfx + ".pointwise_conv2.weight"), bias_t=st.p(pfx + ".pointwise_conv2.bias"), res=x,
+                          drop=d_out)
+        return NS(out=out, ln=ln, y2=y2, z=z, mean=mean, rstd=rstd, a=a, pfx=pfx, B=B, T=T, d=d, training=training, d_out=d_out)
 
     def conv_bwd(self, c: NS, dres, dy, nxt=None, want_lo=False):
         st, d, pfx = self.st, c.d, c.pfx
@@ -399,10 +425,11 @@ class Engine:
             self.st.derived[key] = w
         return self.st.derived[key]
 
-    def embed_fwd(self, xs, pfx, d) -> NS:
+    def embed_fwd(self, xs, pfx, d, d_out=None) -> NS:
+        """d_out: dropout on ``x * sqrt(d)`` (positional_encoding.py:73-75), applied in the output Linear's epilogue."""
         B, T, F = xs.shape
         if self.adt == torch.bfloat16 and ops.planes_supported(d, T, F):
-            return self._embed_fwd_planes(xs, pfx, d)
+            return self._embed_fwd_planes(xs, pfx, d, d_out)
         T1, F1 = (T - 3) // 2 + 1, (F - 3) // 2 + 1
         T2, F2 = (T1 - 3) // 2 + 1, (F1 - 3) // 2 + 1
         st = self.st
@@ -412,10 +439,11 @@ class Engine:
         ops.im2col_s2(h1, col)
         h2 = self.linear(col, None, self.adt, w=self._conv2_weight(pfx, d), bias_t=st.p(pfx + ".conv.2.bias"), act=ACT_RELU)
         h2v = h2.view(B * T2, F2 * d)
-        x0 = self.linear(h2v, None, torch.float32, w=self._out_weight(pfx, d, F2), bias_t=st.p(pfx + ".out.bias"), alpha=math.sqrt(d))
-        return NS(out=x0, xs=xs, h1=h1, col=col, h2=h2, B=B, T1=T1, F1=F1, T2=T2, F2=F2, d=d, pfx=pfx, planes=False)
+        x0 = self.linear(h2v, None, torch.float32, w=self._out_weight(pfx, d, F2), bias_t=st.p(pfx + ".out.bias"), alpha=math.sqrt(d),
+                         drop=d_out)
+        return NS(out=x0, xs=xs, h1=h1, col=col, h2=h2, B=B, T1=T1, F1=F1, T2=T2, F2=F2, d=d, pfx=pfx, planes=False, d_out=d_out)
 
-    def _embed_fwd_planes(self, xs, pfx, d) -> NS:
+    def _embed_fwd_planes(self, xs, pfx, d, d_out=None) -> NS:
         """bf16 mode: conv1 writes parity planes, conv2 runs as an implicit GEMM on them (no im2col matrix); conv2's output keeps
         V = F2 + 1 slots per frame, the output Linear reads the first F2 of them through its row stride."""
         B, T, F = xs.shape
@@ -426,8 +454,10 @@ class Engine:
         h2p = _empty((B * T2, V * d), self.adt, self.dev)
         ops.conv2_fwd(h1p, self._conv2_weight(pfx, d), st.p(pfx + ".conv.2.bias"), h2p, B, T, F)
         h2v = h2p[:, : F2 * d]
-        x0 = self.linear(h2v, None, torch.float32, w=self._out_weight(pfx, d, F2), bias_t=st.p(pfx + ".out.bias"), alpha=math.sqrt(d))
-        return NS(out=x0, xs=xs, h1p=h1p, h2p=h2p, h2v=h2v, B=B, T=T, F=F, T1=T1, F1=F1, U=U, V=V, T2=T2, F2=F2, d=d, pfx=pfx, planes=True)
+        x0 = self.linear(h2v, None, torch.float32, w=self._out_weight(pfx, d, F2), bias_t=st.p(pfx + ".out.bias"), alpha=math.sqrt(d),
+                         drop=d_out)
+        return NS(out=x0, xs=xs, h1p=h1p, h2p=h2p, h2v=h2v, B=B, T=T, F=F, T1=T1, F1=F1, U=U, V=V, T2=T2, F2=F2, d=d, pfx=pfx, planes=True,
+                  d_out=d_out)
 
     def embed_bwd(self, c: NS, dy) -> None:
         """dy: operand-dtype gradient wrt the front end's output (out.bias gradient already taken by the producer of dy)."""
@@ -481,23 +511,36 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     # encoder (nets/transformer_encoder.py:107-127; use_rel=True, arch=conformer, activation=swish)
     # ------------------------------------------------------------------------------------------
-    def encoder_fwd(self, enc, xs, xlens, training: bool) -> NS:
-        """xs (B,T,F) fp32, xlens (B,) int64 or None (maskless inference call).  Returns ctx with ctx.out (B,T',d) fp32."""
+    def encoder_fwd(self, enc, xs, xlens, training: bool, rng=None) -> NS:
+        """xs (B,T,F) fp32, xlens (B,) int64 or None (maskless inference call).  Returns ctx with ctx.out (B,T',d) fp32.
+        rng: RNG snapshot of this pass (dropout.RngState.begin_pass) -- dropout is applied iff training and rng is given."""
         d, H = enc.h_dim, enc.n_head
         B = xs.shape[0]
         pfx = enc._lasr_prefix
-        emb = self.embed_fwd(xs, pfx + "embed", d)
+        if not training:
+            rng = None
+        E, G = DR.NET_ENC, DR.GLOBAL_LAYER
+        emb = self.embed_fwd(xs, pfx + "embed", d, DR.drop(rng, E, G, DR.ENC_POS_X, enc.pe.dropout_rate))
         Tp = emb.T2
         enc.pe.ensure(Tp, self.dev)  # extend_pe (positional_encoding.py:40-53): T' may exceed max_len = 5000
-        pos = self.to_adt(enc.pe.pe[0, :Tp])  # absolute positions 0..T'-1 (positional_encoding.py:74); contiguous slice
+        d_pos = DR.drop(rng, E, G, DR.ENC_POS_EMB, enc.pe.dropout_rate)
+        if d_pos is None:
+            pos = self.to_adt(enc.pe.pe[0, :Tp])  # absolute positions 0..T'-1 (positional_encoding.py:74); contiguous slice
+        else:  # ONE dropped pos_emb shared by every layer, as in the reference (transformer_encoder.py:116-124)
+            pos = ops.dropout(enc.pe.pe[0, :Tp], _empty((Tp, d), self.adt, self.dev), d_pos)
         x = emb.out
         layers = []
         for i, layer in enumerate(enc.enc_layers):
             lp = f"{pfx}enc_layers.{i}"
-            c1 = self.ffn_fwd(x, lp + ".feed_forward_macaron_norm", lp + ".feed_forward_macaron", ACT_SWISH, 0.5)
-            c2 = self.rel_mha_fwd(c1.out, lp + ".self_attn_norm", lp + ".self_attn", pos, B, Tp, H, xlens)
-            c3 = self.conv_fwd(c2.out, lp + ".conv_norm", lp + ".conv", B, Tp, layer.conv.norm, training)
-            c4 = self.ffn_fwd(c3.out, lp + ".feed_forward_norm", lp + ".feed_forward", ACT_SWISH, 0.5)
+            p_out, p_ffm, p_ff = layer.dropout_rate, layer.feed_forward_macaron.dropout_rate, layer.feed_forward.dropout_rate
+            c1 = self.ffn_fwd(x, lp + ".feed_forward_macaron_norm", lp + ".feed_forward_macaron", ACT_SWISH, 0.5,
+                              DR.drop(rng, E, i, DR.ENC_FFM_INNER, p_ffm), DR.drop(rng, E, i, DR.ENC_FFM_OUT, p_out))
+            c2 = self.rel_mha_fwd(c1.out, lp + ".self_attn_norm", lp + ".self_attn", pos, B, Tp, H, xlens,
+                                  DR.drop(rng, E, i, DR.ENC_ATT_PROB, layer.self_attn.dropout_rate), DR.drop(rng, E, i, DR.ENC_ATT_OUT, p_out))
+            c3 = self.conv_fwd(c2.out, lp + ".conv_norm", lp + ".conv", B, Tp, layer.conv.norm, training,
+                               DR.drop(rng, E, i, DR.ENC_CONV_OUT, p_out))
+            c4 = self.ffn_fwd(c3.out, lp + ".feed_forward_norm", lp + ".feed_forward", ACT_SWISH, 0.5,
+                              DR.drop(rng, E, i, DR.ENC_FF_INNER, p_ff), DR.drop(rng, E, i, DR.ENC_FF_OUT, p_out))
             c5 = self.layernorm(c4.out, lp + ".final_norm", torch.float32)
             layers.append((c1, c2, c3, c4, c5))
             x = c5.y
@@ -520,16 +563,19 @@ class Engine:
             nxt = _empty(dres.shape, torch.float32, self.dev)
             # every LayerNorm backward also emits the bias gradient of the Linear that closes the block that runs NEXT in
             # backward order (its output gradient is exactly the residual-stream gradient being written) + the bf16 copy
-            dy = self.layernorm_bwd(c5, dres, nxt, False, (g(lp + ".feed_forward.fc2.bias"), 0.5))
+            dy = self.layernorm_bwd(c5, dres, nxt, False, (g(lp + ".feed_forward.fc2.bias"), 0.5, c4.d_out))
             dres = nxt
-            dy = self.ffn_bwd(c4, dres, dy, (g(lp + ".conv.pointwise_conv2.bias"), 1.0))
-            dy = self.conv_bwd(c3, dres, dy, (g(lp + ".self_attn.linear_o.bias"), 1.0))
-            dy = self.rel_mha_bwd(c2, dres, dy, (g(lp + ".feed_forward_macaron.fc2.bias"), 0.5))
-            dy = self.ffn_bwd(c1, dres, dy, (g(c.pfx + "embed.out.bias"), math.sqrt(c.d)) if i == 0 else None)
+            dy = self.ffn_bwd(c4, dres, dy, (g(lp + ".conv.pointwise_conv2.bias"), 1.0, c3.d_out))
+            dy = self.conv_bwd(c3, dres, dy, (g(lp + ".self_attn.linear_o.bias"), 1.0, c2.d_out))
+            dy = self.rel_mha_bwd(c2, dres, dy, (g(lp + ".feed_forward_macaron.fc2.bias"), 0.5, c1.d_out))
+            dy = self.ffn_bwd(c1, dres, dy, (g(c.pfx + "embed.out.bias"), math.sqrt(c.d), c.emb.d_out) if i == 0 else None)
             if hook is not None:
                 hook(*st.range_of(lp + "."))
         if len(c.layers) == 0:
-            dy = self.to_adt(dres)
+            if c.emb.d_out is not None:
+                dy = ops.dropout(dres, _empty(dres.shape, self.adt, self.dev), c.emb.d_out)
+            else:
+                dy = self.to_adt(dres)
             ops.act_bwd(dy, None, None, g(c.pfx + "embed.out.bias"), ACT_NONE, math.sqrt(c.d))
         self.embed_bwd(c.emb, dy)
         if hook is not None:
@@ -538,24 +584,32 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     # CTC head (nets/ctc.py:28-30): logits = ctc_lo(dropout(h)); dropout p must be 0 here
     # ------------------------------------------------------------------------------------------
-    def ctc_head_fwd(self, ctc, h_enc) -> NS:
+    def ctc_head_fwd(self, ctc, h_enc, rng=None) -> NS:
+        """rng given: ``ctc_lo(F.dropout(h, p))`` -- the reference applies this dropout in train AND eval mode (nets/ctc.py:29,
+        quirk Q3), so callers pass an rng whenever they go through ``CTC.forward``; the inference path
+        (``CTC.log_softmax``, nets/ctc.py:25-26) has no dropout and passes None."""
         B, Tp, d = h_enc.shape
-        hb = self.to_adt(h_enc.reshape(B * Tp, d))
+        drop = DR.drop(rng, DR.NET_CTC, DR.GLOBAL_LAYER, DR.CTC_IN, ctc.dropout_rate)
+        h2 = h_enc.reshape(B * Tp, d)
+        if drop is None:
+            hb = self.to_adt(h2)
+        else:  # dropout fused with the fp32 -> operand-dtype cast
+            hb = ops.dropout(h2, _empty((B * Tp, d), self.adt, self.dev), drop)
         pfx = ctc._lasr_prefix + "ctc_lo"
         logits = self.linear(hb, pfx, self.adt)
         V = logits.shape[1]
-        return NS(out=logits, hb=hb, pfx=pfx, B=B, Tp=Tp, V=V, d=d)
+        return NS(out=logits, hb=hb, pfx=pfx, B=B, Tp=Tp, V=V, d=d, drop=drop)
 
     def ctc_head_bwd(self, c: NS, dlogits, dh32=None) -> torch.Tensor:
         """dlogits (B*T', V) adt view -> dh (B*T', d) fp32 (accumulated into dh32 when given)."""
         if dh32 is None:
-            return self.linear_bwd(dlogits, c.hb, c.pfx, dx_dtype=torch.float32)
-        return self.linear_bwd(dlogits, c.hb, c.pfx, dx_res=dh32)
+            return self.linear_bwd(dlogits, c.hb, c.pfx, dx_dtype=torch.float32, dx_drop=c.drop)
+        return self.linear_bwd(dlogits, c.hb, c.pfx, dx_res=dh32, dx_drop=c.drop)
 
     # ------------------------------------------------------------------------------------------
     # decoder (nets/transformer_decoder.py:70-93, nets/transformer_layer.py:179-221)
     # ------------------------------------------------------------------------------------------
-    def decoder_fwd(self, dec, ys, ylens, h_enc, xlens, mem_mask_mode: int = 3) -> NS:
+    def decoder_fwd(self, dec, ys, ylens, h_enc, xlens, mem_mask_mode: int = 3, training: bool = False, rng=None) -> NS:
         """ys (B,L) int64 decoder input tokens ([sos | ys], models/u2.py:339-358); ylens (B,) so that key j of the
         self-attention is valid iff j < ylens[b]+1 (and j <= i); h_enc (B,T',d) fp32; xlens raw input lengths or None.
         mem_mask_mode 3: memory key j valid iff 4j < xlens[b] (training: the reference's re-subsampled padding mask);
@@ -569,18 +623,28 @@ class Engine:
         y = _empty((B * L, d), torch.float32, self.dev)
         dec.pe.ensure(L, self.dev)
         ops.embed_fwd(ys, st.p(pfx + "embed.weight"), dec.pe.pe[0], y, math.sqrt(d))
+        if not training:
+            rng = None
+        D = DR.NET_DEC
+        d_pos = DR.drop(rng, D, DR.GLOBAL_LAYER, DR.DEC_POS, dec.pe.dropout_rate)
+        if d_pos is not None:  # dropout(embed * sqrt(d) + pe), positional_encoding.py:54-55 (a (B*L, d) tensor: in place)
+            ops.dropout(y, y, d_pos)
         mem = self.to_adt(h_enc.reshape(B * Tp, d))
         layers = []
-        for i in range(len(dec.dec_layers)):
+        for i, layer in enumerate(dec.dec_layers):
             lp = f"{pfx}dec_layers.{i}"
-            c1 = self.self_mha_fwd(y, lp + ".self_attn_norm", lp + ".self_attn", B, L, H, ylens)
-            c2 = self.src_mha_fwd(c1.out, mem, lp + ".src_attn_norm", lp + ".src_attn", B, L, Tp, H, xlens, mem_mask_mode)
-            c3 = self.ffn_fwd(c2.out, lp + ".feed_forward_norm", lp + ".feed_forward", ACT_RELU, 1.0)
+            p_out = layer.dropout_rate
+            c1 = self.self_mha_fwd(y, lp + ".self_attn_norm", lp + ".self_attn", B, L, H, ylens,
+                                   DR.drop(rng, D, i, DR.DEC_SELF_PROB, layer.self_attn.dropout_rate), DR.drop(rng, D, i, DR.DEC_SELF_OUT, p_out))
+            c2 = self.src_mha_fwd(c1.out, mem, lp + ".src_attn_norm", lp + ".src_attn", B, L, Tp, H, xlens, mem_mask_mode,
+                                  DR.drop(rng, D, i, DR.DEC_SRC_PROB, layer.src_attn.dropout_rate), DR.drop(rng, D, i, DR.DEC_SRC_OUT, p_out))
+            c3 = self.ffn_fwd(c2.out, lp + ".feed_forward_norm", lp + ".feed_forward", ACT_RELU, 1.0,
+                              DR.drop(rng, D, i, DR.DEC_FF_INNER, layer.feed_forward.dropout_rate), DR.drop(rng, D, i, DR.DEC_FF_OUT, p_out))
             layers.append((c1, c2, c3))
             y = c3.out
         fin = self.layernorm(y, pfx + "after_norm", self.adt)
         logits = self.linear(fin.y, pfx + "linear_out", self.adt)
-        return NS(out=logits, ys=ys, layers=layers, fin=fin, mem=mem, B=B, L=L, Tp=Tp, d=d, V=V, pfx=pfx)
+        return NS(out=logits, ys=ys, layers=layers, fin=fin, mem=mem, B=B, L=L, Tp=Tp, d=d, V=V, pfx=pfx, d_pos=d_pos)
 
     def decoder_bwd(self, c: NS, dlogits, dmem32: torch.Tensor) -> None:
         """dlogits (B*L, V) adt view; dmem32 (B*T', d) fp32 is accumulated into (memory gradient)."""
@@ -588,13 +652,17 @@ class Engine:
         dfin = self.linear_bwd(dlogits, c.fin.y, c.pfx + "linear_out")
         dres = _empty((c.B * c.L, c.d), torch.float32, self.dev)
         n = len(c.layers)
-        dy = self.layernorm_bwd(c.fin, dfin, dres, False, (g(f"{c.pfx}dec_layers.{n - 1}.feed_forward.fc2.bias"), 1.0) if n else None)
+        dy = self.layernorm_bwd(c.fin, dfin, dres, False,
+                                (g(f"{c.pfx}dec_layers.{n - 1}.feed_forward.fc2.bias"), 1.0, c.layers[n - 1][2].d_out) if n else None)
         for i in range(n - 1, -1, -1):
             c1, c2, c3 = c.layers[i]
             lp = f"{c.pfx}dec_layers.{i}"
-            dy = self.ffn_bwd(c3, dres, dy, (g(lp + ".src_attn.linear_o.bias"), 1.0))
-            dy = self.src_mha_bwd(c2, dres, dy, dmem32, (g(lp + ".self_attn.linear_o.bias"), 1.0))
-            dy = self.self_mha_bwd(c1, dres, dy, (g(f"{c.pfx}dec_layers.{i - 1}.feed_forward.fc2.bias"), 1.0) if i > 0 else None)
+            dy = self.ffn_bwd(c3, dres, dy, (g(lp + ".src_attn.linear_o.bias"), 1.0, c2.d_out))
+            dy = self.src_mha_bwd(c2, dres, dy, dmem32, (g(lp + ".self_attn.linear_o.bias"), 1.0, c1.d_out))
+            dy = self.self_mha_bwd(c1, dres, dy, (g(f"{c.pfx}dec_layers.{i - 1}.feed_forward.fc2.bias"), 1.0, c.layers[i - 1][2].d_out)
+                                   if i > 0 else None)
+        if c.d_pos is not None:  # gradient through dropout(embed * sqrt(d) + pe)
+            dres = ops.dropout(dres, _empty(dres.shape, torch.float32, self.dev), c.d_pos)
         ops.embed_bwd(c.ys, dres, st.g(c.pfx + "embed.weight"), math.sqrt(c.d))
         if st.grad_ready_hook is not None:
             st.grad_ready_hook(*st.range_of(c.pfx))

@@ -14,6 +14,7 @@ from typing import List, Optional, Tuple
 import torch
 import torch.nn as nn
 
+from . import dropout as DR
 from . import ops
 from .engine import Engine
 from .store import ParamStore, get_store
@@ -86,7 +87,8 @@ class EncoderFn(torch.autograd.Function):
     def forward(ctx, module, xs, xlens, anchor, *params):
         st, eng, pfx = bind(module, xs.device)
         st.refresh_operands(force=True)
-        c = eng.encoder_fwd(module, xs.contiguous().float(), xlens, module.training)
+        rng = st.rng.begin_pass() if module.training and DR.has_dropout(module) else None
+        c = eng.encoder_fwd(module, xs.contiguous().float(), xlens, module.training, rng)
         ctx.c, ctx.st, ctx.eng, ctx.pfx, ctx.np = c, st, eng, pfx, len(params)
         return c.out
 
@@ -103,7 +105,8 @@ class CTCHeadFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, h_enc, anchor, *params):
         st, eng, pfx = bind(module, h_enc.device)
-        c = eng.ctc_head_fwd(module, h_enc.contiguous().float())
+        rng = st.rng.begin_pass() if DR.has_dropout(module) else None  # train AND eval (nets/ctc.py:29, quirk Q3)
+        c = eng.ctc_head_fwd(module, h_enc.contiguous().float(), rng)
         ctx.c, ctx.st, ctx.eng, ctx.pfx, ctx.np = c, st, eng, pfx, len(params)
         return c.out.view(c.B, c.Tp, -1) if c.out.is_contiguous() else c.out.unflatten(0, (c.B, c.Tp))
 
@@ -122,7 +125,8 @@ class DecoderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, tokens, ylens, memory, xlens, anchor, *params):
         st, eng, pfx = bind(module, memory.device)
-        c = eng.decoder_fwd(module, tokens.contiguous(), ylens, memory.contiguous().float(), xlens)
+        rng = st.rng.begin_pass() if module.training and DR.has_dropout(module) else None
+        c = eng.decoder_fwd(module, tokens.contiguous(), ylens, memory.contiguous().float(), xlens, training=module.training, rng=rng)
         ctx.c, ctx.st, ctx.eng, ctx.pfx, ctx.np = c, st, eng, pfx, len(params)
         return c.out.unflatten(0, (c.B, c.L))
 
@@ -209,10 +213,13 @@ class HybridLossFn(torch.autograd.Function):
             bind(sub, xs.device)
         st.refresh_operands(force=True)
         B = xs.shape[0]
-        ce = eng.encoder_fwd(model.encoder, xs.contiguous().float(), xlens, model.training)
-        cc = eng.ctc_head_fwd(model.ctc, ce.out)
+        # one RNG snapshot for the whole step; the CTC-head site is live in eval mode too (nets/ctc.py:29, quirk Q3)
+        need_rng = (model.training and DR.has_dropout(model)) or DR.has_dropout(model.ctc)
+        rng = st.rng.begin_pass() if need_rng else None
+        ce = eng.encoder_fwd(model.encoder, xs.contiguous().float(), xlens, model.training, rng)
+        cc = eng.ctc_head_fwd(model.ctc, ce.out, rng)
         tokens = model.decoder_tokens(ys)
-        cd = eng.decoder_fwd(model.decoder, tokens, ylens, ce.out, xlens)
+        cd = eng.decoder_fwd(model.decoder, tokens, ylens, ce.out, xlens, training=model.training, rng=rng)
         V, Tp, L = cc.V, ce.Tp, cd.L
         ld = (V + 7) // 8 * 8
         dl_ctc = torch.empty((B * Tp, ld), dtype=eng.adt, device=xs.device)

@@ -4,14 +4,14 @@ from __future__ import annotations
 import torch.nn as nn
 
 from .. import functions as F
-from .layers import check_no_dropout
+from .layers import check_rates
 
 
 class CTC(nn.Module):
     def __init__(self, i_dim: int, o_dim: int, dropout_rate: float):
         super().__init__()
         # quirk Q3: the reference applies F.dropout(p) even in eval(); p = 0 (the U2Config default) makes it the identity
-        check_no_dropout(self, dropout_rate)
+        check_rates(self, dropout_rate)
         self.ctc_lo = nn.Linear(i_dim, o_dim)
         self.dropout_rate = dropout_rate
 

@@ -177,10 +177,4 @@ class DecoderLayer(_Container):
         self.src_attn_norm = LayerNorm(size)
 
 
-def check_no_dropout(module: nn.Module, *rates: float) -> None:
-    """Round-1 scope: the fused kernels implement the reference at its dataclass default dropout_rate = 0.0
-    (models/u2.py:39); non-zero rates are rejected loudly instead of being silently ignored."""
-    if any(float(r) != 0.0 for r in rates):
-        raise NotImplementedError(
-            f"{type(module).__name__}: dropout rates {rates} != 0 are not implemented in liteasr_b200 yet "
-            "(U2Config's default dropout_rate is 0.0)")
+from ..dropout import check_rates  # noqa: E402,F401  (re-exported: the nets validate their rates with it)

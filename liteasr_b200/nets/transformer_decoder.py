@@ -9,7 +9,7 @@ from torch import Tensor
 
 from .. import functions as F
 from .layers import (DecoderLayer, LayerNorm, MultiHeadAttention, PositionalEncoding, PositionwiseFeedForward,
-                     check_no_dropout)
+                     check_rates)
 
 
 class TransformerDecoder(nn.Module):
@@ -17,7 +17,7 @@ class TransformerDecoder(nn.Module):
                  pos_dropout_rate: float, self_attn_dropout_rate: float, src_attn_dropout_rate: float, ff_dropout_rate: float,
                  arch: str) -> None:
         super().__init__()
-        check_no_dropout(self, dropout_rate, pos_dropout_rate, self_attn_dropout_rate, src_attn_dropout_rate, ff_dropout_rate)
+        check_rates(self, dropout_rate, pos_dropout_rate, self_attn_dropout_rate, src_attn_dropout_rate, ff_dropout_rate)
         self.vocab, self.h_dim, self.n_head = i_dim, h_dim, n_head
         self.embed = nn.Embedding(i_dim, h_dim)
         self.pe = PositionalEncoding(h_dim, dropout_rate=pos_dropout_rate)

@@ -9,7 +9,7 @@ from torch import Tensor
 
 from .. import functions as F
 from .layers import (Conv2DLayer, Convolution, LayerNorm, PositionwiseFeedForward, RelativeEncoderLayer,
-                     RelativeMultiHeadAttention, RelativePositionalEncoding, Swish, check_no_dropout)
+                     RelativeMultiHeadAttention, RelativePositionalEncoding, Swish, check_rates)
 
 
 class TransformerEncoder(nn.Module):
@@ -21,7 +21,7 @@ class TransformerEncoder(nn.Module):
         super().__init__()
         if not use_rel or arch != "conformer" or activation != "swish":
             raise NotImplementedError("liteasr_b200.TransformerEncoder implements use_rel=True, arch='conformer', activation='swish'")
-        check_no_dropout(self, dropout_rate, pos_dropout_rate, attn_dropout_rate, ff_dropout_rate)
+        check_rates(self, dropout_rate, pos_dropout_rate, attn_dropout_rate, ff_dropout_rate)
         self.i_dim, self.h_dim, self.n_head = i_dim, h_dim, n_head
         self.embed = Conv2DLayer(i_dim, h_dim, dropout_rate)
         self.pe = RelativePositionalEncoding(h_dim, dropout_rate=pos_dropout_rate)

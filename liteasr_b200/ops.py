@@ -44,8 +44,10 @@ def gemm(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, m: int, n: int, k: i
          accumulate: bool = False, split_k: int = 1, batch: Tuple[int, int] = (1, 1), sa: Tuple[int, int] = (0, 0),
          sb: Tuple[int, int] = (0, 0), sc: Tuple[int, int] = (0, 0), dact: Optional[torch.Tensor] = None,
          colsum: Optional[torch.Tensor] = None, cs: Tuple[int, int] = (0, 0), n_store: int = 0,
-         recompute: Optional[Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]] = None) -> None:
-    """C[b1,b2] = alpha * act(A.B^T + bias) (+ res); see include/lasr.h ``lasr_gemm``."""
+         recompute: Optional[Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]] = None,
+         drop=None, drop_mark_aux: bool = False) -> None:
+    """C[b1,b2] = alpha * act(A.B^T + bias) (+ res); see include/lasr.h ``lasr_gemm``.  ``drop`` = ``Drop`` (dropout on the
+    output before the residual add) or None."""
     _require_cuda(a, b, c, bias, res, aux, dact, colsum)
     if a.dtype != b.dtype:
         raise TypeError("gemm operands must share a dtype")
@@ -76,6 +78,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, m: int, n: int, k: i
         g.a2, g.b2 = x2.data_ptr(), w2.data_ptr()
         g.bias2 = b2.data_ptr() if b2 is not None else None
         g.lda2, g.ldb2, g.k2 = x2.stride(0), w2.stride(0), x2.shape[1]
+    if drop is not None and drop.thr:
+        g.drop_state, g.drop_site, g.drop_thr, g.drop_scale = drop.state.data_ptr(), drop.site, drop.thr, drop.scale
+        g.drop_mark_aux = int(drop_mark_aux)
     if dact is not None and (dact.dtype != a.dtype or dact.dim() != 2 or dact.stride(1) != 1):
         raise TypeError("dact must be a 2-D row-major tensor of the operand dtype")
     if colsum is not None and colsum.dtype != torch.float32:
@@ -186,16 +191,54 @@ def layernorm_fwd(x, gamma, beta, y, mean=None, rstd=None, eps=1e-12):
     return y
 
 
-def layernorm_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, accumulate: bool, dx_lo=None, colsum=None, colsum_scale=1.0):
-    """dx (+)= LN'(dy); optional fused outputs: dx_lo (bf16 copy of the final dx), colsum += colsum_scale * sum_rows dx."""
+def layernorm_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, accumulate: bool, dx_lo=None, colsum=None, colsum_scale=1.0,
+                  drop=None):
+    """dx (+)= LN'(dy); optional fused outputs: dx_lo (bf16 or fp32 copy of the final dx), colsum += colsum_scale * sum_rows dx.
+    ``drop``: the dropout site of the block that consumes dx_lo / colsum (mask applied to those two outputs only)."""
     _require_cuda(dy, x, dx, dx_lo, colsum)
     rows, d = x.shape
-    if dx_lo is not None and dx_lo.dtype != torch.bfloat16:
-        raise TypeError("dx_lo must be bf16")
-    _lib.check(_lib.lib().lasr_layernorm_bwd(_ptr(dy), _i(dtype_code(dy)), _l(dy.stride(0)), _ptr(x), _l(x.stride(0)), _ptr(mean),
-                                             _ptr(rstd), _ptr(gamma), _ptr(dx), _l(dx.stride(0)), _i(accumulate), _ptr(dgamma),
-                                             _ptr(dbeta), _i(rows), _i(d), _ptr(dx_lo), _l(dx_lo.stride(0) if dx_lo is not None else 0),
-                                             _ptr(colsum), _f(colsum_scale), _stream()), "layernorm_bwd")
+    if drop is not None and not drop.thr:
+        drop = None
+    _lib.check(_lib.lib().lasr_layernorm_bwd_drop(
+        _ptr(dy), _i(dtype_code(dy)), _l(dy.stride(0)), _ptr(x), _l(x.stride(0)), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(dx),
+        _l(dx.stride(0)), _i(accumulate), _ptr(dgamma), _ptr(dbeta), _i(rows), _i(d), _ptr(dx_lo),
+        _i(dtype_code(dx_lo) if dx_lo is not None else BF16), _l(dx_lo.stride(0) if dx_lo is not None else 0), _ptr(colsum),
+        _f(colsum_scale), _ptr(drop.state if drop is not None else None), C.c_uint32(drop.site if drop is not None else 0),
+        C.c_uint32(drop.thr if drop is not None else 0), _f(drop.scale if drop is not None else 1.0), _stream()), "layernorm_bwd")
+
+
+class Drop:
+    """One dropout site of one step: device RNG state {seed, step}, site id, 16-bit threshold and the 1/(1-p) scale
+    (include/lasr.h, "Dropout"; liteasr_b200/dropout.py builds these)."""
+    __slots__ = ("state", "site", "thr", "scale")
+
+    def __init__(self, state: torch.Tensor, site: int, p: float):
+        self.state, self.site = state, int(site)
+        self.thr = int(min(65535, max(0, round(float(p) * 65536.0))))
+        self.scale = 65536.0 / (65536.0 - self.thr)
+
+
+def rng_advance(state: torch.Tensor) -> None:
+    """state[1] += 1 on the device (inside the captured step: every replay draws fresh masks)."""
+    _require_cuda(state)
+    assert state.dtype == torch.int64 and state.numel() >= 2
+    _lib.check(_lib.lib().lasr_rng_advance(_ptr(state), _stream()), "rng_advance")
+
+
+def dropout(x: torch.Tensor, y: torch.Tensor, drop: Drop) -> torch.Tensor:
+    """y = keep * scale * x over the logical (rows, cols) = (numel / last, last) tensor; x, y 2-D views (or contiguous N-D)."""
+    _require_cuda(x, y)
+    if x.dim() != 2:
+        assert x.is_contiguous() and y.is_contiguous()
+        x, y2 = x.view(-1, x.shape[-1]), y.view(-1, y.shape[-1])
+    else:
+        y2 = y
+    assert x.shape == y2.shape and x.stride(1) == 1 and y2.stride(1) == 1
+    rows, cols = x.shape
+    _lib.check(_lib.lib().lasr_dropout(_ptr(x), _i(dtype_code(x)), _l(x.stride(0)), _ptr(y2), _i(dtype_code(y2)), _l(y2.stride(0)),
+                                       _l(rows), _i(cols), _ptr(drop.state), C.c_uint32(drop.site), C.c_uint32(drop.thr),
+                                       _f(drop.scale), _stream()), "dropout")
+    return y
 
 
 def act_bwd(da, saved, dh, dbias, act, scale=1.0):

@@ -82,6 +82,8 @@ class ParamStore:
                 for bname, buf in list(mod._buffers.items()):
                     if buf is not None and buf.device != device:
                         mod._buffers[bname] = buf.to(device)
+        from .dropout import RngState
+        self.rng = RngState(device)  # {seed, step} of the dropout stream (seeded from torch.initial_seed())
         self.direct_grads = False
         self._cast_version = None
         self.derived: Dict[str, torch.Tensor] = {}

@@ -219,8 +219,8 @@ class Trainer:
             loss /= dist.get_world_size()
         opt = self.step_fn.optimizer
         if not dist.is_initialized() or dist.get_rank() == 0:
-            self.log("{} - current loss: {:.2f}".format(self._progress(), loss.item()))
-            self.log(f"    lr {opt.rate():.3e} grad_norm {opt.last_grad_norm():.3f} updates {opt.num_updates()}")
+            self.log("{} - current loss: {:.2f}".format(self._progress(), loss.item()) +
+                     f" (lr {opt.rate():.3e}, grad_norm {opt.last_grad_norm():.3f}, updates {opt.num_updates()})")
 
     @torch.no_grad()
     def valid(self, batches: Iterable) -> float:

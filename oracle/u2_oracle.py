@@ -55,6 +55,58 @@ class U2Shape:
 
 
 # --------------------------------------------------------------------------------------
+# dropout (nn.Dropout / F.dropout sites of the reference; masks = the product's own Philox stream, replayed)
+# --------------------------------------------------------------------------------------
+NET_ENC, NET_DEC, NET_CTC = 1, 2, 3
+(ENC_POS_X, ENC_POS_EMB, ENC_FFM_INNER, ENC_FFM_OUT, ENC_ATT_PROB, ENC_ATT_OUT, ENC_CONV_OUT, ENC_FF_INNER,
+ ENC_FF_OUT) = range(1, 10)
+DEC_POS, DEC_SELF_PROB, DEC_SELF_OUT, DEC_SRC_PROB, DEC_SRC_OUT, DEC_FF_INNER, DEC_FF_OUT = range(1, 8)
+CTC_IN = 1
+GLOBAL_LAYER = 0xFFFF
+
+
+@dataclass
+class DropRates:
+    """The ten dropout fields of ``U2Config`` (models/u2.py:39,49-52,62-66) after interpolation."""
+
+    dropout_rate: float = 0.0            # CTC head input (nets/ctc.py:29; applied in train AND eval, quirk Q3)
+    enc_dropout_rate: float = 0.0        # Conformer sub-layer outputs (nets/conformer_layer.py:42,54,63,125)
+    enc_pos_dropout_rate: float = 0.0    # x * sqrt(d) and pos_emb (nets/positional_encoding.py:75)
+    enc_attn_dropout_rate: float = 0.0   # attention probabilities (nets/attention.py:55)
+    enc_ff_dropout_rate: float = 0.0     # FFN inner (nets/feed_forward.py:19)
+    dec_dropout_rate: float = 0.0
+    dec_pos_dropout_rate: float = 0.0
+    dec_self_attn_dropout_rate: float = 0.0
+    dec_src_attn_dropout_rate: float = 0.0
+    dec_ff_dropout_rate: float = 0.0
+
+    @classmethod
+    def uniform(cls, p: float, attn: float = 0.0) -> "DropRates":
+        """config/model/my_U2.yaml: one rate everywhere, the three attention rates overridden."""
+        return cls(p, p, p, attn, p, p, p, attn, attn, p)
+
+
+class Dropper:
+    """x -> x * keep / (1 - p) with keep from oracle/philox_oracle.py (the published Philox4x32-10 + the product's site /
+    row / column indexing, restated).  The reference draws its masks from torch's global generator, which fused kernels cannot
+    replay: parity with dropout is therefore stated as 'the reference arithmetic under the SAME masks'."""
+
+    def __init__(self, rates: DropRates, seed: int, step: int, training: bool = True):
+        self.r, self.seed, self.step, self.training = rates, int(seed), int(step), training
+
+    def __call__(self, x: Tensor, net: int, layer: int, kind: int, p: float, always: bool = False) -> Tensor:
+        if p <= 0.0 or not (self.training or always):
+            return x
+        from oracle import philox_oracle
+        site = ((net & 0xFF) << 24) | ((layer & 0xFFFF) << 8) | (kind & 0xFF)
+        return philox_oracle.apply(x, site, self.seed, self.step, p)
+
+
+def _nodrop(x, *a, **k):
+    return x
+
+
+# --------------------------------------------------------------------------------------
 # masks / lengths / targets
 # --------------------------------------------------------------------------------------
 def pad_mask(lens: Tensor, width: Optional[int] = None) -> Tensor:
@@ -165,18 +217,18 @@ def split_heads(x: Tensor, h: int) -> Tensor:
     return x.view(b, t, h, d // h).transpose(1, 2)  # (B,H,T,dk)
 
 
-def softmax_attend(scores: Tensor, v: Tensor, mask: Optional[Tensor]) -> Tensor:
-    """nets/attention.py:46-59 minus linear_o: masked_fill(-1e38) -> softmax -> @V -> merge heads.
+def softmax_attend(scores: Tensor, v: Tensor, mask: Optional[Tensor], drop=_nodrop) -> Tensor:
+    """nets/attention.py:46-59 minus linear_o: masked_fill(-1e38) -> softmax -> dropout -> @V -> merge heads.
     No post-softmax re-zeroing (quirk Q4)."""
     if mask is not None:
         scores = scores.masked_fill(mask, MASK_FILL)
-    a = torch.softmax(scores, dim=-1)
+    a = drop(torch.softmax(scores, dim=-1))
     o = a @ v
     b, h, t, dk = o.shape
     return o.transpose(1, 2).reshape(b, t, h * dk)
 
 
-def rel_self_attention(sd: SD, p: str, x: Tensor, pos: Tensor, mask: Optional[Tensor], h: int) -> Tensor:
+def rel_self_attention(sd: SD, p: str, x: Tensor, pos: Tensor, mask: Optional[Tensor], h: int, drop=_nodrop) -> Tensor:
     """nets/attention.py:120-154.  x (B,T,d) already layer-normed; pos (1,T,d); mask (B,1,1,T)."""
     d = x.size(-1)
     dk = d // h
@@ -189,22 +241,22 @@ def rel_self_attention(sd: SD, p: str, x: Tensor, pos: Tensor, mask: Optional[Te
     ac = qu @ k.transpose(-2, -1)
     bd = rel_shift(qv @ pp.transpose(-2, -1))
     scores = (ac + bd) * (dk ** -0.5)
-    return dense(sd, p + ".linear_o", softmax_attend(scores, v, mask))
+    return dense(sd, p + ".linear_o", softmax_attend(scores, v, mask, drop))
 
 
-def attention(sd: SD, p: str, xq: Tensor, xkv: Tensor, mask: Optional[Tensor], h: int) -> Tensor:
+def attention(sd: SD, p: str, xq: Tensor, xkv: Tensor, mask: Optional[Tensor], h: int, drop=_nodrop) -> Tensor:
     """nets/attention.py:61-71 (plain scaled dot-product MHA; decoder self/src attention)."""
     dk = xq.size(-1) // h
     q = split_heads(dense(sd, p + ".linear_q", xq), h)
     k = split_heads(dense(sd, p + ".linear_k", xkv), h)
     v = split_heads(dense(sd, p + ".linear_v", xkv), h)
     scores = (dk ** -0.5) * (q @ k.transpose(-2, -1))
-    return dense(sd, p + ".linear_o", softmax_attend(scores, v, mask))
+    return dense(sd, p + ".linear_o", softmax_attend(scores, v, mask, drop))
 
 
-def feed_forward(sd: SD, p: str, x: Tensor, act) -> Tensor:
-    """nets/feed_forward.py:18-19 (dropout = identity at rate 0)."""
-    return dense(sd, p + ".fc2", act(dense(sd, p + ".fc1", x)))
+def feed_forward(sd: SD, p: str, x: Tensor, act, drop=_nodrop) -> Tensor:
+    """nets/feed_forward.py:18-19: fc2(dropout(act(fc1 x)))."""
+    return dense(sd, p + ".fc2", drop(act(dense(sd, p + ".fc1", x))))
 
 
 def conv_module(sd: SD, p: str, x: Tensor, training: bool, bn_out: Optional[dict]) -> Tensor:
@@ -240,39 +292,54 @@ def conv_module(sd: SD, p: str, x: Tensor, training: bool, bn_out: Optional[dict
     return y @ sd[p + ".pointwise_conv2.weight"].squeeze(-1).t() + sd[p + ".pointwise_conv2.bias"]
 
 
-def conformer_layer(sd: SD, p: str, x: Tensor, pos: Tensor, mask, h: int, training: bool, bn_out) -> Tensor:
-    """nets/conformer_layer.py:130-147 (pre-norm, macaron FFN scale 0.5, extra final_norm)."""
-    x = x + 0.5 * feed_forward(sd, p + ".feed_forward_macaron", layer_norm(sd, p + ".feed_forward_macaron_norm", x), swish)
-    x = x + rel_self_attention(sd, p + ".self_attn", layer_norm(sd, p + ".self_attn_norm", x), pos, mask, h)
-    x = x + conv_module(sd, p + ".conv", layer_norm(sd, p + ".conv_norm", x), training, bn_out)
-    x = x + 0.5 * feed_forward(sd, p + ".feed_forward", layer_norm(sd, p + ".feed_forward_norm", x), swish)
+def conformer_layer(sd: SD, p: str, x: Tensor, pos: Tensor, mask, h: int, training: bool, bn_out, dp=None, li: int = 0) -> Tensor:
+    """nets/conformer_layer.py:130-147 (pre-norm, macaron FFN scale 0.5, extra final_norm); ``dp`` = Dropper or None."""
+    def d(kind, rate):
+        return (lambda t: dp(t, NET_ENC, li, kind, rate)) if dp is not None else _nodrop
+    r = dp.r if dp is not None else DropRates()
+    out = r.enc_dropout_rate
+    x = x + 0.5 * d(ENC_FFM_OUT, out)(feed_forward(sd, p + ".feed_forward_macaron", layer_norm(sd, p + ".feed_forward_macaron_norm", x),
+                                                     swish, d(ENC_FFM_INNER, r.enc_ff_dropout_rate)))
+    x = x + d(ENC_ATT_OUT, out)(rel_self_attention(sd, p + ".self_attn", layer_norm(sd, p + ".self_attn_norm", x), pos, mask, h,
+                                                    d(ENC_ATT_PROB, r.enc_attn_dropout_rate)))
+    x = x + d(ENC_CONV_OUT, out)(conv_module(sd, p + ".conv", layer_norm(sd, p + ".conv_norm", x), training, bn_out))
+    x = x + 0.5 * d(ENC_FF_OUT, out)(feed_forward(sd, p + ".feed_forward", layer_norm(sd, p + ".feed_forward_norm", x), swish,
+                                                    d(ENC_FF_INNER, r.enc_ff_dropout_rate)))
     return layer_norm(sd, p + ".final_norm", x)
 
 
 def encoder(sd: SD, cfg: U2Shape, xs: Tensor, xs_mask: Optional[Tensor], training: bool = True,
-            bn_out: Optional[dict] = None) -> Tensor:
+            bn_out: Optional[dict] = None, dp=None) -> Tensor:
     """nets/transformer_encoder.py:107-127 with use_rel=True, arch=conformer, activation=swish."""
     d = cfg.enc_dim
     x = conv2d_subsampling(sd, "encoder.embed", xs)
     x = x * math.sqrt(d)  # positional_encoding.py:73
     pos = sinusoid_table(x.size(1), d, x.dtype).unsqueeze(0)  # :74 -- absolute positions 0..T'-1
+    if dp is not None:  # :75 -- dropout on both, ONE dropped pos_emb for all layers
+        x = dp(x, NET_ENC, GLOBAL_LAYER, ENC_POS_X, dp.r.enc_pos_dropout_rate)
+        pos = dp(pos, NET_ENC, GLOBAL_LAYER, ENC_POS_EMB, dp.r.enc_pos_dropout_rate)
     mask = None
     if xs_mask is not None:
         assert tuple(xs_mask.shape) == tuple(xs.shape[:2])
         m = subsample_mask(xs_mask)
         mask = m.view(m.size(0), 1, 1, m.size(1))
     for i in range(cfg.enc_layers):
-        x = conformer_layer(sd, f"encoder.enc_layers.{i}", x, pos, mask, cfg.enc_attn_heads, training, bn_out)
+        x = conformer_layer(sd, f"encoder.enc_layers.{i}", x, pos, mask, cfg.enc_attn_heads, training, bn_out, dp, i)
     return layer_norm(sd, "encoder.after_norm", x)
 
 
 def decoder(sd: SD, cfg: U2Shape, ys_in: Tensor, self_mask: Tensor, memory: Tensor,
-            memory_mask: Optional[Tensor]) -> Tensor:
+            memory_mask: Optional[Tensor], dp=None) -> Tensor:
     """nets/transformer_decoder.py:70-93 + nets/transformer_layer.py:179-221 (ReLU FFN, pre-norm)."""
     d = cfg.dec_dim
     h = cfg.dec_attn_heads
+    r = dp.r if dp is not None else DropRates()
+
+    def dr(li, kind, rate):
+        return (lambda t: dp(t, NET_DEC, li, kind, rate)) if dp is not None else _nodrop
     y = sd["decoder.embed.weight"][ys_in]
     y = y * math.sqrt(d) + sinusoid_table(y.size(1), d, y.dtype).unsqueeze(0)
+    y = dr(GLOBAL_LAYER, DEC_POS, r.dec_pos_dropout_rate)(y)  # positional_encoding.py:54-55
     smask = self_mask.unsqueeze(1)
     mmask = None
     if memory_mask is not None:
@@ -281,22 +348,26 @@ def decoder(sd: SD, cfg: U2Shape, ys_in: Tensor, self_mask: Tensor, memory: Tens
         mmask = m.view(m.size(0), 1, 1, m.size(1))
     for i in range(cfg.dec_layers):
         p = f"decoder.dec_layers.{i}"
+        out = r.dec_dropout_rate
         z = layer_norm(sd, p + ".self_attn_norm", y)
-        y = y + attention(sd, p + ".self_attn", z, z, smask, h)
+        y = y + dr(i, DEC_SELF_OUT, out)(attention(sd, p + ".self_attn", z, z, smask, h, dr(i, DEC_SELF_PROB, r.dec_self_attn_dropout_rate)))
         z = layer_norm(sd, p + ".src_attn_norm", y)
-        y = y + attention(sd, p + ".src_attn", z, memory, mmask, h)
-        y = y + feed_forward(sd, p + ".feed_forward", layer_norm(sd, p + ".feed_forward_norm", y), torch.relu)
+        y = y + dr(i, DEC_SRC_OUT, out)(attention(sd, p + ".src_attn", z, memory, mmask, h, dr(i, DEC_SRC_PROB, r.dec_src_attn_dropout_rate)))
+        y = y + dr(i, DEC_FF_OUT, out)(feed_forward(sd, p + ".feed_forward", layer_norm(sd, p + ".feed_forward_norm", y), torch.relu,
+                                                     dr(i, DEC_FF_INNER, r.dec_ff_dropout_rate)))
     return dense(sd, "decoder.linear_out", layer_norm(sd, "decoder.after_norm", y))
 
 
-def u2_forward(sd: SD, cfg: U2Shape, xs, xlens, ys, ylens, training: bool = True, bn_out=None):
-    """models/u2.py:116-159 -> (h_attn (B,L+1,V), h_ctc (B,T',V), h_enc). CTC-head dropout = 0."""
+def u2_forward(sd: SD, cfg: U2Shape, xs, xlens, ys, ylens, training: bool = True, bn_out=None, dp=None):
+    """models/u2.py:116-159 -> (h_attn (B,L+1,V), h_ctc (B,T',V), h_enc).  ``dp`` = Dropper (its ``training`` flag gates every
+    site except the CTC head's, which the reference applies unconditionally: nets/ctc.py:29, quirk Q3)."""
     xs_mask = pad_mask(xlens, xs.size(1))
     ys_in, ys_mask = decoder_inputs(ys, ylens, cfg.vocab_size)
-    h_enc = encoder(sd, cfg, xs, xs_mask, training, bn_out)
+    h_enc = encoder(sd, cfg, xs, xs_mask, training, bn_out, dp)
     dec_mask = ys_mask.unsqueeze(1) | causal_mask(ys_mask.size(1)).unsqueeze(0)
-    h_attn = decoder(sd, cfg, ys_in, dec_mask, h_enc, xs_mask)
-    h_ctc = dense(sd, "ctc.ctc_lo", h_enc)
+    h_attn = decoder(sd, cfg, ys_in, dec_mask, h_enc, xs_mask, dp)
+    h_in = h_enc if dp is None else dp(h_enc, NET_CTC, GLOBAL_LAYER, CTC_IN, dp.r.dropout_rate, always=True)
+    h_ctc = dense(sd, "ctc.ctc_lo", h_in)
     return h_attn, h_ctc, h_enc
 
 
@@ -451,9 +522,9 @@ def label_smoothing_kl(h_attn: Tensor, tgt: Tensor, smoothing: float) -> Tensor:
 
 
 def hybrid_loss(sd: SD, cfg: U2Shape, xs, xlens, ys, ylens, ctc_weight: float, smoothing: float,
-                training: bool = True, bn_out=None):
+                training: bool = True, bn_out=None, dp=None):
     """criterions/hybrid_ctc_attn.py:39-79 -> dict(loss, loss_ctc, loss_attn, h_attn, h_ctc, h_enc)."""
-    h_attn, h_ctc, h_enc = u2_forward(sd, cfg, xs, xlens, ys, ylens, training, bn_out)
+    h_attn, h_ctc, h_enc = u2_forward(sd, cfg, xs, xlens, ys, ylens, training, bn_out, dp)
     b = ys.size(0)
     loss_attn = label_smoothing_kl(h_attn, attention_targets(ys, ylens, cfg.vocab_size), smoothing) / b
     lp = torch.log_softmax(h_ctc.transpose(0, 1), dim=-1)

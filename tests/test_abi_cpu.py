@@ -41,7 +41,7 @@ def test_gemm_args_ctypes_layout_matches_the_header():
     body = re.search(r"typedef struct lasr_gemm_args \{(.*?)\} lasr_gemm_args;", src, flags=re.S).group(1)
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     ctype_of = {"const void*": ctypes.c_void_p, "void*": ctypes.c_void_p, "const float*": ctypes.c_void_p, "float*": ctypes.c_void_p,
-                "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "float": ctypes.c_float}
+                "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "float": ctypes.c_float, "uint32_t": ctypes.c_uint32}
     header = []
     for decl in body.split(";"):
         decl = " ".join(decl.split())

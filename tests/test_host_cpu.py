@@ -43,10 +43,25 @@ def test_state_dict_schema_matches_reference_keys():
 
 def test_unsupported_configs_fail_loudly():
     from liteasr_b200.models.u2 import U2, U2Config
-    with pytest.raises(NotImplementedError):
-        U2(U2Config(input_dim=80, vocab_size=50, dropout_rate=0.1))
+    with pytest.raises(ValueError):
+        U2(U2Config(input_dim=80, vocab_size=50, enc_layers=1, dec_layers=1, dropout_rate=1.0))
     with pytest.raises(NotImplementedError):
         U2(U2Config(input_dim=80, vocab_size=50, use_rel=False))
+
+
+def test_reference_yaml_dropout_rates_construct_and_interpolate():
+    """config/model/my_U2.yaml: dropout_rate 0.1, every ${model...} rate follows it, the three attention rates are 0.0."""
+    from liteasr_b200.dropout import has_dropout
+    from liteasr_b200.models.u2 import U2, U2Config
+    m = U2(U2Config(input_dim=80, vocab_size=50, enc_layers=1, dec_layers=1, dropout_rate=0.1, enc_attn_dropout_rate=0.0,
+                    dec_self_attn_dropout_rate=0.0, dec_src_attn_dropout_rate=0.0))
+    e, d = m.encoder.enc_layers[0], m.decoder.dec_layers[0]
+    assert (e.dropout_rate, e.feed_forward.dropout_rate, e.feed_forward_macaron.dropout_rate, e.self_attn.dropout_rate) == (0.1, 0.1, 0.1, 0.0)
+    assert (d.dropout_rate, d.feed_forward.dropout_rate, d.self_attn.dropout_rate, d.src_attn.dropout_rate) == (0.1, 0.1, 0.0, 0.0)
+    assert m.encoder.pe.dropout_rate == 0.1 and m.decoder.pe.dropout_rate == 0.1 and m.ctc.dropout_rate == 0.1
+    assert has_dropout(m) and has_dropout(m.ctc)
+    m0 = U2(U2Config(input_dim=80, vocab_size=50, enc_layers=1, dec_layers=1))
+    assert not has_dropout(m0)
 
 
 def test_cpu_forward_fails_loudly():

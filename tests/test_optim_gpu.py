@@ -88,8 +88,8 @@ def test_clip_adam_step_matches_torch(variant):
         assert upd > 1e-4 or nan or i == 0
         assert err <= 1e-5 * upd + 2.4e-7, (variant, i, err, upd)
     assert ref.skipped == 1
-    assert torch.allclose(m, torch.cat([ref.opt.state[q]["exp_avg"].reshape(-1) for q in ref.params]), rtol=1e-5, atol=1e-9)
-    assert torch.allclose(v, torch.cat([ref.opt.state[q]["exp_avg_sq"].reshape(-1) for q in ref.params]), rtol=1e-5, atol=1e-12)
+    assert torch.allclose(m, torch.cat([ref.opt.state[q]["exp_avg"].reshape(-1) for q in ref.params]), rtol=1e-4, atol=1e-9)
+    assert torch.allclose(v, torch.cat([ref.opt.state[q]["exp_avg_sq"].reshape(-1) for q in ref.params]), rtol=1e-4, atol=1e-12)
 
 
 def test_fused_noam_through_the_store_matches_reference_tail():

@@ -144,3 +144,23 @@ def test_log_add_and_prefix_search_small_known_answer():
     assert math.isclose(math.exp(hyps[(2,)]), 0.12, rel_tol=1e-12)
     assert math.isclose(O.log_add([math.log(0.25), math.log(0.75)]), 0.0, abs_tol=1e-15)
     assert O.log_add([-float("inf"), -float("inf")]) == -float("inf")
+
+
+def test_dropout_placement_matches_the_unmodified_reference():
+    """tests/golden/u2_dropout_placement.json was produced by the UNMODIFIED reference with ``torch.nn.functional.dropout``
+    swapped for a call-order-deterministic stand-in (oracle/make_dropout_golden.py).  The oracle with the same call-order masks
+    must give the same loss, the same 30 dropout calls (shape and rate, in order) and the same gradients: sites, order, rates,
+    1/(1-p) scaling and the always-on CTC-head site (quirk Q3, eval record) are thereby pinned."""
+    import json
+    from oracle import make_dropout_golden as G
+    g = json.load(open(os.path.join(GOLDEN, "u2_dropout_placement.json")))
+    assert g["rates"] == G.RATES and g["dims"] == G.DIMS.__dict__ and g["base"] == G.BASE
+    tr = G.run_oracle(True)
+    assert tr["calls"] == g["train"]["calls"] and len(tr["calls"]) == 30
+    assert math.isclose(tr["loss"], g["train"]["loss"], rel_tol=1e-12)
+    for k, v in g["train"]["grad_l2"].items():
+        assert math.isclose(tr["grad_l2"][k], v, rel_tol=1e-9, abs_tol=1e-12), k
+        assert math.isclose(tr["grad_sum"][k], g["train"]["grad_sum"][k], rel_tol=1e-7, abs_tol=1e-10), k
+    ev = G.run_oracle(False)
+    assert ev["calls"] == g["eval"]["calls"] == [[[3, 18, 64], 0.11]]   # eval(): only F.dropout of nets/ctc.py:29 is live
+    assert math.isclose(ev["loss"], g["eval"]["loss"], rel_tol=1e-12)

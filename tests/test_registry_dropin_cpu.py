@@ -99,7 +99,7 @@ print("DROPIN-OK")
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/liteasr/nets"), reason="reference tree not present (GPU box)")
-@pytest.mark.parametrize("dropout", [0.0])
+@pytest.mark.parametrize("dropout", [0.1])
 def test_integration_md_section1_against_unmodified_reference_registry(dropout):
     src = f"ROOT = {ROOT!r}\nDROPOUT = {dropout!r}\n" + textwrap.dedent(SCRIPT)
     r = subprocess.run([sys.executable, "-c", src], capture_output=True, text=True, timeout=600, cwd=ROOT)
