@@ -37,6 +37,7 @@ extern "C" {
 #define LASR_ACT_NONE 0
 #define LASR_ACT_RELU 1
 #define LASR_ACT_SWISH 2
+#define LASR_ACT_MUL 3 /* only with `dact`: the saved tensor IS the factor (C = alpha * (A.B^T) * dact), see aux_deriv */
 
 int lasr_version(void);             /* 100 * major + minor */
 int lasr_arch(void);                /* 100 (sm_100a) */
@@ -116,9 +117,30 @@ typedef struct lasr_gemm_args {
     uint32_t drop_thr;
     float drop_scale;
     int32_t drop_mark_aux;
+    /* aux_deriv = 1 (act = swish, aux set): `aux` receives act'(A.B^T + bias) -- the DERIVATIVE of the activation at the
+     * pre-activation -- instead of the pre-activation itself, and 0 at elements dropped by drop_mark_aux.  The backward GEMM then
+     * runs with dact = aux, act = LASR_ACT_MUL: one multiply per element instead of re-evaluating swish'() (tanh + 6 flops) in an
+     * epilogue that is instruction-bound (nets/feed_forward.py:18-19 backward), and lasr_ffn_bwd consumes the same tensor. */
+    int32_t aux_deriv;
 } lasr_gemm_args;
 
 int lasr_gemm(const lasr_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused backward of the two inner GEMMs of a position-wise feed-forward block (nets/feed_forward.py:18-19 backward; the
+ * encoder runs the block twice per Conformer layer, nets/conformer_layer.py:37-47,58-66), bf16 / tcgen05:
+ *     dh  (M, f) = alpha * (dy (M, d) . W2 (d, f)) * g (M, f)      W2 = fc2.weight, g = act'(fc1 pre-activation) saved by the
+ *                                                                 forward GEMM (aux_deriv; 0 where the inner dropout dropped)
+ *     colsum (f) += sum_rows dh                                    fc1's bias gradient (optional)
+ *     dln (M, d) = dh . W1 (f, d)                                  W1 = fc1.weight
+ * One persistent kernel: a 128-row tile of dh exists only as 64-column chunks that go TMEM -> registers -> a shared-memory slab
+ * that is both the A operand of the second MMA and the source of the bulk tensor store of dh (kept for the fc1 weight-gradient
+ * GEMM).  Replaces lasr_gemm(dact) + lasr_gemm for d % 64 == 0, 64 <= d <= 256, f % 64 == 0 (lasr_ffn_bwd_supported); other
+ * shapes return LASR_ERR_UNSUPPORTED.  All matrices row-major with 16-byte aligned bases and row strides.
+ * ------------------------------------------------------------------------------------------------ */
+int lasr_ffn_bwd_supported(int d, int f);
+int lasr_ffn_bwd(const void* dy, int64_t lddy, const void* g, int64_t ldg, const void* w2, int64_t ldw2, const void* w1, int64_t ldw1,
+                 void* dh, int64_t lddh, void* dln, int64_t lddln, float* colsum, float alpha, int M, int d, int f, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * CTC forward-backward fused with the log-softmax backward.

@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("LASR_LIB_PATH") or os.path.join(_HERE, "liblasr.so") 
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "lasr.h")
 
 F32, BF16 = 0, 1
-ACT_NONE, ACT_RELU, ACT_SWISH = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_SWISH, ACT_MUL = 0, 1, 2, 3
 
 
 class GemmArgs(C.Structure):
@@ -30,7 +30,7 @@ class GemmArgs(C.Structure):
         ("n_store", C.c_int32),
         ("a2", C.c_void_p), ("b2", C.c_void_p), ("bias2", C.c_void_p), ("lda2", C.c_int64), ("ldb2", C.c_int64), ("k2", C.c_int32),
         ("drop_state", C.c_void_p), ("drop_site", C.c_uint32), ("drop_thr", C.c_uint32), ("drop_scale", C.c_float),
-        ("drop_mark_aux", C.c_int32),
+        ("drop_mark_aux", C.c_int32), ("aux_deriv", C.c_int32),
     ]
 
 

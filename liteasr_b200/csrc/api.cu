@@ -49,8 +49,11 @@ int lasr_gemm(const lasr_gemm_args* a, void* stream) {
         LASR_REQUIRE(a->c_dtype == LASR_F32 && !a->bias && !a->res && !a->aux && !a->dact && !a->colsum && a->act == LASR_ACT_NONE,
                      "gemm: accumulate needs fp32 C and no epilogue");
     if (a->dact)
-        LASR_REQUIRE(!a->bias && !a->res && !a->aux && (a->act == LASR_ACT_SWISH || a->act == LASR_ACT_RELU) && a->lddact > 0,
-                     "gemm: dact needs act = swish|relu and no bias/res/aux");
+        LASR_REQUIRE(!a->bias && !a->res && !a->aux && (a->act == LASR_ACT_SWISH || a->act == LASR_ACT_RELU || a->act == LASR_ACT_MUL) && a->lddact > 0,
+                     "gemm: dact needs act = swish|relu|mul and no bias/res/aux");
+    else
+        LASR_REQUIRE(a->act != LASR_ACT_MUL, "gemm: act = mul needs dact");
+    if (a->aux_deriv) LASR_REQUIRE(a->aux && a->act == LASR_ACT_SWISH && !a->a2, "gemm: aux_deriv needs aux and act = swish");
     if (a->a2)
         LASR_REQUIRE(a->b2 && a->ab_dtype == LASR_BF16 && a->c_dtype == LASR_BF16 && !a->bias && !a->res && !a->aux && !a->dact &&
                          !a->accumulate && !a->n_store && a->batch1 == 1 && a->batch2 == 1 && !a->trans_a && a->k2 > 0 &&

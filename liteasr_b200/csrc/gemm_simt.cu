@@ -31,6 +31,7 @@ struct SimtParams {
     int n_store;
     DropCfg drop;
     int drop_mark;
+    int aux_deriv;
 };
 
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams p) {
@@ -108,10 +109,13 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams p) {
             const bool keep = (keep4 >> j) & 1u;
             if (p.dact) {
                 const float sv = p.dact[boff + (long)m * p.lddact + n];
-                v *= p.alpha * (p.act == LASR_ACT_SWISH ? dswishf_(sv) : (sv > 0.f ? 1.f : 0.f));
+                v *= p.alpha * (p.act == LASR_ACT_SWISH ? dswishf_(sv) : (p.act == LASR_ACT_MUL ? sv : (sv > 0.f ? 1.f : 0.f)));
             } else {
                 if (p.bias) v += p.bias[n];
-                if (p.aux) p.aux[off] = (keep || !p.drop_mark) ? v : LASR_DROP_MARK;
+                if (p.aux) {
+                    if (p.aux_deriv) p.aux[off] = (keep || !p.drop_mark) ? dswishf_(v) : 0.f;   // act'(pre-activation); 0 where dropped
+                    else p.aux[off] = (keep || !p.drop_mark) ? v : LASR_DROP_MARK;
+                }
                 v = p.alpha * apply_act(v, p.act);
                 if (drop_on) v = keep ? v * dk.scale : 0.f;
                 if (p.res) v += p.res[boff + (long)m * p.ldres + n];
@@ -143,6 +147,7 @@ int gemm_simt_dispatch(const lasr_gemm_args* a, cudaStream_t st) {
     p.dact = (const float*)a->dact; p.lddact = a->lddact; p.colsum = a->colsum; p.cs1 = a->cs1; p.cs2 = a->cs2;
     p.drop.state = (const unsigned long long*)a->drop_state; p.drop.site = a->drop_site; p.drop.thr = a->drop_thr; p.drop.scale = a->drop_scale;
     p.drop_mark = a->drop_mark_aux;
+    p.aux_deriv = a->aux_deriv;
     dim3 grid(ceil_div(a->m, SBM), ceil_div(p.n_store, SBN), a->batch1 * a->batch2 * p.split_k);
     gemm_simt_kernel<<<grid, 256, 0, st>>>(p);
     return check_launch("gemm_simt");

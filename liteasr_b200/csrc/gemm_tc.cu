@@ -87,7 +87,8 @@ struct TcParams {
     int conv_plane[9]; // parity plane of the tap: (kh & 1) * 2 + (kw & 1)
     int conv_tap[9];   // tap id kh * 3 + kw (column block of the (co, tap, ci) weight)
     DropCfg drop;      // dropout on the output (philox.cuh); thr = 0: off
-    int drop_mark;     // dropped elements of aux receive LASR_DROP_MARK
+    int drop_mark;     // dropped elements of aux receive LASR_DROP_MARK (0 with aux_deriv)
+    int aux_deriv;     // aux = act'(pre-activation) instead of the pre-activation (Swish)
 };
 
 
@@ -141,9 +142,18 @@ __device__ __forceinline__ float dswish_scaled(float x, float half_scale) {
     return (2.f * half_scale) * (r * fmaf(x, 1.f - r, 1.f));
 }
 __device__ __forceinline__ float dswish_fast(float x) { return dswish_scaled(x, 0.5f); }
+// a = swish(x) and g = swish'(x) from ONE tanh: with h = x/2, t = tanh(h):  a = h + h t,  g = (1 + t + h (1 - t^2)) / 2
+__device__ __forceinline__ void swish_and_deriv(float x, float& a, float& g) {
+    const float h = 0.5f * x;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    a = fmaf(h, t, h);
+    g = fmaf(fmaf(h, fmaf(-t, t, 1.f), t), 0.5f, 0.5f);
+}
 __device__ __forceinline__ float dact_fast(float saved, int act) {
     if (act == LASR_ACT_RELU) return saved > 0.f ? 1.f : 0.f;
     if (act == LASR_ACT_SWISH) return dswish_fast(saved);
+    if (act == LASR_ACT_MUL) return saved;
     return 1.f;
 }
 __device__ __forceinline__ float act_fast(float x, int act) {
@@ -168,7 +178,8 @@ __device__ __forceinline__ void store4(CT* dst, const float4& f) {
 
 // Epilogue modes: the column phase is specialised so that its inner loop carries no run-time flag tests.
 enum { EPI_PLAIN = 0, EPI_RELU = 1, EPI_SWISH = 2, EPI_RES = 3, EPI_ACC = 4, EPI_GENERIC = 5, EPI_DSWISH = 6, EPI_DRELU = 7,
-       EPI_DUAL_DSWISH = 8, EPI_DUAL_DRELU = 9 };  // DUAL: act'(.) of a pre-activation recomputed into a second accumulator
+       EPI_DUAL_DSWISH = 8, EPI_DUAL_DRELU = 9,  // DUAL: act'(.) of a pre-activation recomputed into a second accumulator
+       EPI_DMUL = 10 };                          // C = alpha * acc * saved factor (the forward pass saved act'() itself: aux_deriv)
 
 // CW = staged chunk width in fp32 columns (32, or 16 in the B-stationary kernels).  The staging buffer holds 32 rows x CW
 // columns; a row is PIECES = CW/4 16-byte pieces, XOR-swizzled so that both the row-per-thread writes and the row-contiguous
@@ -191,7 +202,7 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, const Unit& w, 
     const float* rbase = p.res ? p.res + boff : nullptr;
     const bf16* dbase = p.dact ? p.dact + boff : nullptr;
     float* csbase = p.colsum ? p.colsum + (long)w.b1 * p.cs1 + (long)w.b2 * p.cs2 : nullptr;
-    constexpr bool DACT = (MODE == EPI_DSWISH || MODE == EPI_DRELU);
+    constexpr bool DACT = (MODE == EPI_DSWISH || MODE == EPI_DRELU || MODE == EPI_DMUL);
     uint8_t* wr = stage + lane * ROWB;
     const int wx = (CW == 32) ? ((lane & 7) << 4) : (((lane >> 1) & 3) << 4);
     // CW = 32: rows 4i + rsub alternate between two swizzle phases (i even / odd); CW = 16: rows 8i + rsub share one
@@ -292,6 +303,9 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, const Unit& w, 
                             const float ha = 0.5f * alpha;
                             f.x *= dswish_scaled(__low2float(h0), ha); f.y *= dswish_scaled(__high2float(h0), ha);
                             f.z *= dswish_scaled(__low2float(h1), ha); f.w *= dswish_scaled(__high2float(h1), ha);
+                        } else if constexpr (MODE == EPI_DMUL) {
+                            f.x *= alpha * __low2float(h0); f.y *= alpha * __high2float(h0);
+                            f.z *= alpha * __low2float(h1); f.w *= alpha * __high2float(h1);
                         } else {
                             f.x = __low2float(h0) > 0.f ? alpha * f.x : 0.f; f.y = __high2float(h0) > 0.f ? alpha * f.y : 0.f;
                             f.z = __low2float(h1) > 0.f ? alpha * f.z : 0.f; f.w = __high2float(h1) > 0.f ? alpha * f.w : 0.f;
@@ -315,7 +329,8 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, const Unit& w, 
                         red_add_f32x4(reinterpret_cast<float*>(crow), f);
                     } else {  // EPI_RELU / EPI_SWISH (+ optional pre-activation copy)
                         f.x += b4.x; f.y += b4.y; f.z += b4.z; f.w += b4.w;
-                        if (has_aux) {
+                        const bool deriv = MODE == EPI_SWISH && p.aux_deriv != 0;  // warp-uniform
+                        if (has_aux && !deriv) {
                             float4 h = f;
                             if (drop_on && p.drop_mark) {
                                 h.x = (keep4 & 1u) ? h.x : LASR_DROP_MARK; h.y = (keep4 & 2u) ? h.y : LASR_DROP_MARK;
@@ -325,6 +340,15 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, const Unit& w, 
                         }
                         if constexpr (MODE == EPI_RELU) {
                             f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f);
+                        } else if (deriv) {
+                            float4 gq;
+                            swish_and_deriv(f.x, f.x, gq.x); swish_and_deriv(f.y, f.y, gq.y);
+                            swish_and_deriv(f.z, f.z, gq.z); swish_and_deriv(f.w, f.w, gq.w);
+                            if (drop_on && p.drop_mark) {
+                                gq.x = (keep4 & 1u) ? gq.x : 0.f; gq.y = (keep4 & 2u) ? gq.y : 0.f;
+                                gq.z = (keep4 & 4u) ? gq.z : 0.f; gq.w = (keep4 & 8u) ? gq.w : 0.f;
+                            }
+                            if (has_aux) store4<CT>(abase + off, gq);
                         } else {
                             f.x = swish_fast(f.x); f.y = swish_fast(f.y); f.z = swish_fast(f.z); f.w = swish_fast(f.w);
                         }
@@ -366,7 +390,10 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, const Unit& w, 
                             x = alpha * f[e] * dact_fast(__bfloat162float(dbase[(long)grow * p.lddact + col + e]), p.act);
                         } else {
                             const bool keep = !drop_on || drop_keep1(dk, (uint32_t)grow, (uint32_t)(col + e));
-                            if (abase) abase[off] = from_f32<CT>((keep || !p.drop_mark) ? f[e] : LASR_DROP_MARK);
+                            if (abase) {
+                                if (p.aux_deriv) abase[off] = from_f32<CT>((keep || !p.drop_mark) ? dswish_fast(f[e]) : 0.f);
+                                else abase[off] = from_f32<CT>((keep || !p.drop_mark) ? f[e] : LASR_DROP_MARK);
+                            }
                             x = alpha * act_fast(f[e], p.act);
                             if (drop_on) x = keep ? x * dk.scale : 0.f;
                             if (rbase) x += rbase[(long)grow * p.ldres + col + e];
@@ -409,7 +436,7 @@ template <typename CT, int MODE, bool DROP>
 __device__ __forceinline__ void epilogue_unit_tma(const TcParams& p, const Unit& w, uint32_t tmem_acc, uint8_t* stage, int q, int part,
                                                   int lane, const CUtensorMap* mc, const CUtensorMap* mx, int& buf) {
     constexpr bool BF = sizeof(CT) == 2;
-    constexpr bool DACT = (MODE == EPI_DSWISH || MODE == EPI_DRELU);
+    constexpr bool DACT = (MODE == EPI_DSWISH || MODE == EPI_DRELU || MODE == EPI_DMUL);
     const long boff = (long)w.b1 * p.sc1 + (long)w.b2 * p.sc2;
     const int col_limit = min(p.n_store, w.n0 + p.bn);
     const int row0 = w.m0 + q * 32, row = row0 + lane;
@@ -475,6 +502,9 @@ __device__ __forceinline__ void epilogue_unit_tma(const TcParams& p, const Unit&
                     if constexpr (MODE == EPI_DSWISH) {
                         v[8 * j + 2 * e] *= dswish_scaled(a0, 0.5f * alpha);
                         v[8 * j + 2 * e + 1] *= dswish_scaled(a1, 0.5f * alpha);
+                    } else if constexpr (MODE == EPI_DMUL) {
+                        v[8 * j + 2 * e] *= alpha * a0;
+                        v[8 * j + 2 * e + 1] *= alpha * a1;
                     } else {
                         v[8 * j + 2 * e] = a0 > 0.f ? alpha * v[8 * j + 2 * e] : 0.f;
                         v[8 * j + 2 * e + 1] = a1 > 0.f ? alpha * v[8 * j + 2 * e + 1] : 0.f;
@@ -519,7 +549,24 @@ __device__ __forceinline__ void epilogue_unit_tma(const TcParams& p, const Unit&
         }
         __syncwarp();
         if constexpr (MODE == EPI_RELU || MODE == EPI_SWISH) {
-            if (has_aux) {  // pre-activation copy (bf16 on this path); dropped elements carry the marker whose act'() is 0
+            const bool deriv = MODE == EPI_SWISH && has_aux && p.aux_deriv != 0;  // warp-uniform
+            if (deriv) {  // aux = swish'(h) (0 where dropped) and v = swish(h), 8 columns at a time (one tanh serves both)
+                uint8_t* sx = stage + 2048;
+                const uint32_t hk = (drop_on && p.drop_mark) ? keep : 0xffffffffu;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float gq[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        swish_and_deriv(v[8 * j + e], v[8 * j + e], gq[e]);
+                        gq[e] = ((hk >> (8 * j + e)) & 1u) ? gq[e] : 0.f;
+                    }
+                    uint4 u;
+                    u.x = pack_bf16x2(gq[0], gq[1]); u.y = pack_bf16x2(gq[2], gq[3]);
+                    u.z = pack_bf16x2(gq[4], gq[5]); u.w = pack_bf16x2(gq[6], gq[7]);
+                    *reinterpret_cast<uint4*>(sx + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = u;
+                }
+            } else if (has_aux) {  // pre-activation copy (bf16 on this path); dropped elements carry the marker whose act'() is 0
                 uint8_t* sx = stage + 2048;
                 const uint32_t hk = (drop_on && p.drop_mark) ? keep : 0xffffffffu;
 #pragma unroll
@@ -534,8 +581,10 @@ __device__ __forceinline__ void epilogue_unit_tma(const TcParams& p, const Unit&
                 }
             }
             const bool unit_alpha = alpha == 1.f;
+            if (!deriv) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = (MODE == EPI_RELU) ? fmaxf(v[j], 0.f) : swish_fast(v[j]);
+                for (int j = 0; j < 32; ++j) v[j] = (MODE == EPI_RELU) ? fmaxf(v[j], 0.f) : swish_fast(v[j]);
+            }
             if (!unit_alpha) {  // warp-uniform: no multiply on the alpha == 1 path (every FFN fc1)
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] *= alpha;
@@ -918,7 +967,7 @@ static void setup_tma_epilogue(TcParams& p, CUtensorMap* mc, CUtensorMap* mx, in
     // 31-shuffle transpose: measured slower than the column-phase epilogue (fc2 + residual 62 vs 51 us, dswish + colsum 128 vs
     // 103 us at C2/B=126), so those modes keep it.  LASR_GEMM_TMA_EPI=2 forces the TMA path for every mode (tests).
     const bool force = env && atoi(env) == 2;
-    if (!force && (p.epi_mode == EPI_RES || p.epi_mode == EPI_DSWISH || p.epi_mode == EPI_DRELU || p.colsum)) return;
+    if (!force && (p.epi_mode == EPI_RES || p.epi_mode == EPI_DSWISH || p.epi_mode == EPI_DRELU || p.epi_mode == EPI_DMUL || p.colsum)) return;
     // bulk tensor stores clip at 16-byte granularity (measured: tools/tma_clip_probe.py): a row whose last 16-byte chunk is
     // partial would get zeros written past column n_store, so ragged widths keep the register epilogue
     if (((long)p.n_store * (p.c_dtype == LASR_F32 ? 4 : 2)) & 15) return;
@@ -969,6 +1018,7 @@ static TcKernel pick_kernel(int mode, bool f32) {
             case EPI_ACC: return configured_kernel<EPI_ACC, true, BS>();
             case EPI_DSWISH: return configured_kernel<EPI_DSWISH, true, BS>();
             case EPI_DRELU: return configured_kernel<EPI_DRELU, true, BS>();
+            case EPI_DMUL: return configured_kernel<EPI_DMUL, true, BS>();
             default: return configured_kernel<EPI_GENERIC, true, BS>();
         }
     }
@@ -978,6 +1028,7 @@ static TcKernel pick_kernel(int mode, bool f32) {
         case EPI_SWISH: return configured_kernel<EPI_SWISH, false, BS>();
         case EPI_DSWISH: return configured_kernel<EPI_DSWISH, false, BS>();
         case EPI_DRELU: return configured_kernel<EPI_DRELU, false, BS>();
+        case EPI_DMUL: return configured_kernel<EPI_DMUL, false, BS>();
         case EPI_DUAL_DSWISH: return BS ? nullptr : configured_kernel<EPI_DUAL_DSWISH, false, false>();
         case EPI_DUAL_DRELU: return BS ? nullptr : configured_kernel<EPI_DUAL_DRELU, false, false>();
         default: return configured_kernel<EPI_GENERIC, false, BS>();
@@ -1008,7 +1059,7 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtenso
     const bool f32 = p.c_dtype == LASR_F32;
     TcKernel kern;
     if (p.drop.thr != 0) {
-        if (p.b_stationary || p.dual || p.epi_mode == EPI_ACC || p.epi_mode == EPI_DSWISH || p.epi_mode == EPI_DRELU) {
+        if (p.b_stationary || p.dual || p.epi_mode == EPI_ACC || p.epi_mode == EPI_DSWISH || p.epi_mode == EPI_DRELU || p.epi_mode == EPI_DMUL) {
             set_error("gemm_tc: dropout is not available with this epilogue");
             return LASR_ERR_UNSUPPORTED;
         }
@@ -1085,10 +1136,12 @@ int gemm_tc_dispatch(const lasr_gemm_args* a, cudaStream_t st) {
     p.drop.state = reinterpret_cast<const unsigned long long*>(a->drop_state);
     p.drop.site = a->drop_site; p.drop.thr = a->drop_thr; p.drop.scale = a->drop_scale;
     p.drop_mark = a->drop_mark_aux;
+    p.aux_deriv = a->aux_deriv;
     if (a->a2) p.epi_mode = a->act == LASR_ACT_SWISH ? EPI_DUAL_DSWISH : EPI_DUAL_DRELU;
     else if (a->accumulate) p.epi_mode = EPI_ACC;
     else if (a->dact && a->act == LASR_ACT_SWISH) p.epi_mode = EPI_DSWISH;
     else if (a->dact && a->act == LASR_ACT_RELU) p.epi_mode = EPI_DRELU;
+    else if (a->dact && a->act == LASR_ACT_MUL) p.epi_mode = EPI_DMUL;
     else if (a->colsum && (a->res || a->aux || a->act != LASR_ACT_NONE)) p.epi_mode = EPI_GENERIC;
     else if (a->res && a->act == LASR_ACT_NONE && !a->aux) p.epi_mode = EPI_RES;
     else if (!a->res && a->act == LASR_ACT_RELU) p.epi_mode = EPI_RELU;

@@ -23,7 +23,7 @@ import torch
 
 from . import dropout as DR
 from . import ops
-from .ops import ACT_NONE, ACT_RELU, ACT_SWISH
+from .ops import ACT_MUL, ACT_NONE, ACT_RELU, ACT_SWISH
 from .store import ParamStore
 
 LN_EPS = 1e-12
@@ -55,6 +55,8 @@ class Engine:
         # SLOWER (32.0 vs 30.7 ms per step): two accumulators force 128-column N tiles, and at K = 256 the four operand slabs of a
         # tile (256 KB for a 128 x 128 output) make the GEMM L2 -> shared-memory bound (1.2 GB per launch against 0.45 GB).
         self.ffn_recompute = store.adt == torch.bfloat16 and os.environ.get("LASR_FFN_RECOMPUTE", "0") == "1"
+        # LASR_FUSED_FFN=0: developer switch back to the two separate backward GEMMs of a feed-forward block (csrc/ffn_fused.cu)
+        self.fused_ffn = store.adt == torch.bfloat16 and os.environ.get("LASR_FUSED_FFN", "1") != "0"
 
     # ------------------------------------------------------------------------------------------
     # small helpers
@@ -115,7 +117,7 @@ class Engine:
         return s
 
     def linear(self, x, wname, out_dtype, *, bias=True, act=ACT_NONE, res=None, alpha=1.0, aux=False, w=None, n=None,
-               bias_t=None, drop=None, drop_mark_aux=False):
+               bias_t=None, drop=None, drop_mark_aux=False, aux_deriv=False):
         """y = drop(alpha * act(x @ W^T + b)) (+ res).  W (N,K) from the store (or ``w``)."""
         w = self.st.w(wname + ".weight") if w is None else w
         n = w.shape[0] if n is None else n
@@ -130,7 +132,7 @@ class Engine:
         b = bias_t if bias_t is not None else (self.st.p(wname + ".bias") if bias else None)
         ops.gemm(x, w, out, m, n, x.shape[1], lda=x.stride(0), ldb=w.stride(0), ldc=ld, bias=b, res=res,
                  ldres=(res.stride(0) if res is not None else 0), aux=auxbuf, alpha=alpha, act=act, drop=drop,
-                 drop_mark_aux=drop_mark_aux)
+                 drop_mark_aux=drop_mark_aux, aux_deriv=aux_deriv)
         return (out, auxbuf) if aux else out
 
     def wgrad(self, dy, x, gw, alpha=1.0) -> None:
@@ -170,13 +172,15 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     def ffn_fwd(self, x, pfx_norm, pfx_ff, act, scale, d_in=None, d_out=None) -> NS:
         """d_in: dropout on the activation (feed_forward.py:19); d_out: dropout on the block output before the residual add
-        (conformer_layer.py:42,63, transformer_layer.py:58).  The inner mask is not regenerated in backward: the dropped
-        elements of the saved pre-activation carry a marker whose Swish' is 0 (Swish), or the saved output is 0 there (ReLU)."""
+        (conformer_layer.py:42,63, transformer_layer.py:58).  Swish: what fc1 saves for the backward pass is ``g = swish'(h)``
+        (``aux_deriv``), not the pre-activation ``h``: the backward epilogue then multiplies by ``g`` instead of re-evaluating
+        swish' (it is instruction-bound), and the inner dropout mask needs no regeneration either -- ``g`` is 0 at dropped
+        elements (ReLU: the saved output is 0 there)."""
         ln = self.layernorm(x, pfx_norm, self.adt)
         if act == ACT_SWISH and d_in is not None and self.ffn_recompute:
             raise NotImplementedError("LASR_FFN_RECOMPUTE=1 cannot be combined with FFN dropout (the mask lives in the saved pre-activation)")
         if act == ACT_SWISH and not self.ffn_recompute:
-            a, h = self.linear(ln.y, pfx_ff + ".fc1", self.adt, act=act, aux=True, drop=d_in, drop_mark_aux=True)
+            a, h = self.linear(ln.y, pfx_ff + ".fc1", self.adt, act=act, aux=True, drop=d_in, drop_mark_aux=True, aux_deriv=True)
         else:  # ReLU: act'(.) from the output; Swish in bf16 mode: the pre-activation is recomputed in the backward GEMM
             a, h = self.linear(ln.y, pfx_ff + ".fc1", self.adt, act=act, drop=d_in), None
         out = self.linear(a, pfx_ff + ".fc2", torch.float32, res=x, alpha=scale, drop=d_out)
@@ -195,9 +199,19 @@ class Engine:
             # written by the forward pass and read back: 154 MB less written and 135 MB less read per FFN at C2/B=126
             dh = self.dgrad(dy, st.w(c.pfx + ".fc2.weight"), alpha=c.scale, act=c.act, colsum=st.g(c.pfx + ".fc1.bias"),
                             recompute=(c.ln.y, st.w(c.pfx + ".fc1.weight"), st.p(c.pfx + ".fc1.bias")))
+        elif (c.act == ACT_SWISH and self.fused_ffn and ops.ffn_bwd_supported(dy.shape[1], c.h.shape[1]) and c.h.stride(0) % 8 == 0
+              and dy.stride(0) % 8 == 0):
+            # ONE kernel: dh = s (dy @ W2) * g, db1 += colsum(dh), dln = dh @ W1 -- dh is written once (the fc1 weight gradient
+            # needs it) and never read back by the second contraction
+            dh = _empty(c.h.shape, self.adt, self.dev)
+            dln = _empty(dy.shape, self.adt, self.dev)
+            ops.ffn_bwd(dy, c.h, st.w(c.pfx + ".fc2.weight"), st.w(c.pfx + ".fc1.weight"), dh, dln, colsum=st.g(c.pfx + ".fc1.bias"),
+                        alpha=s_in)
+            self.wgrad(dh, c.ln.y, st.gw(c.pfx + ".fc1.weight"))
+            return self.layernorm_bwd(c.ln, dln, dres, True, nxt, want_lo)
         else:
-            dh = self.dgrad(dy, st.w(c.pfx + ".fc2.weight"), alpha=s_in, dact=(c.h if c.act == ACT_SWISH else c.a), act=c.act,
-                            colsum=st.g(c.pfx + ".fc1.bias"))
+            dh = self.dgrad(dy, st.w(c.pfx + ".fc2.weight"), alpha=s_in, dact=(c.h if c.act == ACT_SWISH else c.a),
+                            act=(ACT_MUL if c.act == ACT_SWISH else c.act), colsum=st.g(c.pfx + ".fc1.bias"))
         self.wgrad(dh, c.ln.y, st.gw(c.pfx + ".fc1.weight"))
         dln = self.dgrad(dh, st.w(c.pfx + ".fc1.weight"))
         return self.layernorm_bwd(c.ln, dln, dres, True, nxt, want_lo)

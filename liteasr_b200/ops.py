@@ -11,7 +11,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import ACT_NONE, ACT_RELU, ACT_SWISH, BF16, F32  # noqa: F401
+from ._lib import ACT_MUL, ACT_NONE, ACT_RELU, ACT_SWISH, BF16, F32  # noqa: F401
 
 _P = C.c_void_p
 
@@ -45,7 +45,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, m: int, n: int, k: i
          sb: Tuple[int, int] = (0, 0), sc: Tuple[int, int] = (0, 0), dact: Optional[torch.Tensor] = None,
          colsum: Optional[torch.Tensor] = None, cs: Tuple[int, int] = (0, 0), n_store: int = 0,
          recompute: Optional[Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]] = None,
-         drop=None, drop_mark_aux: bool = False) -> None:
+         drop=None, drop_mark_aux: bool = False, aux_deriv: bool = False) -> None:
     """C[b1,b2] = alpha * act(A.B^T + bias) (+ res); see include/lasr.h ``lasr_gemm``.  ``drop`` = ``Drop`` (dropout on the
     output before the residual add) or None."""
     _require_cuda(a, b, c, bias, res, aux, dact, colsum)
@@ -81,6 +81,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, m: int, n: int, k: i
     if drop is not None and drop.thr:
         g.drop_state, g.drop_site, g.drop_thr, g.drop_scale = drop.state.data_ptr(), drop.site, drop.thr, drop.scale
         g.drop_mark_aux = int(drop_mark_aux)
+    g.aux_deriv = int(aux_deriv)
     if dact is not None and (dact.dtype != a.dtype or dact.dim() != 2 or dact.stride(1) != 1):
         raise TypeError("dact must be a 2-D row-major tensor of the operand dtype")
     if colsum is not None and colsum.dtype != torch.float32:
@@ -102,6 +103,27 @@ def linear(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, re
     gemm(x, w, out, m, n, k, lda=x.stride(0), ldb=w.stride(0), ldc=out.stride(0), bias=bias, res=res,
          ldres=(res.stride(0) if res is not None else 0), aux=aux, alpha=alpha, act=act)
     return out
+
+
+def ffn_bwd_supported(d: int, f: int) -> bool:
+    return bool(_lib.lib().lasr_ffn_bwd_supported(C.c_int(d), C.c_int(f)))
+
+
+def ffn_bwd(dy, g, w2, w1, dh, dln, colsum=None, alpha: float = 1.0) -> None:
+    """dh = alpha * (dy @ w2) * g ; colsum += sum_rows dh ; dln = dh @ w1  (one fused tcgen05 kernel, include/lasr.h)."""
+    _require_cuda(dy, g, w2, w1, dh, dln, colsum)
+    for t in (dy, g, w2, w1, dh, dln):
+        if t.dtype != torch.bfloat16 or t.dim() != 2 or t.stride(1) != 1:
+            raise TypeError("ffn_bwd takes 2-D row-major bf16 tensors")
+    m, d = dy.shape
+    f = g.shape[1]
+    assert g.shape == (m, f) and w2.shape == (d, f) and w1.shape == (f, d) and dh.shape == (m, f) and dln.shape == (m, d)
+    if colsum is not None:
+        assert colsum.dtype == torch.float32 and colsum.numel() == f
+    _lib.check(_lib.lib().lasr_ffn_bwd(_ptr(dy), C.c_int64(dy.stride(0)), _ptr(g), C.c_int64(g.stride(0)), _ptr(w2), C.c_int64(w2.stride(0)),
+                                       _ptr(w1), C.c_int64(w1.stride(0)), _ptr(dh), C.c_int64(dh.stride(0)), _ptr(dln),
+                                       C.c_int64(dln.stride(0)), _ptr(colsum), C.c_float(alpha), C.c_int(m), C.c_int(d), C.c_int(f),
+                                       _stream()), "ffn_bwd")
 
 
 def ctc_workspace_bytes(T: int, B: int, lmax: int) -> int:

@@ -98,13 +98,13 @@ def test_gemm_epilogue_dropout_matches_reference_under_same_mask(dtype, m, n, k,
     if mode == "swish_aux":
         c = torch.empty(m, ld, device=DEV, dtype=lo)[:, :n]
         aux = torch.empty(m, ld, device=DEV, dtype=lo)[:, :n]
+        # (a) the pre-activation variant: dropped elements of the saved tensor carry the marker whose swish'() is exactly 0
         ops.gemm(x, w, c, m, n, k, lda=k, ldb=k, ldc=ld, bias=bias, aux=aux, act=2, drop=d, drop_mark_aux=True)
         h, a = _ref_linear(x, w, bias, 2, 1.0)
         want = torch.where(keep, a * d.scale, torch.zeros_like(a))
         assert (aux.float()[~keep] < -1e29).all(), "dropped elements of the saved pre-activation must carry the marker"
         tol = 2e-2 if dtype == torch.bfloat16 else 1e-5
         assert torch.allclose(aux.float()[keep], h[keep], rtol=tol, atol=tol)
-        # the activation-backward epilogue turns the marker into an exact zero (no mask regeneration in backward)
         dy = (torch.randn(m, k, generator=g, device=DEV) * 0.5).to(dtype)
         wt = (torch.randn(k, n, generator=g, device=DEV) * 0.1).to(dtype)   # W2 (K_in = n columns): dh = dy @ W2
         dh = torch.empty(m, ld, device=DEV, dtype=lo)[:, :n]
@@ -113,7 +113,20 @@ def test_gemm_epilogue_dropout_matches_reference_under_same_mask(dtype, m, n, k,
         hs = h[keep]
         sg = torch.sigmoid(hs)
         want_dh = (dy.float() @ wt.float())[keep] * (0.5 * d.scale) * (sg * (1 + hs * (1 - sg)))
-        assert torch.allclose(dh.float()[keep], want_dh, rtol=3e-2 if dtype == torch.bfloat16 else 1e-4, atol=3e-2 if dtype == torch.bfloat16 else 1e-5)
+        btol = 3e-2 if dtype == torch.bfloat16 else 1e-4
+        assert torch.allclose(dh.float()[keep], want_dh, rtol=btol, atol=btol * float(want_dh.abs().max()))
+        # (b) the derivative variant the engine uses (aux_deriv): aux = swish'(h), 0 where dropped; backward = one multiply
+        c2 = torch.empty(m, ld, device=DEV, dtype=lo)[:, :n]
+        aux2 = torch.empty(m, ld, device=DEV, dtype=lo)[:, :n]
+        ops.gemm(x, w, c2, m, n, k, lda=k, ldb=k, ldc=ld, bias=bias, aux=aux2, act=2, drop=d, drop_mark_aux=True, aux_deriv=True)
+        assert torch.equal(c2, c)
+        sga = torch.sigmoid(h)
+        assert (aux2.float()[~keep] == 0).all()
+        assert torch.allclose(aux2.float()[keep], (sga * (1 + h * (1 - sga)))[keep], rtol=tol, atol=tol)
+        dh2 = torch.empty(m, ld, device=DEV, dtype=lo)[:, :n]
+        ops.gemm(dy, wt, dh2, m, n, k, lda=k, ldb=n, ldc=ld, tb=True, alpha=0.5 * d.scale, dact=aux2, act=3)
+        assert (dh2.float()[~keep] == 0).all()
+        assert torch.allclose(dh2.float()[keep], want_dh, rtol=btol, atol=btol * float(want_dh.abs().max()))
     elif mode == "relu":
         c = torch.empty(m, ld, device=DEV, dtype=lo)[:, :n]
         ops.gemm(x, w, c, m, n, k, lda=k, ldb=k, ldc=ld, bias=bias, act=1, drop=d)
