@@ -273,7 +273,17 @@ def _record_gemms(step_fn, batch):
             fn(*args)
         return wrapped
 
+    ffn_orig = ops.ffn_bwd
+
+    def ffn_recorder(dy, g, w2, w1, dh, dln, **kw):  # the fused feed-forward backward: two contractions (2 x 2 m d f flops) in one kernel
+        m, d = dy.shape
+        f = g.shape[1]
+        byt = sum(t.numel() * t.element_size() for t in (dy, g, w2, w1, dh, dln))
+        rec.append((ffn_orig, (dy, g, w2, w1, dh, dln), kw, 4.0 * m * d * f, float(byt), d))
+        ffn_orig(dy, g, w2, w1, dh, dln, **kw)
+
     ops.gemm = recording
+    ops.ffn_bwd = ffn_recorder
     for n in conv_names:
         setattr(ops, n, conv_recorder(n))
     try:
@@ -281,6 +291,7 @@ def _record_gemms(step_fn, batch):
         torch.cuda.synchronize()
     finally:
         ops.gemm = orig
+        ops.ffn_bwd = ffn_orig
         for n in conv_names:
             setattr(ops, n, conv_orig[n])
     return rec
@@ -572,7 +583,7 @@ def run_gpu(args, wl):
     tflops = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     traffic = _traffic()
     fam_traffic = (traffic or {}).get("gemm_family_bytes_per_step")
-    roof = {"kernel": "gemm_tc_kernel (tcgen05.mma bf16, all GEMMs of one step)" if args.precision == "bf16" else "gemm_simt_kernel",
+    roof = {"kernel": "gemm_tc_kernel + ffn_bwd_kernel (tcgen05.mma bf16: every GEMM, implicit-GEMM convolution and fused FFN backward of one step)" if args.precision == "bf16" else "gemm_simt_kernel",
             "bound": "tensor", "achieved": tflops, "peak": pk["tc_sustained"], "unit": "TFLOP/s", "frac": tflops / pk["tc_sustained"],
             "traffic": fam_traffic,
             "traffic_note": ((traffic or {}).get("note") if traffic else "no ncu capture found under profiles/"),

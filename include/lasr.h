@@ -139,6 +139,7 @@ int lasr_gemm(const lasr_gemm_args* args, void* stream);
  * shapes return LASR_ERR_UNSUPPORTED.  All matrices row-major with 16-byte aligned bases and row strides.
  * ------------------------------------------------------------------------------------------------ */
 int lasr_ffn_bwd_supported(int d, int f);
+void lasr_ffn_bwd_set_trace(void* buf); /* developer aid: 32 x 8 clock64 stamps of CTA 0's first chunks (NULL = off) */
 int lasr_ffn_bwd(const void* dy, int64_t lddy, const void* g, int64_t ldg, const void* w2, int64_t ldw2, const void* w1, int64_t ldw1,
                  void* dh, int64_t lddh, void* dln, int64_t lddln, float* colsum, float alpha, int M, int d, int f, void* stream);
 

@@ -507,13 +507,14 @@ class Engine:
         ops.permute4d(gwo, st.g(pfx + ".out.weight"), (d, F2, d, 1), (F2 * d, d, 1, 0), (F2 * d, 1, F2, 0), accumulate=True)
         # dh2 = s * (dy @ W_out) * relu'(h2) into the padded (B*T2, V*d) layout, conv.2.bias gradient as the epilogue's column sums
         dh2p = _empty((B * T2, V * d), self.adt, self.dev)
-        dh2p.view(B * T2, V, d)[:, F2:, :].zero_()  # the padding slot of every frame must be zero for the implicit GEMMs
+        ops.zero_(dh2p)  # the padding slot of every frame must be zero for the implicit GEMMs (one memset; the GEMM fills the rest)
         wo = self._out_weight(pfx, d, F2)
         csum = torch.empty((F2 * d,), dtype=torch.float32, device=self.dev)
         ops.zero_(csum)
         ops.gemm(dy, wo, dh2p, B * T2, F2 * d, d, lda=dy.stride(0), ldb=wo.stride(0), ldc=V * d, tb=True, alpha=s, dact=c.h2v,
                  act=ACT_RELU, colsum=csum)
-        st.g(pfx + ".conv.2.bias").add_(csum.view(F2, d).sum(0))
+        # conv.2.bias gradient = the F2 per-slot column sums folded over the slots (column sums of the (F2, d) view)
+        ops.act_bwd(csum.view(F2, d), None, None, st.g(pfx + ".conv.2.bias"), ACT_NONE)
         gw2 = torch.empty((d, 9 * d), dtype=torch.float32, device=self.dev)
         ops.zero_(gw2)
         ops.conv2_wgrad(dh2p, c.h1p, gw2, B, c.T, c.F)

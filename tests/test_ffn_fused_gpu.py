@@ -20,7 +20,7 @@ def _case(m, d, f, seed=0):
     return dy, w2, w1, gd
 
 
-@pytest.mark.parametrize("m,d,f", [(300, 256, 2048), (129, 128, 192), (5, 64, 64), (1000, 256, 128), (37674, 256, 2048)])
+@pytest.mark.parametrize("m,d,f", [(300, 256, 2048), (129, 128, 384), (5, 64, 128), (1000, 256, 128), (37674, 256, 2048)])
 def test_ffn_bwd_fused_matches_reference(m, d, f):
     from liteasr_b200 import ops
     assert ops.ffn_bwd_supported(d, f)
@@ -62,7 +62,7 @@ def test_ffn_bwd_fused_equals_the_two_gemms_it_replaces():
 
 def test_ffn_bwd_rejects_unsupported_shapes():
     from liteasr_b200 import ops
-    assert not ops.ffn_bwd_supported(512, 2048) and not ops.ffn_bwd_supported(144, 320) and not ops.ffn_bwd_supported(256, 100)
+    assert not ops.ffn_bwd_supported(512, 2048) and not ops.ffn_bwd_supported(144, 320) and not ops.ffn_bwd_supported(256, 192) and not ops.ffn_bwd_supported(256, 4096)
     x = torch.zeros(8, 512, device=DEV, dtype=torch.bfloat16)
     with pytest.raises(RuntimeError):
         ops.ffn_bwd(x, torch.zeros(8, 64, device=DEV, dtype=torch.bfloat16), torch.zeros(512, 64, device=DEV, dtype=torch.bfloat16),
