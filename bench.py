@@ -523,6 +523,63 @@ def measure_step(args, wl, dev, dropout: float, rank: int, world: int, want_e2e:
     return res
 
 
+def variable_shape_run(args, wl, dev, dropout: float):
+    """training over the shapes the reference's length-bucketed batching produces (utils/batchify.py:76-112,
+    `SeqBatch` over a length-sorted corpus): every batch has its own (Tmax, Lmax).  One epoch runs eagerly (no shape has been
+    seen before), the second captures each shape at its second occurrence (bounded LRU cache), the third replays."""
+    import types
+
+    import torch
+    from liteasr_b200.criterions.hybrid_ctc_attn import HybridCTCLoss, HybridCTCLossConfig
+    from liteasr_b200.models.u2 import U2, U2Config
+    from liteasr_b200.optims import FusedNoam, NoamConfig
+    from liteasr_b200.schema import U2Dims
+    from liteasr_b200.trainer import TrainStep
+    from liteasr_b200.utils.batchify import SeqBatch, length_sorted_indices
+    from liteasr_b200.utils.synthetic import pred_len
+    dims = U2Dims(*wl["dims"])
+    g = torch.Generator().manual_seed(7)
+    nb, B = 12, wl["batch"]
+    n = nb * B
+    xl = torch.randint(int(0.3 * wl["tmax"]), wl["tmax"] + 1, (n,), generator=g)
+    yl = torch.minimum(torch.randint(wl["lmax"] // 2, wl["lmax"] + 1, (n,), generator=g), torch.clamp(pred_len(xl) // 2, min=1))
+    order = length_sorted_indices(xl.tolist())
+    pol = SeqBatch(types.SimpleNamespace(batch_size=B, min_batch_size=1, max_len_in=10 ** 9, max_len_out=10 ** 9))
+    pol.batchify(order, [types.SimpleNamespace(xlen=int(xl[i]), ylen=int(yl[i])) for i in order])
+    batches = []
+    for idx in pol.data:
+        xlens, ylens = xl[idx], yl[idx]
+        tmax, lmax = int(xlens.max()), int(ylens.max())
+        xs = torch.randn(len(idx), tmax, 80, generator=g) * (torch.arange(tmax).view(1, -1, 1) < xlens.view(-1, 1, 1))
+        ys = torch.randint(1, dims.vocab_size - 1, (len(idx), lmax), generator=g)
+        ys = ys.masked_fill(torch.arange(lmax).view(1, -1) >= ylens.view(-1, 1), -1)
+        batches.append(tuple(t.to(dev) for t in (xs, xlens, ys, ylens)))
+    audio = float(xl.sum()) * FRAME_SHIFT_S
+    torch.manual_seed(42)
+    model = U2(U2Config(**dims.__dict__, precision=args.precision, **my_u2_rates(dropout))).to(dev).train()
+    crit = HybridCTCLoss(HybridCTCLossConfig(vocab_size=dims.vocab_size, smoothing=wl["smoothing"], ctc_weight=wl["ctc_weight"]))
+    step = TrainStep(model, crit, None, clip_grad_norm=5.0, use_graph=True, device=dev, graph_min_hits=2, max_graphs=len(batches))
+    step.optimizer = FusedNoam(step.store, NoamConfig(model_dim=dims.enc_dim))
+    step.step_eager(*batches[0])  # library warm-up (lazy module load), not timed
+
+    def epoch():
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for b in batches:
+            step(*b)
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0
+
+    t_eager, t_capture, t_replay = epoch(), epoch(), epoch()
+    return {"what": f"{len(batches)} length-bucketed batches of {B} utterances (SeqBatch over {n} utterances, Tmax {int(xl.min())}..{int(xl.max())}), "
+                    f"{len(set((tuple(b[0].shape), tuple(b[2].shape)) for b in batches))} distinct (Tmax, Lmax) shapes; host-timed epochs",
+            "audio_s_per_epoch": audio,
+            "epoch1_eager": {"value": audio / t_eager, "unit": "audio-s/s", "s": t_eager},
+            "epoch2_capturing": {"value": audio / t_capture, "unit": "audio-s/s", "s": t_capture},
+            "epoch3_replaying": {"value": audio / t_replay, "unit": "audio-s/s", "s": t_replay},
+            "cache": dict(step.stats, entries=len(step.graphs), pool_gb=sum(e[3] for e in step.graphs.values()) / 1e9)}
+
+
 def gpu_incumbent(wl, dev, dropout: float, host_batch):
     """SURVEY 8d / BASELINE.md 3.7: the reference's own modules on torch-CUDA on this GPU -- eager fp32 and autocast(bf16) --
     same batch, same step (fwd + bwd + clip + Adam).  torch's library kernels are the only GPU incumbent the reference has."""
@@ -574,6 +631,9 @@ def run_gpu(args, wl):
     if world > 1 and not args.no_ddp_check:
         from liteasr_b200.distributed.check import ddp_numeric_check
         ddp_check = ddp_numeric_check(dev)
+        if args.check_ddp_shapes:  # opt-in: ranks with different batch shapes capturing graphs at different steps
+            from liteasr_b200.distributed.check import ddp_varshape_check
+            ddp_check["varshape"] = ddp_varshape_check(dev)
 
     r = measure_step(args, wl, dev, args.dropout, rank, world, want_e2e=True, want_clocks=True, steps=args.steps)
     ms, audio, dims, step = r["ms"], r["audio"], r["dims"], r["step"]
@@ -652,6 +712,11 @@ def run_gpu(args, wl):
                 torch.cuda.empty_cache()
         except Exception as e:  # noqa: BLE001
             extra["c3"] = {"error": str(e)}
+        try:
+            extra["variable_shapes"] = variable_shape_run(args, wl, dev, args.dropout)
+        except Exception as e:  # noqa: BLE001
+            extra["variable_shapes"] = {"error": str(e)}
+        torch.cuda.empty_cache()
         line["extra"] = extra
         try:
             line["roofline_ctc"] = ctc_standalone(pk)
@@ -698,6 +763,7 @@ def main():
                          "attention-probability rates stay 0.0); 0 = U2Config's dataclass default (round-1's bench)")
     ap.add_argument("--quick", action="store_true", help="headline numbers only (no extras: dropout-0 / C3 / CTC grid / GPU incumbent / CPU baseline)")
     ap.add_argument("--no-ddp-check", action="store_true", help="skip the NCCL gradient / buffer numeric check that runs first at N > 1")
+    ap.add_argument("--check-ddp-shapes", action="store_true", help="N > 1: also run TrainStep with rank-dependent batch shapes (graph capture at different steps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])

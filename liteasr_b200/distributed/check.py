@@ -86,3 +86,43 @@ def ddp_numeric_check(device, precision: str = "fp32") -> dict:
         res["ok_all_ranks"] = bool(flag.item() == 1.0)
     st.grad_ready_hook = None
     return res
+
+
+def ddp_varshape_check(device, steps: int = 6) -> dict:
+    """ranks that see DIFFERENT batch shapes capture their CUDA graphs at different steps.  Every rank runs
+    `steps` optimizer steps of a small model through ``TrainStep`` (graphs on, capture at the second occurrence of a shape) with
+    a rank-dependent shape schedule, so that in most steps some ranks replay, some capture and some run eagerly; the run must
+    neither hang nor diverge: after every step the parameters of all ranks are identical (same all-reduced gradients)."""
+    from ..criterions.hybrid_ctc_attn import HybridCTCLoss, HybridCTCLossConfig
+    from ..models.u2 import U2, U2Config
+    from ..schema import U2Dims
+    from ..trainer import TrainStep
+    from ..utils.synthetic import synth_batch, synth_state_dict
+
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    dims = U2Dims(input_dim=80, vocab_size=200, enc_dim=128, enc_ff_dim=256, enc_attn_heads=2, enc_layers=2, dec_dim=128,
+                  dec_ff_dim=256, dec_attn_heads=2, dec_layers=1)
+    model = U2(U2Config(**dims.__dict__, precision="bf16"))
+    model.load_state_dict(synth_state_dict(dims, seed=7))
+    model = model.to(device).train()
+    crit = HybridCTCLoss(HybridCTCLossConfig(vocab_size=dims.vocab_size, smoothing=0.1, ctc_weight=0.3))
+    step = TrainStep(model, crit, device=device, use_graph=True, graph_min_hits=2, max_graphs=2)
+    max_dev = 0.0
+    for i in range(steps):
+        # rank r alternates between two shapes with period r + 2: the ranks repeat (and therefore capture) at different steps
+        tmax = 200 + 16 * ((i % (rank + 2)) == 0) + 8 * rank
+        batch = tuple(t.to(device) for t in synth_batch(4, tmax, 10, dims.vocab_size, seed=900 + 17 * i + rank))
+        step(*batch)
+        torch.cuda.synchronize(device)
+        if world > 1:
+            flat = step.store.flat
+            ref = flat.clone()
+            dist.broadcast(ref, src=0)
+            max_dev = max(max_dev, float((flat - ref).abs().max()))
+    res = {"world": world, "steps": steps, "max_param_deviation_from_rank0": max_dev, "stats": dict(step.stats), "ok": bool(max_dev == 0.0)}
+    if dist.is_initialized() and world > 1:
+        flag = torch.tensor([1.0 if res["ok"] else 0.0], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        res["ok_all_ranks"] = bool(flag.item() == 1.0)
+    return res

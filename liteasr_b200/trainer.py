@@ -3,8 +3,14 @@
 ``TrainStep`` is one optimizer step of ``Trainer.run`` (trainer.py:140-171) restated for a flat-store model:
     zero grads -> [micro-steps: criterion(model, batch) -> backward (bucketed all-reduce overlapped)] ->
     fused global-norm clip + non-finite skip + (Noam) Adam.
-Host->device copies excepted, the whole step is captured once per input shape into a CUDA graph and replayed, so the ~1.5k
-kernel launches of a 12-layer Conformer step cost one ``cudaGraphLaunch`` (the d=256 working set is launch-bound otherwise).
+Host->device copies excepted, the whole step can be captured per input shape into a CUDA graph and replayed, so the ~950
+kernel launches of a 12-layer Conformer step cost one ``cudaGraphLaunch``.  Real length-bucketed batches (``utils/batchify``)
+have a different (Tmax, Lmax) almost every step, and padding to a bucket is not parity-neutral here (BatchNorm statistics
+include padded frames, quirk Q2), so the graph cache is a bounded LRU that only captures shapes it has SEEN BEFORE
+(``graph_min_hits``), evicts by count and by pool memory, and runs every other step eagerly -- the eager step is within a few
+percent of a replay at the bench shape (programmatic dependent launch hides the launch gaps).  Under DDP the capture is safe
+with different shapes on different ranks: the warm-up steps of a capture issue NO collectives (their results are thrown away
+anyway), so every rank issues exactly one set of NCCL calls per optimizer step whether it replays, captures or runs eagerly.
 Semantics kept from the reference: losses of the micro-steps are summed un-scaled (quirk Q9); the loss is normalised by the
 batch size inside the criterion; a non-finite gradient norm skips the update (decided on the device, identically on all ranks
 because it is evaluated after the all-reduce); ``grad = None``-style zeroing becomes one memset of the flat buffer.
@@ -12,6 +18,7 @@ because it is evaluated after the all-reduce); ``grad = None``-style zeroing bec
 from __future__ import annotations
 
 import time
+from collections import OrderedDict
 from typing import Callable, Dict, Iterable, Optional, Tuple
 
 import torch
@@ -25,7 +32,11 @@ from .optims import FusedAdam, FusedNoam, NoamConfig
 
 class TrainStep:
     def __init__(self, model, criterion, optimizer=None, *, clip_grad_norm: float = 5.0, accum_grad: int = 1,
-                 use_graph: bool = True, ddp: Optional[bool] = None, bucket_bytes: int = 64 << 20, device=None):
+                 use_graph: bool = True, ddp: Optional[bool] = None, bucket_bytes: int = 64 << 20, device=None,
+                 graph_min_hits: int = 1, max_graphs: int = 8, graph_mem_fraction: float = 0.5):
+        """use_graph: replay CUDA graphs where one exists.  graph_min_hits: capture a shape at its n-th occurrence (1 = at
+        once: fixed-shape training; >= 2: only shapes that repeat).  max_graphs / graph_mem_fraction: LRU bounds of the cache
+        (entries; their private activation pools as a fraction of the device memory)."""
         self.model, self.criterion = model, criterion
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.store, _, _ = F.bind(model, self.device)
@@ -37,19 +48,26 @@ class TrainStep:
         if ddp is None:
             ddp = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         self.ddp = FlatDDP(model, self.store, bucket_bytes=bucket_bytes) if ddp else None
-        self.graphs: Dict[Tuple, Tuple] = {}
+        self.graphs: "OrderedDict[Tuple, Tuple]" = OrderedDict()  # key -> (graph, static inputs, loss, pool bytes); LRU order
+        self.hits: Dict[Tuple, int] = {}
+        self.graph_min_hits, self.max_graphs = max(1, int(graph_min_hits)), max(1, int(max_graphs))
+        self.graph_mem_cap = int(graph_mem_fraction * torch.cuda.get_device_properties(self.device).total_memory)
+        self.stats = dict(replays=0, eager=0, captures=0, evictions=0, capture_s=0.0)
+        self._warm = False
         self.loss_out = torch.zeros(3, dtype=torch.float32, device=self.device)
 
     # ------------------------------------------------------------------ one optimizer step, eager
     def _body(self, batches) -> torch.Tensor:
         self.store.zero_grads()
-        if self.ddp is not None:
+        if self.ddp is not None and not self._warm:
             self.ddp.broadcast_buffers()
         total = None
         for i, (xs, xlens, ys, ylens) in enumerate(batches):
             last = i == len(batches) - 1
             if self.ddp is not None:
-                self.ddp.sync_grads = last  # no_sync on all but the last micro-step (trainer.py:142-145)
+                # no_sync on all but the last micro-step (trainer.py:142-145); the throw-away warm-up steps of a graph capture
+                # issue no collective at all (ranks with other shapes are not capturing)
+                self.ddp.sync_grads = last and not self._warm
                 self.ddp.begin_backward()
             direct = getattr(self.criterion, "direct_step", None)
             loss = direct(self.model, xs, xlens, ys, ylens) if direct is not None else None
@@ -74,16 +92,26 @@ class TrainStep:
     def __call__(self, xs, xlens, ys, ylens) -> torch.Tensor:
         """Device tensors in, device loss out (sum over micro-steps).  Copies the batch into the graph's static buffers."""
         if not self.use_graph:
+            self.stats["eager"] += 1
             return self.step_eager(xs, xlens, ys, ylens)
         key = (tuple(xs.shape), tuple(ys.shape), self.model.training)
         entry = self.graphs.get(key)
         if entry is None:
+            n = self.hits[key] = self.hits.get(key, 0) + 1
+            if len(self.hits) > 4096:  # the hit counters themselves stay bounded
+                self.hits = {key: n}
+            if n < self.graph_min_hits:
+                self.stats["eager"] += 1
+                return self.step_eager(xs, xlens, ys, ylens)
             entry = self._capture(key, xs, xlens, ys, ylens)
-        graph, static, loss = entry
+        else:
+            self.graphs.move_to_end(key)
+        graph, static, loss, _ = entry
         for dst, src in zip(static, (xs, xlens, ys, ylens)):
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
         graph.replay()
+        self.stats["replays"] += 1
         return loss
 
     def static_inputs(self, xs, xlens, ys, ylens):
@@ -93,22 +121,42 @@ class TrainStep:
             self._capture(key, xs, xlens, ys, ylens)
         return self.graphs[key][1]
 
+    def _evict_for(self, need_bytes: int) -> None:
+        """LRU eviction: keep at most max_graphs entries and at most graph_mem_cap bytes of private graph pools."""
+        def used():
+            return sum(e[3] for e in self.graphs.values())
+        while self.graphs and (len(self.graphs) >= self.max_graphs or used() + need_bytes > self.graph_mem_cap):
+            _, (g, static, loss, nbytes) = self.graphs.popitem(last=False)
+            del g, static, loss
+            self.stats["evictions"] += 1
+        torch.cuda.empty_cache()
+
     def _capture(self, key, xs, xlens, ys, ylens):
+        t0 = time.perf_counter()
+        est = max((e[3] for e in self.graphs.values()), default=0)  # a new pool is about as large as the largest so far
+        self._evict_for(est)
         static = tuple(t.clone() for t in (xs, xlens, ys, ylens))
         # snapshot state mutated by the warm-up steps so capture does not change training semantics
         snap = (self.store.flat.clone(), self.optimizer.exp_avg.clone(), self.optimizer.exp_avg_sq.clone(),
                 self.optimizer.state.clone(), {k: v.clone() for k, v in self.model.state_dict().items() if "running" in k or "num_batches" in k})
+        snap_rng = self.store.rng.state.clone()
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(2):
-                self._body(self._split(static))
+        self._warm = True  # throw-away steps: no NCCL calls (ADVICE r1: ranks see different shapes and capture at different steps)
+        try:
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self._body(self._split(static))
+        finally:
+            self._warm = False
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        mem0 = torch.cuda.memory_reserved(self.device)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             loss = self._body(self._split(static))
         torch.cuda.synchronize()
+        pool_bytes = max(0, torch.cuda.memory_reserved(self.device) - mem0)
         with torch.no_grad():
             self.store.flat.copy_(snap[0])
             self.optimizer.exp_avg.copy_(snap[1])
@@ -117,7 +165,10 @@ class TrainStep:
             sd = self.model.state_dict()
             for k, v in snap[4].items():
                 sd[k].copy_(v)
-        self.graphs[key] = (graph, static, loss)
+            self.store.rng.state.copy_(snap_rng)
+        self.graphs[key] = (graph, static, loss, pool_bytes)
+        self.stats["captures"] += 1
+        self.stats["capture_s"] += time.perf_counter() - t0
         return self.graphs[key]
 
 
@@ -173,9 +224,12 @@ class Trainer:
     tensors, the collator contract of dataset/asr_dataset.py:115-126).  Data loading itself is out of scope (SURVEY 2 #12)."""
 
     def __init__(self, model, criterion, optimizer=None, *, clip_grad_norm=5.0, accum_grad=1, report_interval=100,
-                 use_graph=True, device=None, log: Callable[[str], None] = print, max_iter: int = 0, max_epoch: int = 0):
+                 use_graph=True, device=None, log: Callable[[str], None] = print, max_iter: int = 0, max_epoch: int = 0,
+                 graph_min_hits: int = 50, max_graphs: int = 8):
+        # a capture costs ~1.4 s (two warm-up steps + instantiation of a ~950-node graph) and a replay is only ~2 % faster than the eager
+        # step, so a shape must come back about 50 times before its graph pays off: real length-bucketed batches mostly run eagerly
         self.step_fn = TrainStep(model, criterion, optimizer, clip_grad_norm=clip_grad_norm, accum_grad=accum_grad,
-                                 use_graph=use_graph, device=device)
+                                 use_graph=use_graph, device=device, graph_min_hits=graph_min_hits, max_graphs=max_graphs)
         self.model, self.criterion = model, criterion
         self.device = self.step_fn.device
         self.report = Trigger(report_interval)
