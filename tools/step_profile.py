@@ -37,13 +37,13 @@ def sig_of(name, args, kw):
     return " ".join(parts), 0.0
 
 
-def main(workload="c2", batch="0", top="60"):
+def main(workload="c2", batch="0", top="60", dropout="0"):
     wl = dict(bench.WORKLOADS[workload])
     if int(batch) > 0:
         wl["batch"] = int(batch)
     dims = U2Dims(*wl["dims"])
     dev = torch.device("cuda:0")
-    model = U2(U2Config(**dims.__dict__, precision="bf16")).to(dev).train()
+    model = U2(U2Config(**dims.__dict__, precision="bf16", **bench.my_u2_rates(float(dropout)))).to(dev).train()
     crit = HybridCTCLoss(HybridCTCLossConfig(vocab_size=dims.vocab_size, smoothing=wl["smoothing"], ctc_weight=wl["ctc_weight"]))
     step = TrainStep(model, crit, use_graph=False, device=dev)
     b = tuple(t.to(dev) for t in synth_batch(wl["batch"], wl["tmax"], wl["lmax"], dims.vocab_size, seed=42))
