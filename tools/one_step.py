@@ -15,11 +15,12 @@ from liteasr_b200.utils.synthetic import synth_batch  # noqa: E402
 
 workload = sys.argv[1] if len(sys.argv) > 1 else "c2"
 precision = sys.argv[2] if len(sys.argv) > 2 else "bf16"
+dropout = float(sys.argv[3]) if len(sys.argv) > 3 else 0.0
 wl = bench.WORKLOADS[workload]
 dims = U2Dims(*wl["dims"])
 dev = torch.device("cuda:0")
 torch.manual_seed(42)
-model = U2(U2Config(**dims.__dict__, precision=precision)).to(dev).train()
+model = U2(U2Config(**dims.__dict__, precision=precision, **bench.my_u2_rates(dropout))).to(dev).train()
 crit = HybridCTCLoss(HybridCTCLossConfig(vocab_size=dims.vocab_size, smoothing=wl["smoothing"], ctc_weight=wl["ctc_weight"]))
 step = TrainStep(model, crit, use_graph=False, device=dev)
 batch = tuple(t.to(dev) for t in synth_batch(wl["batch"], wl["tmax"], wl["lmax"], dims.vocab_size, seed=42))
