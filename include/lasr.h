@@ -107,7 +107,7 @@ typedef struct lasr_gemm_args {
      * nets/conformer_layer.py:42,54,63,125, nets/transformer_layer.py:48,58,174, nets/positional_encoding.py:75, and -- as the
      * backward of nets/ctc.py:29 -- the input gradient of ctc_lo):
      *   C = keep(m,n) * drop_scale * alpha * act(A.B^T + bias)  (+ res: the residual is added AFTER the mask)
-     * keep(m,n) comes from Philox4x32-10 keyed by drop_state = device {seed, step} (two uint64), drop_site and the element's
+     * keep(m,n) comes from Philox4x32-7 keyed by drop_state = device {seed, step} (two uint64), drop_site and the element's
      * (row, column) -- see the "dropout" section below; drop_thr = round(p * 65536) (0 = off), drop_scale = 65536 / (65536 - thr).
      * drop_mark_aux = 1: dropped elements of `aux` (the saved pre-activation) receive -1e30, whose act'() is exactly 0, so the
      * activation-backward GEMM (dact = aux) applies the SAME mask without regenerating it (its alpha carries drop_scale).
@@ -189,8 +189,9 @@ int lasr_layernorm_bwd_drop(const void* dy, int dy_dtype, int64_t lddy, const fl
  * Dropout (the reference's nn.Dropout / F.dropout sites: nets/positional_encoding.py:55,75, nets/attention.py:55,
  * nets/feed_forward.py:19, nets/conformer_layer.py:42,54,63,125, nets/transformer_layer.py:48,58,174, nets/ctc.py:29).
  * torch's generator stream cannot be replayed by fused kernels, so the masks come from the library's own counter-based
- * stream (Philox4x32-10): for a logical row-major (rows, n) tensor
- *     keep(r, c)  <=>  16-bit lane (c & 7) of philox4x32_10(counter = (c >> 3, r, site, step), key = seed)  >=  thr
+ * stream (Philox4x32 with 7 rounds, Random123's philox4x32_R<7>: the minimum Crush-resistant round count; csrc/philox.cuh says
+ * why): for a logical row-major (rows, n) tensor
+ *     keep(r, c)  <=>  16-bit lane (c & 7) of philox4x32_7(counter = (c >> 3, r, site, step), key = seed)  >=  thr
  * with thr = round(p * 65536) and kept values multiplied by scale = 65536 / (65536 - thr).  `state` is a device array
  * {uint64 seed, uint64 step}; lasr_rng_advance (one tiny kernel, CUDA-graph capturable) increments step, so every optimizer
  * step -- every replay of a captured step -- draws fresh masks.  Masks are never stored: lasr_gemm / lasr_layernorm_bwd_drop
@@ -198,8 +199,11 @@ int lasr_layernorm_bwd_drop(const void* dy, int dy_dtype, int64_t lddy, const fl
  *   lasr_dropout: y[r,c] = keep * scale * x[r,c] as a stand-alone pass (x fp32|bf16 -> y fp32|bf16; in place allowed when the
  *   dtypes agree) for the sites that sit behind no GEMM: pos_emb, the CTC head's input (fused with the operand cast), the
  *   decoder's embedded input and its gradient, attention probabilities when an attention dropout rate is non-zero.
+ *   lasr_philox_raw: known-answer hook -- out[0..3] = philox4x32 with `rounds` (10 = the Random123 kat_vectors, 7 = the
+ *   masks) rounds of counter ctr_key[0..3], key ctr_key[4..5] (device pointers).
  * ------------------------------------------------------------------------------------------------ */
 int lasr_rng_advance(void* state, void* stream);
+int lasr_philox_raw(const uint32_t* ctr_key, uint32_t* out, int rounds, void* stream);
 int lasr_dropout(const void* x, int x_dtype, int64_t ldx, void* y, int y_dtype, int64_t ldy, int64_t rows, int cols,
                  const void* state, uint32_t site, uint32_t thr, float scale, void* stream);
 

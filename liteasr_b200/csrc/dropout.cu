@@ -14,6 +14,15 @@ __global__ void rng_advance_kernel(unsigned long long* state) {
     if (threadIdx.x == 0 && blockIdx.x == 0) state[1] += 1ULL;
 }
 
+// known-answer hook: one Philox4x32 block with a run-time round count (7 = the masks, 10 = the Random123 vectors)
+__global__ void philox_raw_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int rounds) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint32_t c0 = in[0], c1 = in[1], c2 = in[2], c3 = in[3];
+    if (rounds == 10) philox4x32<10>(c0, c1, c2, c3, in[4], in[5]);
+    else philox4x32<LASR_PHILOX_ROUNDS>(c0, c1, c2, c3, in[4], in[5]);
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
 template <typename TX, typename TY>
 __global__ void __launch_bounds__(256) dropout_kernel(const TX* __restrict__ x, long ldx, TY* __restrict__ y, long ldy, long rows, int cols,
                                                       DropCfg cfg) {
@@ -47,6 +56,12 @@ int lasr_rng_advance(void* state, void* stream) {
     LASR_REQUIRE(state, "rng_advance: null state");
     rng_advance_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((unsigned long long*)state);
     return check_launch("rng_advance");
+}
+
+int lasr_philox_raw(const uint32_t* ctr_key, uint32_t* out, int rounds, void* stream) {
+    LASR_REQUIRE(ctr_key && out && (rounds == 10 || rounds == LASR_PHILOX_ROUNDS), "philox_raw: rounds must be 10 or %d", LASR_PHILOX_ROUNDS);
+    philox_raw_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(ctr_key, out, rounds);
+    return check_launch("philox_raw");
 }
 
 int lasr_dropout(const void* x, int x_dtype, int64_t ldx, void* y, int y_dtype, int64_t ldy, int64_t rows, int cols,

@@ -140,6 +140,23 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TD* __restrict
             }
         }
         const float m1 = warp_sum(s1) / d, m2 = warp_sum(s2) / d;
+        // keep bits of this lane's chunks.  One Philox call covers 8 columns = the chunks of a lane PAIR, so the pair splits the
+        // calls: for chunk slots (i, i + 1) the even lane evaluates the group of slot i, the odd lane the group of slot i + 1
+        // (groups (lane >> 1) + 16 i), and one shuffle hands each lane the nibbles it needs -- half the Philox work.
+        uint32_t k4[NV];
+        if (drop_on) {
+            if constexpr (NV >= 2) {
+#pragma unroll
+                for (int i = 0; i < NV; i += 2) {
+                    const uint32_t mine = drop_keep8(dk, (uint32_t)row, (uint32_t)((lane >> 1) + 16 * (i + (lane & 1))));
+                    const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
+                    k4[i] = (lane & 1) ? (other >> 4) : (mine & 15u);
+                    k4[i + 1] = (lane & 1) ? (mine >> 4) : (other & 15u);
+                }
+            } else {
+                k4[0] = drop_keep4(dk, (uint32_t)row, (uint32_t)(4 * lane));
+            }
+        }
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const int c = lane + 32 * i;
@@ -149,9 +166,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TD* __restrict
                 *reinterpret_cast<float4*>(dxr + 4 * c) = o;
                 float4 om = o;
                 if (drop_on) {
-                    const uint32_t k4 = drop_keep4(dk, (uint32_t)row, (uint32_t)(4 * c));
-                    om.x = (k4 & 1u) ? o.x * dk.scale : 0.f; om.y = (k4 & 2u) ? o.y * dk.scale : 0.f;
-                    om.z = (k4 & 4u) ? o.z * dk.scale : 0.f; om.w = (k4 & 8u) ? o.w * dk.scale : 0.f;
+                    om.x = (k4[i] & 1u) ? o.x * dk.scale : 0.f; om.y = (k4[i] & 2u) ? o.y * dk.scale : 0.f;
+                    om.z = (k4[i] & 4u) ? o.z * dk.scale : 0.f; om.w = (k4[i] & 8u) ? o.w * dk.scale : 0.f;
                 }
                 if (dx_lo) {
                     if constexpr (sizeof(TLO) == 4) {

@@ -1,5 +1,9 @@
-// Dropout masks from a counter-based generator: Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as
-// 1, 2, 3", SC'11; Random123 constants), evaluated INSIDE the kernels that produce or consume the dropped tensor -- no mask
+// Dropout masks from a counter-based generator: Philox4x32 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as
+// 1, 2, 3", SC'11; Random123 constants) with LASR_PHILOX_ROUNDS = 7 rounds -- the paper's (and Random123's philox4x32_R<7>)
+// minimum Crush-resistant round count; the 10-round default only adds a safety margin that dropout masks do not need, and the
+// rounds are the dominant cost of dropout here (integer instructions in issue-bound GEMM epilogues: 7 rounds instead of 10
+// removes 30 % of them).  The round function is pinned by the Random123 known-answer vectors at 10 rounds
+// (oracle/philox_oracle.py, tests/test_philox_cpu.py, and lasr_philox_raw on the GPU).  Masks are evaluated INSIDE the kernels that produce or consume the dropped tensor -- no mask
 // tensor exists, the backward pass regenerates (or, for the FFN inner site, reads back from the saved pre-activation) the mask
 // the forward pass applied.
 //
@@ -9,7 +13,7 @@
 // library's own:
 //
 //   keep(row, col) of a logical row-major (rows, n) tensor at dropout site `site` in optimizer step `step`:
-//       w[0..3] = philox4x32_10(counter = (col >> 3, row, site, step), key = (seed_lo, seed_hi))
+//       w[0..3] = philox4x32<7>(counter = (col >> 3, row, site, step), key = (seed_lo, seed_hi))
 //       u16     = 16-bit lane (col & 7) of w  (lane e = word e >> 1, low half first)
 //       keep  <=>  u16 >= thr,   thr = round(p * 65536),   kept values are multiplied by scale = 65536 / (65536 - thr)
 //
@@ -45,9 +49,12 @@ __device__ __forceinline__ DropKey drop_key(const DropCfg& c) {
     return k;
 }
 
-__device__ __forceinline__ void philox4x32_10(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0, uint32_t k1) {
+#define LASR_PHILOX_ROUNDS 7
+
+template <int ROUNDS = LASR_PHILOX_ROUNDS>
+__device__ __forceinline__ void philox4x32(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < ROUNDS; ++r) {
         const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
         const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
         c0 = hi1 ^ c1 ^ k0;
@@ -62,7 +69,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t& c0, uint32_t& c1, uint32
 // keep bits of the 8 columns [8g, 8g + 8) of `row`: bit e set <=> column 8g + e is kept
 __device__ __forceinline__ uint32_t drop_keep8(const DropKey& k, uint32_t row, uint32_t g) {
     uint32_t c0 = g, c1 = row, c2 = k.site, c3 = k.step;
-    philox4x32_10(c0, c1, c2, c3, k.k0, k.k1);
+    philox4x32<>(c0, c1, c2, c3, k.k0, k.k1);
     uint32_t bits = 0;
     bits |= ((c0 & 0xffffu) >= k.thr) ? 1u : 0u;
     bits |= ((c0 >> 16) >= k.thr) ? 2u : 0u;

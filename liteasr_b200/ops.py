@@ -247,6 +247,15 @@ def rng_advance(state: torch.Tensor) -> None:
     _lib.check(_lib.lib().lasr_rng_advance(_ptr(state), _stream()), "rng_advance")
 
 
+def philox_raw(ctr_key: torch.Tensor, rounds: int) -> torch.Tensor:
+    """Known-answer hook: philox4x32 with ``rounds`` (10 or 7) rounds of counter ctr_key[0:4], key ctr_key[4:6] (int32 bit patterns)."""
+    _require_cuda(ctr_key)
+    assert ctr_key.dtype == torch.int32 and ctr_key.numel() == 6 and ctr_key.is_contiguous()
+    out = torch.empty(4, dtype=torch.int32, device=ctr_key.device)
+    _lib.check(_lib.lib().lasr_philox_raw(_ptr(ctr_key), _ptr(out), _i(rounds), _stream()), "philox_raw")
+    return out
+
+
 def dropout(x: torch.Tensor, y: torch.Tensor, drop: Drop) -> torch.Tensor:
     """y = keep * scale * x over the logical (rows, cols) = (numel / last, last) tensor; x, y 2-D views (or contiguous N-D)."""
     _require_cuda(x, y)

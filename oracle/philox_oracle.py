@@ -2,12 +2,14 @@
 
 The reference draws its dropout masks from torch's global generator (nn.Dropout / F.dropout, nets/feed_forward.py:19,
 nets/conformer_layer.py:42-63, nets/attention.py:55, nets/positional_encoding.py:55,75, nets/ctc.py:29); fused kernels cannot
-replay that stream, so the product uses its OWN counter-based stream: Philox4x32-10 (Salmon et al., SC'11 --
-"Parallel random numbers: as easy as 1, 2, 3"; the Random123 constants) keyed by the seed and indexed by
+replay that stream, so the product uses its OWN counter-based stream: Philox4x32 (Salmon et al., SC'11 --
+"Parallel random numbers: as easy as 1, 2, 3"; the Random123 constants) with ROUNDS = 7 rounds (the paper's minimum
+Crush-resistant count, Random123's philox4x32_R<7>; csrc/philox.cuh says why not 10), keyed by the seed and indexed by
 (step, site, row, 8-column group).  This file restates that published algorithm and the product's indexing so that the float64
-oracle can apply EXACTLY the masks the kernels apply; it is pinned by the Random123 known-answer vectors below.
+oracle can apply EXACTLY the masks the kernels apply; the round function is pinned by the Random123 known-answer vectors
+below, which exist for 10 rounds (same function, `rounds=10`).
 
-    keep(row, col) of a logical (rows, n) tensor:  u16 = 16-bit lane (col & 7) of philox4x32_10(ctr = (col >> 3, row, site, step),
+    keep(row, col) of a logical (rows, n) tensor:  u16 = 16-bit lane (col & 7) of philox4x32(ctr = (col >> 3, row, site, step),
                                                                                              key = (seed_lo, seed_hi))
                                                    keep iff u16 >= thr,  thr = round(p * 65536);  scale = 65536 / (65536 - thr)
 """
@@ -20,12 +22,15 @@ W0, W1 = np.uint32(0x9E3779B9), np.uint32(0xBB67AE85)
 MASK32 = np.uint64(0xFFFFFFFF)
 
 
-def philox4x32_10(c0, c1, c2, c3, k0, k1):
+ROUNDS = 7  # csrc/philox.cuh LASR_PHILOX_ROUNDS
+
+
+def philox4x32(c0, c1, c2, c3, k0, k1, rounds=ROUNDS):
     """Vectorised over numpy uint32 arrays (broadcastable).  Returns four uint32 arrays."""
     c0, c1, c2, c3 = (np.asarray(x, dtype=np.uint32) for x in (c0, c1, c2, c3))
     k0, k1 = np.uint32(k0), np.uint32(k1)
     with np.errstate(over="ignore"):
-        for _ in range(10):
+        for _ in range(rounds):
             p0 = c0.astype(np.uint64) * M0
             p1 = c2.astype(np.uint64) * M1
             hi0, lo0 = (p0 >> np.uint64(32)).astype(np.uint32), (p0 & MASK32).astype(np.uint32)
@@ -33,6 +38,10 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
             c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
             k0, k1 = np.uint32(k0 + W0), np.uint32(k1 + W1)
     return c0, c1, c2, c3
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    return philox4x32(c0, c1, c2, c3, k0, k1, rounds=10)
 
 
 # Random123 known-answer vectors (kat_vectors: "philox4x32 10")
@@ -60,7 +69,7 @@ def keep_mask(rows: int, n: int, site: int, seed: int, step: int, p: float) -> n
     groups = (n + 7) // 8
     g = np.arange(groups, dtype=np.uint32)[None, :]
     r = np.arange(rows, dtype=np.uint32)[:, None]
-    w = philox4x32_10(g, r, np.uint32(site), np.uint32(step & 0xFFFFFFFF), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    w = philox4x32(g, r, np.uint32(site), np.uint32(step & 0xFFFFFFFF), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
     lanes = np.empty((rows, groups, 8), dtype=np.uint32)
     for i in range(4):
         wi = np.broadcast_to(w[i], (rows, groups))
