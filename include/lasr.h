@@ -108,7 +108,7 @@ typedef struct lasr_gemm_args {
      * backward of nets/ctc.py:29 -- the input gradient of ctc_lo):
      *   C = keep(m,n) * drop_scale * alpha * act(A.B^T + bias)  (+ res: the residual is added AFTER the mask)
      * keep(m,n) comes from Philox4x32-7 keyed by drop_state = device {seed, step} (two uint64), drop_site and the element's
-     * (row, column) -- see the "dropout" section below; drop_thr = round(p * 65536) (0 = off), drop_scale = 65536 / (65536 - thr).
+     * (row, column) -- see the "dropout" section below; drop_thr = round(p * 32768) <= 0x7c00 (0 = off), drop_scale = 32768 / (32768 - thr).
      * drop_mark_aux = 1: dropped elements of `aux` (the saved pre-activation) receive -1e30, whose act'() is exactly 0, so the
      * activation-backward GEMM (dact = aux) applies the SAME mask without regenerating it (its alpha carries drop_scale).
      * Unbatched GEMMs only; not with accumulate / dact / n_store / recompute. */
@@ -191,8 +191,10 @@ int lasr_layernorm_bwd_drop(const void* dy, int dy_dtype, int64_t lddy, const fl
  * torch's generator stream cannot be replayed by fused kernels, so the masks come from the library's own counter-based
  * stream (Philox4x32 with 7 rounds, Random123's philox4x32_R<7>: the minimum Crush-resistant round count; csrc/philox.cuh says
  * why): for a logical row-major (rows, n) tensor
- *     keep(r, c)  <=>  16-bit lane (c & 7) of philox4x32_7(counter = (c >> 3, r, site, step), key = seed)  >=  thr
- * with thr = round(p * 65536) and kept values multiplied by scale = 65536 / (65536 - thr).  `state` is a device array
+ *     w[0..3] = philox4x32_7(counter = (c >> 4, r, site, step), key = seed);   e = c & 15, i = e >> 2, j = e & 3
+ *     keep(r, c)  <=>  (((byte j of w[i]) << 8 | (byte j of w[i ^ 1])) & 0x7fff)  >=  thr
+ * with thr = round(p * 32768) <= 0x7c00 (p <= 0.96875) and kept values multiplied by scale = 32768 / (32768 - thr): one call
+ * serves 16 columns, and 15-bit lanes let the kernels compare two of them with one half2 instruction (csrc/philox.cuh).  `state` is a device array
  * {uint64 seed, uint64 step}; lasr_rng_advance (one tiny kernel, CUDA-graph capturable) increments step, so every optimizer
  * step -- every replay of a captured step -- draws fresh masks.  Masks are never stored: lasr_gemm / lasr_layernorm_bwd_drop
  * evaluate them in their epilogues, the backward pass regenerates them from the same (step, site, row, column).

@@ -64,9 +64,9 @@ int lasr_gemm(const lasr_gemm_args* a, void* stream) {
         LASR_REQUIRE(a->n_store >= a->n && a->n_store <= a->ldc && !a->bias && !a->res && !a->aux && !a->dact && !a->colsum && !a->accumulate,
                      "gemm: n_store must satisfy n <= n_store <= ldc and excludes every epilogue operand");
     if (a->drop_thr)
-        LASR_REQUIRE(a->drop_state && a->drop_thr < 65536u && a->batch1 == 1 && a->batch2 == 1 && !a->accumulate && !a->dact && !a->n_store &&
+        LASR_REQUIRE(a->drop_state && a->drop_thr <= 0x7c00u && a->batch1 == 1 && a->batch2 == 1 && !a->accumulate && !a->dact && !a->n_store &&
                          !a->a2 && !a->colsum,
-                     "gemm: dropout needs drop_state, thr < 65536, an unbatched GEMM and no accumulate / dact / n_store / recompute / colsum");
+                     "gemm: dropout needs drop_state, thr = round(p * 32768) <= 0x7c00, an unbatched GEMM and no accumulate / dact / n_store / recompute / colsum");
     cudaStream_t st = (cudaStream_t)stream;
     if (a->ab_dtype == LASR_BF16) return gemm_tc_dispatch(a, st);
     if (a->ab_dtype == LASR_F32) {

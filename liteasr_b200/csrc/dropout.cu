@@ -27,18 +27,18 @@ template <typename TX, typename TY>
 __global__ void __launch_bounds__(256) dropout_kernel(const TX* __restrict__ x, long ldx, TY* __restrict__ y, long ldy, long rows, int cols,
                                                       DropCfg cfg) {
     LASR_PDL_SYNC();
-    const int groups = (cols + 7) >> 3;
+    const int groups = (cols + 15) >> 4;
     const long total = rows * groups;
     const DropKey dk = drop_key(cfg);
     for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
         const long r = i / groups;
         const int g = (int)(i - r * groups);
-        const uint32_t keep = drop_keep8(dk, (uint32_t)r, (uint32_t)g);
-        const TX* xr = x + r * ldx + 8 * g;
-        TY* yr = y + r * ldy + 8 * g;
-        const int n = min(8, cols - 8 * g);
+        const uint32_t keep = drop_keep16(dk, (uint32_t)r, (uint32_t)g);
+        const TX* xr = x + r * ldx + 16 * g;
+        TY* yr = y + r * ldy + 16 * g;
+        const int n = min(16, cols - 16 * g);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
+        for (int e = 0; e < 16; ++e) {
             if (e < n) {
                 const float v = to_f32<TX>(xr[e]);
                 yr[e] = from_f32<TY>(((keep >> e) & 1u) ? v * dk.scale : 0.f);
@@ -66,11 +66,11 @@ int lasr_philox_raw(const uint32_t* ctr_key, uint32_t* out, int rounds, void* st
 
 int lasr_dropout(const void* x, int x_dtype, int64_t ldx, void* y, int y_dtype, int64_t ldy, int64_t rows, int cols,
                  const void* state, uint32_t site, uint32_t thr, float scale, void* stream) {
-    LASR_REQUIRE(x && y && state && rows > 0 && cols > 0 && thr < 65536u, "dropout: bad args");
+    LASR_REQUIRE(x && y && state && rows > 0 && cols > 0 && thr <= LASR_DROP_THR_MAX, "dropout: bad args (thr = round(p * 32768) <= 0x7c00)");
     LASR_REQUIRE(rows <= 0xffffffffLL, "dropout: more than 2^32 rows");
     DropCfg cfg;
     cfg.state = (const unsigned long long*)state; cfg.site = site; cfg.thr = thr; cfg.scale = scale;
-    const long total = rows * ((cols + 7) / 8);
+    const long total = rows * ((cols + 15) / 16);
     int grid = ceil_div(total, 256);
     if (grid > 148 * 16) grid = 148 * 16;
     cudaStream_t st = (cudaStream_t)stream;

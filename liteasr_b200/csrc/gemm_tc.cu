@@ -449,15 +449,23 @@ __device__ __forceinline__ void epilogue_unit_tma(const TcParams& p, const Unit&
     const bool drop_on = DROP && p.drop.thr != 0;  // warp-uniform
     DropKey dk = {};
     if (drop_on) dk = drop_key(p.drop);
+    const float alpha_s = drop_on ? alpha * dk.scale : alpha;  // 1 / (1 - p) rides on alpha
     for (int cc = part * 32; cc < p.bn; cc += 32 * (EPI_WARPS / 4)) {
         const int col0 = w.n0 + cc;
         if (col0 >= col_limit) break;  // warp-uniform
         const bool full = col0 + 32 <= col_limit;
-        // dropout: the 32 keep bits of this thread's row segment (4 Philox calls), computed BEFORE the TMEM load is waited for:
+        // dropout: the keep masks of this thread's 32-column row segment, computed BEFORE the TMEM load is waited for:
         // they depend on nothing the accumulator holds, so their ~300 integer instructions fill issue slots the latency chain
         // TMEM -> math -> staging leaves idle
-        uint32_t keep = 0xffffffffu;
-        if (drop_on) keep = drop_keep32(dk, (uint32_t)row, (uint32_t)col0);
+        // (two calls: packed 0xffff / 0 lane masks, mk[t] = columns col0 + 2t and col0 + 2t + 1 -- philox.cuh)
+        uint32_t mk[16];
+        if (drop_on) {
+            uint32_t h0[8], h1[8];
+            drop_masks16(dk, (uint32_t)row, (uint32_t)col0 >> 4, h0);
+            drop_masks16(dk, (uint32_t)row, ((uint32_t)col0 >> 4) + 1u, h1);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) { mk[t] = h0[t]; mk[8 + t] = h1[t]; }
+        }
         // row-wise global operands first (in flight while TMEM is read)
         float4 r4[MODE == EPI_RES ? 8 : 1];
         uint4 s4[DACT ? 4 : 1];
@@ -529,11 +537,11 @@ __device__ __forceinline__ void epilogue_unit_tma(const TcParams& p, const Unit&
                     }
                 }
                 if constexpr (MODE == EPI_PLAIN || MODE == EPI_RES) {
-                    v[4 * j] = fmaf(v[4 * j], alpha, alpha * b.x); v[4 * j + 1] = fmaf(v[4 * j + 1], alpha, alpha * b.y);
-                    v[4 * j + 2] = fmaf(v[4 * j + 2], alpha, alpha * b.z); v[4 * j + 3] = fmaf(v[4 * j + 3], alpha, alpha * b.w);
-                    if (drop_on) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) v[4 * j + e] = ((keep >> (4 * j + e)) & 1u) ? v[4 * j + e] * dk.scale : 0.f;
+                    v[4 * j] = fmaf(v[4 * j], alpha_s, alpha_s * b.x); v[4 * j + 1] = fmaf(v[4 * j + 1], alpha_s, alpha_s * b.y);
+                    v[4 * j + 2] = fmaf(v[4 * j + 2], alpha_s, alpha_s * b.z); v[4 * j + 3] = fmaf(v[4 * j + 3], alpha_s, alpha_s * b.w);
+                    if (drop_on) {  // dropped -> +0 (the residual is added after the mask)
+                        v[4 * j] = drop_and(v[4 * j], drop_mask_lo(mk[2 * j])); v[4 * j + 1] = drop_and(v[4 * j + 1], drop_mask_hi(mk[2 * j]));
+                        v[4 * j + 2] = drop_and(v[4 * j + 2], drop_mask_lo(mk[2 * j + 1])); v[4 * j + 3] = drop_and(v[4 * j + 3], drop_mask_hi(mk[2 * j + 1]));
                     }
                     if constexpr (MODE == EPI_RES) { v[4 * j] += r4[j].x; v[4 * j + 1] += r4[j].y; v[4 * j + 2] += r4[j].z; v[4 * j + 3] += r4[j].w; }
                 } else {  // EPI_RELU / EPI_SWISH: pre-activation = acc + bias
@@ -550,48 +558,48 @@ __device__ __forceinline__ void epilogue_unit_tma(const TcParams& p, const Unit&
         __syncwarp();
         if constexpr (MODE == EPI_RELU || MODE == EPI_SWISH) {
             const bool deriv = MODE == EPI_SWISH && has_aux && p.aux_deriv != 0;  // warp-uniform
+            const bool hmask = drop_on && p.drop_mark;  // warp-uniform: the saved tensor carries the mask
             if (deriv) {  // aux = swish'(h) (0 where dropped) and v = swish(h), 8 columns at a time (one tanh serves both)
                 uint8_t* sx = stage + 2048;
-                const uint32_t hk = (drop_on && p.drop_mark) ? keep : 0xffffffffu;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     float gq[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        swish_and_deriv(v[8 * j + e], v[8 * j + e], gq[e]);
-                        gq[e] = ((hk >> (8 * j + e)) & 1u) ? gq[e] : 0.f;
-                    }
+                    for (int e = 0; e < 8; ++e) swish_and_deriv(v[8 * j + e], v[8 * j + e], gq[e]);
                     uint4 u;
                     u.x = pack_bf16x2(gq[0], gq[1]); u.y = pack_bf16x2(gq[2], gq[3]);
                     u.z = pack_bf16x2(gq[4], gq[5]); u.w = pack_bf16x2(gq[6], gq[7]);
+                    if (hmask) { u.x &= mk[4 * j]; u.y &= mk[4 * j + 1]; u.z &= mk[4 * j + 2]; u.w &= mk[4 * j + 3]; }
                     *reinterpret_cast<uint4*>(sx + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = u;
                 }
             } else if (has_aux) {  // pre-activation copy (bf16 on this path); dropped elements carry the marker whose act'() is 0
                 uint8_t* sx = stage + 2048;
-                const uint32_t hk = (drop_on && p.drop_mark) ? keep : 0xffffffffu;
+                const uint32_t mark2 = pack_bf16x2(LASR_DROP_MARK, LASR_DROP_MARK);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    float h[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) h[e] = ((hk >> (8 * j + e)) & 1u) ? v[8 * j + e] : LASR_DROP_MARK;
                     uint4 u;
-                    u.x = pack_bf16x2(h[0], h[1]); u.y = pack_bf16x2(h[2], h[3]);
-                    u.z = pack_bf16x2(h[4], h[5]); u.w = pack_bf16x2(h[6], h[7]);
+                    u.x = pack_bf16x2(v[8 * j], v[8 * j + 1]); u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                    u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                    if (hmask) {
+                        u.x = (u.x & mk[4 * j]) | (mark2 & ~mk[4 * j]); u.y = (u.y & mk[4 * j + 1]) | (mark2 & ~mk[4 * j + 1]);
+                        u.z = (u.z & mk[4 * j + 2]) | (mark2 & ~mk[4 * j + 2]); u.w = (u.w & mk[4 * j + 3]) | (mark2 & ~mk[4 * j + 3]);
+                    }
                     *reinterpret_cast<uint4*>(sx + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = u;
                 }
             }
-            const bool unit_alpha = alpha == 1.f;
             if (!deriv) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = (MODE == EPI_RELU) ? fmaxf(v[j], 0.f) : swish_fast(v[j]);
             }
-            if (!unit_alpha) {  // warp-uniform: no multiply on the alpha == 1 path (every FFN fc1)
+            if (alpha_s != 1.f) {  // warp-uniform: no multiply on the alpha == 1, p == 0 path
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] *= alpha;
+                for (int j = 0; j < 32; ++j) v[j] *= alpha_s;
             }
-            if (drop_on) {
+            if constexpr (!BF) {  // fp32 result: mask the values; the bf16 result is masked after packing (one AND per pair)
+                if (drop_on) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = ((keep >> j) & 1u) ? v[j] * dk.scale : 0.f;
+                    for (int t = 0; t < 16; ++t) { v[2 * t] = drop_and(v[2 * t], drop_mask_lo(mk[t])); v[2 * t + 1] = drop_and(v[2 * t + 1], drop_mask_hi(mk[t])); }
+                }
             }
         }
         if constexpr (BF) {
@@ -600,6 +608,9 @@ __device__ __forceinline__ void epilogue_unit_tma(const TcParams& p, const Unit&
                 uint4 u;
                 u.x = pack_bf16x2(v[8 * j], v[8 * j + 1]); u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
                 u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                if constexpr (MODE == EPI_RELU || MODE == EPI_SWISH) {
+                    if (drop_on) { u.x &= mk[4 * j]; u.y &= mk[4 * j + 1]; u.z &= mk[4 * j + 2]; u.w &= mk[4 * j + 3]; }
+                }
                 *reinterpret_cast<uint4*>(sb + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = u;
             }
         } else {

@@ -140,18 +140,18 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TD* __restrict
             }
         }
         const float m1 = warp_sum(s1) / d, m2 = warp_sum(s2) / d;
-        // keep bits of this lane's chunks.  One Philox call covers 8 columns = the chunks of a lane PAIR, so the pair splits the
-        // calls: for chunk slots (i, i + 1) the even lane evaluates the group of slot i, the odd lane the group of slot i + 1
-        // (groups (lane >> 1) + 16 i), and one shuffle hands each lane the nibbles it needs -- half the Philox work.
+        // keep bits of this lane's chunks.  One Philox call covers 16 columns = the chunks of a lane QUAD (chunk lane + 32 i is
+        // nibble lane & 3 of group (lane >> 2) + 8 i), so the quad splits the calls: for chunk slots (i, i + 1) the even lanes
+        // evaluate the group of slot i, the odd lanes the group of slot i + 1, and two shuffles hand every lane its nibbles.
         uint32_t k4[NV];
         if (drop_on) {
             if constexpr (NV >= 2) {
+                const int q0 = lane & ~3, sh = 4 * (lane & 3);
 #pragma unroll
                 for (int i = 0; i < NV; i += 2) {
-                    const uint32_t mine = drop_keep8(dk, (uint32_t)row, (uint32_t)((lane >> 1) + 16 * (i + (lane & 1))));
-                    const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
-                    k4[i] = (lane & 1) ? (other >> 4) : (mine & 15u);
-                    k4[i + 1] = (lane & 1) ? (mine >> 4) : (other & 15u);
+                    const uint32_t mine = drop_keep16(dk, (uint32_t)row, (uint32_t)((lane >> 2) + 8 * (i + (lane & 1))));
+                    k4[i] = (__shfl_sync(0xffffffffu, mine, q0) >> sh) & 15u;
+                    k4[i + 1] = (__shfl_sync(0xffffffffu, mine, q0 + 1) >> sh) & 15u;
                 }
             } else {
                 k4[0] = drop_keep4(dk, (uint32_t)row, (uint32_t)(4 * lane));
@@ -246,7 +246,7 @@ int lasr_layernorm_bwd_drop(const void* dy, int dy_dtype, int64_t lddy, const fl
                             float colsum_scale, const void* drop_state, uint32_t drop_site, uint32_t drop_thr, float drop_scale,
                             void* stream) {
     using namespace lasr;
-    LASR_REQUIRE(drop_thr == 0 || (drop_state && drop_thr < 65536u), "layernorm_bwd: dropout needs drop_state and thr < 65536");
+    LASR_REQUIRE(drop_thr == 0 || (drop_state && drop_thr <= LASR_DROP_THR_MAX), "layernorm_bwd: dropout needs drop_state and thr <= 0x7c00");
     LASR_REQUIRE(lo_dtype == LASR_BF16 || lo_dtype == LASR_F32, "layernorm_bwd: bad dx_lo dtype");
     DropCfg drop;
     drop.state = (const unsigned long long*)drop_state; drop.site = drop_site; drop.thr = drop_thr; drop.scale = drop_scale;

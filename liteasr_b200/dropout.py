@@ -62,8 +62,6 @@ def drop(rng: Optional[torch.Tensor], net: int, layer: int, kind: int, p) -> Opt
     """``ops.Drop`` for one site, or None when dropout is off there (no rng snapshot = eval mode, or p rounds to 0)."""
     if rng is None or p is None or float(p) <= 0.0:
         return None
-    if float(p) >= 1.0:
-        raise ValueError("dropout rate must be < 1")
     d = ops.Drop(rng, site_id(net, layer, kind), float(p))
     return d if d.thr else None
 
@@ -80,5 +78,5 @@ def has_dropout(module) -> bool:
 
 def check_rates(module, *rates) -> None:
     for r in rates:
-        if not (isinstance(r, (int, float)) and 0.0 <= float(r) < 1.0):
-            raise ValueError(f"{type(module).__name__}: dropout rate {r!r} must be a number in [0, 1)")
+        if not (isinstance(r, (int, float)) and 0.0 <= float(r) <= ops.DROP_P_MAX):
+            raise ValueError(f"{type(module).__name__}: dropout rate {r!r} must be a number in [0, {ops.DROP_P_MAX}]")

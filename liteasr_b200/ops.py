@@ -229,15 +229,20 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, accumulate: bool,
         C.c_uint32(drop.thr if drop is not None else 0), _f(drop.scale if drop is not None else 1.0), _stream()), "layernorm_bwd")
 
 
+DROP_P_MAX = 0.96875  # thr = round(p * 32768) <= 0x7c00
+
+
 class Drop:
-    """One dropout site of one step: device RNG state {seed, step}, site id, 16-bit threshold and the 1/(1-p) scale
+    """One dropout site of one step: device RNG state {seed, step}, site id, 15-bit threshold and the 1/(1-p) scale
     (include/lasr.h, "Dropout"; liteasr_b200/dropout.py builds these)."""
     __slots__ = ("state", "site", "thr", "scale")
 
     def __init__(self, state: torch.Tensor, site: int, p: float):
         self.state, self.site = state, int(site)
-        self.thr = int(min(65535, max(0, round(float(p) * 65536.0))))
-        self.scale = 65536.0 / (65536.0 - self.thr)
+        if not 0.0 <= float(p) <= DROP_P_MAX:
+            raise ValueError(f"dropout rate {p!r} outside [0, {DROP_P_MAX}] (15-bit lanes compared as fp16 patterns: csrc/philox.cuh)")
+        self.thr = int(max(0, round(float(p) * 32768.0)))
+        self.scale = 32768.0 / (32768.0 - self.thr)
 
 
 def rng_advance(state: torch.Tensor) -> None:

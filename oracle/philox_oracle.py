@@ -9,9 +9,11 @@ Crush-resistant count, Random123's philox4x32_R<7>; csrc/philox.cuh says why not
 oracle can apply EXACTLY the masks the kernels apply; the round function is pinned by the Random123 known-answer vectors
 below, which exist for 10 rounds (same function, `rounds=10`).
 
-    keep(row, col) of a logical (rows, n) tensor:  u16 = 16-bit lane (col & 7) of philox4x32(ctr = (col >> 3, row, site, step),
-                                                                                             key = (seed_lo, seed_hi))
-                                                   keep iff u16 >= thr,  thr = round(p * 65536);  scale = 65536 / (65536 - thr)
+    keep(row, col) of a logical (rows, n) tensor:  w = philox4x32(ctr = (col >> 4, row, site, step), key = (seed_lo, seed_hi))
+                                                   e = col & 15, i = e >> 2, j = e & 3
+                                                   u15 = ((byte j of w[i]) << 8 | (byte j of w[i ^ 1])) & 0x7fff
+                                                   keep iff u15 >= thr,  thr = round(p * 32768) <= 0x7c00;  scale = 32768 / (32768 - thr)
+(one call serves 16 columns; 15-bit lanes so that the kernels can compare two of them with one half2 instruction)
 """
 from __future__ import annotations
 
@@ -52,13 +54,30 @@ KAT = [
 ]
 
 
+THR_MAX = 0x7C00
+
+
 def threshold(p: float) -> int:
-    """Drop threshold on a 16-bit lane; p_eff = thr / 65536 (|p_eff - p| <= 2^-17)."""
-    return int(min(65535, max(0, round(float(p) * 65536.0))))
+    """Drop threshold on a 15-bit lane; p_eff = thr / 32768 (|p_eff - p| <= 2^-16); p <= 0.96875."""
+    thr = int(max(0, round(float(p) * 32768.0)))
+    if thr > THR_MAX:
+        raise ValueError("dropout rate above 0.96875")
+    return thr
 
 
 def scale_of(thr: int) -> float:
-    return 65536.0 / (65536.0 - thr)
+    return 32768.0 / (32768.0 - thr)
+
+
+def lanes15(w):
+    """The 16 fifteen-bit lanes of Philox blocks w = (w0, w1, w2, w3) (uint32 arrays of one shape) -> uint32 array (..., 16)."""
+    out = np.empty(np.shape(w[0]) + (16,), dtype=np.uint32)
+    for e in range(16):
+        i, j = e >> 2, e & 3
+        hi = (w[i] >> np.uint32(8 * j)) & np.uint32(0xFF)
+        lo = (w[i ^ 1] >> np.uint32(8 * j)) & np.uint32(0xFF)
+        out[..., e] = ((hi << np.uint32(8)) | lo) & np.uint32(0x7FFF)
+    return out
 
 
 def keep_mask(rows: int, n: int, site: int, seed: int, step: int, p: float) -> np.ndarray:
@@ -66,16 +85,12 @@ def keep_mask(rows: int, n: int, site: int, seed: int, step: int, p: float) -> n
     thr = threshold(p)
     if thr == 0:
         return np.ones((rows, n), dtype=bool)
-    groups = (n + 7) // 8
+    groups = (n + 15) // 16
     g = np.arange(groups, dtype=np.uint32)[None, :]
     r = np.arange(rows, dtype=np.uint32)[:, None]
     w = philox4x32(g, r, np.uint32(site), np.uint32(step & 0xFFFFFFFF), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
-    lanes = np.empty((rows, groups, 8), dtype=np.uint32)
-    for i in range(4):
-        wi = np.broadcast_to(w[i], (rows, groups))
-        lanes[:, :, 2 * i] = wi & np.uint32(0xFFFF)
-        lanes[:, :, 2 * i + 1] = wi >> np.uint32(16)
-    return (lanes.reshape(rows, groups * 8)[:, :n] >= thr)
+    w = [np.broadcast_to(x, (rows, groups)) for x in w]
+    return (lanes15(w).reshape(rows, groups * 16)[:, :n] >= thr)
 
 
 def apply(x, site: int, seed: int, step: int, p: float):

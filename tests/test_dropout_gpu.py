@@ -37,8 +37,8 @@ def test_dropout_kernel_bit_exact_vs_numpy_philox(rows, cols, p):
     buf[:, :cols] = x
     ops.dropout(buf[:, :cols], buf[:, :cols], d)
     assert torch.equal(buf[:, :cols], want) and (buf[:, cols:] == 0).all()
-    if rows * cols > 50000:  # keep rate = 1 - thr / 65536 within 4 sigma
-        pe = d.thr / 65536.0
+    if rows * cols > 50000:  # keep rate = 1 - thr / 32768 within 4 sigma
+        pe = d.thr / 32768.0
         assert abs(float(keep.float().mean()) - (1 - pe)) < 4 * math.sqrt(pe * (1 - pe) / (rows * cols))
 
 
