@@ -321,6 +321,21 @@ int lasr_rel_attn_fwd(const void* qu, const void* qv, long ldq, const void* k, c
                       int dk, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Attention backward, the two contractions that consume one (B,H,Tq,Tk) gradient tensor X (autograd backward of
+ * nets/attention.py:46-59 and :120-154 -- matrix_ac / matrix_bd), in ONE tcgen05 kernel that streams X through HBM once:
+ *     dl[b, i, 64h:64h+64] = sum_j X[b,h,i,j] r[b, j, 64h:]          X = dscores: r = k,   dl = d(q + pos_bias_u)
+ *     dr[b, j, 64h:64h+64] = sum_i X[b,h,i,j] l[b, i, 64h:]          X = dscores: l = q+u, dr = dk
+ *   X (B,H,Tq,ldx) bf16 (columns [Tk,ldx) are never read); r: (B*Tk, *) rows of stride ldr, or ONE (Tk, *) matrix shared by
+ *   every utterance when r_batched = 0 (X = dbd: r = linear_pos(pos_emb)); l, dl: (B*Tq, *) rows; dr: bf16 (B*Tk, *) rows, or --
+ *   reduce_b = 1 -- fp32 (Tk, *) rows that RECEIVE (+=) the sum over the batch (X = dbd: l = q + pos_bias_v, dr = d pos).
+ *   colsum (H*64 floats, may be NULL; reduce_b = 0 only) += column sums of dr over (b, j): the bias gradient of the projection
+ *   that produced r.  Replaces two batched lasr_gemm launches for dk == 64, Tk <= 320 (lasr_attn_bwd_pair_supported).
+ * ------------------------------------------------------------------------------------------------ */
+int lasr_attn_bwd_pair_supported(int Tk, int dk);
+int lasr_attn_bwd_pair(const void* x, int64_t ldx, const void* r, int64_t ldr, int r_batched, const void* l, int64_t ldl, void* dl, int64_t lddl,
+                       void* dr, int64_t lddr, int reduce_b, float* colsum, int B, int H, int Tq, int Tk, int dk, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Label-smoothed KL on the decoder logits, forward + gradient (criterions/hybrid_ctc_attn.py:49-64;
  * targets built on the fly from ys/ylens as models/u2.py:323-328), and the hybrid mix (:78).
  * row_loss: B*(lmax+1) floats.  hybrid_combine: out[0]=loss, out[1]=ctc term, out[2]=attention term.

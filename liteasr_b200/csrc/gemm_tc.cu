@@ -279,6 +279,21 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, const Unit& w, 
             float4 ba = b4;
             if constexpr (MODE == EPI_PLAIN || MODE == EPI_RES) { ba.x *= alpha; ba.y *= alpha; ba.z *= alpha; ba.w *= alpha; }
             float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+            // dropout: one Philox call covers 16 columns = the four lanes of a quad (same rows, same 16-column group), so the quad
+            // splits the row groups: lane t of the quad evaluates row groups i = t (mod 4) and one shuffle per row group hands every
+            // lane its nibble -- ITERS / 4 calls per lane instead of ITERS
+            uint32_t knib = 0xffffffffu;  // 4 keep bits per row group
+            if (drop_on) {
+                static_assert(ITERS % 4 == 0 && ITERS <= 8, "quad sharing of the dropout masks");
+                knib = 0u;
+#pragma unroll
+                for (int s = 0; s < ITERS / 4; ++s) {
+                    const uint32_t k16 = drop_keep16(dk, (uint32_t)(row_base + rsub + RGRP * (4 * s + (lane & 3))), (uint32_t)col >> 4);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        knib |= ((__shfl_sync(0xffffffffu, k16, (lane & ~3) | t) >> (col & 12)) & 15u) << (4 * (4 * s + t));
+                }
+            }
 #pragma unroll
             for (int i = 0; i < ITERS; ++i) {
                 float4 f = *reinterpret_cast<const float4*>(((i & 1) ? rd1 : rd0) + i * (RGRP * ROWB));
@@ -288,7 +303,7 @@ __device__ __forceinline__ void epilogue_unit(const TcParams& p, const Unit& w, 
                     float kx = 1.f, ky = 1.f, kz = 1.f, kw = 1.f;
                     uint32_t keep4 = 15u;
                     if (drop_on) {
-                        keep4 = drop_keep4(dk, (uint32_t)(row_base + rsub + RGRP * i), (uint32_t)col);
+                        keep4 = (knib >> (4 * i)) & 15u;
                         kx = (keep4 & 1u) ? dk.scale : 0.f; ky = (keep4 & 2u) ? dk.scale : 0.f;
                         kz = (keep4 & 4u) ? dk.scale : 0.f; kw = (keep4 & 8u) ? dk.scale : 0.f;
                     }
@@ -454,18 +469,10 @@ __device__ __forceinline__ void epilogue_unit_tma(const TcParams& p, const Unit&
         const int col0 = w.n0 + cc;
         if (col0 >= col_limit) break;  // warp-uniform
         const bool full = col0 + 32 <= col_limit;
-        // dropout: the keep masks of this thread's 32-column row segment, computed BEFORE the TMEM load is waited for:
-        // they depend on nothing the accumulator holds, so their ~300 integer instructions fill issue slots the latency chain
-        // TMEM -> math -> staging leaves idle
+        // dropout: the keep masks of this thread's 32-column row segment are evaluated between the ISSUE of the TMEM load and
+        // its wait: they depend on nothing the accumulator holds, so the Philox latency chain hides behind the load's
         // (two calls: packed 0xffff / 0 lane masks, mk[t] = columns col0 + 2t and col0 + 2t + 1 -- philox.cuh)
         uint32_t mk[16];
-        if (drop_on) {
-            uint32_t h0[8], h1[8];
-            drop_masks16(dk, (uint32_t)row, (uint32_t)col0 >> 4, h0);
-            drop_masks16(dk, (uint32_t)row, ((uint32_t)col0 >> 4) + 1u, h1);
-#pragma unroll
-            for (int t = 0; t < 8; ++t) { mk[t] = h0[t]; mk[8 + t] = h1[t]; }
-        }
         // row-wise global operands first (in flight while TMEM is read)
         float4 r4[MODE == EPI_RES ? 8 : 1];
         uint4 s4[DACT ? 4 : 1];
@@ -495,7 +502,19 @@ __device__ __forceinline__ void epilogue_unit_tma(const TcParams& p, const Unit&
             }
         }
         float v[32];
-        tc_ld32(taddr + (uint32_t)cc, v);
+        if constexpr (DROP) {
+            tc_ld32_issue(taddr + (uint32_t)cc, v);
+            if (drop_on) {
+                uint32_t h0[8], h1[8];
+                drop_masks16(dk, (uint32_t)row, (uint32_t)col0 >> 4, h0);
+                drop_masks16(dk, (uint32_t)row, ((uint32_t)col0 >> 4) + 1u, h1);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) { mk[t] = h0[t]; mk[8 + t] = h1[t]; }
+            }
+            tc_ld_wait32(v);
+        } else {
+            tc_ld32(taddr + (uint32_t)cc, v);
+        }
         // ---- finish the row in place
         if constexpr (MODE == EPI_ACC) {
 #pragma unroll

@@ -91,7 +91,7 @@ __device__ __forceinline__ float4 load4(const TD* p) {
 // regenerated here (philox.cuh) and applied to dx_lo and to the column sums; dx itself (the residual-stream gradient) is not
 // masked.  TLO = bf16 (tensor-core mode) or float (fp32 parity mode, where the masked copy is a second fp32 tensor).
 template <typename TD, typename TLO, int NV>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TD* __restrict__ dy, long lddy,
+__global__ void __launch_bounds__(256, (NV <= 2 ? 3 : 1)) layernorm_bwd_kernel(const TD* __restrict__ dy, long lddy,
                                                             const float* __restrict__ x, long ldx,
                                                             const float* __restrict__ mean,
                                                             const float* __restrict__ rstd,
@@ -204,6 +204,20 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TD* __restrict
     }
 }
 
+// CTAs of 256 threads of `kern` that are resident at once on the device (cached per instantiation), capped by the row count
+template <typename K>
+static int resident_grid(K kern, int rows) {
+    static int cap = 0;
+    if (!cap) {
+        int dev = 0, sms = 148, occ = 2;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0) != cudaSuccess || occ <= 0) occ = 2;
+        cap = sms * occ;
+    }
+    const int need = ceil_div(rows, 8);
+    return need < cap ? need : cap;
+}
+
 }  // namespace lasr
 
 extern "C" {
@@ -256,16 +270,19 @@ int lasr_layernorm_bwd_drop(const void* dy, int dy_dtype, int64_t lddy, const fl
     LASR_REQUIRE(((uintptr_t)dgamma & 15) == 0 && ((uintptr_t)dbeta & 15) == 0 && ((uintptr_t)colsum & 15) == 0,
                  "layernorm_bwd: dgamma/dbeta/colsum must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    int grid = ceil_div(rows, 8);
-    if (grid > 148 * 3) grid = 148 * 3;
+    // the kernel walks the rows with a grid stride and keeps its column partials in registers: launch exactly the CTAs that are
+    // resident at once (444 CTAs on 296 slots ran as one and a half waves, the second at half occupancy)
 #define LASR_LNB(TD, NV)                                                                                                            \
     do {                                                                                                                            \
-        if (lo_dtype == LASR_F32)                                                                                                   \
+        if (lo_dtype == LASR_F32) {                                                                                                 \
+            const int grid = resident_grid(layernorm_bwd_kernel<TD, float, NV>, rows);                                              \
             launch_pdl(layernorm_bwd_kernel<TD, float, NV>, grid, 256, 0, st, (const TD*)dy, lddy, x, ldx, mean, rstd, gamma, dx, lddx,  \
                        accumulate, dgamma, dbeta, rows, d, (float*)dx_lo, lddxlo, colsum, colsum_scale, drop);                      \
-        else                                                                                                                        \
+        } else {                                                                                                                    \
+            const int grid = resident_grid(layernorm_bwd_kernel<TD, bf16, NV>, rows);                                               \
             launch_pdl(layernorm_bwd_kernel<TD, bf16, NV>, grid, 256, 0, st, (const TD*)dy, lddy, x, ldx, mean, rstd, gamma, dx, lddx,   \
                        accumulate, dgamma, dbeta, rows, d, (bf16*)dx_lo, lddxlo, colsum, colsum_scale, drop);                       \
+        }                                                                                                                           \
     } while (0)
 #define LASR_LNB_D(TD)                  \
     do {                                \

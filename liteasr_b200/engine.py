@@ -50,6 +50,7 @@ class Engine:
         self.dev = store.device
         # LASR_FUSED_ATTN=0: developer switch back to GEMM -> softmax kernel -> GEMM for the rel-pos attention forward
         self.fused_attn = os.environ.get("LASR_FUSED_ATTN", "1") != "0"
+        self.fused_attn_bwd = os.environ.get("LASR_FUSED_ATTN_BWD", "1") != "0"
         # LASR_FFN_RECOMPUTE=1 (developer switch, off): fc1 of a Swish FFN does not save its pre-activation and the backward GEMM
         # recomputes it into a second TMEM accumulator.  Saves 154 MB written + 135 MB read per FFN at C2/B=126 but measured
         # SLOWER (32.0 vs 30.7 ms per step): two accumulators force 128-column N tiles, and at K = 256 the four operand slabs of a
@@ -277,6 +278,15 @@ class Engine:
         dsc = _empty((B, H, Tq, ld), self.adt, self.dev)
         dbd = _empty((B, H, Tq, ld), self.adt, self.dev) if c.qv is not None else None
         ops.attn_softmax_bwd(c.probs, dprobs, dsc, dbd, c.scale, Tk)
+        pair = (self.fused_attn_bwd and self.adt == torch.bfloat16 and ops.attn_bwd_pair_supported(Tk, dk) and bq is None
+                and c.k.stride(0) % 8 == 0 and c.q.stride(0) % 8 == 0 and dq.stride(0) % 8 == 0 and dk_.stride(0) % 8 == 0
+                and (c.qv is None or (c.p.stride(0) % 8 == 0 and c.qv.stride(0) % 8 == 0 and dqv.stride(0) % 8 == 0)))
+        if pair:
+            # each (B,H,Tq,Tk) gradient tensor feeds its two contractions from ONE pass through HBM (csrc/attn_pair.cu)
+            ops.attn_bwd_pair(dsc, c.k, c.q, dq, dk_, B, H, Tq, Tk, dk, colsum=bk)
+            if c.qv is not None:
+                ops.attn_bwd_pair(dbd, c.p, c.qv, dqv, dp32, B, H, Tq, Tk, dk, r_batched=False, reduce_b=True)
+            return
         # dQ[i] = sum_j ds[i,j] K[j] ; dK[j] = sum_i ds[i,j] Q[i]
         ops.gemm(dsc, c.k, dq, Tq, dk, Tk, lda=ld, ldb=c.k.stride(0), ldc=dq.stride(0), tb=True, batch=(B, H), sa=bs,
                  sb=(Tk * c.k.stride(0), dk), sc=(Tq * dq.stride(0), dk), colsum=bq, cs=(0, dk))

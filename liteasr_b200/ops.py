@@ -435,6 +435,24 @@ def rel_attn_fwd(qu, qv, k, v, pos, probs, o, lens, mask_mode, scale, B, H, T, d
                                             _i(B), _i(H), _i(T), _i(dk), _stream()), "rel_attn_fwd")
 
 
+def attn_bwd_pair_supported(Tk: int, dk: int) -> bool:
+    return bool(_lib.lib().lasr_attn_bwd_pair_supported(_i(Tk), _i(dk)))
+
+
+def attn_bwd_pair(x, r, l, dl, dr, B, H, Tq, Tk, dk, r_batched=True, reduce_b=False, colsum=None):
+    """dl = X . r and dr = X^T . l per (utterance, head) with X (B,H,Tq,ld) read once (include/lasr.h ``lasr_attn_bwd_pair``)."""
+    _require_cuda(x, r, l, dl, dr, colsum)
+    for t in (x, r, l, dl):
+        if t.dtype != torch.bfloat16:
+            raise TypeError("attn_bwd_pair takes bf16 operands")
+    if dr.dtype != (torch.float32 if reduce_b else torch.bfloat16):
+        raise TypeError("attn_bwd_pair: dr is fp32 with reduce_b, bf16 otherwise")
+    assert x.is_contiguous() and x.shape[:3] == (B, H, Tq) and r.stride(1) == 1 and l.stride(1) == 1 and dl.stride(1) == 1 and dr.stride(1) == 1
+    _lib.check(_lib.lib().lasr_attn_bwd_pair(_ptr(x), _l(x.shape[-1]), _ptr(r), _l(r.stride(0)), _i(1 if r_batched else 0), _ptr(l), _l(l.stride(0)),
+                                             _ptr(dl), _l(dl.stride(0)), _ptr(dr), _l(dr.stride(0)), _i(1 if reduce_b else 0), _ptr(colsum),
+                                             _i(B), _i(H), _i(Tq), _i(Tk), _i(dk), _stream()), "attn_bwd_pair")
+
+
 def attn_softmax_bwd(probs, dprobs, dsc, dbd, scale, Tk):
     B, H, Tq, ld = probs.shape
     _lib.check(_lib.lib().lasr_attn_softmax_bwd(_ptr(probs), _ptr(dprobs), _i(dtype_code(dprobs)), _ptr(dsc), _ptr(dbd), _i(dtype_code(probs)), _f(scale),
