@@ -282,8 +282,27 @@ def _record_gemms(step_fn, batch):
         rec.append((ffn_orig, (dy, g, w2, w1, dh, dln), kw, 4.0 * m * d * f, float(byt), d))
         ffn_orig(dy, g, w2, w1, dh, dln, **kw)
 
+    pair_orig = ops.attn_bwd_pair
+
+    def pair_recorder(x, r, l, dl, dr, B, H, Tq, Tk, dk, **kw):  # the paired attention-backward contractions: 2 x (2 B H Tq Tk dk) flops
+        byt = B * H * Tq * Tk * x.element_size() + sum(t.numel() * t.element_size() for t in (l, dl))
+        byt += (B if kw.get("r_batched", True) else 1) * Tk * H * dk * r.element_size() + dr.numel() * dr.element_size()
+        rec.append((pair_orig, (x, r, l, dl, dr, B, H, Tq, Tk, dk), kw, 4.0 * B * H * Tq * Tk * dk, float(byt), dk))
+        pair_orig(x, r, l, dl, dr, B, H, Tq, Tk, dk, **kw)
+
+    ffwd_orig = ops.ffn_fwd
+
+    def ffwd_recorder(ln, w1, b1, w2, b2, res, a, g, out, **kw):  # the fused feed-forward forward: two contractions (2 x 2 m d f flops)
+        m, d = ln.shape
+        f = w1.shape[0]
+        byt = sum(t.numel() * t.element_size() for t in (ln, w1, w2, res, a, g, out))
+        rec.append((ffwd_orig, (ln, w1, b1, w2, b2, res, a, g, out), kw, 4.0 * m * d * f, float(byt), d))
+        ffwd_orig(ln, w1, b1, w2, b2, res, a, g, out, **kw)
+
     ops.gemm = recording
     ops.ffn_bwd = ffn_recorder
+    ops.ffn_fwd = ffwd_recorder
+    ops.attn_bwd_pair = pair_recorder
     for n in conv_names:
         setattr(ops, n, conv_recorder(n))
     try:
@@ -292,6 +311,8 @@ def _record_gemms(step_fn, batch):
     finally:
         ops.gemm = orig
         ops.ffn_bwd = ffn_orig
+        ops.ffn_fwd = ffwd_orig
+        ops.attn_bwd_pair = pair_orig
         for n in conv_names:
             setattr(ops, n, conv_orig[n])
     return rec
@@ -643,7 +664,7 @@ def run_gpu(args, wl):
     tflops = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     traffic = _traffic()
     fam_traffic = (traffic or {}).get("gemm_family_bytes_per_step")
-    roof = {"kernel": "gemm_tc_kernel + ffn_bwd_kernel (tcgen05.mma bf16: every GEMM, implicit-GEMM convolution and fused FFN backward of one step)" if args.precision == "bf16" else "gemm_simt_kernel",
+    roof = {"kernel": "gemm_tc_kernel + ffn_fwd_kernel + ffn_bwd_kernel + attn_pair_kernel (tcgen05.mma bf16: every GEMM, implicit-GEMM convolution, fused FFN forward / backward and paired attention-backward contraction of one step)" if args.precision == "bf16" else "gemm_simt_kernel",
             "bound": "tensor", "achieved": tflops, "peak": pk["tc_sustained"], "unit": "TFLOP/s", "frac": tflops / pk["tc_sustained"],
             "traffic": fam_traffic,
             "traffic_note": ((traffic or {}).get("note") if traffic else "no ncu capture found under profiles/"),

@@ -144,6 +144,23 @@ int lasr_ffn_bwd(const void* dy, int64_t lddy, const void* g, int64_t ldg, const
                  void* dh, int64_t lddh, void* dln, int64_t lddln, float* colsum, float alpha, int M, int d, int f, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Fused FORWARD of the same block (nets/feed_forward.py:18-19 with the Swish activation, inside nets/conformer_layer.py:37-47
+ * and :58-66: x + ff_scale * dropout(ff(LN x))), bf16 / tcgen05, one persistent kernel:
+ *     a   (M, f) = drop_in(swish(ln (M, d) . W1 (f, d)^T + b1))         bf16, kept for fc2's weight gradient
+ *     g   (M, f) = swish'(ln . W1^T + b1), 0 where drop_in dropped       bf16, what lasr_ffn_bwd multiplies by
+ *     out (M, d) = res + drop_out(alpha * (a . W2 (d, f)^T + b2))         fp32 residual stream (res fp32, may alias nothing)
+ * The pre-activation never exists in memory and a is not read back: a 128-row tile of a lives as 64-column chunks that go
+ * TMEM -> registers -> a shared-memory slab that is the A operand of the second MMA and the source of its bulk tensor store.
+ * Replaces lasr_gemm(act = Swish, aux_deriv) + lasr_gemm(res) for the shapes of lasr_ffn_fwd_supported (= lasr_ffn_bwd's).
+ * Dropout: the two sites share drop_state; *_thr = 0 switches a site off (see "Dropout" below).
+ * ------------------------------------------------------------------------------------------------ */
+int lasr_ffn_fwd_supported(int d, int f);
+int lasr_ffn_fwd(const void* ln, int64_t ldln, const void* w1, int64_t ldw1, const float* b1, const void* w2, int64_t ldw2, const float* b2,
+                 const float* res, int64_t ldres, void* a, int64_t lda, void* g, int64_t ldg, float* out, int64_t ldout, float alpha, int M, int d,
+                 int f, const void* drop_state, uint32_t in_site, uint32_t in_thr, float in_scale, uint32_t out_site, uint32_t out_thr,
+                 float out_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * CTC forward-backward fused with the log-softmax backward.
  * Replaces criterions/hybrid_ctc_attn.py:67-75 (transpose + log_softmax + nn.CTCLoss(sum) and the
  * autograd backward of all three).  logits (T,B,V) with element strides (st, sb, 1) so the model's

@@ -13,8 +13,8 @@
 //     boxes, K = 128 queries): only the UMMA descriptor differs (LBO = box pitch), nothing is transposed or copied;
 //   * R (all keys of the unit, MN-major B of the first contraction) is loaded once per unit and double-buffered across units,
 //     the L tile (MN-major B of the second contraction) per query tile;
-//   * accumulators in tensor memory: dL tile 2 x 64 columns (double-buffered against the epilogue), dR 3 x 64 columns (three
-//     128-key M tiles), accumulated over the unit's query tiles -- and, in the batch-reduced mode (dP), over the units of the
+//   * accumulators in tensor memory (all 512 columns): dL tile 2 x 64 columns, dR 2 x (3 x 64) columns (three 128-key M tiles), both
+//     double-buffered against the epilogue; dR is accumulated over the unit's query tiles -- and, in the batch-reduced mode (dP), over the units of the
 //     same head the CTA owns, so that the fp32 red.add traffic is one flush per (CTA, head) instead of one per utterance;
 //   * box pair p of the X buffer is refilled for the next tile as soon as the second contraction has consumed it
 //     (tcgen05.commit -> mbarrier), so loads of tile n + 1 overlap the MMAs of tile n without a second 80 KB buffer.
@@ -39,10 +39,10 @@ constexpr int OFF_L = OFF_R + 2 * RBUF;              // 2 buffers x 128 rows x 1
 constexpr int OFF_BAR = OFF_L + 2 * BOX;
 constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
 static_assert(SMEM_BYTES <= 232448, "shared-memory budget");
-constexpr int TM_DL = 0, TM_DR = 128;                // TMEM columns: dL 2 x 64, dR 3 x 64
+constexpr int TM_DL = 0, TM_DR = 128, DR_COLS = MAXPAIR * DK;  // TMEM columns: dL 2 x 64, dR 2 x (3 x 64): both double-buffered against the epilogue
 
 enum { R_FULL = 0, R_EMPTY = 2, L_FULL = 4, L_EMPTY = 6, X_FULL = 8, X_EMPTY = X_FULL + MAXPAIR, DL_FULL = X_EMPTY + MAXPAIR, DL_EMPTY = DL_FULL + 2,
-       DR_FULL = DL_EMPTY + 2, DR_EMPTY, NBARS };
+       DR_FULL = DL_EMPTY + 2, DR_EMPTY = DR_FULL + 2, NBARS = DR_EMPTY + 2 };
 
 struct Params {
     bf16* dl;        // (B * Tq, *) rows, head h at column h * 64
@@ -93,7 +93,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap m_x, const __grid_constant_
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < NBARS; ++i) {
-            const bool epi = (i == DL_EMPTY || i == DL_EMPTY + 1 || i == DR_EMPTY);
+            const bool epi = (i == DL_EMPTY || i == DL_EMPTY + 1 || i == DR_EMPTY || i == DR_EMPTY + 1);
             mbar_init(bars + i, epi ? EPI_W : 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -153,7 +153,8 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap m_x, const __grid_constant_
                 const int h = u / p.B;
                 const uint32_t ru = (uint32_t)(u - u0), rs = ru & 1u;
                 mbar_wait(bars + R_FULL + rs, (ru >> 1) & 1u);
-                if (fresh) mbar_wait(bars + DR_EMPTY, (flushes & 1u) ^ 1u);  // the epilogue has read the previous flush out of TMEM
+                const uint32_t fb = flushes & 1u;  // dR accumulator buffer of this flush group
+                if (fresh) mbar_wait(bars + DR_EMPTY + fb, ((flushes >> 1) & 1u) ^ 1u);  // the epilogue has read this buffer's previous flush
                 for (int t = 0; t < p.ntile; ++t, ++g) {
                     const uint32_t ls = g & 1u, lph = (g >> 1) & 1u;
                     mbar_wait(bars + L_FULL + ls, lph);
@@ -175,7 +176,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap m_x, const __grid_constant_
                         // dR[keys of the pair, :] += X[:, pair]^T . L tile
 #pragma unroll
                         for (int kk = 0; kk < 8; ++kk)
-                            tc_mma_bf16(tmem_base + TM_DR + pr * DK, d_xm + (uint64_t)((2 * pr * BOX + kk * 2048) >> 4), dl_b + (uint64_t)((kk * 2048) >> 4), id2,
+                            tc_mma_bf16(tmem_base + TM_DR + fb * DR_COLS + pr * DK, d_xm + (uint64_t)((2 * pr * BOX + kk * 2048) >> 4), dl_b + (uint64_t)((kk * 2048) >> 4), id2,
                                         (!fresh || t > 0 || kk > 0) ? 1u : 0u);
                         tc_commit(bars + X_EMPTY + pr);
                     }
@@ -186,7 +187,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap m_x, const __grid_constant_
                 fresh = false;
                 const bool flush = !p.reduce_b || u + 1 == u1 || (u + 1) / p.B != h;
                 if (flush) {
-                    tc_commit(bars + DR_FULL);
+                    tc_commit(bars + DR_FULL + fb);
                     ++flushes;
                     fresh = true;
                 }
@@ -222,12 +223,13 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap m_x, const __grid_constant_
             }
             const bool flush = !p.reduce_b || u + 1 == u1 || (u + 1) / p.B != h;
             if (!flush) continue;
-            mbar_wait(bars + DR_FULL, flushes & 1u);
+            const uint32_t fb = flushes & 1u;
+            mbar_wait(bars + DR_FULL + fb, (flushes >> 1) & 1u);
             ++flushes;
             tc_fence_after();
             for (int pr = 0; pr < p.npair; ++pr) {
                 float v[32];
-                tc_ld32(lane_addr + TM_DR + pr * DK + 32 * half, v);
+                tc_ld32(lane_addr + TM_DR + fb * DR_COLS + pr * DK + 32 * half, v);
                 const int key = pr * TM + r;
                 if (key < p.Tk) {
                     if (p.reduce_b) {
@@ -252,7 +254,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap m_x, const __grid_constant_
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bars + DR_EMPTY);
+            if (lane == 0) mbar_arrive(bars + DR_EMPTY + fb);
         }
     }
     tc_fence_before();

@@ -20,6 +20,7 @@
 namespace lasr {
 
 constexpr int KW = 15, HALO = 7, TCH = 32;
+constexpr int NRED = KW + 3;  // depthwise taps + bias + the two pointwise-bias column sums
 
 template <typename TD> __device__ __forceinline__ float2 ld2(const TD* p);
 template <> __device__ __forceinline__ float2 ld2<float>(const float* p) { return *reinterpret_cast<const float2*>(p); }
@@ -301,6 +302,119 @@ __global__ void __launch_bounds__(256, 4) glu_dwconv_fwd_kernel(const TD* __rest
     }
 }
 
+// ---------------------------------------------------------------- fwd 1 (streaming, bf16, d % 64 == 0)
+// One CTA = one utterance x 64 channels, streaming the T' frames in 32-row chunks: no halo re-reads, no tile quantisation at
+// T' = 299, and -- the point -- the loads of chunk j + 2 (cp.async, 16 B per thread and tensor half) are in flight while chunk j is
+// computed.  The tiled kernel above alternates a load phase and a compute phase per CTA and is ~60 % issue-bound by ~1000
+// instructions per thread (ncu: 21.7 M warp instructions, 38 us at C2 / B = 126, 2 TB/s).
+//   raw ring (3 stages)  : the value / gate halves of a chunk as they sit in memory; every thread converts exactly the 16 bytes it
+//                          fetched itself (no barrier between the copy and the GLU)
+//   g ring (64 rows)     : GLU outputs, fp32; chunk j occupies rows [32 j, 32 j + 32) mod 64, so the 14 rows of history a chunk needs
+//                          are still there
+//   outputs lag 7 rows   : iteration j writes z rows [32 j - 7, 32 j + 25) from g rows [32 j - 14, 32 j + 32); one extra iteration
+//                          flushes the tail against zero rows
+// Statistics: per-thread running sums over the whole utterance, reduced over the four row groups at the end and written as ONE
+// partial row per (utterance, channel block); the utterance's other rows of the ABI's 32-step layout are zeroed.
+constexpr int SR = 32, SCH = 64, SRING = 64, SSTG = 3;
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    const int n = valid ? 16 : 0;  // src-size 0: the 16 bytes are zero-filled, nothing is read
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// sigmoid(x) = 0.5 tanh(x / 2) + 0.5: one MUFU op instead of ex2 + rcp (rel. error ~2^-11, the inputs are bf16)
+__device__ __forceinline__ float sigmoid_tanh(float x) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+    return fmaf(t, 0.5f, 0.5f);
+}
+__device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+
+__global__ void __launch_bounds__(256, 4) glu_dwconv_fwd_stream_kernel(const bf16* __restrict__ y2, long ldy, const float* __restrict__ w,
+                                                                       const float* __restrict__ bias, float* __restrict__ z,
+                                                                       float* __restrict__ partial, int T, int d) {
+    LASR_PDL_SYNC();
+    __shared__ __align__(16) bf16 raw[SSTG][2][SR][SCH];
+    __shared__ __align__(16) float ring[SRING][SCH];
+    __shared__ float wt[SCH * KW];
+    __shared__ float red[2][4][SCH];
+    const int b = blockIdx.y, c0 = blockIdx.x * SCH, tid = threadIdx.x;
+    const int nch = (T + SR - 1) / SR;
+    const int lrow = tid >> 3, lpc = (tid & 7) * 8;     // loader / GLU role: one row, 8 channels
+    const int c = tid & (SCH - 1), rg = tid >> 6;       // convolution role: one channel, 8 rows
+    const bf16* src0 = y2 + (long)b * T * ldy + c0 + lpc;
+    auto issue = [&](int j) {
+        const int t = j * SR + lrow;
+        const bool ok = j < nch && t < T;
+        const bf16* sp = src0 + (long)(ok ? t : 0) * ldy;
+        cp_async16(&raw[j % SSTG][0][lrow][lpc], sp, ok);
+        cp_async16(&raw[j % SSTG][1][lrow][lpc], sp + d, ok);
+        cp_async_commit();
+    };
+    issue(0);
+    issue(1);
+    for (int i = tid; i < SCH * KW; i += 256) wt[i] = w[(long)c0 * KW + i];
+    for (int i = tid; i < SRING * SCH / 4; i += 256) reinterpret_cast<float4*>(&ring[0][0])[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    float wk[KW];
+#pragma unroll
+    for (int k = 0; k < KW; ++k) wk[k] = wt[c * KW + k];
+    const float b0 = bias[c0 + c];
+    float s = 0.f, q = 0.f;
+    float* zc = z + (long)b * T * d + c0 + c;
+    for (int j = 0; j <= nch; ++j) {
+        issue(j + 2);
+        cp_async_wait<2>();  // this thread's copies of chunk j have landed
+        const uint4 v = *reinterpret_cast<const uint4*>(&raw[j % SSTG][0][lrow][lpc]);
+        const uint4 gt = *reinterpret_cast<const uint4*>(&raw[j % SSTG][1][lrow][lpc]);
+        float4 g0, g1;
+        g0.x = bf16lo(v.x) * sigmoid_tanh(bf16lo(gt.x)); g0.y = bf16hi(v.x) * sigmoid_tanh(bf16hi(gt.x));
+        g0.z = bf16lo(v.y) * sigmoid_tanh(bf16lo(gt.y)); g0.w = bf16hi(v.y) * sigmoid_tanh(bf16hi(gt.y));
+        g1.x = bf16lo(v.z) * sigmoid_tanh(bf16lo(gt.z)); g1.y = bf16hi(v.z) * sigmoid_tanh(bf16hi(gt.z));
+        g1.z = bf16lo(v.w) * sigmoid_tanh(bf16lo(gt.w)); g1.w = bf16hi(v.w) * sigmoid_tanh(bf16hi(gt.w));
+        __syncthreads();  // the previous iteration's convolution has read the rows this chunk overwrites
+        float* rp = &ring[(j * SR + lrow) & (SRING - 1)][lpc];
+        *reinterpret_cast<float4*>(rp) = g0;
+        *reinterpret_cast<float4*>(rp + 4) = g1;
+        __syncthreads();
+        const int base = j * SR - 2 * HALO + 8 * rg;  // window row 0; output row i of this thread = base + HALO + i
+        float win[8 + KW - 1];
+#pragma unroll
+        for (int k = 0; k < 8 + KW - 1; ++k) win[k] = ring[(base + k) & (SRING - 1)][c];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int t = base + HALO + i;
+            if (t >= 0 && t < T) {
+                float a = b0;
+#pragma unroll
+                for (int k = 0; k < KW; ++k) a = fmaf(wk[k], win[i + k], a);
+                zc[(long)t * d] = a;
+                s += a;
+                q = fmaf(a, a, q);
+            }
+        }
+    }
+    cp_async_wait<0>();
+    red[0][rg][c] = s;
+    red[1][rg][c] = q;
+    __syncthreads();
+    if (tid < 2 * SCH) {
+        const int which = tid >> 6, cc = tid & (SCH - 1);
+        const float v = (red[which][0][cc] + red[which][1][cc]) + (red[which][2][cc] + red[which][3][cc]);
+        float* part = partial + (long)b * nch * 2 * d + which * d + c0 + cc;
+        part[0] = v;
+        for (int r = 1; r < nch; ++r) part[(long)r * 2 * d] = 0.f;
+    }
+}
+
 // ---------------------------------------------------------------- column reduction of [nblk][2][d] partials (double)
 // One thread-block CLUSTER of CL CTAs per 32 channels: every CTA (32 channels x RG row groups = 1024 threads) reduces a
 // 1/CL slice of the rows, rank 0 then adds the CL slice sums through distributed shared memory in a fixed order
@@ -424,7 +538,6 @@ struct BwdSmem {
     float sg[FT][FC];
     float wt[FC * KW];
 };
-constexpr int NRED = KW + 3;
 
 template <typename TD>
 __global__ void __launch_bounds__(256, 3) dwconv_glu_bwd_kernel(const TD* __restrict__ da, const float* __restrict__ z,
@@ -552,6 +665,11 @@ __global__ void __launch_bounds__(256, 3) dwconv_glu_bwd_kernel(const TD* __rest
     }
 }
 
+// (A streaming variant of the backward kernel -- the scheme of glu_dwconv_fwd_stream_kernel with three more rings -- was built and
+//  measured: 76 us against 63 us for the tiled kernel above at C2 / B = 126.  Both execute ~40 M warp instructions; the streaming one
+//  needs 105 KB of shared memory and 119 registers, i.e. 2 CTAs per SM, and the kernel is bound by its instruction stream (issue
+//  slots 56-63 % busy), not by loads in flight.  profiles/r2_convmod_stream.txt.)
+
 // second stage of the depthwise-weight / bias / pointwise-bias gradient: block (32 channels, RG row groups), grid (d/32, KW+3)
 // (already 144 CTAs of 1024 threads at d = 256: a cluster split like bn_reduce's measured 3x slower here)
 __global__ void __launch_bounds__(32 * RG) dwconv_reduce_kernel(const float* __restrict__ wpartial, int nblk, int d, float* __restrict__ dw,
@@ -588,6 +706,12 @@ int lasr_glu_dwconv_fwd(const void* y2, int dtype, int64_t ldy, const float* w, 
     LASR_REQUIRE(y2 && w && bias && z && partial && B > 0 && T > 0 && d > 0 && d % 2 == 0 && ldy % 2 == 0, "glu_dwconv_fwd: bad args");
     cudaStream_t st = (cudaStream_t)stream;
     const bool fast = fast_d(d) && ldy % 4 == 0 && ((uintptr_t)y2 & 15) == 0 && ((uintptr_t)z & 15) == 0;
+    static int stream_on = -1;  // LASR_CONVMOD_STREAM=0: developer switch back to the tiled kernels
+    if (stream_on < 0) { const char* e = getenv("LASR_CONVMOD_STREAM"); stream_on = e ? atoi(e) : 1; }
+    if (stream_on && dtype == LASR_BF16 && d % SCH == 0 && ldy % 8 == 0 && ((uintptr_t)y2 & 15) == 0) {
+        launch_pdl(glu_dwconv_fwd_stream_kernel, dim3(d / SCH, B), 256, 0, st, (const bf16*)y2, ldy, w, bias, z, partial, T, d);
+        return check_launch("glu_dwconv_fwd");
+    }
     if (fast) {
         dim3 grid(ceil_div(T, FT), B, ceil_div(d, FC));
         if (dtype == LASR_F32) launch_pdl(glu_dwconv_fwd_kernel<float>, grid, 256, 0, st, (const float*)y2, ldy, w, bias, z, partial, T, d);

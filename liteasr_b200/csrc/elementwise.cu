@@ -191,6 +191,74 @@ __global__ void __launch_bounds__(256) pos_bias_bwd_kernel(const TD* __restrict_
     }
 }
 
+// bf16, d % 8 == 0: 16-byte loads (8 columns per thread), ~256 rows per CTA so that a launch issues one set of column-sum atomics
+// per CTA of a single wave instead of one per 64 rows (589 CTAs x 768 scalar atomics on 768 addresses at C2 / B = 126: 32 us for
+// 58 MB = 1.8 TB/s)
+__device__ __forceinline__ void acc_bf16x8(float (&acc)[8], const uint4& u) {
+    acc[0] += __uint_as_float(u.x << 16); acc[1] += __uint_as_float(u.x & 0xffff0000u);
+    acc[2] += __uint_as_float(u.y << 16); acc[3] += __uint_as_float(u.y & 0xffff0000u);
+    acc[4] += __uint_as_float(u.z << 16); acc[5] += __uint_as_float(u.z & 0xffff0000u);
+    acc[6] += __uint_as_float(u.w << 16); acc[7] += __uint_as_float(u.w & 0xffff0000u);
+}
+__device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(a << 16) + __uint_as_float(b << 16),
+                                                   __uint_as_float(a & 0xffff0000u) + __uint_as_float(b & 0xffff0000u));
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+__global__ void __launch_bounds__(256) pos_bias_bwd_wide_kernel(const bf16* __restrict__ dqu, const bf16* __restrict__ dqv, long ldi,
+                                                                bf16* __restrict__ dq, long ldq, float* __restrict__ du,
+                                                                float* __restrict__ dv, float* __restrict__ dqb, int rows, int d,
+                                                                int rows_per_cta) {
+    LASR_PDL_SYNC();
+    __shared__ float red[2][8][32][9];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = (blockIdx.x * 32 + tx) * 8;
+    const int r0 = blockIdx.y * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+    float au[8], av[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { au[e] = 0.f; av[e] = 0.f; }
+    if (c < d) {
+        int r = r0 + ty;
+        for (; r + 24 < r1; r += 32) {  // 4 rows per trip, all 8 loads issued before the first use
+            uint4 a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                a[i] = *reinterpret_cast<const uint4*>(dqu + (long)(r + 8 * i) * ldi + c);
+                b[i] = *reinterpret_cast<const uint4*>(dqv + (long)(r + 8 * i) * ldi + c);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                uint4 o;
+                o.x = add_bf16x2(a[i].x, b[i].x); o.y = add_bf16x2(a[i].y, b[i].y); o.z = add_bf16x2(a[i].z, b[i].z); o.w = add_bf16x2(a[i].w, b[i].w);
+                *reinterpret_cast<uint4*>(dq + (long)(r + 8 * i) * ldq + c) = o;
+                acc_bf16x8(au, a[i]);
+                acc_bf16x8(av, b[i]);
+            }
+        }
+        for (; r < r1; r += 8) {
+            const uint4 a = *reinterpret_cast<const uint4*>(dqu + (long)r * ldi + c), b = *reinterpret_cast<const uint4*>(dqv + (long)r * ldi + c);
+            uint4 o;
+            o.x = add_bf16x2(a.x, b.x); o.y = add_bf16x2(a.y, b.y); o.z = add_bf16x2(a.z, b.z); o.w = add_bf16x2(a.w, b.w);
+            *reinterpret_cast<uint4*>(dq + (long)r * ldq + c) = o;
+            acc_bf16x8(au, a);
+            acc_bf16x8(av, b);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { red[0][ty][tx][e] = au[e]; red[1][ty][tx][e] = av[e]; }
+    __syncthreads();
+    // thread -> one column of the CTA's 256: sum the 8 row lanes, then one atomic per column and tensor
+    const int col = threadIdx.x, cx = col >> 3, ce = col & 7, cg = blockIdx.x * 256 + col;
+    if (cg < d) {
+        float t = 0.f, u = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { t += red[0][w][cx][ce]; u += red[1][w][cx][ce]; }
+        atomicAdd(du + cg, t);
+        atomicAdd(dv + cg, u);
+        if (dqb) atomicAdd(dqb + cg, t + u);  // bias gradient of linear_q: colsum(dq) = colsum(dqu) + colsum(dqv)
+    }
+}
+
 // ------------------------------------------------------------------ decoder embedding + PE
 // out[b,l] = emb[tokens[b,l]] * scale + pe[l]   (nets/transformer_decoder.py:77-78, positional_encoding.py:49-56)
 __global__ void __launch_bounds__(256) embed_fwd_kernel(const int64_t* __restrict__ tokens, int L, const float* __restrict__ emb,
@@ -279,8 +347,16 @@ int lasr_pos_bias_fwd(const void* q, int64_t ldq, const float* u, const float* v
 int lasr_pos_bias_bwd(const void* dqu, const void* dqv, int64_t ldi, void* dq, int64_t ldq, float* du, float* dv, float* dqbias,
                       int rows, int d, int dtype, void* stream) {
     LASR_REQUIRE(dqu && dqv && dq && du && dv && rows > 0 && d % 4 == 0 && ldi % 4 == 0 && ldq % 4 == 0, "pos_bias_bwd: bad args");
-    dim3 grid(ceil_div(d, 256), ceil_div(rows, 64));
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == LASR_BF16 && d % 8 == 0 && ldi % 8 == 0 && ldq % 8 == 0 && (((uintptr_t)dqu | (uintptr_t)dqv | (uintptr_t)dq) & 15) == 0) {
+        const int cx = ceil_div(d, 256);
+        int per = ceil_div(rows, ceil_div(2 * 148, cx));  // about two CTAs per SM
+        per = ceil_div(per < 32 ? 32 : per, 8) * 8;
+        launch_pdl(pos_bias_bwd_wide_kernel, dim3(cx, ceil_div(rows, per)), 256, 0, st, (const bf16*)dqu, (const bf16*)dqv, ldi, (bf16*)dq, ldq, du, dv,
+                   dqbias, rows, d, per);
+        return check_launch("pos_bias_bwd");
+    }
+    dim3 grid(ceil_div(d, 256), ceil_div(rows, 64));
     if (dtype == LASR_F32) launch_pdl(pos_bias_bwd_kernel<float>, grid, 256, 0, st, (const float*)dqu, (const float*)dqv, ldi, (float*)dq, ldq, du, dv, dqbias, rows, d);
     else if (dtype == LASR_BF16) launch_pdl(pos_bias_bwd_kernel<bf16>, grid, 256, 0, st, (const bf16*)dqu, (const bf16*)dqv, ldi, (bf16*)dq, ldq, du, dv, dqbias, rows, d);
     else { set_error("pos_bias_bwd: bad dtype"); return LASR_ERR_UNSUPPORTED; }

@@ -28,6 +28,7 @@
 #include <cudaTypedefs.h>
 
 #include "common.cuh"
+#include "philox.cuh"
 #include "tc_ptx.cuh"
 
 namespace lasr {
@@ -106,6 +107,14 @@ __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t* r) {
           "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
         : "memory");
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+// a = swish(x) and g = swish'(x) from ONE tanh (the arithmetic of gemm_tc.cu::swish_and_deriv): h = x/2, t = tanh(h)
+__device__ __forceinline__ void swish_and_deriv(float x, float& a, float& g) {
+    const float h = 0.5f * x;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    a = fmaf(h, t, h);
+    g = fmaf(fmaf(h, fmaf(-t, t, 1.f), t), 0.5f, 0.5f);
 }
 __device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
@@ -419,6 +428,311 @@ ffn_bwd_kernel(const __grid_constant__ CUtensorMap m_w2, const __grid_constant__
     }
 }
 
+// =================================================================================================================================
+// Fused FORWARD of the same block (nets/feed_forward.py:18-19 inside nets/conformer_layer.py:37-47,58-66):
+//
+//     h   = ln . W1^T + b1                               (never stored)
+//     a   = drop_in(swish(h))            -> HBM (bf16)   fc2's weight gradient needs it
+//     g   = swish'(h), 0 where dropped   -> HBM (bf16)   what the fused backward above multiplies by
+//     out = res + drop_out(alpha * (a . W2^T + b2))      -> HBM (fp32 residual stream)
+//
+// STATUS: correct (a and g bit-identical to the GEMM pair, tests/test_ffn_fused_gpu.py) but NOT faster, so engine.py keeps it behind
+// LASR_FUSED_FFN_FWD=1: 137 us per block against 75 + 51 us for lasr_gemm(Swish, aux_deriv) + lasr_gemm(res) without dropout, 153
+// against 91 + 53 us with the shipped rates (tools/ffn_bench.py ... fwd0.1).  The block is bound by WRITING a and g: 308 MB at the
+// ~4.1 TB/s the machine sustains for stores (fc1 alone runs at exactly that), and the fused pipeline -- one chunk per ~4 k cycles,
+// epilogue groups of 8 warps, bias loads and Philox on the chunk's critical path -- loses more than the 154 MB read it saves.
+// Unfused, a (154 MB at C2 / B = 126) is written by fc1's epilogue and read back by fc2; here a 128-row tile of a exists as 64-column chunks that go
+// TMEM -> registers (bias, one tanh for swish and swish', Philox masks) -> a shared-memory slab that is at the same time the A
+// operand of the second MMA and the source of the bulk tensor store; the second contraction rides under the first one's epilogue.
+// Same skeleton as the backward kernel: ln tile = A operand of the first MMA from TENSOR MEMORY, two alternating groups of 8
+// epilogue warps, separate producers for the two weight rings, a store thread.
+//   warp 0: W1 chunk loads (2 stages)   warp 1: MMA issue   warp 2: bulk stores of the a / g slabs   warp 3: W2 chunk loads (3 stages)
+// TMEM: acc1 2 x 64 columns, acc2 d columns, ln 128 columns.
+// =================================================================================================================================
+constexpr int F_R1S = 2, F_R2S = 3;
+constexpr int FOFF_R1 = 0;                            // W1 chunk ring: d/64 boxes of {64 k, 64 n} (K-major B of the first MMA)
+constexpr int FOFF_R2 = FOFF_R1 + F_R1S * 32768;      // W2 chunk ring: one box {64 k, d n}        (K-major B of the second MMA)
+constexpr int FOFF_A = FOFF_R2 + F_R2S * 32768;       // 2 a slabs of 128 rows x 64 bf16 (K-major A of the second MMA)
+constexpr int FOFF_G = FOFF_A + 2 * 16384;            // 2 g slabs (store staging only)
+constexpr int FOFF_BAR = FOFF_G + 2 * 16384;
+constexpr int FSMEM_BYTES = FOFF_BAR + 512 + 1024;
+static_assert(FSMEM_BYTES <= 232448, "shared-memory budget (forward)");
+
+enum { F_LN_FULL = 0, F_LN_EMPTY, F_R1_FULL, F_R1_EMPTY = F_R1_FULL + F_R1S, F_R2_FULL = F_R1_EMPTY + F_R1S, F_R2_EMPTY = F_R2_FULL + F_R2S,
+       F_ACC1_FULL = F_R2_EMPTY + F_R2S, F_ACC1_EMPTY = F_ACC1_FULL + 2, F_SLAB_FULL = F_ACC1_EMPTY + 2, F_SLAB_EMPTY = F_SLAB_FULL + 2,
+       F_ACC2_FULL = F_SLAB_EMPTY + 2, F_ACC2_EMPTY, F_NBARS };
+
+struct FwdParams {
+    const bf16* ln;    // (M, D)
+    long ldln;
+    const float* b1;   // (F)
+    const float* b2;   // (D)
+    const float* res;  // (M, D) fp32
+    long ldres;
+    float* out;        // (M, D) fp32
+    long ldout;
+    float alpha;       // block scale (0.5 for the macaron halves)
+    int M, D, F, tiles;
+    DropCfg drop_in, drop_out;
+};
+
+template <int KBD>
+__global__ void __launch_bounds__(THREADS, 1)
+ffn_fwd_kernel(const __grid_constant__ CUtensorMap m_w1, const __grid_constant__ CUtensorMap m_w2, const __grid_constant__ CUtensorMap m_a,
+               const __grid_constant__ CUtensorMap m_g, const FwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FOFF_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + FOFF_BAR + 8 * F_NBARS);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int NC = p.F >> 6;
+    const int rot = (int)((blockIdx.x * 7u) % (unsigned)NC);  // per-CTA chunk rotation (see the backward kernel)
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&m_w1) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&m_w2) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&m_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&m_g) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < F_NBARS; ++i) {
+            uint32_t cnt = 1;
+            if (i == F_ACC2_EMPTY || i == F_LN_FULL) cnt = EPI_W;
+            if (i == F_ACC1_EMPTY || i == F_ACC1_EMPTY + 1 || i == F_SLAB_FULL || i == F_SLAB_FULL + 1) cnt = EPI_W / 2;
+            if (i == F_SLAB_EMPTY || i == F_SLAB_EMPTY + 1) cnt = 2;  // the second MMA has read the a slab AND both bulk stores have
+            mbar_init(bars + i, cnt);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t s1 = 0, ph1 = 0;
+            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+                for (int jj = 0; jj < NC; ++jj) {
+                    const int j = jj + rot < NC ? jj + rot : jj + rot - NC;
+                    mbar_wait(bars + F_R1_EMPTY + s1, ph1 ^ 1u);
+                    mbar_arrive_expect_tx(bars + F_R1_FULL + s1, (uint32_t)(KBD * 8192));
+                    for (int kb = 0; kb < KBD; ++kb)  // W1 (f, d) row-major = (N, K): box {64 k, 64 n}
+                        tma_load_4d(smem + FOFF_R1 + s1 * 32768 + kb * 8192, &m_w1, bars + F_R1_FULL + s1, kb * 64, j * CN, 0, 0);
+                    if (++s1 == F_R1S) { s1 = 0; ph1 ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // c = f32, a = b = bf16, both operands K-major, N >> 3, M >> 4
+            const uint32_t id1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+            const uint32_t id2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.D >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+            const uint64_t d_r1 = umma_desc(smem_u32(smem + FOFF_R1), 16, 1024), d_r2 = umma_desc(smem_u32(smem + FOFF_R2), 16, 1024),
+                           d_a = umma_desc(smem_u32(smem + FOFF_A), 16, 1024);
+            uint32_t c1 = 0, c2 = 0, t = 0;
+            uint32_t ws1 = 0, wp1 = 0, ws2 = 0, wp2 = 0;
+            auto mma1 = [&]() {  // acc1[c1 & 1] = ln (TMEM) . W1[chunk, :]^T
+                const uint32_t a = c1 & 1u, aph = (c1 >> 1) & 1u;
+                mbar_wait(bars + F_R1_FULL + ws1, wp1);
+                mbar_wait(bars + F_ACC1_EMPTY + a, aph ^ 1u);
+                tc_fence_after();
+                const uint32_t td = tmem_base + TM_ACC1 + a * CN, ta = tmem_base + TM_DY;
+                const uint64_t db = d_r1 + (uint64_t)(ws1 * (32768u >> 4));
+#pragma unroll
+                for (int kb = 0; kb < KBD; ++kb)
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        tc_mma_bf16_ts(td, ta + kb * 32 + kk * 8, db + (uint64_t)((kb * 8192 + kk * 32) >> 4), id1, (kb | kk) ? 1u : 0u);
+                tc_commit(bars + F_R1_EMPTY + ws1);
+                tc_commit(bars + F_ACC1_FULL + a);
+                ++c1;
+                if (++ws1 == F_R1S) { ws1 = 0; wp1 ^= 1u; }
+            };
+            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++t) {
+                mbar_wait(bars + F_LN_FULL, t & 1u);
+                tc_fence_after();
+                mma1();
+                for (int j = 0; j < NC; ++j, ++c2) {
+                    if (j + 1 < NC) mma1();
+                    else tc_commit(bars + F_LN_EMPTY);  // every MMA reading this tile's ln has been issued
+                    const uint32_t s = c2 & 1u, ph = (c2 >> 1) & 1u;
+                    mbar_wait(bars + F_R2_FULL + ws2, wp2);
+                    mbar_wait(bars + F_SLAB_FULL + s, ph);
+                    if (j == 0) mbar_wait(bars + F_ACC2_EMPTY, (t & 1u) ^ 1u);
+                    tc_fence_after();
+                    const uint64_t da2 = d_a + (uint64_t)(s * (16384u >> 4)), db2 = d_r2 + (uint64_t)(ws2 * (32768u >> 4));
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)  // acc2 += a_chunk (K-major slab) . W2[:, chunk]^T
+                        tc_mma_bf16(tmem_base + TM_ACC2, da2 + (uint64_t)((kk * 32) >> 4), db2 + (uint64_t)((kk * 32) >> 4), id2, (j | kk) ? 1u : 0u);
+                    tc_commit(bars + F_R2_EMPTY + ws2);
+                    tc_commit(bars + F_SLAB_EMPTY + s);
+                    if (++ws2 == F_R2S) { ws2 = 0; wp2 ^= 1u; }
+                }
+                tc_commit(bars + F_ACC2_FULL);
+            }
+        }
+    } else if (warp == 3) {
+        if (lane == 0) {
+            uint32_t s2 = 0, ph2 = 0;
+            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+                for (int jj = 0; jj < NC; ++jj) {
+                    const int j = jj + rot < NC ? jj + rot : jj + rot - NC;
+                    mbar_wait(bars + F_R2_EMPTY + s2, ph2 ^ 1u);
+                    mbar_arrive_expect_tx(bars + F_R2_FULL + s2, (uint32_t)(p.D * 128));
+                    tma_load_4d(smem + FOFF_R2 + s2 * 32768, &m_w2, bars + F_R2_FULL + s2, j * CN, 0, 0, 0);  // W2 (d, f): box {64 k, d n}
+                    if (++s2 == F_R2S) { s2 = 0; ph2 ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 2) {
+        if (lane == 0) {
+            uint32_t c = 0;
+            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+                const int m0 = tile * TM;
+                for (int jj = 0; jj < NC; ++jj, ++c) {
+                    const int j = jj + rot < NC ? jj + rot : jj + rot - NC;
+                    const uint32_t s = c & 1u, ph = (c >> 1) & 1u;
+                    mbar_wait(bars + F_SLAB_FULL + s, ph);
+                    tma_store_4d(&m_a, smem + FOFF_A + s * 16384, j * CN, m0, 0, 0);
+                    tma_store_4d(&m_g, smem + FOFF_G + s * 16384, j * CN, m0, 0, 0);
+                    bulk_commit();
+                    bulk_wait_read<0>();
+                    mbar_arrive(bars + F_SLAB_EMPTY + s);
+                }
+            }
+        }
+    } else {
+        const int ew = warp - CTRL_W;
+        const int q = warp & 3;             // TMEM lane quarter of this warp
+        const int part = ew >> 2;           // ln / out: 64 of the 256 columns
+        const int grp = ew >> 3;            // chunk parity served by this warp
+        const int half = (ew >> 2) & 1;     // 32 of a chunk's 64 columns
+        const int r = q * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const bool din = p.drop_in.thr != 0, dout = p.drop_out.thr != 0;  // uniform
+        DropKey dki = {}, dko = {};
+        if (din) dki = drop_key(p.drop_in);
+        if (dout) dko = drop_key(p.drop_out);
+        const float sc_in = din ? dki.scale : 1.f;
+        const float alpha_s = dout ? p.alpha * dko.scale : p.alpha;
+        uint32_t t = 0;
+        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++t) {
+            const int row = tile * TM + r;
+            const bool row_ok = row < p.M;
+            {   // this warp's share of the ln tile -> tensor memory
+                uint4 x[8];
+                const bf16* dp = p.ln + (long)row * p.ldln + 64 * part;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = ldg_pred_u4(dp + 8 * i, row_ok && 64 * part + 8 * i < p.D);
+                mbar_wait(bars + F_LN_EMPTY, (t & 1u) ^ 1u);
+                tc_fence_after();
+                tc_st32(lane_addr + TM_DY + 32 * part, reinterpret_cast<const uint32_t*>(x));
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bars + F_LN_FULL);
+            }
+            for (int jj = grp; jj < NC; jj += 2) {
+                const uint32_t c = t * (uint32_t)NC + (uint32_t)jj;
+                const int j = jj + rot < NC ? jj + rot : jj + rot - NC;
+                const uint32_t s = (uint32_t)grp, ph = (c >> 1) & 1u;
+                const int col0 = j * CN + 32 * half;
+                mbar_wait(bars + F_ACC1_FULL + s, ph);
+                tc_fence_after();
+                float v[32];
+                tc_ld32_issue(lane_addr + TM_ACC1 + s * CN + 32 * half, v);
+                uint32_t mk[16];  // packed keep masks of this thread's 32 columns, evaluated while the TMEM load is in flight
+                if (din) {
+                    uint32_t h0[8], h1[8];
+                    drop_masks16(dki, (uint32_t)row, (uint32_t)col0 >> 4, h0);
+                    drop_masks16(dki, (uint32_t)row, ((uint32_t)col0 >> 4) + 1u, h1);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { mk[i] = h0[i]; mk[8 + i] = h1[i]; }
+                }
+                tc_ld_wait32(v);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bars + F_ACC1_EMPTY + s);
+                // (finishing all 32 columns in registers BEFORE this wait measured slower: 148 vs 137 us per block)
+                mbar_wait(bars + F_SLAB_EMPTY + s, ph ^ 1u);
+                uint8_t* arow = smem + FOFF_A + s * 16384 + r * 128;
+                uint8_t* grow = smem + FOFF_G + s * 16384 + r * 128;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 ba = __ldg(reinterpret_cast<const float4*>(p.b1 + col0 + 8 * i));
+                    const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b1 + col0 + 8 * i + 4));
+                    const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+                    float a[8], g[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        swish_and_deriv(v[8 * i + e] + bv[e], a[e], g[e]);
+                        a[e] *= sc_in;
+                    }
+                    uint4 ua, ug;
+                    ua.x = pack2(a[0], a[1]); ua.y = pack2(a[2], a[3]); ua.z = pack2(a[4], a[5]); ua.w = pack2(a[6], a[7]);
+                    ug.x = pack2(g[0], g[1]); ug.y = pack2(g[2], g[3]); ug.z = pack2(g[4], g[5]); ug.w = pack2(g[6], g[7]);
+                    if (din) {
+                        ua.x &= mk[4 * i]; ua.y &= mk[4 * i + 1]; ua.z &= mk[4 * i + 2]; ua.w &= mk[4 * i + 3];
+                        ug.x &= mk[4 * i]; ug.y &= mk[4 * i + 1]; ug.z &= mk[4 * i + 2]; ug.w &= mk[4 * i + 3];
+                    }
+                    const int off = ((4 * half + i) ^ (r & 7)) << 4;
+                    *reinterpret_cast<uint4*>(arow + off) = ua;
+                    *reinterpret_cast<uint4*>(grow + off) = ug;
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bars + F_SLAB_FULL + s);
+            }
+            // out tile: res + keep * scale * alpha * (acc2 + b2) -> fp32 (this warp: its 32 rows x 64 columns)
+            mbar_wait(bars + F_ACC2_FULL, t & 1u);
+            tc_fence_after();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int cc = part * 64 + i * 16;
+                if (cc < p.D) {  // warp-uniform
+                    float4 rr[4];
+                    const float* rp = p.res + (long)row * p.ldres + cc;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) rr[e] = ldg_pred_f4(rp + 4 * e, row_ok);
+                    uint32_t keep = 0xffffu;
+                    if (dout) keep = drop_keep16(dko, (uint32_t)row, (uint32_t)cc >> 4);
+                    float v[16];
+                    tc_ld16(lane_addr + TM_ACC2 + cc, v);
+                    if (row_ok) {
+                        float4* dst = reinterpret_cast<float4*>(p.out + (long)row * p.ldout + cc);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(p.b2 + cc + 4 * e));
+                            float4 o;
+                            o.x = fmaf(v[4 * e], alpha_s, alpha_s * b.x); o.y = fmaf(v[4 * e + 1], alpha_s, alpha_s * b.y);
+                            o.z = fmaf(v[4 * e + 2], alpha_s, alpha_s * b.z); o.w = fmaf(v[4 * e + 3], alpha_s, alpha_s * b.w);
+                            const uint32_t k4 = keep >> (4 * e);
+                            o.x = ((k4 & 1u) ? o.x : 0.f) + rr[e].x; o.y = ((k4 & 2u) ? o.y : 0.f) + rr[e].y;
+                            o.z = ((k4 & 4u) ? o.z : 0.f) + rr[e].z; o.w = ((k4 & 8u) ? o.w : 0.f) + rr[e].w;
+                            dst[e] = o;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars + F_ACC2_EMPTY);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+
 static PFN_cuTensorMapEncodeTiled_v12000 encoder() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
     if (!fn) {
@@ -507,6 +821,58 @@ int lasr_ffn_bwd(const void* dy, int64_t lddy, const void* g, int64_t ldg, const
     const int grid = p.tiles < sms ? p.tiles : sms;
     launch_pdl(kern, dim3((unsigned)grid), dim3(ffn::THREADS), (size_t)ffn::SMEM_BYTES, (cudaStream_t)stream, m_w2, m_w1, m_dh, p);
     return check_launch("ffn_bwd");
+}
+
+int lasr_ffn_fwd_supported(int d, int f) { return lasr_ffn_bwd_supported(d, f); }
+
+int lasr_ffn_fwd(const void* ln, int64_t ldln, const void* w1, int64_t ldw1, const float* b1, const void* w2, int64_t ldw2, const float* b2,
+                 const float* res, int64_t ldres, void* a, int64_t lda, void* g, int64_t ldg, float* out, int64_t ldout, float alpha, int M, int d,
+                 int f, const void* drop_state, uint32_t in_site, uint32_t in_thr, float in_scale, uint32_t out_site, uint32_t out_thr,
+                 float out_scale, void* stream) {
+    LASR_REQUIRE(ln && w1 && b1 && w2 && b2 && res && a && g && out && M > 0, "ffn_fwd: null operand or empty problem");
+    if (!lasr_ffn_fwd_supported(d, f)) {
+        set_error("ffn_fwd: needs d %% 64 == 0, 64 <= d <= %d, f %% 128 == 0, f <= %d (got d=%d f=%d)", ffn::DMAX, ffn::FMAX, d, f);
+        return LASR_ERR_UNSUPPORTED;
+    }
+    LASR_REQUIRE(ldln % 8 == 0 && (reinterpret_cast<uintptr_t>(ln) & 15) == 0, "ffn_fwd: ln must be 16-byte aligned with a row stride that is a multiple of 8");
+    LASR_REQUIRE(ldres % 4 == 0 && ldout % 4 == 0 && ((reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+                 "ffn_fwd: res / out must be 16-byte aligned with row strides that are multiples of 4");
+    LASR_REQUIRE(((reinterpret_cast<uintptr_t>(b1) | reinterpret_cast<uintptr_t>(b2)) & 15) == 0, "ffn_fwd: biases must be 16-byte aligned");
+    LASR_REQUIRE((in_thr == 0 && out_thr == 0) || drop_state, "ffn_fwd: dropout needs drop_state");
+    LASR_REQUIRE(in_thr <= LASR_DROP_THR_MAX && out_thr <= LASR_DROP_THR_MAX, "ffn_fwd: thr = round(p * 32768) <= 0x7c00");
+    CUtensorMap m_w1, m_w2, m_a, m_g;
+    int rc;
+    if ((rc = ffn::make_map(&m_w1, w1, d, f, ldw1, 64, false)) != LASR_OK) return rc;   // (f, d): inner = d (K), rows = f (N)
+    if ((rc = ffn::make_map(&m_w2, w2, f, d, ldw2, d, false)) != LASR_OK) return rc;    // (d, f): inner = f (K), rows = d (N), box {64, d}
+    if ((rc = ffn::make_map(&m_a, a, f, M, lda, ffn::TM, true)) != LASR_OK) return rc;
+    if ((rc = ffn::make_map(&m_g, g, f, M, ldg, ffn::TM, true)) != LASR_OK) return rc;
+    typedef void (*Kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const ffn::FwdParams);
+    Kern kern = d == 256 ? ffn::ffn_fwd_kernel<4> : d == 192 ? ffn::ffn_fwd_kernel<3> : d == 128 ? ffn::ffn_fwd_kernel<2> : ffn::ffn_fwd_kernel<1>;
+    static bool configured[5] = {false, false, false, false, false};
+    if (!configured[d >> 6]) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ffn::FSMEM_BYTES) != cudaSuccess)
+            return check_launch("ffn_fwd smem attr");
+        configured[d >> 6] = true;
+    }
+    ffn::FwdParams p;
+    p.ln = reinterpret_cast<const bf16*>(ln); p.ldln = ldln;
+    p.b1 = b1; p.b2 = b2;
+    p.res = res; p.ldres = ldres;
+    p.out = out; p.ldout = ldout;
+    p.alpha = alpha;
+    p.M = M; p.D = d; p.F = f;
+    p.tiles = (M + ffn::TM - 1) / ffn::TM;
+    p.drop_in.state = p.drop_out.state = reinterpret_cast<const unsigned long long*>(drop_state);
+    p.drop_in.site = in_site; p.drop_in.thr = in_thr; p.drop_in.scale = in_scale;
+    p.drop_out.site = out_site; p.drop_out.thr = out_thr; p.drop_out.scale = out_scale;
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    const int grid = p.tiles < sms ? p.tiles : sms;
+    launch_pdl(kern, dim3((unsigned)grid), dim3(ffn::THREADS), (size_t)ffn::FSMEM_BYTES, (cudaStream_t)stream, m_w1, m_w2, m_a, m_g, p);
+    return check_launch("ffn_fwd");
 }
 
 }  // extern "C"

@@ -1126,7 +1126,17 @@ int gemm_tc_dispatch(const lasr_gemm_args* a, cudaStream_t st) {
     const int n_store = a->n_store ? a->n_store : a->n;
     // N tiles are multiples of 32 columns: the TMA-store epilogue writes whole 32-column boxes, clipped only at the tensor edge
     // recompute mode: two accumulators share a 256-column TMEM buffer -> N tiles of at most 128 columns
-    const int bn = a->a2 ? (n_store >= 128 ? 128 : pick_bn(n_store, 64)) : pick_bn(n_store, a->trans_b ? 64 : 32);
+    int bn = a->a2 ? (n_store >= 128 ? 128 : pick_bn(n_store, 64)) : pick_bn(n_store, a->trans_b ? 64 : 32);
+    if (!a->a2) {
+        // Few row tiles (the decoder: 126 x 41 = 5166 rows = 41 tiles for 148 SMs): narrower N tiles until the work units cover at
+        // least half of the SMs -- the A tile is re-read from L2 by more units, but a unit then takes proportionally less time
+        // and 41-unit launches ran on 28 % of the machine.  LASR_GEMM_FILL=0 keeps the widest tile (developer switch).
+        static int fill = -1;
+        if (fill < 0) { const char* e = getenv("LASR_GEMM_FILL"); fill = e ? atoi(e) : 1; }
+        const int gran = a->trans_b ? 64 : 32;
+        const long per_n = (long)ceil_div(a->m, BM) * (a->split_k < 1 ? 1 : a->split_k) * a->batch1 * a->batch2;
+        while (fill && per_n * ceil_div(n_store, bn) * 2 <= sm_count() && bn % (2 * gran) == 0 && bn / 2 >= 64) bn /= 2;
+    }
     CUtensorMap ma, mb, ma2, mb2;
     int rc;
     if (a->a2) {

@@ -58,6 +58,8 @@ class Engine:
         self.ffn_recompute = store.adt == torch.bfloat16 and os.environ.get("LASR_FFN_RECOMPUTE", "0") == "1"
         # LASR_FUSED_FFN=0: developer switch back to the two separate backward GEMMs of a feed-forward block (csrc/ffn_fused.cu)
         self.fused_ffn = store.adt == torch.bfloat16 and os.environ.get("LASR_FUSED_FFN", "1") != "0"
+        # off by default: correct but measured slower than the GEMM pair (csrc/ffn_fused.cu, "STATUS")
+        self.fused_ffn_fwd = store.adt == torch.bfloat16 and os.environ.get("LASR_FUSED_FFN_FWD", "0") == "1"
 
     # ------------------------------------------------------------------------------------------
     # small helpers
@@ -180,6 +182,16 @@ class Engine:
         ln = self.layernorm(x, pfx_norm, self.adt)
         if act == ACT_SWISH and d_in is not None and self.ffn_recompute:
             raise NotImplementedError("LASR_FFN_RECOMPUTE=1 cannot be combined with FFN dropout (the mask lives in the saved pre-activation)")
+        w1, w2 = self.st.w(pfx_ff + ".fc1.weight"), self.st.w(pfx_ff + ".fc2.weight")
+        if (act == ACT_SWISH and not self.ffn_recompute and self.fused_ffn_fwd and ops.ffn_fwd_supported(w1.shape[1], w1.shape[0])
+                and ln.y.stride(0) % 8 == 0 and x.stride(0) % 4 == 0):
+            # ONE kernel: a and g = swish'(h) are written once, the second contraction reads a from shared memory (csrc/ffn_fused.cu)
+            m, f = ln.y.shape[0], w1.shape[0]
+            a, h = _empty((m, f), self.adt, self.dev), _empty((m, f), self.adt, self.dev)
+            out = _empty((m, x.shape[1]), torch.float32, self.dev)
+            ops.ffn_fwd(ln.y, w1, self.st.p(pfx_ff + ".fc1.bias"), w2, self.st.p(pfx_ff + ".fc2.bias"), x, a, h, out, alpha=scale,
+                        drop_in=d_in, drop_out=d_out)
+            return NS(out=out, ln=ln, a=a, h=h, act=act, scale=scale, pfx=pfx_ff, d_in=d_in, d_out=d_out)
         if act == ACT_SWISH and not self.ffn_recompute:
             a, h = self.linear(ln.y, pfx_ff + ".fc1", self.adt, act=act, aux=True, drop=d_in, drop_mark_aux=True, aux_deriv=True)
         else:  # ReLU: act'(.) from the output; Swish in bf16 mode: the pre-activation is recomputed in the backward GEMM

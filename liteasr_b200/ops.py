@@ -126,6 +126,37 @@ def ffn_bwd(dy, g, w2, w1, dh, dln, colsum=None, alpha: float = 1.0) -> None:
                                        _stream()), "ffn_bwd")
 
 
+def ffn_fwd_supported(d: int, f: int) -> bool:
+    return bool(_lib.lib().lasr_ffn_fwd_supported(C.c_int(d), C.c_int(f)))
+
+
+def ffn_fwd(ln, w1, b1, w2, b2, res, a, g, out, alpha: float = 1.0, drop_in=None, drop_out=None) -> None:
+    """a = drop_in(swish(ln @ w1^T + b1)), g = swish'(.) (0 where dropped), out = res + drop_out(alpha * (a @ w2^T + b2)):
+    one fused tcgen05 kernel (include/lasr.h ``lasr_ffn_fwd``).  ``drop_in`` / ``drop_out``: ``Drop`` of the two sites (same pass)."""
+    _require_cuda(ln, w1, b1, w2, b2, res, a, g, out)
+    for t in (ln, w1, w2, a, g):
+        if t.dtype != torch.bfloat16 or t.dim() != 2 or t.stride(1) != 1:
+            raise TypeError("ffn_fwd takes 2-D row-major bf16 operands")
+    for t in (b1, b2, res, out):
+        if t.dtype != torch.float32:
+            raise TypeError("ffn_fwd: biases, residual and output are fp32")
+    m, d = ln.shape
+    f = w1.shape[0]
+    assert w1.shape == (f, d) and w2.shape == (d, f) and a.shape == (m, f) and g.shape == (m, f) and res.shape == (m, d) and out.shape == (m, d)
+    assert b1.numel() == f and b2.numel() == d and res.stride(1) == 1 and out.stride(1) == 1
+    di = drop_in if (drop_in is not None and drop_in.thr) else None
+    do = drop_out if (drop_out is not None and drop_out.thr) else None
+    state = (di or do).state if (di or do) is not None else None
+    if di is not None and do is not None:
+        assert di.state.data_ptr() == do.state.data_ptr(), "the two dropout sites of a block share the pass's RNG snapshot"
+    _lib.check(_lib.lib().lasr_ffn_fwd(_ptr(ln), C.c_int64(ln.stride(0)), _ptr(w1), C.c_int64(w1.stride(0)), _ptr(b1), _ptr(w2),
+                                       C.c_int64(w2.stride(0)), _ptr(b2), _ptr(res), C.c_int64(res.stride(0)), _ptr(a), C.c_int64(a.stride(0)),
+                                       _ptr(g), C.c_int64(g.stride(0)), _ptr(out), C.c_int64(out.stride(0)), C.c_float(alpha), C.c_int(m),
+                                       C.c_int(d), C.c_int(f), _ptr(state), C.c_uint32(di.site if di else 0), C.c_uint32(di.thr if di else 0),
+                                       C.c_float(di.scale if di else 1.0), C.c_uint32(do.site if do else 0), C.c_uint32(do.thr if do else 0),
+                                       C.c_float(do.scale if do else 1.0), _stream()), "ffn_fwd")
+
+
 def ctc_workspace_bytes(T: int, B: int, lmax: int) -> int:
     return int(_lib.lib().lasr_ctc_workspace_bytes(C.c_int(T), C.c_int(B), C.c_int(lmax)))
 

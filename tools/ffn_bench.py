@@ -30,8 +30,49 @@ def timed(fn, iters=20):
     return e0.elapsed_time(e1) / iters * 1e3
 
 
+def main_fwd(m, d, f, p_drop):
+    """the fused forward kernel against lasr_gemm(Swish, aux_deriv) + lasr_gemm(res)"""
+    dev = "cuda"
+    n = 3
+    ln = [torch.randn(m, d, device=dev).bfloat16() for _ in range(n)]
+    res = [torch.randn(m, d, device=dev) for _ in range(n)]
+    w1 = (torch.randn(f, d, device=dev) * d ** -0.5).bfloat16()
+    w2 = (torch.randn(d, f, device=dev) * f ** -0.5).bfloat16()
+    b1, b2 = torch.randn(f, device=dev) * 0.1, torch.randn(d, device=dev) * 0.1
+    a = [torch.empty(m, f, device=dev, dtype=torch.bfloat16) for _ in range(n)]
+    g = [torch.empty(m, f, device=dev, dtype=torch.bfloat16) for _ in range(n)]
+    out = [torch.empty(m, d, device=dev) for _ in range(n)]
+    st = torch.tensor([1234, 5], dtype=torch.int64, device=dev)
+    di = ops.Drop(st, 0x01000103, p_drop) if p_drop > 0 else None
+    do = ops.Drop(st, 0x01000104, p_drop) if p_drop > 0 else None
+    it = {"i": 0}
+
+    def fused():
+        i = it["i"] % n
+        it["i"] += 1
+        ops.ffn_fwd(ln[i], w1, b1, w2, b2, res[i], a[i], g[i], out[i], alpha=0.5, drop_in=di, drop_out=do)
+
+    def fc1():
+        i = it["i"] % n
+        it["i"] += 1
+        ops.gemm(ln[i], w1, a[i], m, f, d, lda=d, ldb=d, ldc=f, bias=b1, aux=g[i], act=ops.ACT_SWISH, drop=di, drop_mark_aux=True, aux_deriv=True)
+
+    def fc2():
+        i = it["i"] % n
+        it["i"] += 1
+        ops.gemm(a[i], w2, out[i], m, d, f, lda=f, ldb=f, ldc=d, bias=b2, res=res[i], ldres=d, alpha=0.5, drop=do)
+
+    tf, t1, t2 = timed(fused), timed(fc1), timed(fc2)
+    fl = 4.0 * m * d * f
+    byt = m * (d * 2 + 2 * f * 2 + 2 * d * 4)
+    print(f"ffn_fwd m={m} d={d} f={f} dropout={p_drop}: fused {tf:.1f} us ({fl / tf / 1e6:.0f} TFLOP/s, {byt / tf / 1e3:.0f} GB/s algorithmic) | "
+          f"fc1 {t1:.1f} us + fc2 {t2:.1f} us = {t1 + t2:.1f} us")
+
+
 def main(m=37674, d=256, f=2048, colsum="1", only=""):
     m, d, f = int(m), int(d), int(f)
+    if only.startswith("fwd"):
+        return main_fwd(m, d, f, float(only[3:] or 0))
     dev = "cuda"
     dy = (torch.randn(m, d, device=dev) * 0.5).bfloat16()
     w2 = (torch.randn(d, f, device=dev) * 0.05).bfloat16()
