@@ -89,6 +89,7 @@ struct TcParams {
     DropCfg drop;      // dropout on the output (philox.cuh); thr = 0: off
     int drop_mark;     // dropped elements of aux receive LASR_DROP_MARK (0 with aux_deriv)
     int aux_deriv;     // aux = act'(pre-activation) instead of the pre-activation (Swish)
+    int epi_rot;       // 1: rotate the chunk -> epilogue-warp assignment from unit to unit (uneven chunk counts)
 };
 
 
@@ -886,15 +887,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         typedef typename std::conditional<C_F32, float, bf16>::type CT;
         constexpr bool TMA_OK = !BS && MODE != EPI_GENERIC && MODE != EPI_DUAL_DSWISH && MODE != EPI_DUAL_DRELU;
         const bool tma_epi = TMA_OK && p.tma_epi != 0;
+        // N tiles whose 32-column chunks do not divide evenly among the four warps of a lane quarter (BN = 160: 5 chunks) leave one
+        // warp with twice the work of the others in EVERY unit; rotating the chunk -> warp assignment from unit to unit spreads it
+        // (the two accumulator buffers let a warp run one unit ahead of the slowest one)
+        int urot = 0;
         while (walk.next(p, w)) {
             mbar_wait(acc_full + as, aph);  // (sleeping between polls, 32-300 ns, changes nothing: the spin is not what limits the epilogue)
             tc_fence_after();
             const uint32_t tmem_acc = tmem_base + (uint32_t)(as * ACC_COLS);
+            const int part_u = (part + urot) & (EPI_WARPS / 4 - 1);
+            urot += p.epi_rot;
             if constexpr (TMA_OK) {
-                if (tma_epi) epilogue_unit_tma<CT, MODE, DROP>(p, w, tmem_acc, stage, q, part, lane, &tma_c, &tma_x, sbuf);
-                else epilogue_unit<CT, MODE, CW, DROP>(p, w, tmem_acc, stage, q, part, lane);
+                if (tma_epi) epilogue_unit_tma<CT, MODE, DROP>(p, w, tmem_acc, stage, q, part_u, lane, &tma_c, &tma_x, sbuf);
+                else epilogue_unit<CT, MODE, CW, DROP>(p, w, tmem_acc, stage, q, part_u, lane);
             } else {
-                epilogue_unit<CT, MODE, CW, DROP>(p, w, tmem_acc, stage, q, part, lane);
+                epilogue_unit<CT, MODE, CW, DROP>(p, w, tmem_acc, stage, q, part_u, lane);
             }
             tc_fence_before();
             __syncwarp();
@@ -1179,6 +1186,11 @@ int gemm_tc_dispatch(const lasr_gemm_args* a, cudaStream_t st) {
     p.drop.site = a->drop_site; p.drop.thr = a->drop_thr; p.drop.scale = a->drop_scale;
     p.drop_mark = a->drop_mark_aux;
     p.aux_deriv = a->aux_deriv;
+    {
+        static int rot = -1;  // LASR_GEMM_ROT=0: developer switch
+        if (rot < 0) { const char* e = getenv("LASR_GEMM_ROT"); rot = e ? atoi(e) : 1; }
+        p.epi_rot = (rot && ((bn + 31) / 32) % (EPI_WARPS / 4) != 0) ? 1 : 0;
+    }
     if (a->a2) p.epi_mode = a->act == LASR_ACT_SWISH ? EPI_DUAL_DSWISH : EPI_DUAL_DRELU;
     else if (a->accumulate) p.epi_mode = EPI_ACC;
     else if (a->dact && a->act == LASR_ACT_SWISH) p.epi_mode = EPI_DSWISH;

@@ -91,7 +91,7 @@ __device__ __forceinline__ float4 load4(const TD* p) {
 // regenerated here (philox.cuh) and applied to dx_lo and to the column sums; dx itself (the residual-stream gradient) is not
 // masked.  TLO = bf16 (tensor-core mode) or float (fp32 parity mode, where the masked copy is a second fp32 tensor).
 template <typename TD, typename TLO, int NV>
-__global__ void __launch_bounds__(256, (NV <= 2 ? 3 : 1)) layernorm_bwd_kernel(const TD* __restrict__ dy, long lddy,
+__global__ void __launch_bounds__(256, (NV <= 2 ? 3 : (NV <= 4 ? 2 : 1))) layernorm_bwd_kernel(const TD* __restrict__ dy, long lddy,
                                                             const float* __restrict__ x, long ldx,
                                                             const float* __restrict__ mean,
                                                             const float* __restrict__ rstd,
