@@ -106,11 +106,20 @@ __global__ void __launch_bounds__(256, (NV <= 2 ? 3 : (NV <= 4 ? 2 : 1))) layern
     const bool drop_on = drop.thr != 0;
     DropKey dk = {};
     if (drop_on) dk = drop_key(drop);
-    float4 gam[NV], ag[NV], abt[NV], acs[NV];
+    // gamma lives in shared memory, not in registers: at 3 CTAs per SM (80 registers) every register held across the row loop is a
+    // spilled one; a conflict-free LDS.128 per chunk and row is cheaper than the local-memory traffic it replaces
+    __shared__ float4 gam_s[NV][32];
+    if (warp == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = lane + 32 * i;
+            gam_s[i][lane] = (c < nchunk) ? *reinterpret_cast<const float4*>(gamma + 4 * c) : make_float4(0, 0, 0, 0);
+        }
+    }
+    __syncthreads();
+    float4 ag[NV], abt[NV], acs[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-        const int c = lane + 32 * i;
-        gam[i] = (c < nchunk) ? *reinterpret_cast<const float4*>(gamma + 4 * c) : make_float4(0, 0, 0, 0);
         ag[i] = make_float4(0, 0, 0, 0);
         abt[i] = make_float4(0, 0, 0, 0);
         acs[i] = make_float4(0, 0, 0, 0);
@@ -132,7 +141,8 @@ __global__ void __launch_bounds__(256, (NV <= 2 ? 3 : (NV <= 4 ? 2 : 1))) layern
                 const float4 xv = *reinterpret_cast<const float4*>(xr + 4 * c);
                 if (accumulate) old[i] = *reinterpret_cast<const float4*>(dxr + 4 * c);
                 xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-                g[i] = make_float4(dv.x * gam[i].x, dv.y * gam[i].y, dv.z * gam[i].z, dv.w * gam[i].w);
+                const float4 gm = gam_s[i][lane];
+                g[i] = make_float4(dv.x * gm.x, dv.y * gm.y, dv.z * gm.z, dv.w * gm.w);
                 s1 += g[i].x + g[i].y + g[i].z + g[i].w;
                 s2 += g[i].x * xh[i].x + g[i].y * xh[i].y + g[i].z * xh[i].z + g[i].w * xh[i].w;
                 ag[i].x += dv.x * xh[i].x; ag[i].y += dv.y * xh[i].y; ag[i].z += dv.z * xh[i].z; ag[i].w += dv.w * xh[i].w;

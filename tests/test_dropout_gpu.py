@@ -58,6 +58,18 @@ def test_gpu_round_function_matches_random123_known_answers():
         assert [int(v) for v in got7] == [int(v) for v in P.philox4x32(*ctr, *key)]
 
 
+def test_rates_above_the_fp16_lane_limit_are_rejected():
+    """15-bit lanes are compared as fp16 bit patterns: thr = round(p * 32768) must not exceed 0x7c00 (p <= 0.96875)."""
+    from liteasr_b200 import ops
+    st = _state()
+    assert ops.Drop(st, 1, 0.96875).thr == 0x7C00
+    with pytest.raises(ValueError):
+        ops.Drop(st, 1, 0.97)
+    x = torch.ones(64, 64, device=DEV)
+    y = ops.dropout(x, torch.empty_like(x), ops.Drop(st, 1, 0.96875))
+    assert 0 < int((y > 0).sum()) < 64 * 64 // 8 and float(y.max()) == 32.0   # 1 / (1 - 0.96875)
+
+
 def test_rng_advance_and_site_separation():
     from liteasr_b200 import ops
     from liteasr_b200.dropout import RngState

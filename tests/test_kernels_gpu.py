@@ -62,7 +62,7 @@ def _conv_module_ref(y2, w, bias, gamma, beta, eps=1e-5):
     return z.transpose(1, 2), a.transpose(1, 2)
 
 
-@pytest.mark.parametrize("B,T,d", [(3, 50, 64), (5, 299, 256), (2, 31, 128), (4, 97, 512)])
+@pytest.mark.parametrize("B,T,d", [(3, 50, 64), (5, 299, 256), (2, 31, 128), (4, 97, 512), (2, 1, 64), (3, 64, 64), (2, 33, 192), (1, 7, 144)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_conv_module_middle_fwd_bwd(B, T, d, dtype):
     from liteasr_b200 import ops
