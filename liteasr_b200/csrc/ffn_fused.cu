@@ -438,9 +438,10 @@ ffn_bwd_kernel(const __grid_constant__ CUtensorMap m_w2, const __grid_constant__
 //
 // STATUS: correct (a and g bit-identical to the GEMM pair, tests/test_ffn_fused_gpu.py) but NOT faster, so engine.py keeps it behind
 // LASR_FUSED_FFN_FWD=1: 137 us per block against 75 + 51 us for lasr_gemm(Swish, aux_deriv) + lasr_gemm(res) without dropout, 153
-// against 91 + 53 us with the shipped rates (tools/ffn_bench.py ... fwd0.1).  The block is bound by WRITING a and g: 308 MB at the
-// ~4.1 TB/s the machine sustains for stores (fc1 alone runs at exactly that), and the fused pipeline -- one chunk per ~4 k cycles,
-// epilogue groups of 8 warps, bias loads and Philox on the chunk's critical path -- loses more than the 154 MB read it saves.
+// against 91 + 53 us with the shipped rates (tools/ffn_bench.py ... fwd0.1).  fc1 is bound by its epilogue's instruction stream
+// (~500 instructions per thread and 32-column chunk: bias, tanh, the Swish / Swish' FMAs, packs, staging stores; Philox on top), and
+// this kernel executes the same epilogue with 8 of its 16 epilogue warps per chunk plus the second contraction's handshakes -- one
+// 64-column chunk per ~4 k cycles -- which costs more than the 154 MB read of a that it saves (profiles/r2_ffn_fwd.txt).
 // Unfused, a (154 MB at C2 / B = 126) is written by fc1's epilogue and read back by fc2; here a 128-row tile of a exists as 64-column chunks that go
 // TMEM -> registers (bias, one tanh for swish and swish', Philox masks) -> a shared-memory slab that is at the same time the A
 // operand of the second MMA and the source of the bulk tensor store; the second contraction rides under the first one's epilogue.
