@@ -9,7 +9,8 @@ One JSON line on rank 0.  `value` = whole-job audio-s/s with the batch resident 
 max over ranks); `e2e` = the same step through the public API with the batch in pinned HOST memory (H2D inside the timed
 region, loss read back every step).  The headline trains with the reference's shipped rates (config/model/my_U2.yaml: dropout
 0.1, attention-probability rates 0.0; BASELINE.md section 3: "0.1 for the throughput run"); `extra.dropout_0` is the same step
-with every rate 0 (round-1's configuration).  `roofline` = the dominant kernel family (tcgen05 GEMM) timed live with CUDA events
+with every rate 0 (round-1's configuration).  `roofline` = the dominant kernel family (every tcgen05 contraction of the step: lasr_gemm,
+the implicit-GEMM convolutions, the fused feed-forward kernels and the paired attention-backward kernel) timed live with CUDA events
 (the family's launches of one step replayed from a CUDA graph), `roofline_split` = its tensor-bound (K >= 1024, convolutions) and
 HBM-bound (K < 1024) halves against their own peaks, `roofline_ctc` = the standalone fused CTC over the whole BASELINE config-4
 grid; `gpu_incumbent` = the reference's own modules (unmodified copy under baseline/_ref, else the oracle port) on torch-CUDA on
