@@ -300,6 +300,16 @@ def _record_gemms(step_fn, batch):
         rec.append((ffwd_orig, (ln, w1, b1, w2, b2, res, a, g, out), kw, 4.0 * m * d * f, float(byt), d))
         ffwd_orig(ln, w1, b1, w2, b2, res, a, g, out, **kw)
 
+    wg2_orig = ops.wgrad2
+
+    def wg2_recorder(dy, x, gw, **kw):  # weight gradients on CTA pairs
+        rows, mo = dy.shape
+        no = x.shape[1]
+        byt = sum(t.numel() * t.element_size() for t in (dy, x, gw))
+        rec.append((wg2_orig, (dy, x, gw), kw, 2.0 * rows * mo * no, float(byt), rows))
+        wg2_orig(dy, x, gw, **kw)
+
+    ops.wgrad2 = wg2_recorder
     ops.gemm = recording
     ops.ffn_bwd = ffn_recorder
     ops.ffn_fwd = ffwd_recorder
@@ -311,6 +321,7 @@ def _record_gemms(step_fn, batch):
         torch.cuda.synchronize()
     finally:
         ops.gemm = orig
+        ops.wgrad2 = wg2_orig
         ops.ffn_bwd = ffn_orig
         ops.ffn_fwd = ffwd_orig
         ops.attn_bwd_pair = pair_orig

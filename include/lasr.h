@@ -127,6 +127,17 @@ typedef struct lasr_gemm_args {
 int lasr_gemm(const lasr_gemm_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Weight gradient of a Linear on CTA pairs (tcgen05.mma.cta_group::2):  c (M, N fp32, row stride ldc) += alpha * a^T . b with
+ * a (K, M) and b (K, N) row-major bf16 -- dW += dy^T x, the autograd backward of every nn.Linear of the path (nets/feed_forward.py:
+ * 18-19, nets/attention.py:35-37, nets/conformer_convolution.py:48,55).  Same contract as lasr_gemm(trans_a = trans_b = 1,
+ * accumulate = 1, split_k); needs M % 256 == 0 and N % 256 == 0 (lasr_wgrad2_supported): each CTA of a pair stages only its half of
+ * both operands for a 256 x 256 tile.
+ * ------------------------------------------------------------------------------------------------ */
+int lasr_wgrad2_supported(int m, int n);
+int lasr_wgrad2(const void* a, int64_t lda, const void* b, int64_t ldb, float* c, int64_t ldc, float alpha, int m, int n, int k, int split_k,
+                void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Fused backward of the two inner GEMMs of a position-wise feed-forward block (nets/feed_forward.py:18-19 backward; the
  * encoder runs the block twice per Conformer layer, nets/conformer_layer.py:37-47,58-66), bf16 / tcgen05:
  *     dh  (M, f) = alpha * (dy (M, d) . W2 (d, f)) * g (M, f)      W2 = fc2.weight, g = act'(fc1 pre-activation) saved by the

@@ -51,6 +51,7 @@ class Engine:
         # LASR_FUSED_ATTN=0: developer switch back to GEMM -> softmax kernel -> GEMM for the rel-pos attention forward
         self.fused_attn = os.environ.get("LASR_FUSED_ATTN", "1") != "0"
         self.fused_attn_bwd = os.environ.get("LASR_FUSED_ATTN_BWD", "1") != "0"
+        self.wgrad2 = store.adt == torch.bfloat16 and os.environ.get("LASR_WGRAD2", "1") != "0"
         # LASR_FFN_RECOMPUTE=1 (developer switch, off): fc1 of a Swish FFN does not save its pre-activation and the backward GEMM
         # recomputes it into a second TMEM accumulator.  Saves 154 MB written + 135 MB read per FFN at C2/B=126 but measured
         # SLOWER (32.0 vs 30.7 ms per step): two accumulators force 128-column N tiles, and at K = 256 the four operand slabs of a
@@ -142,6 +143,13 @@ class Engine:
         """gw (N_out, K_in) += alpha * dy^T x   (split-K tcgen05 / SIMT GEMM with red.add)."""
         m, n = dy.shape
         k = x.shape[1]
+        if (self.wgrad2 and dy.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and ops.wgrad2_supported(n, k) and m >= 1024
+                and dy.stride(0) % 8 == 0 and x.stride(0) % 8 == 0 and gw.stride(0) % 4 == 0):
+            # CTA pairs (tcgen05.mma.cta_group::2): each SM stages half of both operands of a 256 x 256 tile (csrc/gemm2_wgrad.cu);
+            # one work unit per pair, split-K so that the units cover the 74 pairs of the machine
+            tiles = (n // 256) * (k // 256)
+            ops.wgrad2(dy, x, gw, alpha=alpha, split_k=max(1, min(74 // tiles if tiles <= 74 else 1, m // 512)))
+            return
         ops.gemm(dy, x, gw, n, k, m, lda=dy.stride(0), ldb=x.stride(0), ldc=gw.stride(0), ta=True, tb=True, accumulate=True,
                  split_k=self._split_k(n, k, m), alpha=alpha)
 

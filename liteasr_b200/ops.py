@@ -105,6 +105,22 @@ def linear(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, re
     return out
 
 
+def wgrad2_supported(m: int, n: int) -> bool:
+    return bool(_lib.lib().lasr_wgrad2_supported(C.c_int(m), C.c_int(n)))
+
+
+def wgrad2(dy, x, gw, alpha: float = 1.0, split_k: int = 1) -> None:
+    """gw (N_out, K_in) fp32 += alpha * dy^T x on CTA pairs (include/lasr.h ``lasr_wgrad2``); dy (rows, N_out), x (rows, K_in) bf16."""
+    _require_cuda(dy, x, gw)
+    if dy.dtype != torch.bfloat16 or x.dtype != torch.bfloat16 or gw.dtype != torch.float32:
+        raise TypeError("wgrad2 takes bf16 operands and an fp32 gradient")
+    rows, m = dy.shape
+    n = x.shape[1]
+    assert x.shape[0] == rows and gw.shape == (m, n) and dy.stride(1) == 1 and x.stride(1) == 1 and gw.stride(1) == 1
+    _lib.check(_lib.lib().lasr_wgrad2(_ptr(dy), C.c_int64(dy.stride(0)), _ptr(x), C.c_int64(x.stride(0)), _ptr(gw), C.c_int64(gw.stride(0)),
+                                      C.c_float(alpha), C.c_int(m), C.c_int(n), C.c_int(rows), C.c_int(split_k), _stream()), "wgrad2")
+
+
 def ffn_bwd_supported(d: int, f: int) -> bool:
     return bool(_lib.lib().lasr_ffn_bwd_supported(C.c_int(d), C.c_int(f)))
 
