@@ -37,7 +37,7 @@ def main(path, json_out=None):
         print(f"{ns / 1e6:9.3f} {100 * ns / tot[1]:5.1f} {c:5d} {ns / c / 1e3:10.1f} {rd / c / 1e6:13.2f} {wr / c / 1e6:13.2f} {(rd + wr) / ns:10.1f}  {n[:100]}")
     if json_out:
         import json
-        fam = [v for k, v in agg.items() if any(t in k for t in ("gemm_tc_kernel", "ffn_bwd_kernel", "ffn_fwd_kernel", "attn_pair_kernel"))]
+        fam = [v for k, v in agg.items() if any(t in k for t in ("gemm_tc_kernel", "wgrad2_kernel", "ffn_bwd_kernel", "ffn_fwd_kernel", "attn_pair_kernel"))]
         out = {
             "source": path, "launches_per_step": tot[0], "step_ms_cold": tot[1] / 1e6,
             "step_dram_read_bytes": tot[2], "step_dram_write_bytes": tot[3],
