@@ -38,6 +38,12 @@ constexpr int ACC_COLS = 256;
 struct Params {
     int K, tiles_m, tiles_n, splits;
     float alpha;
+    // implicit-GEMM weight gradient of the 3x3 stride-2 convolution over parity planes (gemm_tc.cu::conv2_tc_dispatch, mode 3): the
+    // reduction dimension runs over (utterance, padded output row), the 256-wide N tile selects the tap = (row shift, parity plane)
+    int conv;          // 0 plain | 1 convolution
+    int kbpb;          // k-blocks per utterance
+    int conv_d;        // channels
+    int conv_off[9], conv_plane[9];
 };
 
 __device__ __forceinline__ uint32_t cluster_rank() {
@@ -55,10 +61,10 @@ __device__ __forceinline__ uint32_t map_to_rank(uint32_t local, uint32_t rank) {
     return r;
 }
 // TMA load of this CTA's share of a pair's operand tile; the bytes are counted on the barrier `bar_cluster_addr` (the leader's)
-__device__ __forceinline__ void tma_load_2sm(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1) {
+__device__ __forceinline__ void tma_load_2sm(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1, int c2, int c3) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
 __device__ __forceinline__ void mma2_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -96,7 +102,7 @@ wgrad2_kernel(const __grid_constant__ CUtensorMap m_a, const __grid_constant__ C
     const uint32_t rank = cluster_rank();
     const int unit = blockIdx.x >> 1;
     const int nt = unit % p.tiles_n, mt = (unit / p.tiles_n) % p.tiles_m, split = unit / (p.tiles_n * p.tiles_m);
-    const int total_kb = (p.K + 63) / 64, per = (total_kb + p.splits - 1) / p.splits;
+    const int total_kb = p.conv ? p.K * p.kbpb : (p.K + 63) / 64, per = (total_kb + p.splits - 1) / p.splits;  // conv: K = utterances
     const int kb0 = split * per, nkb = min(total_kb, kb0 + per) - kb0;
 
     if (warp == 0 && lane == 0) {
@@ -124,18 +130,26 @@ wgrad2_kernel(const __grid_constant__ CUtensorMap m_a, const __grid_constant__ C
     if (nkb > 0) {
         if (warp == 0) {
             if (lane == 0) {
-                const int m0 = mt * 256 + (int)rank * 128, n0 = nt * 256 + (int)rank * 128;
+                const int m0 = mt * 256 + (int)rank * 128;
+                int n0 = nt * 256 + (int)rank * 128, boff = 0, bplane = 0;
+                if (p.conv) {  // the N tile lies inside one tap: columns [tap * d, (tap + 1) * d) of the (co, tap, ci) gradient
+                    const int tp = (nt * 256) / p.conv_d;
+                    n0 -= tp * p.conv_d;
+                    boff = p.conv_off[tp];
+                    bplane = p.conv_plane[tp];
+                }
                 uint32_t s = 0, ph = 0;
                 for (int i = 0; i < nkb; ++i) {
                     mbar_wait(empty_bar + s, ph ^ 1u);
                     if (rank == 0) mbar_arrive_expect_tx(full_bar + s, (uint32_t)(2 * STAGE_BYTES));  // both CTAs' bytes
                     const uint32_t bar = map_to_rank(smem_u32(full_bar + s), 0);
                     uint8_t* st = smem + OFF_RING + s * STAGE_BYTES;
-                    const int k0 = (kb0 + i) * 64;
-                    tma_load_2sm(st, &m_a, bar, m0, k0);               // A: box {64 m, 64 k} x 2
-                    tma_load_2sm(st + 8192, &m_a, bar, m0 + 64, k0);
-                    tma_load_2sm(st + 16384, &m_b, bar, n0, k0);       // B: this CTA's 128 of the tile's 256 columns
-                    tma_load_2sm(st + 24576, &m_b, bar, n0 + 64, k0);
+                    int k0 = (kb0 + i) * 64, bi = 0;
+                    if (p.conv) { bi = (kb0 + i) / p.kbpb; k0 = (kb0 + i - bi * p.kbpb) * 64; }  // rows >= YR of dY read as zeros
+                    tma_load_2sm(st, &m_a, bar, m0, k0, 0, bi);               // A: box {64 m, 64 k} x 2
+                    tma_load_2sm(st + 8192, &m_a, bar, m0 + 64, k0, 0, bi);
+                    tma_load_2sm(st + 16384, &m_b, bar, n0, k0 + boff, bplane, bi);       // B: this CTA's 128 of the tile's 256 columns
+                    tma_load_2sm(st + 24576, &m_b, bar, n0 + 64, k0 + boff, bplane, bi);
                     if (++s == STAGES) { s = 0; ph ^= 1u; }
                 }
             }
@@ -203,6 +217,25 @@ static PFN_cuTensorMapEncodeTiled_v12000 encoder() {
     return fn;
 }
 
+// bf16 operand, 4-D (dims / strides innermost first, strides in elements for dims 1..3), box {64, 64, 1, 1}, SWIZZLE_128B
+static int make_map4(CUtensorMap* map, const void* base, const long dims_[4], const long strides_[3]) {
+    auto enc = encoder();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return LASR_ERR_DRIVER; }
+    cuuint64_t dims[4], strides[3];
+    for (int i = 0; i < 4; ++i) dims[i] = (cuuint64_t)(dims_[i] > 0 ? dims_[i] : 1);
+    for (int i = 0; i < 3; ++i) strides[i] = (cuuint64_t)strides_[i] * 2;
+    cuuint32_t box[4] = {64, 64, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (strides[0] & 15) || (strides[1] & 15) || (strides[2] & 15)) {
+        set_error("wgrad2: operand base / strides must be 16-byte aligned");
+        return LASR_ERR_BAD_ARG;
+    }
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("wgrad2: cuTensorMapEncodeTiled failed (%d)", (int)r); return LASR_ERR_DRIVER; }
+    return LASR_OK;
+}
+
 static int make_map2(CUtensorMap* map, const void* base, CUtensorMapDataType dt, int es, long inner, long rows, long ld, int box_inner, int box_rows,
                      CUtensorMapSwizzle sw) {
     auto enc = encoder();
@@ -232,8 +265,11 @@ int lasr_wgrad2(const void* a, int64_t lda, const void* b, int64_t ldb, float* c
     if (!lasr_wgrad2_supported(m, n)) { set_error("wgrad2: needs M %% 256 == 0 and N %% 256 == 0 (got %d x %d)", m, n); return LASR_ERR_UNSUPPORTED; }
     CUtensorMap m_a, m_b, m_c;
     int rc;
-    if ((rc = g2::make_map2(&m_a, a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, m, k, lda, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) != LASR_OK) return rc;
-    if ((rc = g2::make_map2(&m_b, b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, n, k, ldb, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) != LASR_OK) return rc;
+    {
+        const long da[4] = {m, k, 1, 1}, sa[3] = {lda, lda, lda}, db[4] = {n, k, 1, 1}, sb[3] = {ldb, ldb, ldb};
+        if ((rc = g2::make_map4(&m_a, a, da, sa)) != LASR_OK) return rc;
+        if ((rc = g2::make_map4(&m_b, b, db, sb)) != LASR_OK) return rc;
+    }
     if ((rc = g2::make_map2(&m_c, c, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, n, m, ldc, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B)) != LASR_OK) return rc;
     static bool configured = false;
     if (!configured) {
@@ -242,6 +278,7 @@ int lasr_wgrad2(const void* a, int64_t lda, const void* b, int64_t ldb, float* c
         configured = true;
     }
     g2::Params p;
+    memset(&p, 0, sizeof(p));
     p.K = k;
     p.tiles_m = m / 256;
     p.tiles_n = n / 256;
@@ -256,3 +293,49 @@ int lasr_wgrad2(const void* a, int64_t lda, const void* b, int64_t ldb, float* c
 }
 
 }  // extern "C"
+
+namespace lasr {
+// Weight gradient of the sub-sampling front end's second convolution (nets/subsampling.py:33-34 backward) on CTA pairs: the same
+// implicit GEMM as gemm_tc.cu::conv2_tc_dispatch(mode 3) -- dW[co][tap][ci] += sum_b sum_r dY[b][r][co] h1p[b][plane][r + off][ci] --
+// for d % 256 == 0.  Returns LASR_ERR_UNSUPPORTED for other d (the caller keeps the single-CTA kernel).
+int conv2_wgrad2_dispatch(const void* h1p, const void* dy, float* out, int B, int U, int V, int T2, int d, cudaStream_t st) {
+    if (d % 256 != 0 || B < 1 || U < 1 || V < 1 || T2 < 1) return LASR_ERR_UNSUPPORTED;
+    const long PR = (long)U * V, YR = (long)T2 * V;
+    CUtensorMap m_a, m_b, m_c;
+    int rc;
+    {
+        const long da[4] = {d, YR, 1, B}, sa[3] = {d, YR * d, YR * d};
+        const long db[4] = {d, PR, 4, B}, sb[3] = {d, PR * d, 4 * PR * d};
+        if ((rc = g2::make_map4(&m_a, dy, da, sa)) != LASR_OK) return rc;
+        if ((rc = g2::make_map4(&m_b, h1p, db, sb)) != LASR_OK) return rc;
+    }
+    if ((rc = g2::make_map2(&m_c, out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 9L * d, d, 9L * d, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B)) != LASR_OK) return rc;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(g2::wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g2::SMEM_BYTES) != cudaSuccess)
+            return check_launch("conv2_wgrad2 smem attr");
+        configured = true;
+    }
+    g2::Params p;
+    memset(&p, 0, sizeof(p));
+    p.conv = 1;
+    p.K = B;
+    p.kbpb = (int)((YR + 63) / 64);
+    p.conv_d = d;
+    for (int kh = 0, t = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw, ++t) {
+            p.conv_off[t] = (kh >> 1) * V + (kw >> 1);
+            p.conv_plane[t] = (kh & 1) * 2 + (kw & 1);
+        }
+    p.tiles_m = d / 256;
+    p.tiles_n = 9 * d / 256;
+    const int tiles = p.tiles_m * p.tiles_n;
+    const long total_kb = (long)B * p.kbpb;
+    long s = tiles <= 74 ? 74 / tiles : 1;
+    if (s > total_kb) s = total_kb;
+    p.splits = (int)(s < 1 ? 1 : s);
+    p.alpha = 1.f;
+    launch_pdl(g2::wgrad2_kernel, dim3((unsigned)(2L * tiles * p.splits)), dim3(g2::THREADS), (size_t)g2::SMEM_BYTES, st, m_a, m_b, m_c, p);
+    return check_launch("conv2_wgrad2");
+}
+}  // namespace lasr

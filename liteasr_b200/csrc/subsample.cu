@@ -273,6 +273,7 @@ __global__ void __launch_bounds__(256, 3) conv1_bwd_planes_kernel(const float* _
     }
 }
 
+int conv2_wgrad2_dispatch(const void* h1p, const void* dy, float* out, int B, int U, int V, int T2, int d, cudaStream_t st);
 int conv2_tc_dispatch(int mode, int plane_class, const void* h1p, const void* w2, const float* bias, const void* dy, void* out,
                       int B, int U, int V, int T2, int d, int split_k, cudaStream_t st);
 int conv1_wgrad_tc_dispatch(const float* x, const void* dh1p, float* dw, float* dbias, int B, int T, int F, int d, cudaStream_t st);
@@ -405,6 +406,9 @@ int lasr_conv2_dgrad(const void* dy2p, const void* w2k, const void* h1p, void* d
 int lasr_conv2_wgrad(const void* dy2p, const void* h1p, float* dw2k, int B, int T, int F, int d, void* stream) {
     LASR_REQUIRE(dy2p && h1p && dw2k && planes_ok(d), "conv2_wgrad: bad args");
     const int T1 = (T - 3) / 2 + 1, F1 = (F - 3) / 2 + 1, U = (T1 + 1) / 2, V = (F1 + 1) / 2, T2 = (T1 - 3) / 2 + 1;
+    static int pair = -1;  // LASR_CONV2_WGRAD2=0: developer switch back to the single-CTA kernel
+    if (pair < 0) { const char* e = getenv("LASR_CONV2_WGRAD2"); pair = e ? atoi(e) : 1; }
+    if (pair && d % 256 == 0) return conv2_wgrad2_dispatch(h1p, dy2p, dw2k, B, U, V, T2, d, (cudaStream_t)stream);  // CTA pairs (gemm2_wgrad.cu)
     return conv2_tc_dispatch(3, 0, h1p, nullptr, nullptr, dy2p, dw2k, B, U, V, T2, d, 1, (cudaStream_t)stream);
 }
 

@@ -26,7 +26,7 @@ def to_planes(h1, U, V):
     return p.reshape(B, 4, U * V, d).contiguous()
 
 
-@pytest.mark.parametrize("B,T,F,d", [(2, 67, 80, 128), (3, 100, 83, 64), (1, 50, 20, 256), (2, 131, 80, 256)])
+@pytest.mark.parametrize("B,T,F,d", [(2, 67, 80, 128), (3, 100, 83, 64), (1, 50, 20, 256), (2, 131, 80, 256), (2, 67, 80, 512), (5, 203, 80, 256)])
 def test_plane_front_end_matches_torch(B, T, F, d):
     from liteasr_b200 import ops
     g = torch.Generator(device="cuda").manual_seed(B * T + d)
