@@ -15,7 +15,7 @@ the implicit-GEMM convolutions, the fused feed-forward kernels and the paired at
 HBM-bound (K < 1024) halves against their own peaks, `roofline_ctc` = the standalone fused CTC over the whole BASELINE config-4
 grid; `gpu_incumbent` = the reference's own modules (unmodified copy under baseline/_ref, else the oracle port) on torch-CUDA on
 the same GPU, eager fp32 and autocast(bf16), same batch; `cpu_baseline` = the same reference path on the box's host cores, one
-full-batch step.  `--impl reference` runs only the CPU arm on a bounded sample and prints the same line shape.
+step over (at most) 126 utterances of the batch.  `--impl reference` runs only the CPU arm on a bounded sample and prints the same line shape.
 """
 from __future__ import annotations
 
@@ -33,16 +33,19 @@ FRAME_SHIFT_S = 0.01  # Kaldi fbank default frame shift (the reference never sta
 
 WORKLOADS = {
     # BASELINE.json configs[1]: AISHELL-1 shape
-    "c2": dict(dims=(80, 4233, 256, 2048, 4, 12, 256, 2048, 4, 6), batch=126, tmax=1200, lmax=40, ctc_weight=0.3, smoothing=0.1,
+    "c2": dict(dims=(80, 4233, 256, 2048, 4, 12, 256, 2048, 4, 6), batch=252, tmax=1200, lmax=40, ctc_weight=0.3, smoothing=0.1,
                desc="C2: U2 Conformer 12L d256 H4 f2048 + 6L Transformer decoder, V=4233 (AISHELL-1 shape), Tmax=1200 (T'=299), "
-                    "per-GPU batch 126 (builder's choice, SURVEY 8: 126 x 299 rows = 295 row tiles = two full waves of 148 SMs; "
-                    "the reference default 32 is `--batch 32`), Lmax=40, hybrid ctc_weight 0.3, smoothing 0.1, dropout 0 (U2Config default)"),
+                    "per-GPU batch 252 (builder's choice, SURVEY 8: 252 x 299 rows = 589 row tiles = four waves of the 148 SMs, 3.98 of "
+                    "them full; rounds 1 and most of 2 ran two waves = `--batch 126`, 4 % slower per utterance; the reference default 32 "
+                    "is `--batch 32`), Lmax=40, hybrid ctc_weight 0.3, smoothing 0.1, dropout 0 (U2Config default)"),
     # configs[0]: the reference's CPU-runnable case
     "c1": dict(dims=(80, 500, 256, 2048, 4, 4, 256, 2048, 4, 6), batch=8, tmax=500, lmax=30, ctc_weight=0.3, smoothing=0.1,
                desc="C1: U2 Conformer 4L d256 H4 + 6L decoder, V=500, batch 8, Tmax=500"),
     # configs[2]: LibriSpeech-960 shape
-    "c3": dict(dims=(80, 5000, 512, 2048, 8, 12, 512, 2048, 8, 6), batch=16, tmax=1600, lmax=100, ctc_weight=0.3, smoothing=0.1,
-               desc="C3: Conformer-large 12L d512 H8 + 6L decoder d512, V=5000, Tmax=1600 (T'=399), per-GPU batch 16, Lmax=100"),
+    "c3": dict(dims=(80, 5000, 512, 2048, 8, 12, 512, 2048, 8, 6), batch=92, tmax=1600, lmax=100, ctc_weight=0.3, smoothing=0.1,
+               desc="C3: Conformer-large 12L d512 H8 + 6L decoder d512, V=5000, Tmax=1600 (T'=399), per-GPU batch 92 (92 x 399 rows = 287 "
+                    "row tiles = two waves of the 148 SMs, chosen like C2's batch; round 1 and the first half of round 2 ran 16 = a third "
+                    "of ONE wave: 13.2 k audio-s/s), Lmax=100"),
 }
 
 
@@ -765,7 +768,9 @@ def run_gpu(args, wl):
         torch.cuda.empty_cache()
         if not args.no_cpu_baseline:
             try:
-                rc = cpu_oracle_run(wl, 1, 0, sample_batch=wl["batch"], dropout=args.dropout)
+                # a bounded sample (about 30 s of CPU work): at most 126 utterances of the batch -- the reference's CPU step is
+                # linear in the batch (33 s at 126, 68 s at 252 on 16 cores: 36.3 vs 35.5 audio-s/s), so audio-s/s is comparable
+                rc = cpu_oracle_run(wl, 1, 0, sample_batch=min(wl["batch"], 126), dropout=args.dropout)
                 line["cpu_baseline"] = {"value": rc["value"], "unit": "audio-s/s", "cores": rc["cores"], "kind": rc["kind"], "sample": rc["sample"],
                                         "ms_per_step": rc["ms_per_step"]}
             except Exception as e:  # noqa: BLE001

@@ -223,24 +223,20 @@ static PFN_cuTensorMapEncodeTiled_v12000 encoder() {
 // returns LASR_ERR_UNSUPPORTED (without setting an error) when the shape is outside the kernel's range: the caller keeps the SIMT path
 int conv1_fwd_tc_dispatch(const float* x, const float* w, const float* bias, void* h1p, int B, int T, int F, int d, cudaStream_t st) {
     using namespace c1f;
-    if (d != 128 && d != 256) return LASR_ERR_UNSUPPORTED;
+    // d = 512 / 1024 (BASELINE configs[2]): 256-channel slices, one launch each -- the kernel's N is one 256-column accumulator, the
+    // slice's weight rows / bias start at channel c0 and its stores go through a tensor map whose base is shifted by c0 channels
+    // while the row stride stays the full d.  The A rows are rebuilt per slice (x is L2-resident; the op is bound by its stores).
+    if (d != 128 && d != 256 && !(d > 256 && d <= 1024 && d % 256 == 0)) return LASR_ERR_UNSUPPORTED;
     auto enc = encoder();
     if (!enc || (reinterpret_cast<uintptr_t>(h1p) & 15)) return LASR_ERR_UNSUPPORTED;
+    const int dn = d > 256 ? 256 : d;
     Params p;
-    p.x = x; p.w = w; p.bias = bias;
-    p.B = B; p.T = T; p.F = F; p.d = d;
+    p.x = x;
+    p.B = B; p.T = T; p.F = F; p.d = dn;
     p.T1 = (T - 3) / 2 + 1; p.F1 = (F - 3) / 2 + 1; p.U = (p.T1 + 1) / 2; p.V = (p.F1 + 1) / 2;
     const long PR = (long)p.U * p.V;
     p.rblocks = (int)((PR + TM - 1) / TM);
     p.units = (long)B * 4 * p.rblocks;
-    CUtensorMap mo;
-    cuuint64_t dims[4] = {(cuuint64_t)d, (cuuint64_t)PR, (cuuint64_t)B * 4, 1};
-    cuuint64_t strides[3] = {(cuuint64_t)d * 2, (cuuint64_t)PR * d * 2, (cuuint64_t)PR * d * 2};
-    cuuint32_t box[4] = {32, 32, 1, 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    if (enc(&mo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, h1p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-        return LASR_ERR_UNSUPPORTED;
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(conv1_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
@@ -250,8 +246,26 @@ int conv1_fwd_tc_dispatch(const float* x, const float* w, const float* bias, voi
     int sms = 148, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) (void)cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = (int)(p.units < sms ? p.units : sms);
-    launch_pdl(conv1_fwd_tc_kernel, dim3((unsigned)grid), dim3(THREADS), (size_t)SMEM_BYTES, st, mo, p);
-    return check_launch("conv1_fwd_tc");
+    for (int c0 = 0; c0 < d; c0 += dn) {
+        p.w = w + (long)c0 * 9;
+        p.bias = bias + c0;
+        CUtensorMap mo;
+        cuuint64_t dims[4] = {(cuuint64_t)dn, (cuuint64_t)PR, (cuuint64_t)B * 4, 1};
+        cuuint64_t strides[3] = {(cuuint64_t)d * 2, (cuuint64_t)PR * d * 2, (cuuint64_t)PR * d * 2};
+        cuuint32_t box[4] = {32, 32, 1, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        if (enc(&mo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, reinterpret_cast<__nv_bfloat16*>(h1p) + c0, dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+            if (c0 == 0) return LASR_ERR_UNSUPPORTED;
+            set_error("conv1_fwd_tc: tensor map of channel slice %d failed", c0);
+            return LASR_ERR_DRIVER;
+        }
+        launch_pdl(conv1_fwd_tc_kernel, dim3((unsigned)grid), dim3(THREADS), (size_t)SMEM_BYTES, st, mo, p);
+        const int rc = check_launch("conv1_fwd_tc");
+        if (rc != LASR_OK) return rc;
+    }
+    return LASR_OK;
 }
 
 }  // namespace lasr

@@ -1,14 +1,11 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_conv_planes_gpu.py tests/test_wgrad2_gpu.py -x -q --timeout=300 2>&1 | tail -4
-timeout 900 python -m pytest tests -m gpu -q --timeout=600 > gpurun_out/r2v_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/r2v_pytest.log; tail -3 gpurun_out/r2v_pytest.log
-b() { env "$@" timeout 600 python bench.py --steps 20 --warmup 5 --quick 2>/dev/null | python -c "
-import json,sys
-for l in sys.stdin:
+timeout 900 python -m pytest tests/test_full_shape_gpu.py tests/test_conv_planes_gpu.py -x -q -s --timeout=800 2>&1 | grep -v Warning | grep -v "^$" | tail -25
+t0=$(date +%s)
+timeout 1500 python bench.py --batch 252 > gpurun_out/r2z_bench252.log 2> gpurun_out/r2z_bench252.err; echo "bench rc=$? elapsed $(( $(date +%s) - t0 )) s"
+python - <<'PY'
+import json
+for l in open('gpurun_out/r2z_bench252.log'):
     if l.startswith('{'):
-        d=json.loads(l); print('$*', round(d['value'],1), round(d['ms_per_step'],3), round(d['e2e']['ms_per_step'],3), round(d['roofline']['frac'],4))
-"; }
-b LASR_CONV2_WGRAD2=1
-b LASR_CONV2_WGRAD2=0
-b LASR_CONV2_WGRAD2=1
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/r2v_step.csv python tools/one_step.py c2 bf16 0.1 > gpurun_out/r2v_ncu.log 2>&1
-python tools/ncu_summary.py gpurun_out/r2v_step.csv | head -30
+        d=json.loads(l)
+        print(d['value'], d['ms_per_step'], d['e2e'], d['roofline']['frac'], d['gpu_incumbent'], d['cpu_baseline'], d['extra']['c3'])
+PY

@@ -16,7 +16,9 @@ from liteasr_b200.utils.synthetic import synth_batch  # noqa: E402
 workload = sys.argv[1] if len(sys.argv) > 1 else "c2"
 precision = sys.argv[2] if len(sys.argv) > 2 else "bf16"
 dropout = float(sys.argv[3]) if len(sys.argv) > 3 else 0.0
-wl = bench.WORKLOADS[workload]
+wl = dict(bench.WORKLOADS[workload])
+if len(sys.argv) > 4:
+    wl["batch"] = int(sys.argv[4])
 dims = U2Dims(*wl["dims"])
 dev = torch.device("cuda:0")
 torch.manual_seed(42)
