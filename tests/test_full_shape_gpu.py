@@ -30,11 +30,7 @@ def _oracle_on_gpu(BATCH: int, odt: torch.dtype):
     from liteasr_b200.schema import U2Dims
     from liteasr_b200.utils.synthetic import synth_batch, synth_state_dict
     from oracle import u2_oracle as O
-    import gc
     dev = torch.device("cuda:0")
-    gc.collect()
-    torch.cuda.init()
-    torch.cuda.empty_cache()
     torch.cuda.reset_peak_memory_stats(0)
     dims = U2Dims(**C2)
     batch = synth_batch(BATCH, TMAX, LMAX, dims.vocab_size, seed=42)
@@ -58,14 +54,29 @@ def _oracle_on_gpu(BATCH: int, odt: torch.dtype):
     return sd, batch, out
 
 
+def _or_skip(batch, odt):
+    import gc
+    gc.collect()
+    torch.cuda.init()
+    torch.cuda.empty_cache()
+    free, _ = torch.cuda.mem_get_info(0)
+    if free < 125e9:  # the oracle's autograd graph: 100 GB (float64, batch 126) / 103 GB (float32, batch 252), then the product
+        pytest.skip(f"needs 125 GB of free HBM for the oracle at the bench shape ({free / 1e9:.0f} GB free)")
+    try:
+        return _oracle_on_gpu(batch, odt)
+    except torch.cuda.OutOfMemoryError:
+        torch.cuda.empty_cache()
+        pytest.skip("out of device memory while evaluating the oracle at the bench shape")
+
+
 @pytest.fixture(scope="module")
 def oracle_f64():
-    return _oracle_on_gpu(126, torch.float64)
+    return _or_skip(126, torch.float64)
 
 
 @pytest.fixture(scope="module")
 def oracle_f32_b252():
-    return _oracle_on_gpu(252, torch.float32)
+    return _or_skip(252, torch.float32)
 
 
 def _run_product(case, precision, BATCH):
