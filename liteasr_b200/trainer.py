@@ -54,6 +54,7 @@ class TrainStep:
         self.graph_mem_cap = int(graph_mem_fraction * torch.cuda.get_device_properties(self.device).total_memory)
         self.stats = dict(replays=0, eager=0, captures=0, evictions=0, capture_s=0.0)
         self._warm = False
+        self._pool_seen = 0  # largest private graph pool captured so far (bytes)
         self.loss_out = torch.zeros(3, dtype=torch.float32, device=self.device)
 
     # ------------------------------------------------------------------ one optimizer step, eager
@@ -104,6 +105,9 @@ class TrainStep:
                 self.stats["eager"] += 1
                 return self.step_eager(xs, xlens, ys, ylens)
             entry = self._capture(key, xs, xlens, ys, ylens)
+            if entry is None:  # no device memory for another graph pool: this shape stays eager
+                self.stats["eager"] += 1
+                return self.step_eager(xs, xlens, ys, ylens)
         else:
             self.graphs.move_to_end(key)
         graph, static, loss, _ = entry
@@ -117,24 +121,37 @@ class TrainStep:
     def static_inputs(self, xs, xlens, ys, ylens):
         """The static device buffers for this shape (capture on first use) -- fill them in place to skip the D2D copy."""
         key = (tuple(xs.shape), tuple(ys.shape), self.model.training)
-        if key not in self.graphs:
-            self._capture(key, xs, xlens, ys, ylens)
+        if key not in self.graphs and self._capture(key, xs, xlens, ys, ylens) is None:
+            raise RuntimeError("not enough free device memory to capture the training step for this shape")
         return self.graphs[key][1]
 
-    def _evict_for(self, need_bytes: int) -> None:
-        """LRU eviction: keep at most max_graphs entries and at most graph_mem_cap bytes of private graph pools."""
+    def _evict_for(self, need_bytes: int) -> bool:
+        """LRU eviction: keep at most max_graphs entries and at most graph_mem_cap bytes of private graph pools -- and, whatever the
+        bookkeeping says, enough FREE device memory for another pool of the expected size (other graphs, models or processes share
+        the GPU; a capture that runs out of memory cannot be resumed).  False: no room even with an empty cache -> run eagerly."""
         def used():
             return sum(e[3] for e in self.graphs.values())
-        while self.graphs and (len(self.graphs) >= self.max_graphs or used() + need_bytes > self.graph_mem_cap):
+
+        def pop():
             _, (g, static, loss, nbytes) = self.graphs.popitem(last=False)
             del g, static, loss
             self.stats["evictions"] += 1
+        while self.graphs and (len(self.graphs) >= self.max_graphs or used() + need_bytes > self.graph_mem_cap):
+            pop()
         torch.cuda.empty_cache()
+        want = int(1.5 * need_bytes)  # the pool plus the eager warm-up steps' transient activations
+        while need_bytes > 0 and torch.cuda.mem_get_info(self.device)[0] < want:
+            if not self.graphs:
+                return False
+            pop()
+            torch.cuda.empty_cache()
+        return True
 
     def _capture(self, key, xs, xlens, ys, ylens):
         t0 = time.perf_counter()
-        est = max((e[3] for e in self.graphs.values()), default=0)  # a new pool is about as large as the largest so far
-        self._evict_for(est)
+        est = max(max((e[3] for e in self.graphs.values()), default=0), self._pool_seen)  # a new pool is about as large as the largest so far
+        if not self._evict_for(est):
+            return None
         static = tuple(t.clone() for t in (xs, xlens, ys, ylens))
         # snapshot state mutated by the warm-up steps so capture does not change training semantics
         snap = (self.store.flat.clone(), self.optimizer.exp_avg.clone(), self.optimizer.exp_avg_sq.clone(),
@@ -151,12 +168,16 @@ class TrainStep:
             self._warm = False
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        # torch.cuda.graph() empties the allocator cache on entry: do it BEFORE the baseline reading, or the warm-up steps' cached
+        # blocks (about one pool's worth) leave the default pool while the private pool grows and the difference reads as ~0
+        torch.cuda.empty_cache()
         mem0 = torch.cuda.memory_reserved(self.device)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             loss = self._body(self._split(static))
         torch.cuda.synchronize()
         pool_bytes = max(0, torch.cuda.memory_reserved(self.device) - mem0)
+        self._pool_seen = max(self._pool_seen, pool_bytes)
         with torch.no_grad():
             self.store.flat.copy_(snap[0])
             self.optimizer.exp_avg.copy_(snap[1])

@@ -275,9 +275,30 @@ def test_variable_shape_training_bounded_graph_cache_equals_eager():
         lb = b(*bt)
         assert math.isclose(float(la), float(lb), rel_tol=1e-4), (float(la), float(lb))
     assert len(a.graphs) <= 3 and a.stats["captures"] >= 5 and a.stats["evictions"] >= 2, a.stats
+    assert min(e[3] for e in a.graphs.values()) > 0, "a captured graph's private pool was measured as 0 bytes"
     assert a.stats["eager"] >= 5 and a.stats["replays"] >= 5 and a.stats["replays"] + a.stats["eager"] == 20, a.stats
     assert a.optimizer.num_updates() == b.optimizer.num_updates() == 20
     for (n, pa), (_, pb) in zip(model_a.named_parameters(), model_b.named_parameters()):
         if n.endswith("conv.depthwise_conv.bias") or n.endswith("linear_k.bias"):
             continue  # identically-zero gradients: Adam turns rounding noise into +-lr steps (see the test above)
         assert torch.allclose(pa, pb, rtol=1e-4, atol=1e-6), n
+
+
+def test_graph_cache_is_bounded_by_pool_memory():
+    """The LRU's memory bound: with a cap of 1.5 pools only one graph stays resident although max_graphs allows eight (the pool
+    size is read after torch.cuda.graph()'s own cache flush -- a reading taken before it came out as ~0 and the cap never bit:
+    the batch-252 bench ran out of memory in its variable-shape epoch)."""
+    from liteasr_b200.trainer import TrainStep
+    from liteasr_b200.utils.synthetic import synth_batch
+    g, dims, batch, sd, model, crit = _setup("tiny", "fp32")
+    step = TrainStep(model, crit, device=torch.device("cuda:0"), use_graph=True, graph_min_hits=1, max_graphs=8)
+    shapes = [(g["tmax"] - 4 * i, g["lmax"]) for i in range(4)]
+    batches = [tuple(t.cuda() for t in synth_batch(g["batch"], tm, lm, dims.vocab_size, seed=90 + i)) for i, (tm, lm) in enumerate(shapes)]
+    step(*batches[0])
+    pool = next(iter(step.graphs.values()))[3]
+    assert pool > 0
+    step.graph_mem_cap = int(1.5 * pool)
+    for bt in batches[1:]:
+        step(*bt)
+    assert len(step.graphs) == 1 and step.stats["evictions"] == 3, (step.stats, len(step.graphs))
+    assert sum(e[3] for e in step.graphs.values()) <= step.graph_mem_cap
