@@ -55,6 +55,7 @@ class TrainStep:
         self.stats = dict(replays=0, eager=0, captures=0, evictions=0, capture_s=0.0)
         self._warm = False
         self._pool_seen = 0  # largest private graph pool captured so far (bytes)
+        self._evicted = set()  # shape keys the LRU has dropped
         self.loss_out = torch.zeros(3, dtype=torch.float32, device=self.device)
 
     # ------------------------------------------------------------------ one optimizer step, eager
@@ -104,7 +105,9 @@ class TrainStep:
             if n < self.graph_min_hits:
                 self.stats["eager"] += 1
                 return self.step_eager(xs, xlens, ys, ylens)
-            entry = self._capture(key, xs, xlens, ys, ylens)
+            # a shape the cache has already had to drop, and no room without dropping another: the working set of shapes does not
+            # fit (a cyclic epoch over more shapes than pools would re-capture every step, 1.4 - 3 s each) -> this shape stays eager
+            entry = None if (key in self._evicted and self._full()) else self._capture(key, xs, xlens, ys, ylens)
             if entry is None:  # no device memory for another graph pool: this shape stays eager
                 self.stats["eager"] += 1
                 return self.step_eager(xs, xlens, ys, ylens)
@@ -125,6 +128,11 @@ class TrainStep:
             raise RuntimeError("not enough free device memory to capture the training step for this shape")
         return self.graphs[key][1]
 
+    def _full(self) -> bool:
+        """Would another capture have to evict a resident graph?"""
+        est = max(max((e[3] for e in self.graphs.values()), default=0), self._pool_seen)
+        return bool(self.graphs) and (len(self.graphs) >= self.max_graphs or sum(e[3] for e in self.graphs.values()) + est > self.graph_mem_cap)
+
     def _evict_for(self, need_bytes: int) -> bool:
         """LRU eviction: keep at most max_graphs entries and at most graph_mem_cap bytes of private graph pools -- and, whatever the
         bookkeeping says, enough FREE device memory for another pool of the expected size (other graphs, models or processes share
@@ -133,9 +141,12 @@ class TrainStep:
             return sum(e[3] for e in self.graphs.values())
 
         def pop():
-            _, (g, static, loss, nbytes) = self.graphs.popitem(last=False)
+            k, (g, static, loss, nbytes) = self.graphs.popitem(last=False)
             del g, static, loss
             self.stats["evictions"] += 1
+            if len(self._evicted) > 4096:
+                self._evicted.clear()
+            self._evicted.add(k)
         while self.graphs and (len(self.graphs) >= self.max_graphs or used() + need_bytes > self.graph_mem_cap):
             pop()
         torch.cuda.empty_cache()

@@ -302,3 +302,7 @@ def test_graph_cache_is_bounded_by_pool_memory():
         step(*bt)
     assert len(step.graphs) == 1 and step.stats["evictions"] == 3, (step.stats, len(step.graphs))
     assert sum(e[3] for e in step.graphs.values()) <= step.graph_mem_cap
+    # a shape the cache had to drop comes back while the cache is full: it runs eagerly instead of evicting again (no thrashing)
+    before = dict(step.stats)
+    step(*batches[0])
+    assert step.stats["captures"] == before["captures"] and step.stats["eager"] == before["eager"] + 1, (before, step.stats)
