@@ -1,4 +1,4 @@
-# multi-GPU bench lines (run with: gpurun --gpus 8 -- 'bash tools/_run_multi.sh 8')
+# multi-GPU bench lines (run with: gpurun --gpus 8 -- 'bash tools/run_multi.sh 8')
 mkdir -p gpurun_out
 for n in "$@"; do
 extra=""; [ "$n" = "2" ] && extra="--check-ddp-shapes"
